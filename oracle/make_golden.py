@@ -1,0 +1,220 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/* by running the UNMODIFIED reference
+(imported in place from /root/reference, see oracle/ref_import.py) in this container.
+
+    python -m oracle.make_golden            # rewrites tests/golden/
+
+What each fixture pins:
+  blosum_tables.npz        values of sequence_model/blosum_substitute.pt (+ sha256 of the source file)
+  schedule_T{50,500}.pt    PredefinedNoiseScheduleDiscrete.alphas_bar, BlosumTransition tables,
+                           get_Qt_bar at a few alpha_bar values, DiscreteUniformTransition
+  forward_norel_*.pt       logits of the reference forward on installed transformers (no relative_key
+                           term = what 5.5.0 computes) -> pins everything but the relative term
+  forward_rel_*.pt         logits of the reference module tree with the restated 4.38.2 relative_key
+                           self-attention injected (parity UNPINNED for that one term)
+  reverse_step_*.pt        reference sample_p_zs_given_zt_discrete under torch.manual_seed(k):
+                           inputs, the Exp(1) noise E drawn from the same generator state, outputs
+  denoise_T4.pt            the reference denoise() loop end to end (tiny T), same-noise replay
+  apply_aa_noise.pt        PeptideDiff.apply_aa_noise (training q-sample) under a fixed seed
+
+Weights are never stored: both sides regenerate them with oracle.init_state_dict(cfg, seed, variant)
+and the reference model gets them through load_state_dict(strict=True).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_import as R
+from oracle import seqdiff_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def export_blosum():
+    src = os.path.join(R.SEQ_DIR, "blosum_substitute.pt")
+    d = torch.load(src)
+    sha = hashlib.sha256(open(src, "rb").read()).hexdigest()
+    np.savez(os.path.join(GOLDEN, "blosum_tables.npz"),
+             original_score=d["original_score"].numpy(), Qtb_temperature=d["Qtb_temperature"].numpy(),
+             Qt_temperature=d["Qt_temperature"].numpy(), source_sha256=np.array(sha))
+    print("blosum sha256", sha)
+
+
+def golden_schedules():
+    _, _, ref_utils = R.load_reference()
+    for T in (50, 500):
+        sched = ref_utils.PredefinedNoiseScheduleDiscrete("cosine", T)
+        trans = R.make_blosum_transition()
+        uni = ref_utils.DiscreteUniformTransition(20)
+        ab = sched.alphas_bar.clone()
+        probe_t = torch.tensor([[0.0], [1.0 / T], [0.5], [(T - 1.0) / T], [1.0]])
+        a = sched.get_alpha_bar(t_normalized=probe_t)
+        qtb = trans.get_Qt_bar(a, torch.device("cpu")).clone()
+        qt = trans.get_Qt(a, torch.device("cpu")).clone()
+        uq = uni.get_Qt_bar(a, torch.device("cpu")).clone()
+        torch.save({"T": T, "betas": sched.betas.clone(), "alphas_bar": ab, "probe_t": probe_t, "alpha_bar_probe": a,
+                    "temperature_list": trans.temperature_list.clone(), "Qt_temperature": trans.Qt_temperature.clone(),
+                    "Qtb_probe": qtb, "Qt_probe": qt, "uniform_Qtb_probe": uq},
+                   os.path.join(GOLDEN, f"schedule_T{T}.pt"))
+
+
+FORWARD_CASES = [
+    # name, L(max_seq_len), B, n_lig, n_rec, weight seed, variant, input seed, timestep
+    ("cfg1_A", 128, 1, 30, 98, 0, "A", 2, 7.0),
+    ("cfg1_B", 128, 1, 30, 98, 1, "B", 2, 7.0),
+    ("ragged_B", 128, 3, (5, 64), (16, 128), 1, "B", 3, 33.0),
+    ("L64_B", 64, 2, (5, 64), (16, 64), 1, "B", 4, 0.5),
+]
+
+
+def golden_forward():
+    for rel in (False, True):
+        for name, L, B, nl, nr, wseed, variant, iseed, tval in FORWARD_CASES:
+            cfg = O.OracleConfig(max_position_embeddings=L, relative_key=rel)
+            sd = O.init_state_dict(cfg, wseed, variant)
+            m = R.build_reference_model(L, relative_key=rel)
+            m.load_state_dict(sd, strict=True)
+            batch = O.synthetic_batch(B, L, nl, nr, iseed)
+            g = torch.Generator().manual_seed(iseed + 100)
+            x_t = F.one_hot(torch.randint(0, 20, (B, L), generator=g), 20).float()
+            t = torch.full((B, 1), tval)
+            with torch.no_grad():
+                y = m(t, x_t, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                      batch["receptor_angles"], batch["receptor_attn_mask"])
+                y_o = O.denoiser_forward(sd, cfg, t, x_t, batch["ligand_angles"], batch["ligand_attn_mask"],
+                                         batch["receptor_seq"], batch["receptor_angles"], batch["receptor_attn_mask"])
+            err = (y - y_o).abs().max().item()
+            print(f"forward {'rel' if rel else 'norel'} {name}: max|ref-oracle| = {err:.3e}  max|ref| = {y.abs().max():.3f}")
+            assert err < 2e-5, err
+            torch.save({"name": name, "L": L, "B": B, "n_lig": nl, "n_rec": nr, "weight_seed": wseed, "variant": variant,
+                        "input_seed": iseed, "timestep": tval, "relative_key": rel, "x_t_idx": x_t.argmax(-1).to(torch.uint8),
+                        "logits": y.clone()},
+                       os.path.join(GOLDEN, f"forward_{'rel' if rel else 'norel'}_{name}.pt"))
+
+
+def golden_reverse_step():
+    _, ref_sample, ref_utils = R.load_reference()
+    cases = [("T50_s30", 50, 30, True, "blosum"), ("T50_s1", 50, 1, True, "blosum"), ("T500_s499", 500, 499, True, "blosum"),
+             ("T500_s250", 500, 250, True, "blosum"), ("T500_s3_argmax", 500, 3, False, "blosum"),
+             ("T50_s20_uniform", 50, 20, True, "uniform"), ("T50_s0_last", 50, 0, True, "blosum")]
+    for name, T, s_int, diverse, kind in cases:
+        B, L = 4, 48
+        sched = ref_utils.PredefinedNoiseScheduleDiscrete("cosine", T)
+        trans = R.make_blosum_transition() if kind == "blosum" else ref_utils.DiscreteUniformTransition(20)
+        g = torch.Generator().manual_seed(1000 + s_int)
+        x_idx = torch.randint(0, 20, (B, L), generator=g)
+        x_t = F.one_hot(x_idx, 20).float()
+        logits = torch.randn(B, L, 20, generator=g) * 3.0
+        s_arr = s_int * torch.ones((B, 1))
+        s_norm, t_norm = s_arr / T, (s_arr + 1) / T
+        torch.manual_seed(77 + s_int)
+        out = ref_sample.sample_p_zs_given_zt_discrete(t_norm, s_norm, x_t.clone(), logits.clone(), sched, trans, diverse, s_int == 0)
+        torch.manual_seed(77 + s_int)
+        E = torch.empty(B * L, 20).exponential_(1)
+        o_sched = O.NoiseScheduleDiscrete("cosine", T)
+        o_trans = O.BlosumTransition() if kind == "blosum" else O.DiscreteUniformTransition(20)
+        out_o = O.reverse_step(t_norm, s_norm, x_t.clone(), logits.clone(), o_sched, o_trans, diverse, s_int == 0, E)
+        prob = O.reverse_step_probs(t_norm, s_norm, x_t.clone(), logits.clone(), o_sched, o_trans)
+        same = torch.equal(out, out_o)
+        print(f"reverse {name}: oracle == reference: {same}")
+        assert same
+        Qt, Qsb, Qtb = O.step_matrices(t_norm, s_norm, o_sched, o_trans)
+        rec = {"name": name, "T": T, "s_int": s_int, "diverse": diverse, "kind": kind, "x_t_idx": x_idx.to(torch.uint8),
+               "logits": logits, "E": E, "prob": prob, "Qt": Qt[0].clone(), "Qsb": Qsb[0].clone(), "Qtb": Qtb[0].clone()}
+        rec["out"] = out.clone() if s_int == 0 else out.argmax(-1).to(torch.uint8)
+        torch.save(rec, os.path.join(GOLDEN, f"reverse_step_{name}.pt"))
+
+
+def golden_denoise():
+    """reference denoise() (sample.py:181-229) end to end at tiny T, replayed by the oracle with the
+    same noise: x_T from randint, then one Exp(1) block of [N,20] per non-final step, all from the
+    global CPU generator in the reference's draw order."""
+    ref_model, ref_sample, ref_utils = R.load_reference()
+    T, B, L = 4, 2, 64
+    cfg = O.OracleConfig(max_position_embeddings=L, relative_key=True)
+    sd = O.init_state_dict(cfg, 1, "B")
+    m = R.build_reference_model(L, relative_key=True)
+    m.load_state_dict(sd, strict=True)
+    batch = O.synthetic_batch(B, L, (5, 40), (16, 64), 9)
+    batch["structure_ids"] = {"pdb_id": ["xxxx"] * B, "ligand_chain": ["A"] * B}
+    old = ref_sample.CONFIG["timesteps"]
+    ref_sample.CONFIG["timesteps"] = T
+    sched = ref_utils.PredefinedNoiseScheduleDiscrete("cosine", T)
+    trans = R.make_blosum_transition()
+    try:
+        torch.manual_seed(5)
+        ids, true_seq, pred_seq, rates = ref_sample.denoise(batch, m, sched, trans, True)
+    finally:
+        ref_sample.CONFIG["timesteps"] = old
+    torch.manual_seed(5)
+    x_T = O.generate_discrete_noise(B, L, 20)
+    noises = {}
+
+    def noise_fn(s_int):
+        noises[s_int] = torch.empty(B * L, 20).exponential_(1)
+        return noises[s_int]
+
+    with torch.no_grad():
+        final = O.denoise_loop(sd, cfg, batch, O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition(), True, T, x_T, noise_fn)
+    AA = "ACDEFGHIKLMNPQRSTVWY"
+    pred_o = []
+    for i in range(B):
+        mask = batch["ligand_attn_mask"][i].bool()
+        pred_o.append("".join(AA[j] for j in final[i].argmax(1)[mask]))
+    print("denoise ref:", pred_seq, "\n     oracle:", pred_o)
+    assert pred_o == pred_seq
+    torch.save({"T": T, "B": B, "L": L, "weight_seed": 1, "variant": "B", "batch_seed": 9, "n_lig": (5, 40), "n_rec": (16, 64),
+                "x_T_idx": x_T.argmax(-1).to(torch.uint8), "E": torch.stack([noises[s] for s in sorted(noises)]),
+                "E_steps": sorted(noises), "pred_sequences": pred_seq, "true_sequences": true_seq,
+                "recovery_rates": rates, "final_logits": final.clone()},
+               os.path.join(GOLDEN, "denoise_T4.pt"))
+
+
+def golden_apply_aa_noise():
+    ref_model, _, ref_utils = R.load_reference()
+    T, B, L = 50, 4, 32
+
+    class _Shim:  # apply_aa_noise only touches these attributes (model.py:291-311)
+        timesteps = T
+        discrete_noise_schedule = ref_utils.PredefinedNoiseScheduleDiscrete("cosine", T)
+        aa_transition_model = R.make_blosum_transition()
+
+    batch = O.synthetic_batch(B, L, (5, 32), (16, 32), 21)
+    t_int = torch.tensor([[0.0], [13.0], [37.0], [50.0]])
+    torch.manual_seed(11)
+    out = ref_model.PeptideDiff.apply_aa_noise(_Shim(), batch["ligand_seq"], t_int)
+    # replay: the reference draws 20 exponentials per NON-padded row only (model.py:304-308)
+    torch.manual_seed(11)
+    x = batch["ligand_seq"].reshape(B * L, 20)
+    E = torch.ones(B * L, 20)
+    for n in range(B * L):
+        if x[n].sum() != 0:
+            E[n] = torch.empty(20).exponential_(1)
+    out_o = O.apply_aa_noise(batch["ligand_seq"], t_int, T, O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition(), E)
+    same = torch.equal(out, out_o)
+    print("apply_aa_noise oracle == reference:", same)
+    assert same
+    torch.save({"T": T, "B": B, "L": L, "batch_seed": 21, "t_int": t_int, "E": E, "x0_idx": batch["ligand_seq"].argmax(-1).to(torch.uint8),
+                "x0_valid": batch["ligand_attn_mask"].to(torch.uint8), "out_idx": out.argmax(-1).to(torch.uint8)},
+               os.path.join(GOLDEN, "apply_aa_noise.pt"))
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(8)
+    export_blosum()
+    golden_schedules()
+    golden_reverse_step()
+    golden_apply_aa_noise()
+    golden_forward()
+    golden_denoise()
+    print("golden fixtures written to", os.path.normpath(GOLDEN))
+
+
+if __name__ == "__main__":
+    sys.exit(main())
