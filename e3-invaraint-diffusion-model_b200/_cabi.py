@@ -1,0 +1,80 @@
+"""ctypes binding of libseqdiff_b200.so (include/seqdiff_b200.h).  No fallback: if the library is not
+built or does not load, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libseqdiff_b200.so")
+
+FP32, BF16 = 0, 1
+
+
+class SeqdiffConfig(C.Structure):
+    _fields_ = [
+        ("hidden_size", C.c_int32),
+        ("num_attention_heads", C.c_int32),
+        ("intermediate_size", C.c_int32),
+        ("num_hidden_layers", C.c_int32),
+        ("max_position_embeddings", C.c_int32),
+        ("feature_size", C.c_int32),
+        ("relative_key", C.c_int32),
+        ("layer_norm_eps", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes): one entry per symbol declared in include/seqdiff_b200.h
+_vp, _i, _u64, _u32, _i64 = C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_int64
+PROTOTYPES = {
+    "seqdiff_abi_version": (_i, []),
+    "seqdiff_last_error": (C.c_char_p, []),
+    "seqdiff_launch_count": (_u64, []),
+    "seqdiff_model_create": (_i, [C.POINTER(SeqdiffConfig), _i, C.POINTER(_vp)]),
+    "seqdiff_model_destroy": (_i, [_vp]),
+    "seqdiff_model_set_tensor": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
+    "seqdiff_model_finalize": (_i, [_vp, _vp]),
+    "seqdiff_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "seqdiff_reverse_step": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _u64, _u64, _u32, _vp, _vp, _vp]),
+    "seqdiff_apply_aa_noise": (_i, [_vp, _i, _i, _vp, _vp, _u64, _u64, _u32, _vp, _vp, _vp]),
+    "seqdiff_sample": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _u64, _u64, _vp, _vp]),
+    "seqdiff_op_gemm": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "seqdiff_op_attention": (_i, [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "seqdiff_op_philox_u32": (_i, [_u64, _u64, _u32, _i, _i, _vp, _vp]),
+}
+
+_LIB = None
+
+
+class SeqdiffError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the CUDA library.  Raises if it has not been built (python __graft_entry__.py build)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise SeqdiffError(
+                f"{LIB_PATH} is missing: build it with `python e3-invaraint-diffusion-model_b200/build.py` "
+                "(there is no CPU / PyTorch fallback for this path)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.seqdiff_abi_version() != 1:
+            raise SeqdiffError("libseqdiff_b200.so ABI version mismatch")
+        _LIB = l
+    return _LIB
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().seqdiff_last_error()
+        raise SeqdiffError(f"seqdiff error {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,349 @@
+// attention.cu -- the 15 attention cores per forward (3 SELayer + 6 self + 6 cross), i.e. HF
+// BertSelfAttention with transformers-4.38.2 `relative_key` semantics:
+//
+//   S[l,r]  = ( q_l . k_r  +  q_l . E[l - r + P - 1] ) / 8  +  (1 - mask[r]) * -10000
+//   out_l   = softmax_r(S[l,:]) @ V
+//
+// E = distance_embedding [2P-1, 64], shared by all heads; cross-attention has no E term.
+//
+// bf16 kernel: one CTA per (query block of BQ rows, head, graph); each warp owns 16 query rows and runs
+// m16n8k16 bf16 tensor-core MMAs with fp32 accumulation, flash-style online softmax over 128-key blocks.
+// The relative term is a second MMA, QE = Q . Ewin^T, against the (BQ+128)-row window of E that this
+// (query block, key block) pair can touch; warp w only needs window rows [16w, 16w+144).  QE is staged
+// in a per-warp fp32 smem panel and added to S along the skewed diagonal j = l_local - r_local + 127
+// (the "skewing" step; accumulator fragments cannot be shifted in registers).
+// fp32 kernel (parity mode): one warp per query row, straight loops.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace seqdiff {
+
+// ---------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => 16 zero bytes written
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// tiles are [rows][64 bf16] = 128 B rows; 16 B chunks XOR-swizzled by (row & 7) => ldmatrix is conflict-free
+__device__ __forceinline__ uint32_t swz(int row, int chunk) { return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+constexpr int kKB = 128;     // keys per block
+constexpr int kQEPitch = 148;  // floats per staged QE row (144 used)
+
+template <bool REL, int BQ> struct AttnSmem {
+  static constexpr int kWarps = BQ / 16;
+  static constexpr int kERows = BQ + 128;
+  static constexpr int kQ = 0;
+  static constexpr int kK = kQ + BQ * 128;
+  static constexpr int kV = kK + kKB * 128;
+  static constexpr int kE = kV + kKB * 128;
+  static constexpr int kQE = kE + (REL ? kERows * 128 : 0);
+  static constexpr int kMask = kQE + (REL ? kWarps * 16 * kQEPitch * 4 : 0);
+  static constexpr int kBytes = kMask + kKB * 4;
+};
+
+template <bool REL, int BQ>
+__global__ void __launch_bounds__(BQ * 2) attention_bf16_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k, int ldk,
+                                                                const bf16* __restrict__ v, int ldv, const bf16* __restrict__ E, int P,
+                                                                const float* __restrict__ key_mask, bf16* __restrict__ out, int heads,
+                                                                int Lq, int Lk) {
+  using SM = AttnSmem<REL, BQ>;
+  constexpr int NT = BQ * 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  float* sMask = reinterpret_cast<float*>(smem + SM::kMask);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+
+  const bf16* qb = q + (static_cast<size_t>(b) * Lq) * ldq + h * 64;
+  const bf16* kb_ = k + (static_cast<size_t>(b) * Lk) * ldk + h * 64;
+  const bf16* vb = v + (static_cast<size_t>(b) * Lk) * ldv + h * 64;
+
+  // ---- Q tile (once) ----
+  for (int i = tid; i < BQ * 8; i += NT) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = q0 + r < Lq;
+    cp_async16(sbase + SM::kQ + swz(r, c), qb + static_cast<size_t>(ok ? q0 + r : 0) * ldq + c * 8, ok);
+  }
+
+  uint32_t qa[4][4];  // A fragments of this warp's 16 query rows, 4 k-steps
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+  const int nkb = (Lk + kKB - 1) / kKB;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int k0 = kb * kKB;
+    if (kb > 0) __syncthreads();  // previous block fully consumed
+    for (int i = tid; i < kKB * 8; i += NT) {
+      const int r = i >> 3, c = i & 7;
+      const bool ok = k0 + r < Lk;
+      const size_t row = ok ? k0 + r : 0;
+      cp_async16(sbase + SM::kK + swz(r, c), kb_ + row * ldk + c * 8, ok);
+      cp_async16(sbase + SM::kV + swz(r, c), vb + row * ldv + c * 8, ok);
+    }
+    if (REL) {
+      const int ebase = q0 - k0 + P - 1 - 127;
+      for (int i = tid; i < SM::kERows * 8; i += NT) {
+        const int r = i >> 3, c = i & 7;
+        const int idx = ebase + r;
+        const bool ok = idx >= 0 && idx < 2 * P - 1;
+        cp_async16(sbase + SM::kE + swz(r, c), E + static_cast<size_t>(ok ? idx : 0) * 64 + c * 8, ok);
+      }
+    }
+    for (int i = tid; i < kKB; i += NT) {
+      const int r = k0 + i;
+      sMask[i] = (r < Lk) ? (1.0f - key_mask[static_cast<size_t>(b) * Lk + r]) * -10000.0f : -INFINITY;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    if (kb == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        ldsm_x4(sbase + SM::kQ + swz(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+
+    // ---- S = Q K^T : 16 rows x 128 keys per warp ----
+    float s[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+    for (int np = 0; np < 8; ++np) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(sbase + SM::kK + swz(np * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+        mma_bf16(s[2 * np], qa[ks], b0, b1);
+        mma_bf16(s[2 * np + 1], qa[ks], b2, b3);
+      }
+    }
+
+    if (REL) {
+      // ---- QE = Q . Ewin[16w : 16w+144]^T, staged, then added along the skewed diagonal ----
+      float* st = reinterpret_cast<float*>(smem + SM::kQE) + warp * 16 * kQEPitch;
+#pragma unroll 1
+      for (int c = 0; c < 9; ++c) {
+        float e0[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(sbase + SM::kE + swz(warp * 16 + c * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+          mma_bf16(e0, qa[ks], b0, b1);
+          mma_bf16(e1, qa[ks], b2, b3);
+        }
+        const int col = c * 16 + 2 * t;
+        *reinterpret_cast<float2*>(st + g * kQEPitch + col) = make_float2(e0[0], e0[1]);
+        *reinterpret_cast<float2*>(st + (g + 8) * kQEPitch + col) = make_float2(e0[2], e0[3]);
+        *reinterpret_cast<float2*>(st + g * kQEPitch + col + 8) = make_float2(e1[0], e1[1]);
+        *reinterpret_cast<float2*>(st + (g + 8) * kQEPitch + col + 8) = make_float2(e1[2], e1[3]);
+      }
+      __syncwarp();
+      // window-local column of E for (row i, key rl):  j' = i - rl + 127  in [0, 142]
+      const float* r0p = st + g * kQEPitch + g + 127;
+      const float* r1p = st + (g + 8) * kQEPitch + g + 8 + 127;
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        const int rl = n * 8 + 2 * t;
+        s[n][0] += r0p[-rl];
+        s[n][1] += r0p[-rl - 1];
+        s[n][2] += r1p[-rl];
+        s[n][3] += r1p[-rl - 1];
+      }
+      __syncwarp();
+    }
+
+    // ---- scale (after adding Rel), mask, online softmax ----
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      const float2 mk = *reinterpret_cast<const float2*>(sMask + n * 8 + 2 * t);
+      s[n][0] = s[n][0] * 0.125f + mk.x;
+      s[n][1] = s[n][1] * 0.125f + mk.y;
+      s[n][2] = s[n][2] * 0.125f + mk.x;
+      s[n][3] = s[n][3] * 0.125f + mk.y;
+      mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
+    }
+    float corr[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      corr[r] = (m_run[r] == -INFINITY) ? 0.f : __expf(m_run[r] - m_new);
+      m_run[r] = m_new;
+    }
+    uint32_t pa[8][4];  // P as bf16 A fragments for P @ V
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      const float p0 = __expf(s[n][0] - m_run[0]), p1 = __expf(s[n][1] - m_run[0]);
+      const float p2 = __expf(s[n][2] - m_run[1]), p3 = __expf(s[n][3] - m_run[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+      l_run[r] = l_run[r] * corr[r] + rs[r];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(sbase + SM::kV + swz(kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp * 2 + (lane >> 4)), b0, b1, b2, b3);
+        mma_bf16(o[2 * dp], pa[kk], b0, b1);
+        mma_bf16(o[2 * dp + 1], pa[kk], b2, b3);
+      }
+    }
+  }
+
+  // ---- normalise and store ----
+  const int H = heads * 64;
+  const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = h * 64 + n * 8 + 2 * t;
+    if (r0 < Lq) *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * Lq + r0) * H + col) = pack_bf16x2(o[n][0] * inv0, o[n][1] * inv0);
+    if (r1 < Lq) *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * Lq + r1) * H + col) = pack_bf16x2(o[n][2] * inv1, o[n][3] * inv1);
+  }
+}
+
+template <bool REL, int BQ>
+static int launch_attn_bf16(int B, int heads, int Lq, int Lk, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv,
+                            const bf16* E, int P, const float* mask, bf16* out, cudaStream_t s) {
+  using SM = AttnSmem<REL, BQ>;
+  auto kfn = attention_bf16_kernel<REL, BQ>;
+  static bool configured = false;
+  if (!configured) {
+    SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+    configured = true;
+  }
+  dim3 grid(ceil_div(Lq, BQ), heads, B);
+  kfn<<<grid, BQ * 2, SM::kBytes, s>>>(q, ldq, k, ldk, v, ldv, E, P, mask, out, heads, Lq, Lk);
+  SD_LAUNCH_CHECK();
+  return SEQDIFF_OK;
+}
+
+template <>
+int attention<bf16>(int B, int heads, int Lq, int Lk, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv,
+                    const bf16* dist_emb, int P, const float* key_mask, bf16* out, cudaStream_t s) {
+  SD_CHECK(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "empty attention");
+  SD_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "row strides must be multiples of 8 elements");
+  SD_CHECK(!dist_emb || (Lq <= P && Lk <= P), "sequence longer than max_position_embeddings");
+  const bool small = Lq <= 64;
+  if (dist_emb) {
+    return small ? launch_attn_bf16<true, 64>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s)
+                 : launch_attn_bf16<true, 128>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  }
+  return small ? launch_attn_bf16<false, 64>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s)
+               : launch_attn_bf16<false, 128>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 parity kernel: one warp per query row; scores for the whole row live in smem.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                            const float* __restrict__ v, int ldv, const float* __restrict__ E, int P,
+                                                            const float* __restrict__ key_mask, float* __restrict__ out, int heads,
+                                                            int Lq, int Lk) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sq = sm + warp * 64;
+  float* sc = sm + 8 * 64 + warp * Lk;
+  const int l = blockIdx.x * 8 + warp, h = blockIdx.y, b = blockIdx.z;
+  if (l >= Lq) return;
+  const float* qrow = q + (static_cast<size_t>(b) * Lq + l) * ldq + h * 64;
+  sq[lane] = qrow[lane];
+  sq[lane + 32] = qrow[lane + 32];
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int r = lane; r < Lk; r += 32) {
+    const float* kr = k + (static_cast<size_t>(b) * Lk + r) * ldk + h * 64;
+    float acc = 0.f, rel = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < 64; d += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(kr + d);
+      acc = fmaf(sq[d], kk.x, acc); acc = fmaf(sq[d + 1], kk.y, acc);
+      acc = fmaf(sq[d + 2], kk.z, acc); acc = fmaf(sq[d + 3], kk.w, acc);
+    }
+    if (E) {
+      const float* er = E + static_cast<size_t>(l - r + P - 1) * 64;
+#pragma unroll 4
+      for (int d = 0; d < 64; d += 4) {
+        const float4 ee = *reinterpret_cast<const float4*>(er + d);
+        rel = fmaf(sq[d], ee.x, rel); rel = fmaf(sq[d + 1], ee.y, rel);
+        rel = fmaf(sq[d + 2], ee.z, rel); rel = fmaf(sq[d + 3], ee.w, rel);
+      }
+    }
+    const float sv = (acc + rel) / 8.0f + (1.0f - key_mask[static_cast<size_t>(b) * Lk + r]) * -10000.0f;
+    sc[r] = sv;
+    mx = fmaxf(mx, sv);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int r = lane; r < Lk; r += 32) {
+    const float e = expf(sc[r] - mx);
+    sc[r] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float a0 = 0.f, a1 = 0.f;
+  for (int r = 0; r < Lk; ++r) {
+    const float p = sc[r] / sum;
+    const float* vr = v + (static_cast<size_t>(b) * Lk + r) * ldv + h * 64;
+    a0 = fmaf(p, vr[lane], a0);
+    a1 = fmaf(p, vr[lane + 32], a1);
+  }
+  float* orow = out + (static_cast<size_t>(b) * Lq + l) * (heads * 64) + h * 64;
+  orow[lane] = a0;
+  orow[lane + 32] = a1;
+}
+
+template <>
+int attention<float>(int B, int heads, int Lq, int Lk, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                     const float* dist_emb, int P, const float* key_mask, float* out, cudaStream_t s) {
+  SD_CHECK(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "empty attention");
+  SD_CHECK(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "row strides must be multiples of 4 elements");
+  SD_CHECK(!dist_emb || (Lq <= P && Lk <= P), "sequence longer than max_position_embeddings");
+  const size_t smem = (8 * 64 + 8 * static_cast<size_t>(Lk)) * sizeof(float);
+  SD_CHECK(smem <= 48 * 1024, "fp32 attention: Lk too large");
+  dim3 grid(ceil_div(Lq, 8), heads, B);
+  attention_f32_kernel<<<grid, 256, smem, s>>>(q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, heads, Lq, Lk);
+  SD_LAUNCH_CHECK();
+  return SEQDIFF_OK;
+}
+
+}  // namespace seqdiff

@@ -1,0 +1,158 @@
+// cabi.cu -- the extern "C" surface declared in include/seqdiff_b200.h.  Thin: argument checks, handle
+// casts, exception firewall.  No torch types, no allocation on behalf of the caller.
+#include <new>
+
+#include "model.cuh"
+
+namespace seqdiff {
+const char* last_error();
+}
+using namespace seqdiff;
+
+#define SD_GUARD_BEGIN try {
+#define SD_GUARD_END                                         \
+  }                                                          \
+  catch (const std::exception& e) {                          \
+    set_error(std::string("exception: ") + e.what());        \
+    return SEQDIFF_ERR_STATE;                                \
+  }                                                          \
+  catch (...) {                                              \
+    set_error("unknown exception");                          \
+    return SEQDIFF_ERR_STATE;                                \
+  }
+
+struct seqdiff_model {
+  Model impl;
+};
+
+extern "C" {
+
+int seqdiff_abi_version(void) { return SEQDIFF_ABI_VERSION; }
+const char* seqdiff_last_error(void) { return last_error(); }
+uint64_t seqdiff_launch_count(void) { return g_launches.load(); }
+
+int seqdiff_model_create(const seqdiff_config_t* cfg, int device, seqdiff_model_t** out) {
+  SD_GUARD_BEGIN
+  SD_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  int ndev = 0;
+  SD_CUDA(cudaGetDeviceCount(&ndev));
+  SD_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+  seqdiff_model* m = new (std::nothrow) seqdiff_model();
+  SD_CHECK(m != nullptr, "out of host memory");
+  const int rc = m->impl.init(*cfg, device);
+  if (rc != SEQDIFF_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return SEQDIFF_OK;
+  SD_GUARD_END
+}
+
+int seqdiff_model_destroy(seqdiff_model_t* m) {
+  SD_GUARD_BEGIN
+  if (m) {
+    cudaSetDevice(m->impl.device);
+    cudaDeviceSynchronize();
+    delete m;
+  }
+  return SEQDIFF_OK;
+  SD_GUARD_END
+}
+
+int seqdiff_model_set_tensor(seqdiff_model_t* m, const char* name, const float* data, int64_t numel, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && name && data, "null argument");
+  return m->impl.set_tensor(name, data, numel, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_model_finalize(seqdiff_model_t* m, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m, "null argument");
+  return m->impl.finalize(static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_forward(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, const float* timestep,
+                    const float* noised_ligand_seq, const float* ligand_angle, const float* ligand_mask,
+                    const float* receptor_seq, const float* receptor_angle, const float* receptor_mask, float* logits_out,
+                    void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && timestep && noised_ligand_seq && ligand_angle && ligand_mask && receptor_seq && receptor_angle && receptor_mask &&
+               logits_out,
+           "null argument");
+  return m->impl.forward(precision, B, L_lig, L_rec, timestep, nullptr, noised_ligand_seq, ligand_angle, ligand_mask, receptor_seq,
+                         receptor_angle, receptor_mask, logits_out, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_reverse_step(const float* q_tables, int n_tab, int B, int L, const float* noised_data, const float* pred_logits,
+                         int diverse, const float* noise_E, uint64_t seed, uint64_t graph_id0, uint32_t step, float* x_s_out,
+                         uint8_t* idx_out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(q_tables && noised_data && pred_logits && x_s_out, "null argument");
+  return reverse_step(q_tables, n_tab, B, L, noised_data, pred_logits, diverse, noise_E, seed, graph_id0, step, nullptr, x_s_out,
+                      idx_out, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float* noise_E, uint64_t seed,
+                           uint64_t graph_id0, uint32_t step, float* x_t_out, uint8_t* idx_out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(qtb && x0 && x_t_out, "null argument");
+  return apply_aa_noise(qtb, B, L, x0, noise_E, seed, graph_id0, step, x_t_out, idx_out, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_sample(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, int T, const float* q_tables_steps,
+                   const float* x_T, const float* ligand_angle, const float* ligand_mask, const float* receptor_seq,
+                   const float* receptor_angle, const float* receptor_mask, int diverse, const float* noise_E_steps,
+                   uint64_t seed, uint64_t graph_id0, float* final_out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && q_tables_steps && x_T && ligand_angle && ligand_mask && receptor_seq && receptor_angle && receptor_mask && final_out,
+           "null argument");
+  return m->impl.sample(precision, B, L_lig, L_rec, T, q_tables_steps, x_T, ligand_angle, ligand_mask, receptor_seq, receptor_angle,
+                        receptor_mask, diverse, noise_E_steps, seed, graph_id0, final_out, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_op_gemm(int precision, int M, int N, int K, const void* A, const void* W, const float* bias, const void* resid,
+                    int epilogue, void* C, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(A && W && bias && C, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (precision == SEQDIFF_FP32)
+    return gemm_f32(M, N, K, static_cast<const float*>(A), static_cast<const float*>(W), bias, static_cast<const float*>(resid),
+                    epilogue, static_cast<float*>(C), s);
+  // bit 8.. of `precision` may force the tile width (tests): precision = SEQDIFF_BF16 | (bn << 8)
+  const int force_bn = precision >> 8;
+  SD_CHECK((precision & 0xff) == SEQDIFF_BF16, "bad precision");
+  return gemm_bf16(M, N, K, static_cast<const bf16*>(A), static_cast<const bf16*>(W), bias, static_cast<const bf16*>(resid), epilogue,
+                   static_cast<bf16*>(C), s, force_bn);
+  SD_GUARD_END
+}
+
+int seqdiff_op_attention(int precision, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k, int ldk,
+                         const void* v, int ldv, const void* dist_emb, int P, const float* key_mask, void* out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(q && k && v && key_mask && out, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (precision == SEQDIFF_FP32)
+    return attention<float>(B, heads, Lq, Lk, static_cast<const float*>(q), ldq, static_cast<const float*>(k), ldk,
+                            static_cast<const float*>(v), ldv, static_cast<const float*>(dist_emb), P, key_mask,
+                            static_cast<float*>(out), s);
+  SD_CHECK(precision == SEQDIFF_BF16, "bad precision");
+  return attention<bf16>(B, heads, Lq, Lk, static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk,
+                         static_cast<const bf16*>(v), ldv, static_cast<const bf16*>(dist_emb), P, key_mask, static_cast<bf16*>(out), s);
+  SD_GUARD_END
+}
+
+int seqdiff_op_philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(out && B > 0 && L > 0, "bad argument");
+  return philox_u32(seed, graph_id0, step, B, L, out, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+}  // extern "C"

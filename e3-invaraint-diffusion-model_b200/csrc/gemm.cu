@@ -1,0 +1,414 @@
+// gemm.cu -- the Linear layers of the denoiser (90 nn.Linear calls per forward in the reference,
+// sequence_model/model.py:200-237 via HF BertAttention/BertLayer + SELayer + AminoAcidPredictor).
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T + bias[N] (+ resid[M,N]) )
+//
+// nn.Linear keeps W as [out,in] = [N,K] row-major, i.e. K-major for the MMA B operand; activations are
+// [tokens, features] = K-major for the A operand.  No transposes anywhere.
+//
+// bf16 path (the product): persistent, warp-specialised tcgen05 kernel
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles (128B swizzle) into a STAGES-deep smem ring
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> f32 in TMEM);
+//                                owns the TMEM allocation (2 accumulator stages = 2*BN columns)
+//   warps 2..9  epilogue       : tcgen05.ld the finished accumulator (lane quarter = warp%4, column half =
+//                                (warp-2)/4), fused bias / erf-GELU / SiLU / residual add, bf16 stores --
+//                                overlapped with the MMA mainloop of the next tile (double-buffered TMEM).
+// fp32 path (parity gate 1e-5): plain SIMT tiled kernel, fp32 FMA accumulation.
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace seqdiff {
+
+// =====================================================================================================
+// TMA descriptors (host)
+// =====================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int rows, cols, box_rows;
+  bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= (static_cast<size_t>(k.rows) * 0x9E3779B97F4A7C15ull) ^ (static_cast<size_t>(k.cols) << 20) ^ (static_cast<size_t>(k.box_rows) << 44);
+    return h;
+  }
+};
+
+// row-major bf16 matrix [rows, cols]; tile = box_rows x 64 columns, 128B-swizzled, OOB reads give zeros
+static int make_tmap(const bf16* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, rows, cols, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return SEQDIFF_OK;
+    }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return SEQDIFF_ERR_CUDA;
+  }
+  SD_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (cols % 8) == 0, "TMA operand must be 16B aligned with a 16B-multiple row pitch");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * sizeof(bf16)};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return SEQDIFF_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  cache.emplace(key, *out);
+  return SEQDIFF_OK;
+}
+
+// =====================================================================================================
+// tcgen05 kernel
+// =====================================================================================================
+constexpr int kBM = 128;        // UMMA M (one TMEM lane per output row)
+constexpr int kBK = 64;         // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit inputs
+constexpr int kGemmThreads = 320;
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two: 256 / 512)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI, bool RESID>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const float* __restrict__ bias, const bf16* __restrict__ resid, bf16* __restrict__ C, int M, int N, int K) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_n = N / BN;
+  const int num_m = (M + kBM - 1) / kBM;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
+          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -----------------------------------
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // column half of the tile
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * kBM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + static_cast<uint32_t>(c), r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+          v[j] = __uint_as_float(r[j]) + b4.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        }
+        if (EPI == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        } else if (EPI == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+        }
+        if (row_ok) {
+          const size_t off = static_cast<size_t>(row) * N + col0;
+          if (RESID) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float rr[8];
+              load8<bf16>(resid + off + j, rr);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[j + t] += rr[t];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(v[j], v[j + 1]);
+            o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(C + off + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI, bool RESID>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const bf16* resid, bf16* C, int M, int N,
+                     int K, cudaStream_t s) {
+  using Cfg = GemmCfg<BN>;
+  auto kfn = gemm_tcgen05_kernel<BN, EPI, RESID>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ceil_div(M, kBM) * (N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, bias, resid, C, M, N, K);
+  SD_LAUNCH_CHECK();
+  return SEQDIFF_OK;
+}
+
+// tile-width choice: the widest tile whose wave quantisation does not cost more than it saves.
+static int pick_bn(int M, int N) {
+  if (N % 256 != 0) return 128;
+  const int sms = num_sms();
+  const int m_tiles = ceil_div(M, kBM);
+  auto waves_eff = [&](int bn) {
+    const int tiles = m_tiles * (N / bn);
+    const int waves = ceil_div(tiles, sms);
+    return static_cast<double>(tiles) / (static_cast<double>(waves) * sms);
+  };
+  // 128-wide tiles are SMEM-bandwidth marginal (8 KB operands per 64 MMA cycles); prefer 256 unless
+  // quantisation makes it clearly worse.
+  return (waves_eff(256) + 0.08 >= waves_eff(128)) ? 256 : 128;
+}
+
+int gemm_bf16(int M, int N, int K, const bf16* A, const bf16* W, const float* bias, const bf16* resid, int epi, bf16* C,
+              cudaStream_t s, int force_bn) {
+  SD_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
+  SD_CHECK(N % 128 == 0, "tcgen05 GEMM needs N % 128 == 0");
+  SD_CHECK(K % 8 == 0, "tcgen05 GEMM needs K % 8 == 0 (16B TMA pitch)");
+  SD_CHECK(!(resid && epi != 0), "residual add is only fused with the identity epilogue");
+  SD_CHECK(bias != nullptr, "bias required");
+  const int bn = force_bn ? force_bn : pick_bn(M, N);
+  SD_CHECK(bn == 128 || (bn == 256 && N % 256 == 0), "bad tile width");
+  CUtensorMap ta, tb;
+  SD_TRY(make_tmap(A, M, K, kBM, &ta));
+  SD_TRY(make_tmap(W, N, K, bn, &tb));
+#define SD_TC(BN_)                                                                                        \
+  do {                                                                                                    \
+    if (resid) return launch_tc<BN_, 0, true>(ta, tb, bias, resid, C, M, N, K, s);                       \
+    if (epi == 0) return launch_tc<BN_, 0, false>(ta, tb, bias, resid, C, M, N, K, s);                   \
+    if (epi == 1) return launch_tc<BN_, 1, false>(ta, tb, bias, resid, C, M, N, K, s);                   \
+    if (epi == 2) return launch_tc<BN_, 2, false>(ta, tb, bias, resid, C, M, N, K, s);                   \
+  } while (0)
+  if (bn == 256) SD_TC(256);
+  else SD_TC(128);
+#undef SD_TC
+  set_error("unknown GEMM epilogue");
+  return SEQDIFF_ERR_INVALID;
+}
+
+// =====================================================================================================
+// fp32 SIMT kernel (parity mode).  64x64 tile, BK=16, 256 threads x (4x4) outputs, fp32 FMA chain in k order.
+// =====================================================================================================
+template <int EPI, bool RESID>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                       const float* __restrict__ bias, const float* __restrict__ resid,
+                                                       float* __restrict__ C, int M, int N, int K) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ float sA[TK][TM + 4];
+  __shared__ float sW[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  float acc[4][4] = {};
+  const int lr = tid >> 2;        // 0..63 row inside the tile
+  const int lk = (tid & 3) * 4;   // 0,4,8,12
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    float4 a4 = make_float4(0, 0, 0, 0), w4 = make_float4(0, 0, 0, 0);
+    const int ar = m0 + lr, wr = n0 + lr;
+    if (k0 + lk + 3 < K) {
+      if (ar < M) a4 = *reinterpret_cast<const float4*>(A + static_cast<size_t>(ar) * K + k0 + lk);
+      if (wr < N) w4 = *reinterpret_cast<const float4*>(W + static_cast<size_t>(wr) * K + k0 + lk);
+    } else {
+      float ta[4] = {0, 0, 0, 0}, tw[4] = {0, 0, 0, 0};
+      for (int t = 0; t < 4; ++t)
+        if (k0 + lk + t < K) {
+          if (ar < M) ta[t] = A[static_cast<size_t>(ar) * K + k0 + lk + t];
+          if (wr < N) tw[t] = W[static_cast<size_t>(wr) * K + k0 + lk + t];
+        }
+      a4 = make_float4(ta[0], ta[1], ta[2], ta[3]);
+      w4 = make_float4(tw[0], tw[1], tw[2], tw[3]);
+    }
+    sA[lk][lr] = a4.x; sA[lk + 1][lr] = a4.y; sA[lk + 2][lr] = a4.z; sA[lk + 3][lr] = a4.w;
+    sW[lk][lr] = w4.x; sW[lk + 1][lr] = w4.y; sW[lk + 2][lr] = w4.z; sW[lk + 3][lr] = w4.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= N) continue;
+      float v = acc[i][j] + bias[c];
+      if (EPI == 1) v = gelu_erf(v);
+      if (EPI == 2) v = silu(v);
+      if (RESID) v += resid[static_cast<size_t>(r) * N + c];
+      C[static_cast<size_t>(r) * N + c] = v;
+    }
+  }
+}
+
+int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* bias, const float* resid, int epi, float* C,
+             cudaStream_t s) {
+  SD_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
+  SD_CHECK(K % 4 == 0, "fp32 GEMM needs K % 4 == 0");
+  SD_CHECK(!(resid && epi != 0), "residual add is only fused with the identity epilogue");
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  if (resid) gemm_f32_kernel<0, true><<<grid, 256, 0, s>>>(A, W, bias, resid, C, M, N, K);
+  else if (epi == 0) gemm_f32_kernel<0, false><<<grid, 256, 0, s>>>(A, W, bias, resid, C, M, N, K);
+  else if (epi == 1) gemm_f32_kernel<1, false><<<grid, 256, 0, s>>>(A, W, bias, resid, C, M, N, K);
+  else if (epi == 2) gemm_f32_kernel<2, false><<<grid, 256, 0, s>>>(A, W, bias, resid, C, M, N, K);
+  else {
+    set_error("unknown GEMM epilogue");
+    return SEQDIFF_ERR_INVALID;
+  }
+  SD_LAUNCH_CHECK();
+  return SEQDIFF_OK;
+}
+
+}  // namespace seqdiff

@@ -1,0 +1,56 @@
+// kernels.h -- internal launcher interface between the kernel translation units and model.cu/cabi.cu.
+// Every function enqueues on `s`, returns SEQDIFF_OK or an error code (message via set_error()).
+#pragma once
+#include "common.cuh"
+
+namespace seqdiff {
+
+// ---- gemm.cu ----------------------------------------------------------------------------------------
+// epi: 0 identity, 1 erf-GELU, 2 SiLU.  resid (same shape as C) only with epi == 0.
+int gemm_bf16(int M, int N, int K, const bf16* A, const bf16* W, const float* bias, const bf16* resid, int epi, bf16* C,
+              cudaStream_t s, int force_bn = 0);
+int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* bias, const float* resid, int epi, float* C,
+             cudaStream_t s);
+
+// ---- rowwise.cu -------------------------------------------------------------------------------------
+// GaussianFourierProjection (model.py:85-97): out[b, :] = [sin(x), cos(x)], x = ((t*W)*2)*pi in fp32.
+// t = timestep[b], or (float)*step_ptr for every b when step_ptr != NULL (sampling loop, quirk Q3).
+int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, cudaStream_t s);
+// BertEmbeddings (model.py:110-117): out = LN(x @ Wt + b) (+ te[row / L]); Wt is the [fin, H] transpose.
+template <typename T>
+int embed_ln(const float* x, int M, int fin, const float* Wt, const float* b, const float* lnw, const float* lnb, float eps,
+             const float* te, int L, int H, T* out, cudaStream_t s);
+// out = LayerNorm(in) * w + b
+template <typename T>
+int layernorm(const T* in, int M, int H, const float* w, const float* b, float eps, T* out, cudaStream_t s);
+// SELayer residual update (model.py:61-62):
+//   y = affine_first ? LayerNorm(in; lnw, lnb, eps1) : in          (BertSelfOutput.LayerNorm)
+//   out = x + gate * (LayerNorm_noaffine(y, 1e-5) * (1 + scale) + shift)
+// (shift, scale, gate) = mod[row / mod_div, (chunk0 + {0,1,2}) * H : ...], mod row pitch 6H.
+template <typename T>
+int ln_modulate(const T* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1, const T* x,
+                const T* mod, int mod_div, int chunk0, T* out, cudaStream_t s);
+// AminoAcidPredictor tail (model.py:151-152): logits = LayerNorm(y) @ W2^T + b2  (y is already GELU(dense1))
+template <typename T>
+int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb, float eps, const float* W2, const float* b2,
+                   int F, float* logits, cudaStream_t s);
+int f32_to_bf16(const float* in, size_t n, bf16* out, cudaStream_t s);
+int transpose_f32(const float* in, int rows, int cols, float* out, cudaStream_t s);  // out[c][r] = in[r][c]
+int step_advance(int* step_ptr, cudaStream_t s);                                     // *step_ptr -= 1
+
+// ---- attention.cu -----------------------------------------------------------------------------------
+template <typename T>
+int attention(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
+              int P, const float* key_mask, T* out, cudaStream_t s);
+
+// ---- reverse_step.cu --------------------------------------------------------------------------------
+// step_ptr != NULL: tables/noise are indexed by *step_ptr (entry stride 1200 / N*20) and the launch is a
+// no-op when *step_ptr == 0 (last step returns the raw logits, sample.py:147-148).
+int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_t, const float* logits, int diverse,
+                 const float* noise_E, uint64_t seed, uint64_t graph_id0, uint32_t step, const int* step_ptr, float* x_s,
+                 uint8_t* idx_out, cudaStream_t s);
+int apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float* noise_E, uint64_t seed, uint64_t graph_id0,
+                   uint32_t step, float* x_t, uint8_t* idx_out, cudaStream_t s);
+int philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, cudaStream_t s);
+
+}  // namespace seqdiff

@@ -1,0 +1,541 @@
+// model.cu -- host-side orchestration of the denoiser forward (sequence_model/model.py:200-237) and of
+// the reverse-diffusion loop (sequence_model/sample.py:192-207) on top of the kernels in this directory.
+//
+// Data layout in HBM.  Tokens are rows: a padded batch [B, L, H] is a row-major [B*L, H] matrix; the
+// ligand and the receptor batches are stacked into ONE matrix [B*L_lig + B*L_rec, H] because the
+// reference runs both through the same SELayer weights (quirk Q1, model.py:221), so every Linear of
+// that block is one GEMM over all tokens.  The six cross-attention K|V projections of the decoder act on
+// the same receptor features, so they are one GEMM against the stacked [6*2H, H] weight.  Q|K|V of every
+// self-attention are one GEMM against the stacked [3H, H] weight.  Activations are bf16 (product) or
+// fp32 (parity mode); LayerNorm statistics, softmax, biases and logits are always fp32.
+#include "model.cuh"
+
+#include <cstring>
+
+namespace seqdiff {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+std::atomic<uint64_t> g_launches{0};
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <typename T> static const T* pick(const Wt& w);
+template <> const float* pick<float>(const Wt& w) { return w.f; }
+template <> const bf16* pick<bf16>(const Wt& w) { return w.h; }
+
+static int gemm_t(int M, int N, int K, const float* A, const Wt& W, const float* bias, const float* resid, int epi, float* C, cudaStream_t s) {
+  return gemm_f32(M, N, K, A, W.f, bias, resid, epi, C, s);
+}
+static int gemm_t(int M, int N, int K, const bf16* A, const Wt& W, const float* bias, const bf16* resid, int epi, bf16* C, cudaStream_t s) {
+  return gemm_bf16(M, N, K, A, W.h, bias, resid, epi, C, s);
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+// =====================================================================================================
+Model::~Model() {
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  for (void* p : allocs) cudaFree(p);
+  for (void* p : packed_allocs) cudaFree(p);
+  if (ws) cudaFree(ws);
+  if (samp_in) cudaFree(samp_in);
+  if (d_tables) cudaFree(d_tables);
+}
+
+void* Model::dalloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes < 256 ? 256 : bytes) != cudaSuccess) return nullptr;
+  (packing ? packed_allocs : allocs).push_back(p);
+  return p;
+}
+
+static void add_schema(std::map<std::string, RawTensor>& raw, const std::string& name, int64_t numel) {
+  RawTensor t;
+  t.numel = numel;
+  raw[name] = t;
+}
+
+int Model::init(const seqdiff_config_t& c, int dev) {
+  cfg = c;
+  device = dev;
+  SD_CHECK(c.hidden_size % 256 == 0 && c.hidden_size >= 256 && c.hidden_size <= 1024, "hidden_size must be 256/512/768/1024");
+  SD_CHECK(c.num_attention_heads * 64 == c.hidden_size, "head_dim must be 64");
+  SD_CHECK(c.intermediate_size % 128 == 0, "intermediate_size must be a multiple of 128");
+  SD_CHECK(c.num_hidden_layers >= 1 && c.max_position_embeddings >= 1, "bad layer count / max positions");
+  SD_CHECK(c.feature_size >= 1 && c.feature_size <= 32, "feature_size must be in [1,32]");
+  SD_CUDA(cudaSetDevice(dev));
+  const int64_t H = c.hidden_size, I = c.intermediate_size, P = c.max_position_embeddings;
+  // state_dict schema of ConditionalBertForDiffusionBase
+  add_schema(raw, "timestep_projector.W", H / 2);
+  for (const char* side : {"ligand", "receptor"})
+    for (auto kv : {std::pair<const char*, int>{"seq", 20}, std::pair<const char*, int>{"angle", 8}}) {
+      const std::string p = std::string(side) + "_" + kv.first + "_embedding";
+      add_schema(raw, p + ".linear.weight", H * kv.second);
+      add_schema(raw, p + ".linear.bias", H);
+      add_schema(raw, p + ".LayerNorm.weight", H);
+      add_schema(raw, p + ".LayerNorm.bias", H);
+    }
+  auto attn = [&](const std::string& p, bool rel) {
+    for (const char* n : {"query", "key", "value"}) {
+      add_schema(raw, p + ".self." + n + ".weight", H * H);
+      add_schema(raw, p + ".self." + n + ".bias", H);
+    }
+    if (rel && c.relative_key) add_schema(raw, p + ".self.distance_embedding.weight", (2 * P - 1) * 64);
+    add_schema(raw, p + ".output.dense.weight", H * H);
+    add_schema(raw, p + ".output.dense.bias", H);
+    add_schema(raw, p + ".output.LayerNorm.weight", H);
+    add_schema(raw, p + ".output.LayerNorm.bias", H);
+  };
+  for (const char* blk : {"ligand_feature_emb", "receptor_feature_emb", "decoder_normalize"}) {
+    const std::string p = blk;
+    add_schema(raw, p + ".adaLN_modulation.0.weight", H * H);
+    add_schema(raw, p + ".adaLN_modulation.0.bias", H);
+    add_schema(raw, p + ".adaLN_modulation.2.weight", 6 * H * H);
+    add_schema(raw, p + ".adaLN_modulation.2.bias", 6 * H);
+    attn(p + ".attn", true);
+    add_schema(raw, p + ".mlp.0.weight", 4 * H * H);
+    add_schema(raw, p + ".mlp.0.bias", 4 * H);
+    add_schema(raw, p + ".mlp.3.weight", 4 * H * H);
+    add_schema(raw, p + ".mlp.3.bias", H);
+  }
+  for (int i = 0; i < c.num_hidden_layers; ++i) {
+    const std::string p = "decoder.layer." + std::to_string(i);
+    attn(p + ".attention", true);
+    attn(p + ".crossattention", false);
+    add_schema(raw, p + ".intermediate.dense.weight", I * H);
+    add_schema(raw, p + ".intermediate.dense.bias", I);
+    add_schema(raw, p + ".output.dense.weight", H * I);
+    add_schema(raw, p + ".output.dense.bias", H);
+    add_schema(raw, p + ".output.LayerNorm.weight", H);
+    add_schema(raw, p + ".output.LayerNorm.bias", H);
+  }
+  add_schema(raw, "amino_acid_predictor.dense1.weight", H * H);
+  add_schema(raw, "amino_acid_predictor.dense1.bias", H);
+  add_schema(raw, "amino_acid_predictor.layer_norm.weight", H);
+  add_schema(raw, "amino_acid_predictor.layer_norm.bias", H);
+  add_schema(raw, "amino_acid_predictor.dense2.weight", static_cast<int64_t>(c.feature_size) * H);
+  add_schema(raw, "amino_acid_predictor.dense2.bias", c.feature_size);
+  d_step = static_cast<int*>(dalloc(sizeof(int)));
+  SD_CHECK(d_step != nullptr, "cudaMalloc failed");
+  return SEQDIFF_OK;
+}
+
+int Model::set_tensor(const char* name, const float* data, int64_t numel, cudaStream_t s) {
+  auto it = raw.find(name);
+  if (it == raw.end()) {
+    set_error(std::string("unknown tensor name: ") + name);
+    return SEQDIFF_ERR_STATE;
+  }
+  RawTensor& t = it->second;
+  if (t.numel != numel) {
+    set_error(std::string("size mismatch for ") + name + ": expected " + std::to_string(t.numel) + ", got " + std::to_string(numel));
+    return SEQDIFF_ERR_INVALID;
+  }
+  // receptor_feature_emb is dead weight in the reference (quirk Q1): accepted, never stored.
+  if (std::strncmp(name, "receptor_feature_emb.", 21) == 0) {
+    t.set = true;
+    return SEQDIFF_OK;
+  }
+  if (!t.ptr) {
+    t.ptr = static_cast<float*>(dalloc(static_cast<size_t>(numel) * sizeof(float)));
+    SD_CHECK(t.ptr != nullptr, "cudaMalloc failed");
+  }
+  SD_CUDA(cudaMemcpyAsync(t.ptr, data, static_cast<size_t>(numel) * sizeof(float), cudaMemcpyDefault, s));
+  t.set = true;
+  finalized = false;
+  return SEQDIFF_OK;
+}
+
+int Model::finalize(cudaStream_t s) {
+  for (auto& kv : raw)
+    if (!kv.second.set) {
+      set_error("tensor never set: " + kv.first);
+      return SEQDIFF_ERR_STATE;
+    }
+  if (graph_exec) {  // weights changed: captured graph holds stale packed pointers only if re-allocated; be safe
+    cudaGraphExecDestroy(graph_exec);
+    graph_exec = nullptr;
+    graph_key = GraphKey();
+  }
+  if (!packed_allocs.empty()) {  // re-finalize after a weight update: drop the previous packed copies
+    SD_CUDA(cudaDeviceSynchronize());
+    for (void* p : packed_allocs) cudaFree(p);
+    packed_allocs.clear();
+  }
+  packing = true;
+  const int64_t H = cfg.hidden_size, I = cfg.intermediate_size, P = cfg.max_position_embeddings;
+  int rc = SEQDIFF_OK;
+  auto R = [&](const std::string& n) -> const float* { return raw.at(n).ptr; };
+  // fp32 matrix -> Wt with a bf16 copy
+  auto both = [&](const float* f, int64_t n) -> Wt {
+    Wt w;
+    w.f = f;
+    bf16* h = static_cast<bf16*>(dalloc(static_cast<size_t>(n) * sizeof(bf16)));
+    if (!h || f32_to_bf16(f, static_cast<size_t>(n), h, s) != SEQDIFF_OK) rc = SEQDIFF_ERR_CUDA;
+    w.h = h;
+    return w;
+  };
+  // stack several [rows_i, cols] fp32 tensors (row-wise) into a fresh buffer
+  auto stack = [&](const std::vector<const float*>& parts, int64_t each) -> float* {
+    float* dst = static_cast<float*>(dalloc(parts.size() * static_cast<size_t>(each) * sizeof(float)));
+    if (!dst) { rc = SEQDIFF_ERR_CUDA; return nullptr; }
+    for (size_t i = 0; i < parts.size(); ++i)
+      if (cudaMemcpyAsync(dst + i * each, parts[i], static_cast<size_t>(each) * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        rc = SEQDIFF_ERR_CUDA;
+    return dst;
+  };
+  auto emb = [&](const std::string& p, int fin) -> EmbW {
+    EmbW e;
+    e.fin = fin;
+    float* wt = static_cast<float*>(dalloc(static_cast<size_t>(H) * fin * sizeof(float)));
+    if (!wt || transpose_f32(R(p + ".linear.weight"), static_cast<int>(H), fin, wt, s) != SEQDIFF_OK) rc = SEQDIFF_ERR_CUDA;
+    e.Wt_ = wt;
+    e.b = R(p + ".linear.bias");
+    e.ln_w = R(p + ".LayerNorm.weight");
+    e.ln_b = R(p + ".LayerNorm.bias");
+    return e;
+  };
+  auto attn = [&](const std::string& p, bool self_rel) -> AttnW {
+    AttnW a;
+    const float* w = stack({R(p + ".self.query.weight"), R(p + ".self.key.weight"), R(p + ".self.value.weight")}, H * H);
+    a.qkv = both(w, 3 * H * H);
+    a.qkv_b = stack({R(p + ".self.query.bias"), R(p + ".self.key.bias"), R(p + ".self.value.bias")}, H);
+    if (self_rel && cfg.relative_key) a.E = both(R(p + ".self.distance_embedding.weight"), (2 * P - 1) * 64);
+    a.out = both(R(p + ".output.dense.weight"), H * H);
+    a.out_b = R(p + ".output.dense.bias");
+    a.ln_w = R(p + ".output.LayerNorm.weight");
+    a.ln_b = R(p + ".output.LayerNorm.bias");
+    return a;
+  };
+  auto se = [&](const std::string& p) -> SEW {
+    SEW w;
+    w.ada0 = both(R(p + ".adaLN_modulation.0.weight"), H * H);
+    w.ada0_b = R(p + ".adaLN_modulation.0.bias");
+    w.ada2 = both(R(p + ".adaLN_modulation.2.weight"), 6 * H * H);
+    w.ada2_b = R(p + ".adaLN_modulation.2.bias");
+    w.attn = attn(p + ".attn", true);
+    w.m0 = both(R(p + ".mlp.0.weight"), 4 * H * H);
+    w.m0_b = R(p + ".mlp.0.bias");
+    w.m3 = both(R(p + ".mlp.3.weight"), 4 * H * H);
+    w.m3_b = R(p + ".mlp.3.bias");
+    return w;
+  };
+  ts_W = R("timestep_projector.W");
+  lig_seq = emb("ligand_seq_embedding", 20);
+  lig_ang = emb("ligand_angle_embedding", 8);
+  rec_seq = emb("receptor_seq_embedding", 20);
+  rec_ang = emb("receptor_angle_embedding", 8);
+  se_lig = se("ligand_feature_emb");
+  se_dec = se("decoder_normalize");
+  layers.clear();
+  std::vector<const float*> ckv_w, ckv_b;
+  for (int i = 0; i < cfg.num_hidden_layers; ++i) {
+    const std::string p = "decoder.layer." + std::to_string(i);
+    LayerW l;
+    l.self = attn(p + ".attention", true);
+    l.cq = both(R(p + ".crossattention.self.query.weight"), H * H);
+    l.cq_b = R(p + ".crossattention.self.query.bias");
+    ckv_w.push_back(R(p + ".crossattention.self.key.weight"));
+    ckv_w.push_back(R(p + ".crossattention.self.value.weight"));
+    ckv_b.push_back(R(p + ".crossattention.self.key.bias"));
+    ckv_b.push_back(R(p + ".crossattention.self.value.bias"));
+    l.cout = both(R(p + ".crossattention.output.dense.weight"), H * H);
+    l.cout_b = R(p + ".crossattention.output.dense.bias");
+    l.cln_w = R(p + ".crossattention.output.LayerNorm.weight");
+    l.cln_b = R(p + ".crossattention.output.LayerNorm.bias");
+    l.inter = both(R(p + ".intermediate.dense.weight"), I * H);
+    l.inter_b = R(p + ".intermediate.dense.bias");
+    l.outd = both(R(p + ".output.dense.weight"), H * I);
+    l.outd_b = R(p + ".output.dense.bias");
+    l.oln_w = R(p + ".output.LayerNorm.weight");
+    l.oln_b = R(p + ".output.LayerNorm.bias");
+    layers.push_back(l);
+  }
+  ckv_all = both(stack(ckv_w, H * H), static_cast<int64_t>(ckv_w.size()) * H * H);
+  ckv_all_b = stack(ckv_b, H);
+  p1 = both(R("amino_acid_predictor.dense1.weight"), H * H);
+  p1_b = R("amino_acid_predictor.dense1.bias");
+  p_ln_w = R("amino_acid_predictor.layer_norm.weight");
+  p_ln_b = R("amino_acid_predictor.layer_norm.bias");
+  p2_w = R("amino_acid_predictor.dense2.weight");
+  p2_b = R("amino_acid_predictor.dense2.bias");
+  packing = false;
+  if (rc != SEQDIFF_OK) {
+    set_error("finalize: allocation or packing kernel failed");
+    return rc;
+  }
+  finalized = true;
+  return SEQDIFF_OK;
+}
+
+// =====================================================================================================
+// workspace
+// =====================================================================================================
+static size_t align256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
+
+size_t Model::workspace_need(int precision, int B, int Ll, int Lr) const {
+  const size_t es = precision == SEQDIFF_FP32 ? 4 : 2;
+  const size_t H = cfg.hidden_size, I = cfg.intermediate_size, NL = cfg.num_hidden_layers;
+  const size_t Ml = static_cast<size_t>(B) * Ll, Mr = static_cast<size_t>(B) * Lr, Mt = Ml + Mr;
+  size_t n = 0;
+  n += align256(static_cast<size_t>(B) * H * 4);      // te (fp32)
+  n += align256(static_cast<size_t>(B) * H * es);     // te in activation type
+  n += align256((Ml + Mr) * 4);                       // stacked masks
+  n += 8 * align256(Mt * H * es);                     // xcat ccat u ctx o x1 m2 x2
+  n += align256(Mt * 6 * H * es);                     // mod
+  n += align256(Mt * 3 * H * es);                     // qkv
+  n += align256(Mt * 4 * H * es);                     // m1
+  n += align256(Mr * NL * 2 * H * es);                // kv_all
+  n += 4 * align256(Ml * H * es);                     // h x2, cq, y
+  n += align256(Ml * I * es);                         // ffn
+  return n + 4096;
+}
+
+int Model::ensure_workspace(size_t bytes) {
+  if (bytes <= ws_bytes) return SEQDIFF_OK;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  (void)st;
+  if (ws) {
+    SD_CUDA(cudaDeviceSynchronize());
+    SD_CUDA(cudaFree(ws));
+    ws = nullptr;
+    ws_bytes = 0;
+  }
+  SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws), bytes));
+  ws_bytes = bytes;
+  return SEQDIFF_OK;
+}
+
+struct Bump {
+  uint8_t* p;
+  template <typename T> T* take(size_t n) {
+    T* r = reinterpret_cast<T*>(p);
+    p += align256(n * sizeof(T));
+    return r;
+  }
+};
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <typename T> struct SEBufs {
+  T *u, *mod, *qkv, *ctx, *o, *x1, *m1, *m2;
+};
+
+// SELayer.forward (model.py:52-63).  x:[M,H]; c:[Mc,H] with token row r using c row r / mod_div.
+template <typename T>
+static int se_layer(const Model& m, const SEW& w, const T* x, const T* c, int Mc, int mod_div, int M, const std::vector<Segment>& segs,
+                    const SEBufs<T>& b, T* out, cudaStream_t s) {
+  const int H = m.cfg.hidden_size, P = m.cfg.max_position_embeddings, heads = m.cfg.num_attention_heads;
+  SD_TRY(gemm_t(Mc, H, H, c, w.ada0, w.ada0_b, nullptr, 2, b.u, s));          // SiLU(Linear(c))
+  SD_TRY(gemm_t(Mc, 6 * H, H, b.u, w.ada2, w.ada2_b, nullptr, 0, b.mod, s));   // -> 6 chunks
+  SD_TRY(gemm_t(M, 3 * H, H, x, w.attn.qkv, w.attn.qkv_b, nullptr, 0, b.qkv, s));
+  for (const Segment& g : segs) {
+    const T* base = b.qkv + static_cast<size_t>(g.row0) * 3 * H;
+    SD_TRY(attention<T>(g.B, heads, g.L, g.L, base, 3 * H, base + H, 3 * H, base + 2 * H, 3 * H, pick<T>(w.attn.E), P, g.mask,
+                        b.ctx + static_cast<size_t>(g.row0) * H, s));
+  }
+  SD_TRY(gemm_t(M, H, H, b.ctx, w.attn.out, w.attn.out_b, x, 0, b.o, s));      // dense + residual
+  SD_TRY(ln_modulate<T>(b.o, M, H, true, w.attn.ln_w, w.attn.ln_b, m.cfg.layer_norm_eps, x, b.mod, mod_div, 0, b.x1, s));
+  SD_TRY(gemm_t(M, 4 * H, H, b.x1, w.m0, w.m0_b, nullptr, 1, b.m1, s));        // GELU
+  SD_TRY(gemm_t(M, H, 4 * H, b.m1, w.m3, w.m3_b, nullptr, 0, b.m2, s));
+  SD_TRY(ln_modulate<T>(b.m2, M, H, false, nullptr, nullptr, 0.f, b.x1, b.mod, mod_div, 3, out, s));
+  return SEQDIFF_OK;
+}
+
+static int to_act(const float* in, size_t n, float* out, cudaStream_t s) {
+  SD_CUDA(cudaMemcpyAsync(out, in, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return SEQDIFF_OK;
+}
+static int to_act(const float* in, size_t n, bf16* out, cudaStream_t s) { return f32_to_bf16(in, n, out, s); }
+
+template <typename T>
+int Model::forward_t(int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t, const float* lig_angle,
+                     const float* lig_mask, const float* rec_seq_in, const float* rec_angle, const float* rec_mask, float* logits,
+                     cudaStream_t s) {
+  const int H = cfg.hidden_size, I = cfg.intermediate_size, NL = cfg.num_hidden_layers, heads = cfg.num_attention_heads;
+  const int P = cfg.max_position_embeddings;
+  const float eps = cfg.layer_norm_eps;
+  const int Ml = B * Ll, Mr = B * Lr, Mt = Ml + Mr;
+  Bump bp{ws};
+  float* te = bp.take<float>(static_cast<size_t>(B) * H);
+  T* teT = bp.take<T>(static_cast<size_t>(B) * H);
+  float* maskcat = bp.take<float>(static_cast<size_t>(Ml) + Mr);
+  T* xcat = bp.take<T>(static_cast<size_t>(Mt) * H);
+  T* ccat = bp.take<T>(static_cast<size_t>(Mt) * H);
+  SEBufs<T> sb;
+  sb.u = bp.take<T>(static_cast<size_t>(Mt) * H);
+  sb.ctx = bp.take<T>(static_cast<size_t>(Mt) * H);
+  sb.o = bp.take<T>(static_cast<size_t>(Mt) * H);
+  sb.x1 = bp.take<T>(static_cast<size_t>(Mt) * H);
+  sb.m2 = bp.take<T>(static_cast<size_t>(Mt) * H);
+  T* x2 = bp.take<T>(static_cast<size_t>(Mt) * H);
+  sb.mod = bp.take<T>(static_cast<size_t>(Mt) * 6 * H);
+  sb.qkv = bp.take<T>(static_cast<size_t>(Mt) * 3 * H);
+  sb.m1 = bp.take<T>(static_cast<size_t>(Mt) * 4 * H);
+  T* kv_all = bp.take<T>(static_cast<size_t>(Mr) * NL * 2 * H);
+  T* hbuf[2];
+  for (int i = 0; i < 2; ++i) hbuf[i] = bp.take<T>(static_cast<size_t>(Ml) * H);
+  T* cq = bp.take<T>(static_cast<size_t>(Ml) * H);
+  T* y = bp.take<T>(static_cast<size_t>(Ml) * H);
+  T* ffn = bp.take<T>(static_cast<size_t>(Ml) * I);
+
+  // timestep features + the four BertEmbeddings (model.py:211-213,219-220)
+  SD_TRY(timestep_embed(timestep, step_ptr, ts_W, B, H, te, s));
+  SD_TRY(embed_ln<T>(x_t, Ml, 20, lig_seq.Wt_, lig_seq.b, lig_seq.ln_w, lig_seq.ln_b, eps, nullptr, Ll, H, xcat, s));
+  SD_TRY(embed_ln<T>(lig_angle, Ml, 8, lig_ang.Wt_, lig_ang.b, lig_ang.ln_w, lig_ang.ln_b, eps, te, Ll, H, ccat, s));
+  SD_TRY(embed_ln<T>(rec_seq_in, Mr, 20, rec_seq.Wt_, rec_seq.b, rec_seq.ln_w, rec_seq.ln_b, eps, nullptr, Lr, H,
+                     xcat + static_cast<size_t>(Ml) * H, s));
+  SD_TRY(embed_ln<T>(rec_angle, Mr, 8, rec_ang.Wt_, rec_ang.b, rec_ang.ln_w, rec_ang.ln_b, eps, te, Lr, H,
+                     ccat + static_cast<size_t>(Ml) * H, s));
+
+  // ligand_feature_emb on ligand AND receptor tokens in one pass (model.py:214-224, quirk Q1)
+  std::vector<Segment> segs;
+  if (Ll == Lr) {
+    SD_CUDA(cudaMemcpyAsync(maskcat, lig_mask, static_cast<size_t>(Ml) * 4, cudaMemcpyDeviceToDevice, s));
+    SD_CUDA(cudaMemcpyAsync(maskcat + Ml, rec_mask, static_cast<size_t>(Mr) * 4, cudaMemcpyDeviceToDevice, s));
+    segs.push_back({0, 2 * B, Ll, maskcat});
+  } else {
+    segs.push_back({0, B, Ll, lig_mask});
+    segs.push_back({Ml, B, Lr, rec_mask});
+  }
+  SD_TRY(se_layer<T>(*this, se_lig, xcat, ccat, Mt, 1, Mt, segs, sb, x2, s));
+  const T* lig = x2;
+  const T* rec = x2 + static_cast<size_t>(Ml) * H;
+
+  // decoder: 6 x (self-attn -> cross-attn -> FFN), post-LN (HF BertLayer; model.py:226-231)
+  SD_TRY(gemm_t(Mr, NL * 2 * H, H, rec, ckv_all, ckv_all_b, nullptr, 0, kv_all, s));
+  const T* h = lig;
+  for (int i = 0; i < NL; ++i) {
+    const LayerW& w = layers[i];
+    // h is dead once the self-output GEMM has folded it in as the residual, so h1/h3 may reuse its buffer
+    T* h1 = hbuf[0];
+    T* h2 = hbuf[1];
+    T* h3 = hbuf[0];
+    SD_TRY(gemm_t(Ml, 3 * H, H, h, w.self.qkv, w.self.qkv_b, nullptr, 0, sb.qkv, s));
+    SD_TRY(attention<T>(B, heads, Ll, Ll, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s));
+    SD_TRY(gemm_t(Ml, H, H, sb.ctx, w.self.out, w.self.out_b, h, 0, sb.o, s));
+    SD_TRY(layernorm<T>(sb.o, Ml, H, w.self.ln_w, w.self.ln_b, eps, h1, s));
+    SD_TRY(gemm_t(Ml, H, H, h1, w.cq, w.cq_b, nullptr, 0, cq, s));
+    const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
+    SD_TRY(attention<T>(B, heads, Ll, Lr, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s));
+    SD_TRY(gemm_t(Ml, H, H, sb.ctx, w.cout, w.cout_b, h1, 0, sb.o, s));
+    SD_TRY(layernorm<T>(sb.o, Ml, H, w.cln_w, w.cln_b, eps, h2, s));
+    SD_TRY(gemm_t(Ml, I, H, h2, w.inter, w.inter_b, nullptr, 1, ffn, s));
+    SD_TRY(gemm_t(Ml, H, I, ffn, w.outd, w.outd_b, h2, 0, sb.o, s));
+    SD_TRY(layernorm<T>(sb.o, Ml, H, w.oln_w, w.oln_b, eps, h3, s));
+    h = h3;
+  }
+
+  // decoder_normalize: SELayer conditioned on the timestep only (c broadcast over L; model.py:232-235)
+  SD_TRY(to_act(te, static_cast<size_t>(B) * H, teT, s));
+  std::vector<Segment> lseg{{0, B, Ll, lig_mask}};
+  SD_TRY(se_layer<T>(*this, se_dec, h, teT, B, Ll, Ml, lseg, sb, xcat, s));
+
+  // AminoAcidPredictor (model.py:148-153)
+  SD_TRY(gemm_t(Ml, H, H, xcat, p1, p1_b, nullptr, 1, y, s));
+  SD_TRY(predictor_tail<T>(y, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, logits, s));
+  return SEQDIFF_OK;
+}
+
+int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t,
+                   const float* lig_angle, const float* lig_mask, const float* rec_seq_in, const float* rec_angle,
+                   const float* rec_mask, float* logits, cudaStream_t s) {
+  SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
+  SD_CHECK(precision == SEQDIFF_FP32 || precision == SEQDIFF_BF16, "precision must be SEQDIFF_FP32 or SEQDIFF_BF16");
+  SD_CHECK(B > 0 && Ll > 0 && Lr > 0, "empty batch");
+  if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
+  SD_CUDA(cudaSetDevice(device));
+  SD_TRY(ensure_workspace(workspace_need(precision, B, Ll, Lr)));
+  if (precision == SEQDIFF_FP32)
+    return forward_t<float>(B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+  return forward_t<bf16>(B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+}
+
+// =====================================================================================================
+// reverse-diffusion loop: one captured CUDA graph per step shape, replayed T times
+// =====================================================================================================
+int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_tables, const float* x_T, const float* lig_angle,
+                  const float* lig_mask, const float* rec_seq_in, const float* rec_angle, const float* rec_mask, int diverse,
+                  const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t s) {
+  SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
+  SD_CHECK(T >= 1 && B > 0 && Ll > 0 && Lr > 0, "bad sampling arguments");
+  SD_CHECK(cfg.feature_size == SEQDIFF_NUM_CLASSES, "sampling needs feature_size == 20");
+  SD_CUDA(cudaSetDevice(device));
+  const size_t Nl = static_cast<size_t>(B) * Ll, Nr = static_cast<size_t>(B) * Lr;
+  // persistent inputs: x_cur | logits | lig_angle | lig_mask | rec_seq | rec_angle | rec_mask
+  const size_t need_in = align256(Nl * 20 * 4) * 2 + align256(Nl * 8 * 4) + align256(Nl * 4) + align256(Nr * 20 * 4) +
+                         align256(Nr * 8 * 4) + align256(Nr * 4);
+  if (need_in > samp_in_bytes) {
+    if (samp_in) { SD_CUDA(cudaDeviceSynchronize()); SD_CUDA(cudaFree(samp_in)); samp_in = nullptr; samp_in_bytes = 0; }
+    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&samp_in), need_in));
+    samp_in_bytes = need_in;
+  }
+  const size_t tab_floats = static_cast<size_t>(T) * 3 * 400;
+  if (tab_floats > tables_cap) {
+    if (d_tables) { SD_CUDA(cudaDeviceSynchronize()); SD_CUDA(cudaFree(d_tables)); d_tables = nullptr; tables_cap = 0; }
+    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_tables), tab_floats * 4));
+    tables_cap = tab_floats;
+  }
+  SD_TRY(ensure_workspace(workspace_need(precision, B, Ll, Lr)));
+  Bump bp{samp_in};
+  float* x_cur = bp.take<float>(Nl * 20);
+  float* logits = bp.take<float>(Nl * 20);
+  float* c_lang = bp.take<float>(Nl * 8);
+  float* c_lmask = bp.take<float>(Nl);
+  float* c_rseq = bp.take<float>(Nr * 20);
+  float* c_rang = bp.take<float>(Nr * 8);
+  float* c_rmask = bp.take<float>(Nr);
+  SD_CUDA(cudaMemcpyAsync(d_tables, q_tables, tab_floats * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(x_cur, x_T, Nl * 20 * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_lang, lig_angle, Nl * 8 * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_lmask, lig_mask, Nl * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_rseq, rec_seq_in, Nr * 20 * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_rang, rec_angle, Nr * 8 * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_rmask, rec_mask, Nr * 4, cudaMemcpyDefault, s));
+
+  GraphKey key;
+  key.precision = precision; key.B = B; key.Ll = Ll; key.Lr = Lr; key.diverse = diverse; key.noise = noise_E;
+  key.seed = seed; key.gid0 = gid0; key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables;
+  auto one_step = [&](cudaStream_t st) -> int {
+    SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, st));
+    SD_TRY(reverse_step(d_tables, 1, B, Ll, x_cur, logits, diverse, noise_E, seed, gid0, 0, d_step, x_cur, nullptr, st));
+    SD_TRY(step_advance(d_step, st));
+    return SEQDIFF_OK;
+  };
+  if (!graph_exec || !(key == graph_key)) {
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    // un-captured dry run of the forward: sets kernel attributes and fills the TMA descriptor cache
+    set_int_kernel<<<1, 1, 0, s>>>(d_step, T - 1);
+    SD_LAUNCH_CHECK();
+    SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, s));
+    SD_CUDA(cudaStreamSynchronize(s));
+    cudaGraph_t graph = nullptr;
+    SD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = one_step(s);
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc != SEQDIFF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    SD_CUDA(ce);
+    ce = cudaGraphInstantiate(&graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    SD_CUDA(ce);
+    graph_key = key;
+  }
+  set_int_kernel<<<1, 1, 0, s>>>(d_step, T - 1);
+  SD_LAUNCH_CHECK();
+  for (int it = 0; it < T; ++it) SD_CUDA(cudaGraphLaunch(graph_exec, s));
+  SD_CUDA(cudaMemcpyAsync(final_out, logits, Nl * 20 * 4, cudaMemcpyDefault, s));
+  return SEQDIFF_OK;
+}
+
+}  // namespace seqdiff

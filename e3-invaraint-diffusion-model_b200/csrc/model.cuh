@@ -1,0 +1,113 @@
+// model.cuh -- the seqdiff model handle (opaque `seqdiff_model_t` of the C ABI).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace seqdiff {
+
+// one logical matrix, held in both precisions (bf16 copy made by finalize())
+struct Wt {
+  const float* f = nullptr;
+  const bf16* h = nullptr;
+};
+
+struct AttnW {
+  Wt qkv;  // [3H,H] rows = query | key | value  (self-attention only)
+  const float* qkv_b = nullptr;
+  Wt E;  // distance_embedding [2P-1,64] or null
+  Wt out;
+  const float *out_b = nullptr, *ln_w = nullptr, *ln_b = nullptr;
+};
+struct SEW {  // SELayer, model.py:26-66
+  Wt ada0, ada2, m0, m3;
+  const float *ada0_b = nullptr, *ada2_b = nullptr, *m0_b = nullptr, *m3_b = nullptr;
+  AttnW attn;
+};
+struct LayerW {  // HF BertLayer with cross-attention
+  AttnW self;
+  Wt cq, cout, inter, outd;
+  const float *cq_b = nullptr, *cout_b = nullptr, *cln_w = nullptr, *cln_b = nullptr;
+  const float *inter_b = nullptr, *outd_b = nullptr, *oln_w = nullptr, *oln_b = nullptr;
+};
+struct EmbW {  // BertEmbeddings, model.py:99-117
+  const float *Wt_ = nullptr, *b = nullptr, *ln_w = nullptr, *ln_b = nullptr;
+  int fin = 0;
+};
+
+struct RawTensor {
+  float* ptr = nullptr;
+  int64_t numel = 0;
+  bool set = false;
+};
+
+struct Segment {  // a run of graphs sharing one padded length inside a token matrix
+  int row0, B, L;
+  const float* mask;
+};
+
+struct Model {
+  seqdiff_config_t cfg{};
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, RawTensor> raw;  // reference state_dict key -> fp32 device tensor
+  std::vector<void*> allocs;         // raw tensors + small state (life of the handle)
+  std::vector<void*> packed_allocs;  // fused / bf16 copies made by finalize()
+  bool packing = false;
+
+  EmbW lig_seq, lig_ang, rec_seq, rec_ang;
+  SEW se_lig, se_dec;
+  std::vector<LayerW> layers;
+  Wt ckv_all;  // all layers' cross key|value weights stacked: [layers*2H, H]
+  const float* ckv_all_b = nullptr;
+  Wt p1;
+  const float *p1_b = nullptr, *p_ln_w = nullptr, *p_ln_b = nullptr, *p2_w = nullptr, *p2_b = nullptr, *ts_W = nullptr;
+
+  // workspace (grow-only)
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+
+  // sampling-loop state
+  int* d_step = nullptr;
+  float* d_tables = nullptr;
+  size_t tables_cap = 0;
+  uint8_t* samp_in = nullptr;  // persistent copies of the loop inputs + x_t + logits
+  size_t samp_in_bytes = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  struct GraphKey {
+    int precision = -1, B = 0, Ll = 0, Lr = 0, diverse = 0;
+    const float* noise = nullptr;
+    uint64_t seed = 0, gid0 = 0;
+    const void* ws_ptr = nullptr;
+    const void* in_ptr = nullptr;
+    const void* tab_ptr = nullptr;
+    bool operator==(const GraphKey& o) const {
+      return precision == o.precision && B == o.B && Ll == o.Ll && Lr == o.Lr && diverse == o.diverse && noise == o.noise &&
+             seed == o.seed && gid0 == o.gid0 && ws_ptr == o.ws_ptr && in_ptr == o.in_ptr && tab_ptr == o.tab_ptr;
+    }
+  } graph_key;
+
+  ~Model();
+  int init(const seqdiff_config_t& c, int dev);
+  int set_tensor(const char* name, const float* data, int64_t numel, cudaStream_t s);
+  int finalize(cudaStream_t s);
+  int forward(int precision, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t,
+              const float* lig_angle, const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask,
+              float* logits, cudaStream_t s);
+  int sample(int precision, int B, int Ll, int Lr, int T, const float* q_tables, const float* x_T, const float* lig_angle,
+             const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, int diverse,
+             const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t s);
+
+ private:
+  void* dalloc(size_t bytes);
+  size_t workspace_need(int precision, int B, int Ll, int Lr) const;
+  int ensure_workspace(size_t bytes);
+  template <typename T>
+  int forward_t(int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t, const float* lig_angle,
+                const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, float* logits,
+                cudaStream_t s);
+};
+
+}  // namespace seqdiff

@@ -1,0 +1,279 @@
+// reverse_step.cu -- the discrete reverse-diffusion step, sequence_model/sample.py:120-179
+// (sample_p_zs_given_zt_discrete + compute_batched_over0_posterior_distribution), and the training
+// q-sample PeptideDiff.apply_aa_noise (model.py:291-311).
+//
+// Reference arithmetic per residue n of graph b (all fp32, C = 20 classes):
+//   p        = softmax(logits[n])                                              sample.py:162
+//   post[i,j]= (Qt[b][j,:].x_t[n]) * Qsb[b][i,j] / (Qtb[b][i,:].x_t[n])          sample.py:129-138 (0 -> 1e-6)
+//   un[j]    = sum_i p[i] * post[i,j]      (product rounded, then summed over i) sample.py:165-166
+//   un[:]    = 1e-5 if sum_j un[j] == 0;  prob = un / sum_j un                   sample.py:167-168
+//   x_s      = multinomial(prob) = argmax_j prob[j] / E[j], E ~ Exp(1)  |  argmax_j prob[j]   sample.py:169-177
+// The reference materialises three [N,20,20] tensors and loops over N rows in Python.  Here one CTA
+// owns one graph: the (Qt,Qsb,Qtb) triple is staged in shared memory, the 20x20x20 table
+// post_x[i,j] for every possible one-hot x_t is built once per CTA with the SAME rounding sequence
+// (mul, then IEEE divide), and each thread then resolves one residue with 400 multiply-adds.
+// Rows of x_t that are not exactly one-hot take the general (dot-product) formula.
+// Traffic: 80 B logits + 80 B x_t in, 80 B one-hot out per residue (+80 B if the noise E is supplied).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace seqdiff {
+
+constexpr int C = SEQDIFF_NUM_CLASSES;
+constexpr int kRevThreads = 128;
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based: identical streams for any sharding ----------
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c[0];
+  const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c[2];
+  const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c[1] ^ k0;
+  const uint32_t n1 = static_cast<uint32_t>(p1);
+  const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c[3] ^ k1;
+  const uint32_t n3 = static_cast<uint32_t>(p0);
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// raw words for (graph, residue-in-graph, step): class j uses word j%4 of call j/4.
+// counter = (residue, step*8 + call, graph_lo, graph_hi), key = seed.
+__device__ __forceinline__ void philox_row(uint64_t seed, uint64_t graph, uint32_t residue, uint32_t step, uint32_t (&w)[C]) {
+#pragma unroll
+  for (int call = 0; call < C / 4; ++call) {
+    uint32_t c[4] = {residue, step * 8u + call, static_cast<uint32_t>(graph), static_cast<uint32_t>(graph >> 32)};
+    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[call * 4 + i] = c[i];
+  }
+}
+// u in (0,1) exactly representable: ((w >> 9) + 0.5) * 2^-23 ;  E = -log(u) > 0
+__device__ __forceinline__ float exp1_from_u32(uint32_t w) {
+  const float u = (static_cast<float>(w >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  return -logf(u);
+}
+
+// exponential race / argmax over one normalised row
+__device__ __forceinline__ int pick_class(const float (&prob)[C], bool diverse, const float (&E)[C]) {
+  int best = 0;
+  float bv = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const float v = diverse ? __fdiv_rn(prob[j], E[j]) : prob[j];
+    if (v > bv) { bv = v; best = j; }  // first maximum wins, like torch.argmax
+  }
+  return best;
+}
+
+__device__ __forceinline__ void write_onehot(float* __restrict__ row, int idx) {
+#pragma unroll
+  for (int j4 = 0; j4 < C; j4 += 4) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx == j4) o.x = 1.f;
+    if (idx == j4 + 1) o.y = 1.f;
+    if (idx == j4 + 2) o.z = 1.f;
+    if (idx == j4 + 3) o.w = 1.f;
+    *reinterpret_cast<float4*>(row + j4) = o;
+  }
+}
+
+__global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* __restrict__ q_tables, int n_tab, int L,
+                                                                   const float* __restrict__ x_t, const float* __restrict__ logits,
+                                                                   int diverse, const float* __restrict__ noise_E, uint64_t seed,
+                                                                   uint64_t graph_id0, uint32_t step, const int* __restrict__ step_ptr,
+                                                                   float* __restrict__ x_s, uint8_t* __restrict__ idx_out) {
+  __shared__ float sQt[C * C], sQsb[C * C], sQtb[C * C];
+  __shared__ float sPost[C * C * C];  // [x][i][j]
+  const int b = blockIdx.x;
+  const size_t n_res = static_cast<size_t>(gridDim.x) * L;
+  if (step_ptr) {
+    const int sidx = *step_ptr;
+    if (sidx == 0) return;  // last step: caller keeps the raw logits (sample.py:147-148)
+    step = static_cast<uint32_t>(sidx);
+    q_tables += static_cast<size_t>(sidx) * (3 * C * C);
+    if (noise_E) noise_E += static_cast<size_t>(sidx) * n_res * C;
+  }
+  const float* tab = q_tables + static_cast<size_t>(n_tab == 1 ? 0 : b) * (3 * C * C);
+  for (int i = threadIdx.x; i < C * C; i += kRevThreads) {
+    sQt[i] = tab[i];
+    sQsb[i] = tab[C * C + i];
+    sQtb[i] = tab[2 * C * C + i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < C * C * C; e += kRevThreads) {
+    const int x = e / (C * C), i = (e / C) % C, j = e % C;
+    float den = sQtb[i * C + x];
+    if (den == 0.f) den = 1e-6f;
+    sPost[e] = __fdiv_rn(__fmul_rn(sQt[j * C + x], sQsb[i * C + j]), den);
+  }
+  __syncthreads();
+
+  for (int l = threadIdx.x; l < L; l += kRevThreads) {
+    const size_t n = static_cast<size_t>(b) * L + l;
+    float lg[C], xr[C];
+#pragma unroll
+    for (int j4 = 0; j4 < C; j4 += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(logits + n * C + j4);
+      const float4 c4 = *reinterpret_cast<const float4*>(x_t + n * C + j4);
+      lg[j4] = a.x; lg[j4 + 1] = a.y; lg[j4 + 2] = a.z; lg[j4 + 3] = a.w;
+      xr[j4] = c4.x; xr[j4 + 1] = c4.y; xr[j4 + 2] = c4.z; xr[j4 + 3] = c4.w;
+    }
+    // softmax(logits)
+    float mx = lg[0];
+#pragma unroll
+    for (int j = 1; j < C; ++j) mx = fmaxf(mx, lg[j]);
+    float p[C], ps = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { p[j] = expf(lg[j] - mx); ps += p[j]; }
+#pragma unroll
+    for (int j = 0; j < C; ++j) p[j] = __fdiv_rn(p[j], ps);
+    // one-hot?
+    int hot = -1, nnz = 0;
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+      if (xr[j] != 0.f) { ++nnz; hot = (xr[j] == 1.0f) ? j : -2; }
+    float un[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) un[j] = 0.f;
+    if (nnz == 1 && hot >= 0) {
+      const float* post = sPost + hot * (C * C);
+#pragma unroll 4
+      for (int i = 0; i < C; ++i) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) un[j] = __fadd_rn(un[j], __fmul_rn(p[i], post[i * C + j]));
+      }
+    } else {  // general x_t row: left[j] = Qt[j,:].x, den[i] = Qtb[i,:].x
+      float left[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) a = fmaf(xr[k], sQt[j * C + k], a);
+        left[j] = a;
+      }
+      for (int i = 0; i < C; ++i) {
+        float den = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) den = fmaf(sQtb[i * C + k], xr[k], den);
+        if (den == 0.f) den = 1e-6f;
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+          un[j] = __fadd_rn(un[j], __fmul_rn(p[i], __fdiv_rn(__fmul_rn(left[j], sQsb[i * C + j]), den)));
+      }
+    }
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) tot += un[j];
+    if (tot == 0.f) {
+      tot = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) { un[j] = 1e-5f; tot += 1e-5f; }
+    }
+    float prob[C], psum = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { prob[j] = __fdiv_rn(un[j], tot); psum += prob[j]; }
+    float E[C];
+    if (diverse) {
+      if (noise_E) {
+#pragma unroll
+        for (int j4 = 0; j4 < C; j4 += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(noise_E + n * C + j4);
+          E[j4] = a.x; E[j4 + 1] = a.y; E[j4 + 2] = a.z; E[j4 + 3] = a.w;
+        }
+      } else {
+        uint32_t w[C];
+        philox_row(seed, graph_id0 + b, static_cast<uint32_t>(l), step, w);
+#pragma unroll
+        for (int j = 0; j < C; ++j) E[j] = exp1_from_u32(w[j]);
+      }
+    }
+    int idx = 0;
+    if (psum != 0.f) idx = pick_class(prob, diverse != 0, E);
+    write_onehot(x_s + n * C, idx);
+    if (idx_out) idx_out[n] = static_cast<uint8_t>(idx);
+  }
+}
+
+int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_t, const float* logits, int diverse,
+                 const float* noise_E, uint64_t seed, uint64_t graph_id0, uint32_t step, const int* step_ptr, float* x_s,
+                 uint8_t* idx_out, cudaStream_t s) {
+  SD_CHECK(B > 0 && L > 0, "empty reverse step");
+  SD_CHECK(n_tab == 1 || n_tab == B, "q_tables must hold 1 or B (Qt,Qsb,Qtb) triples");
+  reverse_step_kernel<<<B, kRevThreads, 0, s>>>(q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr,
+                                                x_s, idx_out);
+  SD_LAUNCH_CHECK();
+  return SEQDIFF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// q-sample (training): prob[i] = Qtb[b][i,:].x0[n]; all-zero rows (padding) -> class 0  (model.py:301-308)
+__global__ void __launch_bounds__(kRevThreads) apply_aa_noise_kernel(const float* __restrict__ qtb, int L, const float* __restrict__ x0,
+                                                                     const float* __restrict__ noise_E, uint64_t seed, uint64_t graph_id0,
+                                                                     uint32_t step, float* __restrict__ x_t, uint8_t* __restrict__ idx_out) {
+  __shared__ float sQ[C * C];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < C * C; i += kRevThreads) sQ[i] = qtb[static_cast<size_t>(b) * C * C + i];
+  __syncthreads();
+  for (int l = threadIdx.x; l < L; l += kRevThreads) {
+    const size_t n = static_cast<size_t>(b) * L + l;
+    float xr[C];
+#pragma unroll
+    for (int j4 = 0; j4 < C; j4 += 4) {
+      const float4 c4 = *reinterpret_cast<const float4*>(x0 + n * C + j4);
+      xr[j4] = c4.x; xr[j4 + 1] = c4.y; xr[j4 + 2] = c4.z; xr[j4 + 3] = c4.w;
+    }
+    float prob[C], psum = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) a = fmaf(sQ[i * C + k], xr[k], a);  // exact for one-hot rows
+      prob[i] = a;
+      psum += a;
+    }
+    int idx = 0;
+    if (psum != 0.f) {
+      float E[C];
+      if (noise_E) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) E[j] = noise_E[n * C + j];
+      } else {
+        uint32_t w[C];
+        philox_row(seed, graph_id0 + b, static_cast<uint32_t>(l), step, w);
+#pragma unroll
+        for (int j = 0; j < C; ++j) E[j] = exp1_from_u32(w[j]);
+      }
+      idx = pick_class(prob, true, E);
+    }
+    write_onehot(x_t + n * C, idx);
+    if (idx_out) idx_out[n] = static_cast<uint8_t>(idx);
+  }
+}
+
+int apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float* noise_E, uint64_t seed, uint64_t graph_id0,
+                   uint32_t step, float* x_t, uint8_t* idx_out, cudaStream_t s) {
+  SD_CHECK(B > 0 && L > 0, "empty q-sample");
+  apply_aa_noise_kernel<<<B, kRevThreads, 0, s>>>(qtb, L, x0, noise_E, seed, graph_id0, step, x_t, idx_out);
+  SD_LAUNCH_CHECK();
+  return SEQDIFF_OK;
+}
+
+__global__ void philox_u32_kernel(uint64_t seed, uint64_t graph_id0, uint32_t step, int L, uint32_t* __restrict__ out) {
+  const int b = blockIdx.x;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    uint32_t w[C];
+    philox_row(seed, graph_id0 + b, static_cast<uint32_t>(l), step, w);
+    for (int j = 0; j < C; ++j) out[(static_cast<size_t>(b) * L + l) * C + j] = w[j];
+  }
+}
+int philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, cudaStream_t s) {
+  philox_u32_kernel<<<B, 128, 0, s>>>(seed, graph_id0, step, L, out);
+  SD_LAUNCH_CHECK();
+  return SEQDIFF_OK;
+}
+
+}  // namespace seqdiff

@@ -1,0 +1,364 @@
+"""Drop-in for `sequence_model/model.py` of the reference: same class names, constructor and forward
+signatures, same state_dict keys and shapes -- but `forward` runs the
+hand-written sm_100a kernels of libseqdiff_b200.so through the C ABI (include/seqdiff_b200.h).
+
+The nn.Module tree below is a PARAMETER CONTAINER: it exists so `load_state_dict(torch.load(path))`
+(reference sample.py:106), `.to(device)`, `.parameters()` and checkpoints keep working.  None of its
+sub-module forwards are on the product path; there is no PyTorch / CPU fallback -- without the CUDA
+library or a CUDA device `forward` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _cabi
+from .utils import BlosumTransition, DiscreteUniformTransition, PredefinedNoiseScheduleDiscrete, elbo_loss, step_tables
+
+AA_VOCAB = "ACDEFGHIKLMNPQRSTVWY"
+
+
+@dataclass
+class BertConfig:
+    """The subset of transformers.BertConfig the path consumes (reference sample.py:69-92).  A real
+    transformers.BertConfig is accepted everywhere one of these is (duck-typed)."""
+
+    max_position_embeddings: int = 512
+    num_attention_heads: int = 12
+    hidden_size: int = 768
+    intermediate_size: int = 3072
+    num_hidden_layers: int = 12
+    position_embedding_type: str = "absolute"
+    hidden_dropout_prob: float = 0.1
+    attention_probs_dropout_prob: float = 0.1
+    layer_norm_eps: float = 1e-12
+    hidden_act: str = "gelu"
+    use_cache: bool = True
+    is_decoder: bool = False
+    add_cross_attention: bool = False
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (names = reference attribute names => identical state_dict keys)
+# ------------------------------------------------------------------------------------------------
+class _Container(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: the computation runs inside ConditionalBertForDiffusionBase.forward "
+                           "(CUDA, libseqdiff_b200.so)")
+
+
+class _SelfAttention(_Container):  # HF BertSelfAttention, transformers 4.38.2 layout
+    def __init__(self, cfg, relative: bool):
+        super().__init__()
+        H = cfg.hidden_size
+        self.query, self.key, self.value = nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
+        if relative:
+            self.distance_embedding = nn.Embedding(2 * cfg.max_position_embeddings - 1, H // cfg.num_attention_heads)
+
+
+class _SelfOutput(_Container):  # HF BertSelfOutput / BertOutput
+    def __init__(self, cfg, fan_in=None):
+        super().__init__()
+        self.dense = nn.Linear(fan_in or cfg.hidden_size, cfg.hidden_size)
+        self.LayerNorm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+
+
+class _Intermediate(_Container):
+    def __init__(self, cfg):
+        super().__init__()
+        self.dense = nn.Linear(cfg.hidden_size, cfg.intermediate_size)
+
+
+class BertAttention(_Container):
+    def __init__(self, cfg, relative: bool):
+        super().__init__()
+        self.self = _SelfAttention(cfg, relative)
+        self.output = _SelfOutput(cfg)
+
+
+class _BertLayer(_Container):
+    def __init__(self, cfg, relative: bool):
+        super().__init__()
+        self.attention = BertAttention(cfg, relative)
+        self.crossattention = BertAttention(cfg, False)  # 4.38.2: position_embedding_type="absolute"
+        self.intermediate = _Intermediate(cfg)
+        self.output = _SelfOutput(cfg, cfg.intermediate_size)
+
+
+class BertEncoder(_Container):
+    def __init__(self, cfg, relative: bool):
+        super().__init__()
+        self.layer = nn.ModuleList([_BertLayer(cfg, relative) for _ in range(cfg.num_hidden_layers)])
+
+
+class SELayer(_Container):
+    """reference model.py:26-66."""
+
+    def __init__(self, bert_config, mlp_ratio=4.0, **block_kwargs):
+        super().__init__()
+        H = bert_config.hidden_size
+        relative = getattr(bert_config, "position_embedding_type", "absolute") == "relative_key"
+        self.adaLN_modulation = nn.Sequential(nn.Linear(H, H, bias=True), nn.SiLU(), nn.Linear(H, 6 * H, bias=True))
+        self.attn = BertAttention(bert_config, relative)
+        self.mlp = nn.Sequential(nn.Linear(H, int(H * mlp_ratio)), nn.GELU(), nn.Dropout(bert_config.hidden_dropout_prob),
+                                 nn.Linear(int(H * mlp_ratio), H), nn.Dropout(bert_config.hidden_dropout_prob))
+        nn.init.zeros_(self.adaLN_modulation[0].weight)
+        nn.init.zeros_(self.adaLN_modulation[0].bias)
+
+
+class GaussianFourierProjection(_Container):
+    """reference model.py:68-97 (buffer only; sin/cos features are computed in the CUDA forward)."""
+
+    def __init__(self, embed_dim: int = 384, scale: float = 2 * torch.pi):
+        super().__init__()
+        w = torch.randn(embed_dim // 2) * scale
+        self.register_buffer("W", w)
+
+
+class BertEmbeddings(_Container):
+    """reference model.py:99-117."""
+
+    def __init__(self, in_features, bert_config):
+        super().__init__()
+        self.linear = nn.Linear(in_features, bert_config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(bert_config.hidden_size, eps=bert_config.layer_norm_eps)
+
+
+class AminoAcidPredictor(_Container):
+    """reference model.py:119-153."""
+
+    def __init__(self, d_model: int, d_out: int = 4, activation="gelu", eps: float = 1e-12) -> None:
+        super().__init__()
+        if activation != "gelu":
+            raise ValueError("only the reference's default 'gelu' head is implemented in CUDA")
+        self.d_model, self.d_out = d_model, d_out
+        self.dense1 = nn.Linear(d_model, d_model)
+        self.layer_norm = nn.LayerNorm(d_model, eps=eps)
+        self.dense2 = nn.Linear(d_model, d_out)
+
+
+# ------------------------------------------------------------------------------------------------
+class ConditionalBertForDiffusionBase(nn.Module):
+    """reference model.py:156-253.  `precision`: "bf16" (tcgen05 GEMMs; logits within 1e-2 of the fp32
+    reference) or "fp32" (SIMT fp32 kernels; within 1e-5)."""
+
+    def __init__(self, encoder_config, decoder_config, feature_size: int) -> None:
+        super().__init__()
+        self.encoder_config = encoder_config
+        self.decoder_config = decoder_config
+        self.feature_size = feature_size
+        self.precision = "bf16"
+        relative = getattr(decoder_config, "position_embedding_type", "absolute") == "relative_key"
+        self.timestep_projector = GaussianFourierProjection(decoder_config.hidden_size)
+        self.ligand_seq_embedding = BertEmbeddings(20, encoder_config)
+        self.ligand_angle_embedding = BertEmbeddings(8, encoder_config)
+        self.ligand_feature_emb = SELayer(encoder_config)
+        self.receptor_seq_embedding = BertEmbeddings(20, encoder_config)
+        self.receptor_angle_embedding = BertEmbeddings(8, encoder_config)
+        self.receptor_feature_emb = SELayer(encoder_config)  # dead weight in the reference too (model.py:221)
+        self.decoder = BertEncoder(decoder_config, relative)
+        self.decoder_normalize = SELayer(decoder_config)
+        self.amino_acid_predictor = AminoAcidPredictor(decoder_config.hidden_size, feature_size)
+        self.initialize_weights()
+        self._handle = None
+        self._handle_sig = None
+        self._handle_dev = None
+
+    def initialize_weights(self):
+        """reference model.py:183-198."""
+
+        def _basic_init(module):
+            if isinstance(module, nn.Linear):
+                torch.nn.init.xavier_uniform_(module.weight)
+                if module.bias is not None:
+                    nn.init.constant_(module.bias, 0)
+
+        self.apply(_basic_init)
+        nn.init.constant_(self.decoder_normalize.adaLN_modulation[0].weight, 0)
+        nn.init.constant_(self.decoder_normalize.adaLN_modulation[0].bias, 0)
+
+    # ---- C handle management --------------------------------------------------------------------
+    def _config_struct(self):
+        d = self.decoder_config
+        return _cabi.SeqdiffConfig(
+            hidden_size=d.hidden_size, num_attention_heads=d.num_attention_heads, intermediate_size=d.intermediate_size,
+            num_hidden_layers=d.num_hidden_layers, max_position_embeddings=d.max_position_embeddings,
+            feature_size=self.feature_size,
+            relative_key=int(getattr(d, "position_embedding_type", "absolute") == "relative_key"),
+            layer_norm_eps=float(getattr(d, "layer_norm_eps", 1e-12)))
+
+    def _precision_code(self):
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
+        return _cabi.BF16 if self.precision == "bf16" else _cabi.FP32
+
+    def _sync_handle(self):
+        """(Re)uploads the weights into the C handle when any tensor of the state_dict changed."""
+        lib = _cabi.lib()
+        sd = self.state_dict()
+        dev = next(iter(sd.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("the sequence denoiser runs only on a CUDA device (no CPU fallback): call model.to('cuda')")
+        sig = tuple((t.data_ptr(), t._version) for t in sd.values())
+        if self._handle is not None and sig == self._handle_sig and dev == self._handle_dev:
+            return self._handle
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            if self._handle is None or dev != self._handle_dev:
+                self.release()
+                h = ctypes.c_void_p()
+                cfg = self._config_struct()
+                _cabi.check(lib.seqdiff_model_create(ctypes.byref(cfg), dev.index or 0, ctypes.byref(h)))
+                self._handle, self._handle_dev = h, dev
+            keep = []
+            for name, t in sd.items():
+                t32 = t.detach()
+                if t32.dtype != torch.float32 or not t32.is_contiguous():
+                    t32 = t32.float().contiguous()
+                    keep.append(t32)
+                _cabi.check(lib.seqdiff_model_set_tensor(self._handle, name.encode(), _cabi.ptr(t32), t32.numel(), stream))
+            _cabi.check(lib.seqdiff_model_finalize(self._handle, stream))
+            torch.cuda.current_stream(dev).synchronize()
+        self._handle_sig = sig
+        return self._handle
+
+    def release(self):
+        if getattr(self, "_handle", None) is not None:
+            _cabi.lib().seqdiff_model_destroy(self._handle)
+            self._handle = None
+            self._handle_sig = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    # ---- forward --------------------------------------------------------------------------------
+    def forward(self, timestep, noised_ligand_seq, ligand_angle, ligand_attention_masks, receptor_seq, receptor_angle,
+                receptor_attention_masks, ligand_pos_ids=None, receptor_pos_ids=None):
+        """reference model.py:200-237.  pos ids are accepted and ignored, as in the reference."""
+        if self.training and (self.decoder_config.hidden_dropout_prob > 0 or self.decoder_config.attention_probs_dropout_prob > 0):
+            raise RuntimeError("the CUDA forward implements eval-mode (dropout-free) inference; call model.eval()")
+        h = self._sync_handle()
+        dev = self._handle_dev
+        B, Ll = noised_ligand_seq.shape[0], noised_ligand_seq.shape[1]
+        Lr = receptor_seq.shape[1]
+
+        def prep(x, shape):
+            x = x.to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(x.shape) != shape:
+                raise ValueError(f"expected shape {shape}, got {tuple(x.shape)}")
+            return x
+
+        t = timestep.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if t.numel() != B:
+            raise ValueError("timestep must hold one value per batch row")
+        x = prep(noised_ligand_seq, (B, Ll, 20))
+        la = prep(ligand_angle, (B, Ll, 8))
+        lm = prep(ligand_attention_masks, (B, Ll))
+        rs = prep(receptor_seq, (B, Lr, 20))
+        ra = prep(receptor_angle, (B, Lr, 8))
+        rm = prep(receptor_attention_masks, (B, Lr))
+        out = torch.empty((B, Ll, self.feature_size), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(_cabi.lib().seqdiff_forward(h, self._precision_code(), B, Ll, Lr, _cabi.ptr(t), _cabi.ptr(x), _cabi.ptr(la),
+                                                    _cabi.ptr(lm), _cabi.ptr(rs), _cabi.ptr(ra), _cabi.ptr(rm), _cabi.ptr(out), stream))
+        return out
+
+    def _create_pos_ids(self, sequences: torch.Tensor):
+        batch_size, seq_length, *_ = sequences.size()
+        return torch.arange(seq_length).expand(batch_size, -1)
+
+    def _exetend_attention_mask(self, mask):
+        extended = mask[:, None, None, :].type_as(mask)
+        return (1.0 - extended) * -10000.0
+
+
+class PeptideDiff(ConditionalBertForDiffusionBase):
+    """reference model.py:256-450 without the Lightning base class (Trainer is out of scope, SURVEY.md
+    section 2).  Inference-side members match the reference; `apply_aa_noise` runs the CUDA q-sample
+    kernel; `get_loss` evaluates the reference's loss terms on the CUDA forward's logits (no autograd:
+    backward kernels are not part of this round, so `training_step` raises)."""
+
+    def __init__(self, encoder_config, decoder_config, feature_names: List[str], loss_func, noise_schedule, timesteps,
+                 max_epochs: int = 1, lr_scheduler=None, l2_lambda: float = 0.0, steps_per_epoch: int = 250,
+                 learning_rate: float = 5e-5, **kwargs):
+        ConditionalBertForDiffusionBase.__init__(self, encoder_config, decoder_config, len(feature_names))
+        self.noise_schedule = noise_schedule
+        self.timesteps = timesteps
+        self.aa_transition_model = BlosumTransition(x_classes=20)
+        self.discrete_noise_schedule = PredefinedNoiseScheduleDiscrete(noise_schedule=self.noise_schedule, timesteps=self.timesteps)
+        self.loss_function = loss_func
+        self.lr = learning_rate
+        self.l2_lambda = l2_lambda
+        self.lr_scheduler = lr_scheduler
+        self.max_epochs = max_epochs
+        self.steps_per_epoch = steps_per_epoch
+        self.valid_epoch_losses = []
+        self.train_epoch_losses = []
+        self._noise_seed = 0
+        self._noise_calls = 0
+
+    def apply_aa_noise(self, ligand_seq, t_int, noise_E: Optional[torch.Tensor] = None):
+        """reference model.py:291-311.  Qbar_t comes from the host tables exactly as in the reference;
+        the per-residue categorical draw runs on the GPU (explicit Exp(1) `noise_E` [B*L,20] for parity
+        runs, counter-based Philox otherwise)."""
+        B, L, _ = ligand_seq.shape
+        dev = ligand_seq.device
+        if dev.type != "cuda":
+            raise RuntimeError("apply_aa_noise runs only on a CUDA device (no CPU fallback)")
+        t_float = t_int.cpu() / self.timesteps
+        alpha_t_bar = self.discrete_noise_schedule.get_alpha_bar(t_normalized=t_float)
+        Qtb = self.aa_transition_model.get_Qt_bar(alpha_t_bar, device=torch.device("cpu")).float().contiguous().to(dev)
+        x0 = ligand_seq.to(torch.float32).contiguous()
+        out = torch.empty_like(x0)
+        E = None if noise_E is None else noise_E.to(device=dev, dtype=torch.float32).contiguous()
+        self._noise_calls += 1
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(_cabi.lib().seqdiff_apply_aa_noise(_cabi.ptr(Qtb), B, L, _cabi.ptr(x0), _cabi.ptr(E), self._noise_seed, 0,
+                                                           self._noise_calls, _cabi.ptr(out), None, stream))
+        return out
+
+    @torch.no_grad()
+    def get_loss(self, batch, t_norm, noised_ligand_seq):
+        """reference model.py:313-345 (evaluation only)."""
+        ligand_mask = batch["ligand_attn_mask"].bool()
+        noised_mask = noised_ligand_seq.argmax(dim=-1) != batch["ligand_seq"].argmax(dim=-1)
+        pred_aa = self.forward(t_norm, noised_ligand_seq, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                               batch["receptor_angles"], batch["receptor_attn_mask"])
+        aa_noise_rate = noised_ligand_seq.argmax(dim=-1)[ligand_mask] == batch["ligand_seq"][ligand_mask].argmax(dim=-1)
+        aa_noise_rate = aa_noise_rate.sum() / ligand_mask.sum()
+        aa_recovery_rate = pred_aa.argmax(dim=-1)[ligand_mask] == batch["ligand_seq"][ligand_mask].argmax(dim=-1)
+        aa_recovery_rate = aa_recovery_rate.sum() / ligand_mask.sum()
+        aa_noised_loss = self.loss_function(pred_aa[noised_mask].view(-1, 20), batch["ligand_seq"][noised_mask].argmax(dim=-1).view(-1))
+        sel = ligand_mask & (~noised_mask)
+        aa_all_loss = self.loss_function(pred_aa[sel].view(-1, 20), batch["ligand_seq"][sel].argmax(dim=-1).view(-1))
+        elbo = elbo_loss(pred_aa[noised_mask], batch["ligand_seq"][noised_mask])
+        total_loss = aa_noised_loss + elbo
+        return total_loss, elbo, aa_noised_loss, aa_all_loss, aa_recovery_rate, aa_noise_rate
+
+    def validation_step(self, batch, batch_idx):
+        """reference model.py:381-404."""
+        t_int = torch.randint(0, self.timesteps + 1, size=(batch["ligand_seq"].shape[0], 1), device=batch["ligand_seq"].device).float()
+        t_norm = t_int / self.timesteps
+        aa = self.apply_aa_noise(batch["ligand_seq"], t_int)
+        loss, *_ = self.get_loss(batch, t_norm, aa)
+        return torch.mean(loss)
+
+    def training_step(self, batch, batch_idx):
+        raise NotImplementedError("training (backward kernels + NCCL gradient all-reduce) is not part of this round; "
+                                  "see DESIGN.md 'Out of scope / next'")
+
+    def configure_optimizers(self):
+        """reference model.py:416-450 (optimizer only; Lightning scheduler dicts are out of scope)."""
+        if self.lr_scheduler not in (None, "OneCycleLR", "LinearWarmup"):
+            raise ValueError(f"Unknown lr scheduler {self.lr_scheduler}")
+        return {"optimizer": torch.optim.AdamW(self.parameters(), lr=self.lr, weight_decay=self.l2_lambda)}

@@ -1,0 +1,160 @@
+"""Drop-in for `sequence_model/sample.py` of the reference: same module-level CONFIG vocabulary and
+the same free functions / signatures, with the arithmetic on the GPU:
+
+  * `sample_p_zs_given_zt_discrete`  -> one launch of the CUDA reverse-step kernel (instead of three
+    [N,20,20] temporaries plus a Python loop of N multinomial calls with a D2H sync each);
+  * `denoise`                        -> ONE C call (`seqdiff_sample`) that replays a captured CUDA graph
+    (denoiser forward + reverse step) T times; no host round trip inside the loop.
+
+Randomness.  The reference draws from torch's global CPU generator (`randint`, then `multinomial`
+= argmax(prob / Exp(1))).  Here x_T uses the same `torch.randint` call, and the per-step race noise is
+either handed in explicitly (`noise_E`, parity runs) or generated in-kernel by Philox4x32-10 keyed by
+(SEED, global graph id, residue, step) so results do not depend on how a batch is sharded over GPUs.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch.nn import functional as F
+
+from . import _cabi
+from .model import AA_VOCAB, BertConfig, PeptideDiff
+from .utils import BlosumTransition, DiscreteUniformTransition, PredefinedNoiseScheduleDiscrete, loop_tables, step_tables
+
+GPU_ID = 0
+DEVICE = torch.device(f"cuda:{GPU_ID}")
+THREAD_NUM = 16
+SEED = 0          # Philox key for the in-kernel sampling noise
+_CALLS = [0]      # stream offset: every stochastic call consumes one "step" id
+
+# same keys as the reference CONFIG (sample.py:28-50)
+CONFIG = {
+    "pocket_ext": 0,
+    "timesteps": 50,
+    "max_seq_len": 64,
+    "noise_schedule": "cosine",
+    "num_heads": 12,
+    "dropout_p": 0.1,
+    "hidden_size": 768,
+    "num_hidden_layers": 6,
+    "intermediate_size": 1024,
+    "position_embedding_type": "relative_key",
+    "lr": 5e-5,
+    "l2_norm": 0.1,
+    "loss": "smooth_l1",
+    "gradient_clip": 1.0,
+    "lr_scheduler": "LinearWarmup",
+    "min_epochs": 100,
+    "max_epochs": 150,
+    "batch_size": 64,
+}
+
+
+def get_model(steps_per_epoch=1, state_dict=None) -> PeptideDiff:
+    """reference sample.py:68-110; `state_dict` replaces torch.load(MODEL_PATH) (weights are unreachable)."""
+    common = dict(
+        max_position_embeddings=CONFIG["max_seq_len"], num_attention_heads=CONFIG["num_heads"], hidden_size=CONFIG["hidden_size"],
+        intermediate_size=CONFIG["intermediate_size"], num_hidden_layers=CONFIG["num_hidden_layers"],
+        position_embedding_type=CONFIG["position_embedding_type"], hidden_dropout_prob=CONFIG["dropout_p"],
+        attention_probs_dropout_prob=CONFIG["dropout_p"], use_cache=False)
+    encoder_config = BertConfig(**common)
+    decoder_config = BertConfig(**common, is_decoder=True, add_cross_attention=True)
+    model = PeptideDiff(encoder_config=encoder_config, decoder_config=decoder_config, feature_names=list(AA_VOCAB),
+                        max_epochs=CONFIG["max_epochs"], lr_scheduler=CONFIG["lr_scheduler"], l2_lambda=CONFIG["l2_norm"],
+                        steps_per_epoch=steps_per_epoch, learning_rate=CONFIG["lr"], loss_func=torch.nn.CrossEntropyLoss(),
+                        noise_schedule=CONFIG["noise_schedule"], timesteps=CONFIG["timesteps"])
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
+    return model.eval().to(DEVICE)
+
+
+def generate_discrete_noise(batch_size, length, num_classes=20):
+    """reference sample.py:112-116."""
+    random_indices = torch.randint(0, num_classes, (batch_size, length))
+    one_hot_matrix = torch.zeros(batch_size, length, num_classes)
+    one_hot_matrix[torch.arange(batch_size).unsqueeze(1), torch.arange(length), random_indices] = 1
+    return one_hot_matrix.to(DEVICE)
+
+
+def sample_p_zs_given_zt_discrete(t, s, noised_data, pred_noise, noise_schedule, transition, diverse, is_last_step,
+                                  noise_E=None, graph_id0=0):
+    """reference sample.py:141-179: sample zs ~ p(zs | zt).  Extra keyword `noise_E` [B*L,20] = the Exp(1)
+    race noise (what torch.multinomial draws internally) for same-noise parity runs."""
+    if is_last_step:
+        return pred_noise
+    batch_size, seq_len, num_class = noised_data.shape
+    if num_class != 20:
+        raise ValueError("the CUDA reverse step is specialised for 20 classes")
+    dev = pred_noise.device if pred_noise.device.type == "cuda" else DEVICE
+    tables = step_tables(t, s, noise_schedule, transition).to(dev)  # [B,3,20,20], host-built like sample.py:156-160
+    x = noised_data.to(device=dev, dtype=torch.float32).contiguous()
+    logits = pred_noise.to(device=dev, dtype=torch.float32).contiguous()
+    E = None if noise_E is None else noise_E.to(device=dev, dtype=torch.float32).contiguous()
+    out = torch.empty_like(x)
+    _CALLS[0] += 1
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(_cabi.lib().seqdiff_reverse_step(_cabi.ptr(tables), tables.shape[0], batch_size, seq_len, _cabi.ptr(x),
+                                                     _cabi.ptr(logits), int(bool(diverse)), _cabi.ptr(E), SEED, graph_id0,
+                                                     _CALLS[0] & 0x0FFFFFFF, _cabi.ptr(out), None, stream))
+    return out
+
+
+@torch.no_grad()
+def denoise_tensors(batch, model, noise_schedule, transition, diverse, timesteps=None, x_T=None, noise_E_steps=None,
+                    graph_id0=0, seed=None):
+    """The T-step loop of reference denoise() (sample.py:184-207) as one C call.  Returns the final
+    [B,L,20] tensor (raw logits of the last step, quirk Q4) on DEVICE."""
+    T = CONFIG["timesteps"] if timesteps is None else timesteps
+    dev = DEVICE
+    batch_size, max_len, num_class = batch["ligand_seq"].shape
+    if x_T is None:
+        x_T = generate_discrete_noise(batch_size, max_len, num_class)
+
+    def dv(x):
+        return x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+    x_T = dv(x_T)
+    ligand_mask, ligand_angles = dv(batch["ligand_attn_mask"]), dv(batch["ligand_angles"])
+    receptor_seq, receptor_angles = dv(batch["receptor_seq"]), dv(batch["receptor_angles"])
+    receptor_attn_mask = dv(batch["receptor_attn_mask"])
+    Lr = receptor_seq.shape[1]
+    tables = loop_tables(T, noise_schedule, transition)
+    if tables.shape[0] != T or tables.shape[1:] != (3, 20, 20):
+        raise ValueError("transition tables must be [T,3,20,20] (per-step scalar schedule)")
+    tables = tables.to(dev)
+    E = None if noise_E_steps is None else dv(noise_E_steps)
+    if E is not None and tuple(E.shape) != (T, batch_size * max_len, 20):
+        raise ValueError("noise_E_steps must be [T, B*L, 20]")
+    h = model._sync_handle()
+    out = torch.empty((batch_size, max_len, num_class), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(_cabi.lib().seqdiff_sample(h, model._precision_code(), batch_size, max_len, Lr, T, _cabi.ptr(tables), _cabi.ptr(x_T),
+                                               _cabi.ptr(ligand_angles), _cabi.ptr(ligand_mask), _cabi.ptr(receptor_seq),
+                                               _cabi.ptr(receptor_angles), _cabi.ptr(receptor_attn_mask), int(bool(diverse)),
+                                               _cabi.ptr(E), SEED if seed is None else seed, graph_id0, _cabi.ptr(out), stream))
+    return out
+
+
+@torch.no_grad()
+def denoise(batch, model: PeptideDiff, noise_schedule, transition, diverse, **kw):
+    """reference sample.py:181-229: returns (structure_ids, true_sequences, pred_sequences, recovery_rates)."""
+    batch_size = batch["ligand_seq"].shape[0]
+    final = denoise_tensors(batch, model, noise_schedule, transition, diverse, **kw)
+    # decode on the host from ONE device->host copy (the reference syncs once per graph)
+    pred_idx = final.argmax(dim=-1).cpu()
+    true_idx = batch["ligand_seq"].argmax(dim=-1).cpu()
+    masks = batch["ligand_attn_mask"].bool().cpu()
+    recovery_rates, pred_sequences, true_sequences, structure_ids = [], [], [], []
+    for i in range(batch_size):
+        mask = masks[i]
+        pred_seq, true_seq = pred_idx[i][mask], true_idx[i][mask]
+        recovery_rates.append(((pred_seq == true_seq).sum() / mask.sum()).item())
+        pred_sequences.append("".join(AA_VOCAB[j] for j in pred_seq))
+        true_sequences.append("".join(AA_VOCAB[j] for j in true_seq))
+        ids = batch.get("structure_ids")
+        structure_ids.append(f'{ids["pdb_id"][i]}_{ids["ligand_chain"][i]}' if ids is not None else str(i))
+    print(sum(recovery_rates) / len(recovery_rates))
+    return structure_ids, true_sequences, pred_sequences, recovery_rates

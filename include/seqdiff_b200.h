@@ -1,0 +1,129 @@
+/*
+ * seqdiff_b200.h -- C ABI of libseqdiff_b200.so: the B200 (sm_100a) implementation of ONE hot path of
+ * LabJunBMI/E3-invaraint-diffusion-model: the sequence_model denoiser forward and the discrete
+ * BLOSUM-transition reverse-diffusion step.
+ *
+ * The reference is pure Python/PyTorch and has no FFI layer; the boundary a
+ * maintainer binds is therefore "one entry point per reference function on the path".  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes stub that goes into the reference's model.py / sample.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - all tensors are dense, row-major, caller-owned; nothing is allocated for or freed on behalf of
+ *     the caller; a model handle owns its packed weights and its workspace;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     asynchronous on that stream and re-entrant per handle+stream pair;
+ *   - return value 0 = SEQDIFF_OK, otherwise an error code; seqdiff_last_error() returns the
+ *     thread-local message.  There is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns SEQDIFF_ERR_CUDA.
+ */
+#ifndef SEQDIFF_B200_H_
+#define SEQDIFF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SEQDIFF_API __attribute__((visibility("default")))
+#else
+#define SEQDIFF_API
+#endif
+
+#define SEQDIFF_ABI_VERSION 1
+
+#define SEQDIFF_OK 0
+#define SEQDIFF_ERR_INVALID 1   /* bad argument / unsupported shape            */
+#define SEQDIFF_ERR_CUDA 2      /* CUDA runtime / driver error                 */
+#define SEQDIFF_ERR_STATE 3     /* handle not finalised, unknown tensor name   */
+
+#define SEQDIFF_FP32 0 /* fp32 activations, fp32 SIMT GEMMs   (parity gate 1e-5)        */
+#define SEQDIFF_BF16 1 /* bf16 activations, tcgen05 GEMMs, fp32 accumulate/LN (1e-2)    */
+
+#define SEQDIFF_NUM_CLASSES 20
+#define SEQDIFF_ANGLE_FEATS 8
+
+typedef struct seqdiff_model seqdiff_model_t;
+
+/* The BertConfig fields the path consumes: sequence_model/sample.py:69-92. */
+typedef struct seqdiff_config {
+  int32_t hidden_size;         /* 768                                             */
+  int32_t num_attention_heads; /* 12 (head_dim must be 64)                        */
+  int32_t intermediate_size;   /* 1024                                            */
+  int32_t num_hidden_layers;   /* 6                                               */
+  int32_t max_position_embeddings; /* = max_seq_len; distance_embedding rows = 2P-1 */
+  int32_t feature_size;        /* 20                                              */
+  int32_t relative_key;        /* 1: position_embedding_type == "relative_key"    */
+  float layer_norm_eps;        /* 1e-12                                           */
+} seqdiff_config_t;
+
+SEQDIFF_API int seqdiff_abi_version(void);
+SEQDIFF_API const char* seqdiff_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
+SEQDIFF_API uint64_t seqdiff_launch_count(void);
+
+/* ---- model handle: replaces ConditionalBertForDiffusionBase.__init__ + load_state_dict ---------
+ * sequence_model/model.py:156-181, sample.py:106.  Tensor names are the reference state_dict keys
+ * (SURVEY.md Appendix B), e.g. "decoder.layer.0.attention.self.query.weight"; data is fp32. */
+SEQDIFF_API int seqdiff_model_create(const seqdiff_config_t* cfg, int device, seqdiff_model_t** out);
+SEQDIFF_API int seqdiff_model_destroy(seqdiff_model_t* m);
+SEQDIFF_API int seqdiff_model_set_tensor(seqdiff_model_t* m, const char* name, const float* data, int64_t numel, void* stream);
+/* packs fused QKV / cross-KV weights and the bf16 copies; must follow the last set_tensor */
+SEQDIFF_API int seqdiff_model_finalize(seqdiff_model_t* m, void* stream);
+
+/* ---- denoiser forward: replaces ConditionalBertForDiffusionBase.forward, model.py:200-237 --------
+ * timestep [B] f32; noised_ligand_seq [B,L_lig,20]; ligand_angle [B,L_lig,8]; ligand_mask [B,L_lig]
+ * ({0,1} floats); receptor_* likewise with L_rec; logits_out [B,L_lig,feature_size] f32. */
+SEQDIFF_API int seqdiff_forward(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, const float* timestep,
+                    const float* noised_ligand_seq, const float* ligand_angle, const float* ligand_mask,
+                    const float* receptor_seq, const float* receptor_angle, const float* receptor_mask,
+                    float* logits_out, void* stream);
+
+/* ---- reverse step: replaces sample_p_zs_given_zt_discrete (+ compute_batched_over0_posterior_
+ * distribution), sequence_model/sample.py:120-179, for is_last_step == False.
+ * q_tables [n_tab,3,20,20] f32 = (Qt, Qsb, Qtb) per graph (n_tab == B) or shared (n_tab == 1), built by
+ * the host with the caller's noise_schedule/transition objects exactly as sample.py:156-160 does.
+ * noise_E [B*L,20] = the Exp(1) race noise of torch.multinomial (parity mode) or NULL -> counter-based
+ * Philox4x32-10 keyed by (seed, graph_id0 + b, residue, step).  diverse == 0 -> argmax.
+ * x_s_out [B,L,20] one-hot f32 (may alias noised_data); idx_out [B*L] u8 or NULL. */
+SEQDIFF_API int seqdiff_reverse_step(const float* q_tables, int n_tab, int B, int L, const float* noised_data,
+                         const float* pred_logits, int diverse, const float* noise_E, uint64_t seed,
+                         uint64_t graph_id0, uint32_t step, float* x_s_out, uint8_t* idx_out, void* stream);
+
+/* ---- training q-sample: replaces PeptideDiff.apply_aa_noise, model.py:291-311 --------------------
+ * qtb [B,20,20] f32 = get_Qt_bar(alpha_bar(t_int/T)); rows of x0 that are all-zero (padding) -> class 0. */
+SEQDIFF_API int seqdiff_apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float* noise_E, uint64_t seed,
+                           uint64_t graph_id0, uint32_t step, float* x_t_out, uint8_t* idx_out, void* stream);
+
+/* ---- whole reverse-diffusion loop: replaces the T-step loop of denoise(), sample.py:192-207 -------
+ * q_tables_steps [T,3,20,20]: entry s holds (Qt,Qsb,Qtb) for the step s_int = s (t=(s+1)/T).
+ * x_T [B,L_lig,20] one-hot start.  noise_E_steps [T,B*L_lig,20] (entry s used at step s; entry 0 unused)
+ * or NULL -> Philox.  One step = forward + reverse step, replayed from a captured CUDA graph.
+ * final_out [B,L_lig,20]: raw logits of the last step (quirk: sample.py:147-148). */
+SEQDIFF_API int seqdiff_sample(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, int T,
+                   const float* q_tables_steps, const float* x_T, const float* ligand_angle,
+                   const float* ligand_mask, const float* receptor_seq, const float* receptor_angle,
+                   const float* receptor_mask, int diverse, const float* noise_E_steps, uint64_t seed,
+                   uint64_t graph_id0, float* final_out, void* stream);
+
+/* ---- operator-level entry points (used by the parity tests and the micro benchmarks) --------------
+ * C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias[N] (+ resid[M,N])); epilogue: 0 none, 1 erf-GELU, 2 SiLU.
+ * precision BF16: A,W,resid,C are bf16 (tcgen05 + TMA kernel); FP32: all f32 (SIMT kernel). */
+SEQDIFF_API int seqdiff_op_gemm(int precision, int M, int N, int K, const void* A, const void* W, const float* bias,
+                    const void* resid, int epilogue, void* C, void* stream);
+/* multi-head attention core of HF BertSelfAttention (4.38.2 relative_key semantics):
+ * q [B,Lq,*] k,v [B,Lk,*] with row strides (elements) ldq/ldk/ldv, heads x 64; dist_emb [2P-1,64] or NULL;
+ * key_mask [B,Lk] {0,1} -> additive (1-m)*-10000; out [B,Lq,heads*64].  Element type by precision. */
+SEQDIFF_API int seqdiff_op_attention(int precision, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k,
+                         int ldk, const void* v, int ldv, const void* dist_emb, int P, const float* key_mask,
+                         void* out, void* stream);
+/* Philox4x32-10 stream the sampler uses: out[n*20+j] = raw u32 for (seed, graph, residue, step, class) */
+SEQDIFF_API int seqdiff_op_philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQDIFF_B200_H_ */

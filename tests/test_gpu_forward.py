@@ -1,0 +1,167 @@
+"""GPU parity tests of the denoiser forward and of the full reverse-diffusion loop against the oracle and
+the golden vectors produced from the reference (tolerances from BASELINE.json north_star:
+1e-5 relative in fp32 mode, 1e-2 relative in bf16 mode; 'relative' = max|diff| / max|reference|)."""
+import glob
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import GOLDEN, O, assert_indices_match, make_model, rel_err, sd_pkg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = {"fp32": 1e-5, "bf16": 1e-2}
+
+_MODELS = {}
+
+
+def _model(L, rel, wseed, variant, precision):
+    """weights are regenerated from the seed on both sides (never stored)."""
+    key = (L, rel, wseed, variant)
+    if key not in _MODELS:
+        _MODELS.clear()  # one 290 MB fp32 state at a time
+        cfg = O.OracleConfig(max_position_embeddings=L, relative_key=rel)
+        state = O.init_state_dict(cfg, wseed, variant)
+        _MODELS[key] = (cfg, state, make_model(sd_pkg(), cfg, state, precision))
+    cfg, state, m = _MODELS[key]
+    m.precision = precision
+    return cfg, state, m
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "forward_*.pt"))), ids=os.path.basename)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_golden(path, precision):
+    g = torch.load(path, weights_only=False)
+    cfg, state, m = _model(g["L"], g["relative_key"], g["weight_seed"], g["variant"], precision)
+    batch = O.synthetic_batch(g["B"], g["L"], g["n_lig"], g["n_rec"], g["input_seed"])
+    x_t = F.one_hot(g["x_t_idx"].long(), 20).float()
+    t = torch.full((g["B"], 1), g["timestep"])
+    with torch.no_grad():
+        y = m(t.to(DEV), x_t.to(DEV), batch["ligand_angles"].to(DEV), batch["ligand_attn_mask"].to(DEV), batch["receptor_seq"].to(DEV),
+              batch["receptor_angles"].to(DEV), batch["receptor_attn_mask"].to(DEV))
+    assert y.shape == g["logits"].shape and y.dtype == torch.float32 and torch.isfinite(y).all()
+    err = rel_err(y, g["logits"])
+    print(f"{os.path.basename(path)} {precision}: rel err {err:.3e}")
+    assert err < TOL[precision], err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_intermediate_shapes_and_lengths(precision):
+    """different ligand / receptor padded lengths, batch of ragged graphs, large timestep (sin/cos of ~7e4 rad)."""
+    cfg, state, m = _model(128, True, 1, "B", precision)
+    B, Ll, Lr = 5, 48, 112
+    g = torch.Generator().manual_seed(9)
+    lig = O.synthetic_batch(B, Ll, (1, 48), (1, 48), 31)
+    rec = O.synthetic_batch(B, Lr, (1, 112), (16, 112), 32)
+    x_t = O.generate_discrete_noise(B, Ll, generator=g)
+    t = torch.tensor([[499.0], [0.0], [250.0], [3.0], [0.25]])
+    args = (t, x_t, lig["ligand_angles"], lig["ligand_attn_mask"], rec["receptor_seq"], rec["receptor_angles"], rec["receptor_attn_mask"])
+    with torch.no_grad():
+        want = O.denoiser_forward(state, cfg, *args)
+        got = m(*[a.to(DEV) for a in args])
+    err = rel_err(got, want)
+    print(f"ragged Ll={Ll} Lr={Lr} {precision}: rel err {err:.3e}")
+    assert err < TOL[precision], err
+
+
+def test_forward_cfg2_shape_bf16_vs_fp32_modes():
+    """BASELINE cfg 2 batch (B=64, L=128, 16384 tokens): the bf16 product path against this library's own
+    fp32 mode (itself pinned to the oracle above) -- the oracle would need ~3 s of CPU per forward."""
+    cfg, state, m = _model(128, True, 1, "B", "fp32")
+    batch = O.synthetic_batch(64, 128, (5, 64), (16, 128), 3)
+    x_t = O.generate_discrete_noise(64, 128, generator=torch.Generator().manual_seed(4))
+    t = torch.full((64, 1), 123.0)
+    args = [a.to(DEV) for a in (t, x_t, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                                batch["receptor_angles"], batch["receptor_attn_mask"])]
+    with torch.no_grad():
+        m.precision = "fp32"
+        y32 = m(*args)
+        m.precision = "bf16"
+        y16 = m(*args)
+        y16b = m(*args)
+    assert torch.equal(y16, y16b)  # deterministic: no atomics anywhere on the path
+    err = rel_err(y16, y32)
+    print(f"cfg2 bf16 vs fp32-mode: rel err {err:.3e}")
+    assert err < 1e-2
+    # spot-check 2 graphs of the big batch against the oracle (batch rows are independent)
+    with torch.no_grad():
+        want = O.denoiser_forward(state, cfg, *[a[:2].cpu() for a in args])
+    assert rel_err(y32[:2], want) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_denoise_loop_golden(precision):
+    """The reference's denoise() end to end (T=4): same x_T, same race noise -> same decoded sequences.
+    fp32 mode must reproduce the reference strings; the loop (CUDA graph replay, in-place x_t update,
+    last-step logits) is checked step by step against the oracle by teacher forcing."""
+    sd = sd_pkg()
+    g = torch.load(os.path.join(GOLDEN, "denoise_T4.pt"), weights_only=False)
+    T, B, L = g["T"], g["B"], g["L"]
+    cfg, state, m = _model(L, True, g["weight_seed"], g["variant"], precision)
+    batch = O.synthetic_batch(B, L, g["n_lig"], g["n_rec"], g["batch_seed"])
+    batch["structure_ids"] = {"pdb_id": ["xxxx"] * B, "ligand_chain": ["A"] * B}
+    x_T = F.one_hot(g["x_T_idx"].long(), 20).float()
+    E = torch.ones(T, B * L, 20)
+    for i, s in enumerate(g["E_steps"]):
+        E[s] = g["E"][i]
+    sd.sample.DEVICE = torch.device(DEV)
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    ids, true_seq, pred_seq, rates = sd.denoise(batch, m, sched, tr, True, timesteps=T, x_T=x_T, noise_E_steps=E)
+    assert true_seq == g["true_sequences"] and ids == ["xxxx_A"] * B
+    final = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T, noise_E_steps=E)
+    if precision == "fp32":
+        assert pred_seq == g["pred_sequences"]
+        assert rel_err(final, g["final_logits"]) < 1e-4  # 4 chained steps; any index flip would show as O(1)
+    else:
+        # bf16 logits move the posterior slightly, so trajectories may legitimately fork; teacher-force instead
+        x = x_T.clone()
+        o_s, o_t = O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition()
+        for s_int in reversed(range(1, T)):
+            s = s_int * torch.ones((B, 1))
+            with torch.no_grad():
+                lg = m(s.to(DEV), x.to(DEV), batch["ligand_angles"].to(DEV), batch["ligand_attn_mask"].to(DEV),
+                       batch["receptor_seq"].to(DEV), batch["receptor_angles"].to(DEV), batch["receptor_attn_mask"].to(DEV))
+                want_lg = O.denoiser_forward(state, cfg, s, x, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                                             batch["receptor_angles"], batch["receptor_attn_mask"])
+            assert rel_err(lg, want_lg) < 1e-2
+            # same logits on both sides -> indices must agree exactly (up to near-ties)
+            got = sd.sample_p_zs_given_zt_discrete((s + 1) / T, s / T, x.to(DEV), lg, sched, tr, True, False, noise_E=E[s_int])
+            want = O.reverse_step((s + 1) / T, s / T, x, lg.cpu(), o_s, o_t, True, False, E[s_int])
+            prob = O.reverse_step_probs((s + 1) / T, s / T, x, lg.cpu(), o_s, o_t)
+            assert_indices_match(got.argmax(-1), want.argmax(-1), prob / E[s_int], f"step {s_int}")
+            x = want
+
+
+def test_sample_loop_equals_stepwise_calls():
+    """seqdiff_sample (graph replay, device-side step counter) == the same steps issued one by one through
+    forward() + sample_p_zs_given_zt_discrete(), bit for bit, in the product precision; also Philox mode is
+    invariant to how the batch is sharded (graph ids, not batch positions, key the noise)."""
+    sd = sd_pkg()
+    T, B, L = 6, 4, 64
+    cfg, state, m = _model(64, True, 1, "B", "bf16")
+    sd.sample.DEVICE = torch.device(DEV)
+    batch = O.synthetic_batch(B, L, (5, 40), (16, 64), 77)
+    g = torch.Generator().manual_seed(5)
+    x_T = O.generate_discrete_noise(B, L, generator=g)
+    E = torch.empty(T, B * L, 20).exponential_(1, generator=g)
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    final = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T, noise_E_steps=E)
+    x = x_T.to(DEV)
+    dv = {k: v.to(DEV) for k, v in batch.items()}
+    for s_int in reversed(range(T)):
+        s = s_int * torch.ones((B, 1))
+        with torch.no_grad():
+            lg = m(s.to(DEV), x, dv["ligand_angles"], dv["ligand_attn_mask"], dv["receptor_seq"], dv["receptor_angles"], dv["receptor_attn_mask"])
+        x = sd.sample_p_zs_given_zt_discrete((s + 1) / T, s / T, x, lg, sched, tr, True, s_int == 0, noise_E=E[s_int])
+    assert torch.equal(final, x)
+    # Philox mode: whole batch vs two shards of two graphs
+    full = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T, seed=42, graph_id0=10)
+    parts = []
+    for lo in (0, 2):
+        sub = {k: v[lo:lo + 2] for k, v in batch.items()}
+        parts.append(sd.denoise_tensors(sub, m, sched, tr, True, timesteps=T, x_T=x_T[lo:lo + 2], seed=42, graph_id0=10 + lo))
+    assert torch.equal(full, torch.cat(parts, 0))
+    other = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T, seed=43, graph_id0=10)
+    assert not torch.equal(full, other)
