@@ -8,7 +8,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libseqdiff_b200.so")
 
-FP32, BF16 = 0, 1
+FP32, BF16, FP16 = 0, 1, 2
+PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
 
 
 class SeqdiffConfig(C.Structure):

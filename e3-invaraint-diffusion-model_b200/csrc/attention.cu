@@ -6,7 +6,7 @@
 //
 // E = distance_embedding [2P-1, 64], shared by all heads; cross-attention has no E term.
 //
-// bf16 kernel: one CTA per (query block of BQ rows, head, graph); each warp owns 16 query rows and runs
+// 16-bit kernel (bf16 or fp16 operands): one CTA per (query block of BQ rows, head, graph); each warp owns 16 query rows and runs
 // m16n8k16 bf16 tensor-core MMAs with fp32 accumulation, flash-style online softmax over 128-key blocks.
 // The relative term is a second MMA, QE = Q . Ewin^T, against the (BQ+128)-row window of E that this
 // (query block, key block) pair can touch; warp w only needs window rows [16w, 16w+144).  QE is staged
@@ -32,9 +32,16 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r
 __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+template <typename T> __device__ __forceinline__ void mma_16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma_16<bf16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma_16<f16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -56,11 +63,11 @@ template <bool REL, int BQ> struct AttnSmem {
   static constexpr int kBytes = kMask + kKB * 4;
 };
 
-template <bool REL, int BQ>
-__global__ void __launch_bounds__(BQ * 2) attention_bf16_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k, int ldk,
-                                                                const bf16* __restrict__ v, int ldv, const bf16* __restrict__ E, int P,
-                                                                const float* __restrict__ key_mask, bf16* __restrict__ out, int heads,
-                                                                int Lq, int Lk) {
+template <typename T, bool REL, int BQ>
+__global__ void __launch_bounds__(BQ * 2) attention_16_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk,
+                                                              const T* __restrict__ v, int ldv, const T* __restrict__ E, int P,
+                                                              const float* __restrict__ key_mask, T* __restrict__ out, int heads,
+                                                              int Lq, int Lk) {
   using SM = AttnSmem<REL, BQ>;
   constexpr int NT = BQ * 2;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -70,9 +77,9 @@ __global__ void __launch_bounds__(BQ * 2) attention_bf16_kernel(const bf16* __re
   const int g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
 
-  const bf16* qb = q + (static_cast<size_t>(b) * Lq) * ldq + h * 64;
-  const bf16* kb_ = k + (static_cast<size_t>(b) * Lk) * ldk + h * 64;
-  const bf16* vb = v + (static_cast<size_t>(b) * Lk) * ldv + h * 64;
+  const T* qb = q + (static_cast<size_t>(b) * Lq) * ldq + h * 64;
+  const T* kb_ = k + (static_cast<size_t>(b) * Lk) * ldk + h * 64;
+  const T* vb = v + (static_cast<size_t>(b) * Lk) * ldv + h * 64;
 
   // ---- Q tile (once) ----
   for (int i = tid; i < BQ * 8; i += NT) {
@@ -134,8 +141,8 @@ __global__ void __launch_bounds__(BQ * 2) attention_bf16_kernel(const bf16* __re
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t b0, b1, b2, b3;
         ldsm_x4(sbase + SM::kK + swz(np * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
-        mma_bf16(s[2 * np], qa[ks], b0, b1);
-        mma_bf16(s[2 * np + 1], qa[ks], b2, b3);
+        mma_16<T>(s[2 * np], qa[ks], b0, b1);
+        mma_16<T>(s[2 * np + 1], qa[ks], b2, b3);
       }
     }
 
@@ -149,8 +156,8 @@ __global__ void __launch_bounds__(BQ * 2) attention_bf16_kernel(const bf16* __re
         for (int ks = 0; ks < 4; ++ks) {
           uint32_t b0, b1, b2, b3;
           ldsm_x4(sbase + SM::kE + swz(warp * 16 + c * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
-          mma_bf16(e0, qa[ks], b0, b1);
-          mma_bf16(e1, qa[ks], b2, b3);
+          mma_16<T>(e0, qa[ks], b0, b1);
+          mma_16<T>(e1, qa[ks], b2, b3);
         }
         const int col = c * 16 + 2 * t;
         *reinterpret_cast<float2*>(st + g * kQEPitch + col) = make_float2(e0[0], e0[1]);
@@ -201,8 +208,8 @@ __global__ void __launch_bounds__(BQ * 2) attention_bf16_kernel(const bf16* __re
       const float p2 = __expf(s[n][2] - m_run[1]), p3 = __expf(s[n][3] - m_run[1]);
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
-      pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      pa[n >> 1][(n & 1) * 2 + 0] = pack2<T>(p0, p1);
+      pa[n >> 1][(n & 1) * 2 + 1] = pack2<T>(p2, p3);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -222,8 +229,8 @@ __global__ void __launch_bounds__(BQ * 2) attention_bf16_kernel(const bf16* __re
       for (int dp = 0; dp < 4; ++dp) {
         uint32_t b0, b1, b2, b3;
         ldsm_x4_t(sbase + SM::kV + swz(kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp * 2 + (lane >> 4)), b0, b1, b2, b3);
-        mma_bf16(o[2 * dp], pa[kk], b0, b1);
-        mma_bf16(o[2 * dp + 1], pa[kk], b2, b3);
+        mma_16<T>(o[2 * dp], pa[kk], b0, b1);
+        mma_16<T>(o[2 * dp + 1], pa[kk], b2, b3);
       }
     }
   }
@@ -235,16 +242,16 @@ __global__ void __launch_bounds__(BQ * 2) attention_bf16_kernel(const bf16* __re
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int col = h * 64 + n * 8 + 2 * t;
-    if (r0 < Lq) *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * Lq + r0) * H + col) = pack_bf16x2(o[n][0] * inv0, o[n][1] * inv0);
-    if (r1 < Lq) *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * Lq + r1) * H + col) = pack_bf16x2(o[n][2] * inv1, o[n][3] * inv1);
+    if (r0 < Lq) *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * Lq + r0) * H + col) = pack2<T>(o[n][0] * inv0, o[n][1] * inv0);
+    if (r1 < Lq) *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * Lq + r1) * H + col) = pack2<T>(o[n][2] * inv1, o[n][3] * inv1);
   }
 }
 
-template <bool REL, int BQ>
-static int launch_attn_bf16(int B, int heads, int Lq, int Lk, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv,
-                            const bf16* E, int P, const float* mask, bf16* out, cudaStream_t s) {
+template <typename T, bool REL, int BQ>
+static int launch_attn_16(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* E,
+                          int P, const float* mask, T* out, cudaStream_t s) {
   using SM = AttnSmem<REL, BQ>;
-  auto kfn = attention_bf16_kernel<REL, BQ>;
+  auto kfn = attention_16_kernel<T, REL, BQ>;
   static bool configured = false;
   if (!configured) {
     SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
@@ -256,19 +263,29 @@ static int launch_attn_bf16(int B, int heads, int Lq, int Lk, const bf16* q, int
   return SEQDIFF_OK;
 }
 
-template <>
-int attention<bf16>(int B, int heads, int Lq, int Lk, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv,
-                    const bf16* dist_emb, int P, const float* key_mask, bf16* out, cudaStream_t s) {
+template <typename T>
+static int attention_16(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv,
+                        const T* dist_emb, int P, const float* key_mask, T* out, cudaStream_t s) {
   SD_CHECK(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "empty attention");
   SD_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "row strides must be multiples of 8 elements");
   SD_CHECK(!dist_emb || (Lq <= P && Lk <= P), "sequence longer than max_position_embeddings");
   const bool small = Lq <= 64;
   if (dist_emb) {
-    return small ? launch_attn_bf16<true, 64>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s)
-                 : launch_attn_bf16<true, 128>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+    return small ? launch_attn_16<T, true, 64>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s)
+                 : launch_attn_16<T, true, 128>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
   }
-  return small ? launch_attn_bf16<false, 64>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s)
-               : launch_attn_bf16<false, 128>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  return small ? launch_attn_16<T, false, 64>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s)
+               : launch_attn_16<T, false, 128>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+}
+template <>
+int attention<bf16>(int B, int heads, int Lq, int Lk, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv,
+                    const bf16* dist_emb, int P, const float* key_mask, bf16* out, cudaStream_t s) {
+  return attention_16<bf16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+}
+template <>
+int attention<f16>(int B, int heads, int Lq, int Lk, const f16* q, int ldq, const f16* k, int ldk, const f16* v, int ldv,
+                   const f16* dist_emb, int P, const float* key_mask, f16* out, cudaStream_t s) {
+  return attention_16<f16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
 }
 
 // ---------------------------------------------------------------------------------------------------

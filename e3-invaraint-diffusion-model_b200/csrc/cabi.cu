@@ -122,14 +122,16 @@ int seqdiff_op_gemm(int precision, int M, int N, int K, const void* A, const voi
   SD_GUARD_BEGIN
   SD_CHECK(A && W && bias && C, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (precision == SEQDIFF_FP32)
+  // bits 8.. of `precision` may force the tile width (tests): precision = mode | (bn << 8)
+  const int force_bn = precision >> 8;
+  const int mode = precision & 0xff;
+  if (mode == SEQDIFF_FP32)
     return gemm_f32(M, N, K, static_cast<const float*>(A), static_cast<const float*>(W), bias, static_cast<const float*>(resid),
                     epilogue, static_cast<float*>(C), s);
-  // bit 8.. of `precision` may force the tile width (tests): precision = SEQDIFF_BF16 | (bn << 8)
-  const int force_bn = precision >> 8;
-  SD_CHECK((precision & 0xff) == SEQDIFF_BF16, "bad precision");
-  return gemm_bf16(M, N, K, static_cast<const bf16*>(A), static_cast<const bf16*>(W), bias, static_cast<const bf16*>(resid), epilogue,
-                   static_cast<bf16*>(C), s, force_bn);
+  SD_CHECK(mode == SEQDIFF_BF16 || mode == SEQDIFF_FP16, "bad precision");
+  const int a_fmt = mode == SEQDIFF_FP16 ? 0 : 1;
+  const int w_fmt = a_fmt;
+  return gemm_16(M, N, K, A, a_fmt, W, w_fmt, bias, static_cast<const float*>(resid), epilogue, C, resid ? 2 : a_fmt, s, force_bn);
   SD_GUARD_END
 }
 
@@ -142,6 +144,9 @@ int seqdiff_op_attention(int precision, int B, int heads, int Lq, int Lk, const 
     return attention<float>(B, heads, Lq, Lk, static_cast<const float*>(q), ldq, static_cast<const float*>(k), ldk,
                             static_cast<const float*>(v), ldv, static_cast<const float*>(dist_emb), P, key_mask,
                             static_cast<float*>(out), s);
+  if (precision == SEQDIFF_FP16)
+    return attention<f16>(B, heads, Lq, Lk, static_cast<const f16*>(q), ldq, static_cast<const f16*>(k), ldk,
+                          static_cast<const f16*>(v), ldv, static_cast<const f16*>(dist_emb), P, key_mask, static_cast<f16*>(out), s);
   SD_CHECK(precision == SEQDIFF_BF16, "bad precision");
   return attention<bf16>(B, heads, Lq, Lk, static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk,
                          static_cast<const bf16*>(v), ldv, static_cast<const bf16*>(dist_emb), P, key_mask, static_cast<bf16*>(out), s);

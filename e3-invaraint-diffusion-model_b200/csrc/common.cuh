@@ -51,14 +51,19 @@ extern std::atomic<uint64_t> g_launches;
   } while (0)
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
 
 // ---- element conversion --------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<f16>(f16 v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+// fp16 conversions saturate to +-65504 instead of producing inf (the fp16 mode's only range hazard)
+__device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+template <> __device__ __forceinline__ f16 from_f32<f16>(float v) { return __float2half_rn(sat_f16(v)); }
 
 // 8 consecutive elements <-> 8 floats (16B for bf16, 32B for f32); pointers must be 16B aligned
 template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
@@ -79,6 +84,24 @@ template <> __device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// two floats -> one 32-bit word of the 16-bit operand type T
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<bf16>(float lo, float hi) { return pack_bf16x2(lo, hi); }
+template <> __device__ __forceinline__ uint32_t pack2<f16>(float lo, float hi) { return pack_f16x2(lo, hi); }
+template <> __device__ __forceinline__ void load8<f16>(const f16* p, float (&v)[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
 }
 template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
 template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
@@ -101,6 +124,13 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+template <> __device__ __forceinline__ void store8<f16>(f16* p, const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_f16x2(v[0], v[1]); r.y = pack_f16x2(v[2], v[3]);
+  r.z = pack_f16x2(v[4], v[5]); r.w = pack_f16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = r;
 }
 
 // exact-erf GELU (nn.GELU() / HF "gelu": model.py:43,133) and SiLU
@@ -216,9 +246,10 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
   return d;
 }
-// instruction descriptor, kind::f16: bf16 x bf16 -> f32, both operands K-major
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+// instruction descriptor, kind::f16: {f16|bf16} x {f16|bf16} -> f32, both operands K-major.
+// a_fmt / b_fmt: 0 = F16, 1 = BF16 (cute::UMMA::F16F32Format)
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ---- misc -------------------------------------------------------------------------------------------

@@ -11,8 +11,11 @@
 //   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> f32 in TMEM);
 //                                owns the TMEM allocation (2 accumulator stages = 2*BN columns)
 //   warps 2..9  epilogue       : tcgen05.ld the finished accumulator (lane quarter = warp%4, column half =
-//                                (warp-2)/4), fused bias / erf-GELU / SiLU / residual add, bf16 stores --
-//                                overlapped with the MMA mainloop of the next tile (double-buffered TMEM).
+//                                (warp-2)/4), fused bias / erf-GELU / SiLU / fp32 residual add, 16-bit or fp32
+//                                stores -- overlapped with the MMA mainloop of the next tile (double-buffered TMEM).
+// Operands are 16-bit (bf16 or fp16, selected through the instruction descriptor; both operands of one MMA
+// must share the format); GEMMs that feed a LayerNorm write fp32 and take an fp32 residual, so the residual stream of the
+// network never passes through a 16-bit rounding.
 // fp32 path (parity gate 1e-5): plain SIMT tiled kernel, fp32 FMA accumulation.
 #include <mutex>
 #include <unordered_map>
@@ -44,22 +47,26 @@ static PFN_encodeTiled get_encode_fn() {
 
 struct TmapKey {
   const void* ptr;
-  int rows, cols, box_rows;
-  bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+  int rows, cols, box_rows, fmt;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && fmt == o.fmt;
+  }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
-    h ^= (static_cast<size_t>(k.rows) * 0x9E3779B97F4A7C15ull) ^ (static_cast<size_t>(k.cols) << 20) ^ (static_cast<size_t>(k.box_rows) << 44);
+    h ^= (static_cast<size_t>(k.rows) * 0x9E3779B97F4A7C15ull) ^ (static_cast<size_t>(k.cols) << 20) ^ (static_cast<size_t>(k.box_rows) << 44) ^
+         (static_cast<size_t>(k.fmt) << 60);
     return h;
   }
 };
 
-// row-major bf16 matrix [rows, cols]; tile = box_rows x 64 columns, 128B-swizzled, OOB reads give zeros
-static int make_tmap(const bf16* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
+// row-major 16-bit matrix [rows, cols] (fmt 0 = fp16, 1 = bf16); tile = box_rows x 64 columns, 128B-swizzled,
+// OOB reads give zeros
+static int make_tmap(const void* ptr, int fmt, int rows, int cols, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{ptr, rows, cols, box_rows};
+  TmapKey key{ptr, rows, cols, box_rows, fmt};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -75,10 +82,11 @@ static int make_tmap(const bf16* ptr, int rows, int cols, int box_rows, CUtensor
   }
   SD_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (cols % 8) == 0, "TMA operand must be 16B aligned with a 16B-multiple row pitch");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * sizeof(bf16)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
   cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
+  CUresult r = enc(out, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim,
+                   gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -107,10 +115,12 @@ template <int BN> struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, bool RESID>
+// TOut: bf16 / f16 (operand for the next GEMM or attention) or float (LayerNorm input); resid is always fp32.
+template <int BN, int EPI, bool RESID, typename TOut>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const float* __restrict__ bias, const bf16* __restrict__ resid, bf16* __restrict__ C, int M, int N, int K) {
+                    const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
+                    uint32_t idesc) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -172,7 +182,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -240,19 +249,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float rr[8];
-              load8<bf16>(resid + off + j, rr);
+              load8<float>(resid + off + j, rr);
 #pragma unroll
               for (int t = 0; t < 8; ++t) v[j + t] += rr[t];
             }
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(v[j], v[j + 1]);
-            o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-            o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(C + off + j) = o;
+            const float o8[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
+            store8<TOut>(C + off + j, o8);
           }
         }
       }
@@ -271,11 +276,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int EPI, bool RESID>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const bf16* resid, bf16* C, int M, int N,
-                     int K, cudaStream_t s) {
+template <int BN, int EPI, bool RESID, typename TOut>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, void* C, int M, int N, int K,
+                     uint32_t idesc, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
-  auto kfn = gemm_tcgen05_kernel<BN, EPI, RESID>;
+  auto kfn = gemm_tcgen05_kernel<BN, EPI, RESID, TOut>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -283,7 +288,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* 
   }
   const int tiles = ceil_div(M, kBM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, bias, resid, C, M, N, K);
+  kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K, idesc);
   SD_LAUNCH_CHECK();
   return SEQDIFF_OK;
 }
@@ -303,30 +308,42 @@ static int pick_bn(int M, int N) {
   return (waves_eff(256) + 0.08 >= waves_eff(128)) ? 256 : 128;
 }
 
-int gemm_bf16(int M, int N, int K, const bf16* A, const bf16* W, const float* bias, const bf16* resid, int epi, bf16* C,
-              cudaStream_t s, int force_bn) {
+template <int BN>
+static int dispatch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, int epi, void* C,
+                       int out_kind, int M, int N, int K, uint32_t idesc, cudaStream_t s) {
+  if (resid) return launch_tc<BN, 0, true, float>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (out_kind == 2) return launch_tc<BN, 0, false, float>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (out_kind == 1) {
+    if (epi == 0) return launch_tc<BN, 0, false, bf16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    if (epi == 1) return launch_tc<BN, 1, false, bf16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    return launch_tc<BN, 2, false, bf16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  }
+  if (epi == 0) return launch_tc<BN, 0, false, f16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (epi == 1) return launch_tc<BN, 1, false, f16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  return launch_tc<BN, 2, false, f16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+}
+
+// a_fmt / w_fmt: 0 = fp16, 1 = bf16.  out_kind: 0 = fp16, 1 = bf16, 2 = fp32 (identity epilogue only; implied by resid).
+int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
+            void* C, int out_kind, cudaStream_t s, int force_bn) {
   SD_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
   SD_CHECK(N % 128 == 0, "tcgen05 GEMM needs N % 128 == 0");
   SD_CHECK(K % 8 == 0, "tcgen05 GEMM needs K % 8 == 0 (16B TMA pitch)");
-  SD_CHECK(!(resid && epi != 0), "residual add is only fused with the identity epilogue");
+  SD_CHECK(epi >= 0 && epi <= 2, "unknown GEMM epilogue");
+  SD_CHECK(!((resid || out_kind == 2) && epi != 0), "fp32 output / residual add only with the identity epilogue");
+  SD_CHECK(!(resid && out_kind != 2), "a residual GEMM writes fp32");
   SD_CHECK(bias != nullptr, "bias required");
+  SD_CHECK((a_fmt | 1) == 1 && out_kind >= 0 && out_kind <= 2, "bad operand format");
+  // measured on B200: tcgen05.mma.kind::f16 with a_format != b_format faults as an illegal instruction
+  SD_CHECK(a_fmt == w_fmt, "A and W must share one 16-bit format");
   const int bn = force_bn ? force_bn : pick_bn(M, N);
   SD_CHECK(bn == 128 || (bn == 256 && N % 256 == 0), "bad tile width");
   CUtensorMap ta, tb;
-  SD_TRY(make_tmap(A, M, K, kBM, &ta));
-  SD_TRY(make_tmap(W, N, K, bn, &tb));
-#define SD_TC(BN_)                                                                                        \
-  do {                                                                                                    \
-    if (resid) return launch_tc<BN_, 0, true>(ta, tb, bias, resid, C, M, N, K, s);                       \
-    if (epi == 0) return launch_tc<BN_, 0, false>(ta, tb, bias, resid, C, M, N, K, s);                   \
-    if (epi == 1) return launch_tc<BN_, 1, false>(ta, tb, bias, resid, C, M, N, K, s);                   \
-    if (epi == 2) return launch_tc<BN_, 2, false>(ta, tb, bias, resid, C, M, N, K, s);                   \
-  } while (0)
-  if (bn == 256) SD_TC(256);
-  else SD_TC(128);
-#undef SD_TC
-  set_error("unknown GEMM epilogue");
-  return SEQDIFF_ERR_INVALID;
+  SD_TRY(make_tmap(A, a_fmt, M, K, kBM, &ta));
+  SD_TRY(make_tmap(W, w_fmt, N, K, bn, &tb));
+  const uint32_t idesc = umma_idesc_16(kBM, bn, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
+  if (bn == 256) return dispatch_tc<256>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s);
+  return dispatch_tc<128>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s);
 }
 
 // =====================================================================================================

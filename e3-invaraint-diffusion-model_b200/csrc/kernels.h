@@ -7,8 +7,10 @@ namespace seqdiff {
 
 // ---- gemm.cu ----------------------------------------------------------------------------------------
 // epi: 0 identity, 1 erf-GELU, 2 SiLU.  resid (same shape as C) only with epi == 0.
-int gemm_bf16(int M, int N, int K, const bf16* A, const bf16* W, const float* bias, const bf16* resid, int epi, bf16* C,
-              cudaStream_t s, int force_bn = 0);
+// tcgen05 GEMM on 16-bit operands.  a_fmt / w_fmt: 0 = fp16, 1 = bf16.  out_kind: 0 = fp16, 1 = bf16, 2 = fp32.
+// resid is fp32 and implies an fp32 output (the residual stream never takes a 16-bit rounding).
+int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
+            void* C, int out_kind, cudaStream_t s, int force_bn = 0);
 int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* bias, const float* resid, int epi, float* C,
              cudaStream_t s);
 
@@ -17,24 +19,26 @@ int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* b
 // t = timestep[b], or (float)*step_ptr for every b when step_ptr != NULL (sampling loop, quirk Q3).
 int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, cudaStream_t s);
 // BertEmbeddings (model.py:110-117): out = LN(x @ Wt + b) (+ te[row / L]); Wt is the [fin, H] transpose.
+// Rowwise kernels read the fp32 residual stream and may write BOTH an fp32 copy (out32: the stream) and a
+// T copy (outT: the operand of the next GEMM); either pointer may be NULL.
 template <typename T>
 int embed_ln(const float* x, int M, int fin, const float* Wt, const float* b, const float* lnw, const float* lnb, float eps,
-             const float* te, int L, int H, T* out, cudaStream_t s);
+             const float* te, int L, int H, float* out32, T* outT, cudaStream_t s);
 // out = LayerNorm(in) * w + b
 template <typename T>
-int layernorm(const T* in, int M, int H, const float* w, const float* b, float eps, T* out, cudaStream_t s);
+int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, cudaStream_t s);
 // SELayer residual update (model.py:61-62):
 //   y = affine_first ? LayerNorm(in; lnw, lnb, eps1) : in          (BertSelfOutput.LayerNorm)
 //   out = x + gate * (LayerNorm_noaffine(y, 1e-5) * (1 + scale) + shift)
 // (shift, scale, gate) = mod[row / mod_div, (chunk0 + {0,1,2}) * H : ...], mod row pitch 6H.
 template <typename T>
-int ln_modulate(const T* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1, const T* x,
-                const T* mod, int mod_div, int chunk0, T* out, cudaStream_t s);
+int ln_modulate(const float* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1, const float* x,
+                const T* mod, int mod_div, int chunk0, float* out32, T* outT, cudaStream_t s);
 // AminoAcidPredictor tail (model.py:151-152): logits = LayerNorm(y) @ W2^T + b2  (y is already GELU(dense1))
 template <typename T>
 int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb, float eps, const float* W2, const float* b2,
                    int F, float* logits, cudaStream_t s);
-int f32_to_bf16(const float* in, size_t n, bf16* out, cudaStream_t s);
+template <typename T> int f32_to_16(const float* in, size_t n, T* out, cudaStream_t s);  // T = bf16 | f16
 int transpose_f32(const float* in, int rows, int cols, float* out, cudaStream_t s);  // out[c][r] = in[r][c]
 int step_advance(int* step_ptr, cudaStream_t s);                                     // *step_ptr -= 1
 

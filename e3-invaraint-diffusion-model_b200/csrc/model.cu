@@ -11,6 +11,7 @@
 #include "model.cuh"
 
 #include <cstring>
+#include <type_traits>
 
 namespace seqdiff {
 
@@ -29,15 +30,32 @@ int num_sms() {
   return n;
 }
 
+template <typename T> struct Fmt;  // operand format code of the tcgen05 instruction descriptor
+template <> struct Fmt<f16> { static constexpr int v = 0; };
+template <> struct Fmt<bf16> { static constexpr int v = 1; };
+
 template <typename T> static const T* pick(const Wt& w);
 template <> const float* pick<float>(const Wt& w) { return w.f; }
 template <> const bf16* pick<bf16>(const Wt& w) { return w.h; }
+template <> const f16* pick<f16>(const Wt& w) { return w.g; }
 
-static int gemm_t(int M, int N, int K, const float* A, const Wt& W, const float* bias, const float* resid, int epi, float* C, cudaStream_t s) {
-  return gemm_f32(M, N, K, A, W.f, bias, resid, epi, C, s);
+// GEMM writing an operand-typed tensor (input of the next GEMM / attention); wfmt: weight format (0 fp16, 1 bf16)
+static int gemm_T(int, int M, int N, int K, const float* A, const Wt& W, const float* bias, int epi, float* C, cudaStream_t s) {
+  return gemm_f32(M, N, K, A, W.f, bias, nullptr, epi, C, s);
 }
-static int gemm_t(int M, int N, int K, const bf16* A, const Wt& W, const float* bias, const bf16* resid, int epi, bf16* C, cudaStream_t s) {
-  return gemm_bf16(M, N, K, A, W.h, bias, resid, epi, C, s);
+template <typename T>
+static int gemm_T(int wfmt, int M, int N, int K, const T* A, const Wt& W, const float* bias, int epi, T* C, cudaStream_t s) {
+  const void* w = wfmt == 1 ? static_cast<const void*>(W.h) : static_cast<const void*>(W.g);
+  return gemm_16(M, N, K, A, Fmt<T>::v, w, wfmt, bias, nullptr, epi, C, Fmt<T>::v, s);
+}
+// GEMM writing the fp32 residual stream (LayerNorm input), optionally folding in the fp32 residual
+static int gemm_S(int, int M, int N, int K, const float* A, const Wt& W, const float* bias, const float* resid, float* C, cudaStream_t s) {
+  return gemm_f32(M, N, K, A, W.f, bias, resid, 0, C, s);
+}
+template <typename T>
+static int gemm_S(int wfmt, int M, int N, int K, const T* A, const Wt& W, const float* bias, const float* resid, float* C, cudaStream_t s) {
+  const void* w = wfmt == 1 ? static_cast<const void*>(W.h) : static_cast<const void*>(W.g);
+  return gemm_16(M, N, K, A, Fmt<T>::v, w, wfmt, bias, resid, 0, C, 2, s);
 }
 
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
@@ -45,6 +63,9 @@ __global__ void set_int_kernel(int* p, int v) { *p = v; }
 // =====================================================================================================
 Model::~Model() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (loop_stream) cudaStreamDestroy(loop_stream);
+  if (ev_in) cudaEventDestroy(ev_in);
+  if (ev_out) cudaEventDestroy(ev_out);
   for (void* p : allocs) cudaFree(p);
   for (void* p : packed_allocs) cudaFree(p);
   if (ws) cudaFree(ws);
@@ -176,13 +197,17 @@ int Model::finalize(cudaStream_t s) {
   const int64_t H = cfg.hidden_size, I = cfg.intermediate_size, P = cfg.max_position_embeddings;
   int rc = SEQDIFF_OK;
   auto R = [&](const std::string& n) -> const float* { return raw.at(n).ptr; };
-  // fp32 matrix -> Wt with a bf16 copy
+  // fp32 matrix -> Wt with bf16 and fp16 copies
   auto both = [&](const float* f, int64_t n) -> Wt {
     Wt w;
     w.f = f;
     bf16* h = static_cast<bf16*>(dalloc(static_cast<size_t>(n) * sizeof(bf16)));
-    if (!h || f32_to_bf16(f, static_cast<size_t>(n), h, s) != SEQDIFF_OK) rc = SEQDIFF_ERR_CUDA;
+    f16* g = static_cast<f16*>(dalloc(static_cast<size_t>(n) * sizeof(f16)));
+    if (!h || !g || f32_to_16<bf16>(f, static_cast<size_t>(n), h, s) != SEQDIFF_OK ||
+        f32_to_16<f16>(f, static_cast<size_t>(n), g, s) != SEQDIFF_OK)
+      rc = SEQDIFF_ERR_CUDA;
     w.h = h;
+    w.g = g;
     return w;
   };
   // stack several [rows_i, cols] fp32 tensors (row-wise) into a fresh buffer
@@ -284,27 +309,29 @@ int Model::finalize(cudaStream_t s) {
 static size_t align256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
 
 size_t Model::workspace_need(int precision, int B, int Ll, int Lr) const {
-  const size_t es = precision == SEQDIFF_FP32 ? 4 : 2;
+  const size_t es = precision == SEQDIFF_FP32 ? 4 : 2;       // operand element size
+  const size_t dual = precision == SEQDIFF_FP32 ? 4 : 4 + 2;  // fp32 stream (+ 16-bit operand copy)
   const size_t H = cfg.hidden_size, I = cfg.intermediate_size, NL = cfg.num_hidden_layers;
   const size_t Ml = static_cast<size_t>(B) * Ll, Mr = static_cast<size_t>(B) * Lr, Mt = Ml + Mr;
   size_t n = 0;
-  n += align256(static_cast<size_t>(B) * H * 4);      // te (fp32)
-  n += align256(static_cast<size_t>(B) * H * es);     // te in activation type
+  n += 2 * align256(static_cast<size_t>(B) * H * 4);  // te fp32 + operand copy
   n += align256((Ml + Mr) * 4);                       // stacked masks
-  n += 8 * align256(Mt * H * es);                     // xcat ccat u ctx o x1 m2 x2
+  n += 3 * (align256(Mt * H * 4) + align256(Mt * H * 2));  // x, x1, x2 (stream + operand)
+  n += 2 * align256(Mt * H * 4);                      // o, m2 (fp32, LayerNorm inputs)
+  n += 3 * align256(Mt * H * es);                     // c, u, ctx
   n += align256(Mt * 6 * H * es);                     // mod
   n += align256(Mt * 3 * H * es);                     // qkv
   n += align256(Mt * 4 * H * es);                     // m1
   n += align256(Mr * NL * 2 * H * es);                // kv_all
-  n += 4 * align256(Ml * H * es);                     // h x2, cq, y
+  n += 2 * (align256(Ml * H * 4) + align256(Ml * H * 2));  // decoder h ping-pong
+  n += 2 * align256(Ml * H * es);                     // cq, y
   n += align256(Ml * I * es);                         // ffn
-  return n + 4096;
+  (void)dual;
+  return n + 8192;
 }
 
 int Model::ensure_workspace(size_t bytes) {
   if (bytes <= ws_bytes) return SEQDIFF_OK;
-  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  (void)st;
   if (ws) {
     SD_CUDA(cudaDeviceSynchronize());
     SD_CUDA(cudaFree(ws));
@@ -325,79 +352,112 @@ struct Bump {
   }
 };
 
+// a residual-stream tensor: fp32 master (s) + operand-typed copy (t) fed to the next GEMM.
+// In fp32 mode both are the same buffer and the rowwise kernels write it once.
+template <typename T> struct Act {
+  float* s = nullptr;
+  T* t = nullptr;
+  T* t_out() const { return t; }
+};
+template <> struct Act<float> {
+  float* s = nullptr;
+  float* t = nullptr;
+  float* t_out() const { return nullptr; }  // already written through `s`
+};
+template <typename T> static Act<T> take_act(Bump& bp, size_t n) {
+  Act<T> a;
+  a.s = bp.take<float>(n);
+  a.t = bp.take<T>(n);
+  return a;
+}
+template <> Act<float> take_act<float>(Bump& bp, size_t n) {
+  Act<float> a;
+  a.s = bp.take<float>(n);
+  a.t = a.s;
+  return a;
+}
+template <typename T> static Act<T> offset(const Act<T>& a, size_t n) {
+  Act<T> r;
+  r.s = a.s + n;
+  r.t = a.t + n;
+  return r;
+}
+
 // =====================================================================================================
 // forward
 // =====================================================================================================
 template <typename T> struct SEBufs {
-  T *u, *mod, *qkv, *ctx, *o, *x1, *m1, *m2;
+  T *u, *mod, *qkv, *ctx, *m1;
+  float *o, *m2;
+  Act<T> x1;
 };
 
 // SELayer.forward (model.py:52-63).  x:[M,H]; c:[Mc,H] with token row r using c row r / mod_div.
 template <typename T>
-static int se_layer(const Model& m, const SEW& w, const T* x, const T* c, int Mc, int mod_div, int M, const std::vector<Segment>& segs,
-                    const SEBufs<T>& b, T* out, cudaStream_t s) {
+static int se_layer(const Model& m, int wfmt, const SEW& w, const Act<T>& x, const T* c, int Mc, int mod_div, int M,
+                    const std::vector<Segment>& segs, const SEBufs<T>& b, const Act<T>& out, cudaStream_t s) {
   const int H = m.cfg.hidden_size, P = m.cfg.max_position_embeddings, heads = m.cfg.num_attention_heads;
-  SD_TRY(gemm_t(Mc, H, H, c, w.ada0, w.ada0_b, nullptr, 2, b.u, s));          // SiLU(Linear(c))
-  SD_TRY(gemm_t(Mc, 6 * H, H, b.u, w.ada2, w.ada2_b, nullptr, 0, b.mod, s));   // -> 6 chunks
-  SD_TRY(gemm_t(M, 3 * H, H, x, w.attn.qkv, w.attn.qkv_b, nullptr, 0, b.qkv, s));
+  SD_TRY(gemm_T(wfmt, Mc, H, H, c, w.ada0, w.ada0_b, 2, b.u, s));          // SiLU(Linear(c))
+  SD_TRY(gemm_T(wfmt, Mc, 6 * H, H, b.u, w.ada2, w.ada2_b, 0, b.mod, s));   // -> 6 chunks
+  SD_TRY(gemm_T(wfmt, M, 3 * H, H, x.t, w.attn.qkv, w.attn.qkv_b, 0, b.qkv, s));
   for (const Segment& g : segs) {
     const T* base = b.qkv + static_cast<size_t>(g.row0) * 3 * H;
     SD_TRY(attention<T>(g.B, heads, g.L, g.L, base, 3 * H, base + H, 3 * H, base + 2 * H, 3 * H, pick<T>(w.attn.E), P, g.mask,
                         b.ctx + static_cast<size_t>(g.row0) * H, s));
   }
-  SD_TRY(gemm_t(M, H, H, b.ctx, w.attn.out, w.attn.out_b, x, 0, b.o, s));      // dense + residual
-  SD_TRY(ln_modulate<T>(b.o, M, H, true, w.attn.ln_w, w.attn.ln_b, m.cfg.layer_norm_eps, x, b.mod, mod_div, 0, b.x1, s));
-  SD_TRY(gemm_t(M, 4 * H, H, b.x1, w.m0, w.m0_b, nullptr, 1, b.m1, s));        // GELU
-  SD_TRY(gemm_t(M, H, 4 * H, b.m1, w.m3, w.m3_b, nullptr, 0, b.m2, s));
-  SD_TRY(ln_modulate<T>(b.m2, M, H, false, nullptr, nullptr, 0.f, b.x1, b.mod, mod_div, 3, out, s));
+  SD_TRY(gemm_S(wfmt, M, H, H, b.ctx, w.attn.out, w.attn.out_b, x.s, b.o, s));  // dense + residual (fp32)
+  SD_TRY(ln_modulate<T>(b.o, M, H, true, w.attn.ln_w, w.attn.ln_b, m.cfg.layer_norm_eps, x.s, b.mod, mod_div, 0, b.x1.s, b.x1.t_out(), s));
+  SD_TRY(gemm_T(wfmt, M, 4 * H, H, b.x1.t, w.m0, w.m0_b, 1, b.m1, s));        // GELU
+  SD_TRY(gemm_S(wfmt, M, H, 4 * H, b.m1, w.m3, w.m3_b, nullptr, b.m2, s));
+  SD_TRY(ln_modulate<T>(b.m2, M, H, false, nullptr, nullptr, 0.f, b.x1.s, b.mod, mod_div, 3, out.s, out.t_out(), s));
   return SEQDIFF_OK;
 }
 
-static int to_act(const float* in, size_t n, float* out, cudaStream_t s) {
-  SD_CUDA(cudaMemcpyAsync(out, in, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  return SEQDIFF_OK;
-}
-static int to_act(const float* in, size_t n, bf16* out, cudaStream_t s) { return f32_to_bf16(in, n, out, s); }
+static int to_act(const float*, size_t, float*, cudaStream_t) { return SEQDIFF_OK; }  // fp32 mode uses te directly
+template <typename T> static int to_act(const float* in, size_t n, T* out, cudaStream_t s) { return f32_to_16<T>(in, n, out, s); }
 
 template <typename T>
-int Model::forward_t(int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t, const float* lig_angle,
-                     const float* lig_mask, const float* rec_seq_in, const float* rec_angle, const float* rec_mask, float* logits,
-                     cudaStream_t s) {
+int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t,
+                     const float* lig_angle, const float* lig_mask, const float* rec_seq_in, const float* rec_angle,
+                     const float* rec_mask, float* logits, cudaStream_t s) {
+  constexpr bool k16 = !std::is_same<T, float>::value;
   const int H = cfg.hidden_size, I = cfg.intermediate_size, NL = cfg.num_hidden_layers, heads = cfg.num_attention_heads;
   const int P = cfg.max_position_embeddings;
   const float eps = cfg.layer_norm_eps;
   const int Ml = B * Ll, Mr = B * Lr, Mt = Ml + Mr;
+  const size_t MtH = static_cast<size_t>(Mt) * H, MlH = static_cast<size_t>(Ml) * H;
   Bump bp{ws};
   float* te = bp.take<float>(static_cast<size_t>(B) * H);
-  T* teT = bp.take<T>(static_cast<size_t>(B) * H);
+  T* teT = k16 ? bp.take<T>(static_cast<size_t>(B) * H) : reinterpret_cast<T*>(te);
   float* maskcat = bp.take<float>(static_cast<size_t>(Ml) + Mr);
-  T* xcat = bp.take<T>(static_cast<size_t>(Mt) * H);
-  T* ccat = bp.take<T>(static_cast<size_t>(Mt) * H);
+  Act<T> x = take_act<T>(bp, MtH);   // embeddings; reused as the decoder_normalize output
+  Act<T> x2 = take_act<T>(bp, MtH);  // ligand_feature_emb output: [lig | rec]
   SEBufs<T> sb;
-  sb.u = bp.take<T>(static_cast<size_t>(Mt) * H);
-  sb.ctx = bp.take<T>(static_cast<size_t>(Mt) * H);
-  sb.o = bp.take<T>(static_cast<size_t>(Mt) * H);
-  sb.x1 = bp.take<T>(static_cast<size_t>(Mt) * H);
-  sb.m2 = bp.take<T>(static_cast<size_t>(Mt) * H);
-  T* x2 = bp.take<T>(static_cast<size_t>(Mt) * H);
-  sb.mod = bp.take<T>(static_cast<size_t>(Mt) * 6 * H);
-  sb.qkv = bp.take<T>(static_cast<size_t>(Mt) * 3 * H);
-  sb.m1 = bp.take<T>(static_cast<size_t>(Mt) * 4 * H);
+  sb.x1 = take_act<T>(bp, MtH);
+  sb.o = bp.take<float>(MtH);
+  sb.m2 = bp.take<float>(MtH);
+  T* ccat = bp.take<T>(MtH);
+  sb.u = bp.take<T>(MtH);
+  sb.ctx = bp.take<T>(MtH);
+  sb.mod = bp.take<T>(MtH * 6);
+  sb.qkv = bp.take<T>(MtH * 3);
+  sb.m1 = bp.take<T>(MtH * 4);
   T* kv_all = bp.take<T>(static_cast<size_t>(Mr) * NL * 2 * H);
-  T* hbuf[2];
-  for (int i = 0; i < 2; ++i) hbuf[i] = bp.take<T>(static_cast<size_t>(Ml) * H);
-  T* cq = bp.take<T>(static_cast<size_t>(Ml) * H);
-  T* y = bp.take<T>(static_cast<size_t>(Ml) * H);
+  Act<T> hbuf[2] = {take_act<T>(bp, MlH), take_act<T>(bp, MlH)};
+  T* cq = bp.take<T>(MlH);
+  T* y = bp.take<T>(MlH);
   T* ffn = bp.take<T>(static_cast<size_t>(Ml) * I);
 
   // timestep features + the four BertEmbeddings (model.py:211-213,219-220)
   SD_TRY(timestep_embed(timestep, step_ptr, ts_W, B, H, te, s));
-  SD_TRY(embed_ln<T>(x_t, Ml, 20, lig_seq.Wt_, lig_seq.b, lig_seq.ln_w, lig_seq.ln_b, eps, nullptr, Ll, H, xcat, s));
-  SD_TRY(embed_ln<T>(lig_angle, Ml, 8, lig_ang.Wt_, lig_ang.b, lig_ang.ln_w, lig_ang.ln_b, eps, te, Ll, H, ccat, s));
-  SD_TRY(embed_ln<T>(rec_seq_in, Mr, 20, rec_seq.Wt_, rec_seq.b, rec_seq.ln_w, rec_seq.ln_b, eps, nullptr, Lr, H,
-                     xcat + static_cast<size_t>(Ml) * H, s));
+  const Act<T> xr = offset(x, MlH);
+  SD_TRY(embed_ln<T>(x_t, Ml, 20, lig_seq.Wt_, lig_seq.b, lig_seq.ln_w, lig_seq.ln_b, eps, nullptr, Ll, H, x.s, x.t_out(), s));
+  SD_TRY(embed_ln<T>(rec_seq_in, Mr, 20, rec_seq.Wt_, rec_seq.b, rec_seq.ln_w, rec_seq.ln_b, eps, nullptr, Lr, H, xr.s, xr.t_out(), s));
+  // the conditioning c = LN(Linear(angles)) + te only ever feeds a GEMM: operand type only
+  SD_TRY(embed_ln<T>(lig_angle, Ml, 8, lig_ang.Wt_, lig_ang.b, lig_ang.ln_w, lig_ang.ln_b, eps, te, Ll, H,
+                     k16 ? nullptr : reinterpret_cast<float*>(ccat), k16 ? ccat : nullptr, s));
   SD_TRY(embed_ln<T>(rec_angle, Mr, 8, rec_ang.Wt_, rec_ang.b, rec_ang.ln_w, rec_ang.ln_b, eps, te, Lr, H,
-                     ccat + static_cast<size_t>(Ml) * H, s));
+                     k16 ? nullptr : reinterpret_cast<float*>(ccat + MlH), k16 ? ccat + MlH : nullptr, s));
 
   // ligand_feature_emb on ligand AND receptor tokens in one pass (model.py:214-224, quirk Q1)
   std::vector<Segment> segs;
@@ -409,41 +469,38 @@ int Model::forward_t(int B, int Ll, int Lr, const float* timestep, const int* st
     segs.push_back({0, B, Ll, lig_mask});
     segs.push_back({Ml, B, Lr, rec_mask});
   }
-  SD_TRY(se_layer<T>(*this, se_lig, xcat, ccat, Mt, 1, Mt, segs, sb, x2, s));
-  const T* lig = x2;
-  const T* rec = x2 + static_cast<size_t>(Ml) * H;
+  SD_TRY(se_layer<T>(*this, wfmt, se_lig, x, ccat, Mt, 1, Mt, segs, sb, x2, s));
+  const T* rec = x2.t + MlH;
 
   // decoder: 6 x (self-attn -> cross-attn -> FFN), post-LN (HF BertLayer; model.py:226-231)
-  SD_TRY(gemm_t(Mr, NL * 2 * H, H, rec, ckv_all, ckv_all_b, nullptr, 0, kv_all, s));
-  const T* h = lig;
+  SD_TRY(gemm_T(wfmt, Mr, NL * 2 * H, H, rec, ckv_all, ckv_all_b, 0, kv_all, s));
+  Act<T> h = x2;  // ligand rows are the first Ml rows
   for (int i = 0; i < NL; ++i) {
     const LayerW& w = layers[i];
     // h is dead once the self-output GEMM has folded it in as the residual, so h1/h3 may reuse its buffer
-    T* h1 = hbuf[0];
-    T* h2 = hbuf[1];
-    T* h3 = hbuf[0];
-    SD_TRY(gemm_t(Ml, 3 * H, H, h, w.self.qkv, w.self.qkv_b, nullptr, 0, sb.qkv, s));
+    const Act<T> h1 = hbuf[0], h2 = hbuf[1], h3 = hbuf[0];
+    SD_TRY(gemm_T(wfmt, Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, 0, sb.qkv, s));
     SD_TRY(attention<T>(B, heads, Ll, Ll, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s));
-    SD_TRY(gemm_t(Ml, H, H, sb.ctx, w.self.out, w.self.out_b, h, 0, sb.o, s));
-    SD_TRY(layernorm<T>(sb.o, Ml, H, w.self.ln_w, w.self.ln_b, eps, h1, s));
-    SD_TRY(gemm_t(Ml, H, H, h1, w.cq, w.cq_b, nullptr, 0, cq, s));
+    SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, h.s, sb.o, s));
+    SD_TRY(layernorm<T>(sb.o, Ml, H, w.self.ln_w, w.self.ln_b, eps, h1.s, h1.t_out(), s));
+    SD_TRY(gemm_T(wfmt, Ml, H, H, h1.t, w.cq, w.cq_b, 0, cq, s));
     const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
     SD_TRY(attention<T>(B, heads, Ll, Lr, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s));
-    SD_TRY(gemm_t(Ml, H, H, sb.ctx, w.cout, w.cout_b, h1, 0, sb.o, s));
-    SD_TRY(layernorm<T>(sb.o, Ml, H, w.cln_w, w.cln_b, eps, h2, s));
-    SD_TRY(gemm_t(Ml, I, H, h2, w.inter, w.inter_b, nullptr, 1, ffn, s));
-    SD_TRY(gemm_t(Ml, H, I, ffn, w.outd, w.outd_b, h2, 0, sb.o, s));
-    SD_TRY(layernorm<T>(sb.o, Ml, H, w.oln_w, w.oln_b, eps, h3, s));
+    SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.cout, w.cout_b, h1.s, sb.o, s));
+    SD_TRY(layernorm<T>(sb.o, Ml, H, w.cln_w, w.cln_b, eps, h2.s, h2.t_out(), s));
+    SD_TRY(gemm_T(wfmt, Ml, I, H, h2.t, w.inter, w.inter_b, 1, ffn, s));
+    SD_TRY(gemm_S(wfmt, Ml, H, I, ffn, w.outd, w.outd_b, h2.s, sb.o, s));
+    SD_TRY(layernorm<T>(sb.o, Ml, H, w.oln_w, w.oln_b, eps, h3.s, h3.t_out(), s));
     h = h3;
   }
 
   // decoder_normalize: SELayer conditioned on the timestep only (c broadcast over L; model.py:232-235)
   SD_TRY(to_act(te, static_cast<size_t>(B) * H, teT, s));
   std::vector<Segment> lseg{{0, B, Ll, lig_mask}};
-  SD_TRY(se_layer<T>(*this, se_dec, h, teT, B, Ll, Ml, lseg, sb, xcat, s));
+  SD_TRY(se_layer<T>(*this, wfmt, se_dec, h, teT, B, Ll, Ml, lseg, sb, x, s));
 
   // AminoAcidPredictor (model.py:148-153)
-  SD_TRY(gemm_t(Ml, H, H, xcat, p1, p1_b, nullptr, 1, y, s));
+  SD_TRY(gemm_T(wfmt, Ml, H, H, x.t, p1, p1_b, 1, y, s));
   SD_TRY(predictor_tail<T>(y, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, logits, s));
   return SEQDIFF_OK;
 }
@@ -452,14 +509,19 @@ int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, 
                    const float* lig_angle, const float* lig_mask, const float* rec_seq_in, const float* rec_angle,
                    const float* rec_mask, float* logits, cudaStream_t s) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
-  SD_CHECK(precision == SEQDIFF_FP32 || precision == SEQDIFF_BF16, "precision must be SEQDIFF_FP32 or SEQDIFF_BF16");
+  SD_CHECK(precision >= SEQDIFF_FP32 && precision <= SEQDIFF_FP16, "unknown precision mode");
   SD_CHECK(B > 0 && Ll > 0 && Lr > 0, "empty batch");
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
   SD_CUDA(cudaSetDevice(device));
   SD_TRY(ensure_workspace(workspace_need(precision, B, Ll, Lr)));
-  if (precision == SEQDIFF_FP32)
-    return forward_t<float>(B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
-  return forward_t<bf16>(B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+  switch (precision) {
+    case SEQDIFF_FP32:
+      return forward_t<float>(1, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+    case SEQDIFF_BF16:
+      return forward_t<bf16>(1, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+    default:  // SEQDIFF_FP16
+      return forward_t<f16>(0, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+  }
 }
 
 // =====================================================================================================
@@ -467,9 +529,18 @@ int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, 
 // =====================================================================================================
 int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_tables, const float* x_T, const float* lig_angle,
                   const float* lig_mask, const float* rec_seq_in, const float* rec_angle, const float* rec_mask, int diverse,
-                  const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t s) {
+                  const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t caller) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
   SD_CHECK(T >= 1 && B > 0 && Ll > 0 && Lr > 0, "bad sampling arguments");
+  if (!loop_stream) {
+    SD_CUDA(cudaStreamCreateWithFlags(&loop_stream, cudaStreamNonBlocking));
+    SD_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    SD_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+  }
+  // everything below runs on the private stream, ordered after the caller's prior work ...
+  cudaStream_t s = loop_stream;
+  SD_CUDA(cudaEventRecord(ev_in, caller));
+  SD_CUDA(cudaStreamWaitEvent(s, ev_in, 0));
   SD_CHECK(cfg.feature_size == SEQDIFF_NUM_CLASSES, "sampling needs feature_size == 20");
   SD_CUDA(cudaSetDevice(device));
   const size_t Nl = static_cast<size_t>(B) * Ll, Nr = static_cast<size_t>(B) * Lr;
@@ -535,6 +606,9 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
   SD_LAUNCH_CHECK();
   for (int it = 0; it < T; ++it) SD_CUDA(cudaGraphLaunch(graph_exec, s));
   SD_CUDA(cudaMemcpyAsync(final_out, logits, Nl * 20 * 4, cudaMemcpyDefault, s));
+  // ... and the caller's stream continues only after the loop has finished
+  SD_CUDA(cudaEventRecord(ev_out, s));
+  SD_CUDA(cudaStreamWaitEvent(caller, ev_out, 0));
   return SEQDIFF_OK;
 }
 

@@ -8,10 +8,11 @@
 
 namespace seqdiff {
 
-// one logical matrix, held in both precisions (bf16 copy made by finalize())
+// one logical matrix in the three storage formats (16-bit copies made by finalize())
 struct Wt {
   const float* f = nullptr;
   const bf16* h = nullptr;
+  const f16* g = nullptr;
 };
 
 struct AttnW {
@@ -76,6 +77,8 @@ struct Model {
   uint8_t* samp_in = nullptr;  // persistent copies of the loop inputs + x_t + logits
   size_t samp_in_bytes = 0;
   cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t loop_stream = nullptr;  // private stream: graphs cannot be captured on the legacy default stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   struct GraphKey {
     int precision = -1, B = 0, Ll = 0, Lr = 0, diverse = 0;
     const float* noise = nullptr;
@@ -105,7 +108,7 @@ struct Model {
   size_t workspace_need(int precision, int B, int Ll, int Lr) const;
   int ensure_workspace(size_t bytes);
   template <typename T>
-  int forward_t(int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t, const float* lig_angle,
+  int forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t, const float* lig_angle,
                 const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, float* logits,
                 cudaStream_t s);
 };

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_kernel(const float* __re
                                                                const float* __restrict__ Wt, const float* __restrict__ bias,
                                                                const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                                float eps, const float* __restrict__ te, int L, int H,
-                                                               T* __restrict__ out) {
+                                                               float* __restrict__ out32, T* __restrict__ outT) {
   constexpr int TOK = 4;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_kernel(const float* __re
         for (int j = 0; j < 8; ++j) v[i][j] += t8[j];
       }
     }
-    store_row<T, VPL>(out + static_cast<size_t>(tok0 + t) * H, lane, v);
+    if (out32) store_row<float, VPL>(out32 + static_cast<size_t>(tok0 + t) * H, lane, v);
+    if (outT) store_row<T, VPL>(outT + static_cast<size_t>(tok0 + t) * H, lane, v);
   }
 }
 
@@ -138,26 +139,30 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_kernel(const float* __re
 
 template <typename T>
 int embed_ln(const float* x, int M, int fin, const float* Wt, const float* b, const float* lnw, const float* lnb, float eps,
-             const float* te, int L, int H, T* out, cudaStream_t s) {
+             const float* te, int L, int H, float* out32, T* outT, cudaStream_t s) {
   SD_CHECK(H % 256 == 0, "hidden_size must be a multiple of 256");
   const int warps = ceil_div(M, 4);
   const int grid = ceil_div(warps * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, embed_ln_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(x, M, fin, Wt, b, lnw, lnb, eps, te, L, H, out));
+  SD_VPL_DISPATCH(H, embed_ln_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(x, M, fin, Wt, b, lnw, lnb, eps, te, L, H, out32, outT));
   SD_LAUNCH_CHECK();
   return SEQDIFF_OK;
 }
-template int embed_ln<float>(const float*, int, int, const float*, const float*, const float*, const float*, float, const float*, int, int, float*, cudaStream_t);
-template int embed_ln<bf16>(const float*, int, int, const float*, const float*, const float*, const float*, float, const float*, int, int, bf16*, cudaStream_t);
+#define SD_INST_EMBED(T) \
+  template int embed_ln<T>(const float*, int, int, const float*, const float*, const float*, const float*, float, const float*, int, int, float*, T*, cudaStream_t)
+SD_INST_EMBED(float);
+SD_INST_EMBED(bf16);
+SD_INST_EMBED(f16);
 
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int VPL>
-__global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const T* __restrict__ in, int M, int H, const float* __restrict__ w,
-                                                                const float* __restrict__ b, float eps, T* __restrict__ out) {
+__global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const float* __restrict__ in, int M, int H, const float* __restrict__ w,
+                                                                const float* __restrict__ b, float eps, float* __restrict__ out32,
+                                                                T* __restrict__ outT) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
   if (row >= M) return;
   float v[VPL][8];
-  load_row<T, VPL>(in + static_cast<size_t>(row) * H, lane, v);
+  load_row<float, VPL>(in + static_cast<size_t>(row) * H, lane, v);
   float mean, rstd;
   row_stats<VPL>(v, H, eps, mean, rstd);
 #pragma unroll
@@ -168,30 +173,33 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const T* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * g8[j] + b8[j];
   }
-  store_row<T, VPL>(out + static_cast<size_t>(row) * H, lane, v);
+  if (out32) store_row<float, VPL>(out32 + static_cast<size_t>(row) * H, lane, v);
+  if (outT) store_row<T, VPL>(outT + static_cast<size_t>(row) * H, lane, v);
 }
 
 template <typename T>
-int layernorm(const T* in, int M, int H, const float* w, const float* b, float eps, T* out, cudaStream_t s) {
+int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, cudaStream_t s) {
   const int grid = ceil_div(M * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, layernorm_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(in, M, H, w, b, eps, out));
+  SD_VPL_DISPATCH(H, layernorm_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(in, M, H, w, b, eps, out32, outT));
   SD_LAUNCH_CHECK();
   return SEQDIFF_OK;
 }
-template int layernorm<float>(const float*, int, int, const float*, const float*, float, float*, cudaStream_t);
-template int layernorm<bf16>(const bf16*, int, int, const float*, const float*, float, bf16*, cudaStream_t);
+#define SD_INST_LN(T) template int layernorm<T>(const float*, int, int, const float*, const float*, float, float*, T*, cudaStream_t)
+SD_INST_LN(float);
+SD_INST_LN(bf16);
+SD_INST_LN(f16);
 
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int VPL, bool AFFINE_FIRST>
-__global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const T* __restrict__ in, int M, int H, const float* __restrict__ lnw,
-                                                                  const float* __restrict__ lnb, float eps1, const T* __restrict__ x,
+__global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const float* __restrict__ in, int M, int H, const float* __restrict__ lnw,
+                                                                  const float* __restrict__ lnb, float eps1, const float* __restrict__ x,
                                                                   const T* __restrict__ mod, int mod_div, int chunk0,
-                                                                  T* __restrict__ out) {
+                                                                  float* __restrict__ out32, T* __restrict__ outT) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
   if (row >= M) return;
   float v[VPL][8];
-  load_row<T, VPL>(in + static_cast<size_t>(row) * H, lane, v);
+  load_row<float, VPL>(in + static_cast<size_t>(row) * H, lane, v);
   float mean, rstd;
   if (AFFINE_FIRST) {  // BertSelfOutput.LayerNorm (eps 1e-12, affine) -- output of self.attn(x, mask)[0]
     row_stats<VPL>(v, H, eps1, mean, rstd);
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const T* __res
   }
   row_stats<VPL>(v, H, 1e-5f, mean, rstd);  // SELayer.norm1/norm2: elementwise_affine=False, default eps
   const T* mrow = mod + static_cast<size_t>(row / mod_div) * (6 * H);
-  const T* xrow = x + static_cast<size_t>(row) * H;
+  const float* xrow = x + static_cast<size_t>(row) * H;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int e = (i * 32 + lane) * 8;
@@ -214,30 +222,34 @@ __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const T* __res
     load8<T>(mrow + (chunk0 + 0) * H + e, sh);
     load8<T>(mrow + (chunk0 + 1) * H + e, sc);
     load8<T>(mrow + (chunk0 + 2) * H + e, gt);
-    load8<T>(xrow + e, xr);
+    load8<float>(xrow + e, xr);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float n = (v[i][j] - mean) * rstd;
       v[i][j] = xr[j] + gt[j] * (n * (1.0f + sc[j]) + sh[j]);
     }
   }
-  store_row<T, VPL>(out + static_cast<size_t>(row) * H, lane, v);
+  if (out32) store_row<float, VPL>(out32 + static_cast<size_t>(row) * H, lane, v);
+  if (outT) store_row<T, VPL>(outT + static_cast<size_t>(row) * H, lane, v);
 }
 
 template <typename T>
-int ln_modulate(const T* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1, const T* x,
-                const T* mod, int mod_div, int chunk0, T* out, cudaStream_t s) {
+int ln_modulate(const float* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1, const float* x,
+                const T* mod, int mod_div, int chunk0, float* out32, T* outT, cudaStream_t s) {
   const int grid = ceil_div(M * 32, kRowThreads);
   if (affine_first) {
-    SD_VPL_DISPATCH(H, ln_modulate_kernel<T, VPL, true><<<grid, kRowThreads, 0, s>>>(in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out));
+    SD_VPL_DISPATCH(H, ln_modulate_kernel<T, VPL, true><<<grid, kRowThreads, 0, s>>>(in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT));
   } else {
-    SD_VPL_DISPATCH(H, ln_modulate_kernel<T, VPL, false><<<grid, kRowThreads, 0, s>>>(in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out));
+    SD_VPL_DISPATCH(H, ln_modulate_kernel<T, VPL, false><<<grid, kRowThreads, 0, s>>>(in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT));
   }
   SD_LAUNCH_CHECK();
   return SEQDIFF_OK;
 }
-template int ln_modulate<float>(const float*, int, int, bool, const float*, const float*, float, const float*, const float*, int, int, float*, cudaStream_t);
-template int ln_modulate<bf16>(const bf16*, int, int, bool, const float*, const float*, float, const bf16*, const bf16*, int, int, bf16*, cudaStream_t);
+#define SD_INST_LNMOD(T) \
+  template int ln_modulate<T>(const float*, int, int, bool, const float*, const float*, float, const float*, const T*, int, int, float*, T*, cudaStream_t)
+SD_INST_LNMOD(float);
+SD_INST_LNMOD(bf16);
+SD_INST_LNMOD(f16);
 
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int VPL>
@@ -290,21 +302,26 @@ int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb,
 }
 template int predictor_tail<float>(const float*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t);
 template int predictor_tail<bf16>(const bf16*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t);
+template int predictor_tail<f16>(const f16*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, size_t n, bf16* __restrict__ out) {
+template <typename T>
+__global__ void f32_to_16_kernel(const float* __restrict__ in, size_t n, T* __restrict__ out) {
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x);
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+  for (; i < n; i += stride) out[i] = from_f32<T>(in[i]);
 }
-int f32_to_bf16(const float* in, size_t n, bf16* out, cudaStream_t s) {
+template <typename T>
+int f32_to_16(const float* in, size_t n, T* out, cudaStream_t s) {
   if (n == 0) return SEQDIFF_OK;
   size_t blocks = (n + 255) / 256;
   if (blocks > 4096) blocks = 4096;
-  f32_to_bf16_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(in, n, out);
+  f32_to_16_kernel<T><<<static_cast<int>(blocks), 256, 0, s>>>(in, n, out);
   SD_LAUNCH_CHECK();
   return SEQDIFF_OK;
 }
+template int f32_to_16<bf16>(const float*, size_t, bf16*, cudaStream_t);
+template int f32_to_16<f16>(const float*, size_t, f16*, cudaStream_t);
 
 __global__ void transpose_f32_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

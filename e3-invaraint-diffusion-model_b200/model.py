@@ -144,8 +144,11 @@ class AminoAcidPredictor(_Container):
 
 # ------------------------------------------------------------------------------------------------
 class ConditionalBertForDiffusionBase(nn.Module):
-    """reference model.py:156-253.  `precision`: "bf16" (tcgen05 GEMMs; logits within 1e-2 of the fp32
-    reference) or "fp32" (SIMT fp32 kernels; within 1e-5)."""
+    """reference model.py:156-253.  `precision` selects the operand format of the GEMM / attention kernels
+    (accumulators, residual stream, LayerNorm, softmax and logits are fp32 in every mode):
+      "bf16"       bf16 activations x bf16 weights on tcgen05 (the configuration BASELINE.json names)
+      "fp16"       fp16 activations x fp16 weights, same kernels and speed, 8x finer operand rounding
+      "fp32"       fp32 SIMT kernels -- the 1e-5 parity mode."""
 
     def __init__(self, encoder_config, decoder_config, feature_size: int) -> None:
         super().__init__()
@@ -193,9 +196,9 @@ class ConditionalBertForDiffusionBase(nn.Module):
             layer_norm_eps=float(getattr(d, "layer_norm_eps", 1e-12)))
 
     def _precision_code(self):
-        if self.precision not in ("bf16", "fp32"):
-            raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
-        return _cabi.BF16 if self.precision == "bf16" else _cabi.FP32
+        if self.precision not in _cabi.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_cabi.PRECISIONS)}, got {self.precision!r}")
+        return _cabi.PRECISIONS[self.precision]
 
     def _sync_handle(self):
         """(Re)uploads the weights into the C handle when any tensor of the state_dict changed."""

@@ -40,8 +40,13 @@ extern "C" {
 #define SEQDIFF_ERR_CUDA 2      /* CUDA runtime / driver error                 */
 #define SEQDIFF_ERR_STATE 3     /* handle not finalised, unknown tensor name   */
 
-#define SEQDIFF_FP32 0 /* fp32 activations, fp32 SIMT GEMMs   (parity gate 1e-5)        */
-#define SEQDIFF_BF16 1 /* bf16 activations, tcgen05 GEMMs, fp32 accumulate/LN (1e-2)    */
+/* precision modes.  In every 16-bit mode the GEMM/attention OPERANDS are 16-bit while accumulators, the
+ * residual stream, LayerNorm, softmax, biases and logits stay fp32. */
+#define SEQDIFF_FP32 0       /* fp32 everything, SIMT GEMMs                      (parity gate 1e-5) */
+#define SEQDIFF_BF16 1       /* bf16 activations x bf16 weights, tcgen05 GEMMs   (the named config) */
+#define SEQDIFF_FP16 2       /* fp16 activations x fp16 weights, same kernels, 8x finer mantissa    */
+/* (A and B of one tcgen05.mma.kind::f16 must share a format: a bf16 x fp16 mix traps as an illegal
+ * instruction on B200, measured in round 1, so there is no mixed mode.) */
 
 #define SEQDIFF_NUM_CLASSES 20
 #define SEQDIFF_ANGLE_FEATS 8
@@ -111,7 +116,8 @@ SEQDIFF_API int seqdiff_sample(seqdiff_model_t* m, int precision, int B, int L_l
 
 /* ---- operator-level entry points (used by the parity tests and the micro benchmarks) --------------
  * C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias[N] (+ resid[M,N])); epilogue: 0 none, 1 erf-GELU, 2 SiLU.
- * precision BF16: A,W,resid,C are bf16 (tcgen05 + TMA kernel); FP32: all f32 (SIMT kernel). */
+ * precision FP32: all f32 (SIMT kernel).  BF16 / FP16: A and W are 16-bit in the mode's formats
+ * (tcgen05 + TMA kernel); resid (optional) is f32 and makes C f32, otherwise C has A's 16-bit type. */
 SEQDIFF_API int seqdiff_op_gemm(int precision, int M, int N, int K, const void* A, const void* W, const float* bias,
                     const void* resid, int epilogue, void* C, void* stream);
 /* multi-head attention core of HF BertSelfAttention (4.38.2 relative_key semantics):

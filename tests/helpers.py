@@ -12,7 +12,7 @@ if ROOT not in sys.path:
 from oracle import seqdiff_oracle as O  # noqa: E402  (the checker)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-FP32, BF16 = 0, 1
+FP32, BF16, FP16 = 0, 1, 2
 
 
 def sd_pkg():
@@ -42,6 +42,12 @@ def rel_err(a, b):
     """max|a-b| / max|b| -- the 'relative' of the parity tolerances (1e-5 fp32, 1e-2 bf16)."""
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def l2_rel(a, b):
+    """||a-b||_2 / ||b||_2"""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
 def top2_margin(v):
