@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sequence-denoiser hot path (BASELINE.json configs[1]):
+full reverse-diffusion sampling (T=500) of 64 synthetic pocket graphs (L=128) per GPU, bf16 tensor-core
+operands, on N B200s of one node (one process per GPU, graphs sharded across ranks, no collective on the
+data path: weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repository's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on host CPU cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Vocabulary.  graph-step = one pocket graph through one denoiser forward + one reverse-diffusion step
+(sequence_model/sample.py:199-207).  One bench "step" = one complete T-step sampling of the rank's batch
+= B*T graph-steps.  denoised pocket-graphs/s = value / T;  edge msgs/s (attended query-key pairs) =
+value * 15 * L^2.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "denoiser graph-steps/s (forward + reverse-diffusion step per pocket graph; cfg2: 64 pockets x 500 steps, L=128)"
+UNIT = "graph-steps/s"
+L, H, I, NL = 128, 768, 1024, 6
+
+
+# ----------------------------------------------------------------------------------------------------
+def synthetic_workload(B, seed_offset=0):
+    """SURVEY.md section 8d cfg 2: n_lig ~ U{5..64}, n_rec ~ U{16..128} (seed 3), angles ~ U(-pi, pi), zero padding,
+    prefix-ones masks; x_T one-hot of randint (seed 4).  Plain torch on the host -- no oracle import here."""
+    g = torch.Generator().manual_seed(3 + seed_offset)
+    nl = torch.randint(5, 65, (B,), generator=g)
+    nr = torch.randint(16, 129, (B,), generator=g)
+    pos = torch.arange(L)[None, :]
+    lm, rm = (pos < nl[:, None]).float(), (pos < nr[:, None]).float()
+
+    def side(mask):
+        seq = torch.nn.functional.one_hot(torch.randint(0, 20, (B, L), generator=g), 20).float() * mask[..., None]
+        ang = ((torch.rand(B, L, 8, generator=g) * 2 - 1) * math.pi) * mask[..., None]
+        return seq, ang
+
+    lseq, lang = side(lm)
+    rseq, rang = side(rm)
+    g4 = torch.Generator().manual_seed(4 + seed_offset)
+    x_T = torch.nn.functional.one_hot(torch.randint(0, 20, (B, L), generator=g4), 20).float()
+    batch = {"ligand_seq": lseq, "ligand_angles": lang, "ligand_attn_mask": lm, "receptor_seq": rseq, "receptor_angles": rang,
+             "receptor_attn_mask": rm, "structure_ids": {"pdb_id": [f"s{i:04d}" for i in range(B)], "ligand_chain": ["A"] * B}}
+    return batch, x_T
+
+
+def gemm_flops_per_forward(B):
+    """2*M*N*K summed over the 50 GEMM launches of one forward (DESIGN.md section 'Kernels')."""
+    Ml = Mr = B * L
+    Mt = Ml + Mr
+    macs = 19 * Mt * H * H                      # ligand_feature_emb over [lig|rec]: ada0, ada2(6), qkv(3), out, mlp(4+4)
+    macs += 2 * NL * Mr * H * H                 # stacked cross K|V projection
+    macs += NL * Ml * (6 * H * H + 2 * I * H)   # decoder layers: qkv(3) out cq cout + FFN up/down
+    macs += 12 * Ml * H * H + 7 * B * H * H     # decoder_normalize (adaLN on B rows only)
+    macs += Ml * H * H                          # predictor dense1
+    return 2 * macs
+
+
+def algorithmic_flops_per_graph_step():
+    return 18.369e9  # BASELINE.md section 3, L=128 (incl. attention)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                          str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)", d.get("hbm_gbs")
+    return 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)", 6650.0
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_steps(state, batch, x_T, T, n_steps, n_warm, threads):
+    """The reference algorithm on host cores ("port": oracle/seqdiff_oracle.py, which restates
+    sequence_model/model.py:200-237 + sample.py:141-179 incl. its Python multinomial loop).
+    One step = forward + reverse step over the whole batch at s_int = T-1, T-2, ..."""
+    from oracle import seqdiff_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig(max_position_embeddings=L)
+    sched, trans = O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition(timestep=500)
+    B = x_T.shape[0]
+    x = x_T.clone()
+    times = []
+    with torch.no_grad():
+        for i in range(n_warm + n_steps):
+            s_int = T - 1 - i
+            t0 = time.perf_counter()
+            s_array = s_int * torch.ones((B, 1))
+            logits = O.denoiser_forward(state, cfg, s_array, x, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                                        batch["receptor_angles"], batch["receptor_attn_mask"])
+            x = O.reverse_step_python_loop((s_array + 1) / T, s_array / T, x, logits, sched, trans, True, False)
+            dt = time.perf_counter() - t0
+            if i >= n_warm:
+                times.append(dt)
+    return times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import seqdiff_b200 as sd  # host-side module tree only (weights); no CUDA call is made on this arm
+    torch.manual_seed(0)
+    common = dict(max_position_embeddings=L, intermediate_size=I, num_hidden_layers=NL, position_embedding_type="relative_key")
+    model = sd.ConditionalBertForDiffusionBase(sd.BertConfig(**common), sd.BertConfig(**common, is_decoder=True, add_cross_attention=True), 20)
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch, x_T = synthetic_workload(args.batch)
+    threads = os.cpu_count() or 1
+    times = cpu_reference_steps(state, batch, x_T, args.timesteps, args.steps, args.warmup, threads)
+    total = sum(times)
+    value = args.batch * len(times) / total
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"cfg2 sample: one denoise step (forward + reverse step) of the {args.batch}-pocket batch per bench step",
+                      "batch": args.batch, "L": L, "timesteps": args.timesteps, "device": "host CPU"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{len(times)} denoise steps x {args.batch} graphs (of {args.timesteps} steps); oracle port incl. the reference's Python multinomial loop"},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="pocket graphs per GPU")
+    ap.add_argument("--timesteps", type=int, default=500, help="T (500 = the named config; smaller only for profiling runs)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / roofline / cpu legs (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback (use --impl reference for the CPU arm)"}))
+        return 1
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    import seqdiff_b200 as sd
+    lib = sd.lib()
+    sd.sample.DEVICE = dev
+    sd.sample.CONFIG.update(timesteps=args.timesteps, max_seq_len=L, batch_size=args.batch)
+    B, T = args.batch, args.timesteps
+    torch.manual_seed(0)  # identical random-init weights on every rank (replicated model, 145 MB bf16)
+    common = dict(max_position_embeddings=L, intermediate_size=I, num_hidden_layers=NL, position_embedding_type="relative_key")
+    model = sd.ConditionalBertForDiffusionBase(sd.BertConfig(**common), sd.BertConfig(**common, is_decoder=True, add_cross_attention=True), 20)
+    # reference init leaves decoder_normalize an exact identity (gates 0); same FLOPs either way, keep the reference init
+    model = model.eval().to(dev)
+    model.precision = args.precision
+    sched = sd.PredefinedNoiseScheduleDiscrete("cosine", T)
+    trans = sd.BlosumTransition(x_classes=20, timestep=500)
+    batch, x_T = synthetic_workload(B, seed_offset=1000 * rank)
+    gid0 = rank * B  # global graph ids key the Philox noise: results do not depend on the sharding
+    dbatch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    dx_T = x_T.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def one_sampling():
+        return sd.denoise_tensors(dbatch, model, sched, trans, True, timesteps=T, x_T=dx_T, seed=5, graph_id0=gid0)
+
+    # ---- device-resident throughput: K full T-step samplings, CUDA events on the launching stream -------
+    for _ in range(args.warmup):
+        one_sampling()
+    barrier()
+    n0 = lib.seqdiff_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            out = one_sampling()
+        e1.record()
+        barrier()
+    launches = lib.seqdiff_launch_count() - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    value = world * B * T * args.steps / (ms * 1e-3)
+    assert torch.isfinite(out).all()
+
+    result = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+              "data": "synthetic",
+              "config": {"workload": f"BASELINE configs[1]: full reverse-diffusion sampling (T={T}) of {B} synthetic pockets per GPU, L={L}, "
+                                     f"ragged n_lig~U[5,64] n_rec~U[16,128], diverse=True, random-init weights, relative_key attention",
+                         "batch_per_gpu": B, "L": L, "timesteps": T, "sharding": f"graphs x{world} (no data-path collective)",
+                         "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2 (no explicit flush needed)",
+                         "pocket_graphs_per_s": value / T, "edge_msgs_per_s": value * 15 * L * L},
+              "clocks": clk.summary(), "gpu_launches": int(launches)}
+
+    if not args.no_extras:
+        # ---- end to end through the public API: denoise(batch_on_host, ...) -> decoded sequences on the host ----
+        pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        px_T = x_T.pin_memory()
+        h2d = sum(v.numel() * v.element_size() for k, v in pinned.items() if torch.is_tensor(v) and k != "ligand_seq")
+        h2d += px_T.numel() * 4 + T * 3 * 400 * 4
+        d2h = B * L * 8  # argmax indices (int64) of the final logits
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            sd.denoise(pinned, model, sched, trans, True, timesteps=T, x_T=px_T, seed=5, graph_id0=gid0)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ids, true_seq, pred_seq, rates = sd.denoise(pinned, model, sched, trans, True, timesteps=T, x_T=px_T, seed=5, graph_id0=gid0)
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        result["e2e"] = {"value": world * B * T * args.steps / dt.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                         "d2h_bytes_per_step": int(d2h), "api": "denoise(batch_on_pinned_host, model, noise_schedule, transition, diverse)"}
+
+        # ---- roofline of the dominant kernel (tcgen05 GEMM), timed live with CUDA events (library profiler) ----
+        if rank == 0:
+            t_arr = torch.full((B, 1), float(T - 1), device=dev)
+            fwd_args = (t_arr, dx_T, dbatch["ligand_angles"], dbatch["ligand_attn_mask"], dbatch["receptor_seq"], dbatch["receptor_angles"],
+                        dbatch["receptor_attn_mask"])
+            with torch.no_grad():
+                for _ in range(2):
+                    model(*fwd_args)
+                torch.cuda.synchronize(dev)
+                reps = 5
+                prof = sd._cabi.profile(lambda: [model(*fwd_args) for _ in range(reps)])
+            total_ms = sum(v[0] for v in prof.values())
+            gemm_ms, gemm_n = prof.get("gemm_tcgen05", (0.0, 0))
+            peak, peak_src, hbm = measured_peaks()
+            flops = gemm_flops_per_forward(B) * reps
+            achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get("gemm_tcgen05_dram_bytes_per_launch")
+            result["roofline"] = {"kernel": "gemm_tcgen05_kernel (50 launches per forward)", "bound": "tensor", "achieved": achieved, "peak": peak,
+                                  "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                                  "flops_per_launch_avg": flops / max(gemm_n, 1), "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
+                                  "share_of_forward": gemm_ms / total_ms if total_ms else None,
+                                  "kernel_ms_per_forward": {k: v[0] / reps for k, v in sorted(prof.items())},
+                                  "whole_step_model_flops_frac": (value / world) * algorithmic_flops_per_graph_step() / 1e12 / peak}
+
+        # ---- the reference algorithm on this box's host cores (reported baseline, not the target) ----
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+            threads = os.cpu_count() or 1
+            times = cpu_reference_steps(state, batch, x_T, T, 3, 1, threads)
+            result["cpu_baseline"] = {"value": B * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port",
+                                      "sample": f"{len(times)} denoise steps x {B} graphs (of {T}); oracle port incl. the reference's Python multinomial loop"}
+
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -31,6 +31,8 @@ PROTOTYPES = {
     "seqdiff_abi_version": (_i, []),
     "seqdiff_last_error": (C.c_char_p, []),
     "seqdiff_launch_count": (_u64, []),
+    "seqdiff_profile_begin": (_i, [_vp]),
+    "seqdiff_profile_end": (_i, [C.c_char_p, _i, C.POINTER(C.c_float), C.POINTER(C.c_int), _i]),
     "seqdiff_model_create": (_i, [C.POINTER(SeqdiffConfig), _i, C.POINTER(_vp)]),
     "seqdiff_model_destroy": (_i, [_vp]),
     "seqdiff_model_set_tensor": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
@@ -74,6 +76,23 @@ def check(rc: int):
     if rc != 0:
         msg = lib().seqdiff_last_error()
         raise SeqdiffError(f"seqdiff error {rc}: {msg.decode() if msg else '?'}")
+
+
+def profile(fn, stream=None):
+    """Runs fn() with the library's event profiler on; returns {tag: (total_ms, launches)}."""
+    l = lib()
+    check(l.seqdiff_profile_begin(stream))
+    try:
+        fn()
+    finally:
+        cap, stride = 64, 48
+        tags = C.create_string_buffer(cap * stride)
+        ms = (C.c_float * cap)()
+        cnt = (C.c_int * cap)()
+        n = l.seqdiff_profile_end(tags, stride, ms, cnt, cap)
+    if n < 0:
+        raise SeqdiffError("profiler failed")
+    return {tags.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
 
 def ptr(t):

@@ -259,7 +259,7 @@ static int launch_attn_16(int B, int heads, int Lq, int Lk, const T* q, int ldq,
   }
   dim3 grid(ceil_div(Lq, BQ), heads, B);
   kfn<<<grid, BQ * 2, SM::kBytes, s>>>(q, ldq, k, ldk, v, ldv, E, P, mask, out, heads, Lq, Lk);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED(REL ? "attention_16_rel" : "attention_16_norel", s);
   return SEQDIFF_OK;
 }
 
@@ -359,7 +359,7 @@ int attention<float>(int B, int heads, int Lq, int Lk, const float* q, int ldq, 
   SD_CHECK(smem <= 48 * 1024, "fp32 attention: Lk too large");
   dim3 grid(ceil_div(Lq, 8), heads, B);
   attention_f32_kernel<<<grid, 256, smem, s>>>(q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, heads, Lq, Lk);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("attention_f32", s);
   return SEQDIFF_OK;
 }
 

@@ -31,6 +31,16 @@ int seqdiff_abi_version(void) { return SEQDIFF_ABI_VERSION; }
 const char* seqdiff_last_error(void) { return last_error(); }
 uint64_t seqdiff_launch_count(void) { return g_launches.load(); }
 
+int seqdiff_profile_begin(void* stream) {
+  SD_GUARD_BEGIN
+  return profile_begin(static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+int seqdiff_profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap) {
+  if (!tags || !ms || !counts || tag_stride < 8 || cap < 1) return -1;
+  return profile_end(tags, tag_stride, ms, counts, cap);
+}
+
 int seqdiff_model_create(const seqdiff_config_t* cfg, int device, seqdiff_model_t** out) {
   SD_GUARD_BEGIN
   SD_CHECK(cfg != nullptr && out != nullptr, "null argument");

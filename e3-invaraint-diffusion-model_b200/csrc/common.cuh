@@ -43,11 +43,15 @@ extern std::atomic<uint64_t> g_launches;
     if (_r != SEQDIFF_OK) return _r;  \
   } while (0)
 
-// every kernel launch goes through this so `gpu_launches` in bench.py is a count, not a guess
-#define SD_LAUNCH_CHECK()                                   \
-  do {                                                      \
+// every kernel launch goes through this so `gpu_launches` in bench.py is a count, not a guess; with the
+// event profiler on (seqdiff_profile_begin) it also drops a CUDA event behind the kernel on its stream.
+void profile_mark(const char* tag, cudaStream_t s);
+extern bool g_profiling;
+#define SD_LAUNCHED(tag, stream)                                   \
+  do {                                                             \
     ::seqdiff::g_launches.fetch_add(1, std::memory_order_relaxed); \
-    SD_CUDA(cudaGetLastError());                            \
+    SD_CUDA(cudaGetLastError());                                   \
+    if (::seqdiff::g_profiling) ::seqdiff::profile_mark(tag, stream); \
   } while (0)
 
 typedef __nv_bfloat16 bf16;
@@ -135,19 +139,29 @@ template <> __device__ __forceinline__ void store8<f16>(f16* p, const float (&v)
 
 // exact-erf GELU (nn.GELU() / HF "gelu": model.py:43,133) and SiLU
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// bf16-mode GELU: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16 resolution) so the
-// tcgen05 GEMM epilogue is not issue-bound on the libdevice erff polynomial.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 16-bit-mode GELU for the tcgen05 GEMM epilogue.  erf by Abramowitz-Stegun 7.1.25 (|err| <= 2.5e-5, an order of
+// magnitude below fp16 output resolution), folded so one element costs ~11 issue slots (2 of them MUFU):
+//   gelu(x) = max(x,0) - 0.5|x| (a1 t + a2 t^2 + a3 t^3) exp(-x^2/2),   t = 1 / (1 + p |x| / sqrt2)
+// (the libdevice erff path costs ~35 and made the epilogue, not the MMA, the bound of the GELU GEMMs).
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(ax, 0.33267254f, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, 0.3739278f, -0.0479399f), 0.1740121f);  // a_i / 2
+  const float e = ex2_approx(x * x * -0.72134752f);                              // exp(-x^2/2)
+  return fmaf(-ax * poly, e, fmaxf(x, 0.0f));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.0f + ex2_approx(x * -1.44269504f)); }
 
 // ---- PTX: shared-memory addresses, mbarrier ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

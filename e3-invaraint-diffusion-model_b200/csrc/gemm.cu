@@ -112,8 +112,18 @@ template <int BN> struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two: 256 / 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 32 * 32 * 4;  // one 32x32 fp32 transpose panel per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
+
+template <typename T> __device__ __forceinline__ void store4(T* p, const float4& v);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const float4& v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+template <> __device__ __forceinline__ void store4<f16>(f16* p, const float4& v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+}
 
 // TOut: bf16 / f16 (operand for the next GEMM or attention) or float (LayerNorm input); resid is always fp32.
 template <int BN, int EPI, bool RESID, typename TOut>
@@ -210,56 +220,58 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------- epilogue -----------------------------------
+    // Accumulators arrive one TMEM lane (= output row) per thread.  Each 32x32 chunk is transposed through a
+    // per-warp smem panel (128 B rows, 16 B chunks XOR-swizzled by row&7: conflict-free both ways) so that
+    // bias / activation / residual / store run with 8 lanes per row segment: every global instruction touches
+    // 4 cache lines instead of 32, bias is one float4 per chunk, and the fp32 residual is prefetched before the
+    // TMEM load is waited on.
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // column half of the tile
+    float* stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes + 256) + (warp - 2) * 1024;
+    const int lr = lane >> 3, lc = lane & 7;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const int row = m_blk * kBM + q * 32 + lane;
-      const bool row_ok = row < M;
+      const int row_base = m_blk * kBM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      bool waited = false;
 #pragma unroll 1
       for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+        const int col = n_blk * BN + c + 4 * lc;
+        float4 rres[8];
+        if (RESID) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + 4 * i + lr;
+            rres[i] = row < M ? __ldg(reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * N + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+        if (!waited) {
+          mbar_wait(&tfull_bar[as], aphase);
+          tc_fence_after();
+          waited = true;
+        }
         uint32_t r[32];
         tmem_ld_32x32(t_row + static_cast<uint32_t>(c), r);
         tmem_ld_wait();
-        const int col0 = n_blk * BN + c;
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-          v[j] = __uint_as_float(r[j]) + b4.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + lr;
+          float4 v = *reinterpret_cast<const float4*>(stage + rr * 32 + ((lc ^ (rr & 7)) << 2));
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (EPI == 1) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
+          if (EPI == 2) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
+          if (RESID) { v.x += rres[i].x; v.y += rres[i].y; v.z += rres[i].z; v.w += rres[i].w; }
+          const int row = row_base + rr;
+          if (row < M) store4<TOut>(C + static_cast<size_t>(row) * N + col, v);
         }
-        if (EPI == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-        } else if (EPI == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
-        }
-        if (row_ok) {
-          const size_t off = static_cast<size_t>(row) * N + col0;
-          if (RESID) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float rr[8];
-              load8<float>(resid + off + j, rr);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) v[j + t] += rr[t];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const float o8[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
-            store8<TOut>(C + off + j, o8);
-          }
-        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -289,23 +301,16 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* 
   const int tiles = ceil_div(M, kBM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K, idesc);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("gemm_tcgen05", s);
   return SEQDIFF_OK;
 }
 
-// tile-width choice: the widest tile whose wave quantisation does not cost more than it saves.
+// tile-width choice.  Measured on B200 (scripts/gemm_sweep.py, round 1): the mainloop is bound by L2->SM operand
+// traffic, so the 128x256 tile (48 KB of operands per 128x256x64 MACs) beats 128x128 (32 KB per half the MACs) on
+// every shape of this model even where it quantises worse; 128-wide only serves N % 256 != 0 or tiny M.
 static int pick_bn(int M, int N) {
   if (N % 256 != 0) return 128;
-  const int sms = num_sms();
-  const int m_tiles = ceil_div(M, kBM);
-  auto waves_eff = [&](int bn) {
-    const int tiles = m_tiles * (N / bn);
-    const int waves = ceil_div(tiles, sms);
-    return static_cast<double>(tiles) / (static_cast<double>(waves) * sms);
-  };
-  // 128-wide tiles are SMEM-bandwidth marginal (8 KB operands per 64 MMA cycles); prefer 256 unless
-  // quantisation makes it clearly worse.
-  return (waves_eff(256) + 0.08 >= waves_eff(128)) ? 256 : 128;
+  return M > 64 ? 256 : 128;
 }
 
 template <int BN>
@@ -424,7 +429,7 @@ int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* b
     set_error("unknown GEMM epilogue");
     return SEQDIFF_ERR_INVALID;
   }
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("gemm_f32", s);
   return SEQDIFF_OK;
 }
 

@@ -10,6 +10,7 @@
 // fp32 (parity mode); LayerNorm statistics, softmax, biases and logits are always fp32.
 #include "model.cuh"
 
+#include <cstdio>
 #include <cstring>
 #include <type_traits>
 
@@ -19,6 +20,57 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
 std::atomic<uint64_t> g_launches{0};
+
+// ---- event profiler: one CUDA event behind every tagged launch; durations = gaps between consecutive events of
+// one stream (kernels of a stream run back to back).  Used by bench.py for the live roofline numbers.
+bool g_profiling = false;
+struct ProfMark { const char* tag; cudaEvent_t ev; cudaStream_t s; };
+static std::vector<ProfMark> g_marks;
+void profile_mark(const char* tag, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;  // not inside graph capture
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, s);
+  g_marks.push_back({tag, ev, s});
+}
+int profile_begin(cudaStream_t s) {
+  for (auto& m : g_marks) cudaEventDestroy(m.ev);
+  g_marks.clear();
+  g_profiling = true;
+  profile_mark("__begin__", s);
+  return SEQDIFF_OK;
+}
+// writes up to `cap` records "tag" / total ms / launch count (aggregated per tag); returns the number of tags
+int profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap) {
+  g_profiling = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  std::map<std::string, std::pair<double, int>> agg;
+  std::map<cudaStream_t, cudaEvent_t> prev;
+  for (auto& m : g_marks) {
+    auto it = prev.find(m.s);
+    if (it != prev.end() && std::string(m.tag) != "__begin__") {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, it->second, m.ev) == cudaSuccess) {
+        auto& a = agg[m.tag];
+        a.first += t;
+        a.second += 1;
+      }
+    }
+    prev[m.s] = m.ev;
+  }
+  int n = 0;
+  for (auto& kv : agg) {
+    if (n >= cap) break;
+    std::snprintf(tags + static_cast<size_t>(n) * tag_stride, tag_stride, "%s", kv.first.c_str());
+    ms[n] = static_cast<float>(kv.second.first);
+    counts[n] = kv.second.second;
+    ++n;
+  }
+  for (auto& m : g_marks) cudaEventDestroy(m.ev);
+  g_marks.clear();
+  return n;
+}
 
 int num_sms() {
   static int n = 0;
@@ -588,12 +640,14 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
     // un-captured dry run of the forward: sets kernel attributes and fills the TMA descriptor cache
     set_int_kernel<<<1, 1, 0, s>>>(d_step, T - 1);
-    SD_LAUNCH_CHECK();
+    SD_LAUNCHED("set_int", s);
     SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, s));
     SD_CUDA(cudaStreamSynchronize(s));
     cudaGraph_t graph = nullptr;
+    const uint64_t l0 = g_launches.load();
     SD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     const int rc = one_step(s);
+    graph_kernels = static_cast<int>(g_launches.load() - l0);  // kernel nodes per replay
     cudaError_t ce = cudaStreamEndCapture(s, &graph);
     if (rc != SEQDIFF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     SD_CUDA(ce);
@@ -603,8 +657,9 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
     graph_key = key;
   }
   set_int_kernel<<<1, 1, 0, s>>>(d_step, T - 1);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("set_int", s);
   for (int it = 0; it < T; ++it) SD_CUDA(cudaGraphLaunch(graph_exec, s));
+  g_launches.fetch_add(static_cast<uint64_t>(T) * graph_kernels, std::memory_order_relaxed);  // replayed kernel nodes
   SD_CUDA(cudaMemcpyAsync(final_out, logits, Nl * 20 * 4, cudaMemcpyDefault, s));
   // ... and the caller's stream continues only after the loop has finished
   SD_CUDA(cudaEventRecord(ev_out, s));

@@ -49,6 +49,9 @@ struct Segment {  // a run of graphs sharing one padded length inside a token ma
   const float* mask;
 };
 
+int profile_begin(cudaStream_t s);
+int profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap);
+
 struct Model {
   seqdiff_config_t cfg{};
   int device = 0;
@@ -77,6 +80,7 @@ struct Model {
   uint8_t* samp_in = nullptr;  // persistent copies of the loop inputs + x_t + logits
   size_t samp_in_bytes = 0;
   cudaGraphExec_t graph_exec = nullptr;
+  int graph_kernels = 0;
   cudaStream_t loop_stream = nullptr;  // private stream: graphs cannot be captured on the legacy default stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   struct GraphKey {

@@ -205,7 +205,7 @@ int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_
   SD_CHECK(n_tab == 1 || n_tab == B, "q_tables must hold 1 or B (Qt,Qsb,Qtb) triples");
   reverse_step_kernel<<<B, kRevThreads, 0, s>>>(q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr,
                                                 x_s, idx_out);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("reverse_step", s);
   return SEQDIFF_OK;
 }
 
@@ -258,7 +258,7 @@ int apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float*
                    uint32_t step, float* x_t, uint8_t* idx_out, cudaStream_t s) {
   SD_CHECK(B > 0 && L > 0, "empty q-sample");
   apply_aa_noise_kernel<<<B, kRevThreads, 0, s>>>(qtb, L, x0, noise_E, seed, graph_id0, step, x_t, idx_out);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("apply_aa_noise", s);
   return SEQDIFF_OK;
 }
 
@@ -272,7 +272,7 @@ __global__ void philox_u32_kernel(uint64_t seed, uint64_t graph_id0, uint32_t st
 }
 int philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, cudaStream_t s) {
   philox_u32_kernel<<<B, 128, 0, s>>>(seed, graph_id0, step, L, out);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("philox_u32", s);
   return SEQDIFF_OK;
 }
 

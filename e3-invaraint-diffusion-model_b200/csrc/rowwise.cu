@@ -57,7 +57,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ timestep, const 
 int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, cudaStream_t s) {
   const int n = B * (H / 2);
   timestep_embed_kernel<<<ceil_div(n, 128), 128, 0, s>>>(timestep, step_ptr, W, B, H, out);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("timestep_embed", s);
   return SEQDIFF_OK;
 }
 
@@ -144,7 +144,7 @@ int embed_ln(const float* x, int M, int fin, const float* Wt, const float* b, co
   const int warps = ceil_div(M, 4);
   const int grid = ceil_div(warps * 32, kRowThreads);
   SD_VPL_DISPATCH(H, embed_ln_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(x, M, fin, Wt, b, lnw, lnb, eps, te, L, H, out32, outT));
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("embed_ln", s);
   return SEQDIFF_OK;
 }
 #define SD_INST_EMBED(T) \
@@ -181,7 +181,7 @@ template <typename T>
 int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, cudaStream_t s) {
   const int grid = ceil_div(M * 32, kRowThreads);
   SD_VPL_DISPATCH(H, layernorm_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(in, M, H, w, b, eps, out32, outT));
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("layernorm", s);
   return SEQDIFF_OK;
 }
 #define SD_INST_LN(T) template int layernorm<T>(const float*, int, int, const float*, const float*, float, float*, T*, cudaStream_t)
@@ -242,7 +242,7 @@ int ln_modulate(const float* in, int M, int H, bool affine_first, const float* l
   } else {
     SD_VPL_DISPATCH(H, ln_modulate_kernel<T, VPL, false><<<grid, kRowThreads, 0, s>>>(in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT));
   }
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("ln_modulate", s);
   return SEQDIFF_OK;
 }
 #define SD_INST_LNMOD(T) \
@@ -297,7 +297,7 @@ int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb,
   SD_CHECK(F <= 32, "feature_size > 32 not supported");
   const int grid = ceil_div(M * 32, kRowThreads);
   SD_VPL_DISPATCH(H, predictor_tail_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(y, M, H, lnw, lnb, eps, W2, b2, F, logits));
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("predictor_tail", s);
   return SEQDIFF_OK;
 }
 template int predictor_tail<float>(const float*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t);
@@ -317,7 +317,7 @@ int f32_to_16(const float* in, size_t n, T* out, cudaStream_t s) {
   size_t blocks = (n + 255) / 256;
   if (blocks > 4096) blocks = 4096;
   f32_to_16_kernel<T><<<static_cast<int>(blocks), 256, 0, s>>>(in, n, out);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("f32_to_16", s);
   return SEQDIFF_OK;
 }
 template int f32_to_16<bf16>(const float*, size_t, bf16*, cudaStream_t);
@@ -331,14 +331,14 @@ __global__ void transpose_f32_kernel(const float* __restrict__ in, int rows, int
 }
 int transpose_f32(const float* in, int rows, int cols, float* out, cudaStream_t s) {
   transpose_f32_kernel<<<ceil_div(rows * cols, 256), 256, 0, s>>>(in, rows, cols, out);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("transpose_f32", s);
   return SEQDIFF_OK;
 }
 
 __global__ void step_advance_kernel(int* p) { *p -= 1; }
 int step_advance(int* step_ptr, cudaStream_t s) {
   step_advance_kernel<<<1, 1, 0, s>>>(step_ptr);
-  SD_LAUNCH_CHECK();
+  SD_LAUNCHED("step_advance", s);
   return SEQDIFF_OK;
 }
 

@@ -70,6 +70,12 @@ SEQDIFF_API const char* seqdiff_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
 SEQDIFF_API uint64_t seqdiff_launch_count(void);
 
+/* built-in event profiler (bench.py roofline numbers): between begin and end every kernel this library
+ * launches OUTSIDE graph capture is followed by a CUDA event on its stream; end() synchronises the device and
+ * returns per-kernel-tag totals: tags[i*tag_stride..] (NUL-terminated), ms[i], counts[i]; result = #tags or <0. */
+SEQDIFF_API int seqdiff_profile_begin(void* stream);
+SEQDIFF_API int seqdiff_profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap);
+
 /* ---- model handle: replaces ConditionalBertForDiffusionBase.__init__ + load_state_dict ---------
  * sequence_model/model.py:156-181, sample.py:106.  Tensor names are the reference state_dict keys
  * (SURVEY.md Appendix B), e.g. "decoder.layer.0.attention.self.query.weight"; data is fp32. */
