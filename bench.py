@@ -33,16 +33,26 @@ import torch  # noqa: E402
 
 METRIC = "denoiser graph-steps/s (forward + reverse-diffusion step per pocket graph; cfg2: 64 pockets x 500 steps, L=128)"
 UNIT = "graph-steps/s"
-L, H, I, NL = 128, 768, 1024, 6
+H, I, NL = 768, 1024, 6
+L = 128  # set by the workload in main()
+# algorithmic FLOPs per graph-step and the reference's own sizes per workload
+WORKLOADS = {
+    "cfg2": dict(L=128, T=500, batch=64, scaling="weak", n_lig=(5, 64), n_rec=(16, 128), flops=18.369e9,
+                 text="BASELINE configs[1]: full reverse-diffusion sampling (T={T}) of {B} synthetic pockets per GPU, L=128, ragged "
+                      "n_lig~U[5,64] n_rec~U[16,128], diverse=True, random-init weights, relative_key attention"),
+    "cfg3": dict(L=512, T=50, batch=256, scaling="strong", n_lig=(48, 48), n_rec=(464, 464), flops=85.229e9,
+                 text="BASELINE configs[2]: ext-neighbour pockets, 256 graphs of 512 residues (n_lig=48, n_rec=464) sharded over the GPUs, "
+                      "T={T} (reference default), {B} graphs on this rank, diverse=True, random-init weights"),
+}
 
 
 # ----------------------------------------------------------------------------------------------------
-def synthetic_workload(B, seed_offset=0):
+def synthetic_workload(B, seed_offset=0, n_lig=(5, 64), n_rec=(16, 128)):
     """SURVEY.md section 8d cfg 2: n_lig ~ U{5..64}, n_rec ~ U{16..128} (seed 3), angles ~ U(-pi, pi), zero padding,
     prefix-ones masks; x_T one-hot of randint (seed 4).  Plain torch on the host -- no oracle import here."""
     g = torch.Generator().manual_seed(3 + seed_offset)
-    nl = torch.randint(5, 65, (B,), generator=g)
-    nr = torch.randint(16, 129, (B,), generator=g)
+    nl = torch.randint(n_lig[0], n_lig[1] + 1, (B,), generator=g)
+    nr = torch.randint(n_rec[0], n_rec[1] + 1, (B,), generator=g)
     pos = torch.arange(L)[None, :]
     lm, rm = (pos < nl[:, None]).float(), (pos < nr[:, None]).float()
 
@@ -72,8 +82,6 @@ def gemm_flops_per_forward(B):
     return 2 * macs
 
 
-def algorithmic_flops_per_graph_step():
-    return 18.369e9  # BASELINE.md section 3, L=128 (incl. attention)
 
 
 class ClockSampler:
@@ -165,7 +173,9 @@ def run_reference_arm(args):
     common = dict(max_position_embeddings=L, intermediate_size=I, num_hidden_layers=NL, position_embedding_type="relative_key")
     model = sd.ConditionalBertForDiffusionBase(sd.BertConfig(**common), sd.BertConfig(**common, is_decoder=True, add_cross_attention=True), 20)
     state = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    batch, x_T = synthetic_workload(args.batch)
+    cpu_b = args.batch if args.workload == "cfg2" else 4  # L=512: a 4-graph sample keeps a step at a few seconds
+    batch, x_T = synthetic_workload(cpu_b, n_lig=args.wl["n_lig"], n_rec=args.wl["n_rec"])
+    args.batch = cpu_b
     threads = os.cpu_count() or 1
     times = cpu_reference_steps(state, batch, x_T, args.timesteps, args.steps, args.warmup, threads)
     total = sum(times)
@@ -173,7 +183,7 @@ def run_reference_arm(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"cfg2 sample: one denoise step (forward + reverse step) of the {args.batch}-pocket batch per bench step",
+           "config": {"workload": f"{args.workload} sample: one denoise step (forward + reverse step) of a {args.batch}-pocket batch per bench step",
                       "batch": args.batch, "L": L, "timesteps": args.timesteps, "device": "host CPU"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"{len(times)} denoise steps x {args.batch} graphs (of {args.timesteps} steps); oracle port incl. the reference's Python multinomial loop"},
@@ -189,12 +199,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="pocket graphs per GPU")
-    ap.add_argument("--timesteps", type=int, default=500, help="T (500 = the named config; smaller only for profiling runs)")
+    ap.add_argument("--batch", type=int, default=0, help="pocket graphs per GPU (default: the workload's)")
+    ap.add_argument("--timesteps", type=int, default=0, help="T (default: the workload's; smaller only for profiling runs)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"], help="cfg2 = headline (B=64/GPU, L=128); cfg3 = 256 ext-pockets of 512 residues sharded over the GPUs (strong scaling)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / roofline / cpu legs (profiling runs)")
     args = ap.parse_args()
+    global L
+    wl = WORKLOADS[args.workload]
+    L = wl["L"]
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if not args.batch:
+        args.batch = wl["batch"] if wl["scaling"] == "weak" else max(1, wl["batch"] // world_env)
+    if not args.timesteps:
+        args.timesteps = wl["T"]
+    args.wl = wl
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -223,7 +243,7 @@ def main():
     model.precision = args.precision
     sched = sd.PredefinedNoiseScheduleDiscrete("cosine", T)
     trans = sd.BlosumTransition(x_classes=20, timestep=500)
-    batch, x_T = synthetic_workload(B, seed_offset=1000 * rank)
+    batch, x_T = synthetic_workload(B, seed_offset=1000 * rank, n_lig=wl["n_lig"], n_rec=wl["n_rec"])
     gid0 = rank * B  # global graph ids key the Philox noise: results do not depend on the sharding
     dbatch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
     dx_T = x_T.to(dev)
@@ -258,12 +278,11 @@ def main():
     assert torch.isfinite(out).all()
 
     result = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-              "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+              "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": args.precision,
               "data": "synthetic",
-              "config": {"workload": f"BASELINE configs[1]: full reverse-diffusion sampling (T={T}) of {B} synthetic pockets per GPU, L={L}, "
-                                     f"ragged n_lig~U[5,64] n_rec~U[16,128], diverse=True, random-init weights, relative_key attention",
+              "config": {"workload": wl["text"].format(T=T, B=B),
                          "batch_per_gpu": B, "L": L, "timesteps": T, "sharding": f"graphs x{world} (no data-path collective)",
-                         "l2": "per-step working set ~0.9 GB of activations >> 126 MB L2 (no explicit flush needed)",
+                         "l2": "per-step working set of activations (0.9 GB at cfg2, ~10 GB at cfg3) >> 126 MB L2 (no explicit flush needed)",
                          "pocket_graphs_per_s": value / T, "edge_msgs_per_s": value * 15 * L * L},
               "clocks": clk.summary(), "gpu_launches": int(launches)}
 
@@ -314,15 +333,45 @@ def main():
                                   "flops_per_launch_avg": flops / max(gemm_n, 1), "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
                                   "share_of_forward": gemm_ms / total_ms if total_ms else None,
                                   "kernel_ms_per_forward": {k: v[0] / reps for k, v in sorted(prof.items())},
-                                  "whole_step_model_flops_frac": (value / world) * algorithmic_flops_per_graph_step() / 1e12 / peak}
+                                  "whole_step_model_flops_frac": (value / world) * wl["flops"] / 1e12 / peak}
+            # ---- the HBM-bound kernel of the path: reverse step at a size that streams (256 graphs x 512 residues) ----
+            RB, RL = 256, 512
+            rx = torch.nn.functional.one_hot(torch.randint(0, 20, (RB, RL), device=dev), 20).float()
+            rlg = torch.randn(RB, RL, 20, device=dev)
+            rs = torch.full((RB, 1), float(T // 2))
+            call = lambda: sd.sample_p_zs_given_zt_discrete((rs + 1) / T, rs / T, rx, rlg, sched, trans, True, False)
+            for _ in range(3):
+                call()
+            tabs = sd.utils.step_tables((rs + 1) / T, rs / T, sched, trans).to(dev)
+            import ctypes
+            rout = torch.empty_like(rx)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            p = sd._cabi.ptr
+            raw = lambda: lib.seqdiff_reverse_step(p(tabs), RB, RB, RL, p(rx), p(rlg), 1, None, 5, 0, 1, p(rout), None, stream)
+            for _ in range(3):
+                raw()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            r0.record()
+            for _ in range(50):
+                raw()
+            r1.record()
+            torch.cuda.synchronize(dev)
+            rus = r0.elapsed_time(r1) / 50 * 1e3
+            rbytes = RB * RL * 240
+            result["reverse_step_roofline"] = {"kernel": "reverse_step_kernel", "bound": "hbm", "residues": RB * RL, "bytes_per_residue": 240,
+                                               "avg_launch_us": rus, "achieved": rbytes / rus / 1e3, "peak": hbm, "unit": "GB/s",
+                                               "frac": rbytes / rus / 1e3 / hbm, "note": "31 MB per launch fits L2 (126 MB): back-to-back launches re-hit L2, so this is an upper bound on the HBM-resident rate"}
 
         # ---- the reference algorithm on this box's host cores (reported baseline, not the target) ----
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
             threads = os.cpu_count() or 1
-            times = cpu_reference_steps(state, batch, x_T, T, 3, 1, threads)
-            result["cpu_baseline"] = {"value": B * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port",
-                                      "sample": f"{len(times)} denoise steps x {B} graphs (of {T}); oracle port incl. the reference's Python multinomial loop"}
+            cb = B if args.workload == "cfg2" else 4
+            cbatch = {k: (v[:cb] if torch.is_tensor(v) else v) for k, v in batch.items()}
+            times = cpu_reference_steps(state, cbatch, x_T[:cb], T, 3, 1, threads)
+            result["cpu_baseline"] = {"value": cb * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port",
+                                      "sample": f"{len(times)} denoise steps x {cb} graphs (of {T}); oracle port incl. the reference's Python multinomial loop"}
 
     if rank == 0:
         print(json.dumps(result))

@@ -6,7 +6,8 @@ The directory name contains '-', so import it with
     importlib.import_module("e3-invaraint-diffusion-model_b200")
 or through the root-level alias module `seqdiff_b200`.
 """
-from . import _cabi, distributed, model, sample, utils  # noqa: F401
+from . import _cabi, dataset, distributed, model, sample, utils  # noqa: F401
+from .dataset import LigandBindingSiteDataset, collate_complexes  # noqa: F401
 from ._cabi import SeqdiffError, lib  # noqa: F401
 from .distributed import denoise_sharded, shard_batch, shard_bounds  # noqa: F401
 from .model import AA_VOCAB, BertConfig, ConditionalBertForDiffusionBase, PeptideDiff  # noqa: F401

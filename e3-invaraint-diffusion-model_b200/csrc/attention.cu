@@ -13,6 +13,8 @@
 // in a per-warp fp32 smem panel and added to S along the skewed diagonal j = l_local - r_local + 127
 // (the "skewing" step; accumulator fragments cannot be shifted in registers).
 // fp32 kernel (parity mode): one warp per query row, straight loops.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -269,7 +271,10 @@ static int attention_16(int B, int heads, int Lq, int Lk, const T* q, int ldq, c
   SD_CHECK(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "empty attention");
   SD_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "row strides must be multiples of 8 elements");
   SD_CHECK(!dist_emb || (Lq <= P && Lk <= P), "sequence longer than max_position_embeddings");
-  const bool small = Lq <= 64;
+  // BQ = 64 (4 warps, ~101 KB smem) lets two CTAs share an SM so one CTA's cp.async fill overlaps the other's MMAs;
+  // BQ = 128 halves the K/V/E re-reads.  SEQDIFF_ATTN_BQ overrides the choice (tuning knob).
+  static const int forced_bq = [] { const char* e = getenv("SEQDIFF_ATTN_BQ"); return e ? atoi(e) : 0; }();
+  const bool small = forced_bq ? forced_bq == 64 : Lq <= 64;
   if (dist_emb) {
     return small ? launch_attn_16<T, true, 64>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s)
                  : launch_attn_16<T, true, 128>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);

@@ -115,6 +115,20 @@ int seqdiff_apply_aa_noise(const float* qtb, int B, int L, const float* x0, cons
   SD_GUARD_END
 }
 
+int seqdiff_collate(int G, const int32_t* node_offsets, const uint8_t* ligand_mask, const uint8_t* pocket_mask,
+                    const float* angle_features, const float* amino_acid, int pocket_ext, int max_len, float* ligand_angles,
+                    float* ligand_seq, float* ligand_attn_mask, float* receptor_angles, float* receptor_seq, float* receptor_attn_mask,
+                    int32_t* lengths, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(node_offsets && ligand_mask && pocket_mask && angle_features && amino_acid && ligand_angles && ligand_seq && ligand_attn_mask &&
+               receptor_angles && receptor_seq && receptor_attn_mask && lengths,
+           "null argument");
+  SD_CHECK(pocket_ext >= 0, "pocket_ext must be >= 0");
+  return collate(G, node_offsets, ligand_mask, pocket_mask, angle_features, amino_acid, pocket_ext, max_len, ligand_angles, ligand_seq,
+                 ligand_attn_mask, receptor_angles, receptor_seq, receptor_attn_mask, lengths, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
 int seqdiff_sample(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, int T, const float* q_tables_steps,
                    const float* x_T, const float* ligand_angle, const float* ligand_mask, const float* receptor_seq,
                    const float* receptor_angle, const float* receptor_mask, int diverse, const float* noise_E_steps,

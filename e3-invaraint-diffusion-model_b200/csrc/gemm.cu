@@ -107,11 +107,11 @@ constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit inputs
 constexpr int kGemmThreads = 320;
 
 template <int BN> struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two: 256 / 512)
+  static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // two accumulator stages, rounded up to a power of two
   static constexpr int kStagingBytes = 8 * 32 * 32 * 4;  // one 32x32 fp32 transpose panel per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
@@ -306,11 +306,22 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* 
 }
 
 // tile-width choice.  Measured on B200 (scripts/gemm_sweep.py, round 1): the mainloop is bound by L2->SM operand
-// traffic, so the 128x256 tile (48 KB of operands per 128x256x64 MACs) beats 128x128 (32 KB per half the MACs) on
-// every shape of this model even where it quantises worse; 128-wide only serves N % 256 != 0 or tiny M.
+// traffic, so wide tiles win (128x256: 48 KB of operands per 128x256x64 MACs; 128x128: 32 KB per half the MACs).
+// 128x192 exists for wave quantisation: N = 768 at M = 8192 is 192 tiles of 128x256 (2 waves at 65 % fill on 148 SMs)
+// but 256 tiles of 128x192 (2 waves of 3/4-size tiles).  Cost model: waves x tile time, ties to the wider tile.
 static int pick_bn(int M, int N) {
-  if (N % 256 != 0) return 128;
-  return M > 64 ? 256 : 128;
+  if (M <= 64) return 128;
+  const int sms = num_sms();
+  const int m_tiles = ceil_div(M, kBM);
+  int best = 0;
+  double best_cost = 0;
+  for (int bn : {256, 192, 128}) {
+    if (N % bn) continue;
+    const int waves = ceil_div(m_tiles * (N / bn), sms);
+    const double cost = waves * bn * (1.0 + 48.0 / bn);  // per-tile time ~ bn, with a bandwidth penalty for narrow tiles
+    if (!best || cost < best_cost * 0.97) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 
 template <int BN>
@@ -342,12 +353,13 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
   // measured on B200: tcgen05.mma.kind::f16 with a_format != b_format faults as an illegal instruction
   SD_CHECK(a_fmt == w_fmt, "A and W must share one 16-bit format");
   const int bn = force_bn ? force_bn : pick_bn(M, N);
-  SD_CHECK(bn == 128 || (bn == 256 && N % 256 == 0), "bad tile width");
+  SD_CHECK((bn == 128 || bn == 192 || bn == 256) && N % bn == 0, "bad tile width");
   CUtensorMap ta, tb;
   SD_TRY(make_tmap(A, a_fmt, M, K, kBM, &ta));
   SD_TRY(make_tmap(W, w_fmt, N, K, bn, &tb));
   const uint32_t idesc = umma_idesc_16(kBM, bn, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
   if (bn == 256) return dispatch_tc<256>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s);
+  if (bn == 192) return dispatch_tc<192>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s);
   return dispatch_tc<128>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s);
 }
 

@@ -47,6 +47,11 @@ template <typename T>
 int attention(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
               int P, const float* key_mask, T* out, cudaStream_t s);
 
+// ---- collate.cu ---------------------------------------------------------------------------------------
+// LigandBindingSiteDataset.__getitem__ for G ragged complexes (dataset.py:97-129); lengths[g] = (n_lig, n_rec) BEFORE clamping.
+int collate(int G, const int* offsets, const uint8_t* lig_mask, const uint8_t* poc_mask, const float* ang, const float* aa, int ext, int L,
+            float* lig_ang, float* lig_seq, float* lig_attn, float* rec_ang, float* rec_seq, float* rec_attn, int* lengths, cudaStream_t s);
+
 // ---- reverse_step.cu --------------------------------------------------------------------------------
 // step_ptr != NULL: tables/noise are indexed by *step_ptr (entry stride 1200 / N*20) and the launch is a
 // no-op when *step_ptr == 0 (last step returns the raw logits, sample.py:147-148).

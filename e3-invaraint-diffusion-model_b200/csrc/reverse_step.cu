@@ -87,9 +87,12 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
                                                                    uint64_t graph_id0, uint32_t step, const int* __restrict__ step_ptr,
                                                                    float* __restrict__ x_s, uint8_t* __restrict__ idx_out) {
   __shared__ float sQt[C * C], sQsb[C * C], sQtb[C * C];
-  __shared__ float sPost[C * C * C];  // [x][i][j]
-  const int b = blockIdx.x;
-  const size_t n_res = static_cast<size_t>(gridDim.x) * L;
+  // [x][i][j] with an odd x-stride: lanes holding different x_t classes then read 32 different banks (stride 400
+  // would fold all classes onto 2 banks -- measured 16-way conflicts, 567 GB/s)
+  constexpr int kXS = C * C + 1;
+  __shared__ float sPost[C * kXS];
+  const int b = blockIdx.y;  // grid = (ceil(L / 128) residue chunks, graphs): enough CTAs to stream at HBM rate
+  const size_t n_res = static_cast<size_t>(gridDim.y) * L;
   if (step_ptr) {
     const int sidx = *step_ptr;
     if (sidx == 0) return;  // last step: caller keeps the raw logits (sample.py:147-148)
@@ -108,11 +111,11 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
     const int x = e / (C * C), i = (e / C) % C, j = e % C;
     float den = sQtb[i * C + x];
     if (den == 0.f) den = 1e-6f;
-    sPost[e] = __fdiv_rn(__fmul_rn(sQt[j * C + x], sQsb[i * C + j]), den);
+    sPost[x * kXS + i * C + j] = __fdiv_rn(__fmul_rn(sQt[j * C + x], sQsb[i * C + j]), den);
   }
   __syncthreads();
 
-  for (int l = threadIdx.x; l < L; l += kRevThreads) {
+  for (int l = blockIdx.x * kRevThreads + threadIdx.x; l < L; l += gridDim.x * kRevThreads) {
     const size_t n = static_cast<size_t>(b) * L + l;
     float lg[C], xr[C];
 #pragma unroll
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
 #pragma unroll
     for (int j = 0; j < C; ++j) un[j] = 0.f;
     if (nnz == 1 && hot >= 0) {
-      const float* post = sPost + hot * (C * C);
+      const float* post = sPost + hot * kXS;
 #pragma unroll 4
       for (int i = 0; i < C; ++i) {
 #pragma unroll
@@ -203,7 +206,7 @@ int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_
                  uint8_t* idx_out, cudaStream_t s) {
   SD_CHECK(B > 0 && L > 0, "empty reverse step");
   SD_CHECK(n_tab == 1 || n_tab == B, "q_tables must hold 1 or B (Qt,Qsb,Qtb) triples");
-  reverse_step_kernel<<<B, kRevThreads, 0, s>>>(q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr,
+  reverse_step_kernel<<<dim3(ceil_div(L, kRevThreads), B), kRevThreads, 0, s>>>(q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr,
                                                 x_s, idx_out);
   SD_LAUNCHED("reverse_step", s);
   return SEQDIFF_OK;

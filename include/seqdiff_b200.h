@@ -109,6 +109,16 @@ SEQDIFF_API int seqdiff_reverse_step(const float* q_tables, int n_tab, int B, in
 SEQDIFF_API int seqdiff_apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float* noise_E, uint64_t seed,
                            uint64_t graph_id0, uint32_t step, float* x_t_out, uint8_t* idx_out, void* stream);
 
+/* ---- batch collation: replaces LigandBindingSiteDataset.__getitem__, sequence_model/dataset.py:97-129 ----------
+ * G complexes stored ragged: node_offsets [G+1] i32; ligand_mask, pocket_mask [total] u8; angle_features [total,8] f32;
+ * amino_acid [total,20] f32 one-hot.  Pocket mask dilated by exactly +-pocket_ext with torch.roll wrap-around semantics
+ * (quirk Q9), rows compacted in order, zero-padded to max_len; *_attn prefix-ones.  lengths [G,2] i32 = (n_lig, n_rec)
+ * before clamping: a value > max_len is the reference's RuntimeError("Length exceed") (raised by the host wrapper). */
+SEQDIFF_API int seqdiff_collate(int G, const int32_t* node_offsets, const uint8_t* ligand_mask, const uint8_t* pocket_mask,
+                    const float* angle_features, const float* amino_acid, int pocket_ext, int max_len, float* ligand_angles,
+                    float* ligand_seq, float* ligand_attn_mask, float* receptor_angles, float* receptor_seq,
+                    float* receptor_attn_mask, int32_t* lengths, void* stream);
+
 /* ---- whole reverse-diffusion loop: replaces the T-step loop of denoise(), sample.py:192-207 -------
  * q_tables_steps [T,3,20,20]: entry s holds (Qt,Qsb,Qtb) for the step s_int = s (t=(s+1)/T).
  * x_T [B,L_lig,20] one-hot start.  noise_E_steps [T,B*L_lig,20] (entry s used at step s; entry 0 unused)

@@ -204,6 +204,30 @@ def golden_apply_aa_noise():
                os.path.join(GOLDEN, "apply_aa_noise.pt"))
 
 
+def golden_dataset():
+    """reference LigandBindingSiteDataset.__getitem__ (dataset.py:81-129) on synthetic records, ext in {0,1,3}."""
+    R.load_reference()
+    ref_ds = sys.modules["_ref_seq_dataset"]
+    recs = O.synthetic_records(6, 41)
+    out = {}
+    for ext, max_len in ((0, 128), (1, 128), (3, 160)):
+        ds = ref_ds.LigandBindingSiteDataset.__new__(ref_ds.LigandBindingSiteDataset)
+        ds.data, ds.max_len, ds.pocket_ext = recs, max_len, ext
+        items = [ds[i] for i in range(len(recs))]
+        for i, it in enumerate(items):
+            o = O.dataset_item(recs[i], max_len, ext)
+            for k in ("ligand_angles", "ligand_attn_mask", "ligand_seq", "receptor_angles", "receptor_attn_mask", "receptor_seq"):
+                assert torch.equal(it[k], o[k]), (ext, i, k)
+            assert int(it["ligand_length"]) == int(o["ligand_length"]) and int(it["receptor_length"]) == int(o["receptor_length"])
+        out[(ext, max_len)] = {"ligand_length": torch.tensor([int(it["ligand_length"]) for it in items]),
+                               "receptor_length": torch.tensor([int(it["receptor_length"]) for it in items]),
+                               "receptor_seq_idx": torch.stack([it["receptor_seq"].argmax(-1).to(torch.uint8) for it in items]),
+                               "receptor_angle_sum": torch.stack([it["receptor_angles"].double().sum(-1) for it in items]),
+                               "ligand_seq_idx": torch.stack([it["ligand_seq"].argmax(-1).to(torch.uint8) for it in items])}
+    print("dataset items: oracle == reference for ext 0/1/3")
+    torch.save({"n_complex": 6, "seed": 41, "cases": out}, os.path.join(GOLDEN, "dataset_items.pt"))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
@@ -211,6 +235,7 @@ def main():
     golden_schedules()
     golden_reverse_step()
     golden_apply_aa_noise()
+    golden_dataset()
     golden_forward()
     golden_denoise()
     print("golden fixtures written to", os.path.normpath(GOLDEN))

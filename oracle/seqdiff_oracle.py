@@ -489,6 +489,53 @@ def elbo_loss(logits1, logits2, eps=1e-6):
 
 
 # --------------------------------------------------------------------------------------------
+# dataset item construction (sequence_model/dataset.py:41-49, 97-129) -- the "graph construction" analogue
+# --------------------------------------------------------------------------------------------
+def dataset_item(data: Dict, max_len: int, pocket_ext: int) -> Dict:
+    """LigandBindingSiteDataset.__getitem__, dataset.py:97-129."""
+    def pad(x):
+        if x.shape[0] > max_len:
+            raise RuntimeError("Length exceed")
+        return F.pad(x, (0, 0, 0, max_len - x.shape[0]), mode="constant", value=0)
+
+    ligand_mask = data["ligand_mask"]
+    left = torch.roll(data["pocket_mask"], pocket_ext)
+    left[0] = False
+    right = torch.roll(data["pocket_mask"], -pocket_ext)
+    right[-1] = False
+    pocket_mask = data["pocket_mask"] | left | right
+    lig_attn = torch.zeros(max_len)
+    lig_attn[:ligand_mask.sum()] = 1.0
+    rec_attn = torch.zeros(max_len)
+    rec_attn[:pocket_mask.sum()] = 1.0
+    return {"ligand_angles": pad(data["angle_features"][ligand_mask]), "ligand_attn_mask": lig_attn,
+            "ligand_seq": pad(data["amino_acid"][ligand_mask]), "receptor_angles": pad(data["angle_features"][pocket_mask]),
+            "receptor_attn_mask": rec_attn, "receptor_seq": pad(data["amino_acid"][pocket_mask]),
+            "ligand_length": ligand_mask.sum(), "receptor_length": pocket_mask.sum(), "structure_ids": data["structure_ids"]}
+
+
+def synthetic_records(n_complex: int, seed: int, n_lo: int = 40, n_hi: int = 260):
+    """records with the post-_load_file schema of the reference dataset (dataset.py:68-73): a contiguous ligand chain,
+    a sparse pocket on the other chain (incl. first/last residues so the wrap-around quirk Q9 is exercised)."""
+    g = torch.Generator().manual_seed(seed)
+    recs = []
+    for c in range(n_complex):
+        n = int(torch.randint(n_lo, n_hi + 1, (1,), generator=g))
+        nl = int(torch.randint(5, min(40, n // 2) + 1, (1,), generator=g))
+        start = int(torch.randint(0, n - nl + 1, (1,), generator=g))
+        lig = torch.zeros(n, dtype=torch.bool)
+        lig[start:start + nl] = True
+        poc = (torch.rand(n, generator=g) < 0.15) & ~lig
+        if c % 2 == 0:
+            poc[0] = poc[-1] = True  # wrap-around cases
+            poc &= ~lig
+        recs.append({"amino_acid": F.one_hot(torch.randint(0, 20, (n,), generator=g), 20).float(),
+                     "angle_features": (torch.rand(n, 8, generator=g) * 2 - 1) * math.pi, "ligand_mask": lig, "pocket_mask": poc,
+                     "structure_ids": {"pdb_id": f"c{c:03d}", "ligand_chain": "B"}})
+    return recs
+
+
+# --------------------------------------------------------------------------------------------
 # synthetic workloads (SURVEY.md section 8d)
 # --------------------------------------------------------------------------------------------
 def synthetic_batch(B: int, L: int, n_lig, n_rec, seed: int):

@@ -20,7 +20,7 @@ for name, cnt, M, N, K, epi, kind in SHAPES:
     bias = torch.randn(N, device=dev); resid = torch.randn(M, N, device=dev) if kind == "r" else None
     C = torch.empty(M, N, device=dev, dtype=torch.float32 if kind == "r" else torch.bfloat16)
     best = {}
-    for bn in (128, 256):
+    for bn in (128, 192, 256):
         if N % bn: continue
         def call():
             rc = lib.seqdiff_op_gemm(1 | (bn << 8), M, N, K, p(A), p(W), p(bias), p(resid), epi, p(C), stream)

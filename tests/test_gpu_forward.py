@@ -236,3 +236,22 @@ def test_sample_loop_equals_stepwise_calls():
     assert torch.equal(full, torch.cat(parts, 0))
     other = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T, seed=43, graph_id0=10)
     assert not torch.equal(full, other)
+
+
+@pytest.mark.parametrize("precision", MODES)
+def test_forward_cfg3_length_512(precision):
+    """BASELINE cfg 3 shape: max_seq_len 512 (distance_embedding [1023,64]), n_lig = 48, n_rec = 464 + a ragged graph;
+    4 key blocks per attention row (online softmax across blocks, E window moves with the block)."""
+    cfg, state, m = _model(512, True, 1, "B", precision, bf16_ckpt=(precision == "bf16"))
+    B = 2
+    batch = O.synthetic_batch(B, 512, 48, 464, 13)
+    rag = O.synthetic_batch(B, 512, (1, 512), (100, 512), 14)
+    for k in batch:
+        batch[k][1] = rag[k][1]
+    x_t = O.generate_discrete_noise(B, 512, generator=torch.Generator().manual_seed(6))
+    t = torch.tensor([[49.0], [7.0]])
+    args = (t, x_t, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"], batch["receptor_angles"], batch["receptor_attn_mask"])
+    with torch.no_grad():
+        want = O.denoiser_forward(state, cfg, *args)
+        got = m(*[a.to(DEV) for a in args])
+    check_logits(got, want, precision, "cfg3 L=512", bf16_ckpt=(precision == "bf16"))

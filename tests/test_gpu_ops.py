@@ -48,13 +48,15 @@ _TDT = {BF16: (torch.bfloat16, torch.bfloat16), FP16: (torch.float16, torch.floa
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("bn", [0, 128, 256])
+@pytest.mark.parametrize("bn", [0, 128, 192, 256])
 @pytest.mark.parametrize("mode", [BF16, FP16])
 def test_gemm_tcgen05(M, N, K, bn, mode):
     """tcgen05/TMA GEMM: 16-bit operands in each format mix; epilogues none/GELU/SiLU -> 16-bit out;
     fp32 residual add -> fp32 out (the LayerNorm-input variant)."""
     if mode != BF16 and (bn != 0 or M > 1024):
         pytest.skip("format variants share the tile code; checked at the auto tile width on the small shapes")
+    if bn and N % bn:
+        pytest.skip("tile width does not divide N")
     lib = sd_pkg().lib()
     adt, wdt = _TDT[mode]
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N + K + bn)
@@ -230,3 +232,50 @@ def test_apply_aa_noise_golden():
     assert_indices_match(out.argmax(-1), g["out_idx"], probs / g["E"], "apply_aa_noise")
     pad = g["x0_valid"] == 0
     assert (out.argmax(-1).cpu()[pad] == 0).all()  # padded rows -> class 0 (model.py:307-308)
+
+
+@pytest.mark.parametrize("ext,max_len", [(0, 128), (1, 128), (3, 160), (7, 512)])
+def test_collate_matches_reference_dataset(ext, max_len):
+    """seqdiff_collate == LigandBindingSiteDataset.__getitem__ (dataset.py:97-129), bit for bit: the golden values produced
+    by the reference class itself, and the oracle restatement on every item of a wider set (tiny and >256-residue complexes)."""
+    sd = sd_pkg()
+    recs = O.synthetic_records(6, 41)
+    g = torch.load(os.path.join(GOLDEN, "dataset_items.pt"), weights_only=False)
+    if (ext, max_len) in g["cases"]:
+        got = sd.collate_complexes(recs, max_len, ext, DEV)
+        want = g["cases"][(ext, max_len)]
+        assert torch.equal(got["receptor_seq"].argmax(-1).to(torch.uint8).cpu(), want["receptor_seq_idx"])
+        assert torch.equal(got["ligand_seq"].argmax(-1).to(torch.uint8).cpu(), want["ligand_seq_idx"])
+        assert torch.equal(got["receptor_angles"].double().sum(-1).cpu(), want["receptor_angle_sum"])
+        assert torch.equal(got["receptor_length"].long(), want["receptor_length"]) and torch.equal(got["ligand_length"].long(), want["ligand_length"])
+        assert got["structure_ids"]["pdb_id"][:2] == ["c000", "c001"]
+    recs = recs + O.synthetic_records(9, 5, n_lo=3, n_hi=700)
+    big = 512  # roomy enough for 700 residues x 15 % pocket x 3 (dilation)
+    got = sd.collate_complexes(recs, big, ext, DEV)
+    for i, r in enumerate(recs):
+        want = O.dataset_item(r, big, ext)
+        for k in ("ligand_angles", "ligand_seq", "ligand_attn_mask", "receptor_angles", "receptor_seq", "receptor_attn_mask"):
+            assert torch.equal(got[k][i].cpu(), want[k]), (i, k)
+        assert int(got["ligand_length"][i]) == int(want["ligand_length"]) and int(got["receptor_length"][i]) == int(want["receptor_length"])
+    with pytest.raises(RuntimeError, match="Length exceed"):  # dataset.py:42-43
+        sd.collate_complexes(recs, 8, ext, DEV)
+
+
+def test_reverse_step_cfg3_size_properties():
+    """BASELINE cfg 3 size (256 graphs x 512 residues): one-hot output, determinism, agreement with the oracle on a slice."""
+    sd = sd_pkg()
+    T, B, L = 50, 256, 512
+    g = torch.Generator().manual_seed(2)
+    x = F.one_hot(torch.randint(0, 20, (B, L), generator=g), 20).float().to(DEV)
+    logits = (torch.randn(B, L, 20, generator=g) * 3).to(DEV)
+    E = torch.empty(B * L, 20).exponential_(1, generator=g).to(DEV)
+    s = torch.full((B, 1), 31.0)
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    a = sd.sample_p_zs_given_zt_discrete((s + 1) / T, s / T, x, logits, sched, tr, True, False, noise_E=E)
+    b = sd.sample_p_zs_given_zt_discrete((s + 1) / T, s / T, x, logits, sched, tr, True, False, noise_E=E)
+    assert torch.equal(a, b) and torch.equal(a.sum(-1), torch.ones(B, L, device=DEV)) and ((a == 0) | (a == 1)).all()
+    sl = slice(100, 104)
+    want = O.reverse_step((s[sl] + 1) / T, s[sl] / T, x[sl].cpu(), logits[sl].cpu(), O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition(),
+                          True, False, E.view(B, L, 20)[sl].reshape(-1, 20).cpu())
+    prob = O.reverse_step_probs((s[sl] + 1) / T, s[sl] / T, x[sl].cpu(), logits[sl].cpu(), O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition())
+    assert_indices_match(a[sl].argmax(-1), want.argmax(-1), prob / E.view(B, L, 20)[sl].reshape(-1, 20).cpu(), "cfg3 slice")

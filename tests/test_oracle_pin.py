@@ -142,3 +142,20 @@ def test_reference_live_pin():
         yo = O.denoiser_forward(sd, cfg, t, x_t, b["ligand_angles"], b["ligand_attn_mask"], b["receptor_seq"], b["receptor_angles"],
                                 b["receptor_attn_mask"])
     assert (y - yo).abs().max().item() < 1e-5
+
+
+def test_dataset_item_golden():
+    """dataset.py:97-129 restatement against values produced by the reference class (ext 0/1/3, wrap-around quirk Q9)."""
+    g = _load("dataset_items.pt")
+    recs = O.synthetic_records(g["n_complex"], g["seed"])
+    for (ext, max_len), want in g["cases"].items():
+        items = [O.dataset_item(r, max_len, ext) for r in recs]
+        assert torch.equal(torch.tensor([int(i["ligand_length"]) for i in items]), want["ligand_length"])
+        assert torch.equal(torch.tensor([int(i["receptor_length"]) for i in items]), want["receptor_length"])
+        assert torch.equal(torch.stack([i["receptor_seq"].argmax(-1).to(torch.uint8) for i in items]), want["receptor_seq_idx"])
+        assert torch.equal(torch.stack([i["receptor_angles"].double().sum(-1) for i in items]), want["receptor_angle_sum"])
+        assert torch.equal(torch.stack([i["ligand_seq"].argmax(-1).to(torch.uint8) for i in items]), want["ligand_seq_idx"])
+    # ext > 0 really dilates, and only by exactly +-ext
+    assert (g["cases"][(1, 128)]["receptor_length"] >= g["cases"][(0, 128)]["receptor_length"]).all()
+    with pytest.raises(RuntimeError, match="Length exceed"):
+        O.dataset_item(recs[0], 4, 0)
