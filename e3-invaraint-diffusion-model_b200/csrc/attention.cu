@@ -339,15 +339,36 @@ static int attention_16(int B, int heads, int Lq, int Lk, const T* q, int ldq, c
   SD_ATTN(false);
 #undef SD_ATTN
 }
+// 16-bit modes: kernel choice per shape.  SEQDIFF_ATTN = tc | mma forces one implementation (A/B knob); default "auto":
+//   relative-key, one key block (L <= 128): legacy mma.sync kernel, two 100 KB CTAs per SM overlap fill and MMA (0.37 vs 0.43 ms
+//     per forward at cfg 2: the tcgen05 kernel holds S, Q.E^T and O in 448 TMEM columns, so only one CTA fits per SM and its
+//     MMA / softmax / PV phases do not overlap);
+//   everything else (cross-attention, several key blocks): tcgen05 kernel (attention_tc.cu).
+static int attn_choice() {
+  static const int v = [] {
+    const char* e = getenv("SEQDIFF_ATTN");
+    if (!e) return 0;
+    return std::string(e) == "tc" ? 1 : (std::string(e) == "mma" ? 2 : 0);
+  }();
+  return v;
+}
+template <typename T>
+static int attention_any16(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
+                           int P, const float* key_mask, T* out, cudaStream_t s) {
+  const int c = attn_choice();
+  const bool legacy = c == 2 || (c == 0 && dist_emb != nullptr && Lk <= kKB);
+  if (legacy) return attention_16<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  return attention_tc<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+}
 template <>
 int attention<bf16>(int B, int heads, int Lq, int Lk, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv,
                     const bf16* dist_emb, int P, const float* key_mask, bf16* out, cudaStream_t s) {
-  return attention_16<bf16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  return attention_any16<bf16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
 }
 template <>
 int attention<f16>(int B, int heads, int Lq, int Lk, const f16* q, int ldq, const f16* k, int ldk, const f16* v, int ldv,
                    const f16* dist_emb, int P, const float* key_mask, f16* out, cudaStream_t s) {
-  return attention_16<f16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  return attention_any16<f16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -63,7 +63,7 @@ struct TmapKeyHash {
 
 // row-major 16-bit matrix [rows, cols] (fmt 0 = fp16, 1 = bf16); tile = box_rows x 64 columns, 128B-swizzled,
 // OOB reads give zeros
-static int make_tmap(const void* ptr, int fmt, int rows, int cols, int box_rows, CUtensorMap* out) {
+int make_tmap(const void* ptr, int fmt, int rows, int cols, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey key{ptr, rows, cols, box_rows, fmt};

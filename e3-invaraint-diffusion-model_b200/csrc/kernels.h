@@ -14,6 +14,9 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
 int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* bias, const float* resid, int epi, float* C,
              cudaStream_t s);
 
+// TMA descriptor (cached) of a row-major 16-bit matrix [rows, cols]: boxes of box_rows x 64 columns, 128B swizzle, OOB -> 0
+int make_tmap(const void* ptr, int fmt, int rows, int cols, int box_rows, CUtensorMap* out);
+
 // ---- rowwise.cu -------------------------------------------------------------------------------------
 // GaussianFourierProjection (model.py:85-97): out[b, :] = [sin(x), cos(x)], x = ((t*W)*2)*pi in fp32.
 // t = timestep[b], or (float)*step_ptr for every b when step_ptr != NULL (sampling loop, quirk Q3).
@@ -51,6 +54,11 @@ int attention(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k,
 // LigandBindingSiteDataset.__getitem__ for G ragged complexes (dataset.py:97-129); lengths[g] = (n_lig, n_rec) BEFORE clamping.
 int collate(int G, const int* offsets, const uint8_t* lig_mask, const uint8_t* poc_mask, const float* ang, const float* aa, int ext, int L,
             float* lig_ang, float* lig_seq, float* lig_attn, float* rec_ang, float* rec_seq, float* rec_attn, int* lengths, cudaStream_t s);
+
+// ---- attention_tc.cu: tcgen05 attention (S, Q.E^T and P.V on UMMA, accumulators in TMEM) ------------------------------
+template <typename T>
+int attention_tc(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
+                 int P, const float* key_mask, T* out, cudaStream_t s);
 
 // ---- reverse_step.cu --------------------------------------------------------------------------------
 // step_ptr != NULL: tables/noise are indexed by *step_ptr (entry stride 1200 / N*20) and the launch is a

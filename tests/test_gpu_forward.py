@@ -183,8 +183,10 @@ def test_denoise_loop_golden(precision):
         assert rel_err(final, g["final_logits"]) < 1e-4  # 4 chained steps; any index flip would show as O(1)
     elif precision == "fp16":
         # 1e-3-level logit noise flips a sampled residue only at near-ties; if none flipped the strings are identical
+        # (padded query rows are sampled too, quirk Q4, and may fork on their own -- they feed nothing but themselves)
         if pred_seq == g["pred_sequences"]:
-            assert rel_err(final, g["final_logits"]) < 1e-2
+            valid = batch["ligand_attn_mask"].bool()
+            assert rel_err(final.cpu()[valid], g["final_logits"][valid]) < 1e-2
     else:
         # bf16 logits move the posterior slightly, so trajectories may legitimately fork; teacher-force instead
         x = x_T.clone()

@@ -103,6 +103,16 @@ ATTN_CASES = [
 ]
 
 
+def test_attention_both_16bit_kernels_subprocess():
+    """the per-shape dispatch hides one of the two 16-bit kernels for some shapes: run the op tests with each one forced."""
+    import subprocess, sys
+    for impl in ("tc", "mma"):
+        env = dict(os.environ, SEQDIFF_ATTN=impl)
+        r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "test_attention and not subprocess", "-p",
+                            "no:cacheprovider"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, f"SEQDIFF_ATTN={impl}:\n" + r.stdout[-2000:]
+
+
 @pytest.mark.parametrize("B,heads,Lq,Lk,P,rel", ATTN_CASES)
 @pytest.mark.parametrize("prec", [FP32, BF16, FP16])
 def test_attention(B, heads, Lq, Lk, P, rel, prec):
