@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(BQ * 2) attention_16_kernel(const T* __restric
   const T* qb = q + (static_cast<size_t>(b) * Lq) * ldq + h * 64;
   const T* kb_ = k + (static_cast<size_t>(b) * Lk) * ldk + h * 64;
   const T* vb = v + (static_cast<size_t>(b) * Lk) * ldv + h * 64;
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
 
   auto load_block = [&](int kb) {  // issues NG commit groups: {K (+Q on the first call)}, {E}, {V}
     const int k0 = kb * kKB;
@@ -316,7 +318,7 @@ static int launch_attn_16(int B, int heads, int Lq, int Lk, const T* q, int ldq,
     configured = true;
   }
   dim3 grid(ceil_div(Lq, BQ), heads, B);
-  kfn<<<grid, BQ * 2, SM::kBytes, s>>>(q, ldq, k, ldk, v, ldv, E, P, mask, out, heads, Lq, Lk);
+  SD_CUDA(launch_k(kfn, dim3(grid), dim3(BQ * 2), SM::kBytes, s, q, ldq, k, ldk, v, ldv, E, P, mask, out, heads, Lq, Lk));
   SD_LAUNCHED(REL ? "attention_16_rel" : "attention_16_norel", s);
   return SEQDIFF_OK;
 }
@@ -379,6 +381,8 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
                                                             const float* __restrict__ key_mask, float* __restrict__ out, int heads,
                                                             int Lq, int Lk) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sq = sm + warp * 64;
   float* sc = sm + 8 * 64 + warp * Lk;
@@ -441,7 +445,7 @@ int attention<float>(int B, int heads, int Lq, int Lk, const float* q, int ldq, 
   const size_t smem = (8 * 64 + 8 * static_cast<size_t>(Lk)) * sizeof(float);
   SD_CHECK(smem <= 48 * 1024, "fp32 attention: Lk too large");
   dim3 grid(ceil_div(Lq, 8), heads, B);
-  attention_f32_kernel<<<grid, 256, smem, s>>>(q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, heads, Lq, Lk);
+  SD_CUDA(launch_k(attention_f32_kernel, dim3(grid), dim3(256), smem, s, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, heads, Lq, Lk));
   SD_LAUNCHED("attention_f32", s);
   return SEQDIFF_OK;
 }

@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(kTcThreads, REL ? 1 : 2) attention_tc_kernel(c
     tmem_alloc(tmem_slot, SM::kTmemCols);
     tmem_relinquish();
   }
+  pdl_trigger();
+  pdl_wait();  // key_mask / q / k / v come from the predecessor kernels
   load_mask(0);
   tc_fence_before();
   __syncthreads();
@@ -282,7 +284,7 @@ static int launch_tc_attn(int B, int heads, int Lq, int Lk, const T* q, int ldq,
   if (REL) SD_TRY(make_tmap(E, fmt, 2 * P - 1, 64, 256, &te));
   else te = tq;
   dim3 grid(ceil_div(Lq, kTQ), heads, B);
-  kfn<<<grid, kTcThreads, SM::kBytes, s>>>(tq, tk, tv, te, mask, out, heads, Lq, Lk, P, static_cast<uint32_t>(fmt));
+  SD_CUDA(launch_k(kfn, dim3(grid), dim3(kTcThreads), SM::kBytes, s, tq, tk, tv, te, mask, out, heads, Lq, Lk, P, static_cast<uint32_t>(fmt)));
   SD_LAUNCHED(REL ? "attention_tc_rel" : "attention_tc_norel", s);
   return SEQDIFF_OK;
 }

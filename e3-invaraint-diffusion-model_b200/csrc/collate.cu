@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(kColThreads) collate_kernel(const int* __restr
                                                               float* __restrict__ lig_seq, float* __restrict__ lig_attn,
                                                               float* __restrict__ rec_ang, float* __restrict__ rec_seq,
                                                               float* __restrict__ rec_attn, int* __restrict__ lengths) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   __shared__ int warp_tot[kColThreads / 32];
   const int g = blockIdx.x;
   const int n0 = offsets[g], n = offsets[g + 1] - n0;
@@ -96,8 +98,8 @@ __global__ void __launch_bounds__(kColThreads) collate_kernel(const int* __restr
 int collate(int G, const int* offsets, const uint8_t* lig_mask, const uint8_t* poc_mask, const float* ang, const float* aa, int ext, int L,
             float* lig_ang, float* lig_seq, float* lig_attn, float* rec_ang, float* rec_seq, float* rec_attn, int* lengths, cudaStream_t s) {
   SD_CHECK(G > 0 && L > 0, "empty collation");
-  collate_kernel<<<G, kColThreads, 0, s>>>(offsets, lig_mask, poc_mask, ang, aa, ext, L, lig_ang, lig_seq, lig_attn, rec_ang, rec_seq, rec_attn,
-                                          lengths);
+  SD_CUDA(launch_k(collate_kernel, dim3(G), dim3(kColThreads), 0, s, offsets, lig_mask, poc_mask, ang, aa, ext, L, lig_ang, lig_seq, lig_attn, rec_ang, rec_seq, rec_attn,
+                                          lengths));
   SD_LAUNCHED("collate", s);
   return SEQDIFF_OK;
 }

@@ -278,6 +278,29 @@ __host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, uint32_t a_fm
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
+// Every kernel of the path is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may become resident
+// while its predecessor drains, runs its prologue (smem carve-up, mbarrier init, TMEM alloc, descriptor prefetch), and then
+// blocks in pdl_wait() until the predecessor grid has completed and flushed -- before its first dependent global access.
+// pdl_trigger() lets the successor start being scheduled.  Both are no-ops without the attribute (SEQDIFF_PDL=0).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- misc -------------------------------------------------------------------------------------------
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int num_sms();  // SM count of the current device (cached)

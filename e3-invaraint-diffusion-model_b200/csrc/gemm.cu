@@ -172,6 +172,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -300,7 +302,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* 
   }
   const int tiles = ceil_div(M, kBM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K, idesc);
+  SD_CUDA(launch_k(kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K, idesc));
   SD_LAUNCHED("gemm_tcgen05", s);
   return SEQDIFF_OK;
 }
@@ -371,6 +373,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
                                                        const float* __restrict__ bias, const float* __restrict__ resid,
                                                        float* __restrict__ C, int M, int N, int K) {
   constexpr int TM = 64, TN = 64, TK = 16;
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   __shared__ float sA[TK][TM + 4];
   __shared__ float sW[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -433,10 +437,10 @@ int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* b
   SD_CHECK(K % 4 == 0, "fp32 GEMM needs K % 4 == 0");
   SD_CHECK(!(resid && epi != 0), "residual add is only fused with the identity epilogue");
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-  if (resid) gemm_f32_kernel<0, true><<<grid, 256, 0, s>>>(A, W, bias, resid, C, M, N, K);
-  else if (epi == 0) gemm_f32_kernel<0, false><<<grid, 256, 0, s>>>(A, W, bias, resid, C, M, N, K);
-  else if (epi == 1) gemm_f32_kernel<1, false><<<grid, 256, 0, s>>>(A, W, bias, resid, C, M, N, K);
-  else if (epi == 2) gemm_f32_kernel<2, false><<<grid, 256, 0, s>>>(A, W, bias, resid, C, M, N, K);
+  if (resid) SD_CUDA(launch_k(gemm_f32_kernel<0, true>, dim3(grid), dim3(256), 0, s, A, W, bias, resid, C, M, N, K));
+  else if (epi == 0) SD_CUDA(launch_k(gemm_f32_kernel<0, false>, dim3(grid), dim3(256), 0, s, A, W, bias, resid, C, M, N, K));
+  else if (epi == 1) SD_CUDA(launch_k(gemm_f32_kernel<1, false>, dim3(grid), dim3(256), 0, s, A, W, bias, resid, C, M, N, K));
+  else if (epi == 2) SD_CUDA(launch_k(gemm_f32_kernel<2, false>, dim3(grid), dim3(256), 0, s, A, W, bias, resid, C, M, N, K));
   else {
     set_error("unknown GEMM epilogue");
     return SEQDIFF_ERR_INVALID;

@@ -14,13 +14,23 @@
 // (mul, then IEEE divide), and each thread then resolves one residue with 400 multiply-adds.
 // Rows of x_t that are not exactly one-hot take the general (dot-product) formula.
 // Traffic: 80 B logits + 80 B x_t in, 80 B one-hot out per residue (+80 B if the noise E is supplied).
+//
+// Two arithmetic modes (template FAST), same algorithm:
+//   exact (noise_E supplied = a reference noise stream is being replayed, or argmax): the reference's own op sequence --
+//         expf, IEEE divides, product rounded then summed over i -- so indices agree bit for bit up to libm ulps;
+//   fast  (in-kernel Philox noise = production): there is no reference stream to reproduce, only a distribution, so the
+//         posterior uses FMA, ex2/lg2/rcp.approx and 128-bit table loads, and skips the two normalisations (an argmax race is
+//         invariant to positive row scaling).  Deviation of the race scores <= 1e-6 relative.  ncu (round 1): the exact path
+//         costs 5075 thread-instructions per residue at 63 % issue utilisation -- the kernel is issue-bound, not HBM-bound.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace seqdiff {
 
 constexpr int C = SEQDIFF_NUM_CLASSES;
-constexpr int kRevThreads = 128;
+constexpr int kRevThreads = 256;
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: identical streams for any sharding ----------
 __host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
@@ -56,6 +66,16 @@ __device__ __forceinline__ float exp1_from_u32(uint32_t w) {
   const float u = (static_cast<float>(w >> 9) + 0.5f) * 1.1920928955078125e-07f;
   return -logf(u);
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 1 / (-log2 u): the Exp(1) variate up to the constant ln 2, inverted (the race only compares ratios)
+__device__ __forceinline__ float inv_exp1_fast(uint32_t w) {
+  const float u = (static_cast<float>(w >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  return rcp_approx(-lg2_approx(u));
+}
 
 // exponential race / argmax over one normalised row
 __device__ __forceinline__ int pick_class(const float (&prob)[C], bool diverse, const float (&E)[C]) {
@@ -81,16 +101,69 @@ __device__ __forceinline__ void write_onehot(float* __restrict__ row, int idx) {
   }
 }
 
+// Cold path: a row of x_t that is not exactly one-hot (never produced by the sampler itself; sample.py:129-138 accepts it).
+// Kept out of line and fed from global/shared memory so that the hot path's per-class arrays stay in registers.
+//   left[j] = Qt[j,:].x ; den[i] = Qtb[i,:].x (0 -> 1e-6) ; un[j] = sum_i p_i * left[j] * Qsb[i,j] / den[i]
+template <bool FAST>
+__device__ __noinline__ int soft_row_class(const float* __restrict__ lg_row, const float* __restrict__ x_row, const float* sQt,
+                                           const float* sQsb, const float* sQtb, bool diverse, const float* __restrict__ E_row, uint64_t seed,
+                                           uint64_t graph, uint32_t l, uint32_t step) {
+  float mx = lg_row[0];
+  for (int j = 1; j < C; ++j) mx = fmaxf(mx, lg_row[j]);
+  float ps = 0.f;
+  for (int j = 0; j < C; ++j) ps += expf(lg_row[j] - mx);
+  float un[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) un[j] = 0.f;
+  for (int i = 0; i < C; ++i) {
+    const float p = __fdiv_rn(expf(lg_row[i] - mx), ps);
+    float den = 0.f;
+    for (int k = 0; k < C; ++k) den = fmaf(sQtb[i * C + k], x_row[k], den);
+    if (den == 0.f) den = 1e-6f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      float left = 0.f;
+      for (int k = 0; k < C; ++k) left = fmaf(x_row[k], sQt[j * C + k], left);
+      un[j] = __fadd_rn(un[j], __fmul_rn(p, __fdiv_rn(__fmul_rn(left, sQsb[i * C + j]), den)));
+    }
+  }
+  float tot = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) tot += un[j];
+  if (tot == 0.f) {
+    tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { un[j] = 1e-5f; tot += 1e-5f; }
+  }
+  uint32_t w[C];
+  if (diverse && !E_row) philox_row(seed, graph, l, step, w);
+  int best = 0;
+  float bv = -INFINITY, psum = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const float pr = __fdiv_rn(un[j], tot);
+    psum += pr;
+    const float v = !diverse ? pr : (E_row ? __fdiv_rn(pr, E_row[j]) : (FAST ? pr * inv_exp1_fast(w[j]) : __fdiv_rn(pr, exp1_from_u32(w[j]))));
+    if (v > bv) { bv = v; best = j; }
+  }
+  return psum != 0.f ? best : 0;
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* __restrict__ q_tables, int n_tab, int L,
                                                                    const float* __restrict__ x_t, const float* __restrict__ logits,
                                                                    int diverse, const float* __restrict__ noise_E, uint64_t seed,
                                                                    uint64_t graph_id0, uint32_t step, const int* __restrict__ step_ptr,
                                                                    float* __restrict__ x_s, uint8_t* __restrict__ idx_out) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   __shared__ float sQt[C * C], sQsb[C * C], sQtb[C * C];
   // [x][i][j] with an odd x-stride: lanes holding different x_t classes then read 32 different banks (stride 400
   // would fold all classes onto 2 banks -- measured 16-way conflicts, 567 GB/s)
-  constexpr int kXS = C * C + 1;
-  __shared__ float sPost[C * kXS];
+  // (exact: odd stride 401, scalar reads.  fast: stride 404 keeps rows 16 B aligned for 128-bit reads; lanes whose classes
+  //  differ by 8 then share banks -- about 1.5-way on random classes, against 4x fewer load instructions)
+  constexpr int kXS = FAST ? C * C + 4 : C * C + 1;
+  __shared__ __align__(16) float sPost[C * kXS];
   const int b = blockIdx.y;  // grid = (ceil(L / 128) residue chunks, graphs): enough CTAs to stream at HBM rate
   const size_t n_res = static_cast<size_t>(gridDim.y) * L;
   if (step_ptr) {
@@ -107,11 +180,27 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
     sQtb[i] = tab[2 * C * C + i];
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < C * C * C; e += kRevThreads) {
-    const int x = e / (C * C), i = (e / C) % C, j = e % C;
-    float den = sQtb[i * C + x];
-    if (den == 0.f) den = 1e-6f;
-    sPost[x * kXS + i * C + j] = __fdiv_rn(__fmul_rn(sQt[j * C + x], sQsb[i * C + j]), den);
+  __shared__ float sInv[FAST ? C * C : 1];
+  if (FAST) {  // reciprocals of the denominators once (400 instead of 8000 divisions)
+    for (int e = threadIdx.x; e < C * C; e += kRevThreads) {
+      const float den = sQtb[e];
+      sInv[e] = rcp_approx(den == 0.f ? 1e-6f : den);
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < C * C; e += kRevThreads) {  // (i, j) fixed per thread, x runs: no div/mod in the inner loop
+    const int i = e / C, j = e - i * C;
+    const float qsb = sQsb[e];
+#pragma unroll 4
+    for (int x = 0; x < C; ++x) {
+      if (FAST) {
+        sPost[x * kXS + e] = sQt[j * C + x] * qsb * sInv[i * C + x];
+      } else {
+        float den = sQtb[i * C + x];
+        if (den == 0.f) den = 1e-6f;
+        sPost[x * kXS + e] = __fdiv_rn(__fmul_rn(sQt[j * C + x], qsb), den);
+      }
+    }
   }
   __syncthreads();
 
@@ -124,6 +213,60 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
       const float4 c4 = *reinterpret_cast<const float4*>(x_t + n * C + j4);
       lg[j4] = a.x; lg[j4 + 1] = a.y; lg[j4 + 2] = a.z; lg[j4 + 3] = a.w;
       xr[j4] = c4.x; xr[j4 + 1] = c4.y; xr[j4 + 2] = c4.z; xr[j4 + 3] = c4.w;
+    }
+    if (FAST) {
+      float mxf = lg[0];
+#pragma unroll
+      for (int j = 1; j < C; ++j) mxf = fmaxf(mxf, lg[j]);
+      float pf[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) pf[j] = ex2_approx((lg[j] - mxf) * 1.44269504088896f);  // unnormalised softmax
+      int hotf = -1, nnzf = 0;
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+        if (xr[j] != 0.f) { ++nnzf; hotf = (xr[j] == 1.0f) ? j : -2; }
+      float unf[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) unf[j] = 0.f;
+      if (!(nnzf == 1 && hotf >= 0)) {
+        const int idx = soft_row_class<true>(logits + n * C, x_t + n * C, sQt, sQsb, sQtb, true, nullptr, seed, graph_id0 + b, static_cast<uint32_t>(l), step);
+        write_onehot(x_s + n * C, idx);
+        if (idx_out) idx_out[n] = static_cast<uint8_t>(idx);
+        continue;
+      }
+      {
+        const float4* post4 = reinterpret_cast<const float4*>(sPost + hotf * kXS);
+#pragma unroll
+        for (int i = 0; i < C; ++i) {  // fully unrolled: pf[i] must stay in registers (a partial unroll spills it to local memory)
+#pragma unroll
+          for (int j4 = 0; j4 < C / 4; ++j4) {
+            const float4 w = post4[i * (C / 4) + j4];
+            unf[4 * j4] = fmaf(pf[i], w.x, unf[4 * j4]);
+            unf[4 * j4 + 1] = fmaf(pf[i], w.y, unf[4 * j4 + 1]);
+            unf[4 * j4 + 2] = fmaf(pf[i], w.z, unf[4 * j4 + 2]);
+            unf[4 * j4 + 3] = fmaf(pf[i], w.w, unf[4 * j4 + 3]);
+          }
+        }
+      }
+      float totf = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) totf += unf[j];
+      if (totf == 0.f) {  // sample.py:167: all-zero row -> uniform
+#pragma unroll
+        for (int j = 0; j < C; ++j) unf[j] = 1e-5f;
+      }
+      uint32_t w[C];
+      philox_row(seed, graph_id0 + b, static_cast<uint32_t>(l), step, w);
+      int best = 0;
+      float bv = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float v = unf[j] * inv_exp1_fast(w[j]);
+        if (v > bv) { bv = v; best = j; }
+      }
+      write_onehot(x_s + n * C, best);
+      if (idx_out) idx_out[n] = static_cast<uint8_t>(best);
+      continue;
     }
     // softmax(logits)
     float mx = lg[0];
@@ -144,29 +287,17 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
     for (int j = 0; j < C; ++j) un[j] = 0.f;
     if (nnz == 1 && hot >= 0) {
       const float* post = sPost + hot * kXS;
-#pragma unroll 4
+#pragma unroll
       for (int i = 0; i < C; ++i) {
 #pragma unroll
         for (int j = 0; j < C; ++j) un[j] = __fadd_rn(un[j], __fmul_rn(p[i], post[i * C + j]));
       }
-    } else {  // general x_t row: left[j] = Qt[j,:].x, den[i] = Qtb[i,:].x
-      float left[C];
-#pragma unroll
-      for (int j = 0; j < C; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < C; ++k) a = fmaf(xr[k], sQt[j * C + k], a);
-        left[j] = a;
-      }
-      for (int i = 0; i < C; ++i) {
-        float den = 0.f;
-#pragma unroll
-        for (int k = 0; k < C; ++k) den = fmaf(sQtb[i * C + k], xr[k], den);
-        if (den == 0.f) den = 1e-6f;
-#pragma unroll
-        for (int j = 0; j < C; ++j)
-          un[j] = __fadd_rn(un[j], __fmul_rn(p[i], __fdiv_rn(__fmul_rn(left[j], sQsb[i * C + j]), den)));
-      }
+    } else {
+      const int idx = soft_row_class<false>(logits + n * C, x_t + n * C, sQt, sQsb, sQtb, diverse != 0, noise_E ? noise_E + n * C : nullptr, seed,
+                                            graph_id0 + b, static_cast<uint32_t>(l), step);
+      write_onehot(x_s + n * C, idx);
+      if (idx_out) idx_out[n] = static_cast<uint8_t>(idx);
+      continue;
     }
     float tot = 0.f;
 #pragma unroll
@@ -206,8 +337,12 @@ int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_
                  uint8_t* idx_out, cudaStream_t s) {
   SD_CHECK(B > 0 && L > 0, "empty reverse step");
   SD_CHECK(n_tab == 1 || n_tab == B, "q_tables must hold 1 or B (Qt,Qsb,Qtb) triples");
-  reverse_step_kernel<<<dim3(ceil_div(L, kRevThreads), B), kRevThreads, 0, s>>>(q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr,
-                                                x_s, idx_out);
+  static const int rpt = [] { const char* e = getenv("SEQDIFF_REV_RPT"); return e ? atoi(e) : 2; }();
+  const dim3 grid(ceil_div(L, rpt * kRevThreads), B);  // residues per thread: amortises the per-CTA table build
+  if (diverse && !noise_E)
+    SD_CUDA(launch_k(reverse_step_kernel<true>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out));
+  else
+    SD_CUDA(launch_k(reverse_step_kernel<false>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out));
   SD_LAUNCHED("reverse_step", s);
   return SEQDIFF_OK;
 }
@@ -217,6 +352,8 @@ int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_
 __global__ void __launch_bounds__(kRevThreads) apply_aa_noise_kernel(const float* __restrict__ qtb, int L, const float* __restrict__ x0,
                                                                      const float* __restrict__ noise_E, uint64_t seed, uint64_t graph_id0,
                                                                      uint32_t step, float* __restrict__ x_t, uint8_t* __restrict__ idx_out) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   __shared__ float sQ[C * C];
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < C * C; i += kRevThreads) sQ[i] = qtb[static_cast<size_t>(b) * C * C + i];
@@ -260,12 +397,14 @@ __global__ void __launch_bounds__(kRevThreads) apply_aa_noise_kernel(const float
 int apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float* noise_E, uint64_t seed, uint64_t graph_id0,
                    uint32_t step, float* x_t, uint8_t* idx_out, cudaStream_t s) {
   SD_CHECK(B > 0 && L > 0, "empty q-sample");
-  apply_aa_noise_kernel<<<B, kRevThreads, 0, s>>>(qtb, L, x0, noise_E, seed, graph_id0, step, x_t, idx_out);
+  SD_CUDA(launch_k(apply_aa_noise_kernel, dim3(B), dim3(kRevThreads), 0, s, qtb, L, x0, noise_E, seed, graph_id0, step, x_t, idx_out));
   SD_LAUNCHED("apply_aa_noise", s);
   return SEQDIFF_OK;
 }
 
 __global__ void philox_u32_kernel(uint64_t seed, uint64_t graph_id0, uint32_t step, int L, uint32_t* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int b = blockIdx.x;
   for (int l = threadIdx.x; l < L; l += blockDim.x) {
     uint32_t w[C];
@@ -274,7 +413,7 @@ __global__ void philox_u32_kernel(uint64_t seed, uint64_t graph_id0, uint32_t st
   }
 }
 int philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, cudaStream_t s) {
-  philox_u32_kernel<<<B, 128, 0, s>>>(seed, graph_id0, step, L, out);
+  SD_CUDA(launch_k(philox_u32_kernel, dim3(B), dim3(128), 0, s, seed, graph_id0, step, L, out));
   SD_LAUNCHED("philox_u32", s);
   return SEQDIFF_OK;
 }

@@ -43,6 +43,8 @@ __device__ __forceinline__ void row_stats(const float (&v)[VPL][8], int H, float
 // ---------------------------------------------------------------------------------------------------
 __global__ void timestep_embed_kernel(const float* __restrict__ timestep, const int* __restrict__ step_ptr,
                                       const float* __restrict__ W, int B, int H, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int half = H / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -56,7 +58,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ timestep, const 
 
 int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, cudaStream_t s) {
   const int n = B * (H / 2);
-  timestep_embed_kernel<<<ceil_div(n, 128), 128, 0, s>>>(timestep, step_ptr, W, B, H, out);
+  SD_CUDA(launch_k(timestep_embed_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, s, timestep, step_ptr, W, B, H, out));
   SD_LAUNCHED("timestep_embed", s);
   return SEQDIFF_OK;
 }
@@ -69,6 +71,8 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_kernel(const float* __re
                                                                const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                                float eps, const float* __restrict__ te, int L, int H,
                                                                float* __restrict__ out32, T* __restrict__ outT) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   constexpr int TOK = 4;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
@@ -143,7 +147,7 @@ int embed_ln(const float* x, int M, int fin, const float* Wt, const float* b, co
   SD_CHECK(H % 256 == 0, "hidden_size must be a multiple of 256");
   const int warps = ceil_div(M, 4);
   const int grid = ceil_div(warps * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, embed_ln_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(x, M, fin, Wt, b, lnw, lnb, eps, te, L, H, out32, outT));
+  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(embed_ln_kernel<T, VPL>, dim3(grid), dim3(kRowThreads), 0, s, x, M, fin, Wt, b, lnw, lnb, eps, te, L, H, out32, outT)));
   SD_LAUNCHED("embed_ln", s);
   return SEQDIFF_OK;
 }
@@ -158,6 +162,8 @@ template <typename T, int VPL>
 __global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const float* __restrict__ in, int M, int H, const float* __restrict__ w,
                                                                 const float* __restrict__ b, float eps, float* __restrict__ out32,
                                                                 T* __restrict__ outT) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
   if (row >= M) return;
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const float* __r
 template <typename T>
 int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, cudaStream_t s) {
   const int grid = ceil_div(M * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, layernorm_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(in, M, H, w, b, eps, out32, outT));
+  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_kernel<T, VPL>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, w, b, eps, out32, outT)));
   SD_LAUNCHED("layernorm", s);
   return SEQDIFF_OK;
 }
@@ -195,6 +201,8 @@ __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const float* _
                                                                   const float* __restrict__ lnb, float eps1, const float* __restrict__ x,
                                                                   const T* __restrict__ mod, int mod_div, int chunk0,
                                                                   float* __restrict__ out32, T* __restrict__ outT) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
   if (row >= M) return;
@@ -238,9 +246,9 @@ int ln_modulate(const float* in, int M, int H, bool affine_first, const float* l
                 const T* mod, int mod_div, int chunk0, float* out32, T* outT, cudaStream_t s) {
   const int grid = ceil_div(M * 32, kRowThreads);
   if (affine_first) {
-    SD_VPL_DISPATCH(H, ln_modulate_kernel<T, VPL, true><<<grid, kRowThreads, 0, s>>>(in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT));
+    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_kernel<T, VPL, true>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT)));
   } else {
-    SD_VPL_DISPATCH(H, ln_modulate_kernel<T, VPL, false><<<grid, kRowThreads, 0, s>>>(in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT));
+    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_kernel<T, VPL, false>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT)));
   }
   SD_LAUNCHED("ln_modulate", s);
   return SEQDIFF_OK;
@@ -257,6 +265,8 @@ __global__ void __launch_bounds__(kRowThreads) predictor_tail_kernel(const T* __
                                                                      const float* __restrict__ lnb, float eps,
                                                                      const float* __restrict__ W2, const float* __restrict__ b2, int F,
                                                                      float* __restrict__ logits) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
   if (row >= M) return;
@@ -296,7 +306,7 @@ int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb,
                    float* logits, cudaStream_t s) {
   SD_CHECK(F <= 32, "feature_size > 32 not supported");
   const int grid = ceil_div(M * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, predictor_tail_kernel<T, VPL><<<grid, kRowThreads, 0, s>>>(y, M, H, lnw, lnb, eps, W2, b2, F, logits));
+  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(predictor_tail_kernel<T, VPL>, dim3(grid), dim3(kRowThreads), 0, s, y, M, H, lnw, lnb, eps, W2, b2, F, logits)));
   SD_LAUNCHED("predictor_tail", s);
   return SEQDIFF_OK;
 }
@@ -307,6 +317,8 @@ template int predictor_tail<f16>(const f16*, int, int, const float*, const float
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void f32_to_16_kernel(const float* __restrict__ in, size_t n, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x);
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) out[i] = from_f32<T>(in[i]);
@@ -316,7 +328,7 @@ int f32_to_16(const float* in, size_t n, T* out, cudaStream_t s) {
   if (n == 0) return SEQDIFF_OK;
   size_t blocks = (n + 255) / 256;
   if (blocks > 4096) blocks = 4096;
-  f32_to_16_kernel<T><<<static_cast<int>(blocks), 256, 0, s>>>(in, n, out);
+  SD_CUDA(launch_k(f32_to_16_kernel<T>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, in, n, out));
   SD_LAUNCHED("f32_to_16", s);
   return SEQDIFF_OK;
 }
@@ -324,20 +336,26 @@ template int f32_to_16<bf16>(const float*, size_t, bf16*, cudaStream_t);
 template int f32_to_16<f16>(const float*, size_t, f16*, cudaStream_t);
 
 __global__ void transpose_f32_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int r = i / cols, c = i % cols;
   out[static_cast<size_t>(c) * rows + r] = in[i];
 }
 int transpose_f32(const float* in, int rows, int cols, float* out, cudaStream_t s) {
-  transpose_f32_kernel<<<ceil_div(rows * cols, 256), 256, 0, s>>>(in, rows, cols, out);
+  SD_CUDA(launch_k(transpose_f32_kernel, dim3(ceil_div(rows * cols, 256)), dim3(256), 0, s, in, rows, cols, out));
   SD_LAUNCHED("transpose_f32", s);
   return SEQDIFF_OK;
 }
 
-__global__ void step_advance_kernel(int* p) { *p -= 1; }
+__global__ void step_advance_kernel(int* p) {
+  pdl_trigger();
+  pdl_wait();
+  *p -= 1;
+}
 int step_advance(int* step_ptr, cudaStream_t s) {
-  step_advance_kernel<<<1, 1, 0, s>>>(step_ptr);
+  SD_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(1), 0, s, step_ptr));
   SD_LAUNCHED("step_advance", s);
   return SEQDIFF_OK;
 }
