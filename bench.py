@@ -320,7 +320,8 @@ def main():
                 reps = 5
                 prof = sd._cabi.profile(lambda: [model(*fwd_args) for _ in range(reps)])
             total_ms = sum(v[0] for v in prof.values())
-            gemm_ms, gemm_n = prof.get("gemm_tcgen05", (0.0, 0))
+            gemm_ms = sum(v[0] for k, v in prof.items() if k.startswith("gemm_tcgen05"))  # 1-CTA and CTA-pair variants
+            gemm_n = sum(v[1] for k, v in prof.items() if k.startswith("gemm_tcgen05"))
             peak, peak_src, hbm = measured_peaks()
             flops = gemm_flops_per_forward(B) * reps
             achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -328,7 +329,7 @@ def main():
             tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get("gemm_tcgen05_dram_bytes_per_launch")
-            result["roofline"] = {"kernel": "gemm_tcgen05_kernel (50 launches per forward)", "bound": "tensor", "achieved": achieved, "peak": peak,
+            result["roofline"] = {"kernel": "gemm_tcgen05_kernel (50 launches per forward; 1-CTA and cta_group::2 variants)", "bound": "tensor", "achieved": achieved, "peak": peak,
                                   "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                                   "flops_per_launch_avg": flops / max(gemm_n, 1), "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
                                   "share_of_forward": gemm_ms / total_ms if total_ms else None,

@@ -146,8 +146,8 @@ int seqdiff_op_gemm(int precision, int M, int N, int K, const void* A, const voi
   SD_GUARD_BEGIN
   SD_CHECK(A && W && bias && C, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // bits 8.. of `precision` may force the tile width (tests): precision = mode | (bn << 8)
-  const int force_bn = precision >> 8;
+  // upper bits of `precision` may force the tile configuration (tests / sweeps): mode | (bn << 8) | (cta_pair << 20)
+  const int force_bn = ((precision >> 8) & 0xfff) | (((precision >> 20) & 1) << 16);
   const int mode = precision & 0xff;
   if (mode == SEQDIFF_FP32)
     return gemm_f32(M, N, K, static_cast<const float*>(A), static_cast<const float*>(W), bias, static_cast<const float*>(resid),

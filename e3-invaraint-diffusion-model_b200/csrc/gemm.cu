@@ -17,6 +17,7 @@
 // must share the format); GEMMs that feed a LayerNorm write fp32 and take an fp32 residual, so the residual stream of the
 // network never passes through a 16-bit rounding.
 // fp32 path (parity gate 1e-5): plain SIMT tiled kernel, fp32 FMA accumulation.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -106,10 +107,15 @@ constexpr int kBK = 64;         // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit inputs
 constexpr int kGemmThreads = 320;
 
-template <int BN> struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
+// CG2 = CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN output tile per pair; each CTA stages its own 128 rows
+// of A and HALF of the B tile (the MMA reads both halves across the pair), so a CTA pulls 16 KB + BN/2 * 128 B per k-block
+// from L2 for 128 x BN x 64 MACs -- 2/3 of the 1-CTA traffic at BN = 256.  The mainloop of this model's GEMMs is bound by
+// exactly that L2 -> SM operand stream (profiles/prof_gemm_r01.summary.txt).
+template <int BN, bool CG2> struct GemmCfg {
+  static constexpr int kBRows = CG2 ? BN / 2 : BN;
+  static constexpr int kStages = CG2 ? 6 : ((BN == 256 || BN == 192) ? 4 : 6);
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // two accumulator stages, rounded up to a power of two
   static constexpr int kStagingBytes = 8 * 32 * 32 * 4;  // one 32x32 fp32 transpose panel per epilogue warp
@@ -126,13 +132,14 @@ template <> __device__ __forceinline__ void store4<f16>(f16* p, const float4& v)
 }
 
 // TOut: bf16 / f16 (operand for the next GEMM or attention) or float (LayerNorm input); resid is always fp32.
-template <int BN, int EPI, bool RESID, typename TOut>
+template <int BN, int EPI, bool RESID, typename TOut, bool CG2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
                     uint32_t idesc) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG2>;
   constexpr int STAGES = Cfg::kStages;
+  constexpr int TILE_M = CG2 ? 2 * kBM : kBM;  // rows per scheduled tile (per CTA pair / per CTA)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
@@ -147,9 +154,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_n = N / BN;
-  const int num_m = (M + kBM - 1) / kBM;
+  const int num_m = (M + TILE_M - 1) / TILE_M;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + kBK - 1) / kBK;
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
+  const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -160,16 +170,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], CG2 ? 16 : 8);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CG2) {
+      tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);  // collective over the pair: same warp, same slot in both CTAs
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all(); else __syncthreads();  // barriers of BOTH CTAs initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
@@ -180,26 +195,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * kBM;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
-          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (CG2) {
+            // both CTAs' tiles complete on the LEADER's full barrier, which the leader arms for the bytes of the pair
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_cg2(sA + stage * Cfg::kABytes, &tmA, bar, kb * kBK, a_row);
+            tma_load_2d_cg2(sB + stage * Cfg::kBBytes, &tmB, bar, kb * kBK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, a_row);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator stage
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue(s) have drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -211,12 +235,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
             const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG2) umma_cg2(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
+          if (CG2) umma_commit_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (CG2) umma_commit_mc(&tfull_bar[as], 3); else umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue(s)
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -233,9 +259,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int lr = lane >> 3, lc = lane & 7;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int row_base = m_blk * kBM + q * 32;
+      const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * kBM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
       bool waited = false;
 #pragma unroll 1
@@ -277,42 +303,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CG2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));  // the leader's MMA thread waits on it
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all(); else __syncthreads();  // pair: nobody frees TMEM / exits while the other CTA may still signal or read
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int EPI, bool RESID, typename TOut>
+template <int BN, int EPI, bool RESID, typename TOut, bool CG2>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, void* C, int M, int N, int K,
                      uint32_t idesc, cudaStream_t s) {
-  using Cfg = GemmCfg<BN>;
-  auto kfn = gemm_tcgen05_kernel<BN, EPI, RESID, TOut>;
+  using Cfg = GemmCfg<BN, CG2>;
+  auto kfn = gemm_tcgen05_kernel<BN, EPI, RESID, TOut, CG2>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = ceil_div(M, kBM) * (N / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  SD_CUDA(launch_k(kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K, idesc));
-  SD_LAUNCHED("gemm_tcgen05", s);
+  const int tiles = ceil_div(M, CG2 ? 2 * kBM : kBM) * (N / BN);
+  const int slots = CG2 ? num_sms() / 2 : num_sms();
+  const int grid = (tiles < slots ? tiles : slots) * (CG2 ? 2 : 1);
+  SD_CUDA(launch_kc(CG2 ? 2 : 1, kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K,
+                    idesc));
+  SD_LAUNCHED(CG2 ? "gemm_tcgen05_2cta" : "gemm_tcgen05", s);
   return SEQDIFF_OK;
 }
 
-// tile-width choice.  Measured on B200 (scripts/gemm_sweep.py, round 1): the mainloop is bound by L2->SM operand
-// traffic, so wide tiles win (128x256: 48 KB of operands per 128x256x64 MACs; 128x128: 32 KB per half the MACs).
-// 128x192 exists for wave quantisation: N = 768 at M = 8192 is 192 tiles of 128x256 (2 waves at 65 % fill on 148 SMs)
-// but 256 tiles of 128x192 (2 waves of 3/4-size tiles).  Cost model: waves x tile time, ties to the wider tile.
-static int pick_bn(int M, int N) {
+// tile choice, from measurements on B200 (scripts/gemm_sweep.py, profiles/gemm_sweep_r01.log):
+//  * the mainloop is bound by the L2->SM operand stream, so wide tiles win: 128x256 (48 KB of operands per 128x256x64 MACs)
+//    beats 128x128 (32 KB per half the MACs) on every shape of this model;
+//  * 128x192 exists for wave quantisation: N = 768 at M = 8192 is 192 tiles of 128x256 (2 waves at 65 % fill on 148 SMs) but
+//    256 tiles of 128x192 (2 waves of 3/4-size tiles);
+//  * CTA pairs (cta_group::2, 256x256 per pair, 32 KB per CTA for the same MACs) gain 5-7 % on the largest GEMMs
+//    (ada2 1.21, cross-KV 1.23 PFLOP/s) and nothing on the small ones, whose time is ramp / tail: used from 2.5e10 MACs up.
+// SEQDIFF_GEMM_CG2=0 disables the pair kernel.  Returns bn | (cg2 << 16).
+static int pick_cfg(int M, int N, int K) {
+  static const int allow_cg2 = [] { const char* e = getenv("SEQDIFF_GEMM_CG2"); return e ? atoi(e) : 1; }();
   if (M <= 64) return 128;
+  if (allow_cg2 && N % 256 == 0 && static_cast<double>(M) * N * K >= 2.5e10) return 256 | (1 << 16);
   const int sms = num_sms();
   const int m_tiles = ceil_div(M, kBM);
   int best = 0;
@@ -326,24 +363,25 @@ static int pick_bn(int M, int N) {
   return best;
 }
 
-template <int BN>
+template <int BN, bool CG2>
 static int dispatch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, int epi, void* C,
                        int out_kind, int M, int N, int K, uint32_t idesc, cudaStream_t s) {
-  if (resid) return launch_tc<BN, 0, true, float>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  if (out_kind == 2) return launch_tc<BN, 0, false, float>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (resid) return launch_tc<BN, 0, true, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (out_kind == 2) return launch_tc<BN, 0, false, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
   if (out_kind == 1) {
-    if (epi == 0) return launch_tc<BN, 0, false, bf16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-    if (epi == 1) return launch_tc<BN, 1, false, bf16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-    return launch_tc<BN, 2, false, bf16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    if (epi == 0) return launch_tc<BN, 0, false, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    if (epi == 1) return launch_tc<BN, 1, false, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    return launch_tc<BN, 2, false, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
   }
-  if (epi == 0) return launch_tc<BN, 0, false, f16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  if (epi == 1) return launch_tc<BN, 1, false, f16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  return launch_tc<BN, 2, false, f16>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (epi == 0) return launch_tc<BN, 0, false, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (epi == 1) return launch_tc<BN, 1, false, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  return launch_tc<BN, 2, false, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
 }
 
 // a_fmt / w_fmt: 0 = fp16, 1 = bf16.  out_kind: 0 = fp16, 1 = bf16, 2 = fp32 (identity epilogue only; implied by resid).
+// force_cfg: 0 = auto, else  bn | (cg2 << 16)  with bn in {128,192,256} (tests / sweeps).
 int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
-            void* C, int out_kind, cudaStream_t s, int force_bn) {
+            void* C, int out_kind, cudaStream_t s, int force_cfg) {
   SD_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
   SD_CHECK(N % 128 == 0, "tcgen05 GEMM needs N % 128 == 0");
   SD_CHECK(K % 8 == 0, "tcgen05 GEMM needs K % 8 == 0 (16B TMA pitch)");
@@ -354,15 +392,21 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
   SD_CHECK((a_fmt | 1) == 1 && out_kind >= 0 && out_kind <= 2, "bad operand format");
   // measured on B200: tcgen05.mma.kind::f16 with a_format != b_format faults as an illegal instruction
   SD_CHECK(a_fmt == w_fmt, "A and W must share one 16-bit format");
-  const int bn = force_bn ? force_bn : pick_bn(M, N);
+  const int cfg = force_cfg ? force_cfg : pick_cfg(M, N, K);
+  const int bn = cfg & 0xffff;
+  const bool cg2 = (cfg >> 16) != 0;
   SD_CHECK((bn == 128 || bn == 192 || bn == 256) && N % bn == 0, "bad tile width");
   CUtensorMap ta, tb;
   SD_TRY(make_tmap(A, a_fmt, M, K, kBM, &ta));
-  SD_TRY(make_tmap(W, w_fmt, N, K, bn, &tb));
-  const uint32_t idesc = umma_idesc_16(kBM, bn, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
-  if (bn == 256) return dispatch_tc<256>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s);
-  if (bn == 192) return dispatch_tc<192>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s);
-  return dispatch_tc<128>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s);
+  SD_TRY(make_tmap(W, w_fmt, N, K, cg2 ? bn / 2 : bn, &tb));
+  const uint32_t idesc = umma_idesc_16(cg2 ? 2 * kBM : kBM, bn, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
+#define SD_DISPATCH(BN_)                                                                                          \
+  return cg2 ? dispatch_tc<BN_, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s)                   \
+             : dispatch_tc<BN_, false>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s)
+  if (bn == 256) { SD_DISPATCH(256); }
+  if (bn == 192) { SD_DISPATCH(192); }
+  SD_DISPATCH(128);
+#undef SD_DISPATCH
 }
 
 // =====================================================================================================

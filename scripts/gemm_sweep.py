@@ -20,10 +20,11 @@ for name, cnt, M, N, K, epi, kind in SHAPES:
     bias = torch.randn(N, device=dev); resid = torch.randn(M, N, device=dev) if kind == "r" else None
     C = torch.empty(M, N, device=dev, dtype=torch.float32 if kind == "r" else torch.bfloat16)
     best = {}
-    for bn in (128, 192, 256):
+    for bn in (128, 192, 256, 1192, 1256):   # 1xxx = CTA-pair (cta_group::2) kernel with tile width xxx
+        cg2, bn = bn // 1000, bn % 1000
         if N % bn: continue
         def call():
-            rc = lib.seqdiff_op_gemm(1 | (bn << 8), M, N, K, p(A), p(W), p(bias), p(resid), epi, p(C), stream)
+            rc = lib.seqdiff_op_gemm(1 | (bn << 8) | (cg2 << 20), M, N, K, p(A), p(W), p(bias), p(resid), epi, p(C), stream)
             assert rc == 0, lib.seqdiff_last_error()
         for _ in range(3): call()
         torch.cuda.synchronize()
@@ -32,7 +33,7 @@ for name, cnt, M, N, K, epi, kind in SHAPES:
         e0.record()
         for _ in range(n): call()
         e1.record(); torch.cuda.synchronize()
-        best[bn] = e0.elapsed_time(e1) / n * 1e3
+        best[bn + 1000 * cg2] = e0.elapsed_time(e1) / n * 1e3
     fl = 2.0 * M * N * K
     bb = min(best, key=best.get)
     tot += cnt * best[bb]

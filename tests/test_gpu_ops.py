@@ -49,12 +49,15 @@ _TDT = {BF16: (torch.bfloat16, torch.bfloat16), FP16: (torch.float16, torch.floa
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 @pytest.mark.parametrize("bn", [0, 128, 192, 256])
+@pytest.mark.parametrize("cg2", [0, 1])
 @pytest.mark.parametrize("mode", [BF16, FP16])
-def test_gemm_tcgen05(M, N, K, bn, mode):
+def test_gemm_tcgen05(M, N, K, bn, cg2, mode):
     """tcgen05/TMA GEMM: 16-bit operands in each format mix; epilogues none/GELU/SiLU -> 16-bit out;
     fp32 residual add -> fp32 out (the LayerNorm-input variant)."""
     if mode != BF16 and (bn != 0 or M > 1024):
         pytest.skip("format variants share the tile code; checked at the auto tile width on the small shapes")
+    if cg2 and bn == 0:
+        pytest.skip("auto selection is exercised by the cg2=0 / bn=0 case; cg2=1 forces the CTA-pair kernel per tile width")
     if bn and N % bn:
         pytest.skip("tile width does not divide N")
     lib = sd_pkg().lib()
@@ -66,14 +69,14 @@ def test_gemm_tcgen05(M, N, K, bn, mode):
     resid = torch.randn(M, N, generator=g).to(DEV)
     for epi, r in ((0, None), (1, None), (2, None), (0, resid)):
         C = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32 if r is not None else adt)
-        _check(lib.seqdiff_op_gemm(mode | (bn << 8), M, N, K, _p(A), _p(W), _p(bias), _p(r), epi, _p(C), stream_ptr()))
+        _check(lib.seqdiff_op_gemm(mode | (bn << 8) | (cg2 << 20), M, N, K, _p(A), _p(W), _p(bias), _p(r), epi, _p(C), stream_ptr()))
         torch.cuda.synchronize()
         ref = _gemm_ref(A, W, bias, r, epi)
         err = (C.float() - ref).abs().max().item()
         scale = ref.abs().max().item()
         assert torch.isfinite(C.float()).all(), f"non-finite output epi={epi}"
         tol = 2e-5 if r is not None else (1.0 / 128 if adt == torch.bfloat16 else 1.0 / 1024)
-        assert err <= tol * scale + 1e-3 * (r is None), f"M{M} N{N} K{K} bn{bn} mode{mode} epi{epi} resid{r is not None}: err {err} scale {scale}"
+        assert err <= tol * scale + 1e-3 * (r is None), f"M{M} N{N} K{K} bn{bn} cg2{cg2} mode{mode} epi{epi} resid{r is not None}: err {err} scale {scale}"
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 768, 768), (77, 2304, 768), (33, 20, 768), (64, 768, 3072)])
