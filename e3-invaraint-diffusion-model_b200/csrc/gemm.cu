@@ -132,11 +132,12 @@ template <> __device__ __forceinline__ void store4<f16>(f16* p, const float4& v)
 }
 
 // TOut: bf16 / f16 (operand for the next GEMM or attention) or float (LayerNorm input); resid is always fp32.
-template <int BN, int EPI, bool RESID, typename TOut, bool CG2>
+// RESID: 0 none, 1 fp32 residual tensor, 2 residual = LayerNorm(resid) rebuilt from per-row (mean, rstd) + affine (g, b)
+template <int BN, int EPI, int RESID, typename TOut, bool CG2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
-                    uint32_t idesc) {
+                    uint32_t idesc, const float2* __restrict__ ln_stats, const float* __restrict__ ln_g, const float* __restrict__ ln_b) {
   using Cfg = GemmCfg<BN, CG2>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int TILE_M = CG2 ? 2 * kBM : kBM;  // rows per scheduled tile (per CTA pair / per CTA)
@@ -274,6 +275,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = row_base + 4 * i + lr;
             rres[i] = row < M ? __ldg(reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * N + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          if (RESID == 2) {  // residual = LayerNorm(resid row): same fp32 formula and op order as layernorm_kernel
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + col));
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(ln_b + col));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = row_base + 4 * i + lr;
+              const float2 st = row < M ? __ldg(ln_stats + row) : make_float2(0.f, 0.f);
+              rres[i].x = (rres[i].x - st.x) * st.y * g4.x + h4.x;
+              rres[i].y = (rres[i].y - st.x) * st.y * g4.y + h4.y;
+              rres[i].z = (rres[i].z - st.x) * st.y * g4.z + h4.z;
+              rres[i].w = (rres[i].w - st.x) * st.y * g4.w + h4.w;
+            }
+          }
         }
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
         if (!waited) {
@@ -319,9 +333,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int EPI, bool RESID, typename TOut, bool CG2>
+template <int BN, int EPI, int RESID, typename TOut, bool CG2>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, void* C, int M, int N, int K,
-                     uint32_t idesc, cudaStream_t s) {
+                     uint32_t idesc, cudaStream_t s, const LnResid* ln = nullptr) {
   using Cfg = GemmCfg<BN, CG2>;
   auto kfn = gemm_tcgen05_kernel<BN, EPI, RESID, TOut, CG2>;
   static bool configured = false;  // per instantiation
@@ -333,7 +347,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* 
   const int slots = CG2 ? num_sms() / 2 : num_sms();
   const int grid = (tiles < slots ? tiles : slots) * (CG2 ? 2 : 1);
   SD_CUDA(launch_kc(CG2 ? 2 : 1, kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K,
-                    idesc));
+                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr));
   SD_LAUNCHED(CG2 ? "gemm_tcgen05_2cta" : "gemm_tcgen05", s);
   return SEQDIFF_OK;
 }
@@ -365,29 +379,31 @@ static int pick_cfg(int M, int N, int K) {
 
 template <int BN, bool CG2>
 static int dispatch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, int epi, void* C,
-                       int out_kind, int M, int N, int K, uint32_t idesc, cudaStream_t s) {
-  if (resid) return launch_tc<BN, 0, true, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  if (out_kind == 2) return launch_tc<BN, 0, false, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+                       int out_kind, int M, int N, int K, uint32_t idesc, cudaStream_t s, const LnResid* ln) {
+  if (resid && ln) return launch_tc<BN, 0, 2, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s, ln);
+  if (resid) return launch_tc<BN, 0, 1, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (out_kind == 2) return launch_tc<BN, 0, 0, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
   if (out_kind == 1) {
-    if (epi == 0) return launch_tc<BN, 0, false, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-    if (epi == 1) return launch_tc<BN, 1, false, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-    return launch_tc<BN, 2, false, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    if (epi == 0) return launch_tc<BN, 0, 0, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    if (epi == 1) return launch_tc<BN, 1, 0, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    return launch_tc<BN, 2, 0, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
   }
-  if (epi == 0) return launch_tc<BN, 0, false, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  if (epi == 1) return launch_tc<BN, 1, false, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  return launch_tc<BN, 2, false, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (epi == 0) return launch_tc<BN, 0, 0, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (epi == 1) return launch_tc<BN, 1, 0, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  return launch_tc<BN, 2, 0, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
 }
 
 // a_fmt / w_fmt: 0 = fp16, 1 = bf16.  out_kind: 0 = fp16, 1 = bf16, 2 = fp32 (identity epilogue only; implied by resid).
 // force_cfg: 0 = auto, else  bn | (cg2 << 16)  with bn in {128,192,256} (tests / sweeps).
 int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
-            void* C, int out_kind, cudaStream_t s, int force_cfg) {
+            void* C, int out_kind, cudaStream_t s, int force_cfg, const LnResid* ln_resid) {
   SD_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
   SD_CHECK(N % 128 == 0, "tcgen05 GEMM needs N % 128 == 0");
   SD_CHECK(K % 8 == 0, "tcgen05 GEMM needs K % 8 == 0 (16B TMA pitch)");
   SD_CHECK(epi >= 0 && epi <= 2, "unknown GEMM epilogue");
   SD_CHECK(!((resid || out_kind == 2) && epi != 0), "fp32 output / residual add only with the identity epilogue");
   SD_CHECK(!(resid && out_kind != 2), "a residual GEMM writes fp32");
+  SD_CHECK(!ln_resid || (resid && ln_resid->stats && ln_resid->g && ln_resid->b), "LayerNorm-residual needs resid, stats and the affine");
   SD_CHECK(bias != nullptr, "bias required");
   SD_CHECK((a_fmt | 1) == 1 && out_kind >= 0 && out_kind <= 2, "bad operand format");
   // measured on B200: tcgen05.mma.kind::f16 with a_format != b_format faults as an illegal instruction
@@ -401,8 +417,8 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
   SD_TRY(make_tmap(W, w_fmt, N, K, cg2 ? bn / 2 : bn, &tb));
   const uint32_t idesc = umma_idesc_16(cg2 ? 2 * kBM : kBM, bn, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
 #define SD_DISPATCH(BN_)                                                                                          \
-  return cg2 ? dispatch_tc<BN_, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s)                   \
-             : dispatch_tc<BN_, false>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s)
+  return cg2 ? dispatch_tc<BN_, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)         \
+             : dispatch_tc<BN_, false>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)
   if (bn == 256) { SD_DISPATCH(256); }
   if (bn == 192) { SD_DISPATCH(192); }
   SD_DISPATCH(128);

@@ -9,8 +9,14 @@ namespace seqdiff {
 // epi: 0 identity, 1 erf-GELU, 2 SiLU.  resid (same shape as C) only with epi == 0.
 // tcgen05 GEMM on 16-bit operands.  a_fmt / w_fmt: 0 = fp16, 1 = bf16.  out_kind: 0 = fp16, 1 = bf16, 2 = fp32.
 // resid is fp32 and implies an fp32 output (the residual stream never takes a 16-bit rounding).
+// ln_resid != NULL: the residual is LayerNorm(resid) = (resid - mean) * rstd * g + b rebuilt on the fly (see LnResid).
+struct LnResid {
+  const float2* stats;  // [M] (mean, rstd) written by layernorm()
+  const float* g;       // [N] LayerNorm weight
+  const float* b;       // [N] LayerNorm bias
+};
 int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
-            void* C, int out_kind, cudaStream_t s, int force_bn = 0);
+            void* C, int out_kind, cudaStream_t s, int force_bn = 0, const LnResid* ln_resid = nullptr);
 int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* bias, const float* resid, int epi, float* C,
              cudaStream_t s);
 
@@ -29,7 +35,8 @@ int embed_ln(const float* x, int M, int fin, const float* Wt, const float* b, co
              const float* te, int L, int H, float* out32, T* outT, cudaStream_t s);
 // out = LayerNorm(in) * w + b
 template <typename T>
-int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, cudaStream_t s);
+int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, float2* stats, cudaStream_t s);
+// (stats[row] = (mean, rstd), optional: a GEMM epilogue can then rebuild LayerNorm(in) as its residual without an fp32 copy)
 // SELayer residual update (model.py:61-62):
 //   y = affine_first ? LayerNorm(in; lnw, lnb, eps1) : in          (BertSelfOutput.LayerNorm)
 //   out = x + gate * (LayerNorm_noaffine(y, 1e-5) * (1 + scale) + shift)

@@ -113,9 +113,10 @@ static int gemm_S(int, int M, int N, int K, const float* A, const Wt& W, const f
   return gemm_f32(M, N, K, A, W.f, bias, resid, 0, C, s);
 }
 template <typename T>
-static int gemm_S(int wfmt, int M, int N, int K, const T* A, const Wt& W, const float* bias, const float* resid, float* C, cudaStream_t s) {
+static int gemm_S(int wfmt, int M, int N, int K, const T* A, const Wt& W, const float* bias, const float* resid, float* C, cudaStream_t s,
+                  const LnResid* ln = nullptr) {
   const void* w = wfmt == 1 ? static_cast<const void*>(W.h) : static_cast<const void*>(W.g);
-  return gemm_16(M, N, K, A, Fmt<T>::v, w, wfmt, bias, resid, 0, C, 2, s);
+  return gemm_16(M, N, K, A, Fmt<T>::v, w, wfmt, bias, resid, 0, C, 2, s, 0, ln);
 }
 
 __global__ void set_int_kernel(int* p, int v) {
@@ -389,6 +390,7 @@ size_t Model::workspace_need(int precision, int B, int Ll, int Lr) const {
   n += align256(Mr * NL * 2 * H * es);                // kv_all
   n += 2 * (align256(Ml * H * 4) + align256(Ml * H * 2));  // decoder h ping-pong
   n += 2 * align256(Ml * H * es);                     // cq, y
+  n += align256(Ml * H * 4) + align256(Ml * 3 * 8);   // third pre-LN buffer, LayerNorm row statistics
   n += align256(Ml * I * es);                         // ffn
   (void)dual;
   return n + 8192;
@@ -508,6 +510,8 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   sb.m1 = bp.take<T>(MtH * 4);
   T* kv_all = bp.take<T>(static_cast<size_t>(Mr) * NL * 2 * H);
   Act<T> hbuf[2] = {take_act<T>(bp, MlH), take_act<T>(bp, MlH)};
+  float* obuf3 = bp.take<float>(MlH);                                   // third rotating pre-LN buffer (16-bit modes)
+  float2* lnstats = bp.take<float2>(3 * static_cast<size_t>(Ml));        // (mean, rstd) of the three LayerNorms of a layer
   T* cq = bp.take<T>(MlH);
   T* y = bp.take<T>(MlH);
   T* ffn = bp.take<T>(static_cast<size_t>(Ml) * I);
@@ -539,23 +543,61 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   // decoder: 6 x (self-attn -> cross-attn -> FFN), post-LN (HF BertLayer; model.py:226-231)
   SD_TRY(gemm_T(wfmt, Mr, NL * 2 * H, H, rec, ckv_all, ckv_all_b, 0, kv_all, s));
   Act<T> h = x2;  // ligand rows are the first Ml rows
-  for (int i = 0; i < NL; ++i) {
-    const LayerW& w = layers[i];
-    // h is dead once the self-output GEMM has folded it in as the residual, so h1/h3 may reuse its buffer
-    const Act<T> h1 = hbuf[0], h2 = hbuf[1], h3 = hbuf[0];
-    SD_TRY(gemm_T(wfmt, Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, 0, sb.qkv, s));
-    SD_TRY(attention<T>(B, heads, Ll, Ll, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s));
-    SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, h.s, sb.o, s));
-    SD_TRY(layernorm<T>(sb.o, Ml, H, w.self.ln_w, w.self.ln_b, eps, h1.s, h1.t_out(), s));
-    SD_TRY(gemm_T(wfmt, Ml, H, H, h1.t, w.cq, w.cq_b, 0, cq, s));
-    const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
-    SD_TRY(attention<T>(B, heads, Ll, Lr, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s));
-    SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.cout, w.cout_b, h1.s, sb.o, s));
-    SD_TRY(layernorm<T>(sb.o, Ml, H, w.cln_w, w.cln_b, eps, h2.s, h2.t_out(), s));
-    SD_TRY(gemm_T(wfmt, Ml, I, H, h2.t, w.inter, w.inter_b, 1, ffn, s));
-    SD_TRY(gemm_S(wfmt, Ml, H, I, ffn, w.outd, w.outd_b, h2.s, sb.o, s));
-    SD_TRY(layernorm<T>(sb.o, Ml, H, w.oln_w, w.oln_b, eps, h3.s, h3.t_out(), s));
-    h = h3;
+  if constexpr (k16) {
+    // 16-bit modes: a post-LN tensor h = LN(o) is needed (a) as the 16-bit A operand of the next GEMM and (b) in fp32 as the
+    // residual of the GEMM after that.  (b) is rebuilt inside that GEMM's epilogue from the fp32 pre-LN tensor o, the per-row
+    // (mean, rstd) the LN kernel emits and the LN affine -- the same fp32 formula, so bit-identical -- which lets the LN kernel
+    // skip its 3 KB/row fp32 copy.  o needs three buffers with fixed roles (oA, oB, oC): every GEMM reads its residual from a
+    // different buffer than the one it writes (attn_out: oC of the previous layer -> oA; cross_out: oA -> oB; ffn_down: oB -> oC).
+    float* obuf[3] = {sb.o, sb.m2, obuf3};
+    LnResid prev{};        // how to rebuild the current residual-stream value from `o_prev` (layer >= 1)
+    const float* o_prev = nullptr;
+    for (int i = 0; i < NL; ++i) {
+      const LayerW& w = layers[i];
+      const bool last = i + 1 == NL;
+      const Act<T> h1 = hbuf[0], h2 = hbuf[1], h3 = hbuf[0];
+      float* oA = obuf[0];
+      float* oB = obuf[1];
+      float* oC = obuf[2];
+      SD_TRY(gemm_T(wfmt, Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, 0, sb.qkv, s));
+      SD_TRY(attention<T>(B, heads, Ll, Ll, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s));
+      if (i == 0) SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, h.s, oA, s));
+      else SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, o_prev, oA, s, &prev));
+      SD_TRY(layernorm<T>(oA, Ml, H, w.self.ln_w, w.self.ln_b, eps, nullptr, h1.t, lnstats, s));
+      SD_TRY(gemm_T(wfmt, Ml, H, H, h1.t, w.cq, w.cq_b, 0, cq, s));
+      const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
+      SD_TRY(attention<T>(B, heads, Ll, Lr, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s));
+      const LnResid r1{lnstats, w.self.ln_w, w.self.ln_b};
+      SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.cout, w.cout_b, oA, oB, s, &r1));
+      SD_TRY(layernorm<T>(oB, Ml, H, w.cln_w, w.cln_b, eps, nullptr, h2.t, lnstats + Ml, s));
+      SD_TRY(gemm_T(wfmt, Ml, I, H, h2.t, w.inter, w.inter_b, 1, ffn, s));
+      const LnResid r2{lnstats + Ml, w.cln_w, w.cln_b};
+      SD_TRY(gemm_S(wfmt, Ml, H, I, ffn, w.outd, w.outd_b, oB, oC, s, &r2));
+      // the last layer's output feeds decoder_normalize, whose rowwise kernels read the fp32 stream: materialise it there
+      SD_TRY(layernorm<T>(oC, Ml, H, w.oln_w, w.oln_b, eps, last ? h3.s : nullptr, h3.t, lnstats + 2 * static_cast<size_t>(Ml), s));
+      prev = LnResid{lnstats + 2 * static_cast<size_t>(Ml), w.oln_w, w.oln_b};
+      o_prev = oC;
+      h = h3;
+    }
+  } else {
+    for (int i = 0; i < NL; ++i) {
+      const LayerW& w = layers[i];
+      // h is dead once the self-output GEMM has folded it in as the residual, so h1/h3 may reuse its buffer
+      const Act<T> h1 = hbuf[0], h2 = hbuf[1], h3 = hbuf[0];
+      SD_TRY(gemm_T(wfmt, Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, 0, sb.qkv, s));
+      SD_TRY(attention<T>(B, heads, Ll, Ll, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s));
+      SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, h.s, sb.o, s));
+      SD_TRY(layernorm<T>(sb.o, Ml, H, w.self.ln_w, w.self.ln_b, eps, h1.s, h1.t_out(), nullptr, s));
+      SD_TRY(gemm_T(wfmt, Ml, H, H, h1.t, w.cq, w.cq_b, 0, cq, s));
+      const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
+      SD_TRY(attention<T>(B, heads, Ll, Lr, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s));
+      SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.cout, w.cout_b, h1.s, sb.o, s));
+      SD_TRY(layernorm<T>(sb.o, Ml, H, w.cln_w, w.cln_b, eps, h2.s, h2.t_out(), nullptr, s));
+      SD_TRY(gemm_T(wfmt, Ml, I, H, h2.t, w.inter, w.inter_b, 1, ffn, s));
+      SD_TRY(gemm_S(wfmt, Ml, H, I, ffn, w.outd, w.outd_b, h2.s, sb.o, s));
+      SD_TRY(layernorm<T>(sb.o, Ml, H, w.oln_w, w.oln_b, eps, h3.s, h3.t_out(), nullptr, s));
+      h = h3;
+    }
   }
 
   // decoder_normalize: SELayer conditioned on the timestep only (c broadcast over L; model.py:232-235)

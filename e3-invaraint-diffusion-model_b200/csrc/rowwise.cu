@@ -161,7 +161,7 @@ SD_INST_EMBED(f16);
 template <typename T, int VPL>
 __global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const float* __restrict__ in, int M, int H, const float* __restrict__ w,
                                                                 const float* __restrict__ b, float eps, float* __restrict__ out32,
-                                                                T* __restrict__ outT) {
+                                                                T* __restrict__ outT, float2* __restrict__ stats) {
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int lane = threadIdx.x & 31;
@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const float* __r
   load_row<float, VPL>(in + static_cast<size_t>(row) * H, lane, v);
   float mean, rstd;
   row_stats<VPL>(v, H, eps, mean, rstd);
+  if (stats && lane == 0) stats[row] = make_float2(mean, rstd);  // lets a consumer re-derive LN(in) without the fp32 copy
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     float g8[8], b8[8];
@@ -184,13 +185,13 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const float* __r
 }
 
 template <typename T>
-int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, cudaStream_t s) {
+int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, float2* stats, cudaStream_t s) {
   const int grid = ceil_div(M * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_kernel<T, VPL>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, w, b, eps, out32, outT)));
+  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_kernel<T, VPL>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, w, b, eps, out32, outT, stats)));
   SD_LAUNCHED("layernorm", s);
   return SEQDIFF_OK;
 }
-#define SD_INST_LN(T) template int layernorm<T>(const float*, int, int, const float*, const float*, float, float*, T*, cudaStream_t)
+#define SD_INST_LN(T) template int layernorm<T>(const float*, int, int, const float*, const float*, float, float*, T*, float2*, cudaStream_t)
 SD_INST_LN(float);
 SD_INST_LN(bf16);
 SD_INST_LN(f16);
