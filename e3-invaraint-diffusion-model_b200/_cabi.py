@@ -33,6 +33,7 @@ PROTOTYPES = {
     "seqdiff_launch_count": (_u64, []),
     "seqdiff_profile_begin": (_i, [_vp]),
     "seqdiff_profile_end": (_i, [C.c_char_p, _i, C.POINTER(C.c_float), C.POINTER(C.c_int), _i]),
+    "seqdiff_debug_attn_trace": (_i, [_vp]),
     "seqdiff_model_create": (_i, [C.POINTER(SeqdiffConfig), _i, C.POINTER(_vp)]),
     "seqdiff_model_destroy": (_i, [_vp]),
     "seqdiff_model_set_tensor": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),

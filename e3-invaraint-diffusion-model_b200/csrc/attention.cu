@@ -341,16 +341,15 @@ static int attention_16(int B, int heads, int Lq, int Lk, const T* q, int ldq, c
   SD_ATTN(false);
 #undef SD_ATTN
 }
-// 16-bit modes: kernel choice per shape.  SEQDIFF_ATTN = tc | mma forces one implementation (A/B knob); default "auto":
-//   relative-key, one key block (L <= 128): legacy mma.sync kernel, two 100 KB CTAs per SM overlap fill and MMA (0.37 vs 0.43 ms
-//     per forward at cfg 2: the tcgen05 kernel holds S, Q.E^T and O in 448 TMEM columns, so only one CTA fits per SM and its
-//     MMA / softmax / PV phases do not overlap);
-//   everything else (cross-attention, several key blocks): tcgen05 kernel (attention_tc.cu).
+// 16-bit modes.  Default: the persistent pipelined tcgen05 kernel (attention_pipe.cu) for every shape.  SEQDIFF_ATTN =
+// pipe | tc | mma forces one implementation (A/B knob); "tc" = one-item-per-CTA tcgen05 kernel (attention_tc.cu), "mma" = the
+// legacy mma.sync kernel above.  Measured at cfg 2 (ms of attention per forward): mma 0.37 + tc 0.16 -> see profiles/.
 static int attn_choice() {
   static const int v = [] {
     const char* e = getenv("SEQDIFF_ATTN");
     if (!e) return 0;
-    return std::string(e) == "tc" ? 1 : (std::string(e) == "mma" ? 2 : 0);
+    const std::string c(e);
+    return c == "tc" ? 1 : (c == "mma" ? 2 : (c == "auto_r1" ? 3 : 0));
   }();
   return v;
 }
@@ -358,7 +357,9 @@ template <typename T>
 static int attention_any16(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
                            int P, const float* key_mask, T* out, cudaStream_t s) {
   const int c = attn_choice();
-  const bool legacy = c == 2 || (c == 0 && dist_emb != nullptr && Lk <= kKB);
+  if (c == 0) return attention_pipe<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  // "auto_r1": the per-shape choice before the pipelined kernel existed (legacy for one-key-block relative_key, tc otherwise)
+  const bool legacy = c == 2 || (c == 3 && dist_emb != nullptr && Lk <= kKB);
   if (legacy) return attention_16<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
   return attention_tc<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
 }

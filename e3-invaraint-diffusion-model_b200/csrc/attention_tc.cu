@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(kTcThreads, REL ? 1 : 2) attention_tc_kernel(c
   using SM = TcSmem<REL>;
   constexpr float kScale2 = 0.125f * 1.44269504088896f;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024B-align by OFFSET (not through an integer cast): keeps the pointer provably shared, so accesses compile to LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBar);
   uint64_t* bar_q = bars;       // Q landed
   uint64_t* bar_k = bars + 1;   // K (+E) of the current block landed

@@ -41,6 +41,11 @@ int seqdiff_profile_end(char* tags, int tag_stride, float* ms, int* counts, int 
   return profile_end(tags, tag_stride, ms, counts, cap);
 }
 
+int seqdiff_debug_attn_trace(void* device_buf) {
+  g_attn_trace = static_cast<unsigned long long*>(device_buf);
+  return SEQDIFF_OK;
+}
+
 int seqdiff_model_create(const seqdiff_config_t* cfg, int device, seqdiff_model_t** out) {
   SD_GUARD_BEGIN
   SD_CHECK(cfg != nullptr && out != nullptr, "null argument");

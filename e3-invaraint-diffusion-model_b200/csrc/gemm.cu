@@ -99,6 +99,29 @@ int make_tmap(const void* ptr, int fmt, int rows, int cols, int box_rows, CUtens
   return SEQDIFF_OK;
 }
 
+// [B][rows][cols] 16-bit tensor (cols contiguous): boxes of 1 x box_rows x 64 columns, 128B swizzle.  Used for TMA STORES of
+// per-graph tiles: rows past `rows` are clipped per graph instead of spilling into the next graph's rows.
+int make_tmap_3d(const void* ptr, int fmt, int batch, int rows, int cols, int box_rows, CUtensorMap* out) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return SEQDIFF_ERR_CUDA;
+  }
+  SD_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (cols % 8) == 0, "TMA operand must be 16B aligned with a 16B-multiple row pitch");
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(rows) * cols * 2};
+  cuuint32_t box[3] = {64u, static_cast<cuuint32_t>(box_rows), 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(out, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim,
+                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3d) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return SEQDIFF_ERR_CUDA;
+  }
+  return SEQDIFF_OK;
+}
+
 // =====================================================================================================
 // tcgen05 kernel
 // =====================================================================================================
@@ -142,7 +165,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int STAGES = Cfg::kStages;
   constexpr int TILE_M = CG2 ? 2 * kBM : kBM;  // rows per scheduled tile (per CTA pair / per CTA)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024B-align by OFFSET (not through an integer cast): keeps the pointer provably shared, so accesses compile to LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
@@ -152,7 +176,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();  // provably warp-uniform: the TMA / MMA role loops below stay on the uniform datapath
   const int lane = threadIdx.x & 31;
   const int num_n = N / BN;
   const int num_m = (M + TILE_M - 1) / TILE_M;
@@ -193,7 +217,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    // (whole warp runs the loop; one elected lane issues -- see common.cuh "warp-uniform single-issuer variants")
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -203,14 +228,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (CG2) {
             // both CTAs' tiles complete on the LEADER's full barrier, which the leader arms for the bytes of the pair
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            if (cta_rank == 0) mbar_expect_tx_e(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_cg2(sA + stage * Cfg::kABytes, &tmA, bar, kb * kBK, a_row);
-            tma_load_2d_cg2(sB + stage * Cfg::kBBytes, &tmB, bar, kb * kBK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+            tma_load_2d_cg2_e(sA + stage * Cfg::kABytes, &tmA, bar, kb * kBK, a_row);
+            tma_load_2d_cg2_e(sB + stage * Cfg::kBBytes, &tmB, bar, kb * kBK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
           } else {
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, a_row);
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
+            mbar_expect_tx_e(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d_e(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, a_row);
+            tma_load_2d_e(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -218,7 +243,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -236,14 +261,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
             const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
-            if (CG2) umma_cg2(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG2) umma_cg2_e(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_e(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
-          if (CG2) umma_commit_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+          if (CG2) umma_commit_mc_e(&empty_bar[stage], 3); else umma_commit_e(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CG2) umma_commit_mc(&tfull_bar[as], 3); else umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue(s)
+        if (CG2) umma_commit_mc_e(&tfull_bar[as], 3); else umma_commit_e(&tfull_bar[as]);  // accumulator complete -> epilogue(s)
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -408,7 +433,57 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
   SD_CHECK((a_fmt | 1) == 1 && out_kind >= 0 && out_kind <= 2, "bad operand format");
   // measured on B200: tcgen05.mma.kind::f16 with a_format != b_format faults as an illegal instruction
   SD_CHECK(a_fmt == w_fmt, "A and W must share one 16-bit format");
-  const int cfg = force_cfg ? force_cfg : pick_cfg(M, N, K);
+  int cfg = force_cfg;
+  if (!cfg) {
+    // First eager call of a (shape, epilogue) times every legal tile configuration on the caller's buffers and keeps the
+    // fastest (the GEMM is idempotent unless C aliases an input); under stream capture, or with SEQDIFF_GEMM_TUNE=0, the
+    // static cost model decides.  The sampling loop runs one un-captured forward before it captures its graph, so every
+    // shape of the model is tuned by then.
+    static const int tune = [] { const char* e = getenv("SEQDIFF_GEMM_TUNE"); return e ? atoi(e) : 1; }();
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, int> tuned;
+    const int rkind = resid ? (ln_resid ? 2 : 1) : 0;
+    const uint64_t key = (static_cast<uint64_t>(M) << 40) ^ (static_cast<uint64_t>(N) << 24) ^ (static_cast<uint64_t>(K) << 8) ^
+                         (static_cast<uint64_t>(epi) << 6) ^ (static_cast<uint64_t>(out_kind) << 4) ^ (static_cast<uint64_t>(rkind) << 2) ^
+                         static_cast<uint64_t>(a_fmt);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = tuned.find(key);
+      if (it != tuned.end()) cfg = it->second;
+    }
+    if (!cfg) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      SD_CUDA(cudaStreamIsCapturing(s, &cap));
+      const bool can_tune = tune && cap == cudaStreamCaptureStatusNone && M > 64 && C != A && C != static_cast<const void*>(resid);
+      if (!can_tune) {
+        cfg = pick_cfg(M, N, K);
+      } else {
+        cudaEvent_t e0, e1;
+        SD_CUDA(cudaEventCreate(&e0));
+        SD_CUDA(cudaEventCreate(&e1));
+        float best_ms = 0.f;
+        for (int cand : {128, 192, 256, 128 | (1 << 16), 192 | (1 << 16), 256 | (1 << 16)}) {
+          if (N % (cand & 0xffff)) continue;
+          float ms_min = 0.f;
+          for (int rep = 0; rep < 4; ++rep) {  // rep 0 = warm-up (kernel attributes, descriptor cache)
+            SD_CUDA(cudaEventRecord(e0, s));
+            SD_TRY(gemm_16(M, N, K, A, a_fmt, W, w_fmt, bias, resid, epi, C, out_kind, s, cand, ln_resid));
+            SD_CUDA(cudaEventRecord(e1, s));
+            SD_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            SD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && (ms_min == 0.f || ms < ms_min)) ms_min = ms;
+          }
+          if (!cfg || ms_min < best_ms) { cfg = cand; best_ms = ms_min; }
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        std::lock_guard<std::mutex> g(mu);
+        tuned[key] = cfg;
+        return SEQDIFF_OK;  // C already holds the result (every candidate wrote it)
+      }
+    }
+  }
   const int bn = cfg & 0xffff;
   const bool cg2 = (cfg >> 16) != 0;
   SD_CHECK((bn == 128 || bn == 192 || bn == 256) && N % bn == 0, "bad tile width");

@@ -22,6 +22,8 @@ int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* b
 
 // TMA descriptor (cached) of a row-major 16-bit matrix [rows, cols]: boxes of box_rows x 64 columns, 128B swizzle, OOB -> 0
 int make_tmap(const void* ptr, int fmt, int rows, int cols, int box_rows, CUtensorMap* out);
+// [batch][rows][cols] variant (uncached) for per-graph TMA stores: boxes of 1 x box_rows x 64, rows clipped per graph
+int make_tmap_3d(const void* ptr, int fmt, int batch, int rows, int cols, int box_rows, CUtensorMap* out);
 
 // ---- rowwise.cu -------------------------------------------------------------------------------------
 // GaussianFourierProjection (model.py:85-97): out[b, :] = [sin(x), cos(x)], x = ((t*W)*2)*pi in fp32.
@@ -66,6 +68,12 @@ int collate(int G, const int* offsets, const uint8_t* lig_mask, const uint8_t* p
 template <typename T>
 int attention_tc(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
                  int P, const float* key_mask, T* out, cudaStream_t s);
+extern unsigned long long* g_attn_trace;  // debug timeline buffer of the pipelined kernel (NULL = off)
+// ---- attention_pipe.cu: persistent, warp-specialised version (TMA / MMA / softmax roles pipelined over work items) -----
+template <typename T>
+int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
+                   int P, const float* key_mask, T* out, cudaStream_t s);
+
 
 // ---- reverse_step.cu --------------------------------------------------------------------------------
 // step_ptr != NULL: tables/noise are indexed by *step_ptr (entry stride 1200 / N*20) and the launch is a

@@ -75,6 +75,9 @@ SEQDIFF_API uint64_t seqdiff_launch_count(void);
  * returns per-kernel-tag totals: tags[i*tag_stride..] (NUL-terminated), ms[i], counts[i]; result = #tags or <0. */
 SEQDIFF_API int seqdiff_profile_begin(void* stream);
 SEQDIFF_API int seqdiff_profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap);
+/* debug: device buffer of 4 x 1024 uint64 that CTA 0 of the pipelined attention kernel fills with its role timelines
+ * (slot 0 of each role = event count, then (SM clock << 8 | event id)); NULL (default) switches tracing off. */
+SEQDIFF_API int seqdiff_debug_attn_trace(void* device_buf);
 
 /* ---- model handle: replaces ConditionalBertForDiffusionBase.__init__ + load_state_dict ---------
  * sequence_model/model.py:156-181, sample.py:106.  Tensor names are the reference state_dict keys

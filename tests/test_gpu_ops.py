@@ -103,17 +103,19 @@ ATTN_CASES = [
     # B, heads, Lq, Lk, P, rel
     (2, 12, 128, 128, 128, True), (3, 12, 64, 64, 64, True), (2, 12, 128, 128, 128, False), (2, 12, 64, 128, 128, False),
     (2, 4, 100, 100, 128, True), (1, 12, 512, 512, 512, True), (2, 12, 48, 464, 512, False), (2, 2, 17, 17, 32, True),
+    # more work items than SMs: several items per persistent CTA (pipelined kernel), one and several key blocks
+    (40, 12, 128, 128, 128, True), (40, 12, 128, 128, 128, False), (5, 12, 300, 300, 512, True), (7, 12, 200, 464, 512, False),
 ]
 
 
 def test_attention_both_16bit_kernels_subprocess():
     """the per-shape dispatch hides one of the two 16-bit kernels for some shapes: run the op tests with each one forced."""
     import subprocess, sys
-    for impl in ("tc", "mma"):
-        env = dict(os.environ, SEQDIFF_ATTN=impl)
+    for impl, grid in (("tc", "0"), ("mma", "0"), ("pipe", "3")):  # pipe with 3 CTAs: every CTA walks a long item list
+        env = dict(os.environ, SEQDIFF_ATTN=impl, SEQDIFF_ATTN_GRID=grid)
         r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "test_attention and not subprocess", "-p",
                             "no:cacheprovider"], env=env, capture_output=True, text=True)
-        assert r.returncode == 0, f"SEQDIFF_ATTN={impl}:\n" + r.stdout[-2000:]
+        assert r.returncode == 0, f"SEQDIFF_ATTN={impl} SEQDIFF_ATTN_GRID={grid}:\n" + r.stdout[-2000:]
 
 
 @pytest.mark.parametrize("B,heads,Lq,Lk,P,rel", ATTN_CASES)
@@ -139,6 +141,41 @@ def test_attention(B, heads, Lq, Lk, P, rel, prec):
     assert torch.isfinite(out.float()).all()
     tol = {FP32: 2e-5, BF16: 2e-2, FP16: 3e-3}[prec]
     assert rel_err(out, ref) < tol, rel_err(out, ref)
+
+
+@pytest.mark.parametrize("rel", [True, False])
+@pytest.mark.parametrize("prec", [BF16, FP16])
+def test_attention_pipelined_repeatable(rel, prec):
+    """The pipelined kernel hands buffers between roles through mbarriers; a missing edge shows up as a timing-dependent
+    difference.  Same inputs, 40 launches under varying cache state / co-running work: every output must be bit-identical."""
+    lib = sd_pkg().lib()
+    B, heads, L, P = 37, 12, 128, 128
+    H = heads * 64
+    g = torch.Generator().manual_seed(11 + int(rel))
+    dt = {BF16: torch.bfloat16, FP16: torch.float16}[prec]
+    qkv = torch.randn(B * L, 3 * H, generator=g).to(DEV).to(dt)
+    E = (torch.randn(2 * P - 1, 64, generator=g) * 0.5).to(DEV).to(dt) if rel else None
+    nk = torch.randint(1, L + 1, (B,), generator=g)
+    mask = (torch.arange(L)[None, :] < nk[:, None]).float().to(DEV)
+    junk = torch.empty(64 << 20, dtype=torch.uint8, device=DEV)
+    first = None
+    for i in range(40):
+        out = torch.full((B, L, H), float("nan"), device=DEV, dtype=dt)
+        if i % 3 == 1:
+            junk.zero_()  # cold L2
+        _check(lib.seqdiff_op_attention(prec, B, heads, L, L, _p(qkv), 3 * H, _p(qkv[:, H:]), 3 * H, _p(qkv[:, 2 * H:]), 3 * H, _p(E), P,
+                                        _p(mask), _p(out), stream_ptr()))
+        if i % 3 == 2:
+            junk.zero_()  # memory traffic right behind the launch
+        torch.cuda.synchronize()
+        if first is None:
+            first = out
+            q, k, v = (qkv[:, j * H:(j + 1) * H].float().cpu().view(B, L, H) for j in range(3))
+            cfg = O.OracleConfig(hidden_size=H, num_attention_heads=heads, max_position_embeddings=P)
+            ref = O.attention_core(cfg, q, k, v, O.extend_mask(mask.cpu()), None if E is None else E.float().cpu())
+            assert rel_err(out, ref) < {BF16: 2e-2, FP16: 3e-3}[prec]
+        else:
+            assert torch.equal(out, first), f"launch {i} differs from launch 0"
 
 
 # ---------------------------------------------------------------------------------------------------
