@@ -19,6 +19,7 @@
 // fp32 path (parity gate 1e-5): plain SIMT tiled kernel, fp32 FMA accumulation.
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -134,15 +135,26 @@ constexpr int kGemmThreads = 320;
 // of A and HALF of the B tile (the MMA reads both halves across the pair), so a CTA pulls 16 KB + BN/2 * 128 B per k-block
 // from L2 for 128 x BN x 64 MACs -- 2/3 of the 1-CTA traffic at BN = 256.  The mainloop of this model's GEMMs is bound by
 // exactly that L2 -> SM operand stream (profiles/prof_gemm_r01.summary.txt).
+// BN = 384 / 512 (CTA pairs only): the tile is wider than one UMMA (N <= 256), so every k-step issues kNSub = 2 MMAs of
+// kSubN = BN / 2 columns into adjacent TMEM column ranges.  The accumulator then fills most of TMEM (one stage: the epilogue
+// is not overlapped with a next tile) -- these shapes exist for the M = 8192 GEMMs with N = 768 / 1024, where 256 x 384 /
+// 256 x 512 pair tiles cover the whole problem in ONE wave of 128 CTAs (vs 2 ragged waves of 128 x 192) and pull 40 / 48 KB
+// per CTA per k-block for 3 / 4 x the MACs of a 128 x 128 tile.
 template <int BN, bool CG2> struct GemmCfg {
-  static constexpr int kBRows = CG2 ? BN / 2 : BN;
-  static constexpr int kStages = CG2 ? 6 : ((BN == 256 || BN == 192) ? 4 : 6);
+  static constexpr int kNSub = BN > 256 ? 2 : 1;
+  static constexpr int kSubN = BN / kNSub;                         // N of one tcgen05.mma
+  static constexpr int kBoxRows = CG2 ? kSubN / 2 : kSubN;         // rows of one B TMA box (per CTA)
+  static constexpr int kBRows = kBoxRows * kNSub;                  // B rows staged per CTA per k-block
+  static constexpr int kAccStages = BN > 256 ? 1 : 2;
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // two accumulator stages, rounded up to a power of two
+  static constexpr int kStages = BN > 256 ? 4 : (CG2 ? 6 : ((BN == 256 || BN == 192) ? 4 : 6));
+  static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // accumulator stage(s), rounded up to a power of two
   static constexpr int kStagingBytes = 8 * 32 * 32 * 4;  // one 32x32 fp32 transpose panel per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
+  static_assert(BN <= 256 || CG2, "tiles wider than one UMMA are built for CTA pairs only");
+  static_assert(kSmemBytes <= 232448, "over the 227 KB shared-memory limit");
 };
 
 template <typename T> __device__ __forceinline__ void store4(T* p, const float4& v);
@@ -160,7 +172,8 @@ template <int BN, int EPI, int RESID, typename TOut, bool CG2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
-                    uint32_t idesc, const float2* __restrict__ ln_stats, const float* __restrict__ ln_g, const float* __restrict__ ln_b) {
+                    uint32_t idesc, const float2* __restrict__ ln_stats, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                    unsigned long long* __restrict__ trace) {
   using Cfg = GemmCfg<BN, CG2>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int TILE_M = CG2 ? 2 * kBM : kBM;  // rows per scheduled tile (per CTA pair / per CTA)
@@ -186,6 +199,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
+  // optional timeline (debug, seqdiff_debug_attn_trace): CTA 0, lane 0 of the TMA / MMA / two epilogue warps
+  int tr_n = 0;
+  const bool tr_on = trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6);
+  const int tr_base = (warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : 3) * 1024;
+  auto TR = [&](int id) {
+    if (tr_on && tr_n < 1023) trace[tr_base + 1 + tr_n++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned>(id);
+  };
+  TR(40);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -212,8 +233,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CG2) cluster_sync_all(); else __syncthreads();  // barriers of BOTH CTAs initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  TR(41);
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
+  TR(42);
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -226,12 +249,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * kBM;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          TR(1);
           if (CG2) {
             // both CTAs' tiles complete on the LEADER's full barrier, which the leader arms for the bytes of the pair
             if (cta_rank == 0) mbar_expect_tx_e(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
             tma_load_2d_cg2_e(sA + stage * Cfg::kABytes, &tmA, bar, kb * kBK, a_row);
-            tma_load_2d_cg2_e(sB + stage * Cfg::kBBytes, &tmB, bar, kb * kBK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+#pragma unroll
+            for (int j = 0; j < Cfg::kNSub; ++j)  // half of each UMMA's B tile lives in each CTA of the pair
+              tma_load_2d_cg2_e(sB + stage * Cfg::kBBytes + j * Cfg::kBoxRows * kBK * 2, &tmB, bar, kb * kBK,
+                                n_blk * BN + j * Cfg::kSubN + static_cast<int>(cta_rank) * Cfg::kBoxRows);
           } else {
             mbar_expect_tx_e(&full_bar[stage], Cfg::kStageBytes);
             tma_load_2d_e(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, a_row);
@@ -255,21 +282,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          TR(11);
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
-            const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
-            if (CG2) umma_cg2_e(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16_e(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < Cfg::kNSub; ++j) {
+              const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + j * Cfg::kBoxRows * kBK * 2 + k * kUmmaK * 2);
+              if (CG2) umma_cg2_e(tmem_d + j * Cfg::kSubN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_e(tmem_d + j * Cfg::kSubN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
           if (CG2) umma_commit_mc_e(&empty_bar[stage], 3); else umma_commit_e(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (CG2) umma_commit_mc_e(&tfull_bar[as], 3); else umma_commit_e(&tfull_bar[as]);  // accumulator complete -> epilogue(s)
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        TR(12);
+        if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
   } else {
@@ -285,71 +317,117 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int lr = lane >> 3, lc = lane & 7;
     int as = 0;
     uint32_t aphase = 0;
+    constexpr int NCH = BN / 64;  // 32-column chunks per warp and tile
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * kBM + q * 32;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-      bool waited = false;
-#pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-        const int col = n_blk * BN + c + 4 * lc;
-        float4 rres[8];
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN) + half * (BN / 2);
+      const int col0 = n_blk * BN + half * (BN / 2) + 4 * lc;  // this lane's 4 columns of chunk 0; chunk ci adds 32 ci
+      const bool full = row_base + 32 <= M;                    // warp-uniform: no row of this warp's slab is out of range
+      // Everything the tile needs from global memory that does not depend on the accumulator is fetched BEFORE the wait
+      // on the MMAs (LayerNorm row statistics, the first chunk's bias / residual); inside the chunk loop the next chunk's
+      // bias / residual / LayerNorm affine and the next chunk's TMEM load are in flight while the current chunk is transposed and
+      // stored.  (Timeline before: 1450 cycles per chunk, i.e. an epilogue as long as a K = 768 mainloop.)
+      float2 st8[8];
+      if (RESID == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + 4 * i + lr;
+          st8[i] = row < M ? __ldg(ln_stats + row) : make_float2(0.f, 0.f);
+        }
+      }
+      float4 rres[2][8], g4[2], h4[2], b4[2];
+      auto fetch_resid = [&](int ci, int buf) {
+        b4[buf] = __ldg(reinterpret_cast<const float4*>(bias + col0 + 32 * ci));
         if (RESID) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = row_base + 4 * i + lr;
-            rres[i] = row < M ? __ldg(reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * N + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rres[buf][i] = row < M ? __ldg(reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * N + col0 + 32 * ci))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (RESID == 2) {  // residual = LayerNorm(resid row): same fp32 formula and op order as layernorm_kernel
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + col));
-            const float4 h4 = __ldg(reinterpret_cast<const float4*>(ln_b + col));
+          if (RESID == 2) {
+            g4[buf] = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + 32 * ci));
+            h4[buf] = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + 32 * ci));
+          }
+        }
+      };
+      fetch_resid(0, 0);
+      TR(20);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      TR(21);
+      // the TMEM load is double-buffered only without a residual (the residual prefetch already takes 32 registers per
+      // buffer and the kernel is capped at 168: 320 threads are allocated as 12 warps)
+      constexpr bool kPrefT = RESID == 0;
+      uint32_t r[kPrefT ? 2 : 1][32];
+      if (kPrefT) tmem_ld_32x32(t_row, r[0]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = row_base + 4 * i + lr;
-              const float2 st = row < M ? __ldg(ln_stats + row) : make_float2(0.f, 0.f);
-              rres[i].x = (rres[i].x - st.x) * st.y * g4.x + h4.x;
-              rres[i].y = (rres[i].y - st.x) * st.y * g4.y + h4.y;
-              rres[i].z = (rres[i].z - st.x) * st.y * g4.z + h4.z;
-              rres[i].w = (rres[i].w - st.x) * st.y * g4.w + h4.w;
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int cur = ci & 1;
+        const int tc = kPrefT ? cur : 0;
+        if (ci + 1 < NCH) fetch_resid(ci + 1, cur ^ 1);
+        if (!kPrefT) tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * ci), r[0]);
+        tmem_ld_wait();
+        if (kPrefT && ci + 1 < NCH) tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * (ci + 1)), r[tc ^ 1]);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          *reinterpret_cast<uint4*>(stage + lane * 32 + ((jj ^ (lane & 7)) << 2)) =
+              make_uint4(r[tc][4 * jj], r[tc][4 * jj + 1], r[tc][4 * jj + 2], r[tc][4 * jj + 3]);
+        __syncwarp();
+        const int col = col0 + 32 * ci;
+        // rows in two groups of four: the four smem reads of a group are issued back to back (one dependent chain per row
+        // serialised the whole chunk on LDS latency) and the stores of a full tile carry no per-row bounds branch
+        auto emit_rows = [&](auto guard_tag) {
+          constexpr bool kGuard = decltype(guard_tag)::value;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int rr = 4 * (4 * hh + u) + lr;
+              v[u] = *reinterpret_cast<const float4*>(stage + rr * 32 + ((lc ^ (rr & 7)) << 2));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = 4 * hh + u;
+              v[u].x += b4[cur].x; v[u].y += b4[cur].y; v[u].z += b4[cur].z; v[u].w += b4[cur].w;
+              if (EPI == 1) { v[u].x = gelu_fast(v[u].x); v[u].y = gelu_fast(v[u].y); v[u].z = gelu_fast(v[u].z); v[u].w = gelu_fast(v[u].w); }
+              if (EPI == 2) { v[u].x = silu_fast(v[u].x); v[u].y = silu_fast(v[u].y); v[u].z = silu_fast(v[u].z); v[u].w = silu_fast(v[u].w); }
+              if (RESID) {
+                float4 rv = rres[cur][i];
+                if (RESID == 2) {  // residual = LayerNorm(resid row): same fp32 formula and op order as layernorm_kernel
+                  rv.x = (rv.x - st8[i].x) * st8[i].y * g4[cur].x + h4[cur].x;
+                  rv.y = (rv.y - st8[i].x) * st8[i].y * g4[cur].y + h4[cur].y;
+                  rv.z = (rv.z - st8[i].x) * st8[i].y * g4[cur].z + h4[cur].z;
+                  rv.w = (rv.w - st8[i].x) * st8[i].y * g4[cur].w + h4[cur].w;
+                }
+                v[u].x += rv.x; v[u].y += rv.y; v[u].z += rv.z; v[u].w += rv.w;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = row_base + 4 * (4 * hh + u) + lr;
+              if (!kGuard || row < M) store4<TOut>(C + static_cast<size_t>(row) * N + col, v[u]);
             }
           }
-        }
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
-        if (!waited) {
-          mbar_wait(&tfull_bar[as], aphase);
-          tc_fence_after();
-          waited = true;
-        }
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + static_cast<uint32_t>(c), r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + lr;
-          float4 v = *reinterpret_cast<const float4*>(stage + rr * 32 + ((lc ^ (rr & 7)) << 2));
-          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-          if (EPI == 1) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
-          if (EPI == 2) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-          if (RESID) { v.x += rres[i].x; v.y += rres[i].y; v.z += rres[i].z; v.w += rres[i].w; }
-          const int row = row_base + rr;
-          if (row < M) store4<TOut>(C + static_cast<size_t>(row) * N + col, v);
-        }
+        };
+        if (full) emit_rows(std::false_type{}); else emit_rows(std::true_type{});
         __syncwarp();
       }
+      TR(23);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CG2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));  // the leader's MMA thread waits on it
         else mbar_arrive(&tempty_bar[as]);
       }
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
   }
 
+  TR(43);
+  if (tr_on) trace[tr_base] = static_cast<unsigned long long>(tr_n);
   tc_fence_before();
   if (CG2) cluster_sync_all(); else __syncthreads();  // pair: nobody frees TMEM / exits while the other CTA may still signal or read
   if (warp == 1) {
@@ -372,7 +450,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* 
   const int slots = CG2 ? num_sms() / 2 : num_sms();
   const int grid = (tiles < slots ? tiles : slots) * (CG2 ? 2 : 1);
   SD_CUDA(launch_kc(CG2 ? 2 : 1, kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K,
-                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr));
+                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace));
   SD_LAUNCHED(CG2 ? "gemm_tcgen05_2cta" : "gemm_tcgen05", s);
   return SEQDIFF_OK;
 }
@@ -462,7 +540,7 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
         SD_CUDA(cudaEventCreate(&e0));
         SD_CUDA(cudaEventCreate(&e1));
         float best_ms = 0.f;
-        for (int cand : {128, 192, 256, 128 | (1 << 16), 192 | (1 << 16), 256 | (1 << 16)}) {
+        for (int cand : {128, 192, 256, 128 | (1 << 16), 192 | (1 << 16), 256 | (1 << 16), 384 | (1 << 16), 512 | (1 << 16)}) {
           if (N % (cand & 0xffff)) continue;
           float ms_min = 0.f;
           for (int rep = 0; rep < 4; ++rep) {  // rep 0 = warm-up (kernel attributes, descriptor cache)
@@ -486,14 +564,17 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
   }
   const int bn = cfg & 0xffff;
   const bool cg2 = (cfg >> 16) != 0;
-  SD_CHECK((bn == 128 || bn == 192 || bn == 256) && N % bn == 0, "bad tile width");
+  SD_CHECK((bn == 128 || bn == 192 || bn == 256 || ((bn == 384 || bn == 512) && cg2)) && N % bn == 0, "bad tile width");
   CUtensorMap ta, tb;
   SD_TRY(make_tmap(A, a_fmt, M, K, kBM, &ta));
-  SD_TRY(make_tmap(W, w_fmt, N, K, cg2 ? bn / 2 : bn, &tb));
-  const uint32_t idesc = umma_idesc_16(cg2 ? 2 * kBM : kBM, bn, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
+  const int sub_n = bn > 256 ? bn / 2 : bn;  // N of one tcgen05.mma
+  SD_TRY(make_tmap(W, w_fmt, N, K, cg2 ? sub_n / 2 : sub_n, &tb));
+  const uint32_t idesc = umma_idesc_16(cg2 ? 2 * kBM : kBM, sub_n, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
 #define SD_DISPATCH(BN_)                                                                                          \
   return cg2 ? dispatch_tc<BN_, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)         \
              : dispatch_tc<BN_, false>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)
+  if (bn == 512) return dispatch_tc<512, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid);
+  if (bn == 384) return dispatch_tc<384, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid);
   if (bn == 256) { SD_DISPATCH(256); }
   if (bn == 192) { SD_DISPATCH(192); }
   SD_DISPATCH(128);

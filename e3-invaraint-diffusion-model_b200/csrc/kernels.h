@@ -29,12 +29,26 @@ int make_tmap_3d(const void* ptr, int fmt, int batch, int rows, int cols, int bo
 // GaussianFourierProjection (model.py:85-97): out[b, :] = [sin(x), cos(x)], x = ((t*W)*2)*pi in fp32.
 // t = timestep[b], or (float)*step_ptr for every b when step_ptr != NULL (sampling loop, quirk Q3).
 int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, cudaStream_t s);
-// BertEmbeddings (model.py:110-117): out = LN(x @ Wt + b) (+ te[row / L]); Wt is the [fin, H] transpose.
-// Rowwise kernels read the fp32 residual stream and may write BOTH an fp32 copy (out32: the stream) and a
-// T copy (outT: the operand of the next GEMM); either pointer may be NULL.
-template <typename T>
-int embed_ln(const float* x, int M, int fin, const float* Wt, const float* b, const float* lnw, const float* lnb, float eps,
-             const float* te, int L, int H, float* out32, T* outT, cudaStream_t s);
+// BertEmbeddings (model.py:110-117): out = LN(x @ Wt + b) (+ te[row / L]); Wt is the [fin, H] transpose.  Up to four
+// embeddings (jobs) run in one launch.  Rowwise kernels read the fp32 residual stream and may write BOTH an fp32 copy
+// (out32: the stream) and a T copy (outT: the operand of the next GEMM); either pointer may be NULL.
+struct EmbedJob {
+  const float* x;       // [M, fin]
+  const float* Wt;      // [fin, H]
+  const float* b;       // [H]
+  const float* lnw;     // [H]
+  const float* lnb;     // [H]
+  const float* te;      // [M / L, H] added after the LayerNorm, or NULL
+  float* out32;         // [M, H] or NULL
+  void* outT;           // [M, H] operand-typed copy or NULL
+  int M, fin, L;
+  int cta_begin, cta_count;  // filled by embed_ln_multi
+};
+struct EmbedJobs {
+  EmbedJob j[4];
+  int n;
+};
+template <typename T> int embed_ln_multi(EmbedJobs jobs, float eps, int H, cudaStream_t s);
 // out = LayerNorm(in) * w + b
 template <typename T>
 int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, float2* stats, cudaStream_t s);

@@ -519,13 +519,22 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   // timestep features + the four BertEmbeddings (model.py:211-213,219-220)
   SD_TRY(timestep_embed(timestep, step_ptr, ts_W, B, H, te, s));
   const Act<T> xr = offset(x, MlH);
-  SD_TRY(embed_ln<T>(x_t, Ml, 20, lig_seq.Wt_, lig_seq.b, lig_seq.ln_w, lig_seq.ln_b, eps, nullptr, Ll, H, x.s, x.t_out(), s));
-  SD_TRY(embed_ln<T>(rec_seq_in, Mr, 20, rec_seq.Wt_, rec_seq.b, rec_seq.ln_w, rec_seq.ln_b, eps, nullptr, Lr, H, xr.s, xr.t_out(), s));
-  // the conditioning c = LN(Linear(angles)) + te only ever feeds a GEMM: operand type only
-  SD_TRY(embed_ln<T>(lig_angle, Ml, 8, lig_ang.Wt_, lig_ang.b, lig_ang.ln_w, lig_ang.ln_b, eps, te, Ll, H,
-                     k16 ? nullptr : reinterpret_cast<float*>(ccat), k16 ? ccat : nullptr, s));
-  SD_TRY(embed_ln<T>(rec_angle, Mr, 8, rec_ang.Wt_, rec_ang.b, rec_ang.ln_w, rec_ang.ln_b, eps, te, Lr, H,
-                     k16 ? nullptr : reinterpret_cast<float*>(ccat + MlH), k16 ? ccat + MlH : nullptr, s));
+  {
+    auto job = [&](const float* in, int M, const EmbW& e, const float* te_, int L, float* o32, T* oT) {
+      EmbedJob jb{};
+      jb.x = in; jb.Wt = e.Wt_; jb.b = e.b; jb.lnw = e.ln_w; jb.lnb = e.ln_b; jb.te = te_;
+      jb.out32 = o32; jb.outT = oT; jb.M = M; jb.fin = e.fin; jb.L = L;
+      return jb;
+    };
+    EmbedJobs jobs{};
+    jobs.n = 4;
+    jobs.j[0] = job(x_t, Ml, lig_seq, nullptr, Ll, x.s, x.t_out());
+    jobs.j[1] = job(rec_seq_in, Mr, rec_seq, nullptr, Lr, xr.s, xr.t_out());
+    // the conditioning c = LN(Linear(angles)) + te only ever feeds a GEMM: operand type only
+    jobs.j[2] = job(lig_angle, Ml, lig_ang, te, Ll, k16 ? nullptr : reinterpret_cast<float*>(ccat), k16 ? ccat : nullptr);
+    jobs.j[3] = job(rec_angle, Mr, rec_ang, te, Lr, k16 ? nullptr : reinterpret_cast<float*>(ccat + MlH), k16 ? ccat + MlH : nullptr);
+    SD_TRY(embed_ln_multi<T>(jobs, eps, H, s));
+  }
 
   // ligand_feature_emb on ligand AND receptor tokens in one pass (model.py:214-224, quirk Q1)
   std::vector<Segment> segs;

@@ -64,71 +64,89 @@ int timestep_embed(const float* timestep, const int* step_ptr, const float* W, i
 }
 
 // ---------------------------------------------------------------------------------------------------
-// BertEmbeddings: 4 tokens per warp pass so each weight vector load is reused 4x.
+// BertEmbeddings (model.py:110-117), all embeddings of a forward in ONE launch.  A CTA serves one job (one embedding
+// table): it stages that table's transposed weight [fin, H] in shared memory once -- before the PDL wait, weights do not
+// depend on the predecessor -- and then walks the job's tokens, 4 tokens per warp pass so every weight vector read from
+// smem is used 4x.  Input columns that are zero for all 4 tokens are skipped (adding 0 * w is exact): the one-hot sequence
+// inputs touch at most 4 of their 20 weight rows.  (Before: every warp streamed the whole 61 KB table from L2 for its 4
+// tokens, 250 MB per launch, 27 us x 4 launches per forward.)
 template <typename T, int VPL>
-__global__ void __launch_bounds__(kRowThreads) embed_ln_kernel(const float* __restrict__ x, int M, int fin,
-                                                               const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                               const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                                               float eps, const float* __restrict__ te, int L, int H,
-                                                               float* __restrict__ out32, T* __restrict__ outT) {
+__global__ void __launch_bounds__(kRowThreads) embed_ln_multi_kernel(const __grid_constant__ EmbedJobs jobs, float eps, int H) {
+  extern __shared__ float4 sW4[];
+  float* sW = reinterpret_cast<float*>(sW4);
+  int q = 0;
+#pragma unroll
+  for (int t = 1; t < 4; ++t)
+    if (t < jobs.n && static_cast<int>(blockIdx.x) >= jobs.j[t].cta_begin) q = t;
+  const EmbedJob& job = jobs.j[q];
+  const int fin = job.fin, M = job.M;
+  for (int i = threadIdx.x; i < fin * H / 4; i += kRowThreads) sW4[i] = __ldg(reinterpret_cast<const float4*>(job.Wt) + i);
   pdl_trigger();
-  pdl_wait();  // predecessor grid complete + flushed before any dependent global access
+  pdl_wait();  // inputs / timestep features come from the predecessor kernels
+  __syncthreads();
   constexpr int TOK = 4;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
-  const int tok0 = warp * TOK;
-  if (tok0 >= M) return;
-  float acc[TOK][VPL][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cta_local = static_cast<int>(blockIdx.x) - job.cta_begin;
+  T* outT = static_cast<T*>(job.outT);
+  for (int grp = cta_local * (kRowThreads / 32) + warp; grp * TOK < M; grp += job.cta_count * (kRowThreads / 32)) {
+    const int tok0 = grp * TOK;
+    float acc[TOK][VPL][8];
 #pragma unroll
-  for (int t = 0; t < TOK; ++t)
+    for (int t = 0; t < TOK; ++t)
 #pragma unroll
-    for (int i = 0; i < VPL; ++i)
+      for (int i = 0; i < VPL; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[t][i][j] = 0.f;
-  for (int k = 0; k < fin; ++k) {
-    float xv[TOK];
+        for (int jj = 0; jj < 8; ++jj) acc[t][i][jj] = 0.f;
+    for (int k = 0; k < fin; ++k) {
+      float xv[TOK];
+      bool any = false;
 #pragma unroll
-    for (int t = 0; t < TOK; ++t) xv[t] = (tok0 + t < M) ? __ldg(x + static_cast<size_t>(tok0 + t) * fin + k) : 0.f;
+      for (int t = 0; t < TOK; ++t) {
+        xv[t] = (tok0 + t < M) ? __ldg(job.x + static_cast<size_t>(tok0 + t) * fin + k) : 0.f;
+        any |= xv[t] != 0.f;
+      }
+      if (!any) continue;  // warp-uniform (every lane holds the same xv)
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float w[8];
-      load8<float>(Wt + static_cast<size_t>(k) * H + (i * 32 + lane) * 8, w);
+      for (int i = 0; i < VPL; ++i) {
+        float w[8];
+        load8<float>(sW + static_cast<size_t>(k) * H + (i * 32 + lane) * 8, w);
 #pragma unroll
-      for (int t = 0; t < TOK; ++t)
+        for (int t = 0; t < TOK; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][i][j] = fmaf(xv[t], w[j], acc[t][i][j]);
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < TOK; ++t) {
-    if (tok0 + t >= M) break;
-    float v[VPL][8];
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float b8[8];
-      load8<float>(bias + (i * 32 + lane) * 8, b8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = acc[t][i][j] + b8[j];
-    }
-    float mean, rstd;
-    row_stats<VPL>(v, H, eps, mean, rstd);
-    const float* terow = te ? te + static_cast<size_t>((tok0 + t) / L) * H : nullptr;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float g8[8], b8[8];
-      load8<float>(lnw + (i * 32 + lane) * 8, g8);
-      load8<float>(lnb + (i * 32 + lane) * 8, b8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * g8[j] + b8[j];
-      if (terow) {
-        float t8[8];
-        load8<float>(terow + (i * 32 + lane) * 8, t8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] += t8[j];
+          for (int jj = 0; jj < 8; ++jj) acc[t][i][jj] = fmaf(xv[t], w[jj], acc[t][i][jj]);
       }
     }
-    if (out32) store_row<float, VPL>(out32 + static_cast<size_t>(tok0 + t) * H, lane, v);
-    if (outT) store_row<T, VPL>(outT + static_cast<size_t>(tok0 + t) * H, lane, v);
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) {
+      if (tok0 + t >= M) break;
+      float v[VPL][8];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float b8[8];
+        load8<float>(job.b + (i * 32 + lane) * 8, b8);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) v[i][jj] = acc[t][i][jj] + b8[jj];
+      }
+      float mean, rstd;
+      row_stats<VPL>(v, H, eps, mean, rstd);
+      const float* terow = job.te ? job.te + static_cast<size_t>((tok0 + t) / job.L) * H : nullptr;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float g8[8], b8[8];
+        load8<float>(job.lnw + (i * 32 + lane) * 8, g8);
+        load8<float>(job.lnb + (i * 32 + lane) * 8, b8);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) v[i][jj] = (v[i][jj] - mean) * rstd * g8[jj] + b8[jj];
+        if (terow) {
+          float t8[8];
+          load8<float>(terow + (i * 32 + lane) * 8, t8);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) v[i][jj] += t8[jj];
+        }
+      }
+      if (job.out32) store_row<float, VPL>(job.out32 + static_cast<size_t>(tok0 + t) * H, lane, v);
+      if (outT) store_row<T, VPL>(outT + static_cast<size_t>(tok0 + t) * H, lane, v);
+    }
   }
 }
 
@@ -142,20 +160,47 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_kernel(const float* __re
   }
 
 template <typename T>
-int embed_ln(const float* x, int M, int fin, const float* Wt, const float* b, const float* lnw, const float* lnb, float eps,
-             const float* te, int L, int H, float* out32, T* outT, cudaStream_t s) {
+int embed_ln_multi(EmbedJobs jobs, float eps, int H, cudaStream_t s) {
   SD_CHECK(H % 256 == 0, "hidden_size must be a multiple of 256");
-  const int warps = ceil_div(M, 4);
-  const int grid = ceil_div(warps * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(embed_ln_kernel<T, VPL>, dim3(grid), dim3(kRowThreads), 0, s, x, M, fin, Wt, b, lnw, lnb, eps, te, L, H, out32, outT)));
+  SD_CHECK(jobs.n >= 1 && jobs.n <= 4, "1..4 embedding jobs per launch");
+  // CTAs are shared out in proportion to the rows each job writes; one resident CTA per SM in total
+  long total = 0;
+  int max_fin = 0;
+  for (int q = 0; q < jobs.n; ++q) {
+    SD_CHECK(jobs.j[q].M > 0 && jobs.j[q].fin > 0 && jobs.j[q].fin <= 32 && jobs.j[q].L > 0, "bad embedding job");
+    total += jobs.j[q].M;
+    max_fin = jobs.j[q].fin > max_fin ? jobs.j[q].fin : max_fin;
+  }
+  const int budget = num_sms();  // ~170 registers x 256 threads: one CTA per SM
+  int begin = 0;
+  for (int q = 0; q < jobs.n; ++q) {
+    int c = static_cast<int>(static_cast<long>(budget) * jobs.j[q].M / total);
+    const int need = ceil_div(jobs.j[q].M, 4 * (kRowThreads / 32));
+    if (c < 1) c = 1;
+    if (c > need) c = need;
+    jobs.j[q].cta_begin = begin;
+    jobs.j[q].cta_count = c;
+    begin += c;
+  }
+  const size_t smem = static_cast<size_t>(max_fin) * H * sizeof(float);
+#define SD_EMBED_LAUNCH()                                                                                                          \
+  {                                                                                                                                \
+    auto kfn = embed_ln_multi_kernel<T, VPL>;                                                                                      \
+    static bool configured = false;                                                                                                \
+    if (!configured) {                                                                                                             \
+      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4));                              \
+      configured = true;                                                                                                           \
+    }                                                                                                                              \
+    SD_CUDA(launch_k(kfn, dim3(begin), dim3(kRowThreads), smem, s, jobs, eps, H));                                                 \
+  }
+  SD_VPL_DISPATCH(H, SD_EMBED_LAUNCH());
+#undef SD_EMBED_LAUNCH
   SD_LAUNCHED("embed_ln", s);
   return SEQDIFF_OK;
 }
-#define SD_INST_EMBED(T) \
-  template int embed_ln<T>(const float*, int, int, const float*, const float*, const float*, const float*, float, const float*, int, int, float*, T*, cudaStream_t)
-SD_INST_EMBED(float);
-SD_INST_EMBED(bf16);
-SD_INST_EMBED(f16);
+template int embed_ln_multi<float>(EmbedJobs, float, int, cudaStream_t);
+template int embed_ln_multi<bf16>(EmbedJobs, float, int, cudaStream_t);
+template int embed_ln_multi<f16>(EmbedJobs, float, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int VPL>
@@ -261,53 +306,93 @@ SD_INST_LNMOD(bf16);
 SD_INST_LNMOD(f16);
 
 // ---------------------------------------------------------------------------------------------------
+// W2 [F, H] is staged in shared memory once per CTA (before the PDL wait) and every CTA walks its share of the rows, 4 rows
+// per warp pass so each weight vector read from smem serves 4 rows.  (Before: one row per warp, each warp streaming all of
+// W2 -- 61 KB -- from L2: 500 MB and 54 us per launch for 126 MFLOP.)
 template <typename T, int VPL>
 __global__ void __launch_bounds__(kRowThreads) predictor_tail_kernel(const T* __restrict__ y, int M, int H, const float* __restrict__ lnw,
                                                                      const float* __restrict__ lnb, float eps,
                                                                      const float* __restrict__ W2, const float* __restrict__ b2, int F,
                                                                      float* __restrict__ logits) {
+  extern __shared__ float4 sW4[];
+  float* sW = reinterpret_cast<float*>(sW4);
+  for (int i = threadIdx.x; i < F * H / 4; i += kRowThreads) sW4[i] = __ldg(reinterpret_cast<const float4*>(W2) + i);
+  float* sG = sW + static_cast<size_t>(F) * H;  // LayerNorm weight | bias
+  for (int i = threadIdx.x; i < H; i += kRowThreads) {
+    sG[i] = __ldg(lnw + i);
+    sG[H + i] = __ldg(lnb + i);
+  }
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
-  const int lane = threadIdx.x & 31;
-  const int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
-  if (row >= M) return;
-  float v[VPL][8];
-  load_row<T, VPL>(y + static_cast<size_t>(row) * H, lane, v);
-  float mean, rstd;
-  row_stats<VPL>(v, H, eps, mean, rstd);
+  __syncthreads();
+  constexpr int ROWS = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float bias_f = lane < F ? b2[lane] : 0.f;
+  for (int grp = blockIdx.x * (kRowThreads / 32) + warp; grp * ROWS < M; grp += gridDim.x * (kRowThreads / 32)) {
+    const int row0 = grp * ROWS;
+    float v[ROWS][VPL][8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    float g8[8], b8[8];
-    load8<float>(lnw + (i * 32 + lane) * 8, g8);
-    load8<float>(lnb + (i * 32 + lane) * 8, b8);
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = row0 + r < M ? row0 + r : M - 1;  // tail rows recompute the last row (not stored)
+      load_row<T, VPL>(y + static_cast<size_t>(row) * H, lane, v[r]);
+      float mean, rstd;
+      row_stats<VPL>(v[r], H, eps, mean, rstd);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * g8[j] + b8[j];
-  }
-  float mine = 0.f;  // lane f keeps logit f
-  for (int f = 0; f < F; ++f) {
-    float p = 0.f;
+      for (int i = 0; i < VPL; ++i) {
+        float g8[8], be8[8];
+        load8<float>(sG + (i * 32 + lane) * 8, g8);
+        load8<float>(sG + H + (i * 32 + lane) * 8, be8);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float w[8];
-      load8<float>(W2 + static_cast<size_t>(f) * H + (i * 32 + lane) * 8, w);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) p = fmaf(v[i][j], w[j], p);
+        for (int jj = 0; jj < 8; ++jj) v[r][i][jj] = (v[r][i][jj] - mean) * rstd * g8[jj] + be8[jj];
+      }
     }
-    p = warp_sum(p);
-    if (lane == (f & 31)) {
-      mine = p + b2[f];
-      if (f >= 32) logits[static_cast<size_t>(row) * F + f] = mine;  // F > 32 never happens for this model
+    float mine[ROWS];  // lane f keeps logit f of each row
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) mine[r] = 0.f;
+    for (int f = 0; f < F; ++f) {
+      float p[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) p[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float w[8];
+        load8<float>(sW + static_cast<size_t>(f) * H + (i * 32 + lane) * 8, w);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) p[r] = fmaf(v[r][i][jj], w[jj], p[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        p[r] = warp_sum(p[r]);
+        if (lane == f) mine[r] = p[r] + bias_f;
+      }
     }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+      if (lane < F && row0 + r < M) logits[static_cast<size_t>(row0 + r) * F + lane] = mine[r];
   }
-  if (lane < F && lane < 32) logits[static_cast<size_t>(row) * F + lane] = mine;
 }
 
 template <typename T>
 int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb, float eps, const float* W2, const float* b2, int F,
                    float* logits, cudaStream_t s) {
   SD_CHECK(F <= 32, "feature_size > 32 not supported");
-  const int grid = ceil_div(M * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(predictor_tail_kernel<T, VPL>, dim3(grid), dim3(kRowThreads), 0, s, y, M, H, lnw, lnb, eps, W2, b2, F, logits)));
+  const int need = ceil_div(M, 4 * (kRowThreads / 32));
+  const int grid = need < num_sms() ? need : num_sms();  // ~185 registers x 256 threads: one CTA per SM
+  const size_t smem = (static_cast<size_t>(F) + 2) * H * sizeof(float);
+#define SD_PRED_LAUNCH()                                                                                              \
+  {                                                                                                                   \
+    auto kfn = predictor_tail_kernel<T, VPL>;                                                                         \
+    static bool configured = false;                                                                                   \
+    if (!configured) {                                                                                                \
+      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 34 * 1024 * 4));                 \
+      configured = true;                                                                                              \
+    }                                                                                                                 \
+    SD_CUDA(launch_k(kfn, dim3(grid), dim3(kRowThreads), smem, s, y, M, H, lnw, lnb, eps, W2, b2, F, logits));        \
+  }
+  SD_VPL_DISPATCH(H, SD_PRED_LAUNCH());
+#undef SD_PRED_LAUNCH
   SD_LAUNCHED("predictor_tail", s);
   return SEQDIFF_OK;
 }

@@ -31,13 +31,18 @@ for name, cnt, B, Lq, Lk, P, rel in SHAPES:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); call(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
+    gr = torch.cuda.CUDAGraph()  # device time per launch: 20 launches captured in a graph (eager launches are CPU-bound)
+    with torch.cuda.graph(gr):
+        st2 = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(20):
+            rc = lib.seqdiff_op_attention(1, B, heads, Lq, Lk, p(qkv), 3 * H, p(qkv[:, H:]), 3 * H, p(qkv[:, 2 * H:]), 3 * H, p(E), P, p(mask), p(out), st2)
+            assert rc == 0, lib.seqdiff_last_error()
+    gr.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20): call()
-    e1.record(); torch.cuda.synchronize()
+    e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
     warm = e0.elapsed_time(e1) / 20 * 1e3
     fl = B * heads * (4.0 + (4.0 if rel else 0.0)) * Lq * Lk * 64
     cold = sorted(ts)[len(ts) // 2]
     tot += cnt * warm if Lq == 128 else 0
-    print(f"{name:36s} x{cnt} B={B:4d} L={Lq:4d} rel={int(rel)}  cold {cold:7.1f} us  back-to-back {warm:7.1f} us  {fl / warm / 1e6:7.1f} TF/s")
-print(f"impl={os.environ.get('SEQDIFF_ATTN', 'default')}  cfg2 attention per forward (back-to-back): {tot/1e3:.3f} ms")
+    print(f"{name:36s} x{cnt} B={B:4d} L={Lq:4d} rel={int(rel)}  cold {cold:7.1f} us  graph x20 {warm:7.1f} us  {fl / warm / 1e6:7.1f} TF/s")
+print(f"impl={os.environ.get('SEQDIFF_ATTN', 'default')}  cfg2 attention per forward (graph x20): {tot/1e3:.3f} ms")
