@@ -150,7 +150,7 @@ __device__ __noinline__ int soft_row_class(const float* __restrict__ lg_row, con
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* __restrict__ q_tables, int n_tab, int L,
+__global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel(const float* __restrict__ q_tables, int n_tab, int L,
                                                                    const float* __restrict__ x_t, const float* __restrict__ logits,
                                                                    int diverse, const float* __restrict__ noise_E, uint64_t seed,
                                                                    uint64_t graph_id0, uint32_t step, const int* __restrict__ step_ptr,
@@ -158,12 +158,18 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   __shared__ float sQt[C * C], sQsb[C * C], sQtb[C * C];
-  // [x][i][j] with an odd x-stride: lanes holding different x_t classes then read 32 different banks (stride 400
-  // would fold all classes onto 2 banks -- measured 16-way conflicts, 567 GB/s)
-  // (exact: odd stride 401, scalar reads.  fast: stride 404 keeps rows 16 B aligned for 128-bit reads; lanes whose classes
-  //  differ by 8 then share banks -- about 1.5-way on random classes, against 4x fewer load instructions)
-  constexpr int kXS = FAST ? C * C + 4 : C * C + 1;
-  __shared__ __align__(16) float sPost[C * kXS];
+  // exact mode: post[x][i][j] = Qt[j,x] Qsb[i,j] / Qtb[i,x] with the reference's rounding sequence, odd x-stride (401: lanes
+  // holding different x_t classes read 32 different banks; stride 400 folded all classes onto 2 banks -- 16-way conflicts).
+  // fast mode never builds that 32 KB table (its 8000-entry build per CTA and its 1.6 KB of lane-private smem reads per
+  // residue were the bound: 20 us per 131072 residues).  It factors the posterior as
+  //     un[j] = Qt[j,x] * sum_i (p_i / Qtb[i,x]) * Qsb[i,j]
+  // so the 400-term inner product reads Qsb only -- the SAME address in every lane (smem broadcast) -- and the two
+  // x-dependent factors are one 20-float row each of the transposed tables InvT[x][i] = 1 / Qtb[i,x], QtT[x][j] = Qt[j,x].
+  constexpr int kXS = C * C + 1;
+  constexpr int kRS = C + 4;  // row stride of the transposed tables: rows stay 16 B aligned
+  __shared__ float sPost[FAST ? 1 : C * kXS];
+  __shared__ __align__(16) float sInvT[FAST ? C * kRS : 4], sQtT[FAST ? C * kRS : 4];
+  __shared__ __align__(16) float sQsbA[FAST ? C * C : 4];  // 16 B aligned copy of Qsb for 128-bit broadcast reads
   const int b = blockIdx.y;  // grid = (ceil(L / 128) residue chunks, graphs): enough CTAs to stream at HBM rate
   const size_t n_res = static_cast<size_t>(gridDim.y) * L;
   if (step_ptr) {
@@ -180,22 +186,20 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
     sQtb[i] = tab[2 * C * C + i];
   }
   __syncthreads();
-  __shared__ float sInv[FAST ? C * C : 1];
-  if (FAST) {  // reciprocals of the denominators once (400 instead of 8000 divisions)
+  if (FAST) {
     for (int e = threadIdx.x; e < C * C; e += kRevThreads) {
+      const int r = e / C, x = e - r * C;  // r = i for Qtb[i,x], r = j for Qt[j,x]
       const float den = sQtb[e];
-      sInv[e] = rcp_approx(den == 0.f ? 1e-6f : den);
+      sInvT[x * kRS + r] = rcp_approx(den == 0.f ? 1e-6f : den);
+      sQtT[x * kRS + r] = sQt[e];
+      sQsbA[e] = sQsb[e];
     }
-    __syncthreads();
-  }
-  for (int e = threadIdx.x; e < C * C; e += kRevThreads) {  // (i, j) fixed per thread, x runs: no div/mod in the inner loop
-    const int i = e / C, j = e - i * C;
-    const float qsb = sQsb[e];
+  } else {
+    for (int e = threadIdx.x; e < C * C; e += kRevThreads) {  // (i, j) fixed per thread, x runs: no div/mod in the inner loop
+      const int i = e / C, j = e - i * C;
+      const float qsb = sQsb[e];
 #pragma unroll 4
-    for (int x = 0; x < C; ++x) {
-      if (FAST) {
-        sPost[x * kXS + e] = sQt[j * C + x] * qsb * sInv[i * C + x];
-      } else {
+      for (int x = 0; x < C; ++x) {
         float den = sQtb[i * C + x];
         if (den == 0.f) den = 1e-6f;
         sPost[x * kXS + e] = __fdiv_rn(__fmul_rn(sQt[j * C + x], qsb), den);
@@ -235,17 +239,29 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_kernel(const float* 
         continue;
       }
       {
-        const float4* post4 = reinterpret_cast<const float4*>(sPost + hotf * kXS);
+        const float4* inv4 = reinterpret_cast<const float4*>(sInvT + hotf * kRS);
+        const float4* qt4 = reinterpret_cast<const float4*>(sQtT + hotf * kRS);
+        const float4* qsb4 = reinterpret_cast<const float4*>(sQsbA);
 #pragma unroll
-        for (int i = 0; i < C; ++i) {  // fully unrolled: pf[i] must stay in registers (a partial unroll spills it to local memory)
+        for (int i4 = 0; i4 < C / 4; ++i4) {  // a_i = p_i / Qtb[i,x]
+          const float4 w = inv4[i4];
+          pf[4 * i4] *= w.x; pf[4 * i4 + 1] *= w.y; pf[4 * i4 + 2] *= w.z; pf[4 * i4 + 3] *= w.w;
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {  // fully unrolled: pf[i] must stay in registers
 #pragma unroll
           for (int j4 = 0; j4 < C / 4; ++j4) {
-            const float4 w = post4[i * (C / 4) + j4];
+            const float4 w = qsb4[i * (C / 4) + j4];  // same address in every lane: broadcast
             unf[4 * j4] = fmaf(pf[i], w.x, unf[4 * j4]);
             unf[4 * j4 + 1] = fmaf(pf[i], w.y, unf[4 * j4 + 1]);
             unf[4 * j4 + 2] = fmaf(pf[i], w.z, unf[4 * j4 + 2]);
             unf[4 * j4 + 3] = fmaf(pf[i], w.w, unf[4 * j4 + 3]);
           }
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < C / 4; ++j4) {
+          const float4 w = qt4[j4];
+          unf[4 * j4] *= w.x; unf[4 * j4 + 1] *= w.y; unf[4 * j4 + 2] *= w.z; unf[4 * j4 + 3] *= w.w;
         }
       }
       float totf = 0.f;
@@ -337,7 +353,7 @@ int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_
                  uint8_t* idx_out, cudaStream_t s) {
   SD_CHECK(B > 0 && L > 0, "empty reverse step");
   SD_CHECK(n_tab == 1 || n_tab == B, "q_tables must hold 1 or B (Qt,Qsb,Qtb) triples");
-  static const int rpt = [] { const char* e = getenv("SEQDIFF_REV_RPT"); return e ? atoi(e) : 2; }();
+  static const int rpt = [] { const char* e = getenv("SEQDIFF_REV_RPT"); return e ? atoi(e) : 2; }();  // residues per thread
   const dim3 grid(ceil_div(L, rpt * kRevThreads), B);  // residues per thread: amortises the per-CTA table build
   if (diverse && !noise_E)
     SD_CUDA(launch_k(reverse_step_kernel<true>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out));

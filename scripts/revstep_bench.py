@@ -19,9 +19,14 @@ for name, tabs in (("shared table (sampling loop)", tabs1), ("per-graph tables",
     call = lambda: lib.seqdiff_reverse_step(p(tabs), tabs.shape[0], B, L, p(x), p(lg), 1, None, 5, 0, 1, p(out), None, st)
     for _ in range(3): call()
     torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()  # device time: launches captured in a graph (eager launches from Python are CPU-bound at this size)
+    with torch.cuda.graph(gr):
+        st2 = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(n_iter):
+            rc = lib.seqdiff_reverse_step(p(tabs), tabs.shape[0], B, L, p(x), p(lg), 1, None, 5, 0, 1, p(out), None, st2)
+            assert rc == 0
+    gr.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n_iter): call()
-    e1.record(); torch.cuda.synchronize()
+    e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n_iter * 1e3
     print(f"{name}: {us:.1f} us/launch  {B*L*240/us/1e3:.0f} GB/s algorithmic ({B*L} residues x 240 B)")
