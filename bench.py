@@ -348,14 +348,22 @@ def main():
             rout = torch.empty_like(rx)
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             p = sd._cabi.ptr
-            raw = lambda: lib.seqdiff_reverse_step(p(tabs), RB, RB, RL, p(rx), p(rlg), 1, None, 5, 0, 1, p(rout), None, stream)
+            raw = lambda st=stream: lib.seqdiff_reverse_step(p(tabs), RB, RB, RL, p(rx), p(rlg), 1, None, 5, 0, 1, p(rout), None, st)
             for _ in range(3):
                 raw()
+            torch.cuda.synchronize(dev)
+            # device time per launch: 50 launches captured in a CUDA graph (50 eager launches from Python are bound by the
+            # interpreter, not by the 10 us kernel), CUDA events around the replay on the launching stream
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                cst = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                for _ in range(50):
+                    assert raw(cst) == 0
+            gr.replay()
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(dev)
             r0.record()
-            for _ in range(50):
-                raw()
+            gr.replay()
             r1.record()
             torch.cuda.synchronize(dev)
             rus = r0.elapsed_time(r1) / 50 * 1e3

@@ -1,4 +1,4 @@
-# round-end evidence run: full GPU tests, smoke, headline bench, cfg3 bench, ncu launch list + full captures
+# round-end evidence run: full GPU tests, smoke, headline bench, cfg3 bench, ncu launch list (caches left warm between kernels) + full captures
 set +e
 mkdir -p gpurun_out
 R=${ROUND:-r01}
@@ -13,7 +13,7 @@ timeout 600 python scripts/gemm_sweep.py > gpurun_out/gemm_sweep_$R.log 2>&1
 timeout 300 python scripts/revstep_bench.py > gpurun_out/revstep_$R.log 2>&1; cat gpurun_out/revstep_$R.log
 PCMD="python bench.py --steps 1 --warmup 1 --timesteps 4 --no-extras"
 timeout 600 $PCMD > gpurun_out/plain.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 700 --launch-count 230 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --launch-skip 700 --launch-count 240 --csv \
     --log-file gpurun_out/launches_$R.csv $PCMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?"
 timeout 600 $PCMD > gpurun_out/plain2.log 2>&1 && \
