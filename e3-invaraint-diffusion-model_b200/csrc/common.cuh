@@ -273,6 +273,27 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- cluster-scope helpers for epilogue-only exchanges between the CTAs of a cluster (distributed shared memory) ------
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// wait for a phase completed by (possibly remote) release.cluster arrivals; makes the peers' prior DSMEM writes visible
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();
+  } while (!done);
+}
+
 // ---- PTX: CTA pairs (cta_group::2) -- one tcgen05.mma spans the two SMs of a cluster of 2 -------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

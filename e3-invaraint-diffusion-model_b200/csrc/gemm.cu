@@ -152,7 +152,10 @@ template <int BN, bool CG2> struct GemmCfg {
   static constexpr int kStages = BN > 256 ? 4 : (CG2 ? 6 : ((BN == 256 || BN == 192) ? 4 : 6));
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // accumulator stage(s), rounded up to a power of two
   static constexpr int kStagingBytes = 8 * 32 * 32 * 4;  // one 32x32 fp32 transpose panel per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
+  // fused-LayerNorm exchange area (used by the LNOUT instantiations only; 10.3 KB): [2 halves][128] float2 CTA-local partials,
+  // [2 tile parities][4 source CTAs][128] float2 cluster partials, 2 mbarriers
+  static constexpr int kLnBytes = 2 * 128 * 8 + 2 * 4 * 128 * 8 + 64;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes + (BN <= 256 && !CG2 ? kLnBytes : 0);
   static_assert(BN <= 256 || CG2, "tiles wider than one UMMA are built for CTA pairs only");
   static_assert(kSmemBytes <= 232448, "over the 227 KB shared-memory limit");
 };
@@ -168,13 +171,25 @@ template <> __device__ __forceinline__ void store4<f16>(f16* p, const float4& v)
 
 // TOut: bf16 / f16 (operand for the next GEMM or attention) or float (LayerNorm input); resid is always fp32.
 // RESID: 0 none, 1 fp32 residual tensor, 2 residual = LayerNorm(resid) rebuilt from per-row (mean, rstd) + affine (g, b)
-template <int BN, int EPI, int RESID, typename TOut, bool CG2>
+// TH != void: fused output LayerNorm (LnOut in kernels.h).  The grid is then made of clusters of kLnCl = 4 CTAs; CTA r of a
+// cluster owns column quarter r (N == 4 * BN) of the cluster's row blocks.
+constexpr int kLnCl = 4;
+struct LnOutArgs {
+  const float* g;
+  const float* b;
+  float eps;
+  void* h;
+  float2* stats;
+};
+template <int BN, int EPI, int RESID, typename TOut, bool CG2, typename TH = void>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
                     uint32_t idesc, const float2* __restrict__ ln_stats, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                    unsigned long long* __restrict__ trace) {
+                    unsigned long long* __restrict__ trace, const LnOutArgs lno) {
   using Cfg = GemmCfg<BN, CG2>;
+  constexpr bool LNOUT = !std::is_void<TH>::value;
+  static_assert(!LNOUT || (!CG2 && RESID != 0 && EPI == 0 && std::is_same<TOut, float>::value), "fused LayerNorm: 1-CTA MMA, fp32 C with residual");
   constexpr int STAGES = Cfg::kStages;
   constexpr int TILE_M = CG2 ? 2 * kBM : kBM;  // rows per scheduled tile (per CTA pair / per CTA)
   extern __shared__ uint8_t smem_raw[];
@@ -196,8 +211,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + kBK - 1) / kBK;
   const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
+  // LNOUT: CTA r of cluster c walks tiles (m = c, c + #clusters, ...; n = r) -- with num_n == kLnCl that is tile c * 4 + r, step 4 * #clusters
   const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  float2* ln_cpart = reinterpret_cast<float2*>(smem + STAGES * Cfg::kStageBytes + 256 + Cfg::kStagingBytes);  // [2][128]
+  float2* ln_xpart = ln_cpart + 2 * 128;                                                                       // [2][4][128]
+  uint64_t* ln_bar = reinterpret_cast<uint64_t*>(ln_xpart + 2 * 4 * 128);                                      // [2]
 
   // optional timeline (debug, seqdiff_debug_attn_trace): CTA 0, lane 0 of the TMA / MMA / two epilogue warps
   int tr_n = 0;
@@ -217,6 +236,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], CG2 ? 16 : 8);  // one arrival per epilogue warp (of both CTAs of a pair)
+      if (LNOUT) mbar_init(&ln_bar[i], kLnCl * 128);  // 128 row-owner threads of each CTA of the cluster
     }
     fence_mbar_init();
   }
@@ -230,7 +250,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
   tc_fence_before();
-  if (CG2) cluster_sync_all(); else __syncthreads();  // barriers of BOTH CTAs initialised before any remote arrive / TMA signal
+  if (CG2 || LNOUT) cluster_sync_all(); else __syncthreads();  // barriers of every CTA of the cluster initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   TR(41);
@@ -429,7 +449,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   TR(43);
   if (tr_on) trace[tr_base] = static_cast<unsigned long long>(tr_n);
   tc_fence_before();
-  if (CG2) cluster_sync_all(); else __syncthreads();  // pair: nobody frees TMEM / exits while the other CTA may still signal or read
+  if (CG2 || LNOUT) cluster_sync_all(); else __syncthreads();  // cluster: nobody frees TMEM / exits while a peer may still signal, read or write here
   if (warp == 1) {
     tc_fence_after();
     if (CG2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);

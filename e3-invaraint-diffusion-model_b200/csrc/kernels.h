@@ -15,8 +15,19 @@ struct LnResid {
   const float* g;       // [N] LayerNorm weight
   const float* b;       // [N] LayerNorm bias
 };
+// ln_out != NULL (needs resid, fp32 C, N in {512, 768, 1024}): the kernel also applies the LayerNorm that FOLLOWS this
+// Linear -- h = LN(C) * g + b written as the 16-bit operand of the next GEMM, (mean, rstd) per row for a later LnResid
+// rebuild -- so the separate layernorm() launch and its re-read of C disappear.  Four CTAs of a cluster cover the 4 column
+// quarters of a 128-row block and exchange per-row partial sums through distributed shared memory.
+struct LnOut {
+  const float* g;   // [N] LayerNorm weight
+  const float* b;   // [N] LayerNorm bias
+  float eps;
+  void* h;          // [M, N] 16-bit output (format = a_fmt)
+  float2* stats;    // [M] (mean, rstd)
+};
 int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
-            void* C, int out_kind, cudaStream_t s, int force_bn = 0, const LnResid* ln_resid = nullptr);
+            void* C, int out_kind, cudaStream_t s, int force_bn = 0, const LnResid* ln_resid = nullptr, const LnOut* ln_out = nullptr);
 int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* bias, const float* resid, int epi, float* C,
              cudaStream_t s);
 
