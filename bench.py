@@ -263,12 +263,17 @@ def main():
     barrier()
     n0 = lib.seqdiff_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = os.environ.get("SEQDIFF_PROFILER_RANGE") == "1"  # ncu --profile-from-start off: capture the timed region only
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStart()
     with ClockSampler(local) as clk:
         e0.record()
         for _ in range(args.steps):
             out = one_sampling()
         e1.record()
         barrier()
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = lib.seqdiff_launch_count() - n0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:

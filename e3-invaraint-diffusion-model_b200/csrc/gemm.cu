@@ -140,7 +140,7 @@ constexpr int kGemmThreads = 320;
 // is not overlapped with a next tile) -- these shapes exist for the M = 8192 GEMMs with N = 768 / 1024, where 256 x 384 /
 // 256 x 512 pair tiles cover the whole problem in ONE wave of 128 CTAs (vs 2 ragged waves of 128 x 192) and pull 40 / 48 KB
 // per CTA per k-block for 3 / 4 x the MACs of a 128 x 128 tile.
-template <int BN, bool CG2> struct GemmCfg {
+template <int BN, bool CG2, bool LN = false> struct GemmCfg {
   static constexpr int kNSub = BN > 256 ? 2 : 1;
   static constexpr int kSubN = BN / kNSub;                         // N of one tcgen05.mma
   static constexpr int kBoxRows = CG2 ? kSubN / 2 : kSubN;         // rows of one B TMA box (per CTA)
@@ -149,13 +149,14 @@ template <int BN, bool CG2> struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN > 256 ? 4 : (CG2 ? 6 : ((BN == 256 || BN == 192) ? 4 : 6));
+  // (the fused-LayerNorm instantiations give one stage of the deepest rings to their 10 KB exchange area)
+  static constexpr int kStages = BN > 256 ? 4 : (CG2 ? 6 : (BN == 256 ? (LN ? 3 : 4) : (BN == 192 ? 4 : (LN ? 5 : 6))));
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // accumulator stage(s), rounded up to a power of two
   static constexpr int kStagingBytes = 8 * 32 * 32 * 4;  // one 32x32 fp32 transpose panel per epilogue warp
   // fused-LayerNorm exchange area (used by the LNOUT instantiations only; 10.3 KB): [2 halves][128] float2 CTA-local partials,
   // [2 tile parities][4 source CTAs][128] float2 cluster partials, 2 mbarriers
   static constexpr int kLnBytes = 2 * 128 * 8 + 2 * 4 * 128 * 8 + 64;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes + (BN <= 256 && !CG2 ? kLnBytes : 0);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes + (LN ? kLnBytes : 0);
   static_assert(BN <= 256 || CG2, "tiles wider than one UMMA are built for CTA pairs only");
   static_assert(kSmemBytes <= 232448, "over the 227 KB shared-memory limit");
 };
@@ -187,8 +188,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
                     uint32_t idesc, const float2* __restrict__ ln_stats, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                     unsigned long long* __restrict__ trace, const LnOutArgs lno) {
-  using Cfg = GemmCfg<BN, CG2>;
   constexpr bool LNOUT = !std::is_void<TH>::value;
+  using Cfg = GemmCfg<BN, CG2, LNOUT>;
   static_assert(!LNOUT || (!CG2 && RESID != 0 && EPI == 0 && std::is_same<TOut, float>::value), "fused LayerNorm: 1-CTA MMA, fp32 C with residual");
   constexpr int STAGES = Cfg::kStages;
   constexpr int TILE_M = CG2 ? 2 * kBM : kBM;  // rows per scheduled tile (per CTA pair / per CTA)
@@ -337,6 +338,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int lr = lane >> 3, lc = lane & 7;
     int as = 0;
     uint32_t aphase = 0;
+    int ln_it = 0;  // tiles finished by this CTA (fused LayerNorm exchange parity / phase)
+    (void)ln_it;
     constexpr int NCH = BN / 64;  // 32-column chunks per warp and tile
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -356,23 +359,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           st8[i] = row < M ? __ldg(ln_stats + row) : make_float2(0.f, 0.f);
         }
       }
-      float4 rres[2][8], g4[2], h4[2], b4[2];
-      auto fetch_resid = [&](int ci, int buf) {
+      // bias / LayerNorm affine of a chunk: double-buffered, fetched one chunk ahead.  Residual: ONE buffer of 8 float4, each
+      // entry re-filled for the next chunk right after it has been consumed (a second buffer costs 32 registers and spills).
+      float4 rres[8], g4[2], h4[2], b4[2];
+      auto fetch_small = [&](int ci, int buf) {
         b4[buf] = __ldg(reinterpret_cast<const float4*>(bias + col0 + 32 * ci));
-        if (RESID) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = row_base + 4 * i + lr;
-            rres[buf][i] = row < M ? __ldg(reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * N + col0 + 32 * ci))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (RESID == 2) {
-            g4[buf] = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + 32 * ci));
-            h4[buf] = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + 32 * ci));
-          }
+        if (RESID == 2) {
+          g4[buf] = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + 32 * ci));
+          h4[buf] = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + 32 * ci));
         }
       };
-      fetch_resid(0, 0);
+      auto fetch_resid_row = [&](int ci, int i) {
+        const int row = row_base + 4 * i + lr;
+        rres[i] = (full || row < M) ? __ldg(reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * N + col0 + 32 * ci))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      fetch_small(0, 0);
+      if (RESID) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fetch_resid_row(0, i);
+      }
+      float rs[LNOUT ? 8 : 1], rq[LNOUT ? 8 : 1];  // fused LayerNorm: this lane's partial row sums / sums of squares (8 rows x 4 cols x NCH chunks)
+      if (LNOUT) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+      }
       TR(20);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -386,7 +397,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int ci = 0; ci < NCH; ++ci) {
         const int cur = ci & 1;
         const int tc = kPrefT ? cur : 0;
-        if (ci + 1 < NCH) fetch_resid(ci + 1, cur ^ 1);
+        if (ci + 1 < NCH) fetch_small(ci + 1, cur ^ 1);
         if (!kPrefT) tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * ci), r[0]);
         tmem_ld_wait();
         if (kPrefT && ci + 1 < NCH) tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * (ci + 1)), r[tc ^ 1]);
@@ -415,7 +426,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (EPI == 1) { v[u].x = gelu_fast(v[u].x); v[u].y = gelu_fast(v[u].y); v[u].z = gelu_fast(v[u].z); v[u].w = gelu_fast(v[u].w); }
               if (EPI == 2) { v[u].x = silu_fast(v[u].x); v[u].y = silu_fast(v[u].y); v[u].z = silu_fast(v[u].z); v[u].w = silu_fast(v[u].w); }
               if (RESID) {
-                float4 rv = rres[cur][i];
+                float4 rv = rres[i];
+                if (ci + 1 < NCH) fetch_resid_row(ci + 1, i);  // refill this slot for the next chunk
                 if (RESID == 2) {  // residual = LayerNorm(resid row): same fp32 formula and op order as layernorm_kernel
                   rv.x = (rv.x - st8[i].x) * st8[i].y * g4[cur].x + h4[cur].x;
                   rv.y = (rv.y - st8[i].x) * st8[i].y * g4[cur].y + h4[cur].y;
@@ -423,6 +435,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   rv.w = (rv.w - st8[i].x) * st8[i].y * g4[cur].w + h4[cur].w;
                 }
                 v[u].x += rv.x; v[u].y += rv.y; v[u].z += rv.z; v[u].w += rv.w;
+              }
+              if (LNOUT) {
+                rs[i] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+                rq[i] = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, fmaf(v[u].w, v[u].w, rq[i]))));
               }
             }
 #pragma unroll
@@ -441,6 +457,89 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) {
         if (CG2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));  // the leader's MMA thread waits on it
         else mbar_arrive(&tempty_bar[as]);
+      }
+      if constexpr (LNOUT) {
+        // ---- fused LayerNorm of the rows just written (C = pre-LN tensor o; see LnOut in kernels.h) ----
+        // (1) row sums of this warp's 32 x BN/2 slab: reduce over the 8 lanes that share a row, park them in smem
+        const int et = static_cast<int>(threadIdx.x) - 64;  // epilogue thread 0..255
+        const int par = ln_it & 1;                          // exchange buffers alternate per tile
+        // (0) re-read of the tile's pre-LN values for the normalisation pass, issued NOW so that its L2 round trip runs under
+        //     the reduction and the cluster exchange.  Each lane reads back exactly the elements it stored in pass A
+        //     (program order makes them visible; C is not read through the non-coherent path).
+        float4 vc[NCH][8];
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + 4 * i + lr;
+            vc[ci][i] = (full || row < M) ? *reinterpret_cast<const float4*>(C + static_cast<size_t>(row) * N + col0 + 32 * ci)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int off = 1; off < 8; off <<= 1) {
+            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], off);
+            rq[i] += __shfl_xor_sync(0xffffffffu, rq[i], off);
+          }
+        if (lc == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ln_cpart[half * 128 + q * 32 + 4 * i + lr] = make_float2(rs[i], rq[i]);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
+        // (2) one thread per row adds the two column halves and pushes the CTA's partial into every CTA of the cluster
+        if (et < 128) {
+          const float2 a = ln_cpart[et], b2 = ln_cpart[128 + et];
+          const uint32_t my = cluster_ctarank();
+#pragma unroll
+          for (uint32_t pr = 0; pr < kLnCl; ++pr) {
+            st_cluster_f32x2(mapa_u32(smem_u32(&ln_xpart[(par * kLnCl + static_cast<int>(my)) * 128 + et]), pr), a.x + b2.x, a.y + b2.y);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&ln_bar[par]), pr));  // release.cluster: orders the store above
+          }
+        }
+        TR(24);
+        // (3) all four column quarters of these 128 rows have arrived
+        mbar_wait_cluster(&ln_bar[par], static_cast<uint32_t>(ln_it >> 1) & 1u);
+        TR(25);
+        // (4) statistics of this lane's 8 rows (fp32 sums over N; variance as E[x^2] - mean^2, clamped at 0)
+        float mean8[8], rstd8[8];
+        const float inv_n = 1.0f / static_cast<float>(N);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = q * 32 + 4 * i + lr;
+          float sx = 0.f, sq = 0.f;
+#pragma unroll
+          for (int pr = 0; pr < kLnCl; ++pr) {
+            const float2 t2 = ln_xpart[(par * kLnCl + pr) * 128 + rl];
+            sx += t2.x;
+            sq += t2.y;
+          }
+          mean8[i] = sx * inv_n;
+          const float var = fmaxf(fmaf(-mean8[i], mean8[i], sq * inv_n), 0.f);
+          rstd8[i] = 1.0f / sqrtf(var + lno.eps);
+          if (n_blk == 0 && half == 0 && lc == 0 && row_base + 4 * i + lr < M) lno.stats[row_base + 4 * i + lr] = make_float2(mean8[i], rstd8[i]);
+        }
+        // (5) normalise the values prefetched above
+        TH* hout = static_cast<TH*>(lno.h);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int col = col0 + 32 * ci;
+          const float4 gg = __ldg(reinterpret_cast<const float4*>(lno.g + col));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(lno.b + col));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + 4 * i + lr;
+            const float4 vv = vc[ci][i];
+            float4 hv;
+            hv.x = (vv.x - mean8[i]) * rstd8[i] * gg.x + bb.x;
+            hv.y = (vv.y - mean8[i]) * rstd8[i] * gg.y + bb.y;
+            hv.z = (vv.z - mean8[i]) * rstd8[i] * gg.z + bb.z;
+            hv.w = (vv.w - mean8[i]) * rstd8[i] * gg.w + bb.w;
+            if (full || row < M) store4<TH>(hout + static_cast<size_t>(row) * N + col, hv);
+          }
+        }
+        TR(26);
+        ++ln_it;
       }
       if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
@@ -470,9 +569,56 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* 
   const int slots = CG2 ? num_sms() / 2 : num_sms();
   const int grid = (tiles < slots ? tiles : slots) * (CG2 ? 2 : 1);
   SD_CUDA(launch_kc(CG2 ? 2 : 1, kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K,
-                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace));
+                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, LnOutArgs{}));
   SD_LAUNCHED(CG2 ? "gemm_tcgen05_2cta" : "gemm_tcgen05", s);
   return SEQDIFF_OK;
+}
+
+// fused GEMM + residual + LayerNorm: clusters of 4 CTAs (one per column quarter), each cluster walks its row blocks
+template <int BN, int RESID, typename TH>
+static int launch_tc_ln(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, float* C, int M, int N, int K,
+                        uint32_t idesc, cudaStream_t s, const LnResid* ln, const LnOut& lo) {
+  using Cfg = GemmCfg<BN, false, true>;
+  auto kfn = gemm_tcgen05_kernel<BN, 0, RESID, float, false, TH>;
+  static bool configured = false;
+  if (!configured) {
+    SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int num_m = ceil_div(M, kBM);
+  // A cluster needs its 4 SMs inside one GPC, so fewer clusters are co-resident than num_sms / 4 (32, not 37, on a 148-SM
+  // B200); persistent clusters beyond that number would only start after the first wave has finished all of its tiles.
+  static int max_cl = 0;
+  if (!max_cl) {
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(num_sms() / kLnCl * kLnCl);
+    qc.blockDim = dim3(kGemmThreads);
+    qc.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = kLnCl;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    SD_CUDA(cudaOccupancyMaxActiveClusters(&n, kfn, &qc));
+    max_cl = n > 0 ? n : 1;
+  }
+  // equal tile counts per cluster: the smallest cluster count that keeps the wave count of the full-occupancy schedule
+  const int waves = ceil_div(num_m, max_cl);
+  const int clusters = ceil_div(num_m, waves);
+  const LnOutArgs a{lo.g, lo.b, lo.eps, lo.h, lo.stats};
+  SD_CUDA(launch_kc(kLnCl, kfn, dim3(clusters * kLnCl), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, C, M, N, K, idesc,
+                    ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, a));
+  SD_LAUNCHED("gemm_tcgen05_ln", s);
+  return SEQDIFF_OK;
+}
+template <int BN, typename TH>
+static int dispatch_tc_ln(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, float* C, int M, int N, int K,
+                          uint32_t idesc, cudaStream_t s, const LnResid* ln, const LnOut& lo) {
+  if (ln) return launch_tc_ln<BN, 2, TH>(ta, tb, bias, resid, C, M, N, K, idesc, s, ln, lo);
+  return launch_tc_ln<BN, 1, TH>(ta, tb, bias, resid, C, M, N, K, idesc, s, ln, lo);
 }
 
 // tile choice, from measurements on B200 (scripts/gemm_sweep.py, profiles/gemm_sweep_r01.log):
@@ -519,7 +665,7 @@ static int dispatch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float
 // a_fmt / w_fmt: 0 = fp16, 1 = bf16.  out_kind: 0 = fp16, 1 = bf16, 2 = fp32 (identity epilogue only; implied by resid).
 // force_cfg: 0 = auto, else  bn | (cg2 << 16)  with bn in {128,192,256} (tests / sweeps).
 int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
-            void* C, int out_kind, cudaStream_t s, int force_cfg, const LnResid* ln_resid) {
+            void* C, int out_kind, cudaStream_t s, int force_cfg, const LnResid* ln_resid, const LnOut* ln_out) {
   SD_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
   SD_CHECK(N % 128 == 0, "tcgen05 GEMM needs N % 128 == 0");
   SD_CHECK(K % 8 == 0, "tcgen05 GEMM needs K % 8 == 0 (16B TMA pitch)");
@@ -531,6 +677,24 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
   SD_CHECK((a_fmt | 1) == 1 && out_kind >= 0 && out_kind <= 2, "bad operand format");
   // measured on B200: tcgen05.mma.kind::f16 with a_format != b_format faults as an illegal instruction
   SD_CHECK(a_fmt == w_fmt, "A and W must share one 16-bit format");
+  if (ln_out) {  // fused output LayerNorm: fixed tile width N / 4, clusters of 4 CTAs
+    SD_CHECK(resid && out_kind == 2 && epi == 0, "fused LayerNorm needs the fp32 residual form");
+    SD_CHECK(N == 512 || N == 768 || N == 1024, "fused LayerNorm: N must be 512, 768 or 1024 (4 column quarters of 128/192/256)");
+    SD_CHECK(ln_out->g && ln_out->b && ln_out->h && ln_out->stats, "fused LayerNorm: null argument");
+    const int bq = N / kLnCl;
+    CUtensorMap ta, tb;
+    SD_TRY(make_tmap(A, a_fmt, M, K, kBM, &ta));
+    SD_TRY(make_tmap(W, w_fmt, N, K, bq, &tb));
+    const uint32_t idesc = umma_idesc_16(kBM, bq, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
+    float* Cf = static_cast<float*>(C);
+#define SD_LN_DISPATCH(BN_)                                                                                                   \
+  return a_fmt == 1 ? dispatch_tc_ln<BN_, bf16>(ta, tb, bias, resid, Cf, M, N, K, idesc, s, ln_resid, *ln_out)                \
+                    : dispatch_tc_ln<BN_, f16>(ta, tb, bias, resid, Cf, M, N, K, idesc, s, ln_resid, *ln_out)
+    if (bq == 128) { SD_LN_DISPATCH(128); }
+    if (bq == 192) { SD_LN_DISPATCH(192); }
+    SD_LN_DISPATCH(256);
+#undef SD_LN_DISPATCH
+  }
   int cfg = force_cfg;
   if (!cfg) {
     // First eager call of a (shape, epilogue) times every legal tile configuration on the caller's buffers and keeps the

@@ -114,9 +114,28 @@ static int gemm_S(int, int M, int N, int K, const float* A, const Wt& W, const f
 }
 template <typename T>
 static int gemm_S(int wfmt, int M, int N, int K, const T* A, const Wt& W, const float* bias, const float* resid, float* C, cudaStream_t s,
-                  const LnResid* ln = nullptr) {
+                  const LnResid* ln = nullptr, const LnOut* lo = nullptr) {
   const void* w = wfmt == 1 ? static_cast<const void*>(W.h) : static_cast<const void*>(W.g);
-  return gemm_16(M, N, K, A, Fmt<T>::v, w, wfmt, bias, resid, 0, C, 2, s, 0, ln);
+  return gemm_16(M, N, K, A, Fmt<T>::v, w, wfmt, bias, resid, 0, C, 2, s, 0, ln, lo);
+}
+// Linear + residual followed by its LayerNorm.  SEQDIFF_LN_FUSE=1 runs them as ONE launch (gemm.cu, LnOut: 4-CTA clusters
+// exchange row statistics through DSMEM).  Measured at cfg 2 (profiles/ln_fuse_ab_r01.txt) the fused kernel is 2 % SLOWER end
+// to end than GEMM + layernorm(): its 8 epilogue warps per SM do three memory passes (residual in, o out, o back in, h out)
+// that the stand-alone LayerNorm kernel streams with 64 warps per SM, and the epilogue (14 k cycles per tile) becomes the
+// bound of a K = 768 mainloop (4.6 k).  So it stays opt-in until the epilogue keeps the tile in TMEM.
+static bool ln_fuse_enabled(int H) {
+  static const bool on = [] { const char* e = getenv("SEQDIFF_LN_FUSE"); return e && e[0] == '1'; }();
+  return on && (H == 512 || H == 768 || H == 1024);
+}
+template <typename T>
+static int gemm_ln(int wfmt, int M, int H, int K, const T* A, const Wt& W, const float* bias, const float* resid, float* o, const LnResid* lr,
+                   const float* ln_w, const float* ln_b, float eps, T* h, float2* stats, cudaStream_t s) {
+  if (ln_fuse_enabled(H)) {
+    const LnOut lo{ln_w, ln_b, eps, h, stats};
+    return gemm_S(wfmt, M, H, K, A, W, bias, resid, o, s, lr, &lo);
+  }
+  SD_TRY(gemm_S(wfmt, M, H, K, A, W, bias, resid, o, s, lr));
+  return layernorm<T>(o, M, H, ln_w, ln_b, eps, nullptr, h, stats, s);
 }
 
 __global__ void set_int_kernel(int* p, int v) {
@@ -570,20 +589,22 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
       float* oC = obuf[2];
       SD_TRY(gemm_T(wfmt, Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, 0, sb.qkv, s));
       SD_TRY(attention<T>(B, heads, Ll, Ll, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s));
-      if (i == 0) SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, h.s, oA, s));
-      else SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, o_prev, oA, s, &prev));
-      SD_TRY(layernorm<T>(oA, Ml, H, w.self.ln_w, w.self.ln_b, eps, nullptr, h1.t, lnstats, s));
+      SD_TRY(gemm_ln<T>(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, i == 0 ? h.s : o_prev, oA, i == 0 ? nullptr : &prev, w.self.ln_w,
+                        w.self.ln_b, eps, h1.t, lnstats, s));
       SD_TRY(gemm_T(wfmt, Ml, H, H, h1.t, w.cq, w.cq_b, 0, cq, s));
       const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
       SD_TRY(attention<T>(B, heads, Ll, Lr, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s));
       const LnResid r1{lnstats, w.self.ln_w, w.self.ln_b};
-      SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.cout, w.cout_b, oA, oB, s, &r1));
-      SD_TRY(layernorm<T>(oB, Ml, H, w.cln_w, w.cln_b, eps, nullptr, h2.t, lnstats + Ml, s));
+      SD_TRY(gemm_ln<T>(wfmt, Ml, H, H, sb.ctx, w.cout, w.cout_b, oA, oB, &r1, w.cln_w, w.cln_b, eps, h2.t, lnstats + Ml, s));
       SD_TRY(gemm_T(wfmt, Ml, I, H, h2.t, w.inter, w.inter_b, 1, ffn, s));
       const LnResid r2{lnstats + Ml, w.cln_w, w.cln_b};
-      SD_TRY(gemm_S(wfmt, Ml, H, I, ffn, w.outd, w.outd_b, oB, oC, s, &r2));
-      // the last layer's output feeds decoder_normalize, whose rowwise kernels read the fp32 stream: materialise it there
-      SD_TRY(layernorm<T>(oC, Ml, H, w.oln_w, w.oln_b, eps, last ? h3.s : nullptr, h3.t, lnstats + 2 * static_cast<size_t>(Ml), s));
+      if (last) {
+        // the last layer's output feeds decoder_normalize, whose rowwise kernels read the fp32 stream: materialise it there
+        SD_TRY(gemm_S(wfmt, Ml, H, I, ffn, w.outd, w.outd_b, oB, oC, s, &r2));
+        SD_TRY(layernorm<T>(oC, Ml, H, w.oln_w, w.oln_b, eps, h3.s, h3.t, lnstats + 2 * static_cast<size_t>(Ml), s));
+      } else {
+        SD_TRY(gemm_ln<T>(wfmt, Ml, H, I, ffn, w.outd, w.outd_b, oB, oC, &r2, w.oln_w, w.oln_b, eps, h3.t, lnstats + 2 * static_cast<size_t>(Ml), s));
+      }
       prev = LnResid{lnstats + 2 * static_cast<size_t>(Ml), w.oln_w, w.oln_b};
       o_prev = oC;
       h = h3;

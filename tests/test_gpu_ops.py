@@ -100,6 +100,36 @@ def test_gemm_fp32(M, N, K):
         assert rel_err(C, ref.float()) < 2e-6
 
 
+@pytest.mark.parametrize("M,N,K", [(8192, 768, 768), (8192, 768, 1024), (300, 768, 768), (128, 512, 768), (1000, 1024, 768), (16384, 768, 768)])
+@pytest.mark.parametrize("mode", [BF16, FP16])
+def test_gemm_fused_layernorm(M, N, K, mode):
+    """Linear + residual + LayerNorm in one launch (4-CTA clusters exchange row statistics through DSMEM) against fp64:
+    pre-LN tensor, 16-bit LayerNorm output and the per-row (mean, rstd)."""
+    lib = sd_pkg().lib()
+    adt, _ = _TDT[mode]
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV).to(adt)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).to(adt)
+    bias = torch.randn(N, generator=g).to(DEV)
+    resid = (torch.randn(M, N, generator=g) * 2 + 0.5).to(DEV)
+    lw = (1 + 0.2 * torch.randn(N, generator=g)).to(DEV)
+    lb = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    eps = 1e-12
+    for rep in range(3):  # repeated launches: the exchange buffers alternate and must not leak between launches
+        C = torch.full((M, N), float("nan"), device=DEV)
+        h = torch.full((M, N), float("nan"), device=DEV, dtype=adt)
+        st = torch.full((M, 2), float("nan"), device=DEV)
+        _check(lib.seqdiff_op_gemm_ln(mode, M, N, K, _p(A), _p(W), _p(bias), _p(resid), _p(lw), _p(lb), eps, _p(C), _p(h), _p(st), stream_ptr()))
+        torch.cuda.synchronize()
+        ref = A.double() @ W.double().t() + bias.double() + resid.double()
+        assert rel_err(C, ref.float()) < 2e-5
+        mean, var = ref.mean(-1, keepdim=True), ref.var(-1, unbiased=False, keepdim=True)
+        hr = (ref - mean) / torch.sqrt(var + eps) * lw.double() + lb.double()
+        assert rel_err(h, hr.float()) < {BF16: 6e-3, FP16: 8e-4}[mode]
+        assert (st[:, 0:1].double() - mean).abs().max() < 1e-4
+        assert ((st[:, 1:2].double() * torch.sqrt(var + eps)) - 1).abs().max() < 1e-4
+
+
 # ---------------------------------------------------------------------------------------------------
 ATTN_CASES = [
     # B, heads, Lq, Lk, P, rel
