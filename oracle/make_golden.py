@@ -22,6 +22,7 @@ and the reference model gets them through load_state_dict(strict=True).
 from __future__ import annotations
 
 import hashlib
+import math
 import os
 import sys
 
@@ -228,6 +229,32 @@ def golden_dataset():
     torch.save({"n_complex": 6, "seed": 41, "cases": out}, os.path.join(GOLDEN, "dataset_items.pt"))
 
 
+def golden_structure_feed():
+    """BASELINE configs[4]: the reference structure_model denoiser (12 + 12 layers, feature_size 8) on 128-residue synthetic
+    torsion sequences; its output [B, 128, 8] f32 is what sample_by_generated_angles.py:202 hands the sequence model as
+    `ligand_angle`.  Stored: the generated angles (wrapped to [-pi, pi) like structure_model/sample.py:139-141)."""
+    from transformers.models.bert.modeling_bert import BertConfig
+    SM = R.load_structure_reference()
+    B, L = 8, 128
+    torch.manual_seed(21)
+    common = dict(max_position_embeddings=L, num_attention_heads=12, hidden_size=768, intermediate_size=1024, num_hidden_layers=12,
+                  position_embedding_type="relative_key", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    enc = BertConfig(**common)
+    dec = BertConfig(**common, is_decoder=True, add_cross_attention=True)
+    m = SM.ConditionalBertForDiffusionBase(enc, dec, 8).eval()
+    batch = O.synthetic_batch(B, L, (5, 64), (16, 128), 55)
+    g = torch.Generator().manual_seed(56)
+    noised = (torch.rand(B, L, 8, generator=g) * 2 - 1) * math.pi * batch["ligand_attn_mask"][..., None]
+    t = torch.randint(0, 1000, (B,), generator=g)
+    with torch.no_grad():
+        out = m(t, noised, batch["ligand_attn_mask"], batch["receptor_seq"], batch["receptor_angles"], batch["receptor_attn_mask"])
+    assert out.shape == (B, L, 8) and out.dtype == torch.float32 and torch.isfinite(out).all()
+    wrapped = torch.remainder(out + math.pi, 2 * math.pi) - math.pi
+    print(f"structure feed: out {tuple(out.shape)} {out.dtype}  max|out| = {out.abs().max():.3f}")
+    torch.save({"B": B, "L": L, "batch_seed": 55, "n_lig": (5, 64), "n_rec": (16, 128), "timesteps": t, "angles": wrapped.clone()},
+               os.path.join(GOLDEN, "structure_feed_cfg5.pt"))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
@@ -238,6 +265,7 @@ def main():
     golden_dataset()
     golden_forward()
     golden_denoise()
+    golden_structure_feed()
     print("golden fixtures written to", os.path.normpath(GOLDEN))
 
 

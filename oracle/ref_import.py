@@ -104,6 +104,33 @@ def load_reference():
     return _CACHE["mods"]
 
 
+STRUCT_DIR = os.path.join(REFERENCE_ROOT, "structure_model")
+
+
+def load_structure_reference():
+    """The reference's structure_model/model.py imported in place under a private name (its `model` / `utils` module names
+    collide with the sequence model's).  BASELINE configs[4]: only its output SHAPE / dtype feeds the sequence model."""
+    if "struct" in _CACHE:
+        return _CACHE["struct"]
+    if not os.path.isfile(os.path.join(STRUCT_DIR, "model.py")):
+        raise RuntimeError("reference tree not present (expected only in the build container)")
+    _install_stubs()
+    saved = {k: sys.modules.pop(k) for k in ("model", "utils") if k in sys.modules}
+    sys.path.insert(0, STRUCT_DIR)
+    try:
+        with _cwd(STRUCT_DIR):
+            import model as struct_model  # noqa
+    finally:
+        sys.path.remove(STRUCT_DIR)
+        for k in ("model", "utils"):
+            m = sys.modules.pop(k, None)
+            if m is not None:
+                sys.modules["_ref_struct_" + k] = m
+        sys.modules.update(saved)
+    _CACHE["struct"] = struct_model
+    return struct_model
+
+
 def make_blosum_transition(timestep: int = 500):
     _, _, ref_utils = load_reference()
     with _cwd(SEQ_DIR):

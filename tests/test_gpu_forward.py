@@ -257,3 +257,23 @@ def test_forward_cfg3_length_512(precision):
         want = O.denoiser_forward(state, cfg, *args)
         got = m(*[a.to(DEV) for a in args])
     check_logits(got, want, precision, "cfg3 L=512", bf16_ckpt=(precision == "bf16"))
+
+
+@pytest.mark.parametrize("precision", MODES)
+def test_forward_accepts_structure_model_angles_cfg5(precision):
+    """BASELINE configs[4]: angles produced by the reference structure_model denoiser (tests/golden/structure_feed_cfg5.pt,
+    shape [8,128,8] f32) are fed as `ligand_angle` (sample_by_generated_angles.py:202) -- CUDA forward vs the oracle."""
+    g = torch.load(os.path.join(GOLDEN, "structure_feed_cfg5.pt"), weights_only=False)
+    B, L = g["B"], g["L"]
+    cfg, state, m = _model(L, True, 1, "B", precision, bf16_ckpt=(precision == "bf16"))
+    batch = O.synthetic_batch(B, L, g["n_lig"], g["n_rec"], g["batch_seed"])
+    ang = g["angles"] * batch["ligand_attn_mask"][..., None]
+    assert ang.shape == (B, L, 8) and ang.dtype == torch.float32
+    x_t = O.generate_discrete_noise(B, L, generator=torch.Generator().manual_seed(8))
+    t = torch.full((B, 1), 21.0)
+    args = (t, x_t, ang, batch["ligand_attn_mask"], batch["receptor_seq"], batch["receptor_angles"], batch["receptor_attn_mask"])
+    with torch.no_grad():
+        want = O.denoiser_forward(state, cfg, *args)
+        got = m(*[a.to(DEV) for a in args])
+    assert got.shape == (B, L, 20)
+    check_logits(got, want, precision, "cfg5 structure feed", bf16_ckpt=(precision == "bf16"))

@@ -159,3 +159,40 @@ def test_dataset_item_golden():
     assert (g["cases"][(1, 128)]["receptor_length"] >= g["cases"][(0, 128)]["receptor_length"]).all()
     with pytest.raises(RuntimeError, match="Length exceed"):
         O.dataset_item(recs[0], 4, 0)
+
+
+def test_structure_feed_cfg5_fixture_and_oracle():
+    """BASELINE configs[4]: angles generated by the reference structure_model denoiser (12 + 12 layers, feature_size 8;
+    oracle/make_golden.py::golden_structure_feed) have the shape / dtype / range the sequence model takes as `ligand_angle`
+    (sample_by_generated_angles.py:202), and the oracle's sequence forward accepts them."""
+    g = _load("structure_feed_cfg5.pt")
+    B, L = g["B"], g["L"]
+    ang = g["angles"]
+    assert ang.shape == (B, L, 8) and ang.dtype == torch.float32 and torch.isfinite(ang).all()
+    assert ang.min() >= -np.pi and ang.max() < np.pi
+    cfg = O.OracleConfig(max_position_embeddings=L, num_hidden_layers=1)
+    state = O.init_state_dict(cfg, 1, "B")
+    batch = O.synthetic_batch(2, L, g["n_lig"], g["n_rec"], g["batch_seed"])
+    x_t = O.generate_discrete_noise(2, L, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        y = O.denoiser_forward(state, cfg, torch.full((2, 1), 9.0), x_t, ang[:2] * batch["ligand_attn_mask"][..., None],
+                               batch["ligand_attn_mask"], batch["receptor_seq"], batch["receptor_angles"], batch["receptor_attn_mask"])
+    assert y.shape == (2, L, 20) and torch.isfinite(y).all()
+
+
+def test_structure_model_reference_shape_live():
+    """Same check against the reference structure model itself when /root/reference is present (build container only)."""
+    from oracle import ref_import as R
+    if not R.reference_available():
+        pytest.skip("reference tree not present")
+    from transformers.models.bert.modeling_bert import BertConfig
+    SM = R.load_structure_reference()
+    B, L = 2, 128
+    common = dict(max_position_embeddings=L, num_attention_heads=12, hidden_size=768, intermediate_size=1024, num_hidden_layers=2,
+                  position_embedding_type="relative_key")
+    m = SM.ConditionalBertForDiffusionBase(BertConfig(**common), BertConfig(**common, is_decoder=True, add_cross_attention=True), 8).eval()
+    batch = O.synthetic_batch(B, L, (5, 64), (16, 128), 7)
+    with torch.no_grad():
+        out = m(torch.randint(0, 1000, (B,)), torch.zeros(B, L, 8), batch["ligand_attn_mask"], batch["receptor_seq"],
+                batch["receptor_angles"], batch["receptor_attn_mask"])
+    assert out.shape == (B, L, 8) and out.dtype == torch.float32
