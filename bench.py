@@ -221,8 +221,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): anything a library writes to fd 1 meanwhile (NCCL prints its version
+    # banner there when NCCL_DEBUG is set) is sent to stderr; fd 1 is restored just before the result is printed
+    sys.stdout.flush()
+    _saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_saved_stdout_fd, 1)
+        print(json.dumps(obj), flush=True)
+
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback (use --impl reference for the CPU arm)"}))
+        emit({"error": "no CUDA device: this benchmark has no CPU fallback (use --impl reference for the CPU arm)"})
         return 1
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -388,7 +399,7 @@ def main():
                                       "sample": f"{len(times)} denoise steps x {cb} graphs (of {T}); oracle port incl. the reference's Python multinomial loop"}
 
     if rank == 0:
-        print(json.dumps(result))
+        emit(result)
     if world > 1:
         dist.destroy_process_group()
     return 0
