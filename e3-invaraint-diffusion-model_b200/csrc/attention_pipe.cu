@@ -9,12 +9,18 @@
 //   warp 0      TMA producer : Q (double-buffered per item), K (+ the 256-row window of E a step can touch), V (double-buffered)
 //   warp 1      MMA issuer   : S = Q K^T and QE = Q Ewin^T for step g+1 are issued as soon as the softmax threads have DRAINED
 //                              S / QE of step g from TMEM into registers -- i.e. under step g's exp / P / PV work;  O (+)= P V
-//   warps 2..9  softmax      : two threads per query row (TMEM lane), each owning 64 of the step's 128 keys: relative-key skew
-//                              through a private smem row, scale + mask, online softmax, P -> smem (SW128 K-major A operand),
+//   warps 2..9  softmax      : two threads per query row (TMEM lane), each owning two interleaved 32-key chunks of the step: relative-key skew
+//                              by a register barrel shift, scale + mask, online softmax, P -> smem (SW128 K-major A operand),
 //                              O rescale in TMEM when the running maximum moves.
+// Masked keys: a 32-key chunk whose keys are all masked contributes exp2(s - 10000 log2e - m) = 0 exactly (fp32 underflow, the
+// same underflow the reference's additive -10000 relies on), so its TMEM load, skew, scores and exp2 are skipped and zeros go
+// into P -- bit-identical P, half the MUFU work on ragged pockets.  (Chunk 0 of an item's first step is always computed, so
+// a row never ends with an empty sum; only a sequence with NO unmasked key at all deviates from the reference, which then
+// attends uniformly over padding.)
 // The O epilogue of an item is deferred into the first step of the next item (O is double-buffered in TMEM) and the exp2 of a
 // step runs before the wait on the previous step's PV, so no role ever waits on an MMA it has just triggered.  TMEM: REL  S 128 | QE 256 | O 2x64 = 512 columns; no-REL  S 2x128 | O 2x64.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -27,7 +33,6 @@ constexpr int kPQ = 128;            // query rows per item (= UMMA M = TMEM lane
 constexpr int kPK = 128;            // keys per step
 constexpr int kPipeThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
 constexpr int kSoftThreads = 256;
-constexpr int kSkewPitch = 65;      // floats per private skew row (64 used; odd pitch: conflict-free aligned reads)
 constexpr float kLog2e = 1.44269504088896f;
 
 template <bool REL> struct PipeCfg {
@@ -40,17 +45,38 @@ template <bool REL> struct PipeCfg {
   static constexpr int kV = kE + (REL ? 32768 : 0);               // kNVS x [128][64]
   static constexpr int kP = kV + kNVS * 16384;                    // [2 key halves][128][64]
   static constexpr int kOut = kP + 32768;                         // [128][64] 16-bit output staging tile (16B chunks XOR-swizzled by row & 7)
-  static constexpr int kSkew = kOut + 16384;                      // [256 threads][65] fp32 (REL)
-  static constexpr int kMask = kSkew + (REL ? kSoftThreads * kSkewPitch * 4 : 0);  // 2 x [128] fp32 (step parity)
+  static constexpr int kMask = kOut + 16384;                      // 2 x [128] fp32 (step parity)
   static constexpr int kXch = kMask + 2 * kPK * 4;                // [step parity][key half][128] row maxima
   static constexpr int kLsum = kXch + 2 * 2 * kPQ * 4;            // [item parity][key half][128] row sums
-  static constexpr int kBar = kLsum + 2 * 2 * kPQ * 4;            // mbarriers + tmem slot
+  static constexpr int kFlag = kLsum + 2 * 2 * kPQ * 4;           // [step parity][4] int: 32-key chunk holds at least one unmasked key
+  static constexpr int kBar = kFlag + 64;                         // mbarriers + tmem slot
   static constexpr int kBytes = kBar + 256 + 1024;                // + alignment slack
   static constexpr int kColS = 0;
   static constexpr int kColQE = 128;
   static constexpr int kColO = REL ? 384 : 256;
 };
 
+// dst = p ? a : b as an opaque SELP (written as `p ? x[k + sh] : x[k]` the compiler turns the barrel shift back into a
+// dynamically indexed array in local memory)
+__device__ __forceinline__ uint32_t selp_u32(uint32_t a, uint32_t b, uint32_t p) {
+  uint32_t d;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tselp.b32 %0, %1, %2, q;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(p));
+  return d;
+}
+// one stage of the barrel shift  X[k] = on ? X[k + SH] : X[k]  over the 32 + SH - 1 entries later stages still need
+// (X = x0 ++ x1; every index is a compile-time constant after unrolling)
+template <int SH>
+__device__ __forceinline__ void shift_stage(uint32_t (&x0)[32], uint32_t (&x1)[32], uint32_t on) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const uint32_t src = (k + SH < 32) ? x0[(k + SH) & 31] : x1[(k + SH - 32) & 31];
+    x0[k] = selp_u32(src, x0[k], on);
+  }
+#pragma unroll
+  for (int k = 0; k < SH - 1; ++k) x1[k] = selp_u32(x1[(k + SH) & 31], x1[k], on);
+}
 __device__ __forceinline__ void soft_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void soft_bar2_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
@@ -121,6 +147,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   float* sMask = reinterpret_cast<float*>(smem + C::kMask);
   float* xch = reinterpret_cast<float*>(smem + C::kXch);
   float* lsum = reinterpret_cast<float*>(smem + C::kLsum);
+  int* sFlag = reinterpret_cast<int*>(smem + C::kFlag);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = warp_id_uniform();  // provably warp-uniform: the TMA / MMA role loops stay on the uniform datapath
@@ -246,7 +273,6 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int hf = (warp - 2) >> 2;   // which 64-key half of a step this thread owns
     const int row = wq * 32 + lane;   // query row inside the item = TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    float* srow = reinterpret_cast<float*>(smem + C::kSkew) + st * kSkewPitch;
     // additive key mask (log2 domain) of a step: fetched from global TWO steps ahead (raw value parked in a register across a
     // whole step, so its latency never shows), stored to smem one step ahead, published by that step's barrier
     auto mask_cvt = [&](float raw, bool in_range) -> float { return in_range ? (1.0f - raw) * (-10000.0f * kLog2e) : -INFINITY; };
@@ -285,21 +311,28 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     };
 
+    // mask value of key 128 kb + st of a step -> smem; warps 2..5 (st < 128) own one 32-key chunk each and record whether the
+    // chunk holds any unmasked key (warp-uniform call sites only)
+    auto mask_store = [&](int parity, float v, bool first_step_of_item) {
+      sMask[parity * kPK + st] = v;
+      const unsigned any = __ballot_sync(0xffffffffu, v == 0.0f);
+      if (lane == 0) sFlag[parity * 4 + (st >> 5)] = (any != 0u || (first_step_of_item && st < 32)) ? 1 : 0;
+    };
     PipeItem prev{0, 0, 0};
     StepCursor cur, ahead;  // current step / the step two ahead (mask prefetch)
     cur.init(static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), nqb, heads, nkb);
     ahead = cur;
     if (my_items > 0) {
       float raw; bool inr;
-      if (mask_fetch(ahead, raw, inr)) sMask[st] = mask_cvt(raw, inr);
+      if (mask_fetch(ahead, raw, inr)) mask_store(0, mask_cvt(raw, inr), ahead.kb == 0);
       ahead.next_step();
-      if (mask_fetch(ahead, raw, inr)) sMask[kPK + st] = mask_cvt(raw, inr);
+      if (mask_fetch(ahead, raw, inr)) mask_store(1, mask_cvt(raw, inr), ahead.kb == 0);
       ahead.next_step();
     }
     soft_bar_sync();
     int g = 0;
     float m_raw = 0.f;
-    bool m_inr = false, m_have = false;
+    bool m_inr = false, m_have = false, m_first = false;
     for (int it = 0; it < my_items; ++it, cur.next_item()) {
       const PipeItem w = cur.item();
       float m_run = -INFINITY, l_run = 0.f;
@@ -311,38 +344,51 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         TR(21);
         // ---- scores of (row, key half): S + skewed QE, scaled, masked (log2 domain) ----
         float t[2][32];
-        if (REL) {
-          // keys r in [64 hf, 64 hf + 64) pair with window columns j = row + 127 - r; over the warp's 32 rows that is the
-          // 3-chunk band starting at chunk  wq + 2 - 2 hf  (warp-uniform), instead of the whole 8-chunk window
-          const int cc0 = wq + 2 - 2 * hf;
-#pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            uint32_t r[32];
-            tmem_ld_32x32(t_lane + C::kColQE + (cc0 + u) * 32, r);
-            tmem_ld_wait();
-            const int base = row + 127 - 64 * hf - (cc0 + u) * 32;  // local key index of column jj is  base - jj
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              const int rr = base - jj;
-              if (rr >= 0 && rr < 64) srow[rr] = __uint_as_float(r[jj]);
-            }
-          }
-        }
-        const float* mk = sMask + (g & 1) * kPK + 64 * hf;
+        // the two threads of a row own INTERLEAVED 32-key chunks (thread hf: chunks hf and hf + 2), so that a prefix mask --
+        // peptides of 5..64 residues in 128 slots -- leaves both threads with the same number of live chunks
+        const bool cv0 = sFlag[(g & 1) * 4 + hf] != 0, cv1 = sFlag[(g & 1) * 4 + hf + 2] != 0;  // warp-uniform
+        const float* mk = sMask + (g & 1) * kPK + 32 * hf;  // chunk c of this thread: + 64 c
         float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        // (static dispatch on the chunk flags: a run-time condition around the register arrays sends them to local memory)
+        auto score_chunk = [&](auto c_tag) {
+          constexpr int c = decltype(c_tag)::value;
+          uint32_t x0[32], x1[32];  // X[k] = k < 32 ? x0[k] : x1[k - 32]  (two arrays: no address arithmetic across them, stays in registers)
+          if (REL) {
+            // relative-key skew in registers.  Keys r of chunk kc = hf + 2c pair with window columns j = row + 127 - r; for
+            // the warp's 32 rows that is the 2-chunk band of QE starting at chunk qc0 = wq - kc + 3 (warp-uniform), and with
+            // X = those 64 columns of this lane's row:  QE[row, j(r)] = X[lane + 31 - (r - 32 kc)].  The lane-dependent
+            // offset is applied by a 5-stage barrel shift (186 selects on the ALUs of all four sub-partitions); the earlier
+            // scatter through a private smem row was bound by the SM's single LSU: 2.6 k cycles per item.
+            const int qc0 = wq - (hf + 2 * c) + 3;
+            tmem_ld_32x32(t_lane + C::kColQE + qc0 * 32, x0);
+            tmem_ld_32x32(t_lane + C::kColQE + (qc0 + 1) * 32, x1);
+            tmem_ld_wait();
+            const uint32_t ul = static_cast<uint32_t>(lane);
+            shift_stage<16>(x0, x1, ul & 16u);
+            shift_stage<8>(x0, x1, ul & 8u);
+            shift_stage<4>(x0, x1, ul & 4u);
+            shift_stage<2>(x0, x1, ul & 2u);
+            shift_stage<1>(x0, x1, ul & 1u);
+          }
           uint32_t r[32];
-          tmem_ld_32x32(t_lane + C::kColS + ss * 128 + (2 * hf + c) * 32, r);
+          tmem_ld_32x32(t_lane + C::kColS + ss * 128 + (hf + 2 * c) * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float sv = __uint_as_float(r[j]);
-            if (REL) sv += srow[c * 32 + j];
-            sv = fmaf(sv, kScale2, mk[c * 32 + j]);
+            if (REL) sv += __uint_as_float(x0[31 - j]);
+            sv = fmaf(sv, kScale2, mk[c * 64 + j]);
             t[c][j] = sv;
             mx = fmaxf(mx, sv);
           }
+        };
+        if (cv0 && cv1) {
+          score_chunk(std::integral_constant<int, 0>{});
+          score_chunk(std::integral_constant<int, 1>{});
+        } else if (cv0) {
+          score_chunk(std::integral_constant<int, 0>{});
+        } else if (cv1) {
+          score_chunk(std::integral_constant<int, 1>{});
         }
         // S (+QE) of this step now live in registers: hand the TMEM stage back so the MMAs of step g+1 run under the rest
         TR(22);
@@ -350,12 +396,13 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[ss]);
         xch[((g & 1) * 2 + hf) * kPQ + row] = mx;
-        if (g > 0 && m_have) sMask[((g + 1) & 1) * kPK + st] = mask_cvt(m_raw, m_inr);  // step g+1's mask (fetched during step g-1)
+        if (g > 0 && m_have) mask_store((g + 1) & 1, mask_cvt(m_raw, m_inr), m_first);  // step g+1's mask (fetched during step g-1)
         TR(23);
         if (st == 0) tma_store_wait_read();  // previous item's output tile has left smem (next epilogue may overwrite it)
         soft_bar_sync();
         TR(24);
         m_have = mask_fetch(ahead, m_raw, m_inr);  // step g + 2
+        m_first = ahead.kb == 0;
         ahead.next_step();
         const float m_new = fmaxf(m_run, fmaxf(mx, xch[((g & 1) * 2 + (hf ^ 1)) * kPQ + row]));
         const float corr = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
@@ -363,13 +410,32 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
         // ---- p = exp2(t - m) in place (MUFU-bound: runs under the PV of the previous step) ----
         float rs = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
+        auto exp_chunk = [&](auto c_tag) {
+          constexpr int c = decltype(c_tag)::value;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             t[c][j] = ex2_approx(t[c][j] - m_new);
             rs += t[c][j];
           }
+        };
+        auto zero_chunk = [&](auto c_tag) {  // every key of the chunk is masked: its probabilities underflow to exactly 0
+          constexpr int c = decltype(c_tag)::value;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[c][j] = 0.f;
+        };
+        if (cv0 && cv1) {
+          exp_chunk(std::integral_constant<int, 0>{});
+          exp_chunk(std::integral_constant<int, 1>{});
+        } else if (cv0) {
+          exp_chunk(std::integral_constant<int, 0>{});
+          zero_chunk(std::integral_constant<int, 1>{});
+        } else if (cv1) {
+          zero_chunk(std::integral_constant<int, 0>{});
+          exp_chunk(std::integral_constant<int, 1>{});
+        } else {
+          zero_chunk(std::integral_constant<int, 0>{});
+          zero_chunk(std::integral_constant<int, 1>{});
+        }
         l_run = l_run * corr + rs;
         if (kb == nkb - 1) lsum[((it & 1) * 2 + hf) * kPQ + row] = l_run;
 
@@ -389,13 +455,17 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           tmem_st_wait();
         }
         TR(26);
-        // ---- P -> smem (A operand, K-major): key half hf is SW128 tile hf ----
-        uint8_t* prow16 = smem + C::kP + hf * 16384 + row * 128;
+        // ---- P -> smem (A operand, K-major; SW128 tile c holds keys 64 c .. 64 c + 63): this thread's chunk c = keys
+        //      64 c + 32 hf .. + 31 = 16 B chunks 4 hf .. 4 hf + 3 of the row in tile c ----
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const float* p = &t[ch >> 2][(ch & 3) * 8];
-          *reinterpret_cast<uint4*>(prow16 + ((ch ^ (row & 7)) << 4)) =
-              make_uint4(pack2<T>(p[0], p[1]), pack2<T>(p[2], p[3]), pack2<T>(p[4], p[5]), pack2<T>(p[6], p[7]));
+        for (int c = 0; c < 2; ++c) {
+          uint8_t* prow16 = smem + C::kP + c * 16384 + row * 128;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const float* p = &t[c][qd * 8];
+            *reinterpret_cast<uint4*>(prow16 + (((hf * 4 + qd) ^ (row & 7)) << 4)) =
+                make_uint4(pack2<T>(p[0], p[1]), pack2<T>(p[2], p[3]), pack2<T>(p[4], p[5]), pack2<T>(p[6], p[7]));
+          }
         }
         fence_proxy_async_smem();  // generic-proxy smem writes (P) -> visible to the tensor core (async proxy)
         tc_fence_before();

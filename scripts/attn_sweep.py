@@ -18,7 +18,13 @@ tot = 0.0
 for name, cnt, B, Lq, Lk, P, rel in SHAPES:
     qkv = torch.randn(B * Lq, 3 * H, device=dev).bfloat16()
     E = (torch.randn(2 * P - 1, 64, device=dev) * 0.5).bfloat16() if rel else None
-    mask = torch.ones(B, Lk, device=dev)
+    if os.environ.get("ATTN_RAGGED"):  # cfg-2-like ragged pockets: peptide 5..64 residues (self), pocket 16..128 (cross), scaled with L
+        g = torch.Generator().manual_seed(3)
+        lo, hi = ((5, 64) if "self" in name and "stacked" not in name else (16, 128))
+        n = torch.randint(lo * Lk // 128, hi * Lk // 128 + 1, (B,), generator=g)
+        mask = (torch.arange(Lk)[None, :] < n[:, None]).float().to(dev)
+    else:
+        mask = torch.ones(B, Lk, device=dev)
     out = torch.empty(B * Lq, H, device=dev, dtype=torch.bfloat16)
     def call():
         rc = lib.seqdiff_op_attention(1, B, heads, Lq, Lk, p(qkv), 3 * H, p(qkv[:, H:]), 3 * H, p(qkv[:, 2 * H:]), 3 * H, p(E), P, p(mask), p(out), stream)
