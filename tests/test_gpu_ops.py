@@ -176,6 +176,42 @@ def test_attention(B, heads, Lq, Lk, P, rel, prec):
 
 
 @pytest.mark.parametrize("rel", [True, False])
+@pytest.mark.parametrize("L", [128, 300])
+def test_attention_mask_patterns(rel, L):
+    """Key masks that are not a prefix: the kernel skips 32-key chunks without an unmasked key (their probabilities underflow
+    to exactly 0 under the reference's additive -10000), so chunk boundaries, holes, a masked first chunk and whole masked
+    key blocks must all still match the oracle."""
+    lib = sd_pkg().lib()
+    heads, P = 4, 512
+    H = heads * 64
+    pats = []
+    ar = torch.arange(L)
+    pats.append(ar >= L - 5)                      # only the last keys (first chunks / blocks fully masked)
+    pats.append(ar % 2 == 0)                      # holes everywhere
+    pats.append((ar >= 40) & (ar < 50))           # one island inside chunk 1
+    pats.append(ar < 32)                          # exactly one chunk
+    pats.append(ar < 33)                          # one key into the second chunk
+    pats.append((ar >= 32) & (ar < 64))           # chunk 0 masked, chunk 1 live
+    pats.append(ar == min(L - 1, 129))            # a single key (second key block when L > 128)
+    pats.append(torch.ones(L, dtype=torch.bool))
+    B = len(pats)
+    mask = torch.stack(pats).float().to(DEV)
+    g = torch.Generator().manual_seed(L + int(rel))
+    q = torch.randn(B, L, H, generator=g).to(DEV).bfloat16()
+    k = torch.randn(B, L, H, generator=g).to(DEV).bfloat16()
+    v = torch.randn(B, L, H, generator=g).to(DEV).bfloat16()
+    E = (torch.randn(2 * P - 1, 64, generator=g) * 0.5).to(DEV).bfloat16() if rel else None
+    out = torch.full((B, L, H), float("nan"), device=DEV, dtype=torch.bfloat16)
+    _check(lib.seqdiff_op_attention(BF16, B, heads, L, L, _p(q), H, _p(k), H, _p(v), H, _p(E), P, _p(mask), _p(out), stream_ptr()))
+    torch.cuda.synchronize()
+    cfg = O.OracleConfig(hidden_size=H, num_attention_heads=heads, max_position_embeddings=P)
+    ref = O.attention_core(cfg, q.float().cpu(), k.float().cpu(), v.float().cpu(), O.extend_mask(mask.cpu()), None if E is None else E.float().cpu())
+    assert torch.isfinite(out.float()).all()
+    for b in range(B):
+        assert rel_err(out[b], ref[b]) < 2e-2, (b, rel_err(out[b], ref[b]))
+
+
+@pytest.mark.parametrize("rel", [True, False])
 @pytest.mark.parametrize("prec", [BF16, FP16])
 def test_attention_pipelined_repeatable(rel, prec):
     """The pipelined kernel hands buffers between roles through mbarriers; a missing edge shows up as a timing-dependent
