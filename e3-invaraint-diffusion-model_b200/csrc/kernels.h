@@ -39,7 +39,9 @@ int make_tmap_3d(const void* ptr, int fmt, int batch, int rows, int cols, int bo
 // ---- rowwise.cu -------------------------------------------------------------------------------------
 // GaussianFourierProjection (model.py:85-97): out[b, :] = [sin(x), cos(x)], x = ((t*W)*2)*pi in fp32.
 // t = timestep[b], or (float)*step_ptr for every b when step_ptr != NULL (sampling loop, quirk Q3).
-int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, cudaStream_t s);
+// out16 (optional): 16-bit copy in format fmt16 (0 = fp16, 1 = bf16).
+int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, void* out16, int fmt16,
+                   cudaStream_t s);
 // BertEmbeddings (model.py:110-117): out = LN(x @ Wt + b) (+ te[row / L]); Wt is the [fin, H] transpose.  Up to four
 // embeddings (jobs) run in one launch.  Rowwise kernels read the fp32 residual stream and may write BOTH an fp32 copy
 // (out32: the stream) and a T copy (outT: the operand of the next GEMM); either pointer may be NULL.
@@ -58,6 +60,11 @@ struct EmbedJob {
 struct EmbedJobs {
   EmbedJob j[4];
   int n;
+  // optional side job: cat_dst = [cat_a (cat_na floats) | cat_b (cat_nb floats)] (stacked key masks)
+  float* cat_dst;
+  const float* cat_a;
+  const float* cat_b;
+  int cat_na, cat_nb;
 };
 template <typename T> int embed_ln_multi(EmbedJobs jobs, float eps, int H, cudaStream_t s);
 // out = LayerNorm(in) * w + b
@@ -105,7 +112,9 @@ int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const 
 // no-op when *step_ptr == 0 (last step returns the raw logits, sample.py:147-148).
 int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_t, const float* logits, int diverse,
                  const float* noise_E, uint64_t seed, uint64_t graph_id0, uint32_t step, const int* step_ptr, float* x_s,
-                 uint8_t* idx_out, cudaStream_t s);
+                 uint8_t* idx_out, cudaStream_t s, int* advance = nullptr);
+// advance != NULL (with step_ptr): advance[0] is a zeroed arrival counter; the last CTA to have read *step_ptr decrements it
+// (replaces a separate step_advance launch in the sampling loop)
 int apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float* noise_E, uint64_t seed, uint64_t graph_id0,
                    uint32_t step, float* x_t, uint8_t* idx_out, cudaStream_t s);
 int philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, cudaStream_t s);

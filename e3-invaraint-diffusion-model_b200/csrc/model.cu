@@ -93,6 +93,7 @@ int num_sms() {
 template <typename T> struct Fmt;  // operand format code of the tcgen05 instruction descriptor
 template <> struct Fmt<f16> { static constexpr int v = 0; };
 template <> struct Fmt<bf16> { static constexpr int v = 1; };
+template <> struct Fmt<float> { static constexpr int v = -1; };  // fp32 mode: no 16-bit operand copies
 
 template <typename T> static const T* pick(const Wt& w);
 template <> const float* pick<float>(const Wt& w) { return w.f; }
@@ -230,8 +231,9 @@ int Model::init(const seqdiff_config_t& c, int dev) {
   add_schema(raw, "amino_acid_predictor.layer_norm.bias", H);
   add_schema(raw, "amino_acid_predictor.dense2.weight", static_cast<int64_t>(c.feature_size) * H);
   add_schema(raw, "amino_acid_predictor.dense2.bias", c.feature_size);
-  d_step = static_cast<int*>(dalloc(sizeof(int)));
+  d_step = static_cast<int*>(dalloc(256));  // [0] step counter of the sampling loop, [1] arrival counter of its reverse step
   SD_CHECK(d_step != nullptr, "cudaMalloc failed");
+  SD_CUDA(cudaMemset(d_step, 0, 256));
   return SEQDIFF_OK;
 }
 
@@ -498,8 +500,6 @@ static int se_layer(const Model& m, int wfmt, const SEW& w, const Act<T>& x, con
   return SEQDIFF_OK;
 }
 
-static int to_act(const float*, size_t, float*, cudaStream_t) { return SEQDIFF_OK; }  // fp32 mode uses te directly
-template <typename T> static int to_act(const float* in, size_t n, T* out, cudaStream_t s) { return f32_to_16<T>(in, n, out, s); }
 
 template <typename T>
 int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t,
@@ -536,7 +536,7 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   T* ffn = bp.take<T>(static_cast<size_t>(Ml) * I);
 
   // timestep features + the four BertEmbeddings (model.py:211-213,219-220)
-  SD_TRY(timestep_embed(timestep, step_ptr, ts_W, B, H, te, s));
+  SD_TRY(timestep_embed(timestep, step_ptr, ts_W, B, H, te, k16 ? static_cast<void*>(teT) : nullptr, Fmt<T>::v, s));
   const Act<T> xr = offset(x, MlH);
   {
     auto job = [&](const float* in, int M, const EmbW& e, const float* te_, int L, float* o32, T* oT) {
@@ -552,14 +552,15 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
     // the conditioning c = LN(Linear(angles)) + te only ever feeds a GEMM: operand type only
     jobs.j[2] = job(lig_angle, Ml, lig_ang, te, Ll, k16 ? nullptr : reinterpret_cast<float*>(ccat), k16 ? ccat : nullptr);
     jobs.j[3] = job(rec_angle, Mr, rec_ang, te, Lr, k16 ? nullptr : reinterpret_cast<float*>(ccat + MlH), k16 ? ccat + MlH : nullptr);
+    if (Ll == Lr) {  // stacked [lig | rec] key mask for the one-pass ligand_feature_emb attention
+      jobs.cat_dst = maskcat; jobs.cat_a = lig_mask; jobs.cat_b = rec_mask; jobs.cat_na = Ml; jobs.cat_nb = Mr;
+    }
     SD_TRY(embed_ln_multi<T>(jobs, eps, H, s));
   }
 
   // ligand_feature_emb on ligand AND receptor tokens in one pass (model.py:214-224, quirk Q1)
   std::vector<Segment> segs;
   if (Ll == Lr) {
-    SD_CUDA(cudaMemcpyAsync(maskcat, lig_mask, static_cast<size_t>(Ml) * 4, cudaMemcpyDeviceToDevice, s));
-    SD_CUDA(cudaMemcpyAsync(maskcat + Ml, rec_mask, static_cast<size_t>(Mr) * 4, cudaMemcpyDeviceToDevice, s));
     segs.push_back({0, 2 * B, Ll, maskcat});
   } else {
     segs.push_back({0, B, Ll, lig_mask});
@@ -631,7 +632,6 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   }
 
   // decoder_normalize: SELayer conditioned on the timestep only (c broadcast over L; model.py:232-235)
-  SD_TRY(to_act(te, static_cast<size_t>(B) * H, teT, s));
   std::vector<Segment> lseg{{0, B, Ll, lig_mask}};
   SD_TRY(se_layer<T>(*this, wfmt, se_dec, h, teT, B, Ll, Ml, lseg, sb, x, s));
 
@@ -716,8 +716,7 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
   key.seed = seed; key.gid0 = gid0; key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables;
   auto one_step = [&](cudaStream_t st) -> int {
     SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, st));
-    SD_TRY(reverse_step(d_tables, 1, B, Ll, x_cur, logits, diverse, noise_E, seed, gid0, 0, d_step, x_cur, nullptr, st));
-    SD_TRY(step_advance(d_step, st));
+    SD_TRY(reverse_step(d_tables, 1, B, Ll, x_cur, logits, diverse, noise_E, seed, gid0, 0, d_step, x_cur, nullptr, st, d_step + 1));
     return SEQDIFF_OK;
   };
   if (!graph_exec || !(key == graph_key)) {

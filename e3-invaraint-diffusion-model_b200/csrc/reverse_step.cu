@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel
                                                                    const float* __restrict__ x_t, const float* __restrict__ logits,
                                                                    int diverse, const float* __restrict__ noise_E, uint64_t seed,
                                                                    uint64_t graph_id0, uint32_t step, const int* __restrict__ step_ptr,
-                                                                   float* __restrict__ x_s, uint8_t* __restrict__ idx_out) {
+                                                                   float* __restrict__ x_s, uint8_t* __restrict__ idx_out, int* __restrict__ advance) {
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   __shared__ float sQt[C * C], sQsb[C * C], sQtb[C * C];
@@ -173,7 +173,22 @@ __global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel
   const int b = blockIdx.y;  // grid = (ceil(L / 128) residue chunks, graphs): enough CTAs to stream at HBM rate
   const size_t n_res = static_cast<size_t>(gridDim.y) * L;
   if (step_ptr) {
-    const int sidx = *step_ptr;
+    // one read of the step counter per CTA (thread 0), shared through smem; with `advance` the CTA that is last to have
+    // read it moves the counter on to the next step -- no CTA can still be about to read the old value then
+    __shared__ int s_sidx;
+    if (threadIdx.x == 0) {
+      s_sidx = *reinterpret_cast<const volatile int*>(step_ptr);
+      if (advance) {
+        __threadfence();
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(reinterpret_cast<unsigned*>(advance), 1u) == total - 1u) {
+          *reinterpret_cast<volatile unsigned*>(advance) = 0u;
+          *const_cast<int*>(step_ptr) = s_sidx - 1;
+        }
+      }
+    }
+    __syncthreads();
+    const int sidx = s_sidx;
     if (sidx == 0) return;  // last step: caller keeps the raw logits (sample.py:147-148)
     step = static_cast<uint32_t>(sidx);
     q_tables += static_cast<size_t>(sidx) * (3 * C * C);
@@ -350,15 +365,15 @@ __global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel
 
 int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_t, const float* logits, int diverse,
                  const float* noise_E, uint64_t seed, uint64_t graph_id0, uint32_t step, const int* step_ptr, float* x_s,
-                 uint8_t* idx_out, cudaStream_t s) {
+                 uint8_t* idx_out, cudaStream_t s, int* advance) {
   SD_CHECK(B > 0 && L > 0, "empty reverse step");
   SD_CHECK(n_tab == 1 || n_tab == B, "q_tables must hold 1 or B (Qt,Qsb,Qtb) triples");
   static const int rpt = [] { const char* e = getenv("SEQDIFF_REV_RPT"); return e ? atoi(e) : 2; }();  // residues per thread
   const dim3 grid(ceil_div(L, rpt * kRevThreads), B);  // residues per thread: amortises the per-CTA table build
   if (diverse && !noise_E)
-    SD_CUDA(launch_k(reverse_step_kernel<true>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out));
+    SD_CUDA(launch_k(reverse_step_kernel<true>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out, advance));
   else
-    SD_CUDA(launch_k(reverse_step_kernel<false>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out));
+    SD_CUDA(launch_k(reverse_step_kernel<false>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out, advance));
   SD_LAUNCHED("reverse_step", s);
   return SEQDIFF_OK;
 }

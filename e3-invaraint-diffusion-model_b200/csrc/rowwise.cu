@@ -41,8 +41,10 @@ __device__ __forceinline__ void row_stats(const float (&v)[VPL][8], int H, float
 }
 
 // ---------------------------------------------------------------------------------------------------
+// out16 (optional): the same values in the 16-bit operand format (fmt16: 0 = fp16, 1 = bf16) -- the conditioning input of
+// decoder_normalize's adaLN GEMMs, written here instead of by a separate conversion launch
 __global__ void timestep_embed_kernel(const float* __restrict__ timestep, const int* __restrict__ step_ptr,
-                                      const float* __restrict__ W, int B, int H, float* __restrict__ out) {
+                                      const float* __restrict__ W, int B, int H, float* __restrict__ out, void* __restrict__ out16, int fmt16) {
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int half = H / 2;
@@ -52,13 +54,26 @@ __global__ void timestep_embed_kernel(const float* __restrict__ timestep, const 
   const float t = step_ptr ? static_cast<float>(*step_ptr) : timestep[b];
   // x[:, None] * W[None, :] * 2 * torch.pi  -> three separately rounded fp32 multiplies (model.py:95)
   const float x = __fmul_rn(__fmul_rn(__fmul_rn(t, W[j]), 2.0f), 3.14159274101257324f);
-  out[static_cast<size_t>(b) * H + j] = sinf(x);
-  out[static_cast<size_t>(b) * H + half + j] = cosf(x);
+  const float sv = sinf(x), cv = cosf(x);
+  out[static_cast<size_t>(b) * H + j] = sv;
+  out[static_cast<size_t>(b) * H + half + j] = cv;
+  if (out16) {
+    if (fmt16 == 1) {
+      bf16* o = static_cast<bf16*>(out16);
+      o[static_cast<size_t>(b) * H + j] = from_f32<bf16>(sv);
+      o[static_cast<size_t>(b) * H + half + j] = from_f32<bf16>(cv);
+    } else {
+      f16* o = static_cast<f16*>(out16);
+      o[static_cast<size_t>(b) * H + j] = from_f32<f16>(sv);
+      o[static_cast<size_t>(b) * H + half + j] = from_f32<f16>(cv);
+    }
+  }
 }
 
-int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, cudaStream_t s) {
+int timestep_embed(const float* timestep, const int* step_ptr, const float* W, int B, int H, float* out, void* out16, int fmt16,
+                   cudaStream_t s) {
   const int n = B * (H / 2);
-  SD_CUDA(launch_k(timestep_embed_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, s, timestep, step_ptr, W, B, H, out));
+  SD_CUDA(launch_k(timestep_embed_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, s, timestep, step_ptr, W, B, H, out, out16, fmt16));
   SD_LAUNCHED("timestep_embed", s);
   return SEQDIFF_OK;
 }
@@ -83,6 +98,10 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_multi_kernel(const __gri
   for (int i = threadIdx.x; i < fin * H / 4; i += kRowThreads) sW4[i] = __ldg(reinterpret_cast<const float4*>(job.Wt) + i);
   pdl_trigger();
   pdl_wait();  // inputs / timestep features come from the predecessor kernels
+  if (jobs.cat_dst) {  // [mask_a | mask_b] for the stacked ligand|receptor attention (was two memcpy nodes per forward)
+    for (int i = blockIdx.x * kRowThreads + threadIdx.x; i < jobs.cat_na + jobs.cat_nb; i += gridDim.x * kRowThreads)
+      jobs.cat_dst[i] = i < jobs.cat_na ? __ldg(jobs.cat_a + i) : __ldg(jobs.cat_b + (i - jobs.cat_na));
+  }
   __syncthreads();
   constexpr int TOK = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
