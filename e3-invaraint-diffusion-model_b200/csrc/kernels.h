@@ -60,6 +60,7 @@ struct EmbedJob {
 struct EmbedJobs {
   EmbedJob j[4];
   int n;
+  int max_fin;  // filled by embed_ln_multi (smem layout)
   // optional side job: cat_dst = [cat_a (cat_na floats) | cat_b (cat_nb floats)] (stacked key masks)
   float* cat_dst;
   const float* cat_a;

@@ -9,6 +9,7 @@
 namespace seqdiff {
 
 constexpr int kRowThreads = 256;  // 8 warps = 8 rows per CTA
+constexpr int kEmbedTok = 2;     // tokens per warp pass of the embedding kernel (2: ~100 registers, two CTAs per SM)
 
 template <typename T, int VPL>
 __device__ __forceinline__ void load_row(const T* __restrict__ row, int lane, float (&v)[VPL][8]) {
@@ -86,7 +87,7 @@ int timestep_embed(const float* timestep, const int* step_ptr, const float* W, i
 // inputs touch at most 4 of their 20 weight rows.  (Before: every warp streamed the whole 61 KB table from L2 for its 4
 // tokens, 250 MB per launch, 27 us x 4 launches per forward.)
 template <typename T, int VPL>
-__global__ void __launch_bounds__(kRowThreads) embed_ln_multi_kernel(const __grid_constant__ EmbedJobs jobs, float eps, int H) {
+__global__ void __launch_bounds__(kRowThreads, 2) embed_ln_multi_kernel(const __grid_constant__ EmbedJobs jobs, float eps, int H) {
   extern __shared__ float4 sW4[];
   float* sW = reinterpret_cast<float*>(sW4);
   int q = 0;
@@ -103,12 +104,29 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_multi_kernel(const __gri
       jobs.cat_dst[i] = i < jobs.cat_na ? __ldg(jobs.cat_a + i) : __ldg(jobs.cat_b + (i - jobs.cat_na));
   }
   __syncthreads();
-  constexpr int TOK = 4;
+  constexpr int TOK = kEmbedTok;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cta_local = static_cast<int>(blockIdx.x) - job.cta_begin;
   T* outT = static_cast<T*>(job.outT);
-  for (int grp = cta_local * (kRowThreads / 32) + warp; grp * TOK < M; grp += job.cta_count * (kRowThreads / 32)) {
+  // the 4 x fin input values of a group are fetched with coalesced loads ONE GROUP AHEAD into a per-warp smem slot and read
+  // back as broadcasts; scalar __ldg inside the k loop put a ~600-cycle global round trip on every k (66 us per launch)
+  float* sx = sW + static_cast<size_t>(jobs.max_fin) * H + warp * (2 * TOK * 32);
+  const int gstep = job.cta_count * (kRowThreads / 32);
+  auto fetch_x = [&](int grp_n, int buf) {
+    const size_t base = static_cast<size_t>(grp_n) * TOK * fin;
+    const size_t lim = static_cast<size_t>(M) * fin;
+    for (int i = lane; i < TOK * fin; i += 32) sx[buf * TOK * 32 + i] = (base + i < lim) ? __ldg(job.x + base + i) : 0.f;
+  };
+  int xb = 0;
+  {
+    const int g0 = cta_local * (kRowThreads / 32) + warp;
+    if (g0 * TOK < M) fetch_x(g0, 0);
+    __syncwarp();
+  }
+  for (int grp = cta_local * (kRowThreads / 32) + warp; grp * TOK < M; grp += gstep, xb ^= 1) {
     const int tok0 = grp * TOK;
+    if ((grp + gstep) * TOK < M) fetch_x(grp + gstep, xb ^ 1);  // next group's inputs: in flight during this group's math
+    const float* xs = sx + xb * TOK * 32;
     float acc[TOK][VPL][8];
 #pragma unroll
     for (int t = 0; t < TOK; ++t)
@@ -121,7 +139,7 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_multi_kernel(const __gri
       bool any = false;
 #pragma unroll
       for (int t = 0; t < TOK; ++t) {
-        xv[t] = (tok0 + t < M) ? __ldg(job.x + static_cast<size_t>(tok0 + t) * fin + k) : 0.f;
+        xv[t] = xs[t * fin + k];  // (rows past M were staged as zeros)
         any |= xv[t] != 0.f;
       }
       if (!any) continue;  // warp-uniform (every lane holds the same xv)
@@ -166,6 +184,7 @@ __global__ void __launch_bounds__(kRowThreads) embed_ln_multi_kernel(const __gri
       if (job.out32) store_row<float, VPL>(job.out32 + static_cast<size_t>(tok0 + t) * H, lane, v);
       if (outT) store_row<T, VPL>(outT + static_cast<size_t>(tok0 + t) * H, lane, v);
     }
+    __syncwarp();  // next group's staged inputs are complete; this group's slot may be overwritten in the next iteration
   }
 }
 
@@ -190,24 +209,25 @@ int embed_ln_multi(EmbedJobs jobs, float eps, int H, cudaStream_t s) {
     total += jobs.j[q].M;
     max_fin = jobs.j[q].fin > max_fin ? jobs.j[q].fin : max_fin;
   }
-  const int budget = num_sms();  // ~170 registers x 256 threads: one CTA per SM
+  const int budget = 2 * num_sms();  // two resident CTAs per SM
   int begin = 0;
   for (int q = 0; q < jobs.n; ++q) {
     int c = static_cast<int>(static_cast<long>(budget) * jobs.j[q].M / total);
-    const int need = ceil_div(jobs.j[q].M, 4 * (kRowThreads / 32));
+    const int need = ceil_div(jobs.j[q].M, kEmbedTok * (kRowThreads / 32));
     if (c < 1) c = 1;
     if (c > need) c = need;
     jobs.j[q].cta_begin = begin;
     jobs.j[q].cta_count = c;
     begin += c;
   }
-  const size_t smem = static_cast<size_t>(max_fin) * H * sizeof(float);
+  jobs.max_fin = max_fin;
+  const size_t smem = static_cast<size_t>(max_fin) * H * sizeof(float) + (kRowThreads / 32) * 2 * kEmbedTok * 32 * sizeof(float);
 #define SD_EMBED_LAUNCH()                                                                                                          \
   {                                                                                                                                \
     auto kfn = embed_ln_multi_kernel<T, VPL>;                                                                                      \
     static bool configured = false;                                                                                                \
     if (!configured) {                                                                                                             \
-      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4));                              \
+      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4 + 8192));                       \
       configured = true;                                                                                                           \
     }                                                                                                                              \
     SD_CUDA(launch_k(kfn, dim3(begin), dim3(kRowThreads), smem, s, jobs, eps, H));                                                 \
