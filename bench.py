@@ -351,6 +351,49 @@ def main():
                                   "share_of_forward": gemm_ms / total_ms if total_ms else None,
                                   "kernel_ms_per_forward": {k: v[0] / reps for k, v in sorted(prof.items())},
                                   "whole_step_model_flops_frac": (value / world) * wl["flops"] / 1e12 / peak}
+            # ---- the same GEMM shapes timed alone: every (M, N, K, epilogue) of the forward as 20 launches in a captured CUDA
+            #      graph (no CPU launch gaps, no other kernels between them), CUDA events around the replay; against the BURST
+            #      peak, which is the denominator for a kernel timed in isolation ----
+            try:
+                import ctypes as _ct
+                Ml_, Mt_ = B * L, 2 * B * L
+                shapes = [(1, Mt_, H, H, 2, False), (1, Mt_, 6 * H, H, 0, False), (1, Mt_, 3 * H, H, 0, False), (1, Mt_, H, H, 0, True),
+                          (1, Mt_, 4 * H, H, 1, False), (1, Mt_, H, 4 * H, 0, True), (1, Ml_, 2 * NL * H, H, 0, False),
+                          (NL + 1, Ml_, 3 * H, H, 0, False), (2 * NL + 1, Ml_, H, H, 0, True), (NL + 1, Ml_, H, H, 0, False),
+                          (NL, Ml_, I, H, 1, False), (NL, Ml_, H, I, 0, True), (1, Ml_, 4 * H, H, 1, False), (1, Ml_, H, 4 * H, 0, True)]
+                pp = sd._cabi.ptr
+                iso_us, iso_fl = 0.0, 0.0
+                for cnt, M_, N_, K_, epi_, res_ in shapes:
+                    A_ = torch.randn(M_, K_, device=dev).bfloat16()
+                    W_ = (torch.randn(N_, K_, device=dev) / math.sqrt(K_)).bfloat16()
+                    b_ = torch.randn(N_, device=dev)
+                    R_ = torch.randn(M_, N_, device=dev) if res_ else None
+                    C_ = torch.empty(M_, N_, device=dev, dtype=torch.float32 if res_ else torch.bfloat16)
+                    call_ = lambda st_: lib.seqdiff_op_gemm(1, M_, N_, K_, pp(A_), pp(W_), pp(b_), pp(R_), epi_, pp(C_), st_)
+                    assert call_(_ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)) == 0  # first call: tile tuner
+                    torch.cuda.synchronize(dev)
+                    gr_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr_):
+                        cs_ = _ct.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                        for _ in range(20):
+                            assert call_(cs_) == 0
+                    gr_.replay()
+                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize(dev)
+                    g0.record()
+                    gr_.replay()
+                    g1.record()
+                    torch.cuda.synchronize(dev)
+                    iso_us += cnt * g0.elapsed_time(g1) / 20 * 1e3
+                    iso_fl += cnt * 2.0 * M_ * N_ * K_
+                    del gr_
+                burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+                result["roofline_isolated"] = {"kernel": "gemm_tcgen05_kernel, each shape of the forward as 20 launches in a captured graph", "bound": "tensor",
+                                               "achieved": iso_fl / iso_us / 1e6, "peak": burst, "unit": "TFLOP/s", "frac": iso_fl / iso_us / 1e6 / burst,
+                                               "gemm_us_per_forward": iso_us, "flops_per_forward": iso_fl,
+                                               "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)"}
+            except Exception as ex:  # the isolated sweep is an extra; never fail the bench line over it
+                result["roofline_isolated"] = {"error": str(ex)[:200]}
             # ---- the HBM-bound kernel of the path: reverse step at a size that streams (256 graphs x 512 residues) ----
             RB, RL = 256, 512
             rx = torch.nn.functional.one_hot(torch.randint(0, 20, (RB, RL), device=dev), 20).float()

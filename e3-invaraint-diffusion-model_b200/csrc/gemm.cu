@@ -723,8 +723,12 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
         // Candidates are timed the way the sampling loop runs them: 8 launches captured into a CUDA graph on a private
         // stream, replayed once to warm up and once between two events.  (Eager launches between events are dominated by
         // launch latency for these 10-30 us kernels and picked e.g. 256x384 pair tiles where 128x192 is 10 % faster in situ.)
-        static cudaStream_t ts = nullptr;
-        if (!ts) SD_CUDA(cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking));
+        static cudaStream_t tune_streams[64] = {};  // one private stream per device (a process may hold handles on several GPUs)
+        int dev_id = 0;
+        SD_CUDA(cudaGetDevice(&dev_id));
+        SD_CHECK(dev_id >= 0 && dev_id < 64, "device ordinal out of range");
+        if (!tune_streams[dev_id]) SD_CUDA(cudaStreamCreateWithFlags(&tune_streams[dev_id], cudaStreamNonBlocking));
+        cudaStream_t ts = tune_streams[dev_id];
         cudaEvent_t e0, e1;
         SD_CUDA(cudaEventCreate(&e0));
         SD_CUDA(cudaEventCreate(&e1));
