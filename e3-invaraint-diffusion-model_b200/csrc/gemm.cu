@@ -100,6 +100,42 @@ int make_tmap(const void* ptr, int fmt, int rows, int cols, int box_rows, CUtens
   return SEQDIFF_OK;
 }
 
+// Output tile map of the 16-bit GEMM epilogue: row-major [rows, cols], boxes of 32 rows x 32 columns (64 B rows, SWIZZLE_64B).
+// Rows past `rows` are clipped by the TMA store, so the epilogue needs no bounds checks.  Cached like make_tmap.
+int make_tmap_store16(const void* ptr, int fmt, int rows, int cols, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, rows, cols, -32, fmt};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return SEQDIFF_OK;
+    }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return SEQDIFF_ERR_CUDA;
+  }
+  SD_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (cols % 32) == 0, "TMA store operand must be 16B aligned with N a multiple of 32");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim,
+                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (store) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return SEQDIFF_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  cache.emplace(key, *out);
+  return SEQDIFF_OK;
+}
+
 // [B][rows][cols] 16-bit tensor (cols contiguous): boxes of 1 x box_rows x 64 columns, 128B swizzle.  Used for TMA STORES of
 // per-graph tiles: rows past `rows` are clipped per graph instead of spilling into the next graph's rows.
 int make_tmap_3d(const void* ptr, int fmt, int batch, int rows, int cols, int box_rows, CUtensorMap* out) {
@@ -184,10 +220,10 @@ struct LnOutArgs {
 };
 template <int BN, int EPI, int RESID, typename TOut, bool CG2, typename TH = void>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
                     uint32_t idesc, const float2* __restrict__ ln_stats, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                    unsigned long long* __restrict__ trace, const LnOutArgs lno) {
+                    unsigned long long* __restrict__ trace, const LnOutArgs lno, int l2_stream) {
   constexpr bool LNOUT = !std::is_void<TH>::value;
   using Cfg = GemmCfg<BN, CG2, LNOUT>;
   static_assert(!LNOUT || (!CG2 && RESID != 0 && EPI == 0 && std::is_same<TOut, float>::value), "fused LayerNorm: 1-CTA MMA, fp32 C with residual");
@@ -230,6 +266,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (!std::is_same<TOut, float>::value) tma_prefetch_desc(&tmC);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -263,6 +300,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------- TMA producer -------------------------------
     // (whole warp runs the loop; one elected lane issues -- see common.cuh "warp-uniform single-issuer variants")
     {
+      // l2_stream: the output is larger than L2 -- operands are loaded evict_last, the output stored evict_first (below)
+      const uint64_t pol_keep = l2_stream ? l2_policy_evict_last() : 0ull;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -275,15 +314,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // both CTAs' tiles complete on the LEADER's full barrier, which the leader arms for the bytes of the pair
             if (cta_rank == 0) mbar_expect_tx_e(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_cg2_e(sA + stage * Cfg::kABytes, &tmA, bar, kb * kBK, a_row);
+            if (l2_stream) tma_load_2d_cg2_e_hint(sA + stage * Cfg::kABytes, &tmA, bar, kb * kBK, a_row, pol_keep);
+            else tma_load_2d_cg2_e(sA + stage * Cfg::kABytes, &tmA, bar, kb * kBK, a_row);
 #pragma unroll
-            for (int j = 0; j < Cfg::kNSub; ++j)  // half of each UMMA's B tile lives in each CTA of the pair
-              tma_load_2d_cg2_e(sB + stage * Cfg::kBBytes + j * Cfg::kBoxRows * kBK * 2, &tmB, bar, kb * kBK,
-                                n_blk * BN + j * Cfg::kSubN + static_cast<int>(cta_rank) * Cfg::kBoxRows);
+            for (int j = 0; j < Cfg::kNSub; ++j) {  // half of each UMMA's B tile lives in each CTA of the pair
+              if (l2_stream)
+                tma_load_2d_cg2_e_hint(sB + stage * Cfg::kBBytes + j * Cfg::kBoxRows * kBK * 2, &tmB, bar, kb * kBK,
+                                       n_blk * BN + j * Cfg::kSubN + static_cast<int>(cta_rank) * Cfg::kBoxRows, pol_keep);
+              else
+                tma_load_2d_cg2_e(sB + stage * Cfg::kBBytes + j * Cfg::kBoxRows * kBK * 2, &tmB, bar, kb * kBK,
+                                  n_blk * BN + j * Cfg::kSubN + static_cast<int>(cta_rank) * Cfg::kBoxRows);
+            }
           } else {
             mbar_expect_tx_e(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d_e(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, a_row);
-            tma_load_2d_e(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
+            if (l2_stream) {
+              tma_load_2d_e_hint(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, a_row, pol_keep);
+              tma_load_2d_e_hint(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, pol_keep);
+            } else {
+              tma_load_2d_e(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, a_row);
+              tma_load_2d_e(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -340,6 +390,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t aphase = 0;
     int ln_it = 0;  // tiles finished by this CTA (fused LayerNorm exchange parity / phase)
     (void)ln_it;
+    constexpr bool kTmaOut = !std::is_same<TOut, float>::value && RESID == 0;  // 16-bit output tiles leave through TMA stores
+    int pcount = 0;  // staging panels used so far (they alternate across chunks AND tiles)
+    (void)pcount;
+    const uint64_t pol_stream = (kTmaOut && l2_stream) ? l2_policy_evict_first() : 0ull;
+    (void)pol_stream;
     constexpr int NCH = BN / 64;  // 32-column chunks per warp and tile
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -347,6 +402,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN) + half * (BN / 2);
       const int col0 = n_blk * BN + half * (BN / 2) + 4 * lc;  // this lane's 4 columns of chunk 0; chunk ci adds 32 ci
       const bool full = row_base + 32 <= M;                    // warp-uniform: no row of this warp's slab is out of range
+      float rs[LNOUT ? 8 : 1], rq[LNOUT ? 8 : 1];  // fused LayerNorm: this lane's partial row sums / sums of squares (8 rows x 4 cols x NCH chunks)
+      if (LNOUT) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+      }
+      (void)rs; (void)rq;
+      if constexpr (kTmaOut) {
+        // ---- 16-bit outputs without residual: no transpose.  Each thread owns one accumulator row (TMEM lane) and 32
+        // columns per chunk: bias (broadcast loads) / activation / pack, 64 B per row into a SWIZZLE_64B panel, one TMA
+        // store per 32 x 32 chunk.  Per-lane STG of the transposed layout went through the LSU / L1TEX path shared with the
+        // operand fills and slowed the concurrent mainloop by 20 % (timelines with the stores removed: 8.1 k -> 6.75 k cycles
+        // per 128 x 256 x 768 tile); the bulk store leaves the SM through the async proxy, rows past M are clipped by the map.
+        const int colw = n_blk * BN + half * (BN / 2);  // first column of this warp's slab
+        uint8_t* panels = reinterpret_cast<uint8_t*>(stage);  // this warp's 4 KB: two 32 x 64 B panels
+        TR(20);
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        TR(21);
+        uint32_t r[2][32];
+        tmem_ld_32x32(t_row, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int cur = ci & 1;
+          float4 bv[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) bv[j4] = __ldg(reinterpret_cast<const float4*>(bias + colw + 32 * ci + 4 * j4));  // same address in every lane
+          tmem_ld_wait();
+          if (ci + 1 < NCH) tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * (ci + 1)), r[cur ^ 1]);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float a0 = __uint_as_float(r[cur][4 * j4]) + bv[j4].x, a1 = __uint_as_float(r[cur][4 * j4 + 1]) + bv[j4].y;
+            float a2 = __uint_as_float(r[cur][4 * j4 + 2]) + bv[j4].z, a3 = __uint_as_float(r[cur][4 * j4 + 3]) + bv[j4].w;
+            if (EPI == 1) { a0 = gelu_fast(a0); a1 = gelu_fast(a1); a2 = gelu_fast(a2); a3 = gelu_fast(a3); }
+            if (EPI == 2) { a0 = silu_fast(a0); a1 = silu_fast(a1); a2 = silu_fast(a2); a3 = silu_fast(a3); }
+            pk[2 * j4] = pack2<TOut>(a0, a1);
+            pk[2 * j4 + 1] = pack2<TOut>(a2, a3);
+          }
+          uint8_t* panel = panels + (pcount & 1) * 2048;
+          if (lane == 0) tma_store_wait_read1();  // the store that last used this panel (two chunks ago) has read it
+          __syncwarp();
+          // SWIZZLE_64B: 16 B chunk index XOR bits [7:8] of the ABSOLUTE shared address (the panels sit 256 B past a 1 KB
+          // boundary, behind the barrier block, so the pattern is not simply a function of the row number)
+          uint8_t* prow = panel + lane * 64;
+          const uint32_t sw = (smem_u32(prow) >> 7) & 3u;
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16)
+            *reinterpret_cast<uint4*>(prow + ((static_cast<uint32_t>(c16) ^ sw) << 4)) =
+                make_uint4(pk[4 * c16], pk[4 * c16 + 1], pk[4 * c16 + 2], pk[4 * c16 + 3]);
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (l2_stream) tma_store_2d_hint(&tmC, panel, colw + 32 * ci, row_base, pol_stream);
+            else tma_store_2d(&tmC, panel, colw + 32 * ci, row_base);
+            tma_store_commit();
+          }
+          ++pcount;
+        }
+      } else {
       // Everything the tile needs from global memory that does not depend on the accumulator is fetched BEFORE the wait
       // on the MMAs (LayerNorm row statistics, the first chunk's bias / residual); inside the chunk loop the next chunk's
       // bias / residual / LayerNorm affine and the next chunk's TMEM load are in flight while the current chunk is transposed and
@@ -378,11 +492,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (RESID) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) fetch_resid_row(0, i);
-      }
-      float rs[LNOUT ? 8 : 1], rq[LNOUT ? 8 : 1];  // fused LayerNorm: this lane's partial row sums / sums of squares (8 rows x 4 cols x NCH chunks)
-      if (LNOUT) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
       }
       TR(20);
       mbar_wait(&tfull_bar[as], aphase);
@@ -450,6 +559,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         };
         if (full) emit_rows(std::false_type{}); else emit_rows(std::true_type{});
         __syncwarp();
+      }
       }
       TR(23);
       tc_fence_before();
@@ -543,6 +653,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
+    if (kTmaOut && lane == 0) tma_store_wait_all();  // bulk stores complete (and visible) before the CTA exits
   }
 
   TR(43);
@@ -556,8 +667,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int BN, int EPI, int RESID, typename TOut, bool CG2>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, void* C, int M, int N, int K,
-                     uint32_t idesc, cudaStream_t s, const LnResid* ln = nullptr) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias, const float* resid, void* C, int M,
+                     int N, int K, uint32_t idesc, cudaStream_t s, const LnResid* ln = nullptr) {
   using Cfg = GemmCfg<BN, CG2>;
   auto kfn = gemm_tcgen05_kernel<BN, EPI, RESID, TOut, CG2>;
   static bool configured = false;  // per instantiation
@@ -568,8 +679,12 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* 
   const int tiles = ceil_div(M, CG2 ? 2 * kBM : kBM) * (N / BN);
   const int slots = CG2 ? num_sms() / 2 : num_sms();
   const int grid = (tiles < slots ? tiles : slots) * (CG2 ? 2 : 1);
-  SD_CUDA(launch_kc(CG2 ? 2 : 1, kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, static_cast<TOut*>(C), M, N, K,
-                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, LnOutArgs{}));
+  // SEQDIFF_GEMM_L2HINT=1: a 16-bit output that cannot stay in L2 anyway (> 64 MB) is stored evict_first and the operands are
+  // loaded evict_last.  Measured neutral on B200 (tile cadence, per-shape sweep and bench all within noise), so off by default.
+  static const int hint_on = [] { const char* e = getenv("SEQDIFF_GEMM_L2HINT"); return e ? atoi(e) : 0; }();
+  const int l2_stream = (hint_on && !std::is_same<TOut, float>::value && RESID == 0 && static_cast<double>(M) * N * 2 > 64e6) ? 1 : 0;
+  SD_CUDA(launch_kc(CG2 ? 2 : 1, kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, tc, bias, resid, static_cast<TOut*>(C), M, N, K,
+                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, LnOutArgs{}, l2_stream));
   SD_LAUNCHED(CG2 ? "gemm_tcgen05_2cta" : "gemm_tcgen05", s);
   return SEQDIFF_OK;
 }
@@ -609,8 +724,8 @@ static int launch_tc_ln(const CUtensorMap& ta, const CUtensorMap& tb, const floa
   const int waves = ceil_div(num_m, max_cl);
   const int clusters = ceil_div(num_m, waves);
   const LnOutArgs a{lo.g, lo.b, lo.eps, lo.h, lo.stats};
-  SD_CUDA(launch_kc(kLnCl, kfn, dim3(clusters * kLnCl), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, bias, resid, C, M, N, K, idesc,
-                    ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, a));
+  SD_CUDA(launch_kc(kLnCl, kfn, dim3(clusters * kLnCl), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, ta /*unused store map*/, bias, resid, C, M, N, K, idesc,
+                    ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, a, 0));
   SD_LAUNCHED("gemm_tcgen05_ln", s);
   return SEQDIFF_OK;
 }
@@ -647,19 +762,19 @@ static int pick_cfg(int M, int N, int K) {
 }
 
 template <int BN, bool CG2>
-static int dispatch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid, int epi, void* C,
+static int dispatch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias, const float* resid, int epi, void* C,
                        int out_kind, int M, int N, int K, uint32_t idesc, cudaStream_t s, const LnResid* ln) {
-  if (resid && ln) return launch_tc<BN, 0, 2, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s, ln);
-  if (resid) return launch_tc<BN, 0, 1, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  if (out_kind == 2) return launch_tc<BN, 0, 0, float, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (resid && ln) return launch_tc<BN, 0, 2, float, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s, ln);
+  if (resid) return launch_tc<BN, 0, 1, float, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
+  if (out_kind == 2) return launch_tc<BN, 0, 0, float, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
   if (out_kind == 1) {
-    if (epi == 0) return launch_tc<BN, 0, 0, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-    if (epi == 1) return launch_tc<BN, 1, 0, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-    return launch_tc<BN, 2, 0, bf16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+    if (epi == 0) return launch_tc<BN, 0, 0, bf16, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
+    if (epi == 1) return launch_tc<BN, 1, 0, bf16, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
+    return launch_tc<BN, 2, 0, bf16, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
   }
-  if (epi == 0) return launch_tc<BN, 0, 0, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  if (epi == 1) return launch_tc<BN, 1, 0, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
-  return launch_tc<BN, 2, 0, f16, CG2>(ta, tb, bias, resid, C, M, N, K, idesc, s);
+  if (epi == 0) return launch_tc<BN, 0, 0, f16, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
+  if (epi == 1) return launch_tc<BN, 1, 0, f16, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
+  return launch_tc<BN, 2, 0, f16, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
 }
 
 // a_fmt / w_fmt: 0 = fp16, 1 = bf16.  out_kind: 0 = fp16, 1 = bf16, 2 = fp32 (identity epilogue only; implied by resid).
@@ -778,12 +893,14 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
   SD_TRY(make_tmap(A, a_fmt, M, K, kBM, &ta));
   const int sub_n = bn > 256 ? bn / 2 : bn;  // N of one tcgen05.mma
   SD_TRY(make_tmap(W, w_fmt, N, K, cg2 ? sub_n / 2 : sub_n, &tb));
+  CUtensorMap tc = ta;  // store map of 16-bit outputs (unused for fp32 C)
+  if (out_kind != 2) SD_TRY(make_tmap_store16(C, out_kind, M, N, &tc));
   const uint32_t idesc = umma_idesc_16(cg2 ? 2 * kBM : kBM, sub_n, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
 #define SD_DISPATCH(BN_)                                                                                          \
-  return cg2 ? dispatch_tc<BN_, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)         \
-             : dispatch_tc<BN_, false>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)
-  if (bn == 512) return dispatch_tc<512, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid);
-  if (bn == 384) return dispatch_tc<384, true>(ta, tb, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid);
+  return cg2 ? dispatch_tc<BN_, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)         \
+             : dispatch_tc<BN_, false>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)
+  if (bn == 512) return dispatch_tc<512, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid);
+  if (bn == 384) return dispatch_tc<384, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid);
   if (bn == 256) { SD_DISPATCH(256); }
   if (bn == 192) { SD_DISPATCH(192); }
   SD_DISPATCH(128);
