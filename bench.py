@@ -306,9 +306,10 @@ def main():
         # ---- end to end through the public API: denoise(batch_on_host, ...) -> decoded sequences on the host ----
         pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
         px_T = x_T.pin_memory()
-        h2d = sum(v.numel() * v.element_size() for k, v in pinned.items() if torch.is_tensor(v) and k != "ligand_seq")
-        h2d += px_T.numel() * 4 + T * 3 * 400 * 4
-        d2h = B * L * 8  # argmax indices (int64) of the final logits
+        # loop inputs + x_T + the [T,3,20,20] tables; the decode kernel also takes the true sequence and the mask on the device
+        h2d = sum(v.numel() * v.element_size() for k, v in pinned.items() if torch.is_tensor(v))
+        h2d += pinned["ligand_attn_mask"].numel() * 4 + px_T.numel() * 4 + T * 3 * 400 * 4
+        d2h = 2 * B * L + B * 2 * 8  # decode kernel output: pred / true indices (u8) + per-graph (matches, valid) counts (i64)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libseqdiff_b200.so")
-SOURCES = ["gemm.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "attention_pipe.cu", "reverse_step.cu", "collate.cu", "model.cu", "cabi.cu"]
+SOURCES = ["gemm.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "attention_pipe.cu", "reverse_step.cu", "gauss_step.cu", "decode_loss.cu", "collate.cu", "model.cu", "cabi.cu"]
 HEADERS = ["common.cuh", "kernels.h", "model.cuh", os.path.join("..", "..", "include", "seqdiff_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

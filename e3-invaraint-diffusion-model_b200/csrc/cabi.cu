@@ -146,6 +146,69 @@ int seqdiff_sample(seqdiff_model_t* m, int precision, int B, int L_lig, int L_re
   SD_GUARD_END
 }
 
+int seqdiff_struct_model_create(const seqdiff_config_t* cfg, int device, seqdiff_model_t** out) {
+  SD_GUARD_BEGIN
+  SD_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  int ndev = 0;
+  SD_CUDA(cudaGetDeviceCount(&ndev));
+  SD_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+  seqdiff_model* m = new (std::nothrow) seqdiff_model();
+  SD_CHECK(m != nullptr, "out of host memory");
+  const int rc = m->impl.init(*cfg, device, kArchStructure);
+  if (rc != SEQDIFF_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return SEQDIFF_OK;
+  SD_GUARD_END
+}
+
+int seqdiff_struct_forward(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, const float* timestep,
+                           const float* noised_ligand_angles, const float* ligand_mask, const float* receptor_seq,
+                           const float* receptor_angles, const float* receptor_mask, float* out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && timestep && noised_ligand_angles && ligand_mask && receptor_seq && receptor_angles && receptor_mask && out, "null argument");
+  return m->impl.struct_forward(precision, B, L_lig, L_rec, timestep, nullptr, noised_ligand_angles, ligand_mask, receptor_seq, receptor_angles,
+                                receptor_mask, out, 3, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_struct_p_sample(const float* coef_steps, int T, int step, int B, int L, int F, const float* x_t, const float* model_output,
+                            const float* noise, uint64_t seed, uint64_t graph_id0, int wrap, float* x_out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(coef_steps && x_t && model_output && x_out, "null argument");
+  SD_CHECK(B > 0 && L > 0 && F > 0, "empty batch");
+  return gauss_step(coef_steps, T, B, L * F, x_t, model_output, noise, seed, graph_id0, step, nullptr, x_out, nullptr,
+                    static_cast<cudaStream_t>(stream), nullptr, wrap != 0);
+  SD_GUARD_END
+}
+
+int seqdiff_struct_sample(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, int T, const float* coef_steps, const float* x_T,
+                          const float* ligand_mask, const float* receptor_seq, const float* receptor_angles, const float* receptor_mask,
+                          const float* noise_steps, uint64_t seed, uint64_t graph_id0, float* steps_out, float* final_out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && coef_steps && x_T && ligand_mask && receptor_seq && receptor_angles && receptor_mask && final_out, "null argument");
+  return m->impl.struct_sample(precision, B, L_lig, L_rec, T, coef_steps, x_T, ligand_mask, receptor_seq, receptor_angles, receptor_mask,
+                               noise_steps, seed, graph_id0, steps_out, final_out, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_decode(int B, int L, const float* final_seq, const float* true_seq, const float* ligand_mask, uint8_t* pred_idx,
+                   uint8_t* true_idx, int32_t* counts, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(final_seq && true_seq && ligand_mask && pred_idx && true_idx && counts, "null argument");
+  return decode_sequences(B, L, final_seq, true_seq, ligand_mask, pred_idx, true_idx, counts, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* ligand_mask, double* terms, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(logits && x0 && x_t && ligand_mask && terms, "null argument");
+  return loss_terms(N, logits, x0, x_t, ligand_mask, terms, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
 int seqdiff_op_gemm(int precision, int M, int N, int K, const void* A, const void* W, const float* bias, const void* resid,
                     int epilogue, void* C, void* stream) {
   SD_GUARD_BEGIN

@@ -120,4 +120,21 @@ int apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float*
                    uint32_t step, float* x_t, uint8_t* idx_out, cudaStream_t s);
 int philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, cudaStream_t s);
 
+// ---- decode_loss.cu ---------------------------------------------------------------------------------
+// sample.py:208-224: pred_idx / true_idx [B*L] = argmax rows; counts [B,2] = (#masked matches, #masked)
+int decode_sequences(int B, int L, const float* final_seq, const float* true_seq, const float* mask, uint8_t* pred_idx, uint8_t* true_idx,
+                     int* counts, cudaStream_t s);
+// model.py:313-345 + utils.py:132-161: the ten reduction terms documented at seqdiff_loss_terms (include/seqdiff_b200.h).
+// One call in flight per (host thread, device): the per-CTA partials live in a per-thread scratch buffer.
+int loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* mask, double* terms, cudaStream_t s);
+
+// ---- gauss_step.cu ----------------------------------------------------------------------------------
+// Gaussian reverse step + angle wrap of the structure model (structure_model/sample.py:92-101,139-141) on B graphs of
+// per_graph = L * F elements.  coef [T,4] = (1/sqrt(alpha), beta, sqrt(1 - alphabar), sqrt(posterior_variance)) per step.
+// noise: N(0,1) values (one [B*per_graph] block; with step_ptr a [T, B*per_graph] table indexed by the step) or NULL ->
+// in-kernel Philox + Box-Muller.  step_ptr / advance as in reverse_step().  steps_out (optional) [T, B*per_graph]: the result
+// is also stored at entry T-1-step (the reference's per-step history).  wrap = false: p_sample's un-wrapped value.
+int gauss_step(const float* coef, int T, int B, int per_graph, const float* x_t, const float* model_out, const float* noise, uint64_t seed,
+               uint64_t graph_id0, int step, const int* step_ptr, float* x_out, float* steps_out, cudaStream_t s, int* advance = nullptr, bool wrap = true);
+
 }  // namespace seqdiff

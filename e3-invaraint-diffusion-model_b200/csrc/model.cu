@@ -171,9 +171,10 @@ static void add_schema(std::map<std::string, RawTensor>& raw, const std::string&
   raw[name] = t;
 }
 
-int Model::init(const seqdiff_config_t& c, int dev) {
+int Model::init(const seqdiff_config_t& c, int dev, int arch_) {
   cfg = c;
   device = dev;
+  arch = arch_;
   SD_CHECK(c.hidden_size % 256 == 0 && c.hidden_size >= 256 && c.hidden_size <= 1024, "hidden_size must be 256/512/768/1024");
   SD_CHECK(c.num_attention_heads * 64 == c.hidden_size, "head_dim must be 64");
   SD_CHECK(c.intermediate_size % 128 == 0, "intermediate_size must be a multiple of 128");
@@ -183,14 +184,16 @@ int Model::init(const seqdiff_config_t& c, int dev) {
   const int64_t H = c.hidden_size, I = c.intermediate_size, P = c.max_position_embeddings;
   // state_dict schema of ConditionalBertForDiffusionBase
   add_schema(raw, "timestep_projector.W", H / 2);
-  for (const char* side : {"ligand", "receptor"})
-    for (auto kv : {std::pair<const char*, int>{"seq", 20}, std::pair<const char*, int>{"angle", 8}}) {
-      const std::string p = std::string(side) + "_" + kv.first + "_embedding";
-      add_schema(raw, p + ".linear.weight", H * kv.second);
-      add_schema(raw, p + ".linear.bias", H);
-      add_schema(raw, p + ".LayerNorm.weight", H);
-      add_schema(raw, p + ".LayerNorm.bias", H);
-    }
+  auto emb_schema = [&](const std::string& p, int fin) {
+    add_schema(raw, p + ".linear.weight", H * fin);
+    add_schema(raw, p + ".linear.bias", H);
+    add_schema(raw, p + ".LayerNorm.weight", H);
+    add_schema(raw, p + ".LayerNorm.bias", H);
+  };
+  if (arch == kArchSequence)
+    for (const char* side : {"ligand", "receptor"})
+      for (auto kv : {std::pair<const char*, int>{"seq", 20}, std::pair<const char*, int>{"angle", 8}})
+        emb_schema(std::string(side) + "_" + kv.first + "_embedding", kv.second);
   auto attn = [&](const std::string& p, bool rel) {
     for (const char* n : {"query", "key", "value"}) {
       add_schema(raw, p + ".self." + n + ".weight", H * H);
@@ -202,7 +205,18 @@ int Model::init(const seqdiff_config_t& c, int dev) {
     add_schema(raw, p + ".output.LayerNorm.weight", H);
     add_schema(raw, p + ".output.LayerNorm.bias", H);
   };
-  for (const char* blk : {"ligand_feature_emb", "receptor_feature_emb", "decoder_normalize"}) {
+  auto ffn_schema = [&](const std::string& p) {
+    add_schema(raw, p + ".intermediate.dense.weight", I * H);
+    add_schema(raw, p + ".intermediate.dense.bias", I);
+    add_schema(raw, p + ".output.dense.weight", H * I);
+    add_schema(raw, p + ".output.dense.bias", H);
+    add_schema(raw, p + ".output.LayerNorm.weight", H);
+    add_schema(raw, p + ".output.LayerNorm.bias", H);
+  };
+  const std::vector<const char*> se_blocks = arch == kArchSequence
+                                                 ? std::vector<const char*>{"ligand_feature_emb", "receptor_feature_emb", "decoder_normalize"}
+                                                 : std::vector<const char*>{"receptor_emb", "timestep_emb"};
+  for (const char* blk : se_blocks) {
     const std::string p = blk;
     add_schema(raw, p + ".adaLN_modulation.0.weight", H * H);
     add_schema(raw, p + ".adaLN_modulation.0.bias", H);
@@ -218,19 +232,25 @@ int Model::init(const seqdiff_config_t& c, int dev) {
     const std::string p = "decoder.layer." + std::to_string(i);
     attn(p + ".attention", true);
     attn(p + ".crossattention", false);
-    add_schema(raw, p + ".intermediate.dense.weight", I * H);
-    add_schema(raw, p + ".intermediate.dense.bias", I);
-    add_schema(raw, p + ".output.dense.weight", H * I);
-    add_schema(raw, p + ".output.dense.bias", H);
-    add_schema(raw, p + ".output.LayerNorm.weight", H);
-    add_schema(raw, p + ".output.LayerNorm.bias", H);
+    ffn_schema(p);
   }
-  add_schema(raw, "amino_acid_predictor.dense1.weight", H * H);
-  add_schema(raw, "amino_acid_predictor.dense1.bias", H);
-  add_schema(raw, "amino_acid_predictor.layer_norm.weight", H);
-  add_schema(raw, "amino_acid_predictor.layer_norm.bias", H);
-  add_schema(raw, "amino_acid_predictor.dense2.weight", static_cast<int64_t>(c.feature_size) * H);
-  add_schema(raw, "amino_acid_predictor.dense2.bias", c.feature_size);
+  if (arch == kArchStructure) {  // structure_model/model.py:163-178
+    emb_schema("receptor_seq_emb", 20);
+    emb_schema("receptor_angle_emb", c.feature_size);
+    emb_schema("ligand_angle_emb", c.feature_size);
+    for (int i = 0; i < c.num_hidden_layers; ++i) {
+      const std::string p = "encoder.layer." + std::to_string(i);
+      attn(p + ".attention", true);
+      ffn_schema(p);
+    }
+  }
+  const std::string head = arch == kArchSequence ? "amino_acid_predictor" : "angles_predictor";
+  add_schema(raw, head + ".dense1.weight", H * H);
+  add_schema(raw, head + ".dense1.bias", H);
+  add_schema(raw, head + ".layer_norm.weight", H);
+  add_schema(raw, head + ".layer_norm.bias", H);
+  add_schema(raw, head + ".dense2.weight", static_cast<int64_t>(c.feature_size) * H);
+  add_schema(raw, head + ".dense2.bias", c.feature_size);
   d_step = static_cast<int*>(dalloc(256));  // [0] step counter of the sampling loop, [1] arrival counter of its reverse step
   SD_CHECK(d_step != nullptr, "cudaMalloc failed");
   SD_CUDA(cudaMemset(d_step, 0, 256));
@@ -249,7 +269,7 @@ int Model::set_tensor(const char* name, const float* data, int64_t numel, cudaSt
     return SEQDIFF_ERR_INVALID;
   }
   // receptor_feature_emb is dead weight in the reference (quirk Q1): accepted, never stored.
-  if (std::strncmp(name, "receptor_feature_emb.", 21) == 0) {
+  if (arch == kArchSequence && std::strncmp(name, "receptor_feature_emb.", 21) == 0) {
     t.set = true;
     return SEQDIFF_OK;
   }
@@ -342,12 +362,36 @@ int Model::finalize(cudaStream_t s) {
     return w;
   };
   ts_W = R("timestep_projector.W");
-  lig_seq = emb("ligand_seq_embedding", 20);
-  lig_ang = emb("ligand_angle_embedding", 8);
-  rec_seq = emb("receptor_seq_embedding", 20);
-  rec_ang = emb("receptor_angle_embedding", 8);
-  se_lig = se("ligand_feature_emb");
-  se_dec = se("decoder_normalize");
+  auto ffn = [&](const std::string& p, LayerW& l) {
+    l.inter = both(R(p + ".intermediate.dense.weight"), I * H);
+    l.inter_b = R(p + ".intermediate.dense.bias");
+    l.outd = both(R(p + ".output.dense.weight"), H * I);
+    l.outd_b = R(p + ".output.dense.bias");
+    l.oln_w = R(p + ".output.LayerNorm.weight");
+    l.oln_b = R(p + ".output.LayerNorm.bias");
+  };
+  enc_layers.clear();
+  if (arch == kArchSequence) {
+    lig_seq = emb("ligand_seq_embedding", 20);
+    lig_ang = emb("ligand_angle_embedding", 8);
+    rec_seq = emb("receptor_seq_embedding", 20);
+    rec_ang = emb("receptor_angle_embedding", 8);
+    se_lig = se("ligand_feature_emb");
+    se_dec = se("decoder_normalize");
+  } else {  // structure model: se_lig = receptor_emb (x = angles, c = sequence), se_dec = timestep_emb
+    rec_seq = emb("receptor_seq_emb", 20);
+    rec_ang = emb("receptor_angle_emb", cfg.feature_size);
+    lig_ang = emb("ligand_angle_emb", cfg.feature_size);
+    se_lig = se("receptor_emb");
+    se_dec = se("timestep_emb");
+    for (int i = 0; i < cfg.num_hidden_layers; ++i) {
+      const std::string p = "encoder.layer." + std::to_string(i);
+      LayerW l;
+      l.self = attn(p + ".attention", true);
+      ffn(p, l);
+      enc_layers.push_back(l);
+    }
+  }
   layers.clear();
   std::vector<const float*> ckv_w, ckv_b;
   for (int i = 0; i < cfg.num_hidden_layers; ++i) {
@@ -364,22 +408,18 @@ int Model::finalize(cudaStream_t s) {
     l.cout_b = R(p + ".crossattention.output.dense.bias");
     l.cln_w = R(p + ".crossattention.output.LayerNorm.weight");
     l.cln_b = R(p + ".crossattention.output.LayerNorm.bias");
-    l.inter = both(R(p + ".intermediate.dense.weight"), I * H);
-    l.inter_b = R(p + ".intermediate.dense.bias");
-    l.outd = both(R(p + ".output.dense.weight"), H * I);
-    l.outd_b = R(p + ".output.dense.bias");
-    l.oln_w = R(p + ".output.LayerNorm.weight");
-    l.oln_b = R(p + ".output.LayerNorm.bias");
+    ffn(p, l);
     layers.push_back(l);
   }
   ckv_all = both(stack(ckv_w, H * H), static_cast<int64_t>(ckv_w.size()) * H * H);
   ckv_all_b = stack(ckv_b, H);
-  p1 = both(R("amino_acid_predictor.dense1.weight"), H * H);
-  p1_b = R("amino_acid_predictor.dense1.bias");
-  p_ln_w = R("amino_acid_predictor.layer_norm.weight");
-  p_ln_b = R("amino_acid_predictor.layer_norm.bias");
-  p2_w = R("amino_acid_predictor.dense2.weight");
-  p2_b = R("amino_acid_predictor.dense2.bias");
+  const std::string head = arch == kArchSequence ? "amino_acid_predictor" : "angles_predictor";
+  p1 = both(R(head + ".dense1.weight"), H * H);
+  p1_b = R(head + ".dense1.bias");
+  p_ln_w = R(head + ".layer_norm.weight");
+  p_ln_b = R(head + ".layer_norm.bias");
+  p2_w = R(head + ".dense2.weight");
+  p2_b = R(head + ".dense2.bias");
   packing = false;
   if (rc != SEQDIFF_OK) {
     set_error("finalize: allocation or packing kernel failed");
@@ -645,6 +685,7 @@ int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, 
                    const float* lig_angle, const float* lig_mask, const float* rec_seq_in, const float* rec_angle,
                    const float* rec_mask, float* logits, cudaStream_t s) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
+  SD_CHECK(arch == kArchSequence, "handle holds a structure model: use seqdiff_struct_forward");
   SD_CHECK(precision >= SEQDIFF_FP32 && precision <= SEQDIFF_FP16, "unknown precision mode");
   SD_CHECK(B > 0 && Ll > 0 && Lr > 0, "empty batch");
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
@@ -745,6 +786,237 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
   g_launches.fetch_add(static_cast<uint64_t>(T) * graph_kernels, std::memory_order_relaxed);  // replayed kernel nodes
   SD_CUDA(cudaMemcpyAsync(final_out, logits, Nl * 20 * 4, cudaMemcpyDefault, s));
   // ... and the caller's stream continues only after the loop has finished
+  SD_CUDA(cudaEventRecord(ev_out, s));
+  SD_CUDA(cudaStreamWaitEvent(caller, ev_out, 0));
+  return SEQDIFF_OK;
+}
+
+// =====================================================================================================
+// structure (angle) model: structure_model/model.py:155-215 on the same kernels
+// =====================================================================================================
+// HF BertLayer, post-LN, fp32 residual stream: self-attention [-> cross-attention] -> FFN.  `o` is the fp32 pre-LN scratch,
+// h1 / h2 the two rotating residual-stream tensors (h may be h1's buffer: it is dead once the self-output GEMM has folded it
+// in).  Returns the buffer holding the layer output.
+template <typename T>
+static int bert_layer_plain(const Model& m, int wfmt, const LayerW& w, bool cross, int B, int Lq, int Lk, const Act<T>& h, const float* q_mask,
+                            const float* k_mask, const T* kbase, int ldkv, T* qkv, T* ctx, T* cq, T* ffn, float* o, const Act<T>& h1,
+                            const Act<T>& h2, Act<T>* out, cudaStream_t s) {
+  const int H = m.cfg.hidden_size, I = m.cfg.intermediate_size, heads = m.cfg.num_attention_heads, P = m.cfg.max_position_embeddings;
+  const float eps = m.cfg.layer_norm_eps;
+  const int M = B * Lq;
+  SD_TRY(gemm_T(wfmt, M, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, 0, qkv, s));
+  SD_TRY(attention<T>(B, heads, Lq, Lq, qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, q_mask, ctx, s));
+  SD_TRY(gemm_S(wfmt, M, H, H, ctx, w.self.out, w.self.out_b, h.s, o, s));
+  SD_TRY(layernorm<T>(o, M, H, w.self.ln_w, w.self.ln_b, eps, h1.s, h1.t_out(), nullptr, s));
+  Act<T> cur = h1, nxt = h2;
+  if (cross) {
+    SD_TRY(gemm_T(wfmt, M, H, H, h1.t, w.cq, w.cq_b, 0, cq, s));
+    SD_TRY(attention<T>(B, heads, Lq, Lk, cq, H, kbase, ldkv, kbase + H, ldkv, static_cast<const T*>(nullptr), P, k_mask, ctx, s));
+    SD_TRY(gemm_S(wfmt, M, H, H, ctx, w.cout, w.cout_b, h1.s, o, s));
+    SD_TRY(layernorm<T>(o, M, H, w.cln_w, w.cln_b, eps, h2.s, h2.t_out(), nullptr, s));
+    cur = h2;
+    nxt = h1;
+  }
+  SD_TRY(gemm_T(wfmt, M, I, H, cur.t, w.inter, w.inter_b, 1, ffn, s));
+  SD_TRY(gemm_S(wfmt, M, H, I, ffn, w.outd, w.outd_b, cur.s, o, s));
+  SD_TRY(layernorm<T>(o, M, H, w.oln_w, w.oln_b, eps, nxt.s, nxt.t_out(), nullptr, s));
+  *out = nxt;
+  return SEQDIFF_OK;
+}
+
+size_t Model::struct_workspace_need(int precision, int B, int Ll, int Lr) const {
+  const size_t es = precision == SEQDIFF_FP32 ? 4 : 2;
+  const size_t H = cfg.hidden_size, I = cfg.intermediate_size, NL = cfg.num_hidden_layers;
+  const size_t Mr = static_cast<size_t>(B) * Lr, Mx = static_cast<size_t>(B) * (Ll > Lr ? Ll : Lr);
+  size_t n = align256(Mr * NL * 2 * H * es);           // cross K|V of every decoder layer: survives between forwards
+  n += 2 * align256(static_cast<size_t>(B) * H * 4);   // te fp32 + operand copy
+  n += 5 * (align256(Mx * H * 4) + align256(Mx * H * 2));  // x, x2, x1, h ping-pong (stream + operand)
+  n += 2 * align256(Mx * H * 4);                       // o, m2
+  n += 5 * align256(Mx * H * es);                      // c, u, ctx, cq, y
+  n += align256(Mx * 6 * H * es) + align256(Mx * 3 * H * es) + align256(Mx * 4 * H * es);  // mod, qkv, m1
+  n += align256(Mx * I * es);                          // ffn
+  return n + 8192;
+}
+
+template <typename T>
+int Model::struct_forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* noised,
+                            const float* lig_mask, const float* rec_seq_in, const float* rec_angle, const float* rec_mask, float* out,
+                            int phases, cudaStream_t s) {
+  constexpr bool k16 = !std::is_same<T, float>::value;
+  const int H = cfg.hidden_size, I = cfg.intermediate_size, NL = cfg.num_hidden_layers;
+  const float eps = cfg.layer_norm_eps;
+  const int Ml = B * Ll, Mr = B * Lr, Mx = Ml > Mr ? Ml : Mr;
+  const size_t MxH = static_cast<size_t>(Mx) * H;
+  Bump bp{ws};
+  T* kv_all = bp.take<T>(static_cast<size_t>(Mr) * NL * 2 * H);  // first: same address for every (B, Ll, Lr) of a loop
+  float* te = bp.take<float>(static_cast<size_t>(B) * H);
+  T* teT = k16 ? bp.take<T>(static_cast<size_t>(B) * H) : reinterpret_cast<T*>(te);
+  Act<T> x = take_act<T>(bp, MxH);
+  Act<T> x2 = take_act<T>(bp, MxH);
+  SEBufs<T> sb;
+  sb.x1 = take_act<T>(bp, MxH);
+  Act<T> hb[2] = {take_act<T>(bp, MxH), take_act<T>(bp, MxH)};
+  sb.o = bp.take<float>(MxH);
+  sb.m2 = bp.take<float>(MxH);
+  T* cT = bp.take<T>(MxH);
+  sb.u = bp.take<T>(MxH);
+  sb.ctx = bp.take<T>(MxH);
+  T* cq = bp.take<T>(MxH);
+  T* y = bp.take<T>(MxH);
+  sb.mod = bp.take<T>(MxH * 6);
+  sb.qkv = bp.take<T>(MxH * 3);
+  sb.m1 = bp.take<T>(MxH * 4);
+  T* ffn = bp.take<T>(static_cast<size_t>(Mx) * I);
+  auto job = [&](const float* in, int M, const EmbW& e, int L, float* o32, T* oT) {
+    EmbedJob jb{};
+    jb.x = in; jb.Wt = e.Wt_; jb.b = e.b; jb.lnw = e.ln_w; jb.lnb = e.ln_b; jb.te = nullptr;
+    jb.out32 = o32; jb.outT = oT; jb.M = M; jb.fin = e.fin; jb.L = L;
+    return jb;
+  };
+
+  if (phases & 1) {
+    // receptor branch (model.py:192-202): x = LN(Linear(angles)), c = LN(Linear(seq)); receptor_emb; 12 x (self-attn, FFN)
+    EmbedJobs jobs{};
+    jobs.n = 2;
+    jobs.j[0] = job(rec_angle, Mr, rec_ang, Lr, x.s, x.t_out());
+    jobs.j[1] = job(rec_seq_in, Mr, rec_seq, Lr, k16 ? nullptr : reinterpret_cast<float*>(cT), k16 ? cT : nullptr);
+    SD_TRY(embed_ln_multi<T>(jobs, eps, H, s));
+    std::vector<Segment> rseg{{0, B, Lr, rec_mask}};
+    SD_TRY(se_layer<T>(*this, wfmt, se_lig, x, cT, Mr, 1, Mr, rseg, sb, x2, s));
+    Act<T> h = x2;
+    for (int i = 0; i < NL; ++i) {
+      Act<T> nh;
+      SD_TRY(bert_layer_plain<T>(*this, wfmt, enc_layers[i], false, B, Lr, Lr, h, rec_mask, nullptr, nullptr, 0, sb.qkv, sb.ctx, cq, ffn, sb.o,
+                                 hb[0], hb[1], &nh, s));
+      h = nh;
+    }
+    // every decoder layer's cross K|V in one GEMM: the only thing the decoder reads from the receptor side
+    SD_TRY(gemm_T(wfmt, Mr, NL * 2 * H, H, h.t, ckv_all, ckv_all_b, 0, kv_all, s));
+  }
+
+  if (!(phases & 2)) return SEQDIFF_OK;
+  // ligand branch (model.py:203-215)
+  SD_TRY(timestep_embed(timestep, step_ptr, ts_W, B, H, te, k16 ? static_cast<void*>(teT) : nullptr, Fmt<T>::v, s));
+  {
+    EmbedJobs jobs{};
+    jobs.n = 1;
+    jobs.j[0] = job(noised, Ml, lig_ang, Ll, x.s, x.t_out());
+    SD_TRY(embed_ln_multi<T>(jobs, eps, H, s));
+  }
+  std::vector<Segment> lseg{{0, B, Ll, lig_mask}};
+  SD_TRY(se_layer<T>(*this, wfmt, se_dec, x, teT, B, Ll, Ml, lseg, sb, x2, s));  // timestep_emb: c broadcast over L
+  Act<T> h = x2;
+  for (int i = 0; i < NL; ++i) {
+    Act<T> nh;
+    const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
+    SD_TRY(bert_layer_plain<T>(*this, wfmt, layers[i], true, B, Ll, Lr, h, lig_mask, rec_mask, kbase, NL * 2 * H, sb.qkv, sb.ctx, cq, ffn, sb.o,
+                               hb[0], hb[1], &nh, s));
+    h = nh;
+  }
+  SD_TRY(gemm_T(wfmt, Ml, H, H, h.t, p1, p1_b, 1, y, s));
+  SD_TRY(predictor_tail<T>(y, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, out, s));
+  return SEQDIFF_OK;
+}
+
+int Model::struct_forward(int precision, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* noised,
+                          const float* lig_mask, const float* rec_seq_in, const float* rec_angle, const float* rec_mask, float* out,
+                          int phases, cudaStream_t s) {
+  SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
+  SD_CHECK(arch == kArchStructure, "handle holds a sequence model: use seqdiff_forward");
+  SD_CHECK(precision >= SEQDIFF_FP32 && precision <= SEQDIFF_FP16, "unknown precision mode");
+  SD_CHECK(B > 0 && Ll > 0 && Lr > 0, "empty batch");
+  if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
+  SD_CUDA(cudaSetDevice(device));
+  SD_TRY(ensure_workspace(struct_workspace_need(precision, B, Ll, Lr)));
+  switch (precision) {
+    case SEQDIFF_FP32:
+      return struct_forward_t<float>(1, B, Ll, Lr, timestep, step_ptr, noised, lig_mask, rec_seq_in, rec_angle, rec_mask, out, phases, s);
+    case SEQDIFF_BF16:
+      return struct_forward_t<bf16>(1, B, Ll, Lr, timestep, step_ptr, noised, lig_mask, rec_seq_in, rec_angle, rec_mask, out, phases, s);
+    default:
+      return struct_forward_t<f16>(0, B, Ll, Lr, timestep, step_ptr, noised, lig_mask, rec_seq_in, rec_angle, rec_mask, out, phases, s);
+  }
+}
+
+// structure_model/sample.py:104-144.  The receptor branch runs ONCE (it sees neither t nor the ligand; the reference recomputes
+// it every step); each step replays one captured graph: ligand branch + Gaussian reverse step + wrap.
+int Model::struct_sample(int precision, int B, int Ll, int Lr, int T, const float* coef_steps, const float* x_T, const float* lig_mask,
+                         const float* rec_seq_in, const float* rec_angle, const float* rec_mask, const float* noise_steps, uint64_t seed,
+                         uint64_t gid0, float* steps_out, float* final_out, cudaStream_t caller) {
+  SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
+  SD_CHECK(arch == kArchStructure, "handle holds a sequence model: use seqdiff_sample");
+  SD_CHECK(T >= 1 && B > 0 && Ll > 0 && Lr > 0, "bad sampling arguments");
+  SD_CUDA(cudaSetDevice(device));
+  if (!loop_stream) {
+    SD_CUDA(cudaStreamCreateWithFlags(&loop_stream, cudaStreamNonBlocking));
+    SD_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    SD_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+  }
+  cudaStream_t s = loop_stream;
+  SD_CUDA(cudaEventRecord(ev_in, caller));
+  SD_CUDA(cudaStreamWaitEvent(s, ev_in, 0));
+  const int F = cfg.feature_size;
+  const size_t Nl = static_cast<size_t>(B) * Ll, Nr = static_cast<size_t>(B) * Lr;
+  // persistent inputs: x_cur | model_out | lig_mask | rec_seq | rec_angle | rec_mask
+  const size_t need_in = align256(Nl * F * 4) * 2 + align256(Nl * 4) + align256(Nr * 20 * 4) + align256(Nr * F * 4) + align256(Nr * 4);
+  if (need_in > samp_in_bytes) {
+    if (samp_in) { SD_CUDA(cudaDeviceSynchronize()); SD_CUDA(cudaFree(samp_in)); samp_in = nullptr; samp_in_bytes = 0; }
+    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&samp_in), need_in));
+    samp_in_bytes = need_in;
+  }
+  const size_t tab_floats = static_cast<size_t>(T) * 4;
+  if (tab_floats > tables_cap) {
+    if (d_tables) { SD_CUDA(cudaDeviceSynchronize()); SD_CUDA(cudaFree(d_tables)); d_tables = nullptr; tables_cap = 0; }
+    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_tables), tab_floats * 4));
+    tables_cap = tab_floats;
+  }
+  SD_TRY(ensure_workspace(struct_workspace_need(precision, B, Ll, Lr)));
+  Bump bp{samp_in};
+  float* x_cur = bp.take<float>(Nl * F);
+  float* mout = bp.take<float>(Nl * F);
+  float* c_lmask = bp.take<float>(Nl);
+  float* c_rseq = bp.take<float>(Nr * 20);
+  float* c_rang = bp.take<float>(Nr * F);
+  float* c_rmask = bp.take<float>(Nr);
+  SD_CUDA(cudaMemcpyAsync(d_tables, coef_steps, tab_floats * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(x_cur, x_T, Nl * F * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_lmask, lig_mask, Nl * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_rseq, rec_seq_in, Nr * 20 * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_rang, rec_angle, Nr * F * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(c_rmask, rec_mask, Nr * 4, cudaMemcpyDefault, s));
+
+  GraphKey key;
+  key.precision = precision; key.B = B; key.Ll = Ll; key.Lr = Lr; key.diverse = 0; key.noise = noise_steps;
+  key.seed = seed; key.gid0 = gid0; key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables; key.aux_ptr = steps_out; key.T = T;
+  // receptor branch once, eagerly (also the un-captured dry run that sets kernel attributes and fills the TMA descriptor cache)
+  SD_CUDA(launch_k(set_int_kernel, dim3(1), dim3(1), 0, s, d_step, T - 1));
+  SD_LAUNCHED("set_int", s);
+  const bool cached = graph_exec && key == graph_key;
+  SD_TRY(struct_forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lmask, c_rseq, c_rang, c_rmask, mout, cached ? 1 : 3, s));
+  auto one_step = [&](cudaStream_t st) -> int {
+    SD_TRY(struct_forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lmask, c_rseq, c_rang, c_rmask, mout, 2, st));
+    SD_TRY(gauss_step(d_tables, T, B, Ll * F, x_cur, mout, noise_steps, seed, gid0, 0, d_step, x_cur, steps_out, st, d_step + 1));
+    return SEQDIFF_OK;
+  };
+  if (!cached) {
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    SD_CUDA(cudaStreamSynchronize(s));
+    cudaGraph_t graph = nullptr;
+    const uint64_t l0 = g_launches.load();
+    SD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = one_step(s);
+    graph_kernels = static_cast<int>(g_launches.load() - l0);
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc != SEQDIFF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    SD_CUDA(ce);
+    ce = cudaGraphInstantiate(&graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    SD_CUDA(ce);
+    graph_key = key;
+  }
+  for (int it = 0; it < T; ++it) SD_CUDA(cudaGraphLaunch(graph_exec, s));
+  g_launches.fetch_add(static_cast<uint64_t>(T) * graph_kernels, std::memory_order_relaxed);
+  SD_CUDA(cudaMemcpyAsync(final_out, x_cur, Nl * F * 4, cudaMemcpyDefault, s));
   SD_CUDA(cudaEventRecord(ev_out, s));
   SD_CUDA(cudaStreamWaitEvent(caller, ev_out, 0));
   return SEQDIFF_OK;

@@ -27,7 +27,7 @@ struct SEW {  // SELayer, model.py:26-66
   const float *ada0_b = nullptr, *ada2_b = nullptr, *m0_b = nullptr, *m3_b = nullptr;
   AttnW attn;
 };
-struct LayerW {  // HF BertLayer with cross-attention
+struct LayerW {  // HF BertLayer; the cross-attention members stay empty for an encoder layer (structure model)
   AttnW self;
   Wt cq, cout, inter, outd;
   const float *cq_b = nullptr, *cout_b = nullptr, *cln_w = nullptr, *cln_b = nullptr;
@@ -52,8 +52,11 @@ struct Segment {  // a run of graphs sharing one padded length inside a token ma
 int profile_begin(cudaStream_t s);
 int profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap);
 
+enum Arch { kArchSequence = 0, kArchStructure = 1 };
+
 struct Model {
   seqdiff_config_t cfg{};
+  int arch = kArchSequence;  // which reference module tree the handle holds (sequence_model/model.py | structure_model/model.py)
   int device = 0;
   bool finalized = false;
   std::map<std::string, RawTensor> raw;  // reference state_dict key -> fp32 device tensor
@@ -63,7 +66,8 @@ struct Model {
 
   EmbW lig_seq, lig_ang, rec_seq, rec_ang;
   SEW se_lig, se_dec;
-  std::vector<LayerW> layers;
+  std::vector<LayerW> layers;      // decoder
+  std::vector<LayerW> enc_layers;  // structure model only: the 12-layer receptor encoder (self-attention + FFN)
   Wt ckv_all;  // all layers' cross key|value weights stacked: [layers*2H, H]
   const float* ckv_all_b = nullptr;
   Wt p1;
@@ -90,14 +94,16 @@ struct Model {
     const void* ws_ptr = nullptr;
     const void* in_ptr = nullptr;
     const void* tab_ptr = nullptr;
+    const void* aux_ptr = nullptr;
+    int T = 0;
     bool operator==(const GraphKey& o) const {
-      return precision == o.precision && B == o.B && Ll == o.Ll && Lr == o.Lr && diverse == o.diverse && noise == o.noise &&
+      return aux_ptr == o.aux_ptr && T == o.T && precision == o.precision && B == o.B && Ll == o.Ll && Lr == o.Lr && diverse == o.diverse && noise == o.noise &&
              seed == o.seed && gid0 == o.gid0 && ws_ptr == o.ws_ptr && in_ptr == o.in_ptr && tab_ptr == o.tab_ptr;
     }
   } graph_key;
 
   ~Model();
-  int init(const seqdiff_config_t& c, int dev);
+  int init(const seqdiff_config_t& c, int dev, int arch_ = kArchSequence);
   int set_tensor(const char* name, const float* data, int64_t numel, cudaStream_t s);
   int finalize(cudaStream_t s);
   int forward(int precision, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t,
@@ -107,8 +113,24 @@ struct Model {
              const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, int diverse,
              const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t s);
 
+  // structure_model/model.py:180-215.  phases: bit 0 = run the receptor branch, bit 1 = the ligand branch.  The receptor branch (embeddings,
+  // receptor_emb, encoder, all decoder layers' cross K|V) depends on neither the timestep nor the ligand, so the sampling loop runs it
+  // once and keeps the K|V block.
+  int struct_forward(int precision, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* noised_angles,
+                     const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, float* out, int phases,
+                     cudaStream_t s);
+  // structure_model/sample.py:104-144 (STEP = 1): T x (forward, Gaussian reverse step, angle wrap) from one captured graph
+  int struct_sample(int precision, int B, int Ll, int Lr, int T, const float* coef_steps, const float* x_T, const float* lig_mask,
+                    const float* rec_seq, const float* rec_angle, const float* rec_mask, const float* noise_steps, uint64_t seed,
+                    uint64_t gid0, float* steps_out, float* final_out, cudaStream_t s);
+
  private:
   void* dalloc(size_t bytes);
+  size_t struct_workspace_need(int precision, int B, int Ll, int Lr) const;
+  template <typename T>
+  int struct_forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* noised_angles,
+                       const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, float* out, int phases,
+                       cudaStream_t s);
   size_t workspace_need(int precision, int B, int Ll, int Lr) const;
   int ensure_workspace(size_t bytes);
   template <typename T>

@@ -150,6 +150,9 @@ class ConditionalBertForDiffusionBase(nn.Module):
       "fp16"       fp16 activations x fp16 weights, same kernels and speed, 8x finer operand rounding
       "fp32"       fp32 SIMT kernels -- the 1e-5 parity mode."""
 
+    _create_symbol = "seqdiff_model_create"  # C entry point that builds the handle for this module tree
+    _host_only_prefixes = ("discrete_noise_schedule.", "aa_transition_model.")
+
     def __init__(self, encoder_config, decoder_config, feature_size: int) -> None:
         super().__init__()
         self.encoder_config = encoder_config
@@ -203,7 +206,9 @@ class ConditionalBertForDiffusionBase(nn.Module):
     def _sync_handle(self):
         """(Re)uploads the weights into the C handle when any tensor of the state_dict changed."""
         lib = _cabi.lib()
-        sd = self.state_dict()
+        # the denoiser's own tensors only: PeptideDiff also registers the noise schedule's `betas` buffer (reference
+        # utils.py:216), which is host-side table data, not a weight of the forward
+        sd = {k: v for k, v in self.state_dict().items() if not k.startswith(self._host_only_prefixes)}
         dev = next(iter(sd.values())).device
         if dev.type != "cuda":
             raise RuntimeError("the sequence denoiser runs only on a CUDA device (no CPU fallback): call model.to('cuda')")
@@ -216,7 +221,7 @@ class ConditionalBertForDiffusionBase(nn.Module):
                 self.release()
                 h = ctypes.c_void_p()
                 cfg = self._config_struct()
-                _cabi.check(lib.seqdiff_model_create(ctypes.byref(cfg), dev.index or 0, ctypes.byref(h)))
+                _cabi.check(getattr(lib, self._create_symbol)(ctypes.byref(cfg), dev.index or 0, ctypes.byref(h)))
                 self._handle, self._handle_dev = h, dev
             keep = []
             for name, t in sd.items():
@@ -284,11 +289,30 @@ class ConditionalBertForDiffusionBase(nn.Module):
         return (1.0 - extended) * -10000.0
 
 
+def loss_terms(logits, x0, x_t, ligand_mask):
+    """The ten fp64 reduction terms of get_loss / elbo_loss (include/seqdiff_b200.h: seqdiff_loss_terms) as a device tensor."""
+    dev = logits.device
+    if dev.type != "cuda":
+        raise RuntimeError("loss_terms runs only on a CUDA device (no CPU fallback)")
+
+    def prep(t, last):
+        return t.to(device=dev, dtype=torch.float32).reshape(-1, last).contiguous() if last else t.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+
+    lg, a, b, m = prep(logits, 20), prep(x0, 20), prep(x_t, 20), prep(ligand_mask, 0)
+    if not (lg.shape[0] == a.shape[0] == b.shape[0] == m.shape[0]):
+        raise ValueError("logits, x0, x_t and ligand_mask must cover the same rows")
+    out = torch.empty(10, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(_cabi.lib().seqdiff_loss_terms(lg.shape[0], _cabi.ptr(lg), _cabi.ptr(a), _cabi.ptr(b), _cabi.ptr(m), _cabi.ptr(out), stream))
+    return out
+
+
 class PeptideDiff(ConditionalBertForDiffusionBase):
     """reference model.py:256-450 without the Lightning base class (Trainer is out of scope, SURVEY.md
     section 2).  Inference-side members match the reference; `apply_aa_noise` runs the CUDA q-sample
-    kernel; `get_loss` evaluates the reference's loss terms on the CUDA forward's logits (no autograd:
-    backward kernels are not part of this round, so `training_step` raises)."""
+    kernel; `get_loss` evaluates the reference's loss terms with the CUDA forward and the CUDA reduction
+    kernel (no autograd: backward kernels are not part of this round, so `training_step` raises)."""
 
     def __init__(self, encoder_config, decoder_config, feature_names: List[str], loss_func, noise_schedule, timesteps,
                  max_epochs: int = 1, lr_scheduler=None, l2_lambda: float = 0.0, steps_per_epoch: int = 250,
@@ -332,19 +356,21 @@ class PeptideDiff(ConditionalBertForDiffusionBase):
 
     @torch.no_grad()
     def get_loss(self, batch, t_norm, noised_ligand_seq):
-        """reference model.py:313-345 (evaluation only)."""
-        ligand_mask = batch["ligand_attn_mask"].bool()
-        noised_mask = noised_ligand_seq.argmax(dim=-1) != batch["ligand_seq"].argmax(dim=-1)
+        """reference model.py:313-345 (evaluation only: no autograd graph).  The forward and ALL reductions run in CUDA
+        (`seqdiff_loss_terms`: masked counts, the two cross-entropy sums, the entropy and KL sums of `elbo_loss`); the host
+        only forms the ratios.  `loss_func` must be the reference's `torch.nn.CrossEntropyLoss()` (train_model.py)."""
+        if not isinstance(self.loss_function, nn.CrossEntropyLoss) or self.loss_function.reduction != "mean" or \
+                self.loss_function.label_smoothing != 0.0 or self.loss_function.weight is not None:
+            raise ValueError("the CUDA loss reduction implements the reference's plain mean CrossEntropyLoss")
         pred_aa = self.forward(t_norm, noised_ligand_seq, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
                                batch["receptor_angles"], batch["receptor_attn_mask"])
-        aa_noise_rate = noised_ligand_seq.argmax(dim=-1)[ligand_mask] == batch["ligand_seq"][ligand_mask].argmax(dim=-1)
-        aa_noise_rate = aa_noise_rate.sum() / ligand_mask.sum()
-        aa_recovery_rate = pred_aa.argmax(dim=-1)[ligand_mask] == batch["ligand_seq"][ligand_mask].argmax(dim=-1)
-        aa_recovery_rate = aa_recovery_rate.sum() / ligand_mask.sum()
-        aa_noised_loss = self.loss_function(pred_aa[noised_mask].view(-1, 20), batch["ligand_seq"][noised_mask].argmax(dim=-1).view(-1))
-        sel = ligand_mask & (~noised_mask)
-        aa_all_loss = self.loss_function(pred_aa[sel].view(-1, 20), batch["ligand_seq"][sel].argmax(dim=-1).view(-1))
-        elbo = elbo_loss(pred_aa[noised_mask], batch["ligand_seq"][noised_mask])
+        terms = loss_terms(pred_aa, batch["ligand_seq"], noised_ligand_seq, batch["ligand_attn_mask"])
+        n_mask, n_noised, n_sel, n_same, n_rec, ce_noised, ce_sel, ent, kl = (terms[i] for i in range(9))
+        aa_noise_rate = (n_same / n_mask).float()
+        aa_recovery_rate = (n_rec / n_mask).float()
+        aa_noised_loss = (ce_noised / n_noised).float()     # CrossEntropyLoss(mean) over the noised rows (nan if there are none)
+        aa_all_loss = (ce_sel / n_sel).float()
+        elbo = (-ent / n_noised + kl / n_noised).float()    # elbo_loss: nll + kl_div(batchmean)
         total_loss = aa_noised_loss + elbo
         return total_loss, elbo, aa_noised_loss, aa_all_loss, aa_recovery_rate, aa_noise_rate
 

@@ -1,7 +1,8 @@
 /*
  * seqdiff_b200.h -- C ABI of libseqdiff_b200.so: the B200 (sm_100a) implementation of ONE hot path of
  * LabJunBMI/E3-invaraint-diffusion-model: the sequence_model denoiser forward and the discrete
- * BLOSUM-transition reverse-diffusion step.
+ * BLOSUM-transition reverse-diffusion step -- plus, widening along SURVEY.md section 8(f), the output decode, the loss
+ * reductions and the structure_model angle denoiser with its Gaussian reverse step on the same kernels.
  *
  * The reference is pure Python/PyTorch and has no FFI layer; the boundary a
  * maintainer binds is therefore "one entry point per reference function on the path".  Each entry
@@ -132,6 +133,59 @@ SEQDIFF_API int seqdiff_sample(seqdiff_model_t* m, int precision, int B, int L_l
                    const float* ligand_mask, const float* receptor_seq, const float* receptor_angle,
                    const float* receptor_mask, int diverse, const float* noise_E_steps, uint64_t seed,
                    uint64_t graph_id0, float* final_out, void* stream);
+
+/* ---- output decode: replaces the per-graph loop of denoise(), sequence_model/sample.py:208-224 --------------------
+ * final_seq [B,L,20] (the loop's result: raw logits of the last step), true_seq [B,L,20] one-hot, ligand_mask [B,L] {0,1}.
+ * pred_idx / true_idx [B,L] u8 = argmax over classes (first maximum, like torch.argmax); counts [B,2] i32 =
+ * (#masked positions where pred == true, #masked positions): recovery_rate = counts[b][0] / counts[b][1] (sample.py:214-216).
+ * The host only joins AA_VOCAB letters over the masked prefix. */
+SEQDIFF_API int seqdiff_decode(int B, int L, const float* final_seq, const float* true_seq, const float* ligand_mask, uint8_t* pred_idx,
+                   uint8_t* true_idx, int32_t* counts, void* stream);
+
+/* ---- loss terms (evaluation): replaces the reductions of PeptideDiff.get_loss, sequence_model/model.py:313-345, and
+ * elbo_loss, sequence_model/utils.py:132-161, over N = B*L rows.  logits [N,20]; x0, x_t [N,20] one-hot; ligand_mask [N].
+ * noised(n) = argmax(x_t[n]) != argmax(x0[n]); sel(n) = mask(n) && !noised(n).  terms [10] f64 (device):
+ *   [0] #mask  [1] #noised  [2] #sel  [3] #(mask && argmax x_t == argmax x0)  [4] #(mask && argmax logits == argmax x0)
+ *   [5] sum_{noised} CE(logits, x0)   [6] sum_{sel} CE(logits, x0)
+ *   [7] sum_{noised} sum_c softmax(logits)_c * log_softmax(logits + 1e-6)_c          (nll = -[7] / [1])
+ *   [8] sum_{noised} sum_c q_c * (log q_c - log_softmax(logits + 1e-6)_c), q = softmax(x0)   (kl_div batchmean = [8] / [1])
+ *   [9] reserved (0).
+ * total_loss = [5]/[1] + (-[7]/[1] + [8]/[1]).  Backward is not part of this library. */
+SEQDIFF_API int seqdiff_loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* ligand_mask, double* terms,
+                       void* stream);
+
+/* ==== structure (angle) model: SURVEY.md section 8(f) row 3 ===========================================================
+ * Same handle type and the same set_tensor / finalize / destroy calls; tensor names are the state_dict keys of
+ * structure_model/model.py:163-178 ("receptor_seq_emb.linear.weight", "encoder.layer.0.attention.self.query.weight",
+ * "timestep_emb.adaLN_modulation.2.weight", "angles_predictor.dense2.bias", ...).  cfg.feature_size = number of angle
+ * features (8); encoder and decoder share every other BertConfig field (structure_model/sample.py:151-173). */
+SEQDIFF_API int seqdiff_struct_model_create(const seqdiff_config_t* cfg, int device, seqdiff_model_t** out);
+
+/* replaces ConditionalBertForDiffusionBase.forward, structure_model/model.py:180-215.
+ * timestep [B] f32 (the reference passes int64 step indices; the product t * W is formed in fp32 either way);
+ * noised_ligand_angles [B,L_lig,F]; ligand_mask [B,L_lig]; receptor_seq [B,L_rec,20]; receptor_angles [B,L_rec,F];
+ * receptor_mask [B,L_rec]; out [B,L_lig,F] f32 (predicted noise). */
+SEQDIFF_API int seqdiff_struct_forward(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, const float* timestep,
+                           const float* noised_ligand_angles, const float* ligand_mask, const float* receptor_seq,
+                           const float* receptor_angles, const float* receptor_mask, float* out, void* stream);
+
+/* replaces the arithmetic of p_sample after the model call (structure_model/sample.py:92-101) plus, when wrap != 0, the angle
+ * wrap of p_sample_loop (sample.py:139-141; utils.py:20-40).  coef_steps [T,4] f32 = per step index
+ * (1/sqrt(alpha_t), beta_t, sqrt(1 - alphabar_t), sqrt(posterior_variance_t)), built by the host from compute_alphas(betas).
+ * noise [B*L*F] N(0,1) (what torch.randn_like drew) or NULL -> Philox4x32-10 + Box-Muller keyed by
+ * (seed, graph_id0 + b, element group, step); ignored at step 0.  x_out may alias x_t. */
+SEQDIFF_API int seqdiff_struct_p_sample(const float* coef_steps, int T, int step, int B, int L, int F, const float* x_t,
+                            const float* model_output, const float* noise, uint64_t seed, uint64_t graph_id0, int wrap,
+                            float* x_out, void* stream);
+
+/* replaces p_sample_loop, structure_model/sample.py:104-144 (STEP = 1): steps T-1 .. 0, each = forward + p_sample + wrap.
+ * The receptor branch does not depend on the step and is evaluated once.  noise_steps [T, B*L_lig*F] (entry i used at step
+ * index i; entry 0 unused) or NULL -> Philox.  steps_out [T, B*L_lig*F] or NULL: entry k = angles after the k-th reverse step
+ * (the tensor the reference returns); final_out [B,L_lig,F] = its last entry. */
+SEQDIFF_API int seqdiff_struct_sample(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, int T, const float* coef_steps,
+                          const float* x_T, const float* ligand_mask, const float* receptor_seq, const float* receptor_angles,
+                          const float* receptor_mask, const float* noise_steps, uint64_t seed, uint64_t graph_id0,
+                          float* steps_out, float* final_out, void* stream);
 
 /* ---- operator-level entry points (used by the parity tests and the micro benchmarks) --------------
  * C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias[N] (+ resid[M,N])); epilogue: 0 none, 1 erf-GELU, 2 SiLU.

@@ -15,6 +15,10 @@ What each fixture pins:
                            inputs, the Exp(1) noise E drawn from the same generator state, outputs
   denoise_T4.pt            the reference denoise() loop end to end (tiny T), same-noise replay
   apply_aa_noise.pt        PeptideDiff.apply_aa_noise (training q-sample) under a fixed seed
+  get_loss.pt              PeptideDiff.get_loss with its forward replaced by fixed logits (loss reductions + elbo_loss)
+  struct_forward_*.pt      structure_model denoiser forward (norel = as installed, rel = restored relative_key term)
+  struct_schedule_T*.pt    structure_model cosine_beta_schedule / compute_alphas tables
+  struct_p_sample_loop_T4.pt  the reference's own p_sample_loop under torch.manual_seed, with the N(0,1) draws it made
 
 Weights are never stored: both sides regenerate them with oracle.init_state_dict(cfg, seed, variant)
 and the reference model gets them through load_state_dict(strict=True).
@@ -255,6 +259,130 @@ def golden_structure_feed():
                os.path.join(GOLDEN, "structure_feed_cfg5.pt"))
 
 
+def golden_get_loss():
+    """PeptideDiff.get_loss (model.py:313-345) of the reference with its forward replaced by fixed logits: pins the loss
+    reductions (masked rates, the two CrossEntropyLoss terms, elbo_loss) independently of the denoiser."""
+    ref_model, _, _ = R.load_reference()
+    B, L = 6, 48
+    batch = O.synthetic_batch(B, L, (5, 48), (16, 48), 61)
+    g = torch.Generator().manual_seed(62)
+    logits = torch.randn(B, L, 20, generator=g) * 2.5
+    x0_idx = batch["ligand_seq"].argmax(-1)
+    flip = (torch.rand(B, L, generator=g) < 0.4) & batch["ligand_attn_mask"].bool()
+    xt_idx = torch.where(flip, torch.randint(0, 20, (B, L), generator=g), x0_idx)
+    x_t = F.one_hot(xt_idx, 20).float()
+
+    class _Shim:
+        loss_function = torch.nn.CrossEntropyLoss()
+
+        def forward(self, *a, **k):
+            return logits
+
+    out = ref_model.PeptideDiff.get_loss(_Shim(), batch, torch.zeros(B, 1), x_t)
+    out_o = O.get_loss(logits, batch, x_t)
+    for a, b in zip(out, out_o):
+        assert torch.equal(a, b), (a, b)
+    print("get_loss oracle == reference:", [round(float(v), 6) for v in out])
+    torch.save({"B": B, "L": L, "batch_seed": 61, "logits": logits, "x_t_idx": xt_idx.to(torch.uint8), "out": [v.clone() for v in out]},
+               os.path.join(GOLDEN, "get_loss.pt"))
+
+
+STRUCT_CASES = [
+    # name, L, layers, B, n_lig, n_rec, weight_seed, input_seed
+    ("L64_l2", 64, 2, 3, (5, 40), (16, 64), 31, 32),
+    ("L128_l12", 128, 12, 2, (5, 64), (16, 128), 33, 34),
+]
+
+
+def _struct_reference_model(SM, L, layers, rel):
+    from transformers.models.bert.modeling_bert import BertConfig
+    common = dict(max_position_embeddings=L, num_attention_heads=12, hidden_size=768, intermediate_size=1024, num_hidden_layers=layers,
+                  position_embedding_type="relative_key", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, use_cache=False)
+    enc = BertConfig(**common)
+    dec = BertConfig(**common, is_decoder=True, add_cross_attention=True)
+    for c in (enc, dec):
+        try:
+            c._attn_implementation = "eager"
+        except Exception:
+            pass
+    m = SM.ConditionalBertForDiffusionBase(enc, dec, 8)
+    if rel:
+        R.patch_relative_key_struct(m, L)
+    return m.eval()
+
+
+def golden_structure_model():
+    """SURVEY.md section 8(f) row 3.  (i) structure_model forward (model.py:180-215): reference module vs oracle on the same
+    weights, with and without the restored relative_key term; (ii) the reference's own p_sample_loop (sample.py:104-144) for
+    T = 4 under torch.manual_seed, replayed by the oracle with the same N(0,1) draws; (iii) schedule tables."""
+    from oracle import structdiff_oracle as S
+    SM, SS, SU = R.load_structure_sample_reference()
+    for rel in (False, True):
+        for name, L, layers, B, nl, nr, wseed, iseed in STRUCT_CASES:
+            cfg = S.OracleConfig(max_position_embeddings=L, num_hidden_layers=layers, feature_size=8, relative_key=rel)
+            sd = S.init_struct_state_dict(cfg, wseed)
+            m = _struct_reference_model(SM, L, layers, rel)
+            m.load_state_dict(sd, strict=True)
+            batch = O.synthetic_batch(B, L, nl, nr, iseed)
+            g = torch.Generator().manual_seed(iseed + 100)
+            noised = (torch.rand(B, L, 8, generator=g) * 2 - 1) * math.pi * batch["ligand_attn_mask"][..., None]
+            t = torch.randint(0, 1000, (B,), generator=g)
+            with torch.no_grad():
+                y = m(t, noised, batch["ligand_attn_mask"], batch["receptor_seq"], batch["receptor_angles"], batch["receptor_attn_mask"])
+                y_o = S.struct_forward(sd, cfg, t, noised, batch["ligand_attn_mask"], batch["receptor_seq"], batch["receptor_angles"],
+                                       batch["receptor_attn_mask"])
+            err = (y - y_o).abs().max().item()
+            print(f"struct forward {'rel' if rel else 'norel'} {name}: max|ref-oracle| = {err:.3e}  max|ref| = {y.abs().max():.3f}")
+            assert err < 2e-5, err
+            torch.save({"name": name, "L": L, "layers": layers, "B": B, "n_lig": nl, "n_rec": nr, "weight_seed": wseed, "input_seed": iseed,
+                        "relative_key": rel, "timestep": t, "noised": noised, "out": y.clone()},
+                       os.path.join(GOLDEN, f"struct_forward_{'rel' if rel else 'norel'}_{name}.pt"))
+    # schedule tables
+    for T in (50, 1000):
+        b_ref = SU.cosine_beta_schedule(T)
+        ab = SU.compute_alphas(b_ref)
+        b_o = S.cosine_beta_schedule(T)
+        coef = S.step_coefficients(b_o)
+        assert torch.equal(b_ref, b_o)
+        assert torch.equal(coef[:, 0], 1.0 / torch.sqrt(ab["alphas"])) and torch.equal(coef[:, 2], ab["sqrt_one_minus_alphas_cumprod"])
+        assert torch.equal(coef[:, 3], torch.sqrt(ab["posterior_variance"]))
+        torch.save({"T": T, "betas": b_ref.clone(), "coef": coef.clone()}, os.path.join(GOLDEN, f"struct_schedule_T{T}.pt"))
+    v = torch.linspace(-12, 12, 4001)
+    assert torch.equal(SU.modulo_with_wrapped_range(v, -math.pi, math.pi), S.modulo_with_wrapped_range(v, -math.pi, math.pi))
+    # the reference p_sample_loop end to end
+    T, L, layers, B = 4, 64, 2, 2
+    cfg = S.OracleConfig(max_position_embeddings=L, num_hidden_layers=layers, feature_size=8, relative_key=True)
+    sd = S.init_struct_state_dict(cfg, 35)
+    m = _struct_reference_model(SM, L, layers, True)
+    m.load_state_dict(sd, strict=True)
+    batch = O.synthetic_batch(B, L, (5, 40), (16, 64), 36)
+    g = torch.Generator().manual_seed(37)
+    x_T = S.modulo_with_wrapped_range(torch.randn(B, L, 8, generator=g) * batch["ligand_attn_mask"][..., None])
+    betas = SU.cosine_beta_schedule(T)
+    torch.manual_seed(38)
+    ref = SS.p_sample_loop(model=m, ligand_mask=batch["ligand_attn_mask"], ligand_angle_noise=x_T, receptor_seq=batch["receptor_seq"],
+                           receptor_mask=batch["receptor_attn_mask"], receptor_angle=batch["receptor_angles"], total_timesteps=T,
+                           betas=betas, disable_pbar=True)
+    torch.manual_seed(38)
+    noises = {}
+
+    def noise_fn(i):
+        noises[i] = torch.randn(B, L, 8)
+        return noises[i]
+
+    with torch.no_grad():
+        got = S.p_sample_loop(sd, cfg, batch["ligand_attn_mask"], x_T, batch["receptor_seq"], batch["receptor_attn_mask"],
+                              batch["receptor_angles"], T, betas, noise_fn)
+    err = (ref - got).abs().max().item()
+    print(f"struct p_sample_loop T={T}: max|ref-oracle| = {err:.3e}")
+    assert err < 1e-5, err
+    noise = torch.zeros(T, B, L, 8)
+    for i, n in noises.items():
+        noise[i] = n
+    torch.save({"T": T, "L": L, "layers": layers, "B": B, "weight_seed": 35, "batch_seed": 36, "n_lig": (5, 40), "n_rec": (16, 64),
+                "x_T": x_T, "noise": noise, "steps": ref.clone()}, os.path.join(GOLDEN, "struct_p_sample_loop_T4.pt"))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
@@ -266,6 +394,8 @@ def main():
     golden_forward()
     golden_denoise()
     golden_structure_feed()
+    golden_structure_model()
+    golden_get_loss()
     print("golden fixtures written to", os.path.normpath(GOLDEN))
 
 

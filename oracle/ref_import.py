@@ -131,6 +131,51 @@ def load_structure_reference():
     return struct_model
 
 
+def load_structure_sample_reference():
+    """structure_model/{sample,utils}.py imported in place (p_sample, p_sample_loop, compute_alphas, ...).  sample.py selects
+    `cuda:3` at import (sample.py:45-53): `torch.cuda.set_device` is a no-op for the duration of the import and the module's
+    DEVICE global is pointed at the CPU afterwards."""
+    if "struct_sample" in _CACHE:
+        return _CACHE["struct_sample"]
+    if not os.path.isfile(os.path.join(STRUCT_DIR, "sample.py")):
+        raise RuntimeError("reference tree not present (expected only in the build container)")
+    _install_stubs()
+    names = ("model", "sample", "utils", "dataset")
+    saved = {k: sys.modules.pop(k) for k in names if k in sys.modules}
+    sys.path.insert(0, STRUCT_DIR)
+    real_set_device = torch.cuda.set_device
+    torch.cuda.set_device = lambda *a, **k: None
+    try:
+        with _cwd(STRUCT_DIR), contextlib.redirect_stdout(None):
+            import sample as struct_sample  # noqa
+            import utils as struct_utils  # noqa
+            import model as struct_model  # noqa
+    finally:
+        torch.cuda.set_device = real_set_device
+        sys.path.remove(STRUCT_DIR)
+        for k in names:
+            m = sys.modules.pop(k, None)
+            if m is not None:
+                sys.modules["_ref_struct_s_" + k] = m
+        sys.modules.update(saved)
+    struct_sample.DEVICE = "cpu"
+    _CACHE["struct_sample"] = (struct_model, struct_sample, struct_utils)
+    return _CACHE["struct_sample"]
+
+
+def patch_relative_key_struct(model, max_pos: int):
+    """4.38.2 relative_key self-attention restored in the structure model's tree: both SELayers, every encoder and decoder
+    self-attention (NOT the decoder cross-attentions: 4.38.2 builds those with position_embedding_type="absolute")."""
+    hidden = model.decoder_config.hidden_size
+    heads = model.decoder_config.num_attention_heads
+    for blk in (model.receptor_emb, model.timestep_emb):
+        blk.attn.self = _RelKeySelfAttention(blk.attn.self, hidden, heads, max_pos)
+    for stack in (model.encoder, model.decoder):
+        for layer in stack.layer:
+            layer.attention.self = _RelKeySelfAttention(layer.attention.self, hidden, heads, max_pos)
+    return model
+
+
 def make_blosum_transition(timestep: int = 500):
     _, _, ref_utils = load_reference()
     with _cwd(SEQ_DIR):

@@ -488,6 +488,36 @@ def elbo_loss(logits1, logits2, eps=1e-6):
     return nll + kl
 
 
+def get_loss(pred_aa, batch, noised_ligand_seq):
+    """PeptideDiff.get_loss, model.py:313-345, on already computed logits `pred_aa` (loss_function = CrossEntropyLoss()).
+    Returns (total_loss, elbo, aa_noised_loss, aa_all_loss, aa_recovery_rate, aa_noise_rate)."""
+    ligand_mask = batch["ligand_attn_mask"].bool()
+    x0_idx = batch["ligand_seq"].argmax(dim=-1)
+    noised_mask = noised_ligand_seq.argmax(dim=-1) != x0_idx
+    aa_noise_rate = (noised_ligand_seq.argmax(dim=-1)[ligand_mask] == batch["ligand_seq"][ligand_mask].argmax(dim=-1)).sum() / ligand_mask.sum()
+    aa_recovery_rate = (pred_aa.argmax(dim=-1)[ligand_mask] == batch["ligand_seq"][ligand_mask].argmax(dim=-1)).sum() / ligand_mask.sum()
+    aa_noised_loss = F.cross_entropy(pred_aa[noised_mask].view(-1, 20), batch["ligand_seq"][noised_mask].argmax(dim=-1).view(-1))
+    sel = ligand_mask & (~noised_mask)
+    aa_all_loss = F.cross_entropy(pred_aa[sel].view(-1, 20), batch["ligand_seq"][sel].argmax(dim=-1).view(-1))
+    elbo = elbo_loss(pred_aa[noised_mask], batch["ligand_seq"][noised_mask])
+    return aa_noised_loss + elbo, elbo, aa_noised_loss, aa_all_loss, aa_recovery_rate, aa_noise_rate
+
+
+def decode(final, batch):
+    """The per-graph tail of denoise(), sample.py:208-224: (true_sequences, pred_sequences, recovery_rates)."""
+    AA = "ACDEFGHIKLMNPQRSTVWY"
+    rates, preds, trues = [], [], []
+    for i in range(final.shape[0]):
+        pred_seq = final[i].argmax(dim=1)
+        true_seq = batch["ligand_seq"][i].argmax(dim=1)
+        mask = batch["ligand_attn_mask"][i].bool()
+        r = (pred_seq[mask] == true_seq[mask]).sum() / mask.sum()
+        rates.append(r.item())
+        preds.append("".join(AA[j] for j in pred_seq[mask]))
+        trues.append("".join(AA[j] for j in true_seq[mask]))
+    return trues, preds, rates
+
+
 # --------------------------------------------------------------------------------------------
 # dataset item construction (sequence_model/dataset.py:41-49, 97-129) -- the "graph construction" analogue
 # --------------------------------------------------------------------------------------------
