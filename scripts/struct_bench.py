@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Secondary measurement (not the headline bench): structure-model sampling throughput on one B200.
+
+Workload = the reference's structure_model/sample.py defaults: 64 complexes per batch (CONFIG["batch_size"]), max_seq_len 64,
+12 + 12 layers, 8 angle features, T = 1000 cosine steps, bf16 operands, in-kernel Philox noise.  Unit: graph-steps/s (one
+complex through one p_sample step = denoiser forward + Gaussian update + wrap).  Timed with CUDA events around K full
+p_sample_loop calls through the Python mirror (device-resident inputs; the [T,B,L,F] history is produced on the device and its
+device->host copy is inside the timed region only for the e2e figure).  The CPU figure times the oracle port of the same loop
+body (forward with the receptor branch recomputed every step, as the reference does) on a bounded sample of steps.
+
+    python scripts/struct_bench.py [--steps 3] [--warmup 2] [--timesteps 1000] [--no-cpu]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--timesteps", type=int, default=1000)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--L", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    import seqdiff_b200 as sd
+    SM = sd.structure_model
+    B, L, T, Fs = a.batch, a.L, a.timesteps, 8
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    common = dict(max_position_embeddings=L, intermediate_size=1024, num_hidden_layers=12, position_embedding_type="relative_key")
+    m = SM.ConditionalBertForDiffusionBase(sd.BertConfig(**common), sd.BertConfig(**common, is_decoder=True, add_cross_attention=True), Fs)
+    # torch's default init zeroes nothing but adaLN_modulation[0] (model.py:49-50); give it values so no path is an identity
+    for blk in (m.receptor_emb, m.timestep_emb):
+        torch.nn.init.xavier_uniform_(blk.adaLN_modulation[0].weight)
+    m = m.eval().to(dev)
+    m.precision = "bf16"
+    g = torch.Generator().manual_seed(3)
+    nl = torch.randint(5, L + 1, (B,), generator=g)
+    nr = torch.randint(16, L + 1, (B,), generator=g)
+    pos = torch.arange(L)[None, :]
+    lm, rm = (pos < nl[:, None]).float(), (pos < nr[:, None]).float()
+    rseq = torch.nn.functional.one_hot(torch.randint(0, 20, (B, L), generator=g), 20).float() * rm[..., None]
+    rang = ((torch.rand(B, L, Fs, generator=g) * 2 - 1) * math.pi) * rm[..., None]
+    x_T = SM.modulo_with_wrapped_range(torch.randn(B, L, Fs, generator=g))
+    betas = SM.cosine_beta_schedule(T)
+    d = lambda t: t.to(dev)  # noqa: E731
+    args = dict(model=m, ligand_mask=d(lm), ligand_angle_noise=d(x_T), receptor_seq=d(rseq), receptor_mask=d(rm), receptor_angle=d(rang),
+                total_timesteps=T, betas=betas, seed=5)
+    lib = sd.lib()
+    for _ in range(a.warmup):
+        SM.p_sample_loop(**args, keep_history=False)
+    torch.cuda.synchronize()
+    n0 = lib.seqdiff_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        out = SM.p_sample_loop(**args, keep_history=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.seqdiff_launch_count() - n0
+    assert torch.isfinite(out).all()
+    value = B * T * a.steps / (ms * 1e-3)
+    # e2e: host inputs (pinned) in, full [T,B,L,F] history back on the host, as the reference returns it
+    pin = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in args.items() if k != "model"}
+    SM.p_sample_loop(model=m, **pin)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        hist = SM.p_sample_loop(model=m, **pin)
+    torch.cuda.synchronize()
+    e2e = B * T * a.steps / (time.perf_counter() - t0)
+    res = {"metric": "structure-model graph-steps/s (denoiser forward + Gaussian reverse step + wrap per complex)", "value": value,
+           "unit": "graph-steps/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "dtype": "bf16",
+           "data": "synthetic", "higher_is_better": True,
+           "config": {"workload": f"structure_model/sample.py defaults: {B} complexes, max_seq_len {L}, 12+12 layers, 8 angle features, T={T}",
+                      "receptor_branch": "evaluated once per sampling (independent of t and of the ligand); the reference recomputes it every step"},
+           "gpu_launches": int(launches),
+           "e2e": {"value": e2e, "unit": "graph-steps/s", "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in pin.values() if torch.is_tensor(v))),
+                   "d2h_bytes_per_step": int(hist.numel() * 4), "api": "structure_model.p_sample_loop(host tensors) -> [T,B,L,F] history on the host"}}
+    if not a.no_cpu:
+        from oracle import structdiff_oracle as S
+        from oracle import seqdiff_oracle as O  # noqa: F401
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        cfg = S.OracleConfig(max_position_embeddings=L, num_hidden_layers=12, feature_size=Fs, relative_key=True)
+        state = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+        coef = S.step_coefficients(betas)
+        x = x_T.clone()
+        times = []
+        with torch.no_grad():
+            for k in range(3):
+                i = T - 1 - k
+                t0 = time.perf_counter()
+                o = S.struct_forward(state, cfg, torch.full((B,), i, dtype=torch.long), x, lm, rseq, rang, rm)
+                x = S.modulo_with_wrapped_range(S.p_sample_update(x, o, coef, i, torch.randn_like(x)))
+                if k:
+                    times.append(time.perf_counter() - t0)
+        res["cpu_baseline"] = {"value": B * len(times) / sum(times), "unit": "graph-steps/s", "cores": threads, "kind": "port",
+                               "sample": f"{len(times)} p_sample steps x {B} complexes (of {T}); oracle port, receptor branch recomputed per step like the reference"}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
