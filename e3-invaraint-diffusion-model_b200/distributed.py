@@ -74,3 +74,30 @@ def denoise_sharded(batch, model, noise_schedule, transition, diverse, denoise_f
         for dst, src in zip(out, p):
             dst.extend(src)
     return out
+
+
+def p_sample_loop_sharded(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mask, receptor_angle, total_timesteps, betas,
+                          sample_fn: Callable = None, group=None, **kw):
+    """structure_model p_sample_loop (reference structure_model/sample.py:104-144) over the ranks of `group`: every rank samples
+    its contiguous block of complexes on its own GPU (noise keyed by the global graph id), then the CPU [T, b_r, L, F] histories
+    are all-gathered and concatenated along the batch axis in rank order -- each rank returns what one GPU returns for the
+    whole batch.  No collective on the data path; the only exchange is the result tensor the reference returns anyway."""
+    import torch.distributed as dist
+    if sample_fn is None:
+        from .structure_model import p_sample_loop as sample_fn
+    if not (dist.is_available() and dist.is_initialized()):
+        return sample_fn(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mask, receptor_angle, total_timesteps, betas, **kw)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = ligand_angle_noise.shape[0]
+    lo, hi = shard_bounds(n, world, rank)
+    noise_steps = kw.pop("noise_steps", None)
+    if noise_steps is not None:
+        kw["noise_steps"] = noise_steps[:, lo:hi]
+    gid0 = lo + kw.pop("graph_id0", 0)
+    part = None
+    if hi > lo:
+        part = sample_fn(model, ligand_mask[lo:hi], ligand_angle_noise[lo:hi], receptor_seq[lo:hi], receptor_mask[lo:hi],
+                         receptor_angle[lo:hi], total_timesteps, betas, graph_id0=gid0, **kw)
+    parts = [None] * world
+    dist.all_gather_object(parts, part, group=group)
+    return torch.cat([p for p in parts if p is not None], dim=1)

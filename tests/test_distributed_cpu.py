@@ -81,3 +81,45 @@ def test_denoise_sharded_world2_matches_single_process():
         assert slow == 2.0                          # max over ranks
         assert nloc == (4 if rank == 0 else 3) and gid0 == (0 if rank == 0 else 4)
         assert ids == [f"p{i}" for i in range(gid0, gid0 + nloc)]
+
+
+def _fake_p_sample_loop(model, ligand_mask, x, receptor_seq, receptor_mask, receptor_angle, T, betas, graph_id0=0, noise_steps=None, **kw):
+    """stands in for the CUDA structure sampler: entry [k, i] encodes (global graph id, x row, noise slice)"""
+    n = x.shape[0]
+    gid = torch.arange(graph_id0, graph_id0 + n).float()[None, :, None, None]
+    out = gid + x[None] * 0.001 + torch.arange(T).float()[:, None, None, None] * 100
+    if noise_steps is not None:
+        out = out + noise_steps
+    return out
+
+
+def _struct_worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import seqdiff_b200 as sd
+    x = torch.arange(n).float()[:, None, None].expand(n, 4, 8).contiguous()
+    z = torch.arange(3 * n).float().reshape(3, n, 1, 1).expand(3, n, 4, 8).contiguous() * 1e-6
+    out = sd.p_sample_loop_sharded(None, torch.ones(n, 4), x, torch.zeros(n, 4, 20), torch.ones(n, 4), torch.zeros(n, 4, 8), 3, None,
+                                   sample_fn=_fake_p_sample_loop, noise_steps=z)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_struct_p_sample_loop_sharded_world2_matches_single_process():
+    n = 5  # ragged split: 3 + 2
+    x = torch.arange(n).float()[:, None, None].expand(n, 4, 8).contiguous()
+    z = torch.arange(3 * n).float().reshape(3, n, 1, 1).expand(3, n, 4, 8).contiguous() * 1e-6
+    want = _fake_p_sample_loop(None, None, x, None, None, None, 3, None, graph_id0=0, noise_steps=z)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_struct_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in res:
+        assert out.shape == (3, n, 4, 8) and torch.equal(out, want)
