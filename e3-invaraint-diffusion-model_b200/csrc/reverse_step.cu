@@ -77,6 +77,14 @@ __device__ __forceinline__ float inv_exp1_fast(uint32_t w) {
   return rcp_approx(-lg2_approx(u));
 }
 
+// two fp32 FMAs in one instruction (FFMA2 on sm_100a): d = a * b + c on both halves.  Same rounding as two fmaf.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  ra = *reinterpret_cast<uint64_t*>(&a); rb = *reinterpret_cast<uint64_t*>(&b); rc = *reinterpret_cast<uint64_t*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // exponential race / argmax over one normalised row
 __device__ __forceinline__ int pick_class(const float (&prob)[C], bool diverse, const float (&E)[C]) {
   int best = 0;
@@ -149,8 +157,8 @@ __device__ __noinline__ int soft_row_class(const float* __restrict__ lg_row, con
   return psum != 0.f ? best : 0;
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel(const float* __restrict__ q_tables, int n_tab, int L,
+template <bool FAST, int THREADS = kRevThreads, int MINB = (FAST ? 2 : 1)>
+__global__ void __launch_bounds__(THREADS, MINB) reverse_step_kernel(const float* __restrict__ q_tables, int n_tab, int L,
                                                                    const float* __restrict__ x_t, const float* __restrict__ logits,
                                                                    int diverse, const float* __restrict__ noise_E, uint64_t seed,
                                                                    uint64_t graph_id0, uint32_t step, const int* __restrict__ step_ptr,
@@ -195,14 +203,14 @@ __global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel
     if (noise_E) noise_E += static_cast<size_t>(sidx) * n_res * C;
   }
   const float* tab = q_tables + static_cast<size_t>(n_tab == 1 ? 0 : b) * (3 * C * C);
-  for (int i = threadIdx.x; i < C * C; i += kRevThreads) {
+  for (int i = threadIdx.x; i < C * C; i += THREADS) {
     sQt[i] = tab[i];
     sQsb[i] = tab[C * C + i];
     sQtb[i] = tab[2 * C * C + i];
   }
   __syncthreads();
   if (FAST) {
-    for (int e = threadIdx.x; e < C * C; e += kRevThreads) {
+    for (int e = threadIdx.x; e < C * C; e += THREADS) {
       const int r = e / C, x = e - r * C;  // r = i for Qtb[i,x], r = j for Qt[j,x]
       const float den = sQtb[e];
       sInvT[x * kRS + r] = rcp_approx(den == 0.f ? 1e-6f : den);
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel
       sQsbA[e] = sQsb[e];
     }
   } else {
-    for (int e = threadIdx.x; e < C * C; e += kRevThreads) {  // (i, j) fixed per thread, x runs: no div/mod in the inner loop
+    for (int e = threadIdx.x; e < C * C; e += THREADS) {  // (i, j) fixed per thread, x runs: no div/mod in the inner loop
       const int i = e / C, j = e - i * C;
       const float qsb = sQsb[e];
 #pragma unroll 4
@@ -223,7 +231,7 @@ __global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel
   }
   __syncthreads();
 
-  for (int l = blockIdx.x * kRevThreads + threadIdx.x; l < L; l += gridDim.x * kRevThreads) {
+  for (int l = blockIdx.x * THREADS + threadIdx.x; l < L; l += gridDim.x * THREADS) {
     const size_t n = static_cast<size_t>(b) * L + l;
     float lg[C], xr[C];
 #pragma unroll
@@ -262,17 +270,21 @@ __global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel
           const float4 w = inv4[i4];
           pf[4 * i4] *= w.x; pf[4 * i4 + 1] *= w.y; pf[4 * i4 + 2] *= w.z; pf[4 * i4 + 3] *= w.w;
         }
+        float2 un2[C / 2];
+#pragma unroll
+        for (int j = 0; j < C / 2; ++j) un2[j] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < C; ++i) {  // fully unrolled: pf[i] must stay in registers
+          const float2 pp = make_float2(pf[i], pf[i]);
 #pragma unroll
           for (int j4 = 0; j4 < C / 4; ++j4) {
             const float4 w = qsb4[i * (C / 4) + j4];  // same address in every lane: broadcast
-            unf[4 * j4] = fmaf(pf[i], w.x, unf[4 * j4]);
-            unf[4 * j4 + 1] = fmaf(pf[i], w.y, unf[4 * j4 + 1]);
-            unf[4 * j4 + 2] = fmaf(pf[i], w.z, unf[4 * j4 + 2]);
-            unf[4 * j4 + 3] = fmaf(pf[i], w.w, unf[4 * j4 + 3]);
+            un2[2 * j4] = ffma2(pp, make_float2(w.x, w.y), un2[2 * j4]);          // FFMA2: 200 instead of 400 FMA issues
+            un2[2 * j4 + 1] = ffma2(pp, make_float2(w.z, w.w), un2[2 * j4 + 1]);
           }
         }
+#pragma unroll
+        for (int j = 0; j < C / 2; ++j) { unf[2 * j] = un2[j].x; unf[2 * j + 1] = un2[j].y; }
 #pragma unroll
         for (int j4 = 0; j4 < C / 4; ++j4) {
           const float4 w = qt4[j4];
@@ -286,14 +298,24 @@ __global__ void __launch_bounds__(kRevThreads, FAST ? 2 : 1) reverse_step_kernel
 #pragma unroll
         for (int j = 0; j < C; ++j) unf[j] = 1e-5f;
       }
-      uint32_t w[C];
-      philox_row(seed, graph_id0 + b, static_cast<uint32_t>(l), step, w);
+      // race: class j uses word j % 4 of Philox call j / 4 (same stream as philox_row); one call at a time so that only 4 words
+      // are live, winners of each group of 4 found by a 2-level tree, groups folded in order (first maximum wins, as argmax)
       int best = 0;
       float bv = -INFINITY;
+      const uint64_t graph = graph_id0 + b;
 #pragma unroll
-      for (int j = 0; j < C; ++j) {
-        const float v = unf[j] * inv_exp1_fast(w[j]);
-        if (v > bv) { bv = v; best = j; }
+      for (int call = 0; call < C / 4; ++call) {
+        uint32_t c4[4] = {static_cast<uint32_t>(l), step * 8u + call, static_cast<uint32_t>(graph), static_cast<uint32_t>(graph >> 32)};
+        philox4x32_10(c4, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+        const float v0 = unf[4 * call] * inv_exp1_fast(c4[0]), v1 = unf[4 * call + 1] * inv_exp1_fast(c4[1]);
+        const float v2 = unf[4 * call + 2] * inv_exp1_fast(c4[2]), v3 = unf[4 * call + 3] * inv_exp1_fast(c4[3]);
+        const bool a = v1 > v0, c = v3 > v2;
+        const float va = a ? v1 : v0, vc = c ? v3 : v2;
+        const int ia = 4 * call + (a ? 1 : 0), ic = 4 * call + (c ? 3 : 2);
+        const bool e = vc > va;
+        const float vg = e ? vc : va;
+        const int ig = e ? ic : ia;
+        if (vg > bv) { bv = vg; best = ig; }
       }
       write_onehot(x_s + n * C, best);
       if (idx_out) idx_out[n] = static_cast<uint8_t>(best);
@@ -368,12 +390,31 @@ int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_
                  uint8_t* idx_out, cudaStream_t s, int* advance) {
   SD_CHECK(B > 0 && L > 0, "empty reverse step");
   SD_CHECK(n_tab == 1 || n_tab == B, "q_tables must hold 1 or B (Qt,Qsb,Qtb) triples");
-  static const int rpt = [] { const char* e = getenv("SEQDIFF_REV_RPT"); return e ? atoi(e) : 2; }();  // residues per thread
-  const dim3 grid(ceil_div(L, rpt * kRevThreads), B);  // residues per thread: amortises the per-CTA table build
-  if (diverse && !noise_E)
-    SD_CUDA(launch_k(reverse_step_kernel<true>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out, advance));
-  else
+  // launch shape of the production (fast) kernel: SEQDIFF_REV_CFG = threads per CTA * 100 + min CTAs per SM * 10 + residues per thread
+  // (sweep on B200: profiles/revstep_r01.log)
+  static const int cfg = [] { const char* e = getenv("SEQDIFF_REV_CFG"); return e ? atoi(e) : 25622; }();
+  if (diverse && !noise_E) {
+#define SD_REV_LAUNCH(T_, MB_)                                                                                                              \
+  {                                                                                                                                         \
+    const dim3 grid(ceil_div(L, (cfg % 10) * T_), B);                                                                                       \
+    SD_CUDA(launch_k(reverse_step_kernel<true, T_, MB_>, dim3(grid), dim3(T_), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, \
+                     graph_id0, step, step_ptr, x_s, idx_out, advance));                                                                    \
+  }
+    SD_CHECK(cfg % 10 >= 1, "SEQDIFF_REV_CFG: residues per thread must be >= 1");
+    switch (cfg / 10) {
+      case 2562: SD_REV_LAUNCH(256, 2); break;
+      case 2563: SD_REV_LAUNCH(256, 3); break;
+      case 1284: SD_REV_LAUNCH(128, 4); break;
+      case 1285: SD_REV_LAUNCH(128, 5); break;
+      case 1286: SD_REV_LAUNCH(128, 6); break;
+      case 643: SD_REV_LAUNCH(64, 3); break;
+      default: SD_CHECK(false, "SEQDIFF_REV_CFG: unknown launch shape");
+    }
+#undef SD_REV_LAUNCH
+  } else {
+    const dim3 grid(ceil_div(L, 2 * kRevThreads), B);
     SD_CUDA(launch_k(reverse_step_kernel<false>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out, advance));
+  }
   SD_LAUNCHED("reverse_step", s);
   return SEQDIFF_OK;
 }
