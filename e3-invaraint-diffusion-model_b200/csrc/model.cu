@@ -824,6 +824,53 @@ static int bert_layer_plain(const Model& m, int wfmt, const LayerW& w, bool cros
   return SEQDIFF_OK;
 }
 
+// 16-bit modes: the same stack with the LayerNorm-rebuild flow of the sequence decoder (forward_t): a post-LN tensor exists only as
+// the 16-bit operand of the next GEMM; its fp32 value, needed as the residual of the GEMM after that, is rebuilt in that GEMM's
+// epilogue from the fp32 pre-LN tensor, the per-row (mean, rstd) and the affine -- the LayerNorm kernels skip their fp32 copy.
+// Pre-LN buffers with fixed roles: obuf[0] self-output, obuf[1] cross-output, obuf[2] FFN-output (every GEMM reads its residual from
+// a different buffer than the one it writes).  *out = 16-bit output of the last layer (all the consumers of a stack read).
+template <typename T>
+static int bert_stack_lnresid(const Model& m, int wfmt, const std::vector<LayerW>& Ls, bool cross, int B, int Lq, int Lk, const Act<T>& h0,
+                              const float* q_mask, const float* k_mask, const T* kv_all, int ldkv, T* qkv, T* ctx, T* cq, T* ffn,
+                              float* const (&obuf)[3], float2* lnstats, T* hT0, T* hT1, const T** out, cudaStream_t s) {
+  const int H = m.cfg.hidden_size, I = m.cfg.intermediate_size, heads = m.cfg.num_attention_heads, P = m.cfg.max_position_embeddings;
+  const float eps = m.cfg.layer_norm_eps;
+  const int M = B * Lq;
+  float2* stA = lnstats;
+  float2* stB = lnstats + M;
+  float2* stC = lnstats + 2 * static_cast<size_t>(M);
+  LnResid prev{};
+  const float* o_prev = nullptr;
+  const T* h = h0.t;
+  for (size_t i = 0; i < Ls.size(); ++i) {
+    const LayerW& w = Ls[i];
+    SD_TRY(gemm_T(wfmt, M, 3 * H, H, h, w.self.qkv, w.self.qkv_b, 0, qkv, s));
+    SD_TRY(attention<T>(B, heads, Lq, Lq, qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, q_mask, ctx, s));
+    SD_TRY(gemm_ln<T>(wfmt, M, H, H, ctx, w.self.out, w.self.out_b, i == 0 ? h0.s : o_prev, obuf[0], i == 0 ? nullptr : &prev, w.self.ln_w,
+                      w.self.ln_b, eps, hT0, stA, s));
+    const T* cur = hT0;
+    const float* o_cur = obuf[0];
+    LnResid rc{stA, w.self.ln_w, w.self.ln_b};
+    if (cross) {
+      SD_TRY(gemm_T(wfmt, M, H, H, hT0, w.cq, w.cq_b, 0, cq, s));
+      const T* kbase = kv_all + i * 2 * static_cast<size_t>(H);
+      SD_TRY(attention<T>(B, heads, Lq, Lk, cq, H, kbase, ldkv, kbase + H, ldkv, static_cast<const T*>(nullptr), P, k_mask, ctx, s));
+      SD_TRY(gemm_ln<T>(wfmt, M, H, H, ctx, w.cout, w.cout_b, obuf[0], obuf[1], &rc, w.cln_w, w.cln_b, eps, hT1, stB, s));
+      cur = hT1;
+      o_cur = obuf[1];
+      rc = LnResid{stB, w.cln_w, w.cln_b};
+    }
+    SD_TRY(gemm_T(wfmt, M, I, H, cur, w.inter, w.inter_b, 1, ffn, s));
+    T* nxt = cross ? hT0 : hT1;
+    SD_TRY(gemm_ln<T>(wfmt, M, H, I, ffn, w.outd, w.outd_b, o_cur, obuf[2], &rc, w.oln_w, w.oln_b, eps, nxt, stC, s));
+    prev = LnResid{stC, w.oln_w, w.oln_b};
+    o_prev = obuf[2];
+    h = nxt;
+  }
+  *out = h;
+  return SEQDIFF_OK;
+}
+
 size_t Model::struct_workspace_need(int precision, int B, int Ll, int Lr) const {
   const size_t es = precision == SEQDIFF_FP32 ? 4 : 2;
   const size_t H = cfg.hidden_size, I = cfg.intermediate_size, NL = cfg.num_hidden_layers;
@@ -883,15 +930,23 @@ int Model::struct_forward_t(int wfmt, int B, int Ll, int Lr, const float* timest
     SD_TRY(embed_ln_multi<T>(jobs, eps, H, s));
     std::vector<Segment> rseg{{0, B, Lr, rec_mask}};
     SD_TRY(se_layer<T>(*this, wfmt, se_lig, x, cT, Mr, 1, Mr, rseg, sb, x2, s));
-    Act<T> h = x2;
-    for (int i = 0; i < NL; ++i) {
-      Act<T> nh;
-      SD_TRY(bert_layer_plain<T>(*this, wfmt, enc_layers[i], false, B, Lr, Lr, h, rec_mask, nullptr, nullptr, 0, sb.qkv, sb.ctx, cq, ffn, sb.o,
-                                 hb[0], hb[1], &nh, s));
-      h = nh;
+    const T* enc_out = nullptr;
+    if constexpr (k16) {
+      float* const obuf[3] = {sb.o, sb.m2, hb[0].s};
+      SD_TRY(bert_stack_lnresid<T>(*this, wfmt, enc_layers, false, B, Lr, Lr, x2, rec_mask, nullptr, nullptr, 0, sb.qkv, sb.ctx, cq, ffn, obuf,
+                                   reinterpret_cast<float2*>(hb[1].s), hb[0].t, hb[1].t, &enc_out, s));
+    } else {
+      Act<T> h = x2;
+      for (int i = 0; i < NL; ++i) {
+        Act<T> nh;
+        SD_TRY(bert_layer_plain<T>(*this, wfmt, enc_layers[i], false, B, Lr, Lr, h, rec_mask, nullptr, nullptr, 0, sb.qkv, sb.ctx, cq, ffn, sb.o,
+                                   hb[0], hb[1], &nh, s));
+        h = nh;
+      }
+      enc_out = h.t;
     }
     // every decoder layer's cross K|V in one GEMM: the only thing the decoder reads from the receptor side
-    SD_TRY(gemm_T(wfmt, Mr, NL * 2 * H, H, h.t, ckv_all, ckv_all_b, 0, kv_all, s));
+    SD_TRY(gemm_T(wfmt, Mr, NL * 2 * H, H, enc_out, ckv_all, ckv_all_b, 0, kv_all, s));
   }
 
   if (!(phases & 2)) return SEQDIFF_OK;
@@ -905,15 +960,23 @@ int Model::struct_forward_t(int wfmt, int B, int Ll, int Lr, const float* timest
   }
   std::vector<Segment> lseg{{0, B, Ll, lig_mask}};
   SD_TRY(se_layer<T>(*this, wfmt, se_dec, x, teT, B, Ll, Ml, lseg, sb, x2, s));  // timestep_emb: c broadcast over L
-  Act<T> h = x2;
-  for (int i = 0; i < NL; ++i) {
-    Act<T> nh;
-    const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
-    SD_TRY(bert_layer_plain<T>(*this, wfmt, layers[i], true, B, Ll, Lr, h, lig_mask, rec_mask, kbase, NL * 2 * H, sb.qkv, sb.ctx, cq, ffn, sb.o,
-                               hb[0], hb[1], &nh, s));
-    h = nh;
+  const T* dec_out = nullptr;
+  if constexpr (k16) {
+    float* const obuf[3] = {sb.o, sb.m2, hb[0].s};
+    SD_TRY(bert_stack_lnresid<T>(*this, wfmt, layers, true, B, Ll, Lr, x2, lig_mask, rec_mask, kv_all, NL * 2 * H, sb.qkv, sb.ctx, cq, ffn, obuf,
+                                 reinterpret_cast<float2*>(hb[1].s), hb[0].t, hb[1].t, &dec_out, s));
+  } else {
+    Act<T> h = x2;
+    for (int i = 0; i < NL; ++i) {
+      Act<T> nh;
+      const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
+      SD_TRY(bert_layer_plain<T>(*this, wfmt, layers[i], true, B, Ll, Lr, h, lig_mask, rec_mask, kbase, NL * 2 * H, sb.qkv, sb.ctx, cq, ffn, sb.o,
+                                 hb[0], hb[1], &nh, s));
+      h = nh;
+    }
+    dec_out = h.t;
   }
-  SD_TRY(gemm_T(wfmt, Ml, H, H, h.t, p1, p1_b, 1, y, s));
+  SD_TRY(gemm_T(wfmt, Ml, H, H, dec_out, p1, p1_b, 1, y, s));
   SD_TRY(predictor_tail<T>(y, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, out, s));
   return SEQDIFF_OK;
 }

@@ -87,6 +87,33 @@ def main():
            "gpu_launches": int(launches),
            "e2e": {"value": e2e, "unit": "graph-steps/s", "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in pin.values() if torch.is_tensor(v))),
                    "d2h_bytes_per_step": int(hist.numel() * 4), "api": "structure_model.p_sample_loop(host tensors) -> [T,B,L,F] history on the host"}}
+    # live roofline of the dominant kernel (tcgen05 GEMM): one eager forward = receptor branch + ligand branch, library event profiler
+    H, I, NL = 768, 1024, 12
+    Ml = Mr = B * L
+    macs = 19 * Mr * H * H + NL * Mr * (4 * H * H + 2 * I * H) + 2 * NL * Mr * H * H      # receptor_emb, 12 encoder layers, cross K|V
+    macs += 12 * Ml * H * H + 7 * B * H * H + NL * Ml * (6 * H * H + 2 * I * H) + Ml * H * H  # timestep_emb, 12 decoder layers, head
+    t_arr = torch.full((B,), T - 1, dtype=torch.long, device=dev)
+    fargs = (t_arr, d(x_T), d(lm), d(rseq), d(rang), d(rm))
+    with torch.no_grad():
+        for _ in range(2):
+            m(*fargs)
+        torch.cuda.synchronize()
+        reps = 5
+        prof = sd._cabi.profile(lambda: [m(*fargs) for _ in range(reps)])
+    gemm_ms = sum(v[0] for k, v in prof.items() if k.startswith("gemm_tcgen05"))
+    gemm_n = sum(v[1] for k, v in prof.items() if k.startswith("gemm_tcgen05"))
+    total_ms = sum(v[0] for v in prof.values())
+    peak, src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak, src = json.load(open(pk)).get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    ach = 2 * macs * reps / (gemm_ms * 1e-3) / 1e12
+    res["roofline"] = {"kernel": f"gemm_tcgen05_kernel ({gemm_n // reps} launches per full forward at M = {Ml} rows)", "bound": "tensor", "achieved": ach,
+                       "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+                       "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1), "share_of_forward": gemm_ms / total_ms,
+                       "kernel_ms_per_forward": {k: v[0] / reps for k, v in sorted(prof.items())},
+                       "note": "eager launches with an event after each kernel: at M = 4096 every GEMM is a single partial wave (<= 128 tiles on 148 SMs), "
+                               "so the step is launch / ramp bound, not tensor bound"}
     if not a.no_cpu:
         from oracle import structdiff_oracle as S
         from oracle import seqdiff_oracle as O  # noqa: F401
