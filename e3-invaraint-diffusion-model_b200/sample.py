@@ -182,3 +182,28 @@ def denoise(batch, model: PeptideDiff, noise_schedule, transition, diverse, **kw
         structure_ids.append(f'{ids["pdb_id"][i]}_{ids["ligand_chain"][i]}' if ids is not None else str(i))
     print(sum(recovery_rates) / len(recovery_rates))
     return structure_ids, true_sequences, pred_sequences, recovery_rates
+
+
+def sample_dataset(dataloader, model, noise_schedule=None, transition=None, diverse=True, output_path=None, denoise_fn=None, **kw):
+    """The `__main__` block of the reference (sample.py:231-257): every batch of `dataloader` through `denoise`, results
+    collected in the reference's DataFrame (columns structure_ids / true_sequence / predict_sequence / recovery_rate) and, when
+    `output_path` is given, pickled exactly like `res.to_pickle(OUTPUT_PATH)`.  Returns the DataFrame."""
+    import pandas as pd
+    if noise_schedule is None:
+        noise_schedule = PredefinedNoiseScheduleDiscrete(CONFIG["noise_schedule"], CONFIG["timesteps"])
+    if transition is None:
+        transition = BlosumTransition(x_classes=20)
+    fn = denoise if denoise_fn is None else denoise_fn
+    structure_ids, true_sequences, pred_sequences, recovery_rates = [], [], [], []
+    for idx, batch in enumerate(dataloader):
+        print(f"Generating Batch {idx}")
+        ids, true_seq, pred_seq, rec_rates = fn(batch, model, noise_schedule, transition, diverse, **kw)
+        structure_ids.extend(ids)
+        recovery_rates.extend(rec_rates)
+        pred_sequences.extend(pred_seq)
+        true_sequences.extend(true_seq)
+    res = pd.DataFrame(zip(structure_ids, true_sequences, pred_sequences, recovery_rates),
+                       columns=["structure_ids", "true_sequence", "predict_sequence", "recovery_rate"])
+    if output_path is not None:
+        res.to_pickle(output_path)
+    return res

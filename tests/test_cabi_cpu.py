@@ -96,3 +96,21 @@ def test_error_behaviour_matches_reference():
     with pytest.raises(ValueError, match="Unknown lr scheduler"):  # model.py:448
         p.configure_optimizers()
     assert p.timesteps == 50 and hasattr(p, "aa_transition_model") and hasattr(p, "discrete_noise_schedule")
+
+
+def test_sample_dataset_output_format(tmp_path):
+    """reference sample.py:231-257: DataFrame columns and pickle round trip (sampler injected: no GPU here)."""
+    import pandas as pd
+    import seqdiff_b200 as sd
+
+    def fake(batch, model, sched, trans, diverse, **kw):
+        n = len(batch["ids"])
+        return batch["ids"], ["ACD"] * n, ["ACE"] * n, [2 / 3] * n
+
+    loader = [{"ids": ["1abc_A", "2xyz_B"]}, {"ids": ["3pqr_C"]}]
+    out = tmp_path / "sampled.pkl"
+    df = sd.sample_dataset(loader, None, noise_schedule=object(), transition=object(), output_path=str(out), denoise_fn=fake)
+    assert list(df.columns) == ["structure_ids", "true_sequence", "predict_sequence", "recovery_rate"]
+    assert list(df["structure_ids"]) == ["1abc_A", "2xyz_B", "3pqr_C"]
+    back = pd.read_pickle(out)
+    assert back.equals(df) and len(back) == 3
