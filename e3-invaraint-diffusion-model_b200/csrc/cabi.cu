@@ -256,6 +256,19 @@ int seqdiff_op_attention(int precision, int B, int heads, int Lq, int Lk, const 
   SD_GUARD_END
 }
 
+int seqdiff_op_layernorm(int precision, int M, int H, const float* in, const float* ln_w, const float* ln_b, float eps, float* out32, void* out16,
+                         float* stats, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(in && ln_w && ln_b && (out32 || out16) && M > 0, "bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float2* st = reinterpret_cast<float2*>(stats);
+  if (precision == SEQDIFF_FP32) return layernorm<float>(in, M, H, ln_w, ln_b, eps, out32, nullptr, st, s);
+  if (precision == SEQDIFF_FP16) return layernorm<f16>(in, M, H, ln_w, ln_b, eps, out32, static_cast<f16*>(out16), st, s);
+  SD_CHECK(precision == SEQDIFF_BF16, "bad precision");
+  return layernorm<bf16>(in, M, H, ln_w, ln_b, eps, out32, static_cast<bf16*>(out16), st, s);
+  SD_GUARD_END
+}
+
 int seqdiff_op_philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, void* stream) {
   SD_GUARD_BEGIN
   SD_CHECK(out && B > 0 && L > 0, "bad argument");

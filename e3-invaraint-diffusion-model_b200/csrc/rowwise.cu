@@ -3,6 +3,8 @@
 // One warp owns one token row (H = 256*VPL features, 8 contiguous elements per lane per vector => 16 B
 // (bf16) / 32 B (f32) per lane, fully coalesced); LayerNorm statistics are always fp32, two-pass
 // (mean, then centred variance) like ATen's CPU kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -242,36 +244,57 @@ template int embed_ln_multi<bf16>(EmbedJobs, float, int, cudaStream_t);
 template int embed_ln_multi<f16>(EmbedJobs, float, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int VPL>
-__global__ void __launch_bounds__(kRowThreads) layernorm_kernel(const float* __restrict__ in, int M, int H, const float* __restrict__ w,
-                                                                const float* __restrict__ b, float eps, float* __restrict__ out32,
-                                                                T* __restrict__ outT, float2* __restrict__ stats) {
+template <typename T, int VPL, int THREADS = kRowThreads, int RPW = 1>
+__global__ void __launch_bounds__(THREADS) layernorm_kernel(const float* __restrict__ in, int M, int H, const float* __restrict__ w,
+                                                            const float* __restrict__ b, float eps, float* __restrict__ out32,
+                                                            T* __restrict__ outT, float2* __restrict__ stats) {
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int lane = threadIdx.x & 31;
-  const int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5;
-  if (row >= M) return;
-  float v[VPL][8];
-  load_row<float, VPL>(in + static_cast<size_t>(row) * H, lane, v);
-  float mean, rstd;
-  row_stats<VPL>(v, H, eps, mean, rstd);
-  if (stats && lane == 0) stats[row] = make_float2(mean, rstd);  // lets a consumer re-derive LN(in) without the fp32 copy
+  const int row0 = ((blockIdx.x * THREADS + threadIdx.x) >> 5) * RPW;  // RPW consecutive rows per warp, all loads issued up front
+  if (row0 >= M) return;
+  float v[RPW][VPL][8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    float g8[8], b8[8];
-    load8<float>(w + (i * 32 + lane) * 8, g8);
-    load8<float>(b + (i * 32 + lane) * 8, b8);
+  for (int r = 0; r < RPW; ++r)
+    if (row0 + r < M) load_row<float, VPL>(in + static_cast<size_t>(row0 + r) * H, lane, v[r]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * g8[j] + b8[j];
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+    if (row >= M) break;
+    float mean, rstd;
+    row_stats<VPL>(v[r], H, eps, mean, rstd);
+    if (stats && lane == 0) stats[row] = make_float2(mean, rstd);  // lets a consumer re-derive LN(in) without the fp32 copy
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float g8[8], b8[8];
+      load8<float>(w + (i * 32 + lane) * 8, g8);
+      load8<float>(b + (i * 32 + lane) * 8, b8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[r][i][j] = (v[r][i][j] - mean) * rstd * g8[j] + b8[j];
+    }
+    if (out32) store_row<float, VPL>(out32 + static_cast<size_t>(row) * H, lane, v[r]);
+    if (outT) store_row<T, VPL>(outT + static_cast<size_t>(row) * H, lane, v[r]);
   }
-  if (out32) store_row<float, VPL>(out32 + static_cast<size_t>(row) * H, lane, v);
-  if (outT) store_row<T, VPL>(outT + static_cast<size_t>(row) * H, lane, v);
 }
 
 template <typename T>
 int layernorm(const float* in, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT, float2* stats, cudaStream_t s) {
-  const int grid = ceil_div(M * 32, kRowThreads);
-  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_kernel<T, VPL>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, w, b, eps, out32, outT, stats)));
+  // launch shape: SEQDIFF_LN_VAR = threads per CTA * 10 + rows per warp (sweep on B200: profiles/ln_sweep_r01.log)
+  static const int var = [] { const char* e = getenv("SEQDIFF_LN_VAR"); return e ? atoi(e) : 2561; }();
+#define SD_LN_LAUNCH(TH_, RPW_)                                                                                                           \
+  {                                                                                                                                       \
+    const int grid = ceil_div(ceil_div(M, RPW_) * 32, TH_);                                                                               \
+    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_kernel<T, VPL, TH_, RPW_>, dim3(grid), dim3(TH_), 0, s, in, M, H, w, b, eps, out32, outT, stats))); \
+  }
+  switch (var) {
+    case 1281: SD_LN_LAUNCH(128, 1); break;
+    case 5121: SD_LN_LAUNCH(512, 1); break;
+    case 2562: SD_LN_LAUNCH(256, 2); break;
+    case 1282: SD_LN_LAUNCH(128, 2); break;
+    case 641: SD_LN_LAUNCH(64, 1); break;
+    default: SD_LN_LAUNCH(256, 1); break;
+  }
+#undef SD_LN_LAUNCH
   SD_LAUNCHED("layernorm", s);
   return SEQDIFF_OK;
 }

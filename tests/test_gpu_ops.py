@@ -397,3 +397,24 @@ def test_reverse_step_cfg3_size_properties():
                           True, False, E.view(B, L, 20)[sl].reshape(-1, 20).cpu())
     prob = O.reverse_step_probs((s[sl] + 1) / T, s[sl] / T, x[sl].cpu(), logits[sl].cpu(), O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition())
     assert_indices_match(a[sl].argmax(-1), want.argmax(-1), prob / E.view(B, L, 20)[sl].reshape(-1, 20).cpu(), "cfg3 slice")
+
+
+@pytest.mark.parametrize("M,H", [(1, 768), (77, 768), (8192, 768), (300, 256), (129, 1024)])
+def test_layernorm_op(M, H):
+    """seqdiff_op_layernorm == F.layer_norm (fp32 exactly to rounding; 16-bit outputs to one operand ulp); statistics = (mean, rstd)."""
+    sd = sd_pkg()
+    lib = sd.lib()
+    g = torch.Generator().manual_seed(M + H)
+    x = (torch.randn(M, H, generator=g) * 3 + 0.5).to(DEV)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(H, generator=g)).to(DEV)
+    ref = F.layer_norm(x, (H,), w, b, 1e-12)
+    y32 = torch.empty(M, H, device=DEV)
+    st = torch.empty(M, 2, device=DEV)
+    _check(lib.seqdiff_op_layernorm(FP32, M, H, _p(x), _p(w), _p(b), 1e-12, _p(y32), None, _p(st), stream_ptr()))
+    assert (y32 - ref).abs().max().item() < 2e-5
+    assert torch.allclose(st[:, 0], x.mean(1), atol=1e-5) and torch.allclose(st[:, 1], 1 / torch.sqrt(x.var(1, unbiased=False) + 1e-12), rtol=1e-4)
+    for prec, dt, tol in ((BF16, torch.bfloat16, 2 ** -8), (FP16, torch.float16, 2 ** -11)):
+        y16 = torch.empty(M, H, device=DEV, dtype=dt)
+        _check(lib.seqdiff_op_layernorm(prec, M, H, _p(x), _p(w), _p(b), 1e-12, None, _p(y16), None, stream_ptr()))
+        assert ((y16.float() - ref).abs() <= tol * ref.abs() + 1e-5).all()
