@@ -185,19 +185,18 @@ __global__ void __launch_bounds__(kLossThreads) loss_terms_kernel(int N, const f
 
 int loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* mask, double* terms, cudaStream_t s) {
   SD_CHECK(N > 0, "empty loss");
-  // scratch: per-CTA partials + arrival counter, one per device, grown never (fixed CTA cap)
-  static thread_local double* scratch[64] = {};
-  int dev = 0;
-  SD_CUDA(cudaGetDevice(&dev));
-  SD_CHECK(dev >= 0 && dev < 64, "device index out of range");
-  if (!scratch[dev]) {
-    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch[dev]), (kLossMaxCtas * kLossTerms + 2) * sizeof(double)));
-    SD_CUDA(cudaMemset(scratch[dev], 0, (kLossMaxCtas * kLossTerms + 2) * sizeof(double)));
-  }
+  // per-CTA partials + arrival counter: stream-ordered scratch, so concurrent calls on different streams never share it
   int ctas = ceil_div(N, kLossThreads);
   if (ctas > kLossMaxCtas) ctas = kLossMaxCtas;
-  unsigned* arrive = reinterpret_cast<unsigned*>(scratch[dev] + kLossMaxCtas * kLossTerms);
-  SD_CUDA(launch_k(loss_terms_kernel, dim3(ctas), dim3(kLossThreads), 0, s, N, logits, x0, x_t, mask, scratch[dev], arrive, terms));
+  const size_t bytes = (static_cast<size_t>(ctas) * kLossTerms + 2) * sizeof(double);
+  double* scratch = nullptr;
+  SD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, s));
+  unsigned* arrive = reinterpret_cast<unsigned*>(scratch + static_cast<size_t>(ctas) * kLossTerms);
+  cudaError_t e = cudaMemsetAsync(arrive, 0, 2 * sizeof(double), s);
+  if (e == cudaSuccess) e = launch_k(loss_terms_kernel, dim3(ctas), dim3(kLossThreads), 0, s, N, logits, x0, x_t, mask, scratch, arrive, terms);
+  const cudaError_t ef = cudaFreeAsync(scratch, s);
+  SD_CUDA(e);
+  SD_CUDA(ef);
   SD_LAUNCHED("loss_terms", s);
   return SEQDIFF_OK;
 }

@@ -125,7 +125,7 @@ int philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, u
 int decode_sequences(int B, int L, const float* final_seq, const float* true_seq, const float* mask, uint8_t* pred_idx, uint8_t* true_idx,
                      int* counts, cudaStream_t s);
 // model.py:313-345 + utils.py:132-161: the ten reduction terms documented at seqdiff_loss_terms (include/seqdiff_b200.h).
-// One call in flight per (host thread, device): the per-CTA partials live in a per-thread scratch buffer.
+// The per-CTA partials live in stream-ordered scratch (cudaMallocAsync / cudaFreeAsync on `s`).
 int loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* mask, double* terms, cudaStream_t s);
 
 // ---- gauss_step.cu ----------------------------------------------------------------------------------
