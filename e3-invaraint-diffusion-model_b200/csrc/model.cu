@@ -73,11 +73,18 @@ int profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap) {
   return n;
 }
 
+// Programmatic dependent launch.  SEQDIFF_PDL=1 / 0 forces it on / off for every launch.  Unset: off for the sequence path -- measured on
+// B200 inside the replayed CUDA graph it changes the cfg-2 step by -1.8 .. +1 % (the kernels of consecutive nodes cannot co-reside: the
+// persistent GEMM / attention CTAs own the SM's shared memory) -- and ON for the structure model, whose M = 4096 steps are launch / ramp
+// bound (146 kernels of ~10 us): +2.5 .. 2.7 % there (profiles/struct_bench_r01.json vs gpurun A/B).
+static thread_local int g_pdl_scope = 0;
+struct PdlScope {
+  PdlScope() { ++g_pdl_scope; }
+  ~PdlScope() { --g_pdl_scope; }
+};
 bool pdl_enabled() {
-  // measured on B200 (round 1): inside the replayed CUDA graph PDL changes the step time by < 1 % (27.2 k vs 27.7 k
-  // graph-steps/s) -- the graph already hides launch latency -- so it is opt-in: SEQDIFF_PDL=1
-  static const bool v = [] { const char* e = getenv("SEQDIFF_PDL"); return e && e[0] == '1'; }();
-  return v;
+  static const int env = [] { const char* e = getenv("SEQDIFF_PDL"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+  return env >= 0 ? env == 1 : g_pdl_scope > 0;
 }
 
 int num_sms() {
@@ -986,6 +993,7 @@ int Model::struct_forward(int precision, int B, int Ll, int Lr, const float* tim
                           int phases, cudaStream_t s) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
   SD_CHECK(arch == kArchStructure, "handle holds a sequence model: use seqdiff_forward");
+  const PdlScope pdl_on;  // launch-bound path: programmatic dependent launch unless SEQDIFF_PDL=0
   SD_CHECK(precision >= SEQDIFF_FP32 && precision <= SEQDIFF_FP16, "unknown precision mode");
   SD_CHECK(B > 0 && Ll > 0 && Lr > 0, "empty batch");
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
@@ -1008,6 +1016,7 @@ int Model::struct_sample(int precision, int B, int Ll, int Lr, int T, const floa
                          uint64_t gid0, float* steps_out, float* final_out, cudaStream_t caller) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
   SD_CHECK(arch == kArchStructure, "handle holds a sequence model: use seqdiff_sample");
+  const PdlScope pdl_on;
   SD_CHECK(T >= 1 && B > 0 && Ll > 0 && Lr > 0, "bad sampling arguments");
   SD_CUDA(cudaSetDevice(device));
   if (!loop_stream) {
