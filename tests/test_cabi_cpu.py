@@ -114,3 +114,21 @@ def test_sample_dataset_output_format(tmp_path):
     assert list(df["structure_ids"]) == ["1abc_A", "2xyz_B", "3pqr_C"]
     back = pd.read_pickle(out)
     assert back.equals(df) and len(back) == 3
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/seqdiff_b200.h is the boundary a non-Python host binds: it must compile as C99 and a C program must link against the
+    shared library (no C++ / torch types in the signatures)."""
+    import shutil
+    import subprocess
+    import seqdiff_b200 as sd
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hc.c"
+    src.write_text('#include "seqdiff_b200.h"\nint main(void) { return seqdiff_abi_version() != SEQDIFF_ABI_VERSION; }\n')
+    libdir = os.path.dirname(sd._cabi.LIB_PATH)
+    exe = tmp_path / "hc"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir,
+                        "-l:libseqdiff_b200.so", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
