@@ -22,6 +22,7 @@ from .model import (BertEmbeddings, BertEncoder, ConditionalBertForDiffusionBase
 
 SEED = 0          # Philox seed of the in-kernel N(0,1) stream (explicit `noise` tensors override it)
 STEP = 1          # structure_model/sample.py:14; only the reference default is implemented
+CONFIG = {"batch_size": 64, "timesteps": 1000, "max_seq_len": 64, "pocket_ext": 0}  # the keys sample() reads (sample.py:19-41)
 
 
 # ---- structure_model/utils.py --------------------------------------------------------------------------------------
@@ -236,3 +237,36 @@ def p_sample_loop(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor
                                                       _cabi.ptr(rs), _cabi.ptr(ra), _cabi.ptr(rm), _cabi.ptr(z), SEED if seed is None else seed,
                                                       graph_id0, _cabi.ptr(hist), _cabi.ptr(final), stream))
     return (hist if keep_history else final[None]).cpu()
+
+
+def sample(model, test_angle_ds, first_batch_only: bool = True, loop_fn=None, **kw):
+    """reference structure_model/sample.py:191-229: chunk the dataset's features into batches of CONFIG["batch_size"], draw the start
+    noise with the dataset's own `sample_noise`, run `p_sample_loop`, and trim every complex to its ligand length -> a list of numpy
+    arrays [timesteps, len_i, n_ft].  `test_angle_ds` is duck-typed like the reference's NoisedAnglesDataset (`__len__`,
+    `__getitem__` -> dict of tensors, `sample_noise`, `timesteps`, `alpha_beta_terms["betas"]`).  The reference stops after the
+    first batch (the `break` at sample.py:228); `first_batch_only=False` samples the whole dataset."""
+    fn = p_sample_loop if loop_fn is None else loop_fn
+    bs = CONFIG["batch_size"]
+
+    def chunkify_features(feature_name):
+        feats = [test_angle_ds[i][feature_name] for i in range(len(test_angle_ds))]
+        return [torch.stack(feats[i:i + bs]) for i in range(0, len(test_angle_ds), bs)]
+
+    ligand_mask = chunkify_features("ligand_attn_mask")
+    receptor_angle = chunkify_features("receptor_angles")
+    receptor_seq = chunkify_features("receptor_seq")
+    receptor_mask = chunkify_features("receptor_attn_mask")
+    pad, feature_size = test_angle_ds[0]["ligand_angles"].shape
+    ligand_len = [m.sum(dim=1).int() for m in ligand_mask]
+    retval = []
+    for idx, this_lengths in enumerate(ligand_len):
+        print(f"Generating Batch {idx}/{len(ligand_len)}")
+        batch = len(this_lengths)
+        noise = test_angle_ds.sample_noise(torch.zeros((batch, pad, feature_size), dtype=torch.float32))
+        sampled = fn(model=model, ligand_mask=ligand_mask[idx], ligand_angle_noise=noise, receptor_seq=receptor_seq[idx],
+                     receptor_mask=receptor_mask[idx], receptor_angle=receptor_angle[idx], total_timesteps=test_angle_ds.timesteps,
+                     betas=test_angle_ds.alpha_beta_terms["betas"], disable_pbar=False, **kw)
+        retval.extend(sampled[:, i, :int(l), :].numpy() for i, l in enumerate(this_lengths))
+        if first_batch_only:
+            break
+    return retval

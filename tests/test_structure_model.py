@@ -117,6 +117,47 @@ def test_struct_mirror_schema_and_signatures():
         m.eval()(z(1), z(1, 128, 8), torch.ones(1, 128), z(1, 128, 20), z(1, 128, 8), torch.ones(1, 128))
 
 
+def test_struct_sample_driver_trims_and_batches():
+    """reference structure_model/sample.py:191-229 with an injected loop (no GPU): batches of CONFIG["batch_size"], the dataset's own
+    start noise, per-complex trimming to the ligand length, and the reference's stop-after-first-batch quirk."""
+    import seqdiff_b200 as sd
+    SM = sd.structure_model
+
+    class DS:
+        timesteps = 3
+        alpha_beta_terms = {"betas": SM.cosine_beta_schedule(3)}
+
+        def __len__(self):
+            return 5
+
+        def __getitem__(self, i):
+            n = 2 + i
+            m = (torch.arange(8) < n).float()
+            return {"ligand_attn_mask": m, "ligand_angles": torch.zeros(8, 4), "receptor_angles": torch.zeros(8, 4), "receptor_seq": torch.zeros(8, 20),
+                    "receptor_attn_mask": torch.ones(8)}
+
+        def sample_noise(self, v):
+            return torch.full_like(v, 0.5)
+
+    calls = []
+
+    def fake_loop(model, ligand_mask, ligand_angle_noise, total_timesteps, **kw):
+        calls.append(ligand_angle_noise.shape[0])
+        return ligand_angle_noise[None].repeat(total_timesteps, 1, 1, 1) + torch.arange(total_timesteps).float()[:, None, None, None]
+
+    old = SM.CONFIG["batch_size"]
+    SM.CONFIG["batch_size"] = 2
+    try:
+        first = SM.sample(None, DS(), loop_fn=fake_loop)
+        assert calls == [2] and [a.shape for a in first] == [(3, 2, 4), (3, 3, 4)]   # reference quirk: first batch only
+        calls.clear()
+        every = SM.sample(None, DS(), first_batch_only=False, loop_fn=fake_loop)
+        assert calls == [2, 2, 1] and [a.shape[1] for a in every] == [2, 3, 4, 5, 6]
+        assert float(every[4][2, 0, 0]) == 2.5
+    finally:
+        SM.CONFIG["batch_size"] = old
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU: CUDA parity through the C ABI
 # ------------------------------------------------------------------------------------------------------------------
