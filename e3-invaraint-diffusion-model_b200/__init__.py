@@ -11,7 +11,7 @@ from .dataset import LigandBindingSiteDataset, collate_complexes  # noqa: F401
 from ._cabi import SeqdiffError, lib  # noqa: F401
 from .distributed import denoise_sharded, p_sample_loop_sharded, shard_batch, shard_bounds  # noqa: F401
 from .model import AA_VOCAB, BertConfig, ConditionalBertForDiffusionBase, PeptideDiff  # noqa: F401
-from .sample import decode_tensors, denoise, denoise_tensors, sample_dataset, generate_discrete_noise, sample_p_zs_given_zt_discrete  # noqa: F401
+from .sample import decode_tensors, denoise, denoise_tensors, denoise_with_generated_angles, load_generated_angles, sample_dataset, generate_discrete_noise, sample_p_zs_given_zt_discrete  # noqa: F401
 from .utils import BlosumTransition, DiscreteUniformTransition, PredefinedNoiseScheduleDiscrete  # noqa: F401
 
 __all__ = ["model", "sample", "utils", "structure_model", "lib", "SeqdiffError", "BertConfig", "ConditionalBertForDiffusionBase", "PeptideDiff",

@@ -184,10 +184,38 @@ def denoise(batch, model: PeptideDiff, noise_schedule, transition, diverse, **kw
     return structure_ids, true_sequences, pred_sequences, recovery_rates
 
 
-def sample_dataset(dataloader, model, noise_schedule=None, transition=None, diverse=True, output_path=None, denoise_fn=None, **kw):
+def load_generated_angles(angles, max_seq_len=None, batch_size=None):
+    """reference sample_by_generated_angles.py:54-66: per-complex angle arrays [len_i, 8] (a pickle path, or the list itself --
+    e.g. the last step of structure_model.sample()'s outputs) zero-padded to max_seq_len and chunked by batch_size."""
+    import pickle
+
+    import numpy as np
+    if isinstance(angles, (str, bytes)):
+        with open(angles, "rb") as f:
+            angles = pickle.load(f)
+    L = CONFIG["max_seq_len"] if max_seq_len is None else max_seq_len
+    bs = CONFIG["batch_size"] if batch_size is None else batch_size
+    padded = torch.Tensor(np.array([np.pad(np.asarray(a, dtype=np.float32), ((0, L - np.asarray(a).shape[0]), (0, 0)), mode="constant",
+                                           constant_values=0) for a in angles]))
+    return [padded[i:i + bs] for i in range(0, len(padded), bs)]
+
+
+def denoise_with_generated_angles(batch, generated_angles, model, noise_schedule, transition, diverse, denoise_fn=None, **kw):
+    """reference sample_by_generated_angles.py:197-245: `denoise` with the ligand angles replaced by the structure model's output
+    (line 202); the caller passes `DiscreteUniformTransition(20)` as the reference's main block does (line 253)."""
+    if tuple(generated_angles.shape) != tuple(batch["ligand_angles"].shape):
+        raise ValueError(f"generated angles {tuple(generated_angles.shape)} do not match the batch {tuple(batch['ligand_angles'].shape)}")
+    swapped = dict(batch)
+    swapped["ligand_angles"] = generated_angles
+    return (denoise if denoise_fn is None else denoise_fn)(swapped, model, noise_schedule, transition, diverse, **kw)
+
+
+def sample_dataset(dataloader, model, noise_schedule=None, transition=None, diverse=True, output_path=None, denoise_fn=None,
+                   generated_angles=None, **kw):
     """The `__main__` block of the reference (sample.py:231-257): every batch of `dataloader` through `denoise`, results
     collected in the reference's DataFrame (columns structure_ids / true_sequence / predict_sequence / recovery_rate) and, when
-    `output_path` is given, pickled exactly like `res.to_pickle(OUTPUT_PATH)`.  Returns the DataFrame."""
+    `output_path` is given, pickled exactly like `res.to_pickle(OUTPUT_PATH)`.  Returns the DataFrame.  `generated_angles` (chunks
+    from `load_generated_angles`) turns it into the main block of sample_by_generated_angles.py:247-278."""
     import pandas as pd
     if noise_schedule is None:
         noise_schedule = PredefinedNoiseScheduleDiscrete(CONFIG["noise_schedule"], CONFIG["timesteps"])
@@ -197,7 +225,11 @@ def sample_dataset(dataloader, model, noise_schedule=None, transition=None, dive
     structure_ids, true_sequences, pred_sequences, recovery_rates = [], [], [], []
     for idx, batch in enumerate(dataloader):
         print(f"Generating Batch {idx}")
-        ids, true_seq, pred_seq, rec_rates = fn(batch, model, noise_schedule, transition, diverse, **kw)
+        if generated_angles is not None:  # sample_by_generated_angles.py:260-265
+            ids, true_seq, pred_seq, rec_rates = denoise_with_generated_angles(batch, generated_angles[idx], model, noise_schedule, transition,
+                                                                               diverse, denoise_fn=fn, **kw)
+        else:
+            ids, true_seq, pred_seq, rec_rates = fn(batch, model, noise_schedule, transition, diverse, **kw)
         structure_ids.extend(ids)
         recovery_rates.extend(rec_rates)
         pred_sequences.extend(pred_seq)

@@ -132,3 +132,33 @@ def test_header_is_plain_c_and_links(tmp_path):
                         "-l:libseqdiff_b200.so", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_generated_angles_pipeline_host_logic(tmp_path):
+    """reference sample_by_generated_angles.py:54-66,197-202,247-278: pad + chunk the structure model's per-complex angles, swap them
+    in as `ligand_angles`, same result table (sampler injected: no GPU here)."""
+    import pickle
+
+    import numpy as np
+    import seqdiff_b200 as sd
+    S = sd.sample
+    arrays = [np.full((n, 8), float(n), dtype=np.float32) for n in (3, 5, 2)]
+    pk = tmp_path / "angles.pkl"
+    pk.write_bytes(pickle.dumps(arrays))
+    chunks = S.load_generated_angles(str(pk), max_seq_len=6, batch_size=2)
+    assert [tuple(c.shape) for c in chunks] == [(2, 6, 8), (1, 6, 8)]
+    assert chunks[0][1, 4, 0] == 5 and chunks[0][1, 5, 0] == 0 and chunks[0][0, 3, 0] == 0
+    assert torch.equal(S.load_generated_angles(arrays, 6, 2)[1], chunks[1])
+    seen = []
+
+    def fake(batch, model, sched, trans, diverse, **kw):
+        seen.append(batch["ligand_angles"].clone())
+        n = batch["ligand_angles"].shape[0]
+        return [f"id{len(seen)}_{i}" for i in range(n)], ["A"] * n, ["C"] * n, [0.0] * n
+
+    loader = [{"ligand_angles": torch.zeros(2, 6, 8), "ligand_seq": torch.zeros(2, 6, 20)}, {"ligand_angles": torch.zeros(1, 6, 8), "ligand_seq": torch.zeros(1, 6, 20)}]
+    df = S.sample_dataset(loader, None, noise_schedule=object(), transition=sd.DiscreteUniformTransition(20), denoise_fn=fake, generated_angles=chunks)
+    assert len(df) == 3 and torch.equal(seen[0], chunks[0]) and torch.equal(seen[1], chunks[1])
+    assert loader[0]["ligand_angles"].abs().sum() == 0  # the caller's batch is not modified
+    with pytest.raises(ValueError, match="do not match"):
+        S.denoise_with_generated_angles(loader[0], chunks[1], None, None, None, True, denoise_fn=fake)
