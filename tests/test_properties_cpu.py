@@ -82,3 +82,31 @@ def test_loss_terms_identities(seed):
     n_mask = batch["ligand_attn_mask"].sum().item()
     assert abs(nrate.item() - (1 - flip.sum().item() / n_mask)) < 1e-6
     assert ce_n.item() > 0 and ce_all.item() > 0 and elbo.item() > 0
+
+
+def test_padding_never_reaches_valid_rows():
+    """The exactness argument behind packing ragged batches: with the reference's -10000 key mask a padded key's
+    softmax weight underflows to exactly 0 and every other operator is row-local, so the logits of the VALID ligand rows of a padded
+    batch equal those of the same complex run alone at its true lengths (relative positions are within-graph, so nothing shifts)."""
+    L = 48
+    cfg = O.OracleConfig(max_position_embeddings=L, num_hidden_layers=2)
+    state = O.init_state_dict(cfg, 5, "B")
+    batch = O.synthetic_batch(3, L, (5, 30), (9, 48), 91)
+    x_t = O.generate_discrete_noise(3, L, generator=torch.Generator().manual_seed(92))
+    t = torch.full((3, 1), 13.0)
+    torch.set_num_threads(4)
+    with torch.no_grad():
+        padded = O.denoiser_forward(state, cfg, t, x_t, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                                    batch["receptor_angles"], batch["receptor_attn_mask"])
+        for b in range(3):
+            nl, nr = int(batch["ligand_attn_mask"][b].sum()), int(batch["receptor_attn_mask"][b].sum())
+            alone = O.denoiser_forward(state, cfg, t[b:b + 1], x_t[b:b + 1, :nl], batch["ligand_angles"][b:b + 1, :nl], torch.ones(1, nl),
+                                       batch["receptor_seq"][b:b + 1, :nr], batch["receptor_angles"][b:b + 1, :nr], torch.ones(1, nr))
+            assert alone.shape == (1, nl, 20)
+            assert (alone[0] - padded[b, :nl]).abs().max().item() < 2e-5 * padded[b, :nl].abs().max().item()
+            # and garbage in the padded ligand rows of x_t changes nothing on the valid rows
+            x_bad = x_t.clone()
+            x_bad[b, nl:] = torch.roll(x_t[b, nl:], 7, dims=-1)
+            again = O.denoiser_forward(state, cfg, t, x_bad, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                                       batch["receptor_angles"], batch["receptor_attn_mask"])
+            assert torch.equal(again[b, :nl], padded[b, :nl])
