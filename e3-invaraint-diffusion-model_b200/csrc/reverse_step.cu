@@ -438,14 +438,29 @@ __global__ void __launch_bounds__(kRevThreads) apply_aa_noise_kernel(const float
       const float4 c4 = *reinterpret_cast<const float4*>(x0 + n * C + j4);
       xr[j4] = c4.x; xr[j4 + 1] = c4.y; xr[j4 + 2] = c4.z; xr[j4 + 3] = c4.w;
     }
+    // one-hot row (what the dataset holds): prob[i] = Qtb[i, hot] -- a column read, the same value the dot product gives
+    // (1 * q + 0 * ... exactly); anything else takes the general dot product.  (The fully unrolled 400-term form for every row
+    // needed 255 registers and 792 B of spills.)
+    int hot = -1, nnz = 0;
+#pragma unroll
+    for (int k = 0; k < C; ++k)
+      if (xr[k] != 0.f) { ++nnz; hot = (xr[k] == 1.0f) ? k : -2; }
     float prob[C], psum = 0.f;
+    if (nnz == 1 && hot >= 0) {
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-      float a = 0.f;
+      for (int i = 0; i < C; ++i) {
+        prob[i] = sQ[i * C + hot];
+        psum += prob[i];
+      }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < C; ++i) {
+        float a = 0.f;
 #pragma unroll
-      for (int k = 0; k < C; ++k) a = fmaf(sQ[i * C + k], xr[k], a);  // exact for one-hot rows
-      prob[i] = a;
-      psum += a;
+        for (int k = 0; k < C; ++k) a = fmaf(sQ[i * C + k], xr[k], a);
+        prob[i] = a;
+        psum += a;
+      }
     }
     int idx = 0;
     if (psum != 0.f) {
