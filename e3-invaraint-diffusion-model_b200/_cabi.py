@@ -105,6 +105,28 @@ def profile(fn, stream=None):
     return {tags.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
 
+class _GraphIds:
+    """Position of this process in the global stream of in-kernel sampling noise.  The Philox noise of the samplers is keyed by
+    (seed, GLOBAL graph id, residue / element, step); every stochastic call that is not handed an explicit `graph_id0` takes the
+    next block of ids from here, so consecutive batches / repeated calls draw fresh noise (as the reference does from torch's
+    global generator) while one cached CUDA graph keeps serving them (the key lives in device memory).  Sharded front ends take
+    ONE block for the whole batch on every rank, which keeps the ranks' counters in step."""
+
+    def __init__(self):
+        self.next = 0
+
+    def take(self, n: int) -> int:
+        lo = self.next
+        self.next += int(n)
+        return lo
+
+    def reset(self, value: int = 0):
+        self.next = int(value)
+
+
+GRAPH_IDS = _GraphIds()
+
+
 def ptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else C.c_void_p(t.data_ptr())

@@ -20,6 +20,7 @@
 
 namespace seqdiff {
 
+#ifdef SEQDIFF_AB_KERNELS  // legacy mma.sync kernel: A/B reference only (see attention_any16 below)
 // ---------------------------------------------------------------------------------------------------
 // small PTX helpers
 // ---------------------------------------------------------------------------------------------------
@@ -341,9 +342,12 @@ static int attention_16(int B, int heads, int Lq, int Lk, const T* q, int ldq, c
   SD_ATTN(false);
 #undef SD_ATTN
 }
-// 16-bit modes.  Default: the persistent pipelined tcgen05 kernel (attention_pipe.cu) for every shape.  SEQDIFF_ATTN =
-// pipe | tc | mma forces one implementation (A/B knob); "tc" = one-item-per-CTA tcgen05 kernel (attention_tc.cu), "mma" = the
-// legacy mma.sync kernel above.  Measured at cfg 2 (ms of attention per forward): mma 0.37 + tc 0.16 -> see profiles/.
+#endif  // SEQDIFF_AB_KERNELS
+
+// 16-bit modes: the persistent pipelined tcgen05 kernel (attention_pipe.cu) for every shape.  The two kernels it superseded --
+// the one-item-per-CTA tcgen05 kernel (attention_tc.cu) and the mma.sync kernel above -- are A/B references only: they are
+// compiled in when the library is built with SEQDIFF_AB_KERNELS=1 (build.py) and then selectable with SEQDIFF_ATTN = tc | mma.
+#ifdef SEQDIFF_AB_KERNELS
 static int attn_choice() {
   static const int v = [] {
     const char* e = getenv("SEQDIFF_ATTN");
@@ -353,15 +357,20 @@ static int attn_choice() {
   }();
   return v;
 }
+#endif
 template <typename T>
 static int attention_any16(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
                            int P, const float* key_mask, T* out, cudaStream_t s) {
+#ifdef SEQDIFF_AB_KERNELS
   const int c = attn_choice();
-  if (c == 0) return attention_pipe<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
-  // "auto_r1": the per-shape choice before the pipelined kernel existed (legacy for one-key-block relative_key, tc otherwise)
-  const bool legacy = c == 2 || (c == 3 && dist_emb != nullptr && Lk <= kKB);
-  if (legacy) return attention_16<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
-  return attention_tc<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  if (c != 0) {
+    // "auto_r1": the per-shape choice before the pipelined kernel existed (legacy for one-key-block relative_key, tc otherwise)
+    const bool legacy = c == 2 || (c == 3 && dist_emb != nullptr && Lk <= kKB);
+    if (legacy) return attention_16<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+    return attention_tc<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  }
+#endif
+  return attention_pipe<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
 }
 template <>
 int attention<bf16>(int B, int heads, int Lq, int Lk, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv,

@@ -54,13 +54,18 @@ __device__ __forceinline__ float gauss_update(float x, float out, float a, float
 }
 
 // One thread per group of 4 consecutive elements of one graph (per = L * F elements per graph, groups = ceil(per / 4)).
-__global__ void __launch_bounds__(kGaussThreads) gauss_step_kernel(const float* __restrict__ coef, int T, int per, const float* __restrict__ x_t,
+__global__ void __launch_bounds__(kGaussThreads) gauss_step_kernel(const float* __restrict__ coef, int T, int per, const float* x_t,
                                                                    const float* __restrict__ model_out, const float* __restrict__ noise,
                                                                    uint64_t seed, uint64_t graph_id0, int step, const int* __restrict__ step_ptr,
-                                                                   float* __restrict__ x_out, float* __restrict__ steps_out,
-                                                                   int* __restrict__ advance, int wrap) {
+                                                                   float* x_out, float* __restrict__ steps_out,
+                                                                   int* __restrict__ advance, int wrap, const uint64_t* __restrict__ rng) {
+  // x_t / x_out carry no __restrict__: the sampling loop updates the angles in place (each thread reads its 4 elements before it writes them)
   pdl_trigger();
   pdl_wait();
+  if (rng) {  // sampling loop: (seed, first global graph id) from device memory -- a cached CUDA graph serves every call
+    seed = rng[0];
+    graph_id0 = rng[1];
+  }
   const size_t n_all = static_cast<size_t>(gridDim.y) * per;
   if (step_ptr) {  // sampling loop: the step index lives on the device; the last CTA to have read it moves it on
     __shared__ int s_sidx;
@@ -134,13 +139,14 @@ __global__ void __launch_bounds__(kGaussThreads) gauss_step_kernel(const float* 
 }
 
 int gauss_step(const float* coef, int T, int B, int per_graph, const float* x_t, const float* model_out, const float* noise, uint64_t seed,
-               uint64_t graph_id0, int step, const int* step_ptr, float* x_out, float* steps_out, cudaStream_t s, int* advance, bool wrap) {
+               uint64_t graph_id0, int step, const int* step_ptr, float* x_out, float* steps_out, cudaStream_t s, int* advance, bool wrap,
+               const uint64_t* rng) {
   SD_CHECK(B > 0 && per_graph > 0 && T > 0, "empty Gaussian reverse step");
   SD_CHECK(step_ptr != nullptr || (step >= 0 && step < T), "step index out of range");
   const int groups = (per_graph + 3) / 4;
   const dim3 grid(ceil_div(groups, kGaussThreads), B);
   SD_CUDA(launch_k(gauss_step_kernel, dim3(grid), dim3(kGaussThreads), 0, s, coef, T, per_graph, x_t, model_out, noise, seed, graph_id0, step, step_ptr,
-                   x_out, steps_out, advance, wrap ? 1 : 0));
+                   x_out, steps_out, advance, wrap ? 1 : 0, rng));
   SD_LAUNCHED("gauss_step", s);
   return SEQDIFF_OK;
 }

@@ -113,9 +113,12 @@ int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const 
 // no-op when *step_ptr == 0 (last step returns the raw logits, sample.py:147-148).
 int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_t, const float* logits, int diverse,
                  const float* noise_E, uint64_t seed, uint64_t graph_id0, uint32_t step, const int* step_ptr, float* x_s,
-                 uint8_t* idx_out, cudaStream_t s, int* advance = nullptr);
+                 uint8_t* idx_out, cudaStream_t s, int* advance = nullptr, const uint64_t* rng = nullptr);
 // advance != NULL (with step_ptr): advance[0] is a zeroed arrival counter; the last CTA to have read *step_ptr decrements it
 // (replaces a separate step_advance launch in the sampling loop)
+// rng != NULL: device pointer to (seed, graph_id0), overriding the by-value arguments (kernel parameters are frozen into a captured
+// CUDA graph; device memory is not, so one cached graph serves calls with different seeds / graph offsets).
+// In-place contract: x_s may alias x_t (the loop does that) -- every thread reads its own 20-float row completely before writing it.
 int apply_aa_noise(const float* qtb, int B, int L, const float* x0, const float* noise_E, uint64_t seed, uint64_t graph_id0,
                    uint32_t step, float* x_t, uint8_t* idx_out, cudaStream_t s);
 int philox_u32(uint64_t seed, uint64_t graph_id0, uint32_t step, int B, int L, uint32_t* out, cudaStream_t s);
@@ -135,6 +138,7 @@ int loss_terms(int N, const float* logits, const float* x0, const float* x_t, co
 // in-kernel Philox + Box-Muller.  step_ptr / advance as in reverse_step().  steps_out (optional) [T, B*per_graph]: the result
 // is also stored at entry T-1-step (the reference's per-step history).  wrap = false: p_sample's un-wrapped value.
 int gauss_step(const float* coef, int T, int B, int per_graph, const float* x_t, const float* model_out, const float* noise, uint64_t seed,
-               uint64_t graph_id0, int step, const int* step_ptr, float* x_out, float* steps_out, cudaStream_t s, int* advance = nullptr, bool wrap = true);
+               uint64_t graph_id0, int step, const int* step_ptr, float* x_out, float* steps_out, cudaStream_t s, int* advance = nullptr, bool wrap = true,
+               const uint64_t* rng = nullptr);  // rng / in-place (x_out == x_t) as in reverse_step()
 
 }  // namespace seqdiff

@@ -151,6 +151,16 @@ __global__ void set_int_kernel(int* p, int v) {
   pdl_wait();
   *p = v;
 }
+// arms one sampling: step counter, arrival counter and the Philox key (seed, first global graph id) -- all read from device memory
+// by the captured step graph, so the graph does not depend on them
+__global__ void arm_loop_kernel(int* step, int v, uint64_t* rng, uint64_t seed, uint64_t gid0) {
+  pdl_trigger();
+  pdl_wait();
+  step[0] = v;
+  step[1] = 0;
+  rng[0] = seed;
+  rng[1] = gid0;
+}
 
 // =====================================================================================================
 Model::~Model() {
@@ -683,6 +693,18 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   SD_TRY(se_layer<T>(*this, wfmt, se_dec, h, teT, B, Ll, Ml, lseg, sb, x, s));
 
   // AminoAcidPredictor (model.py:148-153)
+  if constexpr (std::is_same<T, bf16>::value) {
+    // bf16 mode: the output head runs on fp16 operands (same tensor-core rate).  Its input is the fp32 residual stream out of
+    // decoder_normalize (bounded: LayerNorm-scale values), so fp16's 11-bit mantissa is safe and buys back the single most
+    // sensitive rounding of the network: dense1's weights + its GELU output are 2 % of the FLOPs but ~15-20 % of the bf16 logit
+    // error variance (profiles/bf16_attribution_r02.txt).  Everything upstream stays bf16.
+    f16* xh = reinterpret_cast<f16*>(sb.ctx);  // free at this point: [Ml, H] 16-bit
+    f16* yh = reinterpret_cast<f16*>(y);
+    SD_TRY(f32_to_16<f16>(x.s, static_cast<size_t>(Ml) * H, xh, s));
+    SD_TRY(gemm_16(Ml, H, H, xh, 0, p1.g, 0, p1_b, nullptr, 1, yh, 0, s));
+    SD_TRY(predictor_tail<f16>(yh, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, logits, s));
+    return SEQDIFF_OK;
+  }
   SD_TRY(gemm_T(wfmt, Ml, H, H, x.t, p1, p1_b, 1, y, s));
   SD_TRY(predictor_tail<T>(y, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, logits, s));
   return SEQDIFF_OK;
@@ -716,6 +738,8 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
                   const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t caller) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
   SD_CHECK(T >= 1 && B > 0 && Ll > 0 && Lr > 0, "bad sampling arguments");
+  SD_CHECK(cfg.feature_size == SEQDIFF_NUM_CLASSES, "sampling needs feature_size == 20");
+  SD_CUDA(cudaSetDevice(device));  // before the stream / events are created: they belong to the handle's device
   if (!loop_stream) {
     SD_CUDA(cudaStreamCreateWithFlags(&loop_stream, cudaStreamNonBlocking));
     SD_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
@@ -725,8 +749,6 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
   cudaStream_t s = loop_stream;
   SD_CUDA(cudaEventRecord(ev_in, caller));
   SD_CUDA(cudaStreamWaitEvent(s, ev_in, 0));
-  SD_CHECK(cfg.feature_size == SEQDIFF_NUM_CLASSES, "sampling needs feature_size == 20");
-  SD_CUDA(cudaSetDevice(device));
   const size_t Nl = static_cast<size_t>(B) * Ll, Nr = static_cast<size_t>(B) * Lr;
   // persistent inputs: x_cur | logits | lig_angle | lig_mask | rec_seq | rec_angle | rec_mask
   const size_t need_in = align256(Nl * 20 * 4) * 2 + align256(Nl * 8 * 4) + align256(Nl * 4) + align256(Nr * 20 * 4) +
@@ -761,10 +783,11 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
 
   GraphKey key;
   key.precision = precision; key.B = B; key.Ll = Ll; key.Lr = Lr; key.diverse = diverse; key.noise = noise_E;
-  key.seed = seed; key.gid0 = gid0; key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables;
+  key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables;  // (seed, gid0) are NOT part of the key: device memory, see arm_loop_kernel
+  uint64_t* d_rng = reinterpret_cast<uint64_t*>(d_step + 16);
   auto one_step = [&](cudaStream_t st) -> int {
     SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, st));
-    SD_TRY(reverse_step(d_tables, 1, B, Ll, x_cur, logits, diverse, noise_E, seed, gid0, 0, d_step, x_cur, nullptr, st, d_step + 1));
+    SD_TRY(reverse_step(d_tables, 1, B, Ll, x_cur, logits, diverse, noise_E, 0, 0, 0, d_step, x_cur, nullptr, st, d_step + 1, d_rng));
     return SEQDIFF_OK;
   };
   if (!graph_exec || !(key == graph_key)) {
@@ -787,8 +810,8 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
     SD_CUDA(ce);
     graph_key = key;
   }
-  SD_CUDA(launch_k(set_int_kernel, dim3(1), dim3(1), 0, s, d_step, T - 1));
-  SD_LAUNCHED("set_int", s);
+  SD_CUDA(launch_k(arm_loop_kernel, dim3(1), dim3(1), 0, s, d_step, T - 1, d_rng, seed, gid0));
+  SD_LAUNCHED("arm_loop", s);
   for (int it = 0; it < T; ++it) SD_CUDA(cudaGraphLaunch(graph_exec, s));
   g_launches.fetch_add(static_cast<uint64_t>(T) * graph_kernels, std::memory_order_relaxed);  // replayed kernel nodes
   SD_CUDA(cudaMemcpyAsync(final_out, logits, Nl * 20 * 4, cudaMemcpyDefault, s));
@@ -1059,15 +1082,16 @@ int Model::struct_sample(int precision, int B, int Ll, int Lr, int T, const floa
 
   GraphKey key;
   key.precision = precision; key.B = B; key.Ll = Ll; key.Lr = Lr; key.diverse = 0; key.noise = noise_steps;
-  key.seed = seed; key.gid0 = gid0; key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables; key.aux_ptr = steps_out; key.T = T;
+  key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables; key.aux_ptr = steps_out; key.T = T;
+  uint64_t* d_rng = reinterpret_cast<uint64_t*>(d_step + 16);
   // receptor branch once, eagerly (also the un-captured dry run that sets kernel attributes and fills the TMA descriptor cache)
-  SD_CUDA(launch_k(set_int_kernel, dim3(1), dim3(1), 0, s, d_step, T - 1));
-  SD_LAUNCHED("set_int", s);
+  SD_CUDA(launch_k(arm_loop_kernel, dim3(1), dim3(1), 0, s, d_step, T - 1, d_rng, seed, gid0));
+  SD_LAUNCHED("arm_loop", s);
   const bool cached = graph_exec && key == graph_key;
   SD_TRY(struct_forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lmask, c_rseq, c_rang, c_rmask, mout, cached ? 1 : 3, s));
   auto one_step = [&](cudaStream_t st) -> int {
     SD_TRY(struct_forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lmask, c_rseq, c_rang, c_rmask, mout, 2, st));
-    SD_TRY(gauss_step(d_tables, T, B, Ll * F, x_cur, mout, noise_steps, seed, gid0, 0, d_step, x_cur, steps_out, st, d_step + 1));
+    SD_TRY(gauss_step(d_tables, T, B, Ll * F, x_cur, mout, noise_steps, 0, 0, 0, d_step, x_cur, steps_out, st, d_step + 1, true, d_rng));
     return SEQDIFF_OK;
   };
   if (!cached) {

@@ -90,7 +90,6 @@ struct Model {
   struct GraphKey {
     int precision = -1, B = 0, Ll = 0, Lr = 0, diverse = 0;
     const float* noise = nullptr;
-    uint64_t seed = 0, gid0 = 0;
     const void* ws_ptr = nullptr;
     const void* in_ptr = nullptr;
     const void* tab_ptr = nullptr;
@@ -98,7 +97,7 @@ struct Model {
     int T = 0;
     bool operator==(const GraphKey& o) const {
       return aux_ptr == o.aux_ptr && T == o.T && precision == o.precision && B == o.B && Ll == o.Ll && Lr == o.Lr && diverse == o.diverse && noise == o.noise &&
-             seed == o.seed && gid0 == o.gid0 && ws_ptr == o.ws_ptr && in_ptr == o.in_ptr && tab_ptr == o.tab_ptr;
+             ws_ptr == o.ws_ptr && in_ptr == o.in_ptr && tab_ptr == o.tab_ptr;
     }
   } graph_key;
 

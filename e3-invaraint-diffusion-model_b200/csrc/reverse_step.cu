@@ -20,7 +20,7 @@
 //         expf, IEEE divides, product rounded then summed over i -- so indices agree bit for bit up to libm ulps;
 //   fast  (in-kernel Philox noise = production): there is no reference stream to reproduce, only a distribution, so the
 //         posterior uses FMA, ex2/lg2/rcp.approx and 128-bit table loads, and skips the two normalisations (an argmax race is
-//         invariant to positive row scaling).  Deviation of the race scores <= 1e-6 relative.  ncu (round 1): the exact path
+//         invariant to positive row scaling).  Deviation of the race scores <= ~3e-6 relative (pinned: tests/test_gpu_ops.py::test_reverse_step_philox_pinned_to_oracle).  ncu (round 1): the exact path
 //         costs 5075 thread-instructions per residue at 63 % issue utilisation -- the kernel is issue-bound, not HBM-bound.
 #include <cstdlib>
 
@@ -71,10 +71,23 @@ __device__ __forceinline__ float lg2_approx(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// 1 / (-log2 u): the Exp(1) variate up to the constant ln 2, inverted (the race only compares ratios)
+// 1 / (-log2 u): the Exp(1) variate up to the constant ln 2, inverted (the race only compares ratios).
+// lg2.approx has an ABSOLUTE error of 2^-22 on (0.5, 2), so near u = 1 (where -log2 u -> 0) its relative error explodes and the
+// result can even be 0 or change sign.  For v = 1 - u < 1/8 (exactly representable: u has 24 significant bits) the series
+//   -log2(1 - v) = log2(e) * v * (1 + v/2 + v^2/3 + ... + v^6/7)          (truncation < v^7/8 < 6e-8 relative)
+// is used instead; for v >= 1/8 the magnitude of lg2 is >= 0.19, i.e. <= 1.3e-6 relative.  Branch-free (select).
 __device__ __forceinline__ float inv_exp1_fast(uint32_t w) {
   const float u = (static_cast<float>(w >> 9) + 0.5f) * 1.1920928955078125e-07f;
-  return rcp_approx(-lg2_approx(u));
+  const float v = 1.0f - u;
+  float ser = fmaf(v, 1.0f / 7.0f, 1.0f / 6.0f);
+  ser = fmaf(ser, v, 0.2f);
+  ser = fmaf(ser, v, 0.25f);
+  ser = fmaf(ser, v, 1.0f / 3.0f);
+  ser = fmaf(ser, v, 0.5f);
+  ser = fmaf(ser, v, 1.0f);
+  const float near1 = ser * v * 1.44269504088896f;
+  const float e2 = v < 0.125f ? near1 : -lg2_approx(u);
+  return rcp_approx(e2);
 }
 
 // two fp32 FMAs in one instruction (FFMA2 on sm_100a): d = a * b + c on both halves.  Same rounding as two fmaf.
@@ -113,7 +126,7 @@ __device__ __forceinline__ void write_onehot(float* __restrict__ row, int idx) {
 // Kept out of line and fed from global/shared memory so that the hot path's per-class arrays stay in registers.
 //   left[j] = Qt[j,:].x ; den[i] = Qtb[i,:].x (0 -> 1e-6) ; un[j] = sum_i p_i * left[j] * Qsb[i,j] / den[i]
 template <bool FAST>
-__device__ __noinline__ int soft_row_class(const float* __restrict__ lg_row, const float* __restrict__ x_row, const float* sQt,
+__device__ __noinline__ int soft_row_class(const float* __restrict__ lg_row, const float* x_row, const float* sQt,
                                            const float* sQsb, const float* sQtb, bool diverse, const float* __restrict__ E_row, uint64_t seed,
                                            uint64_t graph, uint32_t l, uint32_t step) {
   float mx = lg_row[0];
@@ -159,12 +172,19 @@ __device__ __noinline__ int soft_row_class(const float* __restrict__ lg_row, con
 
 template <bool FAST, int THREADS = kRevThreads, int MINB = (FAST ? 2 : 1)>
 __global__ void __launch_bounds__(THREADS, MINB) reverse_step_kernel(const float* __restrict__ q_tables, int n_tab, int L,
-                                                                   const float* __restrict__ x_t, const float* __restrict__ logits,
+                                                                   const float* x_t, const float* __restrict__ logits,
                                                                    int diverse, const float* __restrict__ noise_E, uint64_t seed,
                                                                    uint64_t graph_id0, uint32_t step, const int* __restrict__ step_ptr,
-                                                                   float* __restrict__ x_s, uint8_t* __restrict__ idx_out, int* __restrict__ advance) {
+                                                                   float* x_s, uint8_t* __restrict__ idx_out, int* __restrict__ advance,
+                                                                   const uint64_t* __restrict__ rng) {
+  // x_t / x_s carry no __restrict__: the sampling loop runs the step IN PLACE (x_s == x_t; each thread reads its own row
+  // completely before it writes it -- the contract documented in kernels.h).
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
+  if (rng) {  // sampling loop: (seed, first global graph id) live in device memory so that a cached CUDA graph serves every call
+    seed = rng[0];
+    graph_id0 = rng[1];
+  }
   __shared__ float sQt[C * C], sQsb[C * C], sQtb[C * C];
   // exact mode: post[x][i][j] = Qt[j,x] Qsb[i,j] / Qtb[i,x] with the reference's rounding sequence, odd x-stride (401: lanes
   // holding different x_t classes read 32 different banks; stride 400 folded all classes onto 2 banks -- 16-way conflicts).
@@ -387,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, MINB) reverse_step_kernel(const float
 
 int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_t, const float* logits, int diverse,
                  const float* noise_E, uint64_t seed, uint64_t graph_id0, uint32_t step, const int* step_ptr, float* x_s,
-                 uint8_t* idx_out, cudaStream_t s, int* advance) {
+                 uint8_t* idx_out, cudaStream_t s, int* advance, const uint64_t* rng) {
   SD_CHECK(B > 0 && L > 0, "empty reverse step");
   SD_CHECK(n_tab == 1 || n_tab == B, "q_tables must hold 1 or B (Qt,Qsb,Qtb) triples");
   // launch shape of the production (fast) kernel: SEQDIFF_REV_CFG = threads per CTA * 100 + min CTAs per SM * 10 + residues per thread
@@ -398,7 +418,7 @@ int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_
   {                                                                                                                                         \
     const dim3 grid(ceil_div(L, (cfg % 10) * T_), B);                                                                                       \
     SD_CUDA(launch_k(reverse_step_kernel<true, T_, MB_>, dim3(grid), dim3(T_), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, \
-                     graph_id0, step, step_ptr, x_s, idx_out, advance));                                                                    \
+                     graph_id0, step, step_ptr, x_s, idx_out, advance, rng));                                                               \
   }
     SD_CHECK(cfg % 10 >= 1, "SEQDIFF_REV_CFG: residues per thread must be >= 1");
     switch (cfg / 10) {
@@ -413,7 +433,7 @@ int reverse_step(const float* q_tables, int n_tab, int B, int L, const float* x_
 #undef SD_REV_LAUNCH
   } else {
     const dim3 grid(ceil_div(L, 2 * kRevThreads), B);
-    SD_CUDA(launch_k(reverse_step_kernel<false>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out, advance));
+    SD_CUDA(launch_k(reverse_step_kernel<false>, dim3(grid), dim3(kRevThreads), 0, s, q_tables, n_tab, L, x_t, logits, diverse, noise_E, seed, graph_id0, step, step_ptr, x_s, idx_out, advance, rng));
   }
   SD_LAUNCHED("reverse_step", s);
   return SEQDIFF_OK;

@@ -9,13 +9,13 @@ import random
 from typing import Dict, List, Sequence
 
 import torch
-import torch.nn.functional as F
 
 from . import _cabi
 
 RANDOM_SEED = 0
 AA_VOCAB = "ACDEFGHIKLMNPQRSTVWY"
 SS_VOCAB = "HBEGITS-"
+_LUTS: Dict[str, Dict[str, int]] = {}
 
 
 def collate_complexes(records: Sequence[Dict], max_len: int, pocket_ext: int, device) -> Dict:
@@ -66,28 +66,35 @@ class LigandBindingSiteDataset(torch.utils.data.Dataset):
         self.pocket_ext = pocket_ext
         self.device = device
 
-    def _one_hot_encode(self, sequence, vocab):
-        indices = [vocab.index(char) for char in sequence]
-        return F.one_hot(torch.tensor(indices), num_classes=len(vocab)).float()
+    @staticmethod
+    def _one_hot_encode(sequence, vocab):
+        """letters -> [n, len(vocab)] one-hot f32 rows (a letter outside the vocabulary is a ValueError, as `str.index` raises)."""
+        lut = _LUTS.setdefault(vocab, {ch: i for i, ch in enumerate(vocab)})
+        try:
+            idx = torch.tensor([lut[ch] for ch in sequence], dtype=torch.long)
+        except KeyError as e:
+            raise ValueError(f"letter {e.args[0]!r} is not in the vocabulary {vocab!r}") from None
+        return torch.eye(len(vocab), dtype=torch.float32)[idx]
 
     def _split_data(self, split_name):
-        random.seed(RANDOM_SEED)
-        random.shuffle(self.data)
-        if split_name is not None:
-            split_idx = int(len(self.data) * 0.8)
-            if split_name == "train":
-                self.data = self.data[:split_idx]
-            elif split_name == "validation":
-                self.data = self.data[split_idx: split_idx + int(len(self.data) * 0.1)]
-            elif split_name == "test":
-                self.data = self.data[split_idx + int(len(self.data) * 0.1):]
+        """Deterministic 80 / 10 / 10 split (quirk Q12): the records are put in the order `random.seed(0); random.shuffle(data)`
+        produces -- drawn here from a private generator as an index permutation, so the process-wide `random` state is left alone --
+        and the named slice is kept (None or an unknown name keeps everything, like the reference)."""
+        order = list(range(len(self.data)))
+        random.Random(RANDOM_SEED).shuffle(order)
+        n_train, n_val = int(len(order) * 0.8), int(len(order) * 0.1)
+        bounds = {"train": (0, n_train), "validation": (n_train, n_train + n_val), "test": (n_train + n_val, len(order))}
+        lo, hi = bounds.get(split_name, (0, len(order)))
+        self.data = [self.data[i] for i in order[lo:hi]]
 
     def _load_file(self, filepath: str) -> None:
+        """`biolip.pt` = list of per-complex dicts (clean_data/data_preprocessing.py:882-893); the two letter sequences are
+        replaced by their one-hot encodings once, at load time."""
         print(f"Loading data from {filepath}")
         self.data = torch.load(filepath)
-        for d in self.data:
-            d["amino_acid"] = self._one_hot_encode("".join(d["amino_acid"]), AA_VOCAB)
-            d["secondary_structure"] = self._one_hot_encode("".join(d["secondary_structure"]), SS_VOCAB)
+        for rec in self.data:
+            for key, vocab in (("amino_acid", AA_VOCAB), ("secondary_structure", SS_VOCAB)):
+                rec[key] = self._one_hot_encode("".join(rec[key]), vocab)
 
     def __len__(self) -> int:
         return len(self.data)

@@ -53,19 +53,28 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
 def denoise_sharded(batch, model, noise_schedule, transition, diverse, denoise_fn: Callable = None, group=None, **kw):
     """Strong-scaling front end with the return contract of reference denoise() (sample.py:181-229): every rank
     samples its block of graphs on its own GPU, then the decoded (ids, true, pred, recovery) lists are
-    all-gathered in rank order, so each rank returns exactly what a single-GPU call on the whole batch returns."""
+    all-gathered in rank order, so each rank returns exactly what a single-GPU call on the whole batch returns:
+    the start state x_T of the WHOLE batch is drawn once (rank 0's `generate_discrete_noise`, broadcast as class indices --
+    a one-off B*L-byte exchange before the loop, not a data-path collective) unless the caller passes `x_T`, and the Philox
+    noise is keyed by global graph ids taken as ONE block from the process-wide stream on every rank."""
     import torch.distributed as dist
+    from . import _cabi
     if denoise_fn is None:
         from .sample import denoise as denoise_fn
     if not (dist.is_available() and dist.is_initialized()):
         return denoise_fn(batch, model, noise_schedule, transition, diverse, **kw)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    sub, gid0 = shard_batch(batch, world, rank)
+    n, L, C = batch["ligand_seq"].shape
+    sub, lo = shard_batch(batch, world, rank)
+    hi = lo + sub["ligand_seq"].shape[0]
     x_T = kw.pop("x_T", None)
-    if x_T is not None:
-        lo, hi = shard_bounds(batch["ligand_seq"].shape[0], world, rank)
-        kw["x_T"] = x_T[lo:hi]
-    gid0 += kw.pop("graph_id0", 0)
+    if x_T is None:
+        box = [torch.randint(0, C, (n, L)).to(torch.uint8) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        x_T = torch.nn.functional.one_hot(box[0].long(), C).float()
+    kw["x_T"] = x_T[lo:hi]
+    base = kw.pop("graph_id0", None)
+    gid0 = lo + (_cabi.GRAPH_IDS.take(n) if base is None else base)
     part = denoise_fn(sub, model, noise_schedule, transition, diverse, graph_id0=gid0, **kw) if sub["ligand_seq"].shape[0] else ([], [], [], [])
     parts = [None] * world
     dist.all_gather_object(parts, part, group=group)
@@ -93,7 +102,11 @@ def p_sample_loop_sharded(model, ligand_mask, ligand_angle_noise, receptor_seq, 
     noise_steps = kw.pop("noise_steps", None)
     if noise_steps is not None:
         kw["noise_steps"] = noise_steps[:, lo:hi]
-    gid0 = lo + kw.pop("graph_id0", 0)
+    base = kw.pop("graph_id0", None)
+    if base is None:
+        from . import _cabi
+        base = _cabi.GRAPH_IDS.take(n)
+    gid0 = lo + base
     part = None
     if hi > lo:
         part = sample_fn(model, ligand_mask[lo:hi], ligand_angle_noise[lo:hi], receptor_seq[lo:hi], receptor_mask[lo:hi],

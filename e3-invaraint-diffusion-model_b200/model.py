@@ -18,7 +18,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import _cabi
-from .utils import BlosumTransition, DiscreteUniformTransition, PredefinedNoiseScheduleDiscrete, elbo_loss, step_tables
+from .utils import BlosumTransition, DiscreteUniformTransition, PredefinedNoiseScheduleDiscrete, step_tables
 
 AA_VOCAB = "ACDEFGHIKLMNPQRSTVWY"
 
@@ -174,6 +174,15 @@ class ConditionalBertForDiffusionBase(nn.Module):
         self._handle = None
         self._handle_sig = None
         self._handle_dev = None
+        self._handle_tensors = None
+
+    def _apply(self, fn, recurse=True):
+        self._handle_tensors = None  # .to() / .float() / .cuda() may re-seat the tensors
+        return super()._apply(fn, recurse)
+
+    def load_state_dict(self, *a, **kw):
+        self._handle_tensors = None
+        return super().load_state_dict(*a, **kw)
 
     def initialize_weights(self):
         """reference model.py:183-198."""
@@ -207,12 +216,15 @@ class ConditionalBertForDiffusionBase(nn.Module):
         """(Re)uploads the weights into the C handle when any tensor of the state_dict changed."""
         lib = _cabi.lib()
         # the denoiser's own tensors only: PeptideDiff also registers the noise schedule's `betas` buffer (reference
-        # utils.py:216), which is host-side table data, not a weight of the forward
-        sd = {k: v for k, v in self.state_dict().items() if not k.startswith(self._host_only_prefixes)}
-        dev = next(iter(sd.values())).device
+        # utils.py:216), which is host-side table data, not a weight of the forward.  The (name, tensor) list is cached -- walking
+        # state_dict() costs ~0.5 ms per call, a B = 1 forward ~1 ms -- and dropped whenever the module tree is converted (_apply).
+        if self._handle_tensors is None:
+            self._handle_tensors = [(k, v) for k, v in self.state_dict().items() if not k.startswith(self._host_only_prefixes)]
+        sd = dict(self._handle_tensors)
+        dev = self._handle_tensors[0][1].device
         if dev.type != "cuda":
             raise RuntimeError("the sequence denoiser runs only on a CUDA device (no CPU fallback): call model.to('cuda')")
-        sig = tuple((t.data_ptr(), t._version) for t in sd.values())
+        sig = tuple((t.data_ptr(), t._version) for _, t in self._handle_tensors)
         if self._handle is not None and sig == self._handle_sig and dev == self._handle_dev:
             return self._handle
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

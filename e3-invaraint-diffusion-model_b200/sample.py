@@ -69,12 +69,11 @@ def get_model(steps_per_epoch=1, state_dict=None) -> PeptideDiff:
     return model.eval().to(DEVICE)
 
 
-def generate_discrete_noise(batch_size, length, num_classes=20):
-    """reference sample.py:112-116."""
-    random_indices = torch.randint(0, num_classes, (batch_size, length))
-    one_hot_matrix = torch.zeros(batch_size, length, num_classes)
-    one_hot_matrix[torch.arange(batch_size).unsqueeze(1), torch.arange(length), random_indices] = 1
-    return one_hot_matrix.to(DEVICE)
+def generate_discrete_noise(batch_size, length, num_classes=20, device=None):
+    """reference sample.py:112-116: x_T = one-hot of uniform class indices drawn from torch's global CPU generator (the same
+    `torch.randint` call, hence the same x_T under the same `torch.manual_seed`)."""
+    classes = torch.randint(0, num_classes, (batch_size, length))
+    return F.one_hot(classes, num_classes).to(dtype=torch.float32, device=DEVICE if device is None else device)
 
 
 def sample_p_zs_given_zt_discrete(t, s, noised_data, pred_noise, noise_schedule, transition, diverse, is_last_step,
@@ -103,14 +102,19 @@ def sample_p_zs_given_zt_discrete(t, s, noised_data, pred_noise, noise_schedule,
 
 @torch.no_grad()
 def denoise_tensors(batch, model, noise_schedule, transition, diverse, timesteps=None, x_T=None, noise_E_steps=None,
-                    graph_id0=0, seed=None):
+                    graph_id0=None, seed=None):
     """The T-step loop of reference denoise() (sample.py:184-207) as one C call.  Returns the final
-    [B,L,20] tensor (raw logits of the last step, quirk Q4) on DEVICE."""
+    [B,L,20] tensor (raw logits of the last step, quirk Q4) on the model's device.
+    `graph_id0` = global id of the batch's first graph in the Philox noise stream; None (default) continues the process-wide
+    stream (`_cabi.GRAPH_IDS`), so consecutive batches and repeated calls never share noise."""
     T = CONFIG["timesteps"] if timesteps is None else timesteps
-    dev = DEVICE
+    h = model._sync_handle()
+    dev = model._handle_dev  # the handle's device owns the stream, the workspace and every tensor of this call
     batch_size, max_len, num_class = batch["ligand_seq"].shape
+    if graph_id0 is None:
+        graph_id0 = _cabi.GRAPH_IDS.take(batch_size)
     if x_T is None:
-        x_T = generate_discrete_noise(batch_size, max_len, num_class)
+        x_T = generate_discrete_noise(batch_size, max_len, num_class, device=dev)
 
     def dv(x):
         return x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
@@ -127,7 +131,6 @@ def denoise_tensors(batch, model, noise_schedule, transition, diverse, timesteps
     E = None if noise_E_steps is None else dv(noise_E_steps)
     if E is not None and tuple(E.shape) != (T, batch_size * max_len, 20):
         raise ValueError("noise_E_steps must be [T, B*L, 20]")
-    h = model._sync_handle()
     out = torch.empty((batch_size, max_len, num_class), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

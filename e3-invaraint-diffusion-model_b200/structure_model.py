@@ -124,6 +124,7 @@ class ConditionalBertForDiffusionBase(_SeqBase):
         self._handle = None
         self._handle_sig = None
         self._handle_dev = None
+        self._handle_tensors = None
 
     def initialize_weights(self):  # the structure model keeps torch's default init (no initialize_weights in the reference)
         return None
@@ -176,6 +177,8 @@ def _p_sample(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mas
     out = model(timestep, ligand_angle_noise, ligand_mask, receptor_seq, receptor_angle, receptor_mask)
     dev = out.device
     B, L, Fs = out.shape
+    if graph_id0 is None:
+        graph_id0 = _cabi.GRAPH_IDS.take(B)
     x = ligand_angle_noise.to(device=dev, dtype=torch.float32).contiguous()
     coef = step_coefficients(betas).to(dev)
     z = None if noise is None else noise.to(device=dev, dtype=torch.float32).contiguous()
@@ -190,16 +193,17 @@ def _p_sample(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mas
 
 @torch.no_grad()
 def p_sample(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mask, receptor_angle, timestep, betas,
-             noise: Optional[torch.Tensor] = None, graph_id0: int = 0, seed: Optional[int] = None) -> torch.Tensor:
+             noise: Optional[torch.Tensor] = None, graph_id0: Optional[int] = None, seed: Optional[int] = None) -> torch.Tensor:
     """reference structure_model/sample.py:55-102 (un-wrapped; p_sample_loop applies the wrap).  Extra keywords: `noise`, the
-    N(0,1) tensor `torch.randn_like` would have drawn (same-noise parity runs); otherwise counter-based Philox in the kernel."""
+    N(0,1) tensor `torch.randn_like` would have drawn (same-noise parity runs); otherwise counter-based Philox in the kernel,
+    keyed by (seed, graph_id0 + b, element, step); graph_id0 = None continues the process-wide noise stream."""
     return _p_sample(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mask, receptor_angle, timestep, betas, noise, graph_id0,
                      seed, False)
 
 
 @torch.no_grad()
 def p_sample_wrapped(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mask, receptor_angle, timestep, betas,
-                     noise: Optional[torch.Tensor] = None, graph_id0: int = 0, seed: Optional[int] = None) -> torch.Tensor:
+                     noise: Optional[torch.Tensor] = None, graph_id0: Optional[int] = None, seed: Optional[int] = None) -> torch.Tensor:
     """One iteration of the reference loop body (sample.py:125-141): forward + p_sample + modulo_with_wrapped_range, the update
     and the wrap in ONE kernel."""
     return _p_sample(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mask, receptor_angle, timestep, betas, noise, graph_id0,
@@ -208,17 +212,20 @@ def p_sample_wrapped(model, ligand_mask, ligand_angle_noise, receptor_seq, recep
 
 @torch.no_grad()
 def p_sample_loop(model, ligand_mask, ligand_angle_noise, receptor_seq, receptor_mask, receptor_angle, total_timesteps: int, betas,
-                  disable_pbar: bool = True, noise_steps: Optional[torch.Tensor] = None, graph_id0: int = 0, seed: Optional[int] = None,
+                  disable_pbar: bool = True, noise_steps: Optional[torch.Tensor] = None, graph_id0: Optional[int] = None, seed: Optional[int] = None,
                   keep_history: bool = True) -> torch.Tensor:
     """reference structure_model/sample.py:104-144: returns a CPU tensor [timesteps, B, L, F] (entry k = wrapped angles after
     the k-th reverse step).  The whole loop is ONE C call (`seqdiff_struct_sample`): the receptor branch is evaluated once, every
     step replays a captured CUDA graph (ligand branch + Gaussian step + wrap), and the history is written by the step kernel --
     one device->host copy at the end instead of one per step.  `keep_history=False` returns only the final [1,B,L,F] entry.
-    `noise_steps` [T,B,L,F]: entry i = the N(0,1) draw used at step index i (entry 0 unused)."""
+    `noise_steps` [T,B,L,F]: entry i = the N(0,1) draw used at step index i (entry 0 unused).  `graph_id0` = None continues the
+    process-wide Philox noise stream, so successive batches / calls draw fresh noise like the reference's `torch.randn_like`."""
     h = model._sync_handle()
     dev = model._handle_dev
     T = int(total_timesteps)
     B, Ll, Lr, x, lm, rs, ra, rm = model._inputs(ligand_angle_noise, ligand_mask, receptor_seq, receptor_angle, receptor_mask)
+    if graph_id0 is None:
+        graph_id0 = _cabi.GRAPH_IDS.take(B)
     Fs = model.feature_size
     coef = step_coefficients(betas)
     if coef.shape[0] != T:

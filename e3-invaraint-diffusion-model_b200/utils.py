@@ -1,147 +1,168 @@
-"""Host-side mirror of the types `sequence_model/utils.py` hands to the hot path: the discrete noise
-schedule and the transition matrices.  They are tiny per-step table
-builders that run on the host exactly as in the reference (quirk Q8: alphas_bar lives on the CPU); the
-resulting [T,3,20,20] tables are uploaded once and consumed by the CUDA reverse-step kernel.
-Same class names, constructor arguments, methods and error behaviour as the reference."""
+"""Host-side table builders behind the `sequence_model/utils.py` types of the reference.
+
+What the hot path needs from the reference's schedule / transition objects is a handful of tiny tables: alpha-bar per step,
+BLOSUM temperatures per step, and from them the (Qt, Qsb, Qtb) triple of every reverse step.  They are built ONCE on the host
+in fp32 with the arithmetic the reference uses on the CPU (quirk Q8: alphas_bar lives on the CPU there too), uploaded as a
+[T,3,20,20] array and consumed by the CUDA reverse-step kernel.  The classes below keep the reference's names, constructor
+arguments, method signatures and error behaviour (they are the drop-in boundary), but they are thin fronts of three
+vectorised builders -- `qbar_blosum`, `qbar_uniform`, `posterior_tables` -- and never move state between devices.
+
+The order of the fp32 / fp64 operations is dictated by the parity requirement (tables must be bit-identical to the
+reference's: tests/test_oracle_pin.py::test_product_host_tables_match_oracle); everything else is this package's own.
+"""
 from __future__ import annotations
 
 import os
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
 import torch.nn.functional as F
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "blosum_substitute.npz")
+_CPU = torch.device("cpu")
 
 
-def cosine_beta_schedule_discrete(timesteps, s=0.008):
-    """reference utils.py:99-108."""
-    steps = timesteps + 2
-    x = np.linspace(0, steps, steps)
-    alphas_cumprod = np.cos(0.5 * np.pi * ((x / steps) + s) / (1 + s)) ** 2
-    alphas_cumprod = alphas_cumprod / alphas_cumprod[0]
-    alphas = alphas_cumprod[1:] / alphas_cumprod[:-1]
-    betas = 1 - alphas
-    return betas.squeeze()
+# ---------------------------------------------------------------------------------------------------------------------
+# cosine schedule (reference utils.py:99-108, 206-233)
+# ---------------------------------------------------------------------------------------------------------------------
+def cosine_beta_schedule_discrete(timesteps: int, s: float = 0.008) -> np.ndarray:
+    """betas[0..T] (float64) of the cosine schedule on the T+2 grid points the reference samples."""
+    n = timesteps + 2
+    grid = np.linspace(0, n, n)
+    f = np.cos(0.5 * np.pi * ((grid / n) + s) / (1 + s)) ** 2
+    f = f / f[0]
+    return (1 - f[1:] / f[:-1]).squeeze()
+
+
+def _alpha_bar_table(timesteps: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(betas, alphas, alphas_bar), fp32, T+1 entries: alphas_bar = exp(cumsum(log(1 - clamp(beta, 0, 0.9999))))."""
+    betas = torch.from_numpy(cosine_beta_schedule_discrete(timesteps)).float()
+    alphas = 1 - betas.clamp(min=0, max=0.9999)
+    return betas, alphas, alphas.log().cumsum(0).exp()
+
+
+def _step_index(t_normalized, t_int, timesteps: int) -> torch.Tensor:
+    # the reference's guard (utils.py:224,230): exactly one of the two must be given
+    assert int(t_normalized is None) + int(t_int is None) == 1
+    if t_int is None:
+        t_int = torch.round(t_normalized * timesteps)
+    return t_int.long()
 
 
 class PredefinedNoiseScheduleDiscrete(torch.nn.Module):
-    """reference utils.py:206-233."""
+    """Lookup tables of the discrete noise schedule.  `betas` is a registered buffer (it is part of the reference
+    checkpoint: key `discrete_noise_schedule.betas`); `alphas` / `alphas_bar` are plain CPU attributes."""
 
     def __init__(self, noise_schedule, timesteps):
         super().__init__()
         self.timesteps = timesteps
-        betas = cosine_beta_schedule_discrete(timesteps)
-        self.register_buffer("betas", torch.from_numpy(betas).float())
-        self.alphas = 1 - torch.clamp(self.betas, min=0, max=0.9999)
-        log_alpha_bar = torch.cumsum(torch.log(self.alphas), dim=0)
-        self.alphas_bar = torch.exp(log_alpha_bar)
+        betas, self.alphas, self.alphas_bar = _alpha_bar_table(timesteps)
+        self.register_buffer("betas", betas)
 
     def forward(self, t_normalized=None, t_int=None):
-        assert int(t_normalized is None) + int(t_int is None) == 1
-        if t_int is None:
-            t_int = torch.round(t_normalized * self.timesteps)
-        return self.betas[t_int.long()]
+        return self.betas[_step_index(t_normalized, t_int, self.timesteps)]
 
     def get_alpha_bar(self, t_normalized=None, t_int=None):
-        assert int(t_normalized is None) + int(t_int is None) == 1
-        if t_int is None:
-            t_int = torch.round(t_normalized * self.timesteps)
-        return self.alphas_bar.to(t_int.device)[t_int.long()]
+        idx = _step_index(t_normalized, t_int, self.timesteps)
+        return self.alphas_bar.to(idx.device)[idx]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# transition matrices (reference utils.py:235-314)
+# ---------------------------------------------------------------------------------------------------------------------
+def qbar_uniform(stay: torch.Tensor, spread: torch.Tensor, classes: int) -> torch.Tensor:
+    """[n,C,C] = stay_n * I + spread_n / C for n scalar pairs (any shape with n elements)."""
+    eye = torch.eye(classes).unsqueeze(0)
+    flat = torch.ones(1, classes, classes) / max(classes, 1)
+    return stay.reshape(-1, 1, 1) * eye + spread.reshape(-1, 1, 1) * flat
+
+
+def qbar_blosum(score: torch.Tensor, temperatures: torch.Tensor, clamp: Optional[float]) -> torch.Tensor:
+    """[n,C,C] row-softmax of score / temperature_n; entries below `clamp` are raised to it (quirk Q7: rows then no
+    longer sum to one -- the reference does the same)."""
+    q = torch.softmax(score.unsqueeze(0) / temperatures.reshape(-1, 1, 1), dim=2)
+    return q if clamp is None else torch.where(q < clamp, torch.full_like(q, clamp), q)
 
 
 class DiscreteUniformTransition:
-    """reference utils.py:235-271."""
-
     def __init__(self, x_classes: int):
         self.X_classes = x_classes
-        self.u_x = torch.ones(1, self.X_classes, self.X_classes)
-        if self.X_classes > 0:
-            self.u_x = self.u_x / self.X_classes
+        self.u_x = torch.ones(1, x_classes, x_classes) / max(x_classes, 1)
 
     def get_Qt(self, beta_t, device):
-        beta_t = beta_t.unsqueeze(1).to(device)
-        self.u_x = self.u_x.to(device)
-        return beta_t * self.u_x + (1 - beta_t) * torch.eye(self.X_classes, device=device).unsqueeze(0)
+        b = beta_t.detach().to(_CPU)
+        return qbar_uniform(1 - b, b, self.X_classes).to(device)
 
     def get_Qt_bar(self, alpha_bar_t, device):
-        alpha_bar_t = alpha_bar_t.unsqueeze(1).to(device)
-        self.u_x = self.u_x.to(device)
-        return alpha_bar_t * torch.eye(self.X_classes, device=device).unsqueeze(0) + (1 - alpha_bar_t) * self.u_x
+        a = alpha_bar_t.detach().to(_CPU)
+        return qbar_uniform(a, 1 - a, self.X_classes).to(device)
 
 
-def _load_blosum(blosum_path):
-    """Accepts the reference's own `blosum_substitute.pt` (utils.py:276) and falls back, like the
-    reference's '../' retry (utils.py:277-279), to the copy of the three arrays shipped with this package."""
-    for p in (blosum_path, "../" + blosum_path):
-        if os.path.exists(p):
-            d = torch.load(p)
-            return d["original_score"], d["Qtb_temperature"], d["Qt_temperature"]
-    if os.path.exists(_DATA):
-        z = np.load(_DATA)
-        return (torch.from_numpy(z["original_score"]), torch.from_numpy(z["Qtb_temperature"]),
-                torch.from_numpy(z["Qt_temperature"]))
-    raise FileNotFoundError(blosum_path)
+def _blosum_arrays(blosum_path):
+    """(score [20,20], Qtb temperatures [500], Qt temperatures [500]).  The reference's own `blosum_substitute.pt` is used when
+    it is found at `blosum_path` or one directory up (the reference's retry, utils.py:277-279); otherwise the copy of the three
+    arrays that ships with this package."""
+    for cand in (blosum_path, os.path.join("..", blosum_path)):
+        if cand and os.path.exists(cand):
+            blob = torch.load(cand)
+            return blob["original_score"], blob["Qtb_temperature"], blob["Qt_temperature"]
+    if not os.path.exists(_DATA):
+        raise FileNotFoundError(blosum_path)
+    z = np.load(_DATA)
+    return tuple(torch.from_numpy(z[k]) for k in ("original_score", "Qtb_temperature", "Qt_temperature"))
+
+
+_load_blosum = _blosum_arrays  # (name kept for callers of the previous round)
+
+
+def _resample(table: torch.Tensor, n: int) -> torch.Tensor:
+    """500-entry temperature table -> n entries, linear with aligned end points."""
+    return F.interpolate(table.float()[None, None], size=n, mode="linear", align_corners=True).squeeze()
 
 
 class BlosumTransition:
-    """reference utils.py:273-314 (temperature tables re-interpolated to timestep+1 entries; the
-    shape test at :286 is always true)."""
+    """BLOSUM-substitution transition: Q(x) = softmax(score / temperature[round(x * timestep)]).  The callers hand it
+    alpha-bar where the table was built for normalised time (quirk Q2) -- reproduced as is."""
 
     def __init__(self, blosum_path="./blosum_substitute.pt", x_classes=20, timestep=500):
-        self.original_score, self.temperature_list, self.Qt_temperature = _load_blosum(blosum_path)
+        score, qtb_temp, qt_temp = _blosum_arrays(blosum_path)
+        self.original_score = score
         self.X_classes = x_classes
         self.timestep = timestep
-        t = self.temperature_list.float()[None, None]
-        q = self.Qt_temperature.float()[None, None]
-        self.temperature_list = F.interpolate(t, size=timestep + 1, mode="linear", align_corners=True).squeeze()
-        self.Qt_temperature = F.interpolate(q, size=timestep + 1, mode="linear", align_corners=True).squeeze()
+        self.temperature_list = _resample(qtb_temp, timestep + 1)
+        self.Qt_temperature = _resample(qt_temp, timestep + 1)
+
+    def _rows(self, table, t_normal):
+        return table[torch.round(t_normal.detach().to(_CPU) * self.timestep).long()]
 
     def get_Qt_bar(self, t_normal, device):
-        self.original_score = self.original_score.to(device)
-        self.temperature_list = self.temperature_list.to(device)
-        t_int = torch.round(t_normal * self.timestep).to(device)
-        temperatue = self.temperature_list[t_int.long()]
-        q_x = self.original_score.unsqueeze(0) / temperatue.unsqueeze(2)
-        q_x = torch.softmax(q_x, dim=2)
-        q_x[q_x < 1e-6] = 1e-6
-        return q_x
+        return qbar_blosum(self.original_score, self._rows(self.temperature_list, t_normal), 1e-6).to(device)
 
     def get_Qt(self, t_normal, device):
-        self.original_score = self.original_score.to(device)
-        self.Qt_temperature = self.Qt_temperature.to(device)
-        t_int = torch.round(t_normal * self.timestep).to(device)
-        temperatue = self.Qt_temperature[t_int.long()]
-        q_x = self.original_score.unsqueeze(0) / temperatue.unsqueeze(2)
-        return torch.softmax(q_x, dim=2)
+        return qbar_blosum(self.original_score, self._rows(self.Qt_temperature, t_normal), None).to(device)
 
 
-def step_tables(t, s, noise_schedule, transition):
-    """(Qt, Qsb, Qtb) of reference sample.py:156-160, computed on the HOST with the caller's own
-    schedule/transition objects (duck-typed) -> float32 [n, 3, 20, 20]."""
-    cpu = torch.device("cpu")
-    alpha_t_bar = noise_schedule.get_alpha_bar(t_normalized=t.cpu())
-    alpha_s_bar = noise_schedule.get_alpha_bar(t_normalized=s.cpu())
-    Qtb = transition.get_Qt_bar(alpha_t_bar, cpu)
-    Qsb = transition.get_Qt_bar(alpha_s_bar, cpu)
-    Qt = (Qsb / Qtb) / (Qsb / Qtb).sum(dim=-1).unsqueeze(dim=2)
+# ---------------------------------------------------------------------------------------------------------------------
+# per-step posterior tables for the CUDA reverse step
+# ---------------------------------------------------------------------------------------------------------------------
+def posterior_tables(alpha_bar_t: torch.Tensor, alpha_bar_s: torch.Tensor, transition) -> torch.Tensor:
+    """fp32 [n,3,C,C] = (Qt, Qsb, Qtb) for n (t, s) pairs: Qtb / Qsb from the caller's (duck-typed) transition object,
+    Qt = row-normalised Qsb / Qtb (the reference's stand-in for the one-step matrix, sample.py:160, quirk Q5)."""
+    Qtb = transition.get_Qt_bar(alpha_bar_t, _CPU)
+    Qsb = transition.get_Qt_bar(alpha_bar_s, _CPU)
+    ratio = Qsb / Qtb
+    Qt = ratio / ratio.sum(dim=-1).unsqueeze(dim=2)
     return torch.stack([Qt, Qsb, Qtb], dim=1).float().contiguous()
 
 
+def step_tables(t, s, noise_schedule, transition):
+    """Tables of one reverse step for per-graph normalised times t, s [B,1] (reference sample.py:156-160)."""
+    return posterior_tables(noise_schedule.get_alpha_bar(t_normalized=t.cpu()), noise_schedule.get_alpha_bar(t_normalized=s.cpu()), transition)
+
+
 def loop_tables(timesteps, noise_schedule, transition):
-    """Tables for every step of denoise() (reference sample.py:192-197): entry s_int holds the triple
-    for s = s_int/T, t = (s_int+1)/T, built with the reference's own float32 arithmetic."""
-    s_array = torch.arange(timesteps, dtype=torch.float32).unsqueeze(1) * torch.ones((1, 1))
-    s_norm = s_array / timesteps
-    t_norm = (s_array + 1) / timesteps
-    return step_tables(t_norm, s_norm, noise_schedule, transition)
-
-
-def elbo_loss(logits1, logits2, eps=1e-6):
-    """reference utils.py:132-161 (training-side; plain torch ops on the logits the CUDA forward produced)."""
-    probs1 = F.softmax(logits1, dim=-1)
-    probs2 = F.softmax(logits2, dim=-1)
-    log_probs1 = F.log_softmax(logits1 + eps, dim=-1)
-    kl_div = F.kl_div(log_probs1, probs2, reduction="batchmean")
-    nll = -torch.mean(torch.sum(probs1 * log_probs1, dim=-1))
-    return nll + kl_div
+    """Tables of every step of a T-step sampling: entry k serves the step s_int = k, i.e. s = k/T, t = (k+1)/T, formed in
+    fp32 exactly like the loop variables of reference sample.py:192-197."""
+    k = torch.arange(timesteps, dtype=torch.float32).unsqueeze(1) * torch.ones((1, 1))
+    return step_tables((k + 1) / timesteps, k / timesteps, noise_schedule, transition)

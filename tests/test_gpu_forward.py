@@ -1,24 +1,22 @@
 """GPU parity tests of the denoiser forward and of the full reverse-diffusion loop against the oracle and
 the golden vectors produced from the reference.
 
-Tolerances (BASELINE.json north_star: "within 1e-2 relative (bf16) or 1e-5 (fp32 mode)"), as written below:
+Tolerances (BASELINE.json north_star: "within 1e-2 relative (bf16) or 1e-5 (fp32 mode)"), ONE stated norm per mode, always on
+the SAME fp32 random-init weights on both sides (no bf16-rounded checkpoint on the reference side):
 
-  fp32 mode                      max|d| / max|ref| < 1e-5          arbitrary fp32 weights, vs reference goldens
-  fp16 mode                      max|d| / max|ref| < 1e-2          arbitrary fp32 weights, vs reference goldens
-  bf16 mode, bf16 checkpoint     ||d||_2 / ||ref||_2 < 1e-2        (and max-norm < 1.5e-2) -- the parity gate
-  bf16 mode, fp32 checkpoint     calibrated: closer to the fp32 reference than torch.autocast(bfloat16) of the
-                                 same model on the same inputs, and L2 < 1.5e-2, max-norm < 2.5e-2
+  fp32 mode     max|d| / max|ref|      < 1e-5
+  fp16 mode     max|d| / max|ref|      < 1e-2      (measured 0.9-1.8e-3)
+  bf16 mode     ||d||_2 / ||ref||_2    < 1e-2      (measured 0.6-0.95e-2; the norm of the bf16 gate is the relative L2 norm)
 
-Why bf16 is split in two.  bf16 operands carry 8 mantissa bits.  Rounding ONLY the weights of this 25-sublayer
-model to bf16 (all arithmetic exact otherwise) already moves the logits by 0.9e-2 (max-norm) / 0.6e-2 (L2), and
-PyTorch's own CPU autocast(bfloat16) run of the very same model sits at 1.5-2.6e-2 / 1.2-1.8e-2 from its fp32
-self (numbers in DESIGN.md, "bf16 error budget").  So "the same weights within 1e-2" is only well posed when both
-sides really hold the same weights: a bf16 checkpoint (every tensor bf16-representable), evaluated by the fp32
-oracle on one side and by the bf16 tensor-core path on the other.  There this implementation -- fp32 residual
-stream / LayerNorm / softmax / accumulators, 16-bit rounding only on GEMM and attention operands -- measures
-0.4-0.6e-2.  With arbitrary fp32 weights the weight rounding is added on top, which no bf16 GEMM can avoid; that case
-is gated against stock bf16 autocast instead.  fp16 mode (same kernels, same speed, 11-bit mantissa) meets the
-strict max-norm 1e-2 gate with ~7x margin on arbitrary weights."""
+Why the bf16 margin is what it is (profiles/bf16_attribution_r02.txt, scripts/bf16_attribution.py): the CUDA
+path rounds ONLY tensor-core operands to bf16 (accumulators, residual stream, LayerNorm, softmax, logits are fp32).  Switching
+each class of rounding on alone in the oracle shows that rounding the Linear WEIGHTS to bf16 -- which any bf16 x bf16 GEMM must
+do -- already moves the logits by 5.2-6.7e-3 (L2), 47-62 % of the total error variance; the activation operands that a bf16
+MMA cannot avoid (A operands, Q/K/V, P, context, GELU outputs) add the rest, and no single avoidable rounding holds more
+than 9 %.  The emulated total (7.6-9.4e-3) matches what the GPU measures, i.e. the kernels add nothing beyond operand
+rounding.  A 2x margin under 1e-2 is therefore out of reach for bf16 operands on this 25-sublayer network; fp16 mode (same
+kernels, same speed) has 7x margin.  PyTorch's own CPU autocast(bfloat16) of the same model is at 1.2-1.8e-2 (test below).
+The bf16-checkpoint test (weights bf16-representable on both sides) isolates the non-weight part: < 0.7e-2."""
 import glob
 import os
 
@@ -60,9 +58,9 @@ def check_logits(got, want, precision, what, bf16_ckpt=False):
     elif precision == "fp16":
         assert mx < 1e-2, mx
     elif bf16_ckpt:
-        assert l2 < 1e-2 and mx < 1.5e-2, (l2, mx)
+        assert l2 < 0.7e-2, l2   # same bf16-representable weights on both sides: activation-operand rounding only
     else:
-        assert l2 < 1.5e-2 and mx < 2.5e-2, (l2, mx)
+        assert l2 < 1e-2, l2     # THE bf16 gate: same fp32 weights on both sides, relative L2 norm
     return mx, l2
 
 
@@ -89,7 +87,8 @@ def test_forward_golden(path, precision):
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "forward_rel_*.pt"))), ids=os.path.basename)
 def test_forward_bf16_checkpoint(path):
-    """THE bf16 parity gate: same bf16-representable weights on both sides, fp32 oracle vs bf16 tensor-core path."""
+    """Supplementary: bf16-representable weights on both sides (what a bf16 checkpoint holds) isolate the activation-operand
+    rounding from the weight rounding; the gate proper is test_forward_golden[bf16] on the same fp32 weights."""
     g = torch.load(path, weights_only=False)
     cfg, state, m = _model(g["L"], g["relative_key"], g["weight_seed"], g["variant"], "bf16", bf16_ckpt=True)
     args = _golden_inputs(g)
@@ -166,7 +165,7 @@ def test_denoise_loop_golden(precision):
     sd = sd_pkg()
     g = torch.load(os.path.join(GOLDEN, "denoise_T4.pt"), weights_only=False)
     T, B, L = g["T"], g["B"], g["L"]
-    cfg, state, m = _model(L, True, g["weight_seed"], g["variant"], precision, bf16_ckpt=(precision == "bf16"))
+    cfg, state, m = _model(L, True, g["weight_seed"], g["variant"], precision)
     batch = O.synthetic_batch(B, L, g["n_lig"], g["n_rec"], g["batch_seed"])
     batch["structure_ids"] = {"pdb_id": ["xxxx"] * B, "ligand_chain": ["A"] * B}
     x_T = F.one_hot(g["x_T_idx"].long(), 20).float()
@@ -198,7 +197,7 @@ def test_denoise_loop_golden(precision):
                        batch["receptor_seq"].to(DEV), batch["receptor_angles"].to(DEV), batch["receptor_attn_mask"].to(DEV))
                 want_lg = O.denoiser_forward(state, cfg, s, x, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
                                              batch["receptor_angles"], batch["receptor_attn_mask"])
-            check_logits(lg, want_lg, "bf16", f"teacher-forced step {s_int}", bf16_ckpt=True)
+            check_logits(lg, want_lg, "bf16", f"teacher-forced step {s_int}")
             # same logits on both sides -> indices must agree exactly (up to near-ties)
             got = sd.sample_p_zs_given_zt_discrete((s + 1) / T, s / T, x.to(DEV), lg, sched, tr, True, False, noise_E=E[s_int])
             want = O.reverse_step((s + 1) / T, s / T, x, lg.cpu(), o_s, o_t, True, False, E[s_int])
@@ -240,11 +239,83 @@ def test_sample_loop_equals_stepwise_calls():
     assert not torch.equal(full, other)
 
 
+def test_sample_loop_philox_mode_teacher_forced_vs_oracle():
+    """The loop the benchmark times (seqdiff_sample, Philox noise => reverse_step_kernel<FAST>) against the oracle, step by step:
+    the loop's final tensor equals the same steps issued one by one (forward + single-step Philox reverse step with the loop's
+    key: seed, global graph ids, step index = s_int), and at every step the single-step result equals the oracle's
+    sample_p_zs_given_zt_discrete fed the SAME logits and the SAME noise (Philox words -> Exp(1) on the host)."""
+    import numpy as np
+    sd = sd_pkg()
+    lib = sd.lib()
+    T, B, L = 8, 6, 128
+    seed, gid0 = 1234567, 4242
+    cfg, state, m = _model(128, True, 1, "B", "bf16")
+    sd.sample.DEVICE = torch.device(DEV)
+    batch = O.synthetic_batch(B, L, (5, 64), (16, 128), 78)
+    x_T = O.generate_discrete_noise(B, L, generator=torch.Generator().manual_seed(6))
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    o_s, o_t = O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition()
+    final = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T, seed=seed, graph_id0=gid0)
+    dv = {k: v.to(DEV) for k, v in batch.items()}
+    x = x_T.to(DEV)
+    tables = sd.utils.loop_tables(T, sched, tr).to(DEV)
+    import ctypes
+    p = sd._cabi.ptr
+    flips = 0
+    for s_int in reversed(range(T)):
+        s = s_int * torch.ones((B, 1))
+        with torch.no_grad():
+            lg = m(s.to(DEV), x, dv["ligand_angles"], dv["ligand_attn_mask"], dv["receptor_seq"], dv["receptor_angles"], dv["receptor_attn_mask"])
+        if s_int == 0:
+            x = lg
+            break
+        nxt = torch.empty_like(x)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        assert lib.seqdiff_reverse_step(p(tables[s_int:s_int + 1].contiguous()), 1, B, L, p(x), p(lg), 1, None, seed, gid0, s_int, p(nxt), None, stream) == 0
+        words = torch.zeros(B * L * 20, dtype=torch.int32, device=DEV)
+        assert lib.seqdiff_op_philox_u32(seed, gid0, s_int, B, L, p(words), stream) == 0
+        u = ((words.cpu().numpy().view(np.uint32).astype(np.uint64) >> np.uint64(9)).astype(np.float64) + 0.5) * 2.0 ** -23
+        E = torch.from_numpy(-np.log(u)).float().reshape(B * L, 20)
+        want = O.reverse_step((s + 1) / T, s / T, x.cpu(), lg.cpu(), o_s, o_t, True, False, E)
+        prob = O.reverse_step_probs((s + 1) / T, s / T, x.cpu(), lg.cpu(), o_s, o_t)
+        flips += assert_indices_match(nxt.argmax(-1), want.argmax(-1), prob / E, f"philox loop step {s_int}")
+        x = nxt
+    assert torch.equal(final, x), "graph-replayed loop differs from the same steps issued one by one"
+    print(f"philox loop: {flips} near-tie flips over {T - 1} steps x {B * L} residues")
+
+
+def test_consecutive_calls_draw_fresh_noise_and_explicit_ids_reproduce():
+    """batches / repeated calls must not share the Philox noise field.  Default graph_id0 continues a
+    process-wide stream; explicit ids reproduce; changing seed / ids re-uses the cached CUDA graph (key lives in device memory)."""
+    sd = sd_pkg()
+    T, B, L = 5, 3, 64
+    cfg, state, m = _model(64, True, 1, "B", "bf16")
+    sd.sample.DEVICE = torch.device(DEV)
+    batch = O.synthetic_batch(B, L, (5, 40), (16, 64), 79)
+    x_T = O.generate_discrete_noise(B, L, generator=torch.Generator().manual_seed(7))
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    a = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T)
+    n_graph = sd.lib().seqdiff_launch_count()
+    b = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T)
+    per_call = sd.lib().seqdiff_launch_count() - n_graph
+    assert not torch.equal(a, b), "two default calls on the same batch shared their noise"
+    c1 = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T, graph_id0=1000, seed=3)
+    n0 = sd.lib().seqdiff_launch_count()
+    c2 = sd.denoise_tensors(batch, m, sched, tr, True, timesteps=T, x_T=x_T, graph_id0=1000, seed=3)
+    assert torch.equal(c1, c2)
+    # same launch count as a cached-graph call: a new (seed, graph_id0) did not trigger the dry run + re-capture
+    assert sd.lib().seqdiff_launch_count() - n0 == per_call
+    # graph b of the second block == graph b drawn as part of a shifted batch (ids key the noise, not batch positions)
+    sub = {k: v[1:] for k, v in batch.items()}
+    d = sd.denoise_tensors(sub, m, sched, tr, True, timesteps=T, x_T=x_T[1:], graph_id0=1001, seed=3)
+    assert torch.equal(d, c1[1:])
+
+
 @pytest.mark.parametrize("precision", MODES)
 def test_forward_cfg3_length_512(precision):
     """BASELINE cfg 3 shape: max_seq_len 512 (distance_embedding [1023,64]), n_lig = 48, n_rec = 464 + a ragged graph;
     4 key blocks per attention row (online softmax across blocks, E window moves with the block)."""
-    cfg, state, m = _model(512, True, 1, "B", precision, bf16_ckpt=(precision == "bf16"))
+    cfg, state, m = _model(512, True, 1, "B", precision)
     B = 2
     batch = O.synthetic_batch(B, 512, 48, 464, 13)
     rag = O.synthetic_batch(B, 512, (1, 512), (100, 512), 14)
@@ -256,7 +327,7 @@ def test_forward_cfg3_length_512(precision):
     with torch.no_grad():
         want = O.denoiser_forward(state, cfg, *args)
         got = m(*[a.to(DEV) for a in args])
-    check_logits(got, want, precision, "cfg3 L=512", bf16_ckpt=(precision == "bf16"))
+    check_logits(got, want, precision, "cfg3 L=512")
 
 
 @pytest.mark.parametrize("precision", MODES)
@@ -265,7 +336,7 @@ def test_forward_accepts_structure_model_angles_cfg5(precision):
     shape [8,128,8] f32) are fed as `ligand_angle` (sample_by_generated_angles.py:202) -- CUDA forward vs the oracle."""
     g = torch.load(os.path.join(GOLDEN, "structure_feed_cfg5.pt"), weights_only=False)
     B, L = g["B"], g["L"]
-    cfg, state, m = _model(L, True, 1, "B", precision, bf16_ckpt=(precision == "bf16"))
+    cfg, state, m = _model(L, True, 1, "B", precision)
     batch = O.synthetic_batch(B, L, g["n_lig"], g["n_rec"], g["batch_seed"])
     ang = g["angles"] * batch["ligand_attn_mask"][..., None]
     assert ang.shape == (B, L, 8) and ang.dtype == torch.float32
@@ -276,4 +347,4 @@ def test_forward_accepts_structure_model_angles_cfg5(precision):
         want = O.denoiser_forward(state, cfg, *args)
         got = m(*[a.to(DEV) for a in args])
     assert got.shape == (B, L, 20)
-    check_logits(got, want, precision, "cfg5 structure feed", bf16_ckpt=(precision == "bf16"))
+    check_logits(got, want, precision, "cfg5 structure feed")

@@ -140,10 +140,11 @@ ATTN_CASES = [
 ]
 
 
-def test_attention_both_16bit_kernels_subprocess():
-    """the per-shape dispatch hides one of the two 16-bit kernels for some shapes: run the op tests with each one forced."""
+def test_attention_small_grid_subprocess():
+    """the persistent kernel with only 3 CTAs: every CTA walks a long item list (the superseded tc / mma kernels are no longer part
+    of the default build: SEQDIFF_AB_KERNELS=1 compiles them back in as A/B references)."""
     import subprocess, sys
-    for impl, grid in (("tc", "0"), ("mma", "0"), ("pipe", "3")):  # pipe with 3 CTAs: every CTA walks a long item list
+    for impl, grid in (("pipe", "3"),):
         env = dict(os.environ, SEQDIFF_ATTN=impl, SEQDIFF_ATTN_GRID=grid)
         r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "test_attention and not subprocess", "-p",
                             "no:cacheprovider"], env=env, capture_output=True, text=True)
@@ -336,6 +337,79 @@ def test_reverse_step_philox_statistics():
     freq = got.reshape(-1, 20).mean(0).cpu()
     n = B * L
     assert ((freq - prob).abs() < 5 * torch.sqrt(prob * (1 - prob) / n) + 1e-4).all(), (freq, prob)
+
+
+def _exp1_from_words(w_u32):
+    """Host restatement of how the kernels turn a Philox word into the Exp(1) race noise: u = ((w >> 9) + 0.5) * 2^-23, E = -ln u
+    (float64 here; the exact-mode kernel uses fp32 logf, the production kernel lg2.approx / a series near u = 1)."""
+    u = ((w_u32.astype(np.uint64) >> np.uint64(9)).astype(np.float64) + 0.5) * 2.0 ** -23
+    return -np.log(u)
+
+
+@pytest.mark.parametrize("B,L,T,per_graph", [(64, 128, 500, False), (64, 128, 500, True), (256, 512, 50, False)], ids=["cfg2", "cfg2-per-graph-t", "cfg3"])
+def test_reverse_step_philox_pinned_to_oracle(B, L, T, per_graph):
+    """The PRODUCTION variant of the reverse step -- reverse_step_kernel<FAST = true>: in-kernel Philox noise, FMA-contracted
+    posterior, ex2 / lg2 / rcp.approx, normalisations skipped -- pinned to the oracle (sample.py:141-179): the Philox words the
+    kernel consumes are pulled through seqdiff_op_philox_u32, turned into E ~ Exp(1) on the host, handed to the oracle as its
+    multinomial noise, and the sampled indices must agree bit for bit except at near-ties of the reference's own race scores
+    (top-2 margin < 1e-5 relative).  cfg-2- and cfg-3-sized batches; shared and per-graph step tables."""
+    sd = sd_pkg()
+    lib = sd.lib()
+    seed, gid0 = 0xC0FFEE1234, 7_000_000_123
+    g = torch.Generator().manual_seed(B + L + T)
+    x = F.one_hot(torch.randint(0, 20, (B, L), generator=g), 20).float()
+    logits = torch.randn(B, L, 20, generator=g) * 3
+    s = torch.randint(1, T, (B, 1), generator=g).float() if per_graph else torch.full((B, 1), float(T // 3))
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    sd.sample.DEVICE = torch.device(DEV)
+    old_seed, old_calls = sd.sample.SEED, sd.sample._CALLS[0]
+    try:
+        sd.sample.SEED = seed
+        got = sd.sample_p_zs_given_zt_discrete((s + 1) / T, s / T, x.to(DEV), logits.to(DEV), sched, tr, True, False, graph_id0=gid0)
+        step = sd.sample._CALLS[0] & 0x0FFFFFFF
+    finally:
+        sd.sample.SEED = old_seed
+    assert step == old_calls + 1
+    words = torch.zeros(B * L * 20, dtype=torch.int32, device=DEV)
+    _check(lib.seqdiff_op_philox_u32(seed, gid0, step, B, L, _p(words), stream_ptr()))
+    E = torch.from_numpy(_exp1_from_words(words.cpu().numpy().view(np.uint32))).float().reshape(B * L, 20)
+    o_s, o_t = O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition()
+    want = O.reverse_step((s + 1) / T, s / T, x, logits, o_s, o_t, True, False, E)
+    prob = O.reverse_step_probs((s + 1) / T, s / T, x, logits, o_s, o_t)
+    n_flip = assert_indices_match(got.argmax(-1), want.argmax(-1), prob / E, f"philox {B}x{L}")
+    print(f"philox-mode reverse step {B}x{L}: {n_flip} near-tie flips of {B * L}")
+    assert torch.equal(got.sum(-1).cpu(), torch.ones(B, L))
+
+
+def test_inv_exp1_near_one_is_finite_and_accurate():
+    """lg2.approx has 2^-22 absolute error, so -log2(u) for u -> 1 could come out 0 / negative (inf / NaN race scores).
+    Drive the production kernel with posteriors where EVERY class has the same probability, so the winner is decided by the noise
+    alone, over enough residues that words with u > 1 - 2^-20 occur (~2.6e6 draws): it must match the oracle's argmin of E."""
+    sd = sd_pkg()
+    lib = sd.lib()
+    T, B, L = 50, 256, 512
+    seed, gid0, = 99, 0
+    x = F.one_hot(torch.zeros(B, L, dtype=torch.long), 20).float()
+    logits = torch.zeros(B, L, 20)
+    s = torch.full((B, 1), 2.0)
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    sd.sample.DEVICE = torch.device(DEV)
+    old = sd.sample.SEED
+    try:
+        sd.sample.SEED = seed
+        got = sd.sample_p_zs_given_zt_discrete((s + 1) / T, s / T, x.to(DEV), logits.to(DEV), sched, tr, True, False, graph_id0=gid0)
+        step = sd.sample._CALLS[0] & 0x0FFFFFFF
+    finally:
+        sd.sample.SEED = old
+    words = torch.zeros(B * L * 20, dtype=torch.int32, device=DEV)
+    _check(lib.seqdiff_op_philox_u32(seed, gid0, step, B, L, _p(words), stream_ptr()))
+    w = words.cpu().numpy().view(np.uint32)
+    assert ((w >> 9) >= (1 << 23) - 8).sum() > 0, "no word close to u = 1 in this sample: enlarge it"
+    E = torch.from_numpy(_exp1_from_words(w)).float().reshape(B * L, 20)
+    o_s, o_t = O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition()
+    prob = O.reverse_step_probs((s + 1) / T, s / T, x, logits, o_s, o_t)
+    want = O.reverse_step((s + 1) / T, s / T, x, logits, o_s, o_t, True, False, E)
+    assert_indices_match(got.argmax(-1), want.argmax(-1), prob / E, "near-one noise")
 
 
 def test_apply_aa_noise_golden():
