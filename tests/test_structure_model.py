@@ -347,9 +347,13 @@ def test_struct_sample_loop_matches_reference_golden_and_stepwise_calls():
     assert torch.equal(SM.modulo_with_wrapped_range(raw), hist[0])
     # product mode (bf16, in-kernel Philox): deterministic, sharding-invariant, final entry only
     m.precision = "bf16"
-    a = SM.p_sample_loop(**args, seed=5, keep_history=False)
-    b = SM.p_sample_loop(**args, seed=5)
+    a = SM.p_sample_loop(**args, seed=5, graph_id0=0, keep_history=False)
+    b = SM.p_sample_loop(**args, seed=5, graph_id0=0)
     assert a.shape == (1, g["B"], g["L"], 8) and torch.equal(a[0], b[-1])
+    # without explicit graph ids successive calls continue the process-wide noise stream: fresh noise
+    e1 = SM.p_sample_loop(**args, seed=5, keep_history=False)
+    e2 = SM.p_sample_loop(**args, seed=5, keep_history=False)
+    assert not torch.equal(e1, e2)
     args1 = dict(args, ligand_mask=batch["ligand_attn_mask"][1:], ligand_angle_noise=g["x_T"][1:], receptor_seq=batch["receptor_seq"][1:],
                  receptor_mask=batch["receptor_attn_mask"][1:], receptor_angle=batch["receptor_angles"][1:])
     c = SM.p_sample_loop(**args1, seed=5, graph_id0=1)
