@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build" + ("_ab" if os.environ.get("SEQDIFF_AB_KERNELS") == "1" else "") + ("_dbg" if os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1" else ""))
 LIB = os.path.join(HERE, "libseqdiff_b200.so")
-SOURCES = ["gemm.cu", "rowwise.cu", "attention.cu", "attention_pipe.cu", "reverse_step.cu", "gauss_step.cu", "decode_loss.cu", "collate.cu", "model.cu", "cabi.cu"]
+SOURCES = ["gemm.cu", "rowwise.cu", "attention.cu", "attention_pipe.cu", "reverse_step.cu", "gauss_step.cu", "decode_loss.cu", "collate.cu", "train_kernels.cu", "attention_train.cu", "train.cu", "model.cu", "cabi.cu"]
 # SEQDIFF_AB_KERNELS=1: also build the superseded attention kernels (attention_tc.cu, the mma.sync kernel in attention.cu) as A/B
 # references selectable with SEQDIFF_ATTN=tc|mma.  SEQDIFF_DEBUG_BOUNDS=1: device-side bounds / invariant asserts in every kernel
 # (the stand-in for compute-sanitizer, which the GPU pool does not allow); both change the object directory, not the sources.
@@ -23,7 +23,7 @@ AB_KERNELS = os.environ.get("SEQDIFF_AB_KERNELS") == "1"
 DEBUG_BOUNDS = os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1"
 if AB_KERNELS:
     SOURCES.insert(3, "attention_tc.cu")
-HEADERS = ["common.cuh", "kernels.h", "model.cuh", os.path.join("..", "..", "include", "seqdiff_b200.h")]
+HEADERS = ["common.cuh", "kernels.h", "model.cuh", "philox.cuh", os.path.join("..", "..", "include", "seqdiff_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

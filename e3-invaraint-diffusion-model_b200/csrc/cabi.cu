@@ -1,5 +1,6 @@
 // cabi.cu -- the extern "C" surface declared in include/seqdiff_b200.h.  Thin: argument checks, handle
 // casts, exception firewall.  No torch types, no allocation on behalf of the caller.
+#include <cstdio>
 #include <new>
 
 #include "model.cuh"
@@ -143,6 +144,66 @@ int seqdiff_sample(seqdiff_model_t* m, int precision, int B, int L_lig, int L_re
            "null argument");
   return m->impl.sample(precision, B, L_lig, L_rec, T, q_tables_steps, x_T, ligand_angle, ligand_mask, receptor_seq, receptor_angle,
                         receptor_mask, diverse, noise_E_steps, seed, graph_id0, final_out, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int64_t seqdiff_train_param_count(seqdiff_model_t* m) {
+  try {
+    if (!m) return -1;
+    return m->impl.train_param_count();
+  } catch (...) {
+    return -1;
+  }
+}
+
+int seqdiff_train_param_table(seqdiff_model_t* m, char* names, int name_stride, int64_t* offsets, int64_t* numels, int cap) {
+  try {
+    if (!m || m->impl.build_slots() != SEQDIFF_OK) return -1;
+    const int n = static_cast<int>(m->impl.slots.size());
+    if (cap <= 0) return n;
+    if (!names || !offsets || !numels || name_stride < 16) return -1;
+    for (int i = 0; i < n && i < cap; ++i) {
+      std::snprintf(names + static_cast<size_t>(i) * name_stride, name_stride, "%s", m->impl.slots[i].name.c_str());
+      offsets[i] = m->impl.slots[i].off;
+      numels[i] = m->impl.slots[i].numel;
+    }
+    return n;
+  } catch (...) {
+    return -1;
+  }
+}
+
+int seqdiff_train_step(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, const float* t_norm, const float* noised_ligand_seq,
+                       const float* ligand_seq, const float* ligand_angle, const float* ligand_mask, const float* receptor_seq,
+                       const float* receptor_angle, const float* receptor_mask, float p_hidden, float p_attn, uint64_t seed, uint32_t step,
+                       float* grads_out, double* loss_terms_out, float* logits_out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && t_norm && noised_ligand_seq && ligand_seq && ligand_angle && ligand_mask && receptor_seq && receptor_angle && receptor_mask &&
+               grads_out && loss_terms_out,
+           "null argument");
+  TrainArgs a{};
+  a.precision = precision; a.B = B; a.Ll = L_lig; a.Lr = L_rec;
+  a.t_norm = t_norm; a.x_t = noised_ligand_seq; a.x0 = ligand_seq; a.lig_angle = ligand_angle; a.lig_mask = ligand_mask;
+  a.rec_seq = receptor_seq; a.rec_angle = receptor_angle; a.rec_mask = receptor_mask;
+  a.p_hidden = p_hidden; a.p_attn = p_attn; a.seed = seed; a.step = step;
+  a.grads = grads_out; a.terms = loss_terms_out; a.logits_out = logits_out;
+  return m->impl.train_step(a, static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_adamw_step(seqdiff_model_t* m, const float* grads, float* exp_avg, float* exp_avg_sq, float grad_scale, float max_grad_norm, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, float* grad_norm_out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && grads && exp_avg && exp_avg_sq, "null argument");
+  return m->impl.adamw(grads, exp_avg, exp_avg_sq, grad_scale, max_grad_norm, lr, beta1, beta2, eps, weight_decay, step, grad_norm_out,
+                       static_cast<cudaStream_t>(stream));
+  SD_GUARD_END
+}
+
+int seqdiff_model_get_tensor(seqdiff_model_t* m, const char* name, float* out, int64_t numel, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && name && out, "null argument");
+  return m->impl.get_tensor(name, out, numel, static_cast<cudaStream_t>(stream));
   SD_GUARD_END
 }
 

@@ -2,6 +2,7 @@
 // Every function enqueues on `s`, returns SEQDIFF_OK or an error code (message via set_error()).
 #pragma once
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace seqdiff {
 
@@ -140,5 +141,45 @@ int loss_terms(int N, const float* logits, const float* x0, const float* x_t, co
 int gauss_step(const float* coef, int T, int B, int per_graph, const float* x_t, const float* model_out, const float* noise, uint64_t seed,
                uint64_t graph_id0, int step, const int* step_ptr, float* x_out, float* steps_out, cudaStream_t s, int* advance = nullptr, bool wrap = true,
                const uint64_t* rng = nullptr);  // rng / in-place (x_out == x_t) as in reverse_step()
+
+// ---- train_kernels.cu / attention_train.cu: the training step (reference model.py:313-367 under autograd) ------------
+// out[c][r] = in[r][c] for row-major [rows, cols]; colsum (optional, fp32 [cols]) += column sums (bias gradients); out may be NULL.
+// pitch (default rows): row pitch of `out` in elements, rows <= pitch < rows + 64; columns rows..pitch-1 are written as zeros (the
+// contraction dimension of the weight-gradient GEMM must be a multiple of 8 elements for TMA)
+template <typename T> int transpose_colsum(const T* in, int rows, int cols, T* out, float* colsum, cudaStream_t s, int pitch = 0);
+template <typename T> int transpose_cast(const float* in, int rows, int cols, T* out, cudaStream_t s);  // fp32 [r,c] -> T [c,r]
+// a = dropout(act(z)), kind 1 = erf-GELU, 2 = SiLU;  dz = da * keep * act'(z)
+template <typename T> int act_fwd(const T* z, size_t n, int kind, DropSpec dr, T* a, cudaStream_t s);
+template <typename T, typename TG> int act_bwd(const TG* da, const T* z, size_t n, int kind, DropSpec dr, T* dz, cudaStream_t s);
+int dropout_add(float* d, const float* resid, size_t n, DropSpec dr, cudaStream_t s);           // d = dropout(d) + resid (resid may be NULL)
+template <typename T> int grad_cast(const float* g, size_t n, DropSpec dr, T* out, cudaStream_t s);  // out = T(g * keep)
+// h = LN(o) * gamma + beta:  d_o = LN-backward(dh); dgamma / dbeta += row sums (atomic, fp32 [H])
+int layernorm_bwd(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
+                  cudaStream_t s);
+// backward of ln_modulate(): din = gradient of `in`; sum_out (optional) = din + dout; d(shift, scale, gate) -> dmodT rows (mod_div == 1)
+// or atomically into dmod32 [M / mod_div, 6H]; dgamma / dbeta of the affine LayerNorm when affine_first
+template <typename T>
+int ln_modulate_bwd(const float* dout, const float* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1,
+                    const T* mod, int mod_div, int chunk0, float* din, float* sum_out, T* dmodT, float* dmod32, float* dgamma, float* dbeta,
+                    cudaStream_t s);
+int embed_bwd(const float* dout, const float* x, int M, int fin, int H, const float* Wt, const float* b, const float* gamma, float eps, DropSpec dr,
+              float* dW, float* db, float* dgamma, float* dbeta, cudaStream_t s);
+template <typename T>
+int predictor_tail_bwd(const float* dlogits, const T* y, int M, int H, const float* gamma, const float* beta, float eps, const float* W2, int F,
+                       float* dy, float* dW2, float* db2, float* dgamma, float* dbeta, cudaStream_t s);
+// d(total loss)/d(logits) with total = CE_mean(noised) + elbo_loss(noised); terms = output of loss_terms() (terms[1] = #noised)
+int loss_bwd(int N, const float* logits, const float* x0, const float* x_t, const double* terms, float* dlogits, cudaStream_t s);
+// clip_grad_norm_(max_norm) + AdamW over the flat buffers; d_w / d_off: device tables (master pointers, flat offsets [n + 1]);
+// grad_scale folds the 1 / world of the gradient average; d_scratch: 2 * #SM + 8 doubles; norm_out (optional): the pre-clip norm
+int adamw_step(float* const* d_w, const int64_t* d_off, int n_slots, size_t total, const float* g, float* m, float* v, float grad_scale,
+               float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step, double* d_scratch, float* norm_out, cudaStream_t s);
+// attention with probability dropout (forward) and its backward; SIMT fp32 arithmetic, Lk <= 128.  dq / dk / dv carry their own
+// row strides (they are slices of the fused [M, 3H] / [M, layers * 2H] gradient tensors); dE [2P-1, 64] fp32 is accumulated.
+template <typename T>
+int attention_train_fwd(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
+                        const float* key_mask, DropSpec dr, T* out, cudaStream_t s);
+template <typename T>
+int attention_bwd(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
+                  const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s);
 
 }  // namespace seqdiff

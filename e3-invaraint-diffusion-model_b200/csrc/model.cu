@@ -176,6 +176,10 @@ Model::~Model() {
 }
 
 void* Model::dalloc(size_t bytes) {
+  if (packing && repack_reuse) {  // re-finalize after an optimizer step: same tensors, same order, same sizes -> same buffers
+    if (packed_cursor < packed_allocs.size()) return packed_allocs[packed_cursor++];
+    return nullptr;
+  }
   void* p = nullptr;
   if (cudaMalloc(&p, bytes < 256 ? 256 : bytes) != cudaSuccess) return nullptr;
   (packing ? packed_allocs : allocs).push_back(p);
@@ -306,21 +310,40 @@ int Model::finalize(cudaStream_t s) {
       set_error("tensor never set: " + kv.first);
       return SEQDIFF_ERR_STATE;
     }
-  if (graph_exec) {  // weights changed: captured graph holds stale packed pointers only if re-allocated; be safe
-    cudaGraphExecDestroy(graph_exec);
-    graph_exec = nullptr;
-    graph_key = GraphKey();
+  if (!repack_reuse) {
+    if (graph_exec) {  // the packed copies are re-allocated: a captured graph would hold stale pointers
+      cudaGraphExecDestroy(graph_exec);
+      graph_exec = nullptr;
+      graph_key = GraphKey();
+    }
+    if (!packed_allocs.empty()) {  // re-finalize after a weight upload: drop the previous packed copies
+      SD_CUDA(cudaDeviceSynchronize());
+      for (void* p : packed_allocs) cudaFree(p);
+      packed_allocs.clear();
+    }
   }
-  if (!packed_allocs.empty()) {  // re-finalize after a weight update: drop the previous packed copies
-    SD_CUDA(cudaDeviceSynchronize());
-    for (void* p : packed_allocs) cudaFree(p);
-    packed_allocs.clear();
-  }
+  packed_cursor = 0;
   packing = true;
   const int64_t H = cfg.hidden_size, I = cfg.intermediate_size, P = cfg.max_position_embeddings;
   int rc = SEQDIFF_OK;
   auto R = [&](const std::string& n) -> const float* { return raw.at(n).ptr; };
   // fp32 matrix -> Wt with bf16 and fp16 copies
+  // training: every GEMM weight also gets its transposed copy in the operand type of the training precision
+  auto transposed = [&](Wt& w, int64_t rows, int64_t cols) {
+    w.rows = rows;
+    w.cols = cols;
+    if (train_prec < 0) return;
+    const size_t n = static_cast<size_t>(rows) * cols;
+    void* t = dalloc(n * (train_prec == SEQDIFF_FP32 ? 4 : 2));
+    int r = SEQDIFF_ERR_CUDA;
+    if (t) {
+      if (train_prec == SEQDIFF_FP32) r = transpose_cast<float>(w.f, static_cast<int>(rows), static_cast<int>(cols), static_cast<float*>(t), s);
+      else if (train_prec == SEQDIFF_BF16) r = transpose_cast<bf16>(w.f, static_cast<int>(rows), static_cast<int>(cols), static_cast<bf16*>(t), s);
+      else r = transpose_cast<f16>(w.f, static_cast<int>(rows), static_cast<int>(cols), static_cast<f16*>(t), s);
+    }
+    if (r != SEQDIFF_OK) rc = SEQDIFF_ERR_CUDA;
+    w.t = t;
+  };
   auto both = [&](const float* f, int64_t n) -> Wt {
     Wt w;
     w.f = f;
@@ -357,9 +380,11 @@ int Model::finalize(cudaStream_t s) {
     AttnW a;
     const float* w = stack({R(p + ".self.query.weight"), R(p + ".self.key.weight"), R(p + ".self.value.weight")}, H * H);
     a.qkv = both(w, 3 * H * H);
+    transposed(a.qkv, 3 * H, H);
     a.qkv_b = stack({R(p + ".self.query.bias"), R(p + ".self.key.bias"), R(p + ".self.value.bias")}, H);
     if (self_rel && cfg.relative_key) a.E = both(R(p + ".self.distance_embedding.weight"), (2 * P - 1) * 64);
     a.out = both(R(p + ".output.dense.weight"), H * H);
+    transposed(a.out, H, H);
     a.out_b = R(p + ".output.dense.bias");
     a.ln_w = R(p + ".output.LayerNorm.weight");
     a.ln_b = R(p + ".output.LayerNorm.bias");
@@ -368,21 +393,27 @@ int Model::finalize(cudaStream_t s) {
   auto se = [&](const std::string& p) -> SEW {
     SEW w;
     w.ada0 = both(R(p + ".adaLN_modulation.0.weight"), H * H);
+    transposed(w.ada0, H, H);
     w.ada0_b = R(p + ".adaLN_modulation.0.bias");
     w.ada2 = both(R(p + ".adaLN_modulation.2.weight"), 6 * H * H);
+    transposed(w.ada2, 6 * H, H);
     w.ada2_b = R(p + ".adaLN_modulation.2.bias");
     w.attn = attn(p + ".attn", true);
     w.m0 = both(R(p + ".mlp.0.weight"), 4 * H * H);
+    transposed(w.m0, 4 * H, H);
     w.m0_b = R(p + ".mlp.0.bias");
     w.m3 = both(R(p + ".mlp.3.weight"), 4 * H * H);
+    transposed(w.m3, H, 4 * H);
     w.m3_b = R(p + ".mlp.3.bias");
     return w;
   };
   ts_W = R("timestep_projector.W");
   auto ffn = [&](const std::string& p, LayerW& l) {
     l.inter = both(R(p + ".intermediate.dense.weight"), I * H);
+    transposed(l.inter, I, H);
     l.inter_b = R(p + ".intermediate.dense.bias");
     l.outd = both(R(p + ".output.dense.weight"), H * I);
+    transposed(l.outd, H, I);
     l.outd_b = R(p + ".output.dense.bias");
     l.oln_w = R(p + ".output.LayerNorm.weight");
     l.oln_b = R(p + ".output.LayerNorm.bias");
@@ -416,12 +447,14 @@ int Model::finalize(cudaStream_t s) {
     LayerW l;
     l.self = attn(p + ".attention", true);
     l.cq = both(R(p + ".crossattention.self.query.weight"), H * H);
+    transposed(l.cq, H, H);
     l.cq_b = R(p + ".crossattention.self.query.bias");
     ckv_w.push_back(R(p + ".crossattention.self.key.weight"));
     ckv_w.push_back(R(p + ".crossattention.self.value.weight"));
     ckv_b.push_back(R(p + ".crossattention.self.key.bias"));
     ckv_b.push_back(R(p + ".crossattention.self.value.bias"));
     l.cout = both(R(p + ".crossattention.output.dense.weight"), H * H);
+    transposed(l.cout, H, H);
     l.cout_b = R(p + ".crossattention.output.dense.bias");
     l.cln_w = R(p + ".crossattention.output.LayerNorm.weight");
     l.cln_b = R(p + ".crossattention.output.LayerNorm.bias");
@@ -429,9 +462,11 @@ int Model::finalize(cudaStream_t s) {
     layers.push_back(l);
   }
   ckv_all = both(stack(ckv_w, H * H), static_cast<int64_t>(ckv_w.size()) * H * H);
+  transposed(ckv_all, static_cast<int64_t>(ckv_w.size()) * H, H);
   ckv_all_b = stack(ckv_b, H);
   const std::string head = arch == kArchSequence ? "amino_acid_predictor" : "angles_predictor";
   p1 = both(R(head + ".dense1.weight"), H * H);
+  transposed(p1, H, H);
   p1_b = R(head + ".dense1.bias");
   p_ln_w = R(head + ".layer_norm.weight");
   p_ln_b = R(head + ".layer_norm.bias");

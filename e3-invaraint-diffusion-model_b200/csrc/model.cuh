@@ -13,6 +13,8 @@ struct Wt {
   const float* f = nullptr;
   const bf16* h = nullptr;
   const f16* g = nullptr;
+  const void* t = nullptr;  // training only: the TRANSPOSED matrix [in, out] in the training precision's operand type (dgrad GEMMs)
+  int64_t rows = 0, cols = 0;  // [out, in]
 };
 
 struct AttnW {
@@ -42,6 +44,24 @@ struct RawTensor {
   float* ptr = nullptr;
   int64_t numel = 0;
   bool set = false;
+};
+
+struct ParamSlot {  // one trainable tensor: fp32 master + its place in the flat gradient / AdamW-state buffers
+  std::string name;
+  float* w = nullptr;
+  int64_t numel = 0, off = 0;
+};
+
+// arguments of one training step (forward + loss + backward): reference model.py:313-367
+struct TrainArgs {
+  int precision, B, Ll, Lr;
+  const float *t_norm, *x_t, *x0, *lig_angle, *lig_mask, *rec_seq, *rec_angle, *rec_mask;
+  float p_hidden, p_attn;
+  uint64_t seed;
+  uint32_t step;
+  float* grads;      // flat fp32 [train_param_count()], overwritten
+  double* terms;     // [10] loss terms (seqdiff_loss_terms layout)
+  float* logits_out; // optional [B, Ll, feature_size]
 };
 
 struct Segment {  // a run of graphs sharing one padded length inside a token matrix
@@ -112,6 +132,27 @@ struct Model {
              const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, int diverse,
              const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t s);
 
+  // ---- training (train.cu) ------------------------------------------------------------------------------------------
+  std::vector<ParamSlot> slots;            // trainable tensors in flat-buffer order (fused groups contiguous)
+  std::map<std::string, int> slot_of;
+  int64_t train_total = 0;
+  int train_prec = -1;                     // precision the transposed operand copies (Wt::t) were built for; -1 = none
+  bool repack_reuse = false;               // finalize() after an optimizer step: re-fill the packed buffers in place
+  size_t packed_cursor = 0;
+  float** d_slot_w = nullptr;
+  int64_t* d_slot_off = nullptr;
+  double* d_opt_scratch = nullptr;
+  float* d_zero_bias = nullptr;
+  uint8_t* tws = nullptr;                  // training workspace (tape + backward buffers), grow-only
+  size_t tws_bytes = 0;
+  int build_slots();
+  int64_t train_param_count();
+  int train_step(const TrainArgs& a, cudaStream_t s);
+  int adamw(const float* grads, float* m, float* v, float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float wd,
+            int step, float* norm_out, cudaStream_t s);
+  int get_tensor(const char* name, float* out, int64_t numel, cudaStream_t s);
+  template <typename T> int train_t(int wfmt, const TrainArgs& a, cudaStream_t s);
+
   // structure_model/model.py:180-215.  phases: bit 0 = run the receptor branch, bit 1 = the ligand branch.  The receptor branch (embeddings,
   // receptor_emb, encoder, all decoder layers' cross K|V) depends on neither the timestep nor the ligand, so the sampling loop runs it
   // once and keeps the K|V block.
@@ -123,7 +164,7 @@ struct Model {
                     const float* rec_seq, const float* rec_angle, const float* rec_mask, const float* noise_steps, uint64_t seed,
                     uint64_t gid0, float* steps_out, float* final_out, cudaStream_t s);
 
- private:
+ public:
   void* dalloc(size_t bytes);
   size_t struct_workspace_need(int precision, int B, int Ll, int Lr) const;
   template <typename T>

@@ -26,30 +26,13 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "philox.cuh"
 
 namespace seqdiff {
 
 constexpr int C = SEQDIFF_NUM_CLASSES;
 constexpr int kRevThreads = 256;
 
-// ---- Philox4x32-10 (Salmon et al. 2011), counter-based: identical streams for any sharding ----------
-__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c[0];
-  const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c[2];
-  const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c[1] ^ k0;
-  const uint32_t n1 = static_cast<uint32_t>(p1);
-  const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c[3] ^ k1;
-  const uint32_t n3 = static_cast<uint32_t>(p0);
-  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-}
-__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-}
 // raw words for (graph, residue-in-graph, step): class j uses word j%4 of call j/4.
 // counter = (residue, step*8 + call, graph_lo, graph_hi), key = seed.
 __device__ __forceinline__ void philox_row(uint64_t seed, uint64_t graph, uint32_t residue, uint32_t step, uint32_t (&w)[C]) {

@@ -1,0 +1,827 @@
+// train_kernels.cu -- the rowwise / elementwise kernels of the TRAINING step (BASELINE configs[3]; reference
+// sequence_model/model.py:313-367 `get_loss` + `training_step` under autograd, train_model.py:30-33,95 AdamW + clip):
+// dropout, activation forward / backward, LayerNorm and adaLN-modulate backward, embedding / predictor-tail backward, the loss
+// gradient, 16-bit transposes for the weight-gradient GEMMs, and the fused clip + AdamW update.
+//
+// Conventions.  Gradients of the residual stream are fp32 [rows, H]; gradients that feed a tensor-core GEMM are also written
+// in the operand type T (bf16 / fp16; fp32 in the parity mode).  One warp owns one token row (H = 256 * VPL).  Parameter
+// gradients that are sums over rows (biases, LayerNorm affine, embedding / predictor weights) are reduced per CTA in shared
+// memory and flushed with one atomicAdd per element and CTA into the flat fp32 gradient buffer, which the step zeroes first.
+// Dropout masks are never stored: forward and backward regenerate them from Philox4x32-10 keyed by (seed, site, element).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace seqdiff {
+
+constexpr int kTrThreads = 256;
+
+template <typename T, int VPL>
+__device__ __forceinline__ void ld_row(const T* __restrict__ row, int lane, float (&v)[VPL][8]) {
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) load8<T>(row + (i * 32 + lane) * 8, v[i]);
+}
+template <typename T, int VPL>
+__device__ __forceinline__ void st_row(T* __restrict__ row, int lane, const float (&v)[VPL][8]) {
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) store8<T>(row + (i * 32 + lane) * 8, v[i]);
+}
+// (mean, rstd) exactly as the forward kernels compute them (rowwise.cu: row_stats)
+template <int VPL>
+__device__ __forceinline__ void stats_of(const float (&v)[VPL][8], int H, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+  mean = warp_sum(s) / static_cast<float>(H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[i][j] - mean;
+      q = fmaf(d, d, q);
+    }
+  rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(H) + eps);
+}
+// y = (x - mean) * rstd (no affine).  In: xhat (normalised values), g = dL/dy.  Out (in g): dL/dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
+template <int VPL>
+__device__ __forceinline__ void ln_bwd_core(const float (&xhat)[VPL][8], float (&g)[VPL][8], int H, float rstd) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1 += g[i][j];
+      s2 = fmaf(g[i][j], xhat[i][j], s2);
+    }
+  s1 = warp_sum(s1) / static_cast<float>(H);
+  s2 = warp_sum(s2) / static_cast<float>(H);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[i][j] = rstd * (g[i][j] - s1 - xhat[i][j] * s2);
+}
+
+#define SD_VPL_DISPATCH(H_, ...)                                        \
+  switch ((H_) / 256) {                                                  \
+    case 1: { constexpr int VPL = 1; __VA_ARGS__; } break;                      \
+    case 2: { constexpr int VPL = 2; __VA_ARGS__; } break;                      \
+    case 3: { constexpr int VPL = 3; __VA_ARGS__; } break;                      \
+    case 4: { constexpr int VPL = 4; __VA_ARGS__; } break;                      \
+    default: set_error("hidden_size must be 256, 512, 768 or 1024"); return SEQDIFF_ERR_INVALID; \
+  }
+
+// =====================================================================================================
+// transposes: out[c][r] = in[r][c] for a row-major [rows, cols] matrix of T; optional column sums (bias gradients)
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_colsum_kernel(const T* __restrict__ in, int rows, int cols, T* __restrict__ out, int pitch,
+                                                               float* __restrict__ colsum) {
+  __shared__ float tile[64][65];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  float cs = 0.f;
+#pragma unroll 4
+  for (int i = ty; i < 64; i += 4) {
+    const int r = r0 + i, c = c0 + tx;
+    const float v = (r < rows && c < cols) ? to_f32<T>(in[static_cast<size_t>(r) * cols + c]) : 0.f;
+    tile[i][tx] = v;
+    cs += v;
+  }
+  if (colsum) {  // 4 partial sums per column -> smem -> one atomic per column and CTA
+    __shared__ float part[4][64];
+    part[ty][tx] = cs;
+    __syncthreads();
+    if (ty == 0 && c0 + tx < cols) atomicAdd(colsum + c0 + tx, part[0][tx] + part[1][tx] + part[2][tx] + part[3][tx]);
+  } else {
+    __syncthreads();
+  }
+  if (out) {
+#pragma unroll 4
+    for (int i = ty; i < 64; i += 4) {
+      const int c = c0 + i, r = r0 + tx;
+      if (c < cols && r < pitch) out[static_cast<size_t>(c) * pitch + r] = from_f32<T>(tile[tx][i]);  // rows..pitch-1: zero padding
+    }
+  }
+}
+template <typename T>
+int transpose_colsum(const T* in, int rows, int cols, T* out, float* colsum, cudaStream_t s, int pitch) {
+  SD_CHECK(rows > 0 && cols > 0, "empty transpose");
+  if (pitch <= 0) pitch = rows;
+  SD_CHECK(pitch >= rows && pitch - rows < 64, "transpose: pitch must be rows rounded up by less than one tile");
+  SD_CUDA(launch_k(transpose_colsum_kernel<T>, dim3(ceil_div(cols, 64), ceil_div(pitch, 64)), dim3(256), 0, s, in, rows, cols, out, pitch, colsum));
+  SD_LAUNCHED("transpose", s);
+  return SEQDIFF_OK;
+}
+template int transpose_colsum<float>(const float*, int, int, float*, float*, cudaStream_t, int);
+template int transpose_colsum<bf16>(const bf16*, int, int, bf16*, float*, cudaStream_t, int);
+template int transpose_colsum<f16>(const f16*, int, int, f16*, float*, cudaStream_t, int);
+
+// fp32 [rows, cols] -> T [cols, rows] (weights: the fp32 master -> the transposed operand copy the dgrad GEMMs read)
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ in, int rows, int cols, T* __restrict__ out) {
+  __shared__ float tile[64][65];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll 4
+  for (int i = ty; i < 64; i += 4) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[static_cast<size_t>(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int i = ty; i < 64; i += 4) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) out[static_cast<size_t>(c) * rows + r] = from_f32<T>(tile[tx][i]);
+  }
+}
+template <typename T>
+int transpose_cast(const float* in, int rows, int cols, T* out, cudaStream_t s) {
+  SD_CUDA(launch_k(transpose_cast_kernel<T>, dim3(ceil_div(cols, 64), ceil_div(rows, 64)), dim3(256), 0, s, in, rows, cols, out));
+  SD_LAUNCHED("transpose_w", s);
+  return SEQDIFF_OK;
+}
+template int transpose_cast<float>(const float*, int, int, float*, cudaStream_t);
+template int transpose_cast<bf16>(const float*, int, int, bf16*, cudaStream_t);
+template int transpose_cast<f16>(const float*, int, int, f16*, cudaStream_t);
+
+// =====================================================================================================
+// activations and dropout
+// =====================================================================================================
+__device__ __forceinline__ float gelu_grad(float x) {  // d/dx [0.5 x (1 + erf(x / sqrt 2))]
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  return cdf + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float silu_grad(float x) {
+  const float sg = 1.0f / (1.0f + expf(-x));
+  return sg * (1.0f + x * (1.0f - sg));
+}
+
+// a = dropout(act(z)); kind 1 = erf-GELU, 2 = SiLU.  8 elements per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ z, size_t n8, int kind, DropSpec dr, T* __restrict__ a) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
+    float v[8];
+    load8<T>(z + 8 * i, v);
+    float keep[8];
+    drop_scales8(dr, 8 * i, keep);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (kind == 1 ? gelu_erf(v[j]) : silu(v[j])) * keep[j];
+    store8<T>(a + 8 * i, v);
+  }
+}
+template <typename T>
+int act_fwd(const T* z, size_t n, int kind, DropSpec dr, T* a, cudaStream_t s) {
+  SD_CHECK(n % 8 == 0 && (kind == 1 || kind == 2), "act_fwd: n % 8 and kind");
+  const size_t n8 = n / 8;
+  const int grid = static_cast<int>(n8 / 256 + 1 < 2048 ? n8 / 256 + 1 : 2048);
+  SD_CUDA(launch_k(act_fwd_kernel<T>, dim3(grid), dim3(256), 0, s, z, n8, kind, dr, a));
+  SD_LAUNCHED("act_fwd", s);
+  return SEQDIFF_OK;
+}
+// dz = da * keep * act'(z).  TG = type of the incoming gradient (T from a GEMM, float from a rowwise kernel).
+template <typename T, typename TG>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const TG* __restrict__ da, const T* __restrict__ z, size_t n8, int kind, DropSpec dr,
+                                                      T* __restrict__ dz) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
+    float g[8], v[8], keep[8];
+    load8<TG>(da + 8 * i, g);
+    load8<T>(z + 8 * i, v);
+    drop_scales8(dr, 8 * i, keep);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = g[j] * keep[j] * (kind == 1 ? gelu_grad(v[j]) : silu_grad(v[j]));
+    store8<T>(dz + 8 * i, g);
+  }
+}
+template <typename T, typename TG>
+int act_bwd(const TG* da, const T* z, size_t n, int kind, DropSpec dr, T* dz, cudaStream_t s) {
+  SD_CHECK(n % 8 == 0 && (kind == 1 || kind == 2), "act_bwd: n % 8 and kind");
+  const size_t n8 = n / 8;
+  const int grid = static_cast<int>(n8 / 256 + 1 < 2048 ? n8 / 256 + 1 : 2048);
+  SD_CUDA(launch_k(act_bwd_kernel<T, TG>, dim3(grid), dim3(256), 0, s, da, z, n8, kind, dr, dz));
+  SD_LAUNCHED("act_bwd", s);
+  return SEQDIFF_OK;
+}
+// o = dropout(d) + resid (fp32, in place on d): the hidden-state dropout that sits between a Linear and its residual add
+__global__ void __launch_bounds__(256) dropout_add_kernel(float* __restrict__ d, const float* __restrict__ resid, size_t n8, DropSpec dr) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
+    float v[8], r[8], keep[8];
+    load8<float>(d + 8 * i, v);
+    drop_scales8(dr, 8 * i, keep);
+    if (resid) {
+      load8<float>(resid + 8 * i, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], keep[j], r[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= keep[j];
+    }
+    store8<float>(d + 8 * i, v);
+  }
+}
+int dropout_add(float* d, const float* resid, size_t n, DropSpec dr, cudaStream_t s) {
+  SD_CHECK(n % 8 == 0, "dropout_add: n % 8");
+  const size_t n8 = n / 8;
+  const int grid = static_cast<int>(n8 / 256 + 1 < 2048 ? n8 / 256 + 1 : 2048);
+  SD_CUDA(launch_k(dropout_add_kernel, dim3(grid), dim3(256), 0, s, d, resid, n8, dr));
+  SD_LAUNCHED("dropout_add", s);
+  return SEQDIFF_OK;
+}
+// gT = T(g * keep): the fp32 gradient of a (dropout-ed) Linear output as the 16-bit operand of its backward GEMMs
+template <typename T>
+__global__ void __launch_bounds__(256) grad_cast_kernel(const float* __restrict__ g, size_t n8, DropSpec dr, T* __restrict__ out) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
+    float v[8], keep[8];
+    load8<float>(g + 8 * i, v);
+    drop_scales8(dr, 8 * i, keep);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= keep[j];
+    store8<T>(out + 8 * i, v);
+  }
+}
+template <typename T>
+int grad_cast(const float* g, size_t n, DropSpec dr, T* out, cudaStream_t s) {
+  SD_CHECK(n % 8 == 0, "grad_cast: n % 8");
+  const size_t n8 = n / 8;
+  const int grid = static_cast<int>(n8 / 256 + 1 < 2048 ? n8 / 256 + 1 : 2048);
+  SD_CUDA(launch_k(grad_cast_kernel<T>, dim3(grid), dim3(256), 0, s, g, n8, dr, out));
+  SD_LAUNCHED("grad_cast", s);
+  return SEQDIFF_OK;
+}
+#define SD_INST_ACT(T)                                                                              \
+  template int act_fwd<T>(const T*, size_t, int, DropSpec, T*, cudaStream_t);                       \
+  template int act_bwd<T, T>(const T*, const T*, size_t, int, DropSpec, T*, cudaStream_t);          \
+  template int grad_cast<T>(const float*, size_t, DropSpec, T*, cudaStream_t)
+SD_INST_ACT(float);
+SD_INST_ACT(bf16);
+SD_INST_ACT(f16);
+template int act_bwd<bf16, float>(const float*, const bf16*, size_t, int, DropSpec, bf16*, cudaStream_t);
+template int act_bwd<f16, float>(const float*, const f16*, size_t, int, DropSpec, f16*, cudaStream_t);
+
+// =====================================================================================================
+// LayerNorm backward (affine): h = LN(o) * g + b.  dh [M,H] fp32 -> do [M,H] fp32, dg / db accumulated
+// =====================================================================================================
+// CTA-level accumulation of per-feature sums: every warp adds its rows into registers, the warps of a CTA meet in smem, one
+// atomicAdd per feature and CTA.  Grid-stride over rows so that the number of atomics stays ~ #CTAs * H.
+template <int VPL>
+__device__ __forceinline__ void flush_feature_sums(float (&acc)[VPL][8], float* __restrict__ dst, float* smem_acc /*[H]*/, int H, int lane) {
+  // caller has zeroed smem_acc and synchronised
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(smem_acc + (i * 32 + lane) * 8 + j, acc[i][j]);
+  __syncthreads();
+  for (int e = threadIdx.x; e < H; e += blockDim.x) atomicAdd(dst + e, smem_acc[e]);
+  __syncthreads();
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(kTrThreads) layernorm_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ o, int M, int H,
+                                                                   const float* __restrict__ gamma, float eps, float* __restrict__ d_o,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sacc[];  // [2][H]
+  for (int e = threadIdx.x; e < 2 * H; e += kTrThreads) sacc[e] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ag[VPL][8], ab[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
+  for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
+    float x[VPL][8], g[VPL][8];
+    ld_row<float, VPL>(o + static_cast<size_t>(row) * H, lane, x);
+    ld_row<float, VPL>(dh + static_cast<size_t>(row) * H, lane, g);
+    float mean, rstd;
+    stats_of<VPL>(x, H, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float w8[8];
+      load8<float>(gamma + (i * 32 + lane) * 8, w8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x[i][j] = (x[i][j] - mean) * rstd;  // xhat
+        ag[i][j] = fmaf(g[i][j], x[i][j], ag[i][j]);
+        ab[i][j] += g[i][j];
+        g[i][j] *= w8[j];  // dL/d(xhat)
+      }
+    }
+    ln_bwd_core<VPL>(x, g, H, rstd);
+    st_row<float, VPL>(d_o + static_cast<size_t>(row) * H, lane, g);
+  }
+  flush_feature_sums<VPL>(ag, dgamma, sacc, H, lane);
+  flush_feature_sums<VPL>(ab, dbeta, sacc + H, H, lane);
+}
+int layernorm_bwd(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
+                  cudaStream_t s) {
+  const int need = ceil_div(M, kTrThreads / 32);
+  const int grid = need < 2 * num_sms() ? need : 2 * num_sms();
+  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_bwd_kernel<VPL>, dim3(grid), dim3(kTrThreads), 2 * H * sizeof(float), s, dh, o, M, H, gamma, eps,
+                                      d_o, dgamma, dbeta)));
+  SD_LAUNCHED("layernorm_bwd", s);
+  return SEQDIFF_OK;
+}
+
+// =====================================================================================================
+// SELayer residual update backward (forward: rowwise.cu ln_modulate_kernel)
+//   y = AFF ? LN(in; g, b, eps1) : in ;  n = LN0(y) (no affine, eps 1e-5) ;  out = x + gate * (n * (1 + scale) + shift)
+// dout [M,H] fp32 ->  din [M,H] fp32 (gradient of `in`), optional sum_out = din + dout (gradient that reaches x through BOTH
+// the residual and, for the attention update, through o = ... + x), d(shift, scale, gate) either written as T rows of dmodT
+// (mod_div == 1) or atomically accumulated into dmod32 [M / mod_div, 6H] (conditioning broadcast over the graph).
+// =====================================================================================================
+template <typename T, int VPL, bool AFF>
+__global__ void __launch_bounds__(kTrThreads) ln_modulate_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ in, int M, int H,
+                                                                     const float* __restrict__ lnw, const float* __restrict__ lnb, float eps1,
+                                                                     const T* __restrict__ mod, int mod_div, int chunk0, float* __restrict__ din,
+                                                                     float* __restrict__ sum_out, T* __restrict__ dmodT, float* __restrict__ dmod32,
+                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sacc[];  // [2][H] (AFF only)
+  if (AFF) {
+    for (int e = threadIdx.x; e < 2 * H; e += kTrThreads) sacc[e] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ag[VPL][8], ab[VPL][8];  // (dead code without AFF)
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
+  for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
+    float y[VPL][8], xh1[VPL][8], g[VPL][8];
+    ld_row<float, VPL>(in + static_cast<size_t>(row) * H, lane, y);
+    ld_row<float, VPL>(dout + static_cast<size_t>(row) * H, lane, g);
+    float mean1 = 0.f, rstd1 = 1.f;
+    if (AFF) {
+      stats_of<VPL>(y, H, eps1, mean1, rstd1);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float w8[8], b8[8];
+        load8<float>(lnw + (i * 32 + lane) * 8, w8);
+        load8<float>(lnb + (i * 32 + lane) * 8, b8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh1[i][j] = (y[i][j] - mean1) * rstd1;
+          y[i][j] = xh1[i][j] * w8[j] + b8[j];
+        }
+      }
+    }
+    float mean0, rstd0;
+    stats_of<VPL>(y, H, 1e-5f, mean0, rstd0);
+    const T* mrow = mod + static_cast<size_t>(row / mod_div) * (6 * H);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int e = (i * 32 + lane) * 8;
+      float sh[8], sc[8], gt[8], dsh[8], dsc[8], dgt[8];
+      load8<T>(mrow + (chunk0 + 0) * H + e, sh);
+      load8<T>(mrow + (chunk0 + 1) * H + e, sc);
+      load8<T>(mrow + (chunk0 + 2) * H + e, gt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float n = (y[i][j] - mean0) * rstd0;
+        const float go = g[i][j];
+        dgt[j] = go * (n * (1.0f + sc[j]) + sh[j]);
+        dsc[j] = go * gt[j] * n;
+        dsh[j] = go * gt[j];
+        y[i][j] = n;                              // xhat of LN0
+        g[i][j] = go * gt[j] * (1.0f + sc[j]);    // dL/dn
+      }
+      if (dmodT) {
+        T* drow = dmodT + static_cast<size_t>(row) * (6 * H);
+        store8<T>(drow + (chunk0 + 0) * H + e, dsh);
+        store8<T>(drow + (chunk0 + 1) * H + e, dsc);
+        store8<T>(drow + (chunk0 + 2) * H + e, dgt);
+      } else {
+        float* drow = dmod32 + static_cast<size_t>(row / mod_div) * (6 * H);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(drow + (chunk0 + 0) * H + e + j, dsh[j]);
+          atomicAdd(drow + (chunk0 + 1) * H + e + j, dsc[j]);
+          atomicAdd(drow + (chunk0 + 2) * H + e + j, dgt[j]);
+        }
+      }
+    }
+    ln_bwd_core<VPL>(y, g, H, rstd0);  // g = dL/dy
+    if (AFF) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float w8[8];
+        load8<float>(lnw + (i * 32 + lane) * 8, w8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ag[i][j] = fmaf(g[i][j], xh1[i][j], ag[i][j]);
+          ab[i][j] += g[i][j];
+          g[i][j] *= w8[j];
+        }
+      }
+      ln_bwd_core<VPL>(xh1, g, H, rstd1);
+    }
+    st_row<float, VPL>(din + static_cast<size_t>(row) * H, lane, g);
+    if (sum_out) {
+      float d2[VPL][8];
+      ld_row<float, VPL>(dout + static_cast<size_t>(row) * H, lane, d2);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d2[i][j] += g[i][j];
+      st_row<float, VPL>(sum_out + static_cast<size_t>(row) * H, lane, d2);
+    }
+  }
+  if constexpr (AFF) {
+    flush_feature_sums<VPL>(ag, dgamma, sacc, H, lane);
+    flush_feature_sums<VPL>(ab, dbeta, sacc + H, H, lane);
+  }
+}
+template <typename T>
+int ln_modulate_bwd(const float* dout, const float* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1,
+                    const T* mod, int mod_div, int chunk0, float* din, float* sum_out, T* dmodT, float* dmod32, float* dgamma, float* dbeta,
+                    cudaStream_t s) {
+  SD_CHECK((dmodT != nullptr) != (dmod32 != nullptr), "ln_modulate_bwd: exactly one of dmodT / dmod32");
+  SD_CHECK(!dmodT || mod_div == 1, "ln_modulate_bwd: direct T rows only for per-token conditioning");
+  const int need = ceil_div(M, kTrThreads / 32);
+  const int grid = need < 2 * num_sms() ? need : 2 * num_sms();
+  if (affine_first) {
+    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_bwd_kernel<T, VPL, true>, dim3(grid), dim3(kTrThreads), 2 * H * sizeof(float), s, dout, in, M, H,
+                                        lnw, lnb, eps1, mod, mod_div, chunk0, din, sum_out, dmodT, dmod32, dgamma, dbeta)));
+  } else {
+    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_bwd_kernel<T, VPL, false>, dim3(grid), dim3(kTrThreads), 0, s, dout, in, M, H, lnw, lnb, eps1,
+                                        mod, mod_div, chunk0, din, sum_out, dmodT, dmod32, dgamma, dbeta)));
+  }
+  SD_LAUNCHED("ln_modulate_bwd", s);
+  return SEQDIFF_OK;
+}
+#define SD_INST_LNMB(T)                                                                                                                  \
+  template int ln_modulate_bwd<T>(const float*, const float*, int, int, bool, const float*, const float*, float, const T*, int, int, float*, \
+                                  float*, T*, float*, float*, float*, cudaStream_t)
+SD_INST_LNMB(float);
+SD_INST_LNMB(bf16);
+SD_INST_LNMB(f16);
+
+// =====================================================================================================
+// BertEmbeddings backward (forward: embed_ln_multi_kernel): out = dropout(LN(x Wt + b) * g + beta) [+ te]
+// dout [M,H] fp32 (gradient of `out`).  Parameter gradients only (the inputs are data): dW [H, fin] (nn.Linear layout),
+// db [H], dg [H], dbeta [H].  lin = x Wt + b is recomputed (fin <= 32 multiply-adds per feature).
+// =====================================================================================================
+template <int VPL>
+__global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, int M, int fin, int H,
+                                                               const float* __restrict__ Wt, const float* __restrict__ b,
+                                                               const float* __restrict__ gamma, float eps, DropSpec dr, float* __restrict__ dW,
+                                                               float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sacc[];  // [fin + 3][H]: dW^T rows | db | dgamma | dbeta
+  for (int e = threadIdx.x; e < (fin + 3) * H; e += kTrThreads) sacc[e] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
+    float xin = lane < fin ? x[static_cast<size_t>(row) * fin + lane] : 0.f;
+    float v[VPL][8], g[VPL][8];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) load8<float>(b + (i * 32 + lane) * 8, v[i]);
+    for (int k = 0; k < fin; ++k) {
+      const float xk = __shfl_sync(0xffffffffu, xin, k);
+      if (xk == 0.f) continue;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float w8[8];
+        load8<float>(Wt + static_cast<size_t>(k) * H + (i * 32 + lane) * 8, w8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = fmaf(xk, w8[j], v[i][j]);
+      }
+    }
+    float mean, rstd;
+    stats_of<VPL>(v, H, eps, mean, rstd);
+    ld_row<float, VPL>(dout + static_cast<size_t>(row) * H, lane, g);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float keep[8], w8[8];
+      drop_scales8(dr, static_cast<size_t>(row) * H + (i * 32 + lane) * 8, keep);
+      load8<float>(gamma + (i * 32 + lane) * 8, w8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float go = g[i][j] * keep[j];
+        v[i][j] = (v[i][j] - mean) * rstd;
+        const int e = (i * 32 + lane) * 8 + j;
+        atomicAdd(sacc + (fin + 1) * H + e, go * v[i][j]);
+        atomicAdd(sacc + (fin + 2) * H + e, go);
+        g[i][j] = go * w8[j];
+      }
+    }
+    ln_bwd_core<VPL>(v, g, H, rstd);  // g = dL/d(lin)
+    for (int k = 0; k < fin; ++k) {
+      const float xk = __shfl_sync(0xffffffffu, xin, k);
+      if (xk == 0.f) continue;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(k) * H + (i * 32 + lane) * 8 + j, xk * g[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(fin) * H + (i * 32 + lane) * 8 + j, g[i][j]);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < fin * H; e += kTrThreads) {
+    const int k = e / H, h = e - k * H;
+    const float v = sacc[e];
+    if (v != 0.f) atomicAdd(dW + static_cast<size_t>(h) * fin + k, v);
+  }
+  for (int e = threadIdx.x; e < H; e += kTrThreads) {
+    atomicAdd(db + e, sacc[fin * H + e]);
+    atomicAdd(dgamma + e, sacc[(fin + 1) * H + e]);
+    atomicAdd(dbeta + e, sacc[(fin + 2) * H + e]);
+  }
+}
+int embed_bwd(const float* dout, const float* x, int M, int fin, int H, const float* Wt, const float* b, const float* gamma, float eps, DropSpec dr,
+              float* dW, float* db, float* dgamma, float* dbeta, cudaStream_t s) {
+  SD_CHECK(fin >= 1 && fin <= 32, "embed_bwd: fin in [1,32]");
+  const int need = ceil_div(M, kTrThreads / 32);
+  const int grid = need < num_sms() ? need : num_sms();
+  const size_t smem = static_cast<size_t>(fin + 3) * H * sizeof(float);
+#define SD_EB_LAUNCH()                                                                                              \
+  {                                                                                                                 \
+    auto kfn = embed_bwd_kernel<VPL>;                                                                               \
+    static bool configured = false;                                                                                 \
+    if (!configured) {                                                                                              \
+      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 35 * 1024 * 4));               \
+      configured = true;                                                                                            \
+    }                                                                                                               \
+    SD_CUDA(launch_k(kfn, dim3(grid), dim3(kTrThreads), smem, s, dout, x, M, fin, H, Wt, b, gamma, eps, dr, dW, db, dgamma, dbeta)); \
+  }
+  SD_VPL_DISPATCH(H, SD_EB_LAUNCH());
+#undef SD_EB_LAUNCH
+  SD_LAUNCHED("embed_bwd", s);
+  return SEQDIFF_OK;
+}
+
+// =====================================================================================================
+// AminoAcidPredictor tail backward (forward: predictor_tail_kernel): logits = LN(y; g, b) W2^T + b2
+// dlogits [M,F] fp32 -> dy [M,H] fp32; dW2 [F,H], db2 [F], dg [H], db [H] accumulated.
+// =====================================================================================================
+template <typename T, int VPL>
+__global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ y, int M, int H,
+                                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                        const float* __restrict__ W2, int F, float* __restrict__ dy,
+                                                                        float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dgamma,
+                                                                        float* __restrict__ dbeta) {
+  extern __shared__ float smem[];
+  float* sW = smem;                                   // [F][H]  W2
+  float* sdW = sW + static_cast<size_t>(F) * H;       // [F][H]  dW2 accumulators
+  float* sG = sdW + static_cast<size_t>(F) * H;       // [2][H]  dgamma | dbeta
+  float* sB = sG + 2 * H;                             // [32]    db2
+  for (int i = threadIdx.x; i < F * H; i += kTrThreads) { sW[i] = W2[i]; sdW[i] = 0.f; }
+  for (int i = threadIdx.x; i < 2 * H; i += kTrThreads) sG[i] = 0.f;
+  if (threadIdx.x < 32) sB[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
+    float v[VPL][8], g[VPL][8], ln[VPL][8];
+    ld_row<T, VPL>(y + static_cast<size_t>(row) * H, lane, v);
+    float mean, rstd;
+    stats_of<VPL>(v, H, eps, mean, rstd);
+    const float dl = lane < F ? dlogits[static_cast<size_t>(row) * F + lane] : 0.f;
+    if (lane < F && dl != 0.f) atomicAdd(sB + lane, dl);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float w8[8], b8[8];
+      load8<float>(gamma + (i * 32 + lane) * 8, w8);
+      load8<float>(beta + (i * 32 + lane) * 8, b8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] = (v[i][j] - mean) * rstd;
+        ln[i][j] = v[i][j] * w8[j] + b8[j];
+        g[i][j] = 0.f;
+      }
+    }
+    bool any = false;
+    for (int f = 0; f < F; ++f) {
+      const float d = __shfl_sync(0xffffffffu, dl, f);
+      if (d == 0.f) continue;  // rows outside the noised set carry a zero gradient: skip them entirely
+      any = true;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float w8[8];
+        load8<float>(sW + static_cast<size_t>(f) * H + (i * 32 + lane) * 8, w8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          g[i][j] = fmaf(d, w8[j], g[i][j]);
+          atomicAdd(sdW + static_cast<size_t>(f) * H + (i * 32 + lane) * 8 + j, d * ln[i][j]);
+        }
+      }
+    }
+    if (any) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float w8[8];
+        load8<float>(gamma + (i * 32 + lane) * 8, w8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = (i * 32 + lane) * 8 + j;
+          atomicAdd(sG + e, g[i][j] * v[i][j]);
+          atomicAdd(sG + H + e, g[i][j]);
+          g[i][j] *= w8[j];
+        }
+      }
+      ln_bwd_core<VPL>(v, g, H, rstd);
+    }
+    st_row<float, VPL>(dy + static_cast<size_t>(row) * H, lane, g);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * H; i += kTrThreads)
+    if (sdW[i] != 0.f) atomicAdd(dW2 + i, sdW[i]);
+  for (int i = threadIdx.x; i < H; i += kTrThreads) {
+    atomicAdd(dgamma + i, sG[i]);
+    atomicAdd(dbeta + i, sG[H + i]);
+  }
+  if (threadIdx.x < F) atomicAdd(db2 + threadIdx.x, sB[threadIdx.x]);
+}
+template <typename T>
+int predictor_tail_bwd(const float* dlogits, const T* y, int M, int H, const float* gamma, const float* beta, float eps, const float* W2, int F,
+                       float* dy, float* dW2, float* db2, float* dgamma, float* dbeta, cudaStream_t s) {
+  SD_CHECK(F <= 32, "feature_size > 32 not supported");
+  const int need = ceil_div(M, kTrThreads / 32);
+  const int grid = need < num_sms() ? need : num_sms();
+  const size_t smem = (2 * static_cast<size_t>(F) * H + 2 * H + 32) * sizeof(float);
+#define SD_PTB_LAUNCH()                                                                                              \
+  {                                                                                                                  \
+    auto kfn = predictor_tail_bwd_kernel<T, VPL>;                                                                    \
+    static bool configured = false;                                                                                  \
+    if (!configured) {                                                                                               \
+      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                   \
+      configured = true;                                                                                             \
+    }                                                                                                                \
+    SD_CUDA(launch_k(kfn, dim3(grid), dim3(kTrThreads), smem, s, dlogits, y, M, H, gamma, beta, eps, W2, F, dy, dW2, db2, dgamma, dbeta)); \
+  }
+  SD_VPL_DISPATCH(H, SD_PTB_LAUNCH());
+#undef SD_PTB_LAUNCH
+  SD_LAUNCHED("predictor_tail_bwd", s);
+  return SEQDIFF_OK;
+}
+template int predictor_tail_bwd<float>(const float*, const float*, int, int, const float*, const float*, float, const float*, int, float*, float*,
+                                       float*, float*, float*, cudaStream_t);
+template int predictor_tail_bwd<bf16>(const float*, const bf16*, int, int, const float*, const float*, float, const float*, int, float*, float*,
+                                      float*, float*, float*, cudaStream_t);
+template int predictor_tail_bwd<f16>(const float*, const f16*, int, int, const float*, const float*, float, const float*, int, float*, float*,
+                                     float*, float*, float*, cudaStream_t);
+
+// =====================================================================================================
+// loss gradient: total = CE_mean(noised rows) + elbo_loss(noised rows)   (model.py:330-344, utils.py:132-161)
+// With p = softmax(z), H = -sum p log p, y = one-hot target, q = softmax(one-hot target), N = #noised rows:
+//   dz = [ (p - y) + (p - q) - p * (log p + H) ] / N      on noised rows, 0 elsewhere.
+// (log_softmax(z + 1e-6) = log_softmax(z) analytically; the eps shift has no gradient.)  N is read from the loss-terms buffer
+// written by loss_terms() on the same stream (terms[1]).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) loss_bwd_kernel(int N, const float* __restrict__ logits, const float* __restrict__ x0,
+                                                       const float* __restrict__ x_t, const double* __restrict__ terms, float* __restrict__ dlogits) {
+  constexpr int C = SEQDIFF_NUM_CLASSES;
+  const double n_noised = terms[1];
+  const float inv_n = n_noised > 0.0 ? static_cast<float>(1.0 / n_noised) : 0.f;
+  for (int n = blockIdx.x * 256 + threadIdx.x; n < N; n += gridDim.x * 256) {
+    float z[C], a[C], b[C];
+#pragma unroll
+    for (int j4 = 0; j4 < C; j4 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(logits + static_cast<size_t>(n) * C + j4);
+      const float4 u = *reinterpret_cast<const float4*>(x0 + static_cast<size_t>(n) * C + j4);
+      const float4 w = *reinterpret_cast<const float4*>(x_t + static_cast<size_t>(n) * C + j4);
+      z[j4] = v.x; z[j4 + 1] = v.y; z[j4 + 2] = v.z; z[j4 + 3] = v.w;
+      a[j4] = u.x; a[j4 + 1] = u.y; a[j4 + 2] = u.z; a[j4 + 3] = u.w;
+      b[j4] = w.x; b[j4 + 1] = w.y; b[j4 + 2] = w.z; b[j4 + 3] = w.w;
+    }
+    int tgt = 0, xt = 0;
+#pragma unroll
+    for (int j = 1; j < C; ++j) {
+      if (a[j] > a[tgt]) tgt = j;
+      if (b[j] > b[xt]) xt = j;
+    }
+    float out[C];
+    if (xt != tgt) {
+      float mx = z[0];
+#pragma unroll
+      for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) sum += expf(z[j] - mx);
+      const float lse = logf(sum);
+      float amax = a[0];
+#pragma unroll
+      for (int j = 1; j < C; ++j) amax = fmaxf(amax, a[j]);
+      float qs = 0.f, q[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) { q[j] = expf(a[j] - amax); qs += q[j]; }
+      float ent = 0.f, p[C], lp[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        lp[j] = z[j] - mx - lse;
+        p[j] = expf(lp[j]);
+        ent -= p[j] * lp[j];
+      }
+#pragma unroll
+      for (int j = 0; j < C; ++j) out[j] = ((p[j] - (j == tgt ? 1.f : 0.f)) + (p[j] - q[j] / qs) - p[j] * (lp[j] + ent)) * inv_n;
+    } else {
+#pragma unroll
+      for (int j = 0; j < C; ++j) out[j] = 0.f;
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < C; j4 += 4)
+      *reinterpret_cast<float4*>(dlogits + static_cast<size_t>(n) * C + j4) = make_float4(out[j4], out[j4 + 1], out[j4 + 2], out[j4 + 3]);
+  }
+}
+int loss_bwd(int N, const float* logits, const float* x0, const float* x_t, const double* terms, float* dlogits, cudaStream_t s) {
+  SD_CHECK(N > 0, "empty loss");
+  SD_CUDA(launch_k(loss_bwd_kernel, dim3(ceil_div(N, 256)), dim3(256), 0, s, N, logits, x0, x_t, terms, dlogits));
+  SD_LAUNCHED("loss_bwd", s);
+  return SEQDIFF_OK;
+}
+
+// =====================================================================================================
+// optimizer: global-norm clip + AdamW on the flat (gradient, m, v) buffers and the fp32 master parameters
+// =====================================================================================================
+// sum of squares of the flat gradient, fp64 accumulation, fixed-order fold by the last CTA
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ partial, unsigned* __restrict__ arrive,
+                                                    double* __restrict__ out) {
+  double acc = 0.0;
+  const size_t n4 = n / 4;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * 256) {
+    const float4 v = *reinterpret_cast<const float4*>(g + 4 * i);
+    acc += static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z + static_cast<double>(v.w) * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - 4 * n4) {
+    const float v = g[4 * n4 + threadIdx.x];
+    acc += static_cast<double>(v) * v;
+  }
+  __shared__ double sw[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += sw[w];
+    partial[blockIdx.x] = v;
+    __threadfence();
+    last = atomicAdd(arrive, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned c = 0; c < gridDim.x; ++c) v += reinterpret_cast<const volatile double*>(partial)[c];
+    *out = v;
+    *arrive = 0u;
+  }
+}
+
+struct AdamSlots {  // device table: one entry per parameter tensor
+  float* const* w;        // [n] master weights
+  const int64_t* off;     // [n + 1] offsets into the flat buffers
+  int n;
+};
+// one CTA-stride pass over the flat index space; the tensor of an element is found by binary search in `off`
+__global__ void __launch_bounds__(256) adamw_kernel(AdamSlots sl, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                    size_t total, const double* __restrict__ sumsq, float grad_scale, float max_norm, float lr,
+                                                    float beta1, float beta2, float eps, float wd, float bc1, float bc2, float* __restrict__ norm_out) {
+  // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+  const float total_norm = sqrtf(static_cast<float>(*sumsq)) * grad_scale;
+  float coef = 1.0f;
+  if (max_norm > 0.f) coef = fminf(max_norm / (total_norm + 1e-6f), 1.0f);
+  if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = total_norm;
+  const float gs = grad_scale * coef;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * 256) {
+    int lo = 0, hi = sl.n;  // off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (static_cast<size_t>(sl.off[mid]) <= i) lo = mid; else hi = mid;
+    }
+    float* w = sl.w[lo] + (i - static_cast<size_t>(sl.off[lo]));
+    const float gi = g[i] * gs;
+    float p = *w;
+    p *= 1.0f - lr * wd;                       // decoupled weight decay (torch.optim.AdamW)
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p -= (lr / bc1) * (mi / denom);
+    *w = p;
+  }
+}
+int adamw_step(float* const* d_w, const int64_t* d_off, int n_slots, size_t total, const float* g, float* m, float* v, float grad_scale,
+               float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step, double* d_scratch, float* norm_out, cudaStream_t s) {
+  SD_CHECK(step >= 1 && total > 0, "adamw: step counts from 1");
+  SD_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, "flat gradient buffer must be 16 B aligned");
+  const int ctas = 2 * num_sms();
+  unsigned* arrive = reinterpret_cast<unsigned*>(d_scratch + ctas + 1);
+  SD_CUDA(launch_k(sumsq_kernel, dim3(ctas), dim3(256), 0, s, g, total, d_scratch + 1, arrive, d_scratch));
+  SD_LAUNCHED("grad_sumsq", s);
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  AdamSlots sl{d_w, d_off, n_slots};
+  SD_CUDA(launch_k(adamw_kernel, dim3(4 * num_sms()), dim3(256), 0, s, sl, g, m, v, total, d_scratch, grad_scale, max_norm, lr, beta1, beta2, eps, wd,
+                   bc1, bc2, norm_out));
+  SD_LAUNCHED("adamw", s);
+  return SEQDIFF_OK;
+}
+
+}  // namespace seqdiff

@@ -264,7 +264,8 @@ class ConditionalBertForDiffusionBase(nn.Module):
                 receptor_attention_masks, ligand_pos_ids=None, receptor_pos_ids=None):
         """reference model.py:200-237.  pos ids are accepted and ignored, as in the reference."""
         if self.training and (self.decoder_config.hidden_dropout_prob > 0 or self.decoder_config.attention_probs_dropout_prob > 0):
-            raise RuntimeError("the CUDA forward implements eval-mode (dropout-free) inference; call model.eval()")
+            raise RuntimeError("forward() is the eval-mode (dropout-free) inference path: call model.eval(), or use training_step() "
+                               "for the training-mode forward + backward")
         h = self._sync_handle()
         dev = self._handle_dev
         B, Ll = noised_ligand_seq.shape[0], noised_ligand_seq.shape[1]
@@ -324,7 +325,8 @@ class PeptideDiff(ConditionalBertForDiffusionBase):
     """reference model.py:256-450 without the Lightning base class (Trainer is out of scope, SURVEY.md
     section 2).  Inference-side members match the reference; `apply_aa_noise` runs the CUDA q-sample
     kernel; `get_loss` evaluates the reference's loss terms with the CUDA forward and the CUDA reduction
-    kernel (no autograd: backward kernels are not part of this round, so `training_step` raises)."""
+    kernel; `training_step` runs forward + loss + the full hand-written backward (csrc/train.cu) and
+    `configure_optimizers` returns the fused clip + AdamW step (train.py)."""
 
     def __init__(self, encoder_config, decoder_config, feature_names: List[str], loss_func, noise_schedule, timesteps,
                  max_epochs: int = 1, lr_scheduler=None, l2_lambda: float = 0.0, steps_per_epoch: int = 250,
@@ -394,12 +396,53 @@ class PeptideDiff(ConditionalBertForDiffusionBase):
         loss, *_ = self.get_loss(batch, t_norm, aa)
         return torch.mean(loss)
 
-    def training_step(self, batch, batch_idx):
-        raise NotImplementedError("training (backward kernels + NCCL gradient all-reduce) is not part of this round; "
-                                  "see DESIGN.md 'Out of scope / next'")
+    # ---- training (BASELINE configs[3]) ----------------------------------------------------------
+    def _flat_params(self):
+        from . import train as _train
+        if getattr(self, "_flat", None) is None or self._flat.handle is not self._handle:
+            self._sync_handle()
+            self._flat = _train.FlatParams(self)
+        return self._flat
 
-    def configure_optimizers(self):
-        """reference model.py:416-450 (optimizer only; Lightning scheduler dicts are out of scope)."""
+    def training_step(self, batch, batch_idx, t_int=None, noise_E=None):
+        """reference model.py:347-367.  Draws t (torch.randint, as the reference), q-samples x_t on the GPU, then runs forward
+        (dropout active in train() mode) + get_loss + the FULL backward in one C call: the gradients of the 61.06 M live
+        parameters land in the flat buffer `self._flat.grads` (what `loss.backward()` leaves in the .grad fields), ready for
+        `configure_optimizers()["optimizer"].step()`.  Returns the loss (device scalar); the logged quantities of the reference's
+        `log_dict` are kept in `self.last_log`.  Extra keywords (parity runs): `t_int` [B,1], `noise_E` [B*L,20]."""
+        from . import train as _train
+        x0 = batch["ligand_seq"]
+        dev = self._handle_dev if self._handle_dev is not None else next(self.parameters()).device
+        if t_int is None:
+            t_int = torch.randint(0, self.timesteps + 1, size=(x0.shape[0], 1), device=dev).float()
+        t_norm = t_int / self.timesteps
+        aa = self.apply_aa_noise(x0.to(dev), t_int, noise_E=noise_E)
+        flat = self._flat_params()
+        self._train_steps = getattr(self, "_train_steps", 0) + 1
+        terms, _ = _train.train_step_tensors(self, flat, batch, t_norm, aa, seed=self._noise_seed, step=self._train_steps)
+        loss, elbo, aa_noised_loss, aa_all_loss, aa_recovery_rate, aa_noise_rate = _train.loss_from_terms(terms)
+        self.last_log = {"aa_noise_rate": aa_noise_rate, "aa_recovery_rate": aa_recovery_rate, "avg_timestep": t_int.mean().int(),
+                         "train_loss": loss, "train_aa_noised_loss": aa_noised_loss, "train_aa_all_loss": aa_all_loss, "train_elbo_loss": elbo}
+        return loss
+
+    def configure_optimizers(self, group=None, grad_comm: str = "fp32"):
+        """reference model.py:416-450: AdamW(lr, weight_decay=l2_lambda) over all parameters -- here the fused clip + AdamW kernel
+        over the handle's flat parameter space, with the data-parallel gradient all-reduce in front of it.  The LinearWarmup
+        schedule (stepped per epoch, as Lightning does with interval="epoch") is applied by train.fit()."""
+        from . import train as _train
         if self.lr_scheduler not in (None, "OneCycleLR", "LinearWarmup"):
             raise ValueError(f"Unknown lr scheduler {self.lr_scheduler}")
-        return {"optimizer": torch.optim.AdamW(self.parameters(), lr=self.lr, weight_decay=self.l2_lambda)}
+        if getattr(self, "_optimizer", None) is None or self._optimizer.flat is not self._flat_params():
+            self._optimizer = _train.FlatAdamW(self._flat_params(), lr=self.lr, weight_decay=self.l2_lambda,
+                                               gradient_clip=getattr(self, "gradient_clip", 1.0), group=group, grad_comm=grad_comm)
+        return {"optimizer": self._optimizer}
+
+    def pull_weights(self):
+        """copies the trained masters from the C handle back into this module's parameters (state_dict / checkpoints)."""
+        from . import train as _train
+        _train.pull_weights(self)
+
+    def state_dict(self, *a, **kw):
+        if getattr(self, "_weights_dirty", False):
+            self.pull_weights()
+        return super().state_dict(*a, **kw)

@@ -154,6 +154,37 @@ SEQDIFF_API int seqdiff_decode(int B, int L, const float* final_seq, const float
 SEQDIFF_API int seqdiff_loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* ligand_mask, double* terms,
                        void* stream);
 
+/* ==== training step: BASELINE configs[3] ("sequence_model training step batch 128 graphs with NCCL gradient allreduce") ==========
+ * Replaces, for one optimizer step, autograd over PeptideDiff.training_step / get_loss (sequence_model/model.py:313-367),
+ * torch.optim.AdamW (model.py:420-422; lr 5e-5, weight_decay 0.1: train_model.py:30-31) and Lightning's gradient_clip_val = 1.0
+ * (train_model.py:33,95).  The library never communicates: a data-parallel caller all-reduces the flat gradient buffer between
+ * seqdiff_train_step and seqdiff_adamw_step (train.py does that with torch.distributed / NCCL).
+ *
+ * Trainable tensors = the state_dict of ConditionalBertForDiffusionBase minus the `timestep_projector.W` buffer and minus
+ * `receptor_feature_emb.*`, which the reference never uses (model.py:221) and whose .grad therefore stays None.  They are laid out
+ * in ONE flat fp32 index space (gradients, AdamW moments); seqdiff_train_param_table returns the (name, offset, numel) triples. */
+SEQDIFF_API int64_t seqdiff_train_param_count(seqdiff_model_t* m);   /* elements of the flat buffers, or -1 */
+/* names[i*name_stride..] (NUL-terminated), offsets[i], numels[i]; returns the number of tensors (call with cap = 0 to query it) */
+SEQDIFF_API int seqdiff_train_param_table(seqdiff_model_t* m, char* names, int name_stride, int64_t* offsets, int64_t* numels, int cap);
+/* forward (training mode) + loss + backward.  t_norm [B] = t_int / T as the reference passes it when training (quirk Q3);
+ * noised_ligand_seq = apply_aa_noise(ligand_seq, t_int) (seqdiff_apply_aa_noise); ligand_seq [B,L_lig,20] one-hot targets.
+ * p_hidden / p_attn = hidden_dropout_prob / attention_probs_dropout_prob (0 for parity runs); masks come from Philox keyed by
+ * (seed, dropout site, element, step).  grads_out: flat fp32 [param_count], overwritten with d(total_loss)/d(theta) for
+ * total_loss = CrossEntropy(noised rows) + elbo_loss(noised rows) (model.py:330-344).  loss_terms_out: double[10] on the device,
+ * layout of seqdiff_loss_terms.  logits_out (optional) [B,L_lig,20].  L_lig, L_rec <= 128 and B*L % 8 == 0. */
+SEQDIFF_API int seqdiff_train_step(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, const float* t_norm,
+                       const float* noised_ligand_seq, const float* ligand_seq, const float* ligand_angle, const float* ligand_mask,
+                       const float* receptor_seq, const float* receptor_angle, const float* receptor_mask, float p_hidden, float p_attn,
+                       uint64_t seed, uint32_t step, float* grads_out, double* loss_terms_out, float* logits_out, void* stream);
+/* g <- grad_scale * grads (grad_scale = 1 / world after a summing all-reduce); clip_grad_norm_(max_grad_norm) (<= 0: off);
+ * AdamW step `step` (1-based) on the handle's fp32 master weights with moments exp_avg / exp_avg_sq (flat fp32, zero-initialised
+ * by the caller); then the packed operand copies are refreshed in place.  grad_norm_out (optional, device): pre-clip global norm. */
+SEQDIFF_API int seqdiff_adamw_step(seqdiff_model_t* m, const float* grads, float* exp_avg, float* exp_avg_sq, float grad_scale,
+                       float max_grad_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                       float* grad_norm_out, void* stream);
+/* copies a master tensor out of the handle (checkpointing / tests): state_dict name -> fp32 [numel] */
+SEQDIFF_API int seqdiff_model_get_tensor(seqdiff_model_t* m, const char* name, float* out, int64_t numel, void* stream);
+
 /* ==== structure (angle) model: SURVEY.md section 8(f) row 3 ===========================================================
  * Same handle type and the same set_tensor / finalize / destroy calls; tensor names are the state_dict keys of
  * structure_model/model.py:163-178 ("receptor_seq_emb.linear.weight", "encoder.layer.0.attention.self.query.weight",

@@ -503,6 +503,38 @@ def get_loss(pred_aa, batch, noised_ligand_seq):
     return aa_noised_loss + elbo, elbo, aa_noised_loss, aa_all_loss, aa_recovery_rate, aa_noise_rate
 
 
+# --------------------------------------------------------------------------------------------
+# training step (sequence_model/model.py:347-367 under autograd; train_model.py:30-33,95)
+# --------------------------------------------------------------------------------------------
+def training_grads(sd: Dict[str, Tensor], cfg: OracleConfig, batch, t_norm, noised_ligand_seq):
+    """What `loss = training_step(batch); loss.backward()` leaves behind in the reference with dropout off (eval-mode arithmetic):
+    (loss 6-tuple, {state_dict key: gradient or None}).  torch autograd on the oracle forward: `receptor_feature_emb.*` never
+    enters the graph (model.py:221, quirk Q1) and `timestep_projector.W` is a buffer -> None."""
+    leaf = {k: v.detach().clone().requires_grad_(k != "timestep_projector.W") for k, v in sd.items()}
+    logits = denoiser_forward(leaf, cfg, t_norm, noised_ligand_seq, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                              batch["receptor_angles"], batch["receptor_attn_mask"])
+    out = get_loss(logits, batch, noised_ligand_seq)
+    out[0].backward()
+    return tuple(o.detach() for o in out), {k: (v.grad.detach() if v.grad is not None else None) for k, v in leaf.items()}, logits.detach()
+
+
+def adamw_reference_step(params: Dict[str, Tensor], grads: Dict[str, Optional[Tensor]], state: Dict, lr=5e-5, weight_decay=0.1, betas=(0.9, 0.999),
+                         eps=1e-8, max_norm=1.0):
+    """torch.nn.utils.clip_grad_norm_(max_norm) followed by ONE torch.optim.AdamW step (the real torch objects) on clones of
+    `params`; tensors whose gradient is None are left untouched, as torch does.  `state` carries the optimizer between calls."""
+    if "opt" not in state:
+        state["p"] = {k: torch.nn.Parameter(v.detach().clone()) for k, v in params.items()}
+        state["opt"] = torch.optim.AdamW(list(state["p"].values()), lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)
+    for k, prm in state["p"].items():
+        prm.grad = None if grads.get(k) is None else grads[k].detach().clone()
+    live = [prm for prm in state["p"].values() if prm.grad is not None]
+    norm = torch.nn.utils.clip_grad_norm_(live, max_norm) if max_norm and max_norm > 0 else torch.linalg.vector_norm(torch.stack([p.grad.norm() for p in live]))
+    for g_ in state["opt"].param_groups:
+        g_["lr"] = lr
+    state["opt"].step()
+    return {k: v.detach().clone() for k, v in state["p"].items()}, float(norm)
+
+
 def decode(final, batch):
     """The per-graph tail of denoise(), sample.py:208-224: (true_sequences, pred_sequences, recovery_rates)."""
     AA = "ACDEFGHIKLMNPQRSTVWY"

@@ -1,0 +1,298 @@
+"""Training step (BASELINE configs[3]): gradient parity of the hand-written backward against torch autograd on the oracle, the fused
+clip + AdamW update against torch.optim.AdamW, dropout consistency, and the data-parallel plumbing.
+
+Tolerances as written below: fp32 mode -- every gradient tensor within 1e-5 of the oracle's (max-norm relative to the tensor's own
+max, with an absolute floor for tensors whose gradient is ~0); 16-bit modes -- global relative L2 error of the flat gradient
+vector (bf16 < 3e-2 measured ~1e-2, fp16 < 5e-3) and cosine similarity > 0.999 per large tensor."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import O, make_model, sd_pkg
+
+gpu = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _case(L, B, NL, n_lig, n_rec, seed, T=50, Lr=None):
+    cfg = O.OracleConfig(max_position_embeddings=max(L, Lr or L), num_hidden_layers=NL)
+    state = O.init_state_dict(cfg, seed, "B")
+    batch = O.synthetic_batch(B, L, n_lig, n_rec, seed + 10)
+    if Lr is not None and Lr != L:
+        rec = O.synthetic_batch(B, Lr, n_lig, n_rec, seed + 11)
+        for k in ("receptor_seq", "receptor_angles", "receptor_attn_mask"):
+            batch[k] = rec[k]
+    g = torch.Generator().manual_seed(seed + 20)
+    t_int = torch.linspace(0.15 * T, 0.85 * T, B).round().reshape(B, 1)  # both noised and un-noised residues in every case
+    E = torch.empty(B * L, 20).exponential_(1, generator=g)
+    x_t = O.apply_aa_noise(batch["ligand_seq"], t_int, T, O.NoiseScheduleDiscrete("cosine", T), O.BlosumTransition(), E)
+    return cfg, state, batch, t_int / T, x_t
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU: the formulas the kernels implement, checked against autograd before any GPU is involved
+# ---------------------------------------------------------------------------------------------------
+def test_loss_gradient_formula_matches_autograd():
+    """csrc/train_kernels.cu loss_bwd_kernel: dz = [(p - y) + (p - q) - p (log p + H)] / N on the noised rows."""
+    g = torch.Generator().manual_seed(0)
+    N = 64
+    z = (torch.randn(N, 20, generator=g) * 2).requires_grad_(True)
+    x0 = F.one_hot(torch.randint(0, 20, (N,), generator=g), 20).float()
+    x_t = F.one_hot(torch.randint(0, 20, (N,), generator=g), 20).float()
+    batch = {"ligand_attn_mask": torch.ones(1, N), "ligand_seq": x0[None]}
+    loss = O.get_loss(z[None], batch, x_t[None])[0]
+    loss.backward()
+    noised = x_t.argmax(-1) != x0.argmax(-1)
+    p = torch.softmax(z.detach(), -1)
+    lp = torch.log_softmax(z.detach(), -1)
+    ent = -(p * lp).sum(-1, keepdim=True)
+    q = torch.softmax(x0, -1)
+    want = ((p - x0) + (p - q) - p * (lp + ent)) / noised.sum() * noised[:, None]
+    assert torch.allclose(z.grad, want, atol=2e-6, rtol=1e-4), (z.grad - want).abs().max()
+
+
+def test_linear_warmup_factor_matches_transformers():
+    from transformers import get_linear_schedule_with_warmup
+    import seqdiff_b200 as sd
+    prm = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([prm], lr=1.0)
+    sch = get_linear_schedule_with_warmup(opt, num_warmup_steps=15, num_training_steps=150)
+    for epoch in range(150):
+        assert opt.param_groups[0]["lr"] == pytest.approx(sd.train.linear_warmup_factor(epoch, 15, 150), abs=1e-12)
+        opt.step()
+        sch.step()
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import seqdiff_b200 as sd
+
+    class Flat:  # stand-in for train.FlatParams on CPU: only the flat gradient buffer takes part in the collective
+        grads = torch.arange(5000, dtype=torch.float32) * (rank + 1)
+        device = torch.device("cpu")
+        model = None
+        handle = None
+    opt = sd.train.FlatAdamW.__new__(sd.train.FlatAdamW)
+    opt.flat, opt.group, opt.grad_comm, opt.buckets, opt.last_allreduce_bytes = Flat, None, "fp32", 3, 0
+    opt.all_reduce_grads()
+    q.put((rank, Flat.grads.clone(), opt.last_allreduce_bytes))
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_world2_gloo():
+    """the one collective of the training path: bucketed sum over the data-parallel group (world 2, gloo, CPU)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+    for rank, gsum, nbytes in res:
+        assert torch.equal(gsum, torch.arange(5000, dtype=torch.float32) * 3)
+        assert nbytes == 5000 * 4
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------
+def _run_train_step(sd, m, batch, t_norm, x_t, **kw):
+    flat = sd.train.FlatParams(m)
+    terms, logits = sd.train.train_step_tensors(m, flat, batch, t_norm, x_t, want_logits=True, **kw)
+    torch.cuda.synchronize()
+    return flat, terms, logits
+
+
+def _compare_grads(flat, m, grads_ref, tol_rel, what):
+    worst = (0.0, "")
+    got_all, ref_all = [], []
+    gmax = max(float(v.abs().max()) for v in grads_ref.values() if v is not None)
+    for k, prm in m.named_parameters():
+        ref = grads_ref.get(k)
+        if k.startswith("receptor_feature_emb.") or k == "timestep_projector.W":
+            assert ref is None and k not in flat.table, k  # dead weight: no gradient on either side (quirk Q1)
+            continue
+        assert ref is not None and k in flat.table, k
+        got = flat.grad(k, tuple(prm.shape)).cpu()
+        got_all.append(got.reshape(-1))
+        ref_all.append(ref.reshape(-1))
+        err = float((got - ref).abs().max()) / max(float(ref.abs().max()), 1e-3 * gmax)
+        if err > worst[0]:
+            worst = (err, k)
+    got_all, ref_all = torch.cat(got_all), torch.cat(ref_all)
+    l2 = float((got_all - ref_all).norm() / ref_all.norm())
+    print(f"{what}: worst per-tensor max-norm rel err {worst[0]:.3e} ({worst[1]}); flat-vector L2 rel err {l2:.3e}; {got_all.numel()} gradient elements")
+    if tol_rel is not None:
+        assert worst[0] < tol_rel, worst
+    return worst[0], l2
+
+
+CASES = {"small-2layer": (32, 3, 2, (5, 32), (8, 32), 1, None), "Ll!=Lr": (24, 2, 1, (3, 24), (8, 40), 2, 40), "cfg4-shape": (128, 2, 6, (20, 64), (60, 128), 3, None)}
+
+
+@gpu
+@pytest.mark.parametrize("case", list(CASES), ids=list(CASES))
+def test_gradient_parity_fp32(case):
+    """every one of the live parameter gradients vs torch autograd on the oracle, fp32 mode, dropout off: < 1e-5."""
+    sd = sd_pkg()
+    L, B, NL, n_lig, n_rec, seed, Lr = CASES[case]
+    cfg, state, batch, t_norm, x_t = _case(L, B, NL, n_lig, n_rec, seed, Lr=Lr)
+    loss_ref, grads_ref, logits_ref = O.training_grads(state, cfg, batch, t_norm, x_t)
+    m = make_model(sd, cfg, state, "fp32", DEV)
+    flat, terms, logits = _run_train_step(sd, m, batch, t_norm, x_t)
+    assert float((logits.cpu() - logits_ref).abs().max() / logits_ref.abs().max()) < 1e-5
+    loss = sd.train.loss_from_terms(terms)
+    for a, b in zip(loss, loss_ref):
+        assert float(a) == pytest.approx(float(b), rel=2e-5, abs=1e-6, nan_ok=True)
+    _compare_grads(flat, m, grads_ref, 1e-5, f"fp32 {case}")
+    live = sum(v.numel() for v in grads_ref.values() if v is not None)
+    assert flat.live_numel == live
+    if case == "cfg4-shape":
+        assert 61_000_000 < live < 61_200_000  # ~61.06 M live elements (72.29 M - 11.24 M dead - buffer)
+    m.release()
+
+
+@gpu
+@pytest.mark.parametrize("precision,l2_tol", [("bf16", 3e-2), ("fp16", 5e-3)])
+def test_gradient_parity_16bit(precision, l2_tol):
+    sd = sd_pkg()
+    L, B, NL, n_lig, n_rec, seed, Lr = CASES["cfg4-shape"]
+    cfg, state, batch, t_norm, x_t = _case(L, B, NL, n_lig, n_rec, seed)
+    _, grads_ref, _ = O.training_grads(state, cfg, batch, t_norm, x_t)
+    m = make_model(sd, cfg, state, precision, DEV)
+    flat, terms, _ = _run_train_step(sd, m, batch, t_norm, x_t)
+    _, l2 = _compare_grads(flat, m, grads_ref, None, f"{precision} cfg4-shape")
+    assert l2 < l2_tol, l2
+    for k, prm in m.named_parameters():
+        if k in flat.table and prm.numel() >= 768 * 768:
+            a, b = flat.grad(k).cpu(), grads_ref[k].reshape(-1)
+            cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+            assert cos > 0.999, (k, cos)
+    m.release()
+
+
+@gpu
+def test_adamw_and_clip_match_torch():
+    """the fused 1/world + clip_grad_norm_(1.0) + AdamW kernel against the real torch objects, three steps, fed the SAME gradients
+    (the oracle's, written into the flat buffer by name) so that only the optimizer arithmetic is compared -- Adam's update
+    g / (|g| + eps) amplifies 1e-9-level gradient differences on near-zero elements, which would test the backward, not the update."""
+    sd = sd_pkg()
+    L, B, NL, n_lig, n_rec, seed, Lr = CASES["small-2layer"]
+    cfg, state, batch, t_norm, x_t = _case(L, B, NL, n_lig, n_rec, seed)
+    m = make_model(sd, cfg, state, "fp32", DEV)
+    flat = sd.train.FlatParams(m)
+    opt = sd.train.FlatAdamW(flat, lr=5e-5, weight_decay=0.1, gradient_clip=1.0)
+    cur, ostate = dict(state), {}
+    for step in range(3):
+        _, grads_ref, _ = O.training_grads(cur, cfg, batch, t_norm, x_t)
+        if step == 2:  # a step below the clip threshold as well
+            grads_ref = {k: (None if v is None else v * (0.5 / 80.0)) for k, v in grads_ref.items()}
+        cur, norm_ref = O.adamw_reference_step(cur, grads_ref, ostate, lr=5e-5, weight_decay=0.1, max_norm=1.0)
+        sd.train.train_step_tensors(m, flat, batch, t_norm, x_t)  # (exercises the real path; its result is then overwritten)
+        for k, v in grads_ref.items():
+            if v is not None:
+                flat.grad(k).copy_(v.reshape(-1))
+        opt.step()
+        assert float(opt.grad_norm) == pytest.approx(norm_ref, rel=1e-5)
+    m._flat = flat
+    sd.train.pull_weights(m)
+    worst = 0.0
+    for k, v in m.state_dict().items():
+        ref = cur[k]
+        worst = max(worst, float((v.cpu() - ref).abs().max()) / max(float(ref.abs().max()), 1e-6))
+        if k.startswith("receptor_feature_emb."):
+            assert torch.equal(v.cpu(), state[k])  # no gradient -> untouched (not even weight decay), as torch skips grad=None
+    print(f"weights after 3 AdamW steps: worst rel err {worst:.3e}")
+    assert worst < 2e-6
+    # the forward now runs on the UPDATED weights (packed copies were refreshed in place)
+    args = (t_norm, x_t, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"], batch["receptor_angles"], batch["receptor_attn_mask"])
+    with torch.no_grad():
+        want = O.denoiser_forward(cur, cfg, *args)
+        got = m(*[a.to(DEV) for a in args]).cpu()
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-5
+    m.release()
+
+
+@gpu
+def test_dropout_masks_are_consistent_between_forward_and_backward():
+    """p = 0.1: same (seed, step) -> identical gradients; another step -> different masks; and the gradient is the derivative of
+    the loss UNDER THOSE MASKS: a central finite difference along a random direction (fp32 mode) matches g . d."""
+    sd = sd_pkg()
+    L, B, NL, n_lig, n_rec, seed, Lr = CASES["small-2layer"]
+    cfg, state, batch, t_norm, x_t = _case(L, B, NL, n_lig, n_rec, seed)
+    m = make_model(sd, cfg, state, "fp32", DEV)
+    m.train()
+    kw = dict(p_hidden=0.1, p_attn=0.1, seed=11, step=5)
+    flat, terms, _ = _run_train_step(sd, m, batch, t_norm, x_t, **kw)
+    g0 = flat.grads.clone()
+    loss0 = float(sd.train.loss_from_terms(terms)[0])
+    flat2, terms2, _ = _run_train_step(sd, m, batch, t_norm, x_t, **kw)
+    # same masks -> same gradients (up to the summation order of the atomics that fold bias / LayerNorm / dE gradients)
+    assert float((flat2.grads - g0).abs().max()) < 1e-5 * float(g0.abs().max()) and float(sd.train.loss_from_terms(terms2)[0]) == loss0
+    flat3, terms3, _ = _run_train_step(sd, m, batch, t_norm, x_t, **dict(kw, step=6))
+    assert float((flat3.grads - g0).abs().max()) > 1e-3 * float(g0.abs().max()) and float(sd.train.loss_from_terms(terms3)[0]) != loss0
+    m.eval()
+    _, terms_eval, _ = _run_train_step(sd, m, batch, t_norm, x_t, **kw)  # eval(): dropout off whatever p says
+    assert float(sd.train.loss_from_terms(terms_eval)[0]) != loss0
+    m.train()
+    # directional derivative
+    gen = torch.Generator().manual_seed(3)
+    names = [k for k in flat.table if k.endswith("weight") and "LayerNorm" not in k and "layer_norm" not in k]
+    direction = {k: torch.randn(state[k].shape, generator=gen) * state[k].abs().mean() for k in names}
+    gd = sum(float((flat.grad(k, tuple(state[k].shape)).cpu().double() * direction[k].double()).sum()) for k in names)
+    eps = 2e-3
+    losses = []
+    for sgn in (+1, -1):
+        st = {k: (v + sgn * eps * direction[k] if k in direction else v) for k, v in state.items()}
+        m.load_state_dict(st, strict=True)
+        m.to(DEV)
+        _, t_, _ = _run_train_step(sd, m, batch, t_norm, x_t, **kw)
+        losses.append(float(sd.train.loss_from_terms(t_)[0].double()))
+    fd = (losses[0] - losses[1]) / (2 * eps)
+    print(f"dropout on: directional derivative {gd:.6f} vs central finite difference {fd:.6f}")
+    assert fd == pytest.approx(gd, rel=2e-2, abs=1e-3)
+    m.release()
+
+
+@gpu
+def test_training_step_api_and_fit_reduce_the_loss():
+    """PeptideDiff.training_step / configure_optimizers / train.fit: a few steps on one fixed batch drive the loss down, the trained
+    weights come back through state_dict(), and sampling still works on the updated handle."""
+    sd = sd_pkg()
+    torch.manual_seed(0)
+    L, B = 64, 4
+    sd.sample.DEVICE = torch.device(DEV)
+    sd.sample.CONFIG.update(max_seq_len=L, timesteps=50, num_hidden_layers=2)
+    model = sd.sample.get_model()
+    sd.sample.CONFIG.update(num_hidden_layers=6)
+    model.lr, model.lr_scheduler, model.precision = 2e-4, None, "bf16"
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    batch = O.synthetic_batch(B, L, (20, 60), (30, 64), 5)
+    model.train()
+    opt = model.configure_optimizers()["optimizer"]
+    t_int = torch.full((B, 1), 40.0)
+    g = torch.Generator().manual_seed(9)
+    E = torch.empty(B * L, 20).exponential_(1, generator=g)
+    losses = []
+    for i in range(12):
+        losses.append(float(model.training_step(batch, i, t_int=t_int, noise_E=E)))
+        opt.step()
+    print("losses:", [round(x, 3) for x in losses])
+    assert all(math.isfinite(x) for x in losses) and losses[-1] < losses[0] - 0.2
+    after = model.state_dict()
+    changed = [k for k in before if not torch.equal(before[k].cpu(), after[k].cpu())]
+    assert any(k.startswith("decoder.layer.0") for k in changed) and not any(k.startswith("receptor_feature_emb") for k in changed)
+    hist = sd.train.fit(model, [batch], max_epochs=2, log=None)
+    assert len(hist) == 2 and all(math.isfinite(h) for h in hist)
+    model.eval()
+    out = sd.denoise_tensors(batch, model, sd.PredefinedNoiseScheduleDiscrete("cosine", 5), sd.BlosumTransition(x_classes=20), True, timesteps=5)
+    assert torch.isfinite(out).all()
+    model.release()
