@@ -43,6 +43,9 @@ WORKLOADS = {
     "cfg3": dict(L=512, T=50, batch=256, scaling="strong", n_lig=(48, 48), n_rec=(464, 464), flops=85.229e9,
                  text="BASELINE configs[2]: ext-neighbour pockets, 256 graphs of 512 residues (n_lig=48, n_rec=464) sharded over the GPUs, "
                       "T={T} (reference default), {B} graphs on this rank, diverse=True, random-init weights"),
+    "cfg4": dict(L=128, T=50, batch=128, scaling="strong", n_lig=(5, 64), n_rec=(16, 128), flops=3 * 18.369e9,
+                 text="BASELINE configs[3]: training step, global batch 128 graphs over the GPUs ({B} on this rank), L=128, T={T}, dropout 0.1, "
+                      "AdamW + clip, one NCCL gradient all-reduce per step"),
 }
 
 
@@ -193,6 +196,127 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------------
+def cfg3_strong_record(sd, dev, world, rank, barrier, precision, steps=2, warmup=1):
+    """BASELINE configs[2] on the ranks of this job: 256 ext-pocket graphs of 512 residues (n_lig 48, n_rec 464), T = 50, block-
+    partitioned over the GPUs (strong scaling: 256 / world graphs per rank, no data-path collective).  Device-resident inputs, CUDA
+    events, max over ranks.  Returned as the `cfg3_strong` record of the main JSON line so that the driver's 1/2/4/8-GPU scaling run
+    carries the numbers of the NAMED strong-scaling configuration next to the cfg-2 value."""
+    import torch.distributed as dist
+    global L
+    keep_L, wl = L, WORKLOADS["cfg3"]
+    L = wl["L"]
+    try:
+        total, T = wl["batch"], wl["T"]
+        lo, hi = sd.shard_bounds(total, world, rank)
+        Bl = hi - lo
+        torch.manual_seed(0)
+        common = dict(max_position_embeddings=L, intermediate_size=I, num_hidden_layers=NL, position_embedding_type="relative_key")
+        model = sd.ConditionalBertForDiffusionBase(sd.BertConfig(**common), sd.BertConfig(**common, is_decoder=True, add_cross_attention=True), 20)
+        model = model.eval().to(dev)
+        model.precision = precision
+        sched, trans = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20, timestep=500)
+        batch, x_T = synthetic_workload(total, n_lig=wl["n_lig"], n_rec=wl["n_rec"])  # the SAME 256 graphs for every world size
+        dbatch = {k: (v[lo:hi].to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        dx_T = x_T[lo:hi].to(dev)
+        run = lambda: sd.denoise_tensors(dbatch, model, sched, trans, True, timesteps=T, x_T=dx_T, seed=5, graph_id0=lo)
+        for _ in range(warmup):
+            run()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = run()
+        e1.record()
+        barrier()
+        ms_rank = e0.elapsed_time(e1)
+        ms = torch.tensor([ms_rank], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.item()
+        ok = bool(torch.isfinite(out).all())
+        value = total * T * steps / (ms * 1e-3)
+        peak, _, _ = measured_peaks()
+        model.release()
+        del model
+        torch.cuda.empty_cache()
+        return {"workload": wl["text"].format(T=T, B=Bl), "scaling": "strong", "graphs_total": total, "graphs_per_gpu": Bl, "L": L, "timesteps": T,
+                "value": value, "unit": UNIT, "ms_per_sampling": ms / steps, "ms_this_rank": ms_rank / steps, "steps": steps, "warmup": warmup,
+                "finite": ok, "whole_step_model_flops_frac": (value / world) * wl["flops"] / 1e12 / peak, "dtype": precision}
+    finally:
+        L = keep_L
+
+
+def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=3, global_batch=128, grad_comm="fp32"):
+    """BASELINE configs[3]: one optimizer step of the sequence denoiser on a GLOBAL batch of 128 graphs (L = 128, T = 50, dropout 0.1,
+    AdamW lr 5e-5 wd 0.1, clip 1.0: train_model.py:17-33), data-parallel over the ranks (128 / world graphs each), ONE gradient
+    all-reduce per step over NCCL (61.06 M live parameters).  Reports whole steps (training_step + all-reduce + clip + AdamW), the
+    same without the all-reduce, and the all-reduce alone => exposed-communication fraction and achieved bus bandwidth."""
+    import torch.distributed as dist
+    global L
+    keep_L = L
+    L = 128
+    try:
+        T = 50
+        lo, hi = sd.shard_bounds(global_batch, world, rank)
+        Bl = hi - lo
+        torch.manual_seed(0)
+        common = dict(max_position_embeddings=L, intermediate_size=I, num_hidden_layers=NL, position_embedding_type="relative_key",
+                      hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+        model = sd.PeptideDiff(sd.BertConfig(**common), sd.BertConfig(**common, is_decoder=True, add_cross_attention=True), list(sd.AA_VOCAB),
+                               torch.nn.CrossEntropyLoss(), "cosine", T, max_epochs=150, lr_scheduler="LinearWarmup", l2_lambda=0.1, learning_rate=5e-5)
+        model = model.to(dev).train()
+        model.precision = precision
+        batch, _ = synthetic_workload(global_batch, n_lig=(5, 64), n_rec=(16, 128))
+        dbatch = {k: (v[lo:hi].to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        opt = model.configure_optimizers(grad_comm=grad_comm)["optimizer"]
+
+        def step(i, skip=False):
+            loss = model.training_step(dbatch, i)
+            opt.step(skip_all_reduce=skip)
+            return loss
+
+        def timed(fn, n):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                r = fn(i)
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return ms.item() / n, r
+
+        n0 = sd.lib().seqdiff_launch_count()
+        for i in range(warmup):
+            step(i)
+        launches_per_step = (sd.lib().seqdiff_launch_count() - n0) // max(warmup, 1)
+        ms_full, loss = timed(lambda i: step(i), steps)
+        ms_nocomm, _ = timed(lambda i: step(i, skip=True), steps)
+        ms_ar, _ = timed(lambda i: opt.all_reduce_grads(), steps) if world > 1 else (0.0, None)
+        nbytes = opt.last_allreduce_bytes
+        flops = 3 * 18.369e9 * global_batch  # forward + backward ~ 3x the forward's algorithmic FLOPs
+        peak, _, _ = measured_peaks()
+        rec = {"workload": f"BASELINE configs[3]: training step, global batch {global_batch} graphs ({Bl} on this rank), L=128, T=50, dropout 0.1, "
+                           "AdamW lr 5e-5 wd 0.1, clip 1.0, one NCCL gradient all-reduce per step",
+               "scaling": "strong", "global_batch": global_batch, "graphs_per_gpu": Bl, "dtype": precision,
+               "value": global_batch / (ms_full * 1e-3), "unit": "graphs/s (training)", "steps_per_s": 1e3 / ms_full, "ms_per_step": ms_full,
+               "ms_per_step_without_allreduce": ms_nocomm, "ms_allreduce_alone": ms_ar,
+               "exposed_allreduce_frac": max(0.0, (ms_full - ms_nocomm) / ms_full) if world > 1 else 0.0,
+               "allreduce_bytes": int(nbytes), "grad_comm": grad_comm, "live_parameters": int(opt.flat.live_numel),
+               "allreduce_bus_GBps": (2.0 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9) if (world > 1 and ms_ar > 0) else None,
+               "train_flops_frac_of_peak": flops / world / (ms_full * 1e-3) / 1e12 / peak, "launches_per_step": int(launches_per_step),
+               "loss_last": float(loss), "steps": steps, "warmup": warmup}
+        model.release()
+        del model, opt
+        torch.cuda.empty_cache()
+        return rec
+    finally:
+        L = keep_L
+
+
+# ----------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,7 +327,7 @@ def main():
     ap.add_argument("--timesteps", type=int, default=0, help="T (default: the workload's; smaller only for profiling runs)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"], help="cfg2 = headline (B=64/GPU, L=128); cfg3 = 256 ext-pockets of 512 residues sharded over the GPUs (strong scaling)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"], help="cfg2 = headline (B=64/GPU, L=128); cfg3 = 256 ext-pockets of 512 residues sharded over the GPUs (strong scaling)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / roofline / cpu legs (profiling runs)")
     args = ap.parse_args()
     global L
@@ -244,6 +368,25 @@ def main():
     import seqdiff_b200 as sd
     lib = sd.lib()
     sd.sample.DEVICE = dev
+
+    def barrier0():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    if args.workload == "cfg4":  # the training configuration on its own: one line whose value is training graphs/s
+        with ClockSampler(local) as clk:
+            rec = cfg4_train_record(sd, dev, world, rank, barrier0, args.precision, steps=max(args.steps, 1), warmup=max(args.warmup, 3))
+        if rank == 0:
+            emit({"metric": "training graphs/s (forward + backward + gradient all-reduce + clip + AdamW; cfg4: global batch 128, L=128)",
+                  "value": rec["value"], "unit": rec["unit"], "n_gpus": world, "steps": rec["steps"], "warmup": rec["warmup"],
+                  "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.precision,
+                  "data": "synthetic", "config": {"workload": rec["workload"], "l2": "activations + 244 MB of gradients per step >> 126 MB L2"},
+                  "clocks": clk.summary(), "gpu_launches": rec["launches_per_step"] * rec["steps"], "cfg4_train": rec})
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     sd.sample.CONFIG.update(timesteps=args.timesteps, max_seq_len=L, batch_size=args.batch)
     B, T = args.batch, args.timesteps
     torch.manual_seed(0)  # identical random-init weights on every rank (replicated model, 145 MB bf16)
@@ -301,6 +444,15 @@ def main():
                          "l2": "per-step working set of activations (0.9 GB at cfg2, ~10 GB at cfg3) >> 126 MB L2 (no explicit flush needed)",
                          "pocket_graphs_per_s": value / T, "edge_msgs_per_s": value * 15 * L * L},
               "clocks": clk.summary(), "gpu_launches": int(launches)}
+
+    if not args.no_extras and args.workload == "cfg2":
+        # ---- the two other multi-GPU configurations BASELINE.json names, on the ranks of THIS job (all ranks take part) ----
+        for key, fn in (("cfg3_strong", cfg3_strong_record), ("cfg4_train", cfg4_train_record)):
+            try:
+                result[key] = fn(sd, dev, world, rank, barrier, args.precision)
+            except Exception as ex:  # extras never cost the headline line
+                result[key] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+                barrier()
 
     if not args.no_extras:
         # ---- end to end through the public API: denoise(batch_on_host, ...) -> decoded sequences on the host ----

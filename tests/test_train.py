@@ -201,7 +201,10 @@ def test_adamw_and_clip_match_torch():
             if v is not None:
                 flat.grad(k).copy_(v.reshape(-1))
         opt.step()
-        assert float(opt.grad_norm) == pytest.approx(norm_ref, rel=1e-5)
+        # the kernel accumulates the squared norm in fp64; torch's clip_grad_norm_ (fp32 per-tensor norms) agrees to ~1e-4
+        norm64 = math.sqrt(sum(float((v.double() ** 2).sum()) for v in grads_ref.values() if v is not None))
+        assert float(opt.grad_norm) == pytest.approx(norm64, rel=2e-6)
+        assert float(opt.grad_norm) == pytest.approx(norm_ref, rel=2e-4)
     m._flat = flat
     sd.train.pull_weights(m)
     worst = 0.0
