@@ -360,27 +360,27 @@ static int attn_choice() {
 #endif
 template <typename T>
 static int attention_any16(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
-                           int P, const float* key_mask, T* out, cudaStream_t s) {
+                           int P, const float* key_mask, T* out, cudaStream_t s, const AttnPack* pack) {
 #ifdef SEQDIFF_AB_KERNELS
   const int c = attn_choice();
-  if (c != 0) {
+  if (c != 0 && !pack) {
     // "auto_r1": the per-shape choice before the pipelined kernel existed (legacy for one-key-block relative_key, tc otherwise)
     const bool legacy = c == 2 || (c == 3 && dist_emb != nullptr && Lk <= kKB);
     if (legacy) return attention_16<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
     return attention_tc<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
   }
 #endif
-  return attention_pipe<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  return attention_pipe<T>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, pack);
 }
 template <>
 int attention<bf16>(int B, int heads, int Lq, int Lk, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv,
-                    const bf16* dist_emb, int P, const float* key_mask, bf16* out, cudaStream_t s) {
-  return attention_any16<bf16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+                    const bf16* dist_emb, int P, const float* key_mask, bf16* out, cudaStream_t s, const AttnPack* pack) {
+  return attention_any16<bf16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, pack);
 }
 template <>
 int attention<f16>(int B, int heads, int Lq, int Lk, const f16* q, int ldq, const f16* k, int ldk, const f16* v, int ldv,
-                   const f16* dist_emb, int P, const float* key_mask, f16* out, cudaStream_t s) {
-  return attention_any16<f16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+                   const f16* dist_emb, int P, const float* key_mask, f16* out, cudaStream_t s, const AttnPack* pack) {
+  return attention_any16<f16>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, pack);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
 
 template <>
 int attention<float>(int B, int heads, int Lq, int Lk, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                     const float* dist_emb, int P, const float* key_mask, float* out, cudaStream_t s) {
+                     const float* dist_emb, int P, const float* key_mask, float* out, cudaStream_t s, const AttnPack* pack) {
+  SD_CHECK(pack == nullptr, "packed batches run in the 16-bit modes only");
   SD_CHECK(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "empty attention");
   SD_CHECK(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "row strides must be multiples of 4 elements");
   SD_CHECK(!dist_emb || (Lq <= P && Lk <= P), "sequence longer than max_position_embeddings");

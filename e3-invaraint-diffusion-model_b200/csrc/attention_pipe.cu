@@ -125,7 +125,11 @@ template <typename T, bool REL>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO, const float* __restrict__ key_mask, int heads, int Lq,
-                      int Lk, int P, uint32_t fmt, int nqb, int n_items, unsigned long long* __restrict__ trace) {
+                      int Lk, int P, uint32_t fmt, int nqb, int n_items, unsigned long long* __restrict__ trace, const int* __restrict__ q_off,
+                      const int* __restrict__ k_off, const int* __restrict__ q_len, int Lk_mask, T* __restrict__ out_raw) {
+  // q_off != NULL: packed (ragged) batch -- graph b's rows start at q_off[b] / k_off[b] of the packed q / k / v matrices, Lq / Lk are
+  // the largest lengths of the batch, key_mask keeps its padded pitch Lk_mask, and output rows are stored per thread with a
+  // q_len[b] predicate (a bulk tile store would spill into the next graph's rows).
   using C = PipeCfg<REL>;
   constexpr int NKS = C::kNKS, NS = C::kNS, NVS = C::kNVS;
   constexpr float kScale2 = 0.125f * kLog2e;
@@ -198,19 +202,21 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int qs = it & 1;
         mbar_wait(&q_empty[qs], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx_e(&q_full[qs], 16384);
-        tma_load_2d_e(smem + C::kQ + qs * 16384, &tmQ, &q_full[qs], w.h * 64, w.b * Lq + w.q0);
+        const int q_row0 = q_off ? __ldg(q_off + w.b) : w.b * Lq;
+        const int k_row0 = q_off ? __ldg(k_off + w.b) : w.b * Lk;
+        tma_load_2d_e(smem + C::kQ + qs * 16384, &tmQ, &q_full[qs], w.h * 64, q_row0 + w.q0);
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const int ks = g % NKS;
           mbar_wait(&ke_empty[ks], ((g / NKS) & 1) ^ 1);
           TR(1);
           mbar_expect_tx_e(&ke_full[ks], REL ? 16384 + 32768 : 16384);
-          tma_load_2d_e(smem + C::kK + ks * 16384, &tmK, &ke_full[ks], w.h * 64, w.b * Lk + kb * kPK);
+          tma_load_2d_e(smem + C::kK + ks * 16384, &tmK, &ke_full[ks], w.h * 64, k_row0 + kb * kPK);
           if (REL) tma_load_2d_e(smem + C::kE, &tmE, &ke_full[ks], 0, w.q0 - kb * kPK + P - 1 - 127);
           const int vs = g % NVS;
           mbar_wait(&v_empty[vs], ((g / NVS) & 1) ^ 1);
           TR(2);
           mbar_expect_tx_e(&v_full[vs], 16384);
-          tma_load_2d_e(smem + C::kV + vs * 16384, &tmV, &v_full[vs], w.h * 64, w.b * Lk + kb * kPK);
+          tma_load_2d_e(smem + C::kV + vs * 16384, &tmV, &v_full[vs], w.h * 64, k_row0 + kb * kPK);
         }
       }
     }
@@ -280,8 +286,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto mask_fetch = [&](const StepCursor& c, float& raw, bool& in_range) -> bool {
       if (c.it >= my_items || st >= kPK) return false;
       const int r = c.kb * kPK + st;
-      in_range = r < Lk;
-      raw = in_range ? __ldg(key_mask + static_cast<size_t>(c.b) * Lk + r) : 0.f;
+      in_range = r < Lk_mask;
+      raw = in_range ? __ldg(key_mask + static_cast<size_t>(c.b) * Lk_mask + r) : 0.f;
       return true;
     };
     // O of a finished item -> global.  Each thread scales its 32 of the row's 64 output columns and drops them as 16-bit into
@@ -293,6 +299,21 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       uint32_t r[32];
       tmem_ld_32x32(t_lane + C::kColO + (pit & 1) * 64 + hf * 32, r);
       tmem_ld_wait();
+      if (q_off) {  // packed batch: 64 B per thread straight to its own row, rows past the graph's length are not written
+        if (w.q0 + row < __ldg(q_len + w.b)) {
+          T* dst = out_raw + (static_cast<size_t>(__ldg(q_off + w.b)) + w.q0 + row) * (static_cast<size_t>(heads) * 64) + w.h * 64 + hf * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack2<T>(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+            v.y = pack2<T>(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+            v.z = pack2<T>(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+            v.w = pack2<T>(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + 8 * j) = v;
+          }
+        }
+        return;
+      }
       uint8_t* orow = smem + C::kOut + row * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -503,7 +524,7 @@ template <> struct PipeFmt<bf16> { static constexpr int v = 1; };
 
 template <typename T, bool REL>
 static int launch_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* E, int P,
-                       const float* mask, T* out, cudaStream_t s) {
+                       const float* mask, T* out, cudaStream_t s, const AttnPack* pk) {
   using C = PipeCfg<REL>;
   auto kfn = attention_pipe_kernel<T, REL>;
   static bool configured = false;
@@ -513,10 +534,11 @@ static int launch_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, co
   }
   constexpr int fmt = PipeFmt<T>::v;
   CUtensorMap tq, tk, tv, te, to;
-  SD_TRY(make_tmap(q, fmt, B * Lq, ldq, 128, &tq));
-  SD_TRY(make_tmap_3d(out, fmt, B, Lq, heads * 64, 128, &to));
-  SD_TRY(make_tmap(k, fmt, B * Lk, ldk, 128, &tk));
-  SD_TRY(make_tmap(v, fmt, B * Lk, ldv, 128, &tv));
+  SD_TRY(make_tmap(q, fmt, pk ? pk->q_rows : B * Lq, ldq, 128, &tq));
+  if (pk) to = tq;  // packed: per-thread predicated stores, no tile store
+  else SD_TRY(make_tmap_3d(out, fmt, B, Lq, heads * 64, 128, &to));
+  SD_TRY(make_tmap(k, fmt, pk ? pk->k_rows : B * Lk, ldk, 128, &tk));
+  SD_TRY(make_tmap(v, fmt, pk ? pk->k_rows : B * Lk, ldv, 128, &tv));
   if (REL) SD_TRY(make_tmap(E, fmt, 2 * P - 1, 64, 256, &te));
   else te = tq;
   const int nqb = ceil_div(Lq, kPQ);
@@ -526,22 +548,23 @@ static int launch_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, co
   int grid = n_items < num_sms() ? n_items : num_sms();
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   SD_CUDA(launch_k(kfn, dim3(grid), dim3(kPipeThreads), C::kBytes, s, tq, tk, tv, te, to, mask, heads, Lq, Lk, P, static_cast<uint32_t>(fmt), nqb,
-                   n_items, g_attn_trace));
+                   n_items, g_attn_trace, pk ? pk->q_off : nullptr, pk ? pk->k_off : nullptr, pk ? pk->q_len : nullptr, pk ? pk->Lk_mask : Lk, out));
   SD_LAUNCHED(REL ? "attention_pipe_rel" : "attention_pipe_norel", s);
   return SEQDIFF_OK;
 }
 
 template <typename T>
 int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
-                   const float* key_mask, T* out, cudaStream_t s) {
+                   const float* key_mask, T* out, cudaStream_t s, const AttnPack* pack) {
   SD_CHECK(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "empty attention");
   SD_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "row strides must be multiples of 8 elements");
   SD_CHECK((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) % 16 == 0, "q/k/v must be 16B aligned");
   SD_CHECK(!dist_emb || (Lq <= P && Lk <= P), "sequence longer than max_position_embeddings");
-  if (dist_emb) return launch_pipe<T, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
-  return launch_pipe<T, false>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s);
+  SD_CHECK(!pack || (pack->q_off && pack->k_off && pack->q_len && pack->Lk_mask >= Lk && pack->q_rows > 0 && pack->k_rows > 0), "bad packed-attention descriptor");
+  if (dist_emb) return launch_pipe<T, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, pack);
+  return launch_pipe<T, false>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, pack);
 }
-template int attention_pipe<bf16>(int, int, int, int, const bf16*, int, const bf16*, int, const bf16*, int, const bf16*, int, const float*, bf16*, cudaStream_t);
-template int attention_pipe<f16>(int, int, int, int, const f16*, int, const f16*, int, const f16*, int, const f16*, int, const float*, f16*, cudaStream_t);
+template int attention_pipe<bf16>(int, int, int, int, const bf16*, int, const bf16*, int, const bf16*, int, const bf16*, int, const float*, bf16*, cudaStream_t, const AttnPack*);
+template int attention_pipe<f16>(int, int, int, int, const f16*, int, const f16*, int, const f16*, int, const f16*, int, const float*, f16*, cudaStream_t, const AttnPack*);
 
 }  // namespace seqdiff

@@ -207,6 +207,19 @@ int seqdiff_model_get_tensor(seqdiff_model_t* m, const char* name, float* out, i
   SD_GUARD_END
 }
 
+int seqdiff_sample_ex(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, int T, const float* q_tables_steps, const float* x_T,
+                      const float* ligand_angle, const float* ligand_mask, const float* receptor_seq, const float* receptor_angle,
+                      const float* receptor_mask, int diverse, const float* noise_E_steps, uint64_t seed, uint64_t graph_id0, int flags,
+                      float* final_out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && q_tables_steps && x_T && ligand_angle && ligand_mask && receptor_seq && receptor_angle && receptor_mask && final_out,
+           "null argument");
+  SD_CHECK((flags & ~1) == 0, "unknown sampling flag");
+  return m->impl.sample(precision, B, L_lig, L_rec, T, q_tables_steps, x_T, ligand_angle, ligand_mask, receptor_seq, receptor_angle,
+                        receptor_mask, diverse, noise_E_steps, seed, graph_id0, final_out, static_cast<cudaStream_t>(stream), flags);
+  SD_GUARD_END
+}
+
 int seqdiff_struct_model_create(const seqdiff_config_t* cfg, int device, seqdiff_model_t** out) {
   SD_GUARD_BEGIN
   SD_CHECK(cfg != nullptr && out != nullptr, "null argument");

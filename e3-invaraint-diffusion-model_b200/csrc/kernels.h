@@ -56,6 +56,10 @@ struct EmbedJob {
   float* out32;         // [M, H] or NULL
   void* outT;           // [M, H] operand-typed copy or NULL
   int M, fin, L;
+  // packed (ragged) mode: output row r is computed from input row src_rows[r] (index into the padded [B * L, fin] input) and takes
+  // the timestep features of graph row_graph[r]; NULL = identity / r / L
+  const int* src_rows;
+  const int* row_graph;
   int cta_begin, cta_count;  // filled by embed_ln_multi
 };
 struct EmbedJobs {
@@ -77,21 +81,34 @@ int layernorm(const float* in, int M, int H, const float* w, const float* b, flo
 //   y = affine_first ? LayerNorm(in; lnw, lnb, eps1) : in          (BertSelfOutput.LayerNorm)
 //   out = x + gate * (LayerNorm_noaffine(y, 1e-5) * (1 + scale) + shift)
 // (shift, scale, gate) = mod[row / mod_div, (chunk0 + {0,1,2}) * H : ...], mod row pitch 6H.
+// row_graph (optional, packed mode with graph-level conditioning): row r uses mod row row_graph[r] instead of r / mod_div
 template <typename T>
 int ln_modulate(const float* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1, const float* x,
-                const T* mod, int mod_div, int chunk0, float* out32, T* outT, cudaStream_t s);
+                const T* mod, int mod_div, int chunk0, float* out32, T* outT, cudaStream_t s, const int* row_graph = nullptr);
 // AminoAcidPredictor tail (model.py:151-152): logits = LayerNorm(y) @ W2^T + b2  (y is already GELU(dense1))
+// dst_rows (optional, packed mode): logits of row r are written to row dst_rows[r] of `logits` (the padded [B * L, F] layout)
 template <typename T>
 int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb, float eps, const float* W2, const float* b2,
-                   int F, float* logits, cudaStream_t s);
+                   int F, float* logits, cudaStream_t s, const int* dst_rows = nullptr);
 template <typename T> int f32_to_16(const float* in, size_t n, T* out, cudaStream_t s);  // T = bf16 | f16
 int transpose_f32(const float* in, int rows, int cols, float* out, cudaStream_t s);  // out[c][r] = in[r][c]
 int step_advance(int* step_ptr, cudaStream_t s);                                     // *step_ptr -= 1
 
 // ---- attention.cu -----------------------------------------------------------------------------------
+// Packed (ragged) batches: graph b's query rows are rows q_off[b] .. q_off[b] + q_len[b] - 1 of q / out, its key rows k_off[b] .. of
+// k / v (device arrays of B ints); Lq / Lk are then the LARGEST query / key length of the batch and Lk_mask the row pitch of
+// key_mask (the padded length).  Rows of other graphs that fall into a tile are masked exactly like padding (their probabilities
+// underflow to 0), output rows past q_len[b] are not written.  16-bit modes (pipelined tcgen05 kernel) only.
+struct AttnPack {
+  const int* q_off;
+  const int* k_off;
+  const int* q_len;
+  int q_rows, k_rows;  // total rows of the packed q / k matrices
+  int Lk_mask;
+};
 template <typename T>
 int attention(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
-              int P, const float* key_mask, T* out, cudaStream_t s);
+              int P, const float* key_mask, T* out, cudaStream_t s, const AttnPack* pack = nullptr);
 
 // ---- collate.cu ---------------------------------------------------------------------------------------
 // LigandBindingSiteDataset.__getitem__ for G ragged complexes (dataset.py:97-129); lengths[g] = (n_lig, n_rec) BEFORE clamping.
@@ -106,7 +123,7 @@ extern unsigned long long* g_attn_trace;  // debug timeline buffer of the pipeli
 // ---- attention_pipe.cu: persistent, warp-specialised version (TMA / MMA / softmax roles pipelined over work items) -----
 template <typename T>
 int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
-                   int P, const float* key_mask, T* out, cudaStream_t s);
+                   int P, const float* key_mask, T* out, cudaStream_t s, const AttnPack* pack = nullptr);
 
 
 // ---- reverse_step.cu --------------------------------------------------------------------------------

@@ -173,6 +173,8 @@ Model::~Model() {
   if (ws) cudaFree(ws);
   if (samp_in) cudaFree(samp_in);
   if (d_tables) cudaFree(d_tables);
+  if (d_pack) cudaFree(d_pack);
+  if (tws) cudaFree(tws);
 }
 
 void* Model::dalloc(size_t bytes) {
@@ -572,23 +574,27 @@ template <typename T> struct SEBufs {
 };
 
 // SELayer.forward (model.py:52-63).  x:[M,H]; c:[Mc,H] with token row r using c row r / mod_div.
+// packs (optional, one per segment): ragged batch -- the segment's graphs are addressed through offset / length arrays (absolute rows
+// of the token matrix) and seg.L is the largest length; row_graph: graph of every row (conditioning broadcast over a graph).
 template <typename T>
 static int se_layer(const Model& m, int wfmt, const SEW& w, const Act<T>& x, const T* c, int Mc, int mod_div, int M,
-                    const std::vector<Segment>& segs, const SEBufs<T>& b, const Act<T>& out, cudaStream_t s) {
+                    const std::vector<Segment>& segs, const SEBufs<T>& b, const Act<T>& out, cudaStream_t s,
+                    const std::vector<AttnPack>* packs = nullptr, const int* row_graph = nullptr) {
   const int H = m.cfg.hidden_size, P = m.cfg.max_position_embeddings, heads = m.cfg.num_attention_heads;
   SD_TRY(gemm_T(wfmt, Mc, H, H, c, w.ada0, w.ada0_b, 2, b.u, s));          // SiLU(Linear(c))
   SD_TRY(gemm_T(wfmt, Mc, 6 * H, H, b.u, w.ada2, w.ada2_b, 0, b.mod, s));   // -> 6 chunks
   SD_TRY(gemm_T(wfmt, M, 3 * H, H, x.t, w.attn.qkv, w.attn.qkv_b, 0, b.qkv, s));
-  for (const Segment& g : segs) {
+  for (size_t gi = 0; gi < segs.size(); ++gi) {
+    const Segment& g = segs[gi];
     const T* base = b.qkv + static_cast<size_t>(g.row0) * 3 * H;
     SD_TRY(attention<T>(g.B, heads, g.L, g.L, base, 3 * H, base + H, 3 * H, base + 2 * H, 3 * H, pick<T>(w.attn.E), P, g.mask,
-                        b.ctx + static_cast<size_t>(g.row0) * H, s));
+                        b.ctx + static_cast<size_t>(g.row0) * H, s, packs ? &(*packs)[gi] : nullptr));
   }
   SD_TRY(gemm_S(wfmt, M, H, H, b.ctx, w.attn.out, w.attn.out_b, x.s, b.o, s));  // dense + residual (fp32)
-  SD_TRY(ln_modulate<T>(b.o, M, H, true, w.attn.ln_w, w.attn.ln_b, m.cfg.layer_norm_eps, x.s, b.mod, mod_div, 0, b.x1.s, b.x1.t_out(), s));
+  SD_TRY(ln_modulate<T>(b.o, M, H, true, w.attn.ln_w, w.attn.ln_b, m.cfg.layer_norm_eps, x.s, b.mod, mod_div, 0, b.x1.s, b.x1.t_out(), s, row_graph));
   SD_TRY(gemm_T(wfmt, M, 4 * H, H, b.x1.t, w.m0, w.m0_b, 1, b.m1, s));        // GELU
   SD_TRY(gemm_S(wfmt, M, H, 4 * H, b.m1, w.m3, w.m3_b, nullptr, b.m2, s));
-  SD_TRY(ln_modulate<T>(b.m2, M, H, false, nullptr, nullptr, 0.f, b.x1.s, b.mod, mod_div, 3, out.s, out.t_out(), s));
+  SD_TRY(ln_modulate<T>(b.m2, M, H, false, nullptr, nullptr, 0.f, b.x1.s, b.mod, mod_div, 3, out.s, out.t_out(), s, row_graph));
   return SEQDIFF_OK;
 }
 
@@ -596,17 +602,19 @@ static int se_layer(const Model& m, int wfmt, const SEW& w, const Act<T>& x, con
 template <typename T>
 int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t,
                      const float* lig_angle, const float* lig_mask, const float* rec_seq_in, const float* rec_angle,
-                     const float* rec_mask, float* logits, cudaStream_t s) {
+                     const float* rec_mask, float* logits, cudaStream_t s, const PackInfo* pk) {
   constexpr bool k16 = !std::is_same<T, float>::value;
   const int H = cfg.hidden_size, I = cfg.intermediate_size, NL = cfg.num_hidden_layers, heads = cfg.num_attention_heads;
   const int P = cfg.max_position_embeddings;
   const float eps = cfg.layer_norm_eps;
-  const int Ml = B * Ll, Mr = B * Lr, Mt = Ml + Mr;
+  // packed (ragged) batch: only the valid prefix of every graph is a row; inputs, masks and logits keep their padded layouts
+  const int Ml = pk ? pk->Ml : B * Ll, Mr = pk ? pk->Mr : B * Lr, Mt = Ml + Mr;
+  const int Mlp = B * Ll, Mrp = B * Lr;  // padded row counts (input tensors, key masks)
   const size_t MtH = static_cast<size_t>(Mt) * H, MlH = static_cast<size_t>(Ml) * H;
   Bump bp{ws};
   float* te = bp.take<float>(static_cast<size_t>(B) * H);
   T* teT = k16 ? bp.take<T>(static_cast<size_t>(B) * H) : reinterpret_cast<T*>(te);
-  float* maskcat = bp.take<float>(static_cast<size_t>(Ml) + Mr);
+  float* maskcat = bp.take<float>(static_cast<size_t>(Mlp) + Mrp);
   Act<T> x = take_act<T>(bp, MtH);   // embeddings; reused as the decoder_normalize output
   Act<T> x2 = take_act<T>(bp, MtH);  // ligand_feature_emb output: [lig | rec]
   SEBufs<T> sb;
@@ -631,34 +639,56 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   SD_TRY(timestep_embed(timestep, step_ptr, ts_W, B, H, te, k16 ? static_cast<void*>(teT) : nullptr, Fmt<T>::v, s));
   const Act<T> xr = offset(x, MlH);
   {
-    auto job = [&](const float* in, int M, const EmbW& e, const float* te_, int L, float* o32, T* oT) {
+    auto job = [&](const float* in, int M, const EmbW& e, const float* te_, int L, float* o32, T* oT, bool lig) {
       EmbedJob jb{};
       jb.x = in; jb.Wt = e.Wt_; jb.b = e.b; jb.lnw = e.ln_w; jb.lnb = e.ln_b; jb.te = te_;
       jb.out32 = o32; jb.outT = oT; jb.M = M; jb.fin = e.fin; jb.L = L;
+      if (pk) {
+        jb.src_rows = lig ? pk->src_l : pk->src_r;
+        jb.row_graph = lig ? pk->graph : pk->graph + pk->Ml;
+      }
       return jb;
     };
     EmbedJobs jobs{};
     jobs.n = 4;
-    jobs.j[0] = job(x_t, Ml, lig_seq, nullptr, Ll, x.s, x.t_out());
-    jobs.j[1] = job(rec_seq_in, Mr, rec_seq, nullptr, Lr, xr.s, xr.t_out());
+    jobs.j[0] = job(x_t, Ml, lig_seq, nullptr, Ll, x.s, x.t_out(), true);
+    jobs.j[1] = job(rec_seq_in, Mr, rec_seq, nullptr, Lr, xr.s, xr.t_out(), false);
     // the conditioning c = LN(Linear(angles)) + te only ever feeds a GEMM: operand type only
-    jobs.j[2] = job(lig_angle, Ml, lig_ang, te, Ll, k16 ? nullptr : reinterpret_cast<float*>(ccat), k16 ? ccat : nullptr);
-    jobs.j[3] = job(rec_angle, Mr, rec_ang, te, Lr, k16 ? nullptr : reinterpret_cast<float*>(ccat + MlH), k16 ? ccat + MlH : nullptr);
-    if (Ll == Lr) {  // stacked [lig | rec] key mask for the one-pass ligand_feature_emb attention
-      jobs.cat_dst = maskcat; jobs.cat_a = lig_mask; jobs.cat_b = rec_mask; jobs.cat_na = Ml; jobs.cat_nb = Mr;
+    jobs.j[2] = job(lig_angle, Ml, lig_ang, te, Ll, k16 ? nullptr : reinterpret_cast<float*>(ccat), k16 ? ccat : nullptr, true);
+    jobs.j[3] = job(rec_angle, Mr, rec_ang, te, Lr, k16 ? nullptr : reinterpret_cast<float*>(ccat + MlH), k16 ? ccat + MlH : nullptr, false);
+    if (Ll == Lr) {  // stacked [lig | rec] key mask for the one-pass ligand_feature_emb attention (always the PADDED masks)
+      jobs.cat_dst = maskcat; jobs.cat_a = lig_mask; jobs.cat_b = rec_mask; jobs.cat_na = Mlp; jobs.cat_nb = Mrp;
     }
     SD_TRY(embed_ln_multi<T>(jobs, eps, H, s));
   }
 
   // ligand_feature_emb on ligand AND receptor tokens in one pass (model.py:214-224, quirk Q1)
   std::vector<Segment> segs;
-  if (Ll == Lr) {
+  std::vector<AttnPack> packs;
+  AttnPack pk_self{}, pk_cross{};
+  if (pk) {
+    // offsets are absolute rows of the stacked matrix, so every segment starts at row 0
+    if (Ll == Lr) {
+      segs.push_back({0, 2 * B, pk->max_l > pk->max_r ? pk->max_l : pk->max_r, maskcat});
+      packs.push_back(AttnPack{pk->off_cat, pk->off_cat, pk->len_cat, Mt, Mt, Ll});
+    } else {
+      segs.push_back({0, B, pk->max_l, lig_mask});
+      packs.push_back(AttnPack{pk->off_cat, pk->off_cat, pk->len_cat, Mt, Mt, Ll});
+      segs.push_back({0, B, pk->max_r, rec_mask});
+      packs.push_back(AttnPack{pk->off_cat + B, pk->off_cat + B, pk->len_cat + B, Mt, Mt, Lr});
+    }
+    pk_self = AttnPack{pk->off_l, pk->off_l, pk->len_l, Ml, Ml, Ll};
+    pk_cross = AttnPack{pk->off_l, pk->off_r, pk->len_l, Ml, Mr, Lr};
+  } else if (Ll == Lr) {
     segs.push_back({0, 2 * B, Ll, maskcat});
   } else {
     segs.push_back({0, B, Ll, lig_mask});
     segs.push_back({Ml, B, Lr, rec_mask});
   }
-  SD_TRY(se_layer<T>(*this, wfmt, se_lig, x, ccat, Mt, 1, Mt, segs, sb, x2, s));
+  const int Lq_self = pk ? pk->max_l : Ll, Lk_cross = pk ? pk->max_r : Lr;
+  const AttnPack* aps = pk ? &pk_self : nullptr;
+  const AttnPack* apc = pk ? &pk_cross : nullptr;
+  SD_TRY(se_layer<T>(*this, wfmt, se_lig, x, ccat, Mt, 1, Mt, segs, sb, x2, s, pk ? &packs : nullptr, nullptr));
   const T* rec = x2.t + MlH;
 
   // decoder: 6 x (self-attn -> cross-attn -> FFN), post-LN (HF BertLayer; model.py:226-231)
@@ -681,12 +711,12 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
       float* oB = obuf[1];
       float* oC = obuf[2];
       SD_TRY(gemm_T(wfmt, Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, 0, sb.qkv, s));
-      SD_TRY(attention<T>(B, heads, Ll, Ll, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s));
+      SD_TRY(attention<T>(B, heads, Lq_self, Lq_self, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s, aps));
       SD_TRY(gemm_ln<T>(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, i == 0 ? h.s : o_prev, oA, i == 0 ? nullptr : &prev, w.self.ln_w,
                         w.self.ln_b, eps, h1.t, lnstats, s));
       SD_TRY(gemm_T(wfmt, Ml, H, H, h1.t, w.cq, w.cq_b, 0, cq, s));
       const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
-      SD_TRY(attention<T>(B, heads, Ll, Lr, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s));
+      SD_TRY(attention<T>(B, heads, Lq_self, Lk_cross, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s, apc));
       const LnResid r1{lnstats, w.self.ln_w, w.self.ln_b};
       SD_TRY(gemm_ln<T>(wfmt, Ml, H, H, sb.ctx, w.cout, w.cout_b, oA, oB, &r1, w.cln_w, w.cln_b, eps, h2.t, lnstats + Ml, s));
       SD_TRY(gemm_T(wfmt, Ml, I, H, h2.t, w.inter, w.inter_b, 1, ffn, s));
@@ -708,12 +738,12 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
       // h is dead once the self-output GEMM has folded it in as the residual, so h1/h3 may reuse its buffer
       const Act<T> h1 = hbuf[0], h2 = hbuf[1], h3 = hbuf[0];
       SD_TRY(gemm_T(wfmt, Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, 0, sb.qkv, s));
-      SD_TRY(attention<T>(B, heads, Ll, Ll, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s));
+      SD_TRY(attention<T>(B, heads, Lq_self, Lq_self, sb.qkv, 3 * H, sb.qkv + H, 3 * H, sb.qkv + 2 * H, 3 * H, pick<T>(w.self.E), P, lig_mask, sb.ctx, s, aps));
       SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.self.out, w.self.out_b, h.s, sb.o, s));
       SD_TRY(layernorm<T>(sb.o, Ml, H, w.self.ln_w, w.self.ln_b, eps, h1.s, h1.t_out(), nullptr, s));
       SD_TRY(gemm_T(wfmt, Ml, H, H, h1.t, w.cq, w.cq_b, 0, cq, s));
       const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
-      SD_TRY(attention<T>(B, heads, Ll, Lr, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s));
+      SD_TRY(attention<T>(B, heads, Lq_self, Lk_cross, cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, static_cast<const T*>(nullptr), P, rec_mask, sb.ctx, s, apc));
       SD_TRY(gemm_S(wfmt, Ml, H, H, sb.ctx, w.cout, w.cout_b, h1.s, sb.o, s));
       SD_TRY(layernorm<T>(sb.o, Ml, H, w.cln_w, w.cln_b, eps, h2.s, h2.t_out(), nullptr, s));
       SD_TRY(gemm_T(wfmt, Ml, I, H, h2.t, w.inter, w.inter_b, 1, ffn, s));
@@ -724,8 +754,10 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   }
 
   // decoder_normalize: SELayer conditioned on the timestep only (c broadcast over L; model.py:232-235)
-  std::vector<Segment> lseg{{0, B, Ll, lig_mask}};
-  SD_TRY(se_layer<T>(*this, wfmt, se_dec, h, teT, B, Ll, Ml, lseg, sb, x, s));
+  std::vector<Segment> lseg{{0, B, Lq_self, lig_mask}};
+  std::vector<AttnPack> lpack;
+  if (pk) lpack.push_back(pk_self);
+  SD_TRY(se_layer<T>(*this, wfmt, se_dec, h, teT, B, Ll, Ml, lseg, sb, x, s, pk ? &lpack : nullptr, pk ? pk->graph : nullptr));
 
   // AminoAcidPredictor (model.py:148-153)
   if constexpr (std::is_same<T, bf16>::value) {
@@ -737,19 +769,20 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
     f16* yh = reinterpret_cast<f16*>(y);
     SD_TRY(f32_to_16<f16>(x.s, static_cast<size_t>(Ml) * H, xh, s));
     SD_TRY(gemm_16(Ml, H, H, xh, 0, p1.g, 0, p1_b, nullptr, 1, yh, 0, s));
-    SD_TRY(predictor_tail<f16>(yh, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, logits, s));
+    SD_TRY(predictor_tail<f16>(yh, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, logits, s, pk ? pk->src_l : nullptr));
     return SEQDIFF_OK;
   }
   SD_TRY(gemm_T(wfmt, Ml, H, H, x.t, p1, p1_b, 1, y, s));
-  SD_TRY(predictor_tail<T>(y, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, logits, s));
+  SD_TRY(predictor_tail<T>(y, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, cfg.feature_size, logits, s, pk ? pk->src_l : nullptr));
   return SEQDIFF_OK;
 }
 
 int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t,
                    const float* lig_angle, const float* lig_mask, const float* rec_seq_in, const float* rec_angle,
-                   const float* rec_mask, float* logits, cudaStream_t s) {
+                   const float* rec_mask, float* logits, cudaStream_t s, const PackInfo* pk) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
   SD_CHECK(arch == kArchSequence, "handle holds a structure model: use seqdiff_struct_forward");
+  SD_CHECK(!pk || precision != SEQDIFF_FP32, "ragged packing runs in the 16-bit modes");
   SD_CHECK(precision >= SEQDIFF_FP32 && precision <= SEQDIFF_FP16, "unknown precision mode");
   SD_CHECK(B > 0 && Ll > 0 && Lr > 0, "empty batch");
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
@@ -757,20 +790,94 @@ int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, 
   SD_TRY(ensure_workspace(workspace_need(precision, B, Ll, Lr)));
   switch (precision) {
     case SEQDIFF_FP32:
-      return forward_t<float>(1, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+      return forward_t<float>(1, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s, nullptr);
     case SEQDIFF_BF16:
-      return forward_t<bf16>(1, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+      return forward_t<bf16>(1, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s, pk);
     default:  // SEQDIFF_FP16
-      return forward_t<f16>(0, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s);
+      return forward_t<f16>(0, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s, pk);
   }
 }
 
 // =====================================================================================================
 // reverse-diffusion loop: one captured CUDA graph per step shape, replayed T times
 // =====================================================================================================
+// Ragged packing: lengths from the (prefix-ones) masks, row maps, offsets.  *usable = false when a mask is not a prefix of ones
+// (the caller then stays on the padded path) or a graph has no valid ligand / receptor token.
+int Model::build_pack(int B, int Ll, int Lr, const float* lig_mask, const float* rec_mask, cudaStream_t s, bool* usable) {
+  *usable = false;
+  std::vector<float> hl(static_cast<size_t>(B) * Ll), hr(static_cast<size_t>(B) * Lr);
+  SD_CUDA(cudaMemcpyAsync(hl.data(), lig_mask, hl.size() * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaMemcpyAsync(hr.data(), rec_mask, hr.size() * 4, cudaMemcpyDefault, s));
+  SD_CUDA(cudaStreamSynchronize(s));
+  std::vector<int> len_l(B), len_r(B);
+  auto lengths = [&](const std::vector<float>& m, int L, std::vector<int>& len) -> bool {
+    for (int b = 0; b < B; ++b) {
+      int n = 0;
+      while (n < L && m[static_cast<size_t>(b) * L + n] == 1.0f) ++n;
+      for (int i = n; i < L; ++i)
+        if (m[static_cast<size_t>(b) * L + i] != 0.0f) return false;
+      if (n == 0) return false;
+      len[b] = n;
+    }
+    return true;
+  };
+  if (!lengths(hl, Ll, len_l) || !lengths(hr, Lr, len_r)) return SEQDIFF_OK;
+  int Ml = 0, Mr = 0, max_l = 0, max_r = 0;
+  std::vector<int> off_l(B), off_r(B);
+  for (int b = 0; b < B; ++b) {
+    off_l[b] = Ml; Ml += len_l[b];
+    off_r[b] = Mr; Mr += len_r[b];
+    max_l = len_l[b] > max_l ? len_l[b] : max_l;
+    max_r = len_r[b] > max_r ? len_r[b] : max_r;
+  }
+  // block layout (ints): src_l[Ml] | src_r[Mr] | graph[Ml+Mr] | off_l[B] | off_r[B] | len_l[B] | len_r[B] | off_cat[2B] | len_cat[2B]
+  std::vector<int> blk;
+  blk.reserve(2 * (static_cast<size_t>(Ml) + Mr) + 8 * B);
+  for (int b = 0; b < B; ++b) for (int l = 0; l < len_l[b]; ++l) blk.push_back(b * Ll + l);
+  for (int b = 0; b < B; ++b) for (int l = 0; l < len_r[b]; ++l) blk.push_back(b * Lr + l);
+  for (int b = 0; b < B; ++b) for (int l = 0; l < len_l[b]; ++l) blk.push_back(b);
+  for (int b = 0; b < B; ++b) for (int l = 0; l < len_r[b]; ++l) blk.push_back(b);
+  for (int b = 0; b < B; ++b) blk.push_back(off_l[b]);
+  for (int b = 0; b < B; ++b) blk.push_back(off_r[b]);
+  for (int b = 0; b < B; ++b) blk.push_back(len_l[b]);
+  for (int b = 0; b < B; ++b) blk.push_back(len_r[b]);
+  for (int b = 0; b < B; ++b) blk.push_back(off_l[b]);
+  for (int b = 0; b < B; ++b) blk.push_back(Ml + off_r[b]);
+  for (int b = 0; b < B; ++b) blk.push_back(len_l[b]);
+  for (int b = 0; b < B; ++b) blk.push_back(len_r[b]);
+  uint64_t hsh = 1469598103934665603ull;  // FNV-1a over the block: a changed batch composition re-captures the step graph
+  for (int v : blk) { hsh ^= static_cast<uint32_t>(v); hsh *= 1099511628211ull; }
+  bool fresh = false;
+  if (blk.size() > pack_cap) {
+    if (d_pack) { SD_CUDA(cudaDeviceSynchronize()); SD_CUDA(cudaFree(d_pack)); d_pack = nullptr; pack_cap = 0; }
+    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_pack), blk.size() * sizeof(int)));
+    pack_cap = blk.size();
+    fresh = true;
+  }
+  if (fresh || hsh != pack.hash || pack.B != B) {
+    SD_CUDA(cudaMemcpyAsync(d_pack, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    SD_CUDA(cudaStreamSynchronize(s));  // blk is a stack-lifetime host buffer
+  }
+  PackInfo pi;
+  pi.B = B; pi.Ml = Ml; pi.Mr = Mr; pi.max_l = max_l; pi.max_r = max_r; pi.hash = hsh;
+  const int* p = d_pack;
+  pi.src_l = p; p += Ml;
+  pi.src_r = p; p += Mr;
+  pi.graph = p; p += Ml + Mr;
+  pi.off_l = p; p += B;
+  pi.off_r = p; p += B;
+  pi.len_l = p; p += B;
+  pi.len_r = p; p += B;
+  pi.off_cat = p; p += 2 * B;
+  pi.len_cat = p;
+  pack = pi;
+  *usable = true;
+  return SEQDIFF_OK;
+}
+
 int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_tables, const float* x_T, const float* lig_angle,
                   const float* lig_mask, const float* rec_seq_in, const float* rec_angle, const float* rec_mask, int diverse,
-                  const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t caller) {
+                  const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t caller, int flags) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
   SD_CHECK(T >= 1 && B > 0 && Ll > 0 && Lr > 0, "bad sampling arguments");
   SD_CHECK(cfg.feature_size == SEQDIFF_NUM_CLASSES, "sampling needs feature_size == 20");
@@ -815,13 +922,24 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
   SD_CUDA(cudaMemcpyAsync(c_rseq, rec_seq_in, Nr * 20 * 4, cudaMemcpyDefault, s));
   SD_CUDA(cudaMemcpyAsync(c_rang, rec_angle, Nr * 8 * 4, cudaMemcpyDefault, s));
   SD_CUDA(cudaMemcpyAsync(c_rmask, rec_mask, Nr * 4, cudaMemcpyDefault, s));
+  // ragged packing (flags bit 0): valid prefixes only; needs the 16-bit kernels and prefix masks, otherwise the padded path runs
+  const PackInfo* pk = nullptr;
+  if ((flags & 1) && precision != SEQDIFF_FP32) {
+    bool usable = false;
+    SD_TRY(build_pack(B, Ll, Lr, c_lmask, c_rmask, s, &usable));
+    if (usable) {
+      pk = &pack;
+      SD_CUDA(cudaMemsetAsync(logits, 0, Nl * 20 * 4, s));  // padded positions are never written in packed mode: defined as 0
+    }
+  }
 
   GraphKey key;
+  key.pack_hash = pk ? pk->hash : 0;
   key.precision = precision; key.B = B; key.Ll = Ll; key.Lr = Lr; key.diverse = diverse; key.noise = noise_E;
   key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables;  // (seed, gid0) are NOT part of the key: device memory, see arm_loop_kernel
   uint64_t* d_rng = reinterpret_cast<uint64_t*>(d_step + 16);
   auto one_step = [&](cudaStream_t st) -> int {
-    SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, st));
+    SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, st, pk));
     SD_TRY(reverse_step(d_tables, 1, B, Ll, x_cur, logits, diverse, noise_E, 0, 0, 0, d_step, x_cur, nullptr, st, d_step + 1, d_rng));
     return SEQDIFF_OK;
   };
@@ -830,7 +948,7 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
     // un-captured dry run of the forward: sets kernel attributes and fills the TMA descriptor cache
     SD_CUDA(launch_k(set_int_kernel, dim3(1), dim3(1), 0, s, d_step, T - 1));
     SD_LAUNCHED("set_int", s);
-    SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, s));
+    SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, s, pk));
     SD_CUDA(cudaStreamSynchronize(s));
     cudaGraph_t graph = nullptr;
     const uint64_t l0 = g_launches.load();

@@ -72,6 +72,23 @@ struct Segment {  // a run of graphs sharing one padded length inside a token ma
 int profile_begin(cudaStream_t s);
 int profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap);
 
+// Ragged packing of a sampling batch (DESIGN.md "Ragged batches"): only the valid prefix of every graph is computed.  Token rows of
+// graph b occupy rows [off[b], off[b] + len[b]) of every [rows, H] matrix; all index arrays live in one device block.
+struct PackInfo {
+  int B = 0, Ml = 0, Mr = 0;      // packed ligand / receptor row counts
+  int max_l = 0, max_r = 0;       // largest ligand / receptor length
+  const int* src_l = nullptr;     // [Ml] packed ligand row -> padded row index b * Ll + l
+  const int* src_r = nullptr;     // [Mr]
+  const int* graph = nullptr;     // [Ml + Mr] graph of a stacked row
+  const int* off_l = nullptr;     // [B] first ligand row of graph b
+  const int* off_r = nullptr;     // [B] first receptor row of graph b, relative to the receptor block
+  const int* len_l = nullptr;     // [B]
+  const int* len_r = nullptr;     // [B]
+  const int* off_cat = nullptr;   // [2B] ligand offsets, then receptor offsets + Ml (stacked matrix)
+  const int* len_cat = nullptr;   // [2B]
+  uint64_t hash = 0;              // of the length vectors (part of the CUDA-graph key)
+};
+
 enum Arch { kArchSequence = 0, kArchStructure = 1 };
 
 struct Model {
@@ -115,8 +132,9 @@ struct Model {
     const void* tab_ptr = nullptr;
     const void* aux_ptr = nullptr;
     int T = 0;
+    uint64_t pack_hash = 0;
     bool operator==(const GraphKey& o) const {
-      return aux_ptr == o.aux_ptr && T == o.T && precision == o.precision && B == o.B && Ll == o.Ll && Lr == o.Lr && diverse == o.diverse && noise == o.noise &&
+      return pack_hash == o.pack_hash && aux_ptr == o.aux_ptr && T == o.T && precision == o.precision && B == o.B && Ll == o.Ll && Lr == o.Lr && diverse == o.diverse && noise == o.noise &&
              ws_ptr == o.ws_ptr && in_ptr == o.in_ptr && tab_ptr == o.tab_ptr;
     }
   } graph_key;
@@ -127,10 +145,15 @@ struct Model {
   int finalize(cudaStream_t s);
   int forward(int precision, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t,
               const float* lig_angle, const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask,
-              float* logits, cudaStream_t s);
+              float* logits, cudaStream_t s, const PackInfo* pk = nullptr);
+  // flags bit 0: ragged packing (valid positions bit-identical to the padded computation; padded positions of final_out are 0)
   int sample(int precision, int B, int Ll, int Lr, int T, const float* q_tables, const float* x_T, const float* lig_angle,
              const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, int diverse,
-             const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t s);
+             const float* noise_E, uint64_t seed, uint64_t gid0, float* final_out, cudaStream_t s, int flags = 0);
+  int* d_pack = nullptr;  // device block behind PackInfo (grow-only)
+  size_t pack_cap = 0;
+  PackInfo pack;
+  int build_pack(int B, int Ll, int Lr, const float* lig_mask, const float* rec_mask, cudaStream_t s, bool* usable);
 
   // ---- training (train.cu) ------------------------------------------------------------------------------------------
   std::vector<ParamSlot> slots;            // trainable tensors in flat-buffer order (fused groups contiguous)
@@ -176,7 +199,7 @@ struct Model {
   template <typename T>
   int forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, const int* step_ptr, const float* x_t, const float* lig_angle,
                 const float* lig_mask, const float* rec_seq, const float* rec_angle, const float* rec_mask, float* logits,
-                cudaStream_t s);
+                cudaStream_t s, const PackInfo* pk);
 };
 
 }  // namespace seqdiff

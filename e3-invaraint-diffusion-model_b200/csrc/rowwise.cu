@@ -115,6 +115,13 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_multi_kernel(const __
   float* sx = sW + static_cast<size_t>(jobs.max_fin) * H + warp * (2 * TOK * 32);
   const int gstep = job.cta_count * (kRowThreads / 32);
   auto fetch_x = [&](int grp_n, int buf) {
+    if (job.src_rows) {  // packed mode: output row r reads input row src_rows[r]
+      for (int i = lane; i < TOK * fin; i += 32) {
+        const int r = grp_n * TOK + i / fin;
+        sx[buf * TOK * 32 + i] = r < M ? __ldg(job.x + static_cast<size_t>(__ldg(job.src_rows + r)) * fin + (i % fin)) : 0.f;
+      }
+      return;
+    }
     const size_t base = static_cast<size_t>(grp_n) * TOK * fin;
     const size_t lim = static_cast<size_t>(M) * fin;
     for (int i = lane; i < TOK * fin; i += 32) sx[buf * TOK * 32 + i] = (base + i < lim) ? __ldg(job.x + base + i) : 0.f;
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) embed_ln_multi_kernel(const __
       }
       float mean, rstd;
       row_stats<VPL>(v, H, eps, mean, rstd);
-      const float* terow = job.te ? job.te + static_cast<size_t>((tok0 + t) / job.L) * H : nullptr;
+      const float* terow = job.te ? job.te + static_cast<size_t>(job.row_graph ? __ldg(job.row_graph + tok0 + t) : (tok0 + t) / job.L) * H : nullptr;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         float g8[8], b8[8];
@@ -308,7 +315,7 @@ template <typename T, int VPL, bool AFFINE_FIRST>
 __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const float* __restrict__ in, int M, int H, const float* __restrict__ lnw,
                                                                   const float* __restrict__ lnb, float eps1, const float* __restrict__ x,
                                                                   const T* __restrict__ mod, int mod_div, int chunk0,
-                                                                  float* __restrict__ out32, T* __restrict__ outT) {
+                                                                  float* __restrict__ out32, T* __restrict__ outT, const int* __restrict__ row_graph) {
   pdl_trigger();
   pdl_wait();  // predecessor grid complete + flushed before any dependent global access
   const int lane = threadIdx.x & 31;
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const float* _
     }
   }
   row_stats<VPL>(v, H, 1e-5f, mean, rstd);  // SELayer.norm1/norm2: elementwise_affine=False, default eps
-  const T* mrow = mod + static_cast<size_t>(row / mod_div) * (6 * H);
+  const T* mrow = mod + static_cast<size_t>(row_graph ? __ldg(row_graph + row) : row / mod_div) * (6 * H);
   const float* xrow = x + static_cast<size_t>(row) * H;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -351,18 +358,18 @@ __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const float* _
 
 template <typename T>
 int ln_modulate(const float* in, int M, int H, bool affine_first, const float* lnw, const float* lnb, float eps1, const float* x,
-                const T* mod, int mod_div, int chunk0, float* out32, T* outT, cudaStream_t s) {
+                const T* mod, int mod_div, int chunk0, float* out32, T* outT, cudaStream_t s, const int* row_graph) {
   const int grid = ceil_div(M * 32, kRowThreads);
   if (affine_first) {
-    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_kernel<T, VPL, true>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT)));
+    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_kernel<T, VPL, true>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT, row_graph)));
   } else {
-    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_kernel<T, VPL, false>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT)));
+    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_kernel<T, VPL, false>, dim3(grid), dim3(kRowThreads), 0, s, in, M, H, lnw, lnb, eps1, x, mod, mod_div, chunk0, out32, outT, row_graph)));
   }
   SD_LAUNCHED("ln_modulate", s);
   return SEQDIFF_OK;
 }
 #define SD_INST_LNMOD(T) \
-  template int ln_modulate<T>(const float*, int, int, bool, const float*, const float*, float, const float*, const T*, int, int, float*, T*, cudaStream_t)
+  template int ln_modulate<T>(const float*, int, int, bool, const float*, const float*, float, const float*, const T*, int, int, float*, T*, cudaStream_t, const int*)
 SD_INST_LNMOD(float);
 SD_INST_LNMOD(bf16);
 SD_INST_LNMOD(f16);
@@ -375,7 +382,7 @@ template <typename T, int VPL>
 __global__ void __launch_bounds__(kRowThreads) predictor_tail_kernel(const T* __restrict__ y, int M, int H, const float* __restrict__ lnw,
                                                                      const float* __restrict__ lnb, float eps,
                                                                      const float* __restrict__ W2, const float* __restrict__ b2, int F,
-                                                                     float* __restrict__ logits) {
+                                                                     float* __restrict__ logits, const int* __restrict__ dst_rows) {
   extern __shared__ float4 sW4[];
   float* sW = reinterpret_cast<float*>(sW4);
   for (int i = threadIdx.x; i < F * H / 4; i += kRowThreads) sW4[i] = __ldg(reinterpret_cast<const float4*>(W2) + i);
@@ -432,13 +439,13 @@ __global__ void __launch_bounds__(kRowThreads) predictor_tail_kernel(const T* __
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
-      if (lane < F && row0 + r < M) logits[static_cast<size_t>(row0 + r) * F + lane] = mine[r];
+      if (lane < F && row0 + r < M) logits[static_cast<size_t>(dst_rows ? __ldg(dst_rows + row0 + r) : row0 + r) * F + lane] = mine[r];
   }
 }
 
 template <typename T>
 int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb, float eps, const float* W2, const float* b2, int F,
-                   float* logits, cudaStream_t s) {
+                   float* logits, cudaStream_t s, const int* dst_rows) {
   SD_CHECK(F <= 32, "feature_size > 32 not supported");
   const int need = ceil_div(M, 4 * (kRowThreads / 32));
   const int grid = need < num_sms() ? need : num_sms();  // ~185 registers x 256 threads: one CTA per SM
@@ -451,16 +458,16 @@ int predictor_tail(const T* y, int M, int H, const float* lnw, const float* lnb,
       SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 34 * 1024 * 4));                 \
       configured = true;                                                                                              \
     }                                                                                                                 \
-    SD_CUDA(launch_k(kfn, dim3(grid), dim3(kRowThreads), smem, s, y, M, H, lnw, lnb, eps, W2, b2, F, logits));        \
+    SD_CUDA(launch_k(kfn, dim3(grid), dim3(kRowThreads), smem, s, y, M, H, lnw, lnb, eps, W2, b2, F, logits, dst_rows)); \
   }
   SD_VPL_DISPATCH(H, SD_PRED_LAUNCH());
 #undef SD_PRED_LAUNCH
   SD_LAUNCHED("predictor_tail", s);
   return SEQDIFF_OK;
 }
-template int predictor_tail<float>(const float*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t);
-template int predictor_tail<bf16>(const bf16*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t);
-template int predictor_tail<f16>(const f16*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t);
+template int predictor_tail<float>(const float*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t, const int*);
+template int predictor_tail<bf16>(const bf16*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t, const int*);
+template int predictor_tail<f16>(const f16*, int, int, const float*, const float*, float, const float*, const float*, int, float*, cudaStream_t, const int*);
 
 // ---------------------------------------------------------------------------------------------------
 template <typename T>

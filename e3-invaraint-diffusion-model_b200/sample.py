@@ -102,11 +102,13 @@ def sample_p_zs_given_zt_discrete(t, s, noised_data, pred_noise, noise_schedule,
 
 @torch.no_grad()
 def denoise_tensors(batch, model, noise_schedule, transition, diverse, timesteps=None, x_T=None, noise_E_steps=None,
-                    graph_id0=None, seed=None):
+                    graph_id0=None, seed=None, packed=False):
     """The T-step loop of reference denoise() (sample.py:184-207) as one C call.  Returns the final
     [B,L,20] tensor (raw logits of the last step, quirk Q4) on the model's device.
     `graph_id0` = global id of the batch's first graph in the Philox noise stream; None (default) continues the process-wide
-    stream (`_cabi.GRAPH_IDS`), so consecutive batches and repeated calls never share noise."""
+    stream (`_cabi.GRAPH_IDS`), so consecutive batches and repeated calls never share noise.
+    `packed=True`: ragged packing (seqdiff_sample_ex, SEQDIFF_SAMPLE_PACKED) -- only the valid prefix of every graph is computed;
+    the result is bit-identical at the valid positions (all that denoise() reads) and 0 at the padded ones."""
     T = CONFIG["timesteps"] if timesteps is None else timesteps
     h = model._sync_handle()
     dev = model._handle_dev  # the handle's device owns the stream, the workspace and every tensor of this call
@@ -134,10 +136,11 @@ def denoise_tensors(batch, model, noise_schedule, transition, diverse, timesteps
     out = torch.empty((batch_size, max_len, num_class), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _cabi.check(_cabi.lib().seqdiff_sample(h, model._precision_code(), batch_size, max_len, Lr, T, _cabi.ptr(tables), _cabi.ptr(x_T),
-                                               _cabi.ptr(ligand_angles), _cabi.ptr(ligand_mask), _cabi.ptr(receptor_seq),
-                                               _cabi.ptr(receptor_angles), _cabi.ptr(receptor_attn_mask), int(bool(diverse)),
-                                               _cabi.ptr(E), SEED if seed is None else seed, graph_id0, _cabi.ptr(out), stream))
+        _cabi.check(_cabi.lib().seqdiff_sample_ex(h, model._precision_code(), batch_size, max_len, Lr, T, _cabi.ptr(tables), _cabi.ptr(x_T),
+                                                  _cabi.ptr(ligand_angles), _cabi.ptr(ligand_mask), _cabi.ptr(receptor_seq),
+                                                  _cabi.ptr(receptor_angles), _cabi.ptr(receptor_attn_mask), int(bool(diverse)),
+                                                  _cabi.ptr(E), SEED if seed is None else seed, graph_id0, 1 if packed else 0,
+                                                  _cabi.ptr(out), stream))
     return out
 
 

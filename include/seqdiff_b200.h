@@ -134,6 +134,19 @@ SEQDIFF_API int seqdiff_sample(seqdiff_model_t* m, int precision, int B, int L_l
                    const float* receptor_mask, int diverse, const float* noise_E_steps, uint64_t seed,
                    uint64_t graph_id0, float* final_out, void* stream);
 
+/* The same loop with options.  flags bit 0 (SEQDIFF_SAMPLE_PACKED): ragged packing -- only the valid prefix of every graph
+ * (ligand_mask / receptor_mask must be prefixes of ones, as LigandBindingSiteDataset builds them, dataset.py:110-114) is carried
+ * through the GEMMs / LayerNorms / attention: M = sum of lengths instead of B * L.  Results at valid positions are bit-identical
+ * to the padded computation (a padded key's probability underflows to exactly 0, every other operator is row-local); the
+ * reference also computes and samples the padded positions, which denoise() never reads (sample.py:211-224) -- here they
+ * come back as 0 in final_out.  Non-prefix masks or fp32 mode silently take the padded path. */
+#define SEQDIFF_SAMPLE_PACKED 1
+SEQDIFF_API int seqdiff_sample_ex(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, int T,
+                      const float* q_tables_steps, const float* x_T, const float* ligand_angle,
+                      const float* ligand_mask, const float* receptor_seq, const float* receptor_angle,
+                      const float* receptor_mask, int diverse, const float* noise_E_steps, uint64_t seed,
+                      uint64_t graph_id0, int flags, float* final_out, void* stream);
+
 /* ---- output decode: replaces the per-graph loop of denoise(), sequence_model/sample.py:208-224 --------------------
  * final_seq [B,L,20] (the loop's result: raw logits of the last step), true_seq [B,L,20] one-hot, ligand_mask [B,L] {0,1}.
  * pred_idx / true_idx [B,L] u8 = argmax over classes (first maximum, like torch.argmax); counts [B,2] i32 =

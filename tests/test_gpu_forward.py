@@ -316,6 +316,71 @@ def test_consecutive_calls_draw_fresh_noise_and_explicit_ids_reproduce():
     assert torch.equal(d, c1[1:])
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", ["cfg2-ragged", "cfg3-fixed", "length-1-graph", "Ll!=Lr"])
+def test_packed_sampling_is_bit_identical_at_valid_positions(case, precision):
+    """Ragged packing (seqdiff_sample_ex, SEQDIFF_SAMPLE_PACKED): M = sum of lengths instead of B * L, per-graph offsets in the
+    attention kernel.  A padded key's probability underflows to exactly 0 and every other operator is row-local, so the final
+    logits at the VALID positions must be bit-identical to the padded loop -- through T chained steps with in-kernel Philox
+    sampling, i.e. every intermediate x_t agreed on the valid residues too.  Padded positions come back as 0."""
+    sd = sd_pkg()
+    T = 4
+    if case == "cfg2-ragged":
+        L, B = 128, 64
+        batch = O.synthetic_batch(B, L, (5, 64), (16, 128), 3)
+    elif case == "cfg3-fixed":
+        L, B = 512, 4
+        batch = O.synthetic_batch(B, L, 48, 464, 13)
+    elif case == "length-1-graph":
+        L, B = 128, 3
+        batch = O.synthetic_batch(B, L, (1, 1), (1, 128), 21)
+        two = O.synthetic_batch(B, L, (40, 128), (128, 128), 22)
+        for k in batch:
+            batch[k][1] = two[k][1]
+    else:
+        L, B = 128, 5
+        batch = O.synthetic_batch(B, 48, (1, 48), (1, 48), 31)
+        rec = O.synthetic_batch(B, 112, (1, 112), (16, 112), 32)
+        for k in ("receptor_seq", "receptor_angles", "receptor_attn_mask"):
+            batch[k] = rec[k]
+    cfg, state, m = _model(L, True, 1, "B", precision)
+    sd.sample.DEVICE = torch.device(DEV)
+    Ll = batch["ligand_seq"].shape[1]
+    x_T = O.generate_discrete_noise(B, Ll, generator=torch.Generator().manual_seed(6))
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    kw = dict(timesteps=T, x_T=x_T, seed=77, graph_id0=5)
+    padded = sd.denoise_tensors(batch, m, sched, tr, True, **kw)
+    n0 = sd.lib().seqdiff_launch_count()
+    packed = sd.denoise_tensors(batch, m, sched, tr, True, packed=True, **kw)
+    again = sd.denoise_tensors(batch, m, sched, tr, True, packed=True, **kw)
+    valid = batch["ligand_attn_mask"].bool().to(DEV)
+    assert torch.equal(packed, again)
+    d = (packed[valid] - padded[valid]).abs().max().item()
+    print(f"{case} {precision}: {int(valid.sum())} valid of {valid.numel()} residues; max |packed - padded| at valid positions {d:.3e}")
+    assert torch.equal(packed[valid], padded[valid])
+    assert (packed[~valid] == 0).all()
+    # decoded sequences (all that denoise() returns) are therefore the same
+    b2 = dict(batch, structure_ids={"pdb_id": ["x"] * B, "ligand_chain": ["A"] * B})
+    r1 = sd.denoise(b2, m, sched, tr, True, **kw)
+    r2 = sd.denoise(b2, m, sched, tr, True, packed=True, **kw)
+    assert r1[2] == r2[2] and r1[3] == r2[3]
+
+
+def test_packed_sampling_falls_back_on_non_prefix_masks():
+    sd = sd_pkg()
+    T, L, B = 3, 64, 3
+    cfg, state, m = _model(64, True, 1, "B", "bf16")
+    sd.sample.DEVICE = torch.device(DEV)
+    batch = O.synthetic_batch(B, L, (10, 40), (16, 64), 41)
+    batch["receptor_attn_mask"][1, 3] = 0.0  # a hole: not a prefix of ones
+    x_T = O.generate_discrete_noise(B, L, generator=torch.Generator().manual_seed(6))
+    sched, tr = sd.PredefinedNoiseScheduleDiscrete("cosine", T), sd.BlosumTransition(x_classes=20)
+    kw = dict(timesteps=T, x_T=x_T, seed=7, graph_id0=0)
+    a = sd.denoise_tensors(batch, m, sched, tr, True, **kw)
+    b = sd.denoise_tensors(batch, m, sched, tr, True, packed=True, **kw)
+    assert torch.equal(a, b)  # padded path on both calls, padded positions included
+
+
 @pytest.mark.parametrize("precision", MODES)
 def test_forward_cfg3_length_512(precision):
     """BASELINE cfg 3 shape: max_seq_len 512 (distance_embedding [1023,64]), n_lig = 48, n_rec = 464 + a ragged graph;
