@@ -236,12 +236,28 @@ def cfg3_strong_record(sd, dev, world, rank, barrier, precision, steps=2, warmup
         ok = bool(torch.isfinite(out).all())
         value = total * T * steps / (ms * 1e-3)
         peak, _, _ = measured_peaks()
+        packed_value = None
+        if precision != "fp32":
+            runp = lambda: sd.denoise_tensors(dbatch, model, sched, trans, True, timesteps=T, x_T=dx_T, seed=5, graph_id0=lo, packed=True)
+            outp = runp()
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                outp = runp()
+            e1.record()
+            barrier()
+            msp = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(msp, op=dist.ReduceOp.MAX)
+            vm = dbatch["ligand_attn_mask"].bool()
+            packed_value = {"value": total * T * steps / (msp.item() * 1e-3), "ms_per_sampling": msp.item() / steps,
+                            "identical_to_padded_at_valid_positions": bool(torch.equal(outp[vm], out[vm]))}
         model.release()
         del model
         torch.cuda.empty_cache()
         return {"workload": wl["text"].format(T=T, B=Bl), "scaling": "strong", "graphs_total": total, "graphs_per_gpu": Bl, "L": L, "timesteps": T,
                 "value": value, "unit": UNIT, "ms_per_sampling": ms / steps, "ms_this_rank": ms_rank / steps, "steps": steps, "warmup": warmup,
-                "finite": ok, "whole_step_model_flops_frac": (value / world) * wl["flops"] / 1e12 / peak, "dtype": precision}
+                "finite": ok, "whole_step_model_flops_frac": (value / world) * wl["flops"] / 1e12 / peak, "dtype": precision, "packed": packed_value}
     finally:
         L = keep_L
 
@@ -436,6 +452,28 @@ def main():
     value = world * B * T * args.steps / (ms * 1e-3)
     assert torch.isfinite(out).all()
 
+    # ---- the same samplings with ragged packing (valid prefixes only; bit-identical at every position denoise() reads) ----
+    packed_rec = None
+    if args.precision != "fp32":
+        run_packed = lambda: sd.denoise_tensors(dbatch, model, sched, trans, True, timesteps=T, x_T=dx_T, seed=5, graph_id0=gid0, packed=True)
+        for _ in range(max(1, args.warmup // 2)):
+            outp = run_packed()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(args.steps):
+            outp = run_packed()
+        p1.record()
+        barrier()
+        pms = torch.tensor([p0.elapsed_time(p1)], device=dev)
+        if world > 1:
+            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+        vmask = dbatch["ligand_attn_mask"].bool()
+        tok = (dbatch["ligand_attn_mask"].sum() + dbatch["receptor_attn_mask"].sum()).item() / (2.0 * B * L)
+        packed_rec = {"value": world * B * T * args.steps / (pms.item() * 1e-3), "unit": UNIT, "ms_per_step": pms.item() / args.steps,
+                      "valid_token_frac": tok, "identical_to_padded_at_valid_positions": bool(torch.equal(outp[vmask], out[vmask])),
+                      "note": "ragged packing (seqdiff_sample_ex flag 1): M = sum of lengths; `value` above is the padded computation"}
+
     result = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": args.precision,
               "data": "synthetic",
@@ -444,6 +482,8 @@ def main():
                          "l2": "per-step working set of activations (0.9 GB at cfg2, ~10 GB at cfg3) >> 126 MB L2 (no explicit flush needed)",
                          "pocket_graphs_per_s": value / T, "edge_msgs_per_s": value * 15 * L * L},
               "clocks": clk.summary(), "gpu_launches": int(launches)}
+    if packed_rec is not None:
+        result["packed"] = packed_rec
 
     if not args.no_extras and args.workload == "cfg2":
         # ---- the two other multi-GPU configurations BASELINE.json names, on the ranks of THIS job (all ranks take part) ----
@@ -476,6 +516,20 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         result["e2e"] = {"value": world * B * T * args.steps / dt.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                          "d2h_bytes_per_step": int(d2h), "api": "denoise(batch_on_pinned_host, model, noise_schedule, transition, diverse)"}
+        if packed_rec is not None:
+            with contextlib.redirect_stdout(io.StringIO()):
+                sd.denoise(pinned, model, sched, trans, True, timesteps=T, x_T=px_T, seed=5, graph_id0=gid0, packed=True)
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    ids_p, true_p, pred_p, rates_p = sd.denoise(pinned, model, sched, trans, True, timesteps=T, x_T=px_T, seed=5, graph_id0=gid0, packed=True)
+                barrier()
+                dtp = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+            result["packed"]["e2e"] = {"value": world * B * T * args.steps / dtp.item(), "unit": UNIT,
+                                       "same_decoded_sequences_as_padded": bool(pred_p == pred_seq and rates_p == rates),
+                                       "api": "denoise(batch_on_pinned_host, ..., packed=True)"}
 
         # ---- roofline of the dominant kernel (tcgen05 GEMM), timed live with CUDA events (library profiler) ----
         if rank == 0:

@@ -330,6 +330,42 @@ int seqdiff_op_attention(int precision, int B, int heads, int Lq, int Lk, const 
   SD_GUARD_END
 }
 
+// training attention, operator level: impl 0 = tensor-core kernels (16-bit modes), 1 = fp32 SIMT kernels (every mode)
+int seqdiff_op_attention_train_fwd(int precision, int impl, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k, int ldk,
+                                   const void* v, int ldv, const void* dist_emb, int P, const float* key_mask, float p_drop, uint64_t seed,
+                                   uint32_t site, uint32_t step, void* out, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(q && k && v && key_mask && out, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const DropSpec dr{p_drop, site, step, seed};
+#define SD_ATF(T, FN) FN<T>(B, heads, Lq, Lk, static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv, \
+                           static_cast<const T*>(dist_emb), P, key_mask, dr, static_cast<T*>(out), s)
+  if (precision == SEQDIFF_FP32) return SD_ATF(float, attention_train_fwd);
+  if (precision == SEQDIFF_BF16) return impl ? SD_ATF(bf16, attention_train_fwd) : SD_ATF(bf16, attention_train_fwd_tc);
+  SD_CHECK(precision == SEQDIFF_FP16, "bad precision");
+  return impl ? SD_ATF(f16, attention_train_fwd) : SD_ATF(f16, attention_train_fwd_tc);
+#undef SD_ATF
+  SD_GUARD_END
+}
+int seqdiff_op_attention_train_bwd(int precision, int impl, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k, int ldk,
+                                   const void* v, int ldv, const void* dist_emb, int P, const float* key_mask, float p_drop, uint64_t seed,
+                                   uint32_t site, uint32_t step, const void* dout, void* dq, void* dk, void* dv, float* dE, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(q && k && v && key_mask && dout && dq && dk && dv, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const DropSpec dr{p_drop, site, step, seed};
+  const int Hh = heads * 64;
+#define SD_ATB(T, FN) FN<T>(B, heads, Lq, Lk, static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv, \
+                           static_cast<const T*>(dist_emb), P, key_mask, dr, static_cast<const T*>(dout), static_cast<T*>(dq), Hh,        \
+                           static_cast<T*>(dk), Hh, static_cast<T*>(dv), Hh, dE, s)
+  if (precision == SEQDIFF_FP32) return SD_ATB(float, attention_bwd);
+  if (precision == SEQDIFF_BF16) return impl ? SD_ATB(bf16, attention_bwd) : SD_ATB(bf16, attention_bwd_tc);
+  SD_CHECK(precision == SEQDIFF_FP16, "bad precision");
+  return impl ? SD_ATB(f16, attention_bwd) : SD_ATB(f16, attention_bwd_tc);
+#undef SD_ATB
+  SD_GUARD_END
+}
+
 int seqdiff_op_layernorm(int precision, int M, int H, const float* in, const float* ln_w, const float* ln_b, float eps, float* out32, void* out16,
                          float* stats, void* stream) {
   SD_GUARD_BEGIN

@@ -199,4 +199,13 @@ template <typename T>
 int attention_bwd(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
                   const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s);
 
+// attention_train_tc.cu: the same two operations on warp-level tensor-core MMAs (16-bit modes; the SIMT kernels above stay the fp32
+// parity path and the reference these are tested against)
+template <typename T>
+int attention_train_fwd_tc(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
+                           const float* key_mask, DropSpec dr, T* out, cudaStream_t s);
+template <typename T>
+int attention_bwd_tc(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
+                     const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s);
+
 }  // namespace seqdiff

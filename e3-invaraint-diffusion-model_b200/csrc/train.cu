@@ -14,7 +14,9 @@
 //   db = column sums of dy (fused into the transpose of dy)
 // Residual-stream gradients stay fp32; a gradient becomes 16-bit only as a GEMM operand.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <type_traits>
 
 #include "model.cuh"
@@ -261,6 +263,8 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   auto hid = [&]() { return DropSpec{a.p_hidden, site++, a.step, a.seed}; };
   auto att = [&]() { return DropSpec{a.p_attn, site++, a.step, a.seed}; };
   const DropSpec nodrop{0.f, 0u, 0u, 0ull};
+  // SEQDIFF_TRAIN_ATTN=simt: the fp32 SIMT attention kernels in the 16-bit modes as well (A/B reference of the tensor-core kernels)
+  static const bool simt_attn = [] { const char* e = getenv("SEQDIFF_TRAIN_ATTN"); return e && std::string(e) == "simt"; }();
 
   // ---- workspace ----------------------------------------------------------------------------------
   const size_t es = sizeof(T);
@@ -299,6 +303,9 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
                       const DropSpec& dr, T* out) -> int {
     const T* e = E ? static_cast<const T*>(wsel<T>(*E)) : nullptr;
     if (dr.p <= 0.f) return attention<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, out, s);
+    if constexpr (k16) {
+      if (!simt_attn) return attention_train_fwd_tc<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s);
+    }
     return attention_train_fwd<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s);
   };
 
@@ -483,6 +490,9 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   auto attn_bwd = [&](int nb, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const Wt* E, const float* mask,
                       const DropSpec& dr, const T* dctx, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* gE) -> int {
     const T* e = E ? static_cast<const T*>(wsel<T>(*E)) : nullptr;
+    if constexpr (k16) {
+      if (!simt_attn) return attention_bwd_tc<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s);
+    }
     return attention_bwd<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s);
   };
 

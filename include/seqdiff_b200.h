@@ -249,6 +249,17 @@ SEQDIFF_API int seqdiff_op_gemm_ln(int precision, int M, int N, int K, const voi
 SEQDIFF_API int seqdiff_op_attention(int precision, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k,
                          int ldk, const void* v, int ldv, const void* dist_emb, int P, const float* key_mask,
                          void* out, void* stream);
+/* training attention (csrc/attention_train*.cu): the attention core above with dropout on the probabilities (mask from Philox keyed by
+ * (seed, site, element, step); p_drop = 0: none), and its backward.  impl 0: warp-level tensor-core kernels (16-bit modes only),
+ * 1: fp32 SIMT kernels (all modes; the fp32 parity path).  L <= 128.  out / dout / dq / dk / dv: [B, L, heads*64] dense;
+ * dE [2P-1, 64] f32 is ACCUMULATED into (zero it first); NULL when dist_emb is NULL. */
+SEQDIFF_API int seqdiff_op_attention_train_fwd(int precision, int impl, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k,
+                                   int ldk, const void* v, int ldv, const void* dist_emb, int P, const float* key_mask, float p_drop,
+                                   uint64_t seed, uint32_t site, uint32_t step, void* out, void* stream);
+SEQDIFF_API int seqdiff_op_attention_train_bwd(int precision, int impl, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k,
+                                   int ldk, const void* v, int ldv, const void* dist_emb, int P, const float* key_mask, float p_drop,
+                                   uint64_t seed, uint32_t site, uint32_t step, const void* dout, void* dq, void* dk, void* dv, float* dE,
+                                   void* stream);
 /* post-LN of HF BertSelfOutput / BertOutput: y = LayerNorm(in) * ln_w + ln_b over rows of H (256/512/768/1024) fp32 values.
  * out32 [M,H] f32 and/or out16 [M,H] in the mode's 16-bit format (either may be NULL); stats [M] (mean, rstd) float2 or NULL. */
 SEQDIFF_API int seqdiff_op_layernorm(int precision, int M, int H, const float* in, const float* ln_w, const float* ln_b, float eps,

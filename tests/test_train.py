@@ -179,6 +179,73 @@ def test_gradient_parity_16bit(precision, l2_tol):
     m.release()
 
 
+def _attn_ref(q, k, v, E, mask, P):
+    """attention core of transformers 4.38.2 BertSelfAttention in torch, per head layout [B, L, heads*64]."""
+    B, Lq, H = q.shape
+    Lk, nh = k.shape[1], H // 64
+    qh, kh, vh = (x.view(B, -1, nh, 64).permute(0, 2, 1, 3) for x in (q, k, v))
+    s = qh @ kh.transpose(-1, -2)
+    if E is not None:
+        dist = torch.arange(Lq).view(-1, 1) - torch.arange(Lk).view(1, -1)
+        s = s + torch.einsum("bhld,lrd->bhlr", qh, E[dist + P - 1])
+    s = s / 8.0 + ((1.0 - mask) * -10000.0)[:, None, None, :]
+    return (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B, Lq, H)
+
+
+@gpu
+@pytest.mark.parametrize("B,heads,Lq,Lk,P,rel", [(3, 12, 128, 128, 128, True), (2, 4, 100, 77, 128, True), (2, 12, 48, 128, 128, False), (5, 2, 17, 33, 64, True)])
+def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
+    """training attention at operator level: (1) fp32 SIMT forward / backward == torch autograd on the attention core, 1e-5;
+    (2) the tensor-core kernels (bf16 / fp16 operands) agree with the SIMT kernels run on the same 16-bit inputs -- with and
+    without dropout (same Philox masks on both sides) -- to operand-rounding level."""
+    sd = sd_pkg()
+    lib = sd.lib()
+    from helpers import BF16, FP16, FP32, stream_ptr
+    p = sd._cabi.ptr
+    g = torch.Generator().manual_seed(B * 1000 + Lq + Lk)
+    Hh = heads * 64
+    q, k, v, do = (torch.randn(B, L_, Hh, generator=g) * 0.7 for L_ in (Lq, Lk, Lk, Lq))
+    E = torch.randn(2 * P - 1, 64, generator=g) * 0.5 if rel else None
+    lens = torch.randint(1, Lk + 1, (B,), generator=g)
+    mask = (torch.arange(Lk)[None, :] < lens[:, None]).float()
+
+    def run(prec, impl, dt, pdrop):
+        dev = lambda x: None if x is None else x.to(DEV).to(dt).contiguous()
+        dq_, dk_, dv_, do_, dE_ = dev(q), dev(k), dev(v), dev(do), dev(E)
+        m_ = mask.to(DEV)
+        out = torch.empty(B, Lq, Hh, device=DEV, dtype=dt)
+        gq, gk, gv = torch.empty_like(dq_), torch.empty_like(dk_), torch.empty_like(dv_)
+        gE = torch.zeros(2 * P - 1, 64, device=DEV) if rel else None
+        st = stream_ptr()
+        assert lib.seqdiff_op_attention_train_fwd(prec, impl, B, heads, Lq, Lk, p(dq_), Hh, p(dk_), Hh, p(dv_), Hh, p(dE_), P, p(m_), pdrop, 9, 3, 1,
+                                                  p(out), st) == 0, lib.seqdiff_last_error()
+        assert lib.seqdiff_op_attention_train_bwd(prec, impl, B, heads, Lq, Lk, p(dq_), Hh, p(dk_), Hh, p(dv_), Hh, p(dE_), P, p(m_), pdrop, 9, 3, 1,
+                                                  p(do_), p(gq), p(gk), p(gv), p(gE), st) == 0, lib.seqdiff_last_error()
+        torch.cuda.synchronize()
+        return [x.float().cpu() if x is not None else None for x in (out, gq, gk, gv, gE)]
+
+    # (1) fp32 SIMT vs autograd
+    leaves = [x.clone().requires_grad_(True) for x in (q, k, v)] + ([E.clone().requires_grad_(True)] if rel else [])
+    ref_out = _attn_ref(leaves[0], leaves[1], leaves[2], leaves[3] if rel else None, mask, P)
+    ref_out.backward(do)
+    ref = [ref_out.detach()] + [x.grad for x in leaves[:3]] + [leaves[3].grad if rel else None]
+    got = run(FP32, 1, torch.float32, 0.0)
+    for name, a, b in zip(("out", "dq", "dk", "dv", "dE"), got, ref):
+        if b is not None:
+            err = float((a - b).abs().max() / b.abs().max())
+            assert err < 1e-5, (name, err)
+    # (2) tensor-core vs SIMT on the same 16-bit inputs
+    for prec, dt, tol in ((BF16, torch.bfloat16, 2e-2), (FP16, torch.float16, 3e-3)):
+        for pdrop in (0.0, 0.1):
+            tc, simt = run(prec, 0, dt, pdrop), run(prec, 1, dt, pdrop)
+            for name, a, b in zip(("out", "dq", "dk", "dv", "dE"), tc, simt):
+                if b is not None:
+                    err = float((a - b).norm() / b.norm())
+                    assert err < tol, (name, prec, pdrop, err)
+            if pdrop > 0:
+                assert float((simt[0] - run(prec, 1, dt, 0.0)[0]).abs().max()) > 1e-3  # the mask really was applied
+
+
 @gpu
 def test_adamw_and_clip_match_torch():
     """the fused 1/world + clip_grad_norm_(1.0) + AdamW kernel against the real torch objects, three steps, fed the SAME gradients
