@@ -286,7 +286,8 @@ def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=
         dbatch = {k: (v[lo:hi].to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
         opt = model.configure_optimizers(grad_comm=grad_comm)["optimizer"]
 
-        def step(i, skip=False):
+        def step(i, skip=False, overlap=True):
+            opt.overlap = overlap and not skip
             loss = model.training_step(dbatch, i)
             opt.step(skip_all_reduce=skip)
             return loss
@@ -308,8 +309,10 @@ def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=
         for i in range(warmup):
             step(i)
         launches_per_step = (sd.lib().seqdiff_launch_count() - n0) // max(warmup, 1)
-        ms_full, loss = timed(lambda i: step(i), steps)
+        ms_full, loss = timed(lambda i: step(i), steps)                       # bucketed all-reduce under the backward pass
+        ms_block, _ = timed(lambda i: step(i, overlap=False), steps) if world > 1 else (ms_full, None)  # all-reduce after the backward pass
         ms_nocomm, _ = timed(lambda i: step(i, skip=True), steps)
+        opt.overlap = True
         ms_ar, _ = timed(lambda i: opt.all_reduce_grads(), steps) if world > 1 else (0.0, None)
         nbytes = opt.last_allreduce_bytes
         flops = 3 * 18.369e9 * global_batch  # forward + backward ~ 3x the forward's algorithmic FLOPs
@@ -318,8 +321,11 @@ def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=
                            "AdamW lr 5e-5 wd 0.1, clip 1.0, one NCCL gradient all-reduce per step",
                "scaling": "strong", "global_batch": global_batch, "graphs_per_gpu": Bl, "dtype": precision,
                "value": global_batch / (ms_full * 1e-3), "unit": "graphs/s (training)", "steps_per_s": 1e3 / ms_full, "ms_per_step": ms_full,
-               "ms_per_step_without_allreduce": ms_nocomm, "ms_allreduce_alone": ms_ar,
+               "ms_per_step_without_allreduce": ms_nocomm, "ms_per_step_allreduce_after_backward": ms_block, "ms_allreduce_alone": ms_ar,
+               "allreduce": "4 buckets in backward order on a communication stream, each behind the CUDA event the backward pass records "
+                            "when that bucket is final (seqdiff_train_set_bucket_events)",
                "exposed_allreduce_frac": max(0.0, (ms_full - ms_nocomm) / ms_full) if world > 1 else 0.0,
+               "exposed_allreduce_frac_without_overlap": max(0.0, (ms_block - ms_nocomm) / ms_block) if world > 1 else 0.0,
                "allreduce_bytes": int(nbytes), "grad_comm": grad_comm, "live_parameters": int(opt.flat.live_numel),
                "allreduce_bus_GBps": (2.0 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9) if (world > 1 and ms_ar > 0) else None,
                "train_flops_frac_of_peak": flops / world / (ms_full * 1e-3) / 1e12 / peak, "launches_per_step": int(launches_per_step),

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_train_tc_kernel(int h
                                                                           const T* __restrict__ E, int P, const float* __restrict__ key_mask,
                                                                           DropSpec dr, T* __restrict__ out, const T* __restrict__ dout,
                                                                           T* __restrict__ dq, int lddq, T* __restrict__ dk, int lddk,
-                                                                          T* __restrict__ dv, int lddv, float* __restrict__ dE) {
+                                                                          T* __restrict__ dv, int lddv, float* __restrict__ dE, int n_items) {
   extern __shared__ __align__(128) uint8_t smraw[];
   uint8_t* sm = smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u);
   T* sK = reinterpret_cast<T*>(sm + TcSmem::kK);
@@ -109,15 +109,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_train_tc_kernel(int h
   float* sMask = reinterpret_cast<float*>(sm + TcSmem::kMask);
   float* sdE = reinterpret_cast<float*>(sm + TcSmem::kdE);
 
-  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x, warp = t >> 5;
   const int H = heads * 64;
+  // dE of the distance embedding accumulates in shared memory over ALL (graph, head) items this CTA walks and is flushed once:
+  // with one item per CTA every CTA sent 16 K atomics to the same 255 x 64 addresses (25 M contended atomics per launch at B = 128).
+  if (REL && BWD)
+    for (int e = t; e < 256 * 64; e += kTcThreads) sdE[e] = 0.f;
+  const int l = t >> 3, c = t & 7;  // elementwise phases: row l of the block, keys 16 c .. 16 c + 15
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int h = item % heads, b = item / heads;
+  __syncthreads();  // the previous item's epilogue is done with the staging buffers
   const T* qb = q + static_cast<size_t>(b) * Lq * ldq + h * 64;
   tc_stage<T>(sK, k + static_cast<size_t>(b) * Lk * ldk + h * 64, ldk, Lk, kTcK);
   tc_stage<T>(sV, v + static_cast<size_t>(b) * Lk * ldv + h * 64, ldv, Lk, kTcK);
   for (int r = t; r < kTcK; r += kTcThreads)
     sMask[r] = r < Lk ? (1.0f - key_mask[static_cast<size_t>(b) * Lk + r]) * -10000.0f : -INFINITY;
-  if (REL && BWD)
-    for (int e = t; e < 256 * 64; e += kTcThreads) sdE[e] = 0.f;
 
   // dK / dV of this warp's 16 keys: 4 column tiles each, alive across the query blocks
   wmma::fragment<wmma::accumulator, 16, 16, 16, float> accK[BWD ? 4 : 1], accV[BWD ? 4 : 1];
@@ -125,7 +131,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_train_tc_kernel(int h
 #pragma unroll
     for (int n = 0; n < 4; ++n) { wmma::fill_fragment(accK[n], 0.f); wmma::fill_fragment(accV[n], 0.f); }
   }
-  const int l = t >> 3, c = t & 7;  // elementwise phases: row l of the block, keys 16 c .. 16 c + 15
   const size_t drop_base = (static_cast<size_t>(b) * heads + h) * Lq;
 
   for (int q0 = 0; q0 < Lq; q0 += kTcQB) {
@@ -324,7 +329,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_train_tc_kernel(int h
       }
       __syncthreads();
     }
+  }
+  }  // item loop
+  if (BWD) {
     if (REL) {
+      __syncthreads();
       // diagonal a = (l - r) + 127  <->  E row a - 127 + P - 1
       for (int e = t; e < 256 * 64; e += kTcThreads) {
         const float x = sdE[e];
@@ -346,8 +355,12 @@ static int launch_tc_at(int B, int heads, int Lq, int Lk, const T* q, int ldq, c
     SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kEnd + 128));
     configured = true;
   }
-  SD_CUDA(launch_k(kfn, dim3(heads, B), dim3(kTcThreads), smem, s, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, E, P, mask, dr, out, dout, dq, lddq, dk, lddk,
-                   dv, lddv, dE));
+  // REL backward: a few items per CTA so that the dE flush (16 K atomics per CTA) is amortised; otherwise one item per CTA
+  const int n_items = B * heads;
+  int grid = n_items;
+  if (REL && BWD) { const int cap = 2 * num_sms(); if (grid > cap) grid = cap; }
+  SD_CUDA(launch_k(kfn, dim3(grid), dim3(kTcThreads), smem, s, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, E, P, mask, dr, out, dout, dq, lddq, dk, lddk,
+                   dv, lddv, dE, n_items));
   SD_LAUNCHED(BWD ? "attention_bwd_tc" : "attention_train_fwd_tc", s);
   return SEQDIFF_OK;
 }

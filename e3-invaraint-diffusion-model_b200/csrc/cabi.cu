@@ -173,6 +173,30 @@ int seqdiff_train_param_table(seqdiff_model_t* m, char* names, int name_stride, 
   }
 }
 
+int seqdiff_train_grad_buckets(seqdiff_model_t* m, int64_t* bounds, int cap) {
+  try {
+    if (!m || m->impl.build_slots() != SEQDIFF_OK) return -1;
+    const int n = static_cast<int>(m->impl.grad_bucket_bounds.size()) - 1;
+    if (cap <= 0) return n;
+    if (!bounds || cap < n + 1) return -1;
+    for (int i = 0; i <= n; ++i) bounds[i] = m->impl.grad_bucket_bounds[i];
+    return n;
+  } catch (...) {
+    return -1;
+  }
+}
+
+int seqdiff_train_set_bucket_events(seqdiff_model_t* m, void** events, int n) {
+  SD_GUARD_BEGIN
+  SD_CHECK(m && n >= 0 && (n == 0 || events), "null argument");
+  SD_TRY(m->impl.build_slots());
+  SD_CHECK(n == 0 || n == static_cast<int>(m->impl.grad_bucket_bounds.size()) - 1, "one event slot per gradient bucket (seqdiff_train_grad_buckets)");
+  m->impl.bucket_events.assign(static_cast<size_t>(n), nullptr);
+  for (int i = 0; i < n; ++i) m->impl.bucket_events[i] = static_cast<cudaEvent_t>(events[i]);
+  return SEQDIFF_OK;
+  SD_GUARD_END
+}
+
 int seqdiff_train_step(seqdiff_model_t* m, int precision, int B, int L_lig, int L_rec, const float* t_norm, const float* noised_ligand_seq,
                        const float* ligand_seq, const float* ligand_angle, const float* ligand_mask, const float* receptor_seq,
                        const float* receptor_angle, const float* receptor_mask, float p_hidden, float p_attn, uint64_t seed, uint32_t step,

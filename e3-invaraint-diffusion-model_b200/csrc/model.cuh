@@ -159,6 +159,8 @@ struct Model {
   std::vector<ParamSlot> slots;            // trainable tensors in flat-buffer order (fused groups contiguous)
   std::map<std::string, int> slot_of;
   int64_t train_total = 0;
+  std::vector<int64_t> grad_bucket_bounds;  // flat offsets [n+1]: the backward pass finishes bucket n-1 first, bucket 0 last
+  std::vector<cudaEvent_t> bucket_events;   // caller-owned; event k is recorded on the training stream once bucket k is final
   int train_prec = -1;                     // precision the transposed operand copies (Wt::t) were built for; -1 = none
   bool repack_reuse = false;               // finalize() after an optimizer step: re-fill the packed buffers in place
   size_t packed_cursor = 0;

@@ -121,8 +121,10 @@ int Model::build_slots() {
   };
   for (const char* e : {"ligand_seq_embedding", "ligand_angle_embedding", "receptor_seq_embedding", "receptor_angle_embedding"})
     for (const char* t : {".linear.weight", ".linear.bias", ".LayerNorm.weight", ".LayerNorm.bias"}) add(std::string(e) + t);
-  for (const char* blk : {"ligand_feature_emb", "decoder_normalize"}) {  // receptor_feature_emb: dead weight, no gradient (quirk Q1)
-    const std::string p = blk;
+  // The flat index space follows the FORWARD order of the network, so the backward pass finishes it from the end towards the start
+  // and the data-parallel all-reduce can start on the tail buckets while the head of the buffer is still being computed
+  // (grad_bucket_bounds, bucket_events).  receptor_feature_emb: dead weight, no gradient (quirk Q1).
+  auto se_block = [&](const std::string& p) {
     add(p + ".adaLN_modulation.0.weight");
     add(p + ".adaLN_modulation.0.bias");
     add(p + ".adaLN_modulation.2.weight");
@@ -132,7 +134,11 @@ int Model::build_slots() {
     add(p + ".mlp.0.bias");
     add(p + ".mlp.3.weight");
     add(p + ".mlp.3.bias");
-  }
+  };
+  grad_bucket_bounds.clear();
+  grad_bucket_bounds.push_back(0);        // bucket 0: the four embeddings + ligand_feature_emb (finished last)
+  se_block("ligand_feature_emb");
+  grad_bucket_bounds.push_back(off);      // bucket 1: fused cross K | V + the first half of the decoder layers
   // cross-attention K | V of every layer: contiguous in the order of the fused [layers * 2H, H] projection
   for (int i = 0; i < NL; ++i)
     for (const char* n : {"key", "value"}) add("decoder.layer." + std::to_string(i) + ".crossattention.self." + n + ".weight");
@@ -140,6 +146,7 @@ int Model::build_slots() {
     for (const char* n : {"key", "value"}) add("decoder.layer." + std::to_string(i) + ".crossattention.self." + n + ".bias");
   for (int i = 0; i < NL; ++i) {
     const std::string p = "decoder.layer." + std::to_string(i);
+    if (i == NL / 2 && i > 0) grad_bucket_bounds.push_back(off);  // bucket 2: the second half of the decoder layers
     attn(p + ".attention", true);
     add(p + ".crossattention.self.query.weight");
     add(p + ".crossattention.self.query.bias");
@@ -154,8 +161,11 @@ int Model::build_slots() {
     add(p + ".output.LayerNorm.weight");
     add(p + ".output.LayerNorm.bias");
   }
+  grad_bucket_bounds.push_back(off);      // last bucket: decoder_normalize + the predictor head (finished first)
+  se_block("decoder_normalize");
   for (const char* t : {"dense1.weight", "dense1.bias", "layer_norm.weight", "layer_norm.bias", "dense2.weight", "dense2.bias"})
     add(std::string("amino_acid_predictor.") + t);
+  grad_bucket_bounds.push_back(off);
   if (missing) {
     slots.clear();
     slot_of.clear();
@@ -549,6 +559,12 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   SD_TRY(linear_bwd(Ml, H, H, gT, se2.out.t, p1, g(hp + "dense1.weight"), g(hp + "dense1.bias"), 2, dB, nullptr));
   // decoder_normalize
   SD_TRY(se_backward(se2, dB, dC, dA, dD, nullptr));  // d(h_last) in dA
+  const int n_bk = static_cast<int>(grad_bucket_bounds.size()) - 1;
+  auto bucket_done = [&](int k) -> int {  // gradients of flat range [bounds[k], bounds[k+1]) are final from here on
+    if (k >= 0 && k < static_cast<int>(bucket_events.size()) && bucket_events[k]) SD_CUDA(cudaEventRecord(bucket_events[k], s));
+    return SEQDIFF_OK;
+  };
+  SD_TRY(bucket_done(n_bk - 1));
   // decoder layers, last to first
   float *cur = dA, *s1 = dB, *s2 = dC;
   for (int i = NL - 1; i >= 0; --i) {
@@ -583,11 +599,13 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     float* t_ = cur;
     cur = s2;
     s2 = t_;
+    if (n_bk == 4 && i == NL / 2) SD_TRY(bucket_done(2));
   }
   // gradient of ligand_feature_emb's output: [d(ligand rows) ; d(receptor rows)], the latter through the fused cross K | V projection
   SD_CUDA(cudaMemcpyAsync(dD, cur, MlH * sizeof(float), cudaMemcpyDeviceToDevice, s));
   SD_TRY(linear_bwd(Mr, NL * 2 * H, H, dkv_all, rec_t, ckv_all, g("decoder.layer.0.crossattention.self.key.weight"),
                     g("decoder.layer.0.crossattention.self.key.bias"), 2, dD + MlH, nullptr));
+  SD_TRY(bucket_done(1));
   SD_TRY(se_backward(se1, dD, dC, dA, dB, dc32));  // d(x) in dA, d(c) in dc32
   // the four BertEmbeddings
   SD_TRY(embed_bwd(dA, a.x_t, Ml, 20, H, lig_seq.Wt_, lig_seq.b, lig_seq.ln_w, eps, d_emb[0], g("ligand_seq_embedding.linear.weight"),
@@ -598,6 +616,7 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
                    g("ligand_angle_embedding.linear.bias"), g("ligand_angle_embedding.LayerNorm.weight"), g("ligand_angle_embedding.LayerNorm.bias"), s));
   SD_TRY(embed_bwd(dc32 + MlH, a.rec_angle, Mr, 8, H, rec_ang.Wt_, rec_ang.b, rec_ang.ln_w, eps, d_emb[3], g("receptor_angle_embedding.linear.weight"),
                    g("receptor_angle_embedding.linear.bias"), g("receptor_angle_embedding.LayerNorm.weight"), g("receptor_angle_embedding.LayerNorm.bias"), s));
+  SD_TRY(bucket_done(0));
   return SEQDIFF_OK;
 }
 

@@ -355,9 +355,16 @@ class PeptideDiff(ConditionalBertForDiffusionBase):
         dev = ligand_seq.device
         if dev.type != "cuda":
             raise RuntimeError("apply_aa_noise runs only on a CUDA device (no CPU fallback)")
-        t_float = t_int.cpu() / self.timesteps
-        alpha_t_bar = self.discrete_noise_schedule.get_alpha_bar(t_normalized=t_float)
-        Qtb = self.aa_transition_model.get_Qt_bar(alpha_t_bar, device=torch.device("cpu")).float().contiguous().to(dev)
+        # Qbar_t of EVERY integer step 0..T, built once on the host with the per-step arithmetic of the reference (t_int / T in
+        # fp32 -> alpha_bar -> BLOSUM row softmax: elementwise in t, so row k of the table == what the reference computes for
+        # t_int == k) and kept on the device; the per-graph gather runs there, so a training step never waits on the host.
+        key = (self.timesteps, dev)
+        if getattr(self, "_qtb_all_key", None) != key:
+            t_all = torch.arange(self.timesteps + 1, dtype=torch.float32).unsqueeze(1) / self.timesteps
+            a_all = self.discrete_noise_schedule.get_alpha_bar(t_normalized=t_all)
+            self._qtb_all = self.aa_transition_model.get_Qt_bar(a_all, device=torch.device("cpu")).float().contiguous().to(dev)
+            self._qtb_all_key = key
+        Qtb = self._qtb_all[t_int.to(dev).reshape(-1).long()].contiguous()
         x0 = ligand_seq.to(torch.float32).contiguous()
         out = torch.empty_like(x0)
         E = None if noise_E is None else noise_E.to(device=dev, dtype=torch.float32).contiguous()
@@ -419,7 +426,12 @@ class PeptideDiff(ConditionalBertForDiffusionBase):
         aa = self.apply_aa_noise(x0.to(dev), t_int, noise_E=noise_E)
         flat = self._flat_params()
         self._train_steps = getattr(self, "_train_steps", 0) + 1
+        opt = getattr(self, "_optimizer", None)
+        if opt is not None and opt.flat is flat:
+            opt.arm_overlap()
         terms, _ = _train.train_step_tensors(self, flat, batch, t_norm, aa, seed=self._noise_seed, step=self._train_steps)
+        if opt is not None and opt.flat is flat:
+            opt.launch_overlapped_all_reduce()  # bucket k's all-reduce starts when the backward pass has finished bucket k
         loss, elbo, aa_noised_loss, aa_all_loss, aa_recovery_rate, aa_noise_rate = _train.loss_from_terms(terms)
         self.last_log = {"aa_noise_rate": aa_noise_rate, "aa_recovery_rate": aa_recovery_rate, "avg_timestep": t_int.mean().int(),
                          "train_loss": loss, "train_aa_noised_loss": aa_noised_loss, "train_aa_all_loss": aa_all_loss, "train_elbo_loss": elbo}

@@ -9,9 +9,12 @@ reference: sequence_model/model.py:347-367 (training_step), :313-345 (get_loss),
 train_model.py:30-33 (lr 5e-5, l2_norm 0.1, gradient_clip 1.0, LinearWarmup), :95 (gradient_clip_val).
 
 Data parallelism.  Every rank holds the full model (61.06 M live parameters), runs its block of the global batch and the ranks
-sum their gradients: ONE all-reduce per step over the flat buffer (244 MB fp32, or 122 MB with `grad_comm="bf16"`), issued as
-`buckets` chunks.  The update needs the GLOBAL gradient norm (clip), so it starts only after the last chunk has arrived.
-Lightning DDP semantics: per-rank mean loss, gradients averaged over ranks.
+sum their gradients over the flat buffer (244 MB fp32, or 122 MB with `grad_comm="bf16"`).  The flat index space follows the forward
+order of the network, so the backward pass finishes it from the end: the library records one CUDA event per gradient bucket
+(seqdiff_train_set_bucket_events) and the all-reduce of bucket k runs on a communication stream as soon as event k has fired -- under
+the rest of the backward pass; only the last bucket (embeddings + ligand_feature_emb, 18 % of the bytes) is exposed.  The update
+needs the GLOBAL gradient norm (clip), so it starts only after the last bucket has arrived.  Lightning DDP semantics: per-rank mean
+loss, gradients averaged over ranks.
 """
 from __future__ import annotations
 
@@ -47,6 +50,11 @@ class FlatParams:
             self.table[names.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode()] = (int(offs[i]), int(nums[i]))
         self.grads = torch.zeros(self.total, device=self.device, dtype=torch.float32)
         self.live_numel = sum(v[1] for v in self.table.values())
+        nb = int(lib.seqdiff_train_grad_buckets(self.handle, None, 0))
+        bounds = (ctypes.c_int64 * (nb + 1))()
+        if nb <= 0 or lib.seqdiff_train_grad_buckets(self.handle, bounds, nb + 1) != nb:
+            raise _cabi.SeqdiffError("seqdiff_train_grad_buckets failed")
+        self.bucket_bounds = [int(b) for b in bounds]   # bucket k = grads[bounds[k]:bounds[k+1]]; the backward finishes k = nb-1 first
 
     def grad(self, name: str, shape=None) -> torch.Tensor:
         off, n = self.table[name]
@@ -68,7 +76,7 @@ class FlatAdamW:
     the data-parallel gradient average and torch.nn.utils.clip_grad_norm_(max_norm=gradient_clip).  One fused kernel pass."""
 
     def __init__(self, flat: FlatParams, lr=5e-5, weight_decay=0.1, betas=(0.9, 0.999), eps=1e-8, gradient_clip=1.0, group=None,
-                 grad_comm: str = "fp32", buckets: int = 4):
+                 grad_comm: str = "fp32", overlap: bool = True):
         self.flat = flat
         self.lr, self.weight_decay, self.betas, self.eps, self.gradient_clip = lr, weight_decay, betas, eps, gradient_clip
         self.exp_avg = torch.zeros_like(flat.grads)
@@ -78,7 +86,10 @@ class FlatAdamW:
         if grad_comm not in ("fp32", "bf16"):
             raise ValueError("grad_comm must be 'fp32' or 'bf16'")
         self.grad_comm = grad_comm
-        self.buckets = max(1, int(buckets))
+        self.overlap = bool(overlap)
+        self._events = None
+        self._comm_stream = None
+        self._pending = False
         self.grad_norm = torch.zeros(1, device=flat.device, dtype=torch.float32)
         self.last_allreduce_bytes = 0
         self.param_groups = [{"lr": lr, "weight_decay": weight_decay}]  # what an lr scheduler touches
@@ -87,30 +98,61 @@ class FlatAdamW:
         import torch.distributed as dist
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
-    def all_reduce_grads(self):
-        """sum over the data-parallel ranks, in place on the flat buffer (the averaging 1/world is folded into the update kernel)."""
+    def _reduce_chunk(self, chunk):
         import torch.distributed as dist
+        if self.grad_comm == "bf16":
+            c16 = chunk.to(torch.bfloat16)
+            dist.all_reduce(c16, group=self.group)
+            chunk.copy_(c16)
+            self.last_allreduce_bytes += c16.numel() * 2
+        else:
+            dist.all_reduce(chunk, group=self.group)
+            self.last_allreduce_bytes += chunk.numel() * 4
+
+    def arm_overlap(self):
+        """Registers one CUDA event per gradient bucket with the handle (once).  From then on every seqdiff_train_step records
+        event k when bucket k is final; `launch_overlapped_all_reduce` (called right after training_step) consumes them."""
+        if self._events is not None or not self.overlap or self.world() == 1:
+            return
+        f = self.flat
+        nb = len(f.bucket_bounds) - 1
+        with torch.cuda.device(f.device):
+            self._comm_stream = torch.cuda.Stream(device=f.device)
+            self._events = [torch.cuda.Event(enable_timing=False, blocking=False) for _ in range(nb)]
+            for e in self._events:
+                e.record()  # materialises the cudaEvent_t behind the (lazily created) torch event
+            arr = (ctypes.c_void_p * nb)(*[ctypes.c_void_p(e.cuda_event) for e in self._events])
+            _cabi.check(_cabi.lib().seqdiff_train_set_bucket_events(f.handle, arr, nb))
+
+    def launch_overlapped_all_reduce(self):
+        """Enqueues the per-bucket all-reduces on the communication stream, each behind its bucket's event (tail bucket first: the
+        order in which the backward pass finishes them).  Host-side this returns at once; `step()` joins the stream."""
+        if self._events is None or not self.overlap:
+            return
+        f = self.flat
+        self.last_allreduce_bytes = 0
+        with torch.cuda.stream(self._comm_stream):
+            for k in range(len(self._events) - 1, -1, -1):
+                self._comm_stream.wait_event(self._events[k])
+                self._reduce_chunk(f.grads[f.bucket_bounds[k]:f.bucket_bounds[k + 1]])
+        self._pending = True
+
+    def all_reduce_grads(self):
+        """sum over the data-parallel ranks, in place on the flat buffer (the averaging 1/world is folded into the update kernel).
+        Blocking form (no overlap): the same buckets, on the current stream, after the backward pass."""
         world = self.world()
         self.last_allreduce_bytes = 0
         if world == 1:
             return
-        g = self.flat.grads
-        n = g.numel()
-        step = (n + self.buckets - 1) // self.buckets
-        step = (step + 1023) // 1024 * 1024
-        for lo in range(0, n, step):
-            chunk = g[lo:lo + step]
-            if self.grad_comm == "bf16":
-                c16 = chunk.to(torch.bfloat16)
-                dist.all_reduce(c16, group=self.group)
-                chunk.copy_(c16)
-                self.last_allreduce_bytes += c16.numel() * 2
-            else:
-                dist.all_reduce(chunk, group=self.group)
-                self.last_allreduce_bytes += chunk.numel() * 4
+        f = self.flat
+        for k in range(len(f.bucket_bounds) - 2, -1, -1):
+            self._reduce_chunk(f.grads[f.bucket_bounds[k]:f.bucket_bounds[k + 1]])
 
     def step(self, closure=None, skip_all_reduce: bool = False):
-        if not skip_all_reduce:
+        if self._pending:  # the bucketed all-reduce was launched behind the backward pass: join it
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._comm_stream)
+            self._pending = False
+        elif not skip_all_reduce:
             self.all_reduce_grads()
         self.step_count += 1
         lr = self.param_groups[0]["lr"]

@@ -179,6 +179,15 @@ SEQDIFF_API int seqdiff_loss_terms(int N, const float* logits, const float* x0, 
 SEQDIFF_API int64_t seqdiff_train_param_count(seqdiff_model_t* m);   /* elements of the flat buffers, or -1 */
 /* names[i*name_stride..] (NUL-terminated), offsets[i], numels[i]; returns the number of tensors (call with cap = 0 to query it) */
 SEQDIFF_API int seqdiff_train_param_table(seqdiff_model_t* m, char* names, int name_stride, int64_t* offsets, int64_t* numels, int cap);
+/* Overlap of the data-parallel all-reduce with the backward pass.  The flat index space follows the forward order of the network, so
+ * the backward pass finishes it from the end: seqdiff_train_grad_buckets returns n and bounds[0..n] (ascending offsets, bucket k =
+ * [bounds[k], bounds[k+1])); bucket n-1 (decoder_normalize + head) is final first, bucket 0 (embeddings + ligand_feature_emb) last.
+ * seqdiff_train_set_bucket_events registers n caller-owned cudaEvent_t (NULL entries allowed; n = 0 clears): every following
+ * seqdiff_train_step records event k on its stream as soon as bucket k holds its final gradients, so a communication stream can
+ * wait on it and reduce that range while the rest of the backward pass runs (train.py: FlatAdamW).  Replaces what DDP's gradient
+ * hooks + bucketing do under Lightning for the reference (train_model.py:92-110). */
+SEQDIFF_API int seqdiff_train_grad_buckets(seqdiff_model_t* m, int64_t* bounds, int cap);  /* returns n (cap = 0: query), -1 on error */
+SEQDIFF_API int seqdiff_train_set_bucket_events(seqdiff_model_t* m, void** events, int n);
 /* forward (training mode) + loss + backward.  t_norm [B] = t_int / T as the reference passes it when training (quirk Q3);
  * noised_ligand_seq = apply_aa_noise(ligand_seq, t_int) (seqdiff_apply_aa_noise); ligand_seq [B,L_lig,20] one-hot targets.
  * p_hidden / p_attn = hidden_dropout_prob / attention_probs_dropout_prob (0 for parity runs); masks come from Philox keyed by

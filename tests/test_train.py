@@ -77,8 +77,9 @@ def _ddp_worker(rank, world, port, q):
         device = torch.device("cpu")
         model = None
         handle = None
+        bucket_bounds = [0, 1200, 3100, 5000]  # the library's gradient buckets (seqdiff_train_grad_buckets): reduced tail first
     opt = sd.train.FlatAdamW.__new__(sd.train.FlatAdamW)
-    opt.flat, opt.group, opt.grad_comm, opt.buckets, opt.last_allreduce_bytes = Flat, None, "fp32", 3, 0
+    opt.flat, opt.group, opt.grad_comm, opt.last_allreduce_bytes = Flat, None, "fp32", 0
     opt.all_reduce_grads()
     q.put((rank, Flat.grads.clone(), opt.last_allreduce_bytes))
     dist.destroy_process_group()
