@@ -262,7 +262,7 @@ def cfg3_strong_record(sd, dev, world, rank, barrier, precision, steps=2, warmup
         L = keep_L
 
 
-def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=3, global_batch=128, grad_comm="fp32"):
+def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=3, global_batch=128, grad_comm="fp32", weak=False):
     """BASELINE configs[3]: one optimizer step of the sequence denoiser on a GLOBAL batch of 128 graphs (L = 128, T = 50, dropout 0.1,
     AdamW lr 5e-5 wd 0.1, clip 1.0: train_model.py:17-33), data-parallel over the ranks (128 / world graphs each), ONE gradient
     all-reduce per step over NCCL (61.06 M live parameters).  Reports whole steps (training_step + all-reduce + clip + AdamW), the
@@ -273,6 +273,8 @@ def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=
     L = 128
     try:
         T = 50
+        if weak:  # Lightning-DDP reading of "batch 128": the DataLoader batch size is per process (train_model.py:38,50), global = 128 x world
+            global_batch = global_batch * world
         lo, hi = sd.shard_bounds(global_batch, world, rank)
         Bl = hi - lo
         torch.manual_seed(0)
@@ -319,7 +321,7 @@ def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=
         peak, _, _ = measured_peaks()
         rec = {"workload": f"BASELINE configs[3]: training step, global batch {global_batch} graphs ({Bl} on this rank), L=128, T=50, dropout 0.1, "
                            "AdamW lr 5e-5 wd 0.1, clip 1.0, one NCCL gradient all-reduce per step",
-               "scaling": "strong", "global_batch": global_batch, "graphs_per_gpu": Bl, "dtype": precision,
+               "scaling": "weak" if weak else "strong", "global_batch": global_batch, "graphs_per_gpu": Bl, "dtype": precision,
                "value": global_batch / (ms_full * 1e-3), "unit": "graphs/s (training)", "steps_per_s": 1e3 / ms_full, "ms_per_step": ms_full,
                "ms_per_step_without_allreduce": ms_nocomm, "ms_per_step_allreduce_after_backward": ms_block, "ms_allreduce_alone": ms_ar,
                "allreduce": "4 buckets in backward order on a communication stream, each behind the CUDA event the backward pass records "
@@ -499,6 +501,13 @@ def main():
             except Exception as ex:  # extras never cost the headline line
                 result[key] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
                 barrier()
+        if world > 1 and "error" not in result["cfg4_train"]:
+            # the per-process reading of the same configuration (128 graphs on EVERY GPU, as Lightning DDP shards a DataLoader)
+            try:
+                result["cfg4_train"]["weak_128_per_gpu"] = cfg4_train_record(sd, dev, world, rank, barrier, args.precision, weak=True)
+            except Exception as ex:
+                result["cfg4_train"]["weak_128_per_gpu"] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+                barrier()
 
     if not args.no_extras:
         # ---- end to end through the public API: denoise(batch_on_host, ...) -> decoded sequences on the host ----
@@ -575,7 +584,8 @@ def main():
                           (NL + 1, Ml_, 3 * H, H, 0, False), (2 * NL + 1, Ml_, H, H, 0, True), (NL + 1, Ml_, H, H, 0, False),
                           (NL, Ml_, I, H, 1, False), (NL, Ml_, H, I, 0, True), (1, Ml_, 4 * H, H, 1, False), (1, Ml_, H, 4 * H, 0, True)]
                 pp = sd._cabi.ptr
-                iso_us, iso_fl = 0.0, 0.0
+                iso_us, iso_fl, bound_us, per_shape = 0.0, 0.0, 0.0, []
+                burst0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
                 for cnt, M_, N_, K_, epi_, res_ in shapes:
                     A_ = torch.randn(M_, K_, device=dev).bfloat16()
                     W_ = (torch.randn(N_, K_, device=dev) / math.sqrt(K_)).bfloat16()
@@ -597,13 +607,25 @@ def main():
                     gr_.replay()
                     g1.record()
                     torch.cuda.synchronize(dev)
-                    iso_us += cnt * g0.elapsed_time(g1) / 20 * 1e3
+                    us_ = g0.elapsed_time(g1) / 20 * 1e3
+                    iso_us += cnt * us_
                     iso_fl += cnt * 2.0 * M_ * N_ * K_
+                    # the two floors of this launch: tensor pipe at the burst peak, and its compulsory HBM bytes (16-bit A and W once,
+                    # fp32 residual in + fp32 C out for the residual form, else 16-bit C out) at the measured copy rate
+                    by_ = 2.0 * M_ * K_ + 2.0 * N_ * K_ + (8.0 * M_ * N_ if res_ else 2.0 * M_ * N_)
+                    t_mma, t_mem = 2.0 * M_ * N_ * K_ / burst0 / 1e6, by_ / hbm / 1e3
+                    bound_us += cnt * max(t_mma, t_mem)
+                    per_shape.append({"M": M_, "N": N_, "K": K_, "resid_fp32": bool(res_), "count": cnt, "us": round(us_, 2), "tflops": round(2e-6 * M_ * N_ * K_ / us_, 1),
+                                      "floor_us_tensor": round(t_mma, 2), "floor_us_hbm": round(t_mem, 2), "frac_of_floor": round(max(t_mma, t_mem) / us_, 3)})
                     del gr_
                 burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
                 result["roofline_isolated"] = {"kernel": "gemm_tcgen05_kernel, each shape of the forward as 20 launches in a captured graph", "bound": "tensor",
                                                "achieved": iso_fl / iso_us / 1e6, "peak": burst, "unit": "TFLOP/s", "frac": iso_fl / iso_us / 1e6 / burst,
                                                "gemm_us_per_forward": iso_us, "flops_per_forward": iso_fl,
+                                               "two_floor_bound_us_per_forward": bound_us, "frac_of_two_floor_bound": bound_us / iso_us,
+                                               "two_floor_note": "per launch max(FLOPs / burst tensor peak, compulsory HBM bytes / measured copy rate): the fp32-residual "
+                                                                 "GEMMs (N = 768) are HBM-bound at 153 FLOP/B, so the tensor peak alone overstates what they can reach",
+                                               "per_shape": per_shape,
                                                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)"}
             except Exception as ex:  # the isolated sweep is an extra; never fail the bench line over it
                 result["roofline_isolated"] = {"error": str(ex)[:200]}
@@ -643,6 +665,43 @@ def main():
             result["reverse_step_roofline"] = {"kernel": "reverse_step_kernel", "bound": "hbm", "residues": RB * RL, "bytes_per_residue": 240,
                                                "avg_launch_us": rus, "achieved": rbytes / rus / 1e3, "peak": hbm, "unit": "GB/s",
                                                "frac": rbytes / rus / 1e3 / hbm, "note": "31 MB per launch fits L2 (126 MB): back-to-back launches re-hit L2, so this is an upper bound on the HBM-resident rate"}
+
+        # ---- BASELINE configs[0] shape on the GPU: ONE 128-slot pocket + peptide graph (latency; SURVEY.md section 8d cfg 1) ----
+        if rank == 0:
+            try:
+                b1, x1 = synthetic_workload(1, n_lig=(30, 30), n_rec=(98, 98))
+                d1 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b1.items()}
+                dx1 = x1.to(dev)
+                a1 = (torch.full((1, 1), 7.0, device=dev), dx1, d1["ligand_angles"], d1["ligand_attn_mask"], d1["receptor_seq"], d1["receptor_angles"],
+                      d1["receptor_attn_mask"])
+                with torch.no_grad():
+                    for _ in range(5):
+                        model(*a1)
+                    torch.cuda.synchronize(dev)
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record()
+                    for _ in range(20):
+                        model(*a1)
+                    c1.record()
+                    torch.cuda.synchronize(dev)
+                    fwd_us = c0.elapsed_time(c1) / 20 * 1e3
+                    T1 = 100
+                    s1 = sd.PredefinedNoiseScheduleDiscrete("cosine", T1)
+                    run1 = lambda: sd.denoise_tensors(d1, model, s1, trans, True, timesteps=T1, x_T=dx1, seed=5, graph_id0=0)
+                    run1()
+                    torch.cuda.synchronize(dev)
+                    c0.record()
+                    for _ in range(3):
+                        run1()
+                    c1.record()
+                    torch.cuda.synchronize(dev)
+                    step_us = c0.elapsed_time(c1) / (3 * T1) * 1e3
+                result["cfg1_latency"] = {"workload": f"BASELINE configs[0] shape: one graph, L=128 slots (30 peptide + 98 pocket residues valid), {args.precision}",
+                                          "forward_call_us": fwd_us, "forward_note": "model(...) from Python: ~60 eager launches + ctypes, device-timed over 20 calls",
+                                          "sampling_step_us": step_us, "sampling_note": f"forward + reverse step inside the replayed CUDA graph of denoise (T={T1})",
+                                          "weight_streaming_floor_us": 145e6 / hbm / 1e3}
+            except Exception as ex:
+                result["cfg1_latency"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
         # ---- the reference algorithm on this box's host cores (reported baseline, not the target) ----
         if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -79,9 +79,15 @@ int profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap) {
 // bound (146 kernels of ~10 us): +2.5 .. 2.7 % there (profiles/struct_bench_r01.json vs gpurun A/B).
 static thread_local int g_pdl_scope = 0;
 struct PdlScope {
-  PdlScope() { ++g_pdl_scope; }
-  ~PdlScope() { --g_pdl_scope; }
+  const bool on;
+  explicit PdlScope(bool enable = true) : on(enable) { if (on) ++g_pdl_scope; }
+  ~PdlScope() { if (on) --g_pdl_scope; }
 };
+// Sequence path: a step is ~90 kernels with a fixed cost of ~7 us each (B = 1: 685 us per step).  When the grids are a handful of
+// CTAs the successor's prologue (barrier init, TMEM allocation, descriptor prefetch) can run on idle SMs under the predecessor:
+// measured on B200 (profiles/pdl_small_r02.log) B = 1: 685 -> 616 us, B = 4: 711 -> 665 us per step; from B = 16 on the persistent
+// kernels fill every SM and the early launch only costs (846 -> 919 us).  Hence: on up to 2048 stacked token rows.
+static bool pdl_small_batch(int B, int Ll, int Lr) { return static_cast<long long>(B) * (Ll + Lr) <= 2048; }
 bool pdl_enabled() {
   static const int env = [] { const char* e = getenv("SEQDIFF_PDL"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
   return env >= 0 ? env == 1 : g_pdl_scope > 0;
@@ -788,6 +794,7 @@ int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, 
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
   SD_CUDA(cudaSetDevice(device));
   SD_TRY(ensure_workspace(workspace_need(precision, B, Ll, Lr)));
+  const PdlScope pdl_small(pdl_small_batch(B, Ll, Lr));
   switch (precision) {
     case SEQDIFF_FP32:
       return forward_t<float>(1, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s, nullptr);
@@ -939,6 +946,7 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
   key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables;  // (seed, gid0) are NOT part of the key: device memory, see arm_loop_kernel
   uint64_t* d_rng = reinterpret_cast<uint64_t*>(d_step + 16);
   auto one_step = [&](cudaStream_t st) -> int {
+    const PdlScope pdl_small(pdl_small_batch(B, Ll, Lr));
     SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, st, pk));
     SD_TRY(reverse_step(d_tables, 1, B, Ll, x_cur, logits, diverse, noise_E, 0, 0, 0, d_step, x_cur, nullptr, st, d_step + 1, d_rng));
     return SEQDIFF_OK;

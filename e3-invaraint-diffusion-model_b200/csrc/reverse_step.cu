@@ -234,6 +234,128 @@ __global__ void __launch_bounds__(THREADS, MINB) reverse_step_kernel(const float
   }
   __syncthreads();
 
+  if (FAST) {
+    // Production path.  A thread resolves RJ = 2 residues JOINTLY (l and l + THREADS of its CTA's slab): every 128-bit broadcast read
+    // of Qsb feeds the FFMA2s of both, and the two softmax / Philox / race chains are independent instruction streams for the
+    // scheduler -- the kernel is bound by dependency latency (41 % issue utilisation with one chain per thread),
+    // not by HBM or a pipe.  A residue past L is computed on clamped inputs and not stored.
+    constexpr int RJ = 2;
+    const float4* qsb4 = reinterpret_cast<const float4*>(sQsbA);
+    const uint64_t graph = graph_id0 + b;
+    for (int l0 = blockIdx.x * (RJ * THREADS) + threadIdx.x; l0 < L; l0 += gridDim.x * (RJ * THREADS)) {
+      asm volatile("" ::: "memory");  // keeps the 100 broadcast reads of Qsb inside the iteration (hoisted out of the loop they spill: 1.6 KB of stack)
+      int lr[RJ];
+      bool live[RJ];
+      size_t nr[RJ];
+#pragma unroll
+      for (int r = 0; r < RJ; ++r) {
+        const int l = l0 + r * THREADS;
+        live[r] = l < L;
+        lr[r] = live[r] ? l : l0;
+        nr[r] = static_cast<size_t>(b) * L + lr[r];
+      }
+      float pf[RJ][C];
+      int hotf[RJ];
+      bool onehot[RJ];
+#pragma unroll
+      for (int r = 0; r < RJ; ++r) {
+        float xr[C];
+#pragma unroll
+        for (int j4 = 0; j4 < C; j4 += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(logits + nr[r] * C + j4);
+          const float4 c4 = *reinterpret_cast<const float4*>(x_t + nr[r] * C + j4);
+          pf[r][j4] = a.x; pf[r][j4 + 1] = a.y; pf[r][j4 + 2] = a.z; pf[r][j4 + 3] = a.w;
+          xr[j4] = c4.x; xr[j4 + 1] = c4.y; xr[j4 + 2] = c4.z; xr[j4 + 3] = c4.w;
+        }
+        int h = -1, nnz = 0;
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+          if (xr[j] != 0.f) { ++nnz; h = (xr[j] == 1.0f) ? j : -2; }
+        onehot[r] = nnz == 1 && h >= 0;
+        hotf[r] = onehot[r] ? h : 0;
+      }
+#pragma unroll
+      for (int r = 0; r < RJ; ++r) {
+        float mxf = pf[r][0];
+#pragma unroll
+        for (int j = 1; j < C; ++j) mxf = fmaxf(mxf, pf[r][j]);
+#pragma unroll
+        for (int j = 0; j < C; ++j) pf[r][j] = ex2_approx((pf[r][j] - mxf) * 1.44269504088896f);  // unnormalised softmax
+        const float4* inv4 = reinterpret_cast<const float4*>(sInvT + hotf[r] * kRS);
+#pragma unroll
+        for (int i4 = 0; i4 < C / 4; ++i4) {  // a_i = p_i / Qtb[i,x]
+          const float4 w = inv4[i4];
+          pf[r][4 * i4] *= w.x; pf[r][4 * i4 + 1] *= w.y; pf[r][4 * i4 + 2] *= w.z; pf[r][4 * i4 + 3] *= w.w;
+        }
+      }
+      float2 un2[RJ][C / 2];
+#pragma unroll
+      for (int r = 0; r < RJ; ++r)
+#pragma unroll
+        for (int j = 0; j < C / 2; ++j) un2[r][j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < C; ++i) {  // fully unrolled: pf[.][i] must stay in registers
+#pragma unroll
+        for (int j4 = 0; j4 < C / 4; ++j4) {
+          const float4 w = qsb4[i * (C / 4) + j4];  // same address in every lane: broadcast; one read serves both residues
+#pragma unroll
+          for (int r = 0; r < RJ; ++r) {
+            const float2 pp = make_float2(pf[r][i], pf[r][i]);
+            un2[r][2 * j4] = ffma2(pp, make_float2(w.x, w.y), un2[r][2 * j4]);          // FFMA2: 200 instead of 400 FMA issues per residue
+            un2[r][2 * j4 + 1] = ffma2(pp, make_float2(w.z, w.w), un2[r][2 * j4 + 1]);
+          }
+        }
+      }
+      int best[RJ];
+      float bv[RJ];
+#pragma unroll
+      for (int r = 0; r < RJ; ++r) {
+        const float4* qt4 = reinterpret_cast<const float4*>(sQtT + hotf[r] * kRS);
+        float totf = 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < C / 4; ++j4) {
+          const float4 w = qt4[j4];
+          un2[r][2 * j4].x *= w.x; un2[r][2 * j4].y *= w.y; un2[r][2 * j4 + 1].x *= w.z; un2[r][2 * j4 + 1].y *= w.w;
+          totf += (un2[r][2 * j4].x + un2[r][2 * j4].y) + (un2[r][2 * j4 + 1].x + un2[r][2 * j4 + 1].y);
+        }
+        if (totf == 0.f) {  // sample.py:167: all-zero row -> uniform
+#pragma unroll
+          for (int j = 0; j < C / 2; ++j) un2[r][j] = make_float2(1e-5f, 1e-5f);
+        }
+        best[r] = 0;
+        bv[r] = -INFINITY;
+      }
+      // race: class j uses word j % 4 of Philox call j / 4 (same stream as philox_row); one call per residue at a time so that only
+      // 2 x 4 words are live, winners of each group of 4 found by a 2-level tree, groups folded in order (first maximum wins, as argmax)
+#pragma unroll
+      for (int call = 0; call < C / 4; ++call) {
+#pragma unroll
+        for (int r = 0; r < RJ; ++r) {
+          uint32_t c4[4] = {static_cast<uint32_t>(lr[r]), step * 8u + call, static_cast<uint32_t>(graph), static_cast<uint32_t>(graph >> 32)};
+          philox4x32_10(c4, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+          const float v0 = un2[r][2 * call].x * inv_exp1_fast(c4[0]), v1 = un2[r][2 * call].y * inv_exp1_fast(c4[1]);
+          const float v2 = un2[r][2 * call + 1].x * inv_exp1_fast(c4[2]), v3 = un2[r][2 * call + 1].y * inv_exp1_fast(c4[3]);
+          const bool a = v1 > v0, c = v3 > v2;
+          const float va = a ? v1 : v0, vc = c ? v3 : v2;
+          const int ia = 4 * call + (a ? 1 : 0), ic = 4 * call + (c ? 3 : 2);
+          const bool e = vc > va;
+          const float vg = e ? vc : va;
+          const int ig = e ? ic : ia;
+          if (vg > bv[r]) { bv[r] = vg; best[r] = ig; }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RJ; ++r) {
+        if (!live[r]) continue;
+        int idx = best[r];
+        if (!onehot[r])  // cold: a row of x_t that is not exactly one-hot (never produced by the sampler itself)
+          idx = soft_row_class<true>(logits + nr[r] * C, x_t + nr[r] * C, sQt, sQsb, sQtb, true, nullptr, seed, graph, static_cast<uint32_t>(lr[r]), step);
+        write_onehot(x_s + nr[r] * C, idx);
+        if (idx_out) idx_out[nr[r]] = static_cast<uint8_t>(idx);
+      }
+    }
+    return;
+  }
   for (int l = blockIdx.x * THREADS + threadIdx.x; l < L; l += gridDim.x * THREADS) {
     const size_t n = static_cast<size_t>(b) * L + l;
     float lg[C], xr[C];
@@ -244,86 +366,7 @@ __global__ void __launch_bounds__(THREADS, MINB) reverse_step_kernel(const float
       lg[j4] = a.x; lg[j4 + 1] = a.y; lg[j4 + 2] = a.z; lg[j4 + 3] = a.w;
       xr[j4] = c4.x; xr[j4 + 1] = c4.y; xr[j4 + 2] = c4.z; xr[j4 + 3] = c4.w;
     }
-    if (FAST) {
-      float mxf = lg[0];
-#pragma unroll
-      for (int j = 1; j < C; ++j) mxf = fmaxf(mxf, lg[j]);
-      float pf[C];
-#pragma unroll
-      for (int j = 0; j < C; ++j) pf[j] = ex2_approx((lg[j] - mxf) * 1.44269504088896f);  // unnormalised softmax
-      int hotf = -1, nnzf = 0;
-#pragma unroll
-      for (int j = 0; j < C; ++j)
-        if (xr[j] != 0.f) { ++nnzf; hotf = (xr[j] == 1.0f) ? j : -2; }
-      float unf[C];
-#pragma unroll
-      for (int j = 0; j < C; ++j) unf[j] = 0.f;
-      if (!(nnzf == 1 && hotf >= 0)) {
-        const int idx = soft_row_class<true>(logits + n * C, x_t + n * C, sQt, sQsb, sQtb, true, nullptr, seed, graph_id0 + b, static_cast<uint32_t>(l), step);
-        write_onehot(x_s + n * C, idx);
-        if (idx_out) idx_out[n] = static_cast<uint8_t>(idx);
-        continue;
-      }
-      {
-        const float4* inv4 = reinterpret_cast<const float4*>(sInvT + hotf * kRS);
-        const float4* qt4 = reinterpret_cast<const float4*>(sQtT + hotf * kRS);
-        const float4* qsb4 = reinterpret_cast<const float4*>(sQsbA);
-#pragma unroll
-        for (int i4 = 0; i4 < C / 4; ++i4) {  // a_i = p_i / Qtb[i,x]
-          const float4 w = inv4[i4];
-          pf[4 * i4] *= w.x; pf[4 * i4 + 1] *= w.y; pf[4 * i4 + 2] *= w.z; pf[4 * i4 + 3] *= w.w;
-        }
-        float2 un2[C / 2];
-#pragma unroll
-        for (int j = 0; j < C / 2; ++j) un2[j] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < C; ++i) {  // fully unrolled: pf[i] must stay in registers
-          const float2 pp = make_float2(pf[i], pf[i]);
-#pragma unroll
-          for (int j4 = 0; j4 < C / 4; ++j4) {
-            const float4 w = qsb4[i * (C / 4) + j4];  // same address in every lane: broadcast
-            un2[2 * j4] = ffma2(pp, make_float2(w.x, w.y), un2[2 * j4]);          // FFMA2: 200 instead of 400 FMA issues
-            un2[2 * j4 + 1] = ffma2(pp, make_float2(w.z, w.w), un2[2 * j4 + 1]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < C / 2; ++j) { unf[2 * j] = un2[j].x; unf[2 * j + 1] = un2[j].y; }
-#pragma unroll
-        for (int j4 = 0; j4 < C / 4; ++j4) {
-          const float4 w = qt4[j4];
-          unf[4 * j4] *= w.x; unf[4 * j4 + 1] *= w.y; unf[4 * j4 + 2] *= w.z; unf[4 * j4 + 3] *= w.w;
-        }
-      }
-      float totf = 0.f;
-#pragma unroll
-      for (int j = 0; j < C; ++j) totf += unf[j];
-      if (totf == 0.f) {  // sample.py:167: all-zero row -> uniform
-#pragma unroll
-        for (int j = 0; j < C; ++j) unf[j] = 1e-5f;
-      }
-      // race: class j uses word j % 4 of Philox call j / 4 (same stream as philox_row); one call at a time so that only 4 words
-      // are live, winners of each group of 4 found by a 2-level tree, groups folded in order (first maximum wins, as argmax)
-      int best = 0;
-      float bv = -INFINITY;
-      const uint64_t graph = graph_id0 + b;
-#pragma unroll
-      for (int call = 0; call < C / 4; ++call) {
-        uint32_t c4[4] = {static_cast<uint32_t>(l), step * 8u + call, static_cast<uint32_t>(graph), static_cast<uint32_t>(graph >> 32)};
-        philox4x32_10(c4, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-        const float v0 = unf[4 * call] * inv_exp1_fast(c4[0]), v1 = unf[4 * call + 1] * inv_exp1_fast(c4[1]);
-        const float v2 = unf[4 * call + 2] * inv_exp1_fast(c4[2]), v3 = unf[4 * call + 3] * inv_exp1_fast(c4[3]);
-        const bool a = v1 > v0, c = v3 > v2;
-        const float va = a ? v1 : v0, vc = c ? v3 : v2;
-        const int ia = 4 * call + (a ? 1 : 0), ic = 4 * call + (c ? 3 : 2);
-        const bool e = vc > va;
-        const float vg = e ? vc : va;
-        const int ig = e ? ic : ia;
-        if (vg > bv) { bv = vg; best = ig; }
-      }
-      write_onehot(x_s + n * C, best);
-      if (idx_out) idx_out[n] = static_cast<uint8_t>(best);
-      continue;
-    }
+    if (FAST) continue;  // (the production path is the joint loop above)
     // softmax(logits)
     float mx = lg[0];
 #pragma unroll
