@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "philox.cuh"
 
 namespace seqdiff {
 
@@ -121,12 +122,16 @@ struct StepCursor {
   __device__ __forceinline__ PipeItem item() const { return PipeItem{b, h, qb * kPQ}; }
 };
 
-template <typename T, bool REL>
+// DROP: training-mode forward -- the attention-probability dropout of HF BertSelfAttention (Appendix A: A = dropout(softmax(S))) is
+// applied to P just before it becomes the A operand of P V; the row sums that normalise the output use the un-dropped
+// probabilities.  Mask of element e = ((b * heads + h) * Lq + l) * Lk + r: word e & 3 of Philox4x32-10(counter (e >> 2, site, step),
+// key seed) -- the indexing of attention_train.cu / attention_train_tc.cu, whose backward kernels regenerate the same mask.
+template <typename T, bool REL, bool DROP = false>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO, const float* __restrict__ key_mask, int heads, int Lq,
                       int Lk, int P, uint32_t fmt, int nqb, int n_items, unsigned long long* __restrict__ trace, const int* __restrict__ q_off,
-                      const int* __restrict__ k_off, const int* __restrict__ q_len, int Lk_mask, T* __restrict__ out_raw) {
+                      const int* __restrict__ k_off, const int* __restrict__ q_len, int Lk_mask, T* __restrict__ out_raw, const DropSpec dr) {
   // q_off != NULL: packed (ragged) batch -- graph b's rows start at q_off[b] / k_off[b] of the packed q / k / v matrices, Lq / Lk are
   // the largest lengths of the batch, key_mask keeps its padded pitch Lk_mask, and output rows are stored per thread with a
   // q_len[b] predicate (a bulk tile store would spill into the next graph's rows).
@@ -459,6 +464,26 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         l_run = l_run * corr + rs;
         if (kb == nkb - 1) lsum[((it & 1) * 2 + hf) * kPQ + row] = l_run;
+        if (DROP) {
+          // keys of chunk c: r = 128 kb + 64 c + 32 hf + j; one Philox call serves 4 consecutive keys (Lk % 4 == 0: groups never
+          // straddle a row).  Fully masked chunks hold exact zeros already.
+          const uint32_t thr = static_cast<uint32_t>(static_cast<double>(dr.p) * 4294967296.0);
+          const float sc = 1.0f / (1.0f - dr.p);
+          const size_t e_row = ((static_cast<size_t>(w.b) * heads + w.h) * Lq + w.q0 + row) * Lk + kb * kPK + 32 * hf;
+          auto drop_chunk = [&](auto c_tag) {
+            constexpr int c = decltype(c_tag)::value;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const uint64_t qd = (e_row + 64 * c + 4 * j4) >> 2;
+              uint32_t w4[4] = {static_cast<uint32_t>(qd), static_cast<uint32_t>(qd >> 32), dr.site, dr.step};
+              philox4x32_10(w4, static_cast<uint32_t>(dr.seed), static_cast<uint32_t>(dr.seed >> 32));
+#pragma unroll
+              for (int u = 0; u < 4; ++u) t[c][4 * j4 + u] *= (w4[u] >= thr ? sc : 0.f);
+            }
+          };
+          if (cv0) drop_chunk(std::integral_constant<int, 0>{});
+          if (cv1) drop_chunk(std::integral_constant<int, 1>{});
+        }
 
         // PV of the previous step complete: the P tile is free again and O of this item may be rescaled
         if (g > 0) {
@@ -522,11 +547,11 @@ template <typename T> struct PipeFmt;
 template <> struct PipeFmt<f16> { static constexpr int v = 0; };
 template <> struct PipeFmt<bf16> { static constexpr int v = 1; };
 
-template <typename T, bool REL>
+template <typename T, bool REL, bool DROP = false>
 static int launch_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* E, int P,
-                       const float* mask, T* out, cudaStream_t s, const AttnPack* pk) {
+                       const float* mask, T* out, cudaStream_t s, const AttnPack* pk, const DropSpec dr = DropSpec{0.f, 0u, 0u, 0ull}) {
   using C = PipeCfg<REL>;
-  auto kfn = attention_pipe_kernel<T, REL>;
+  auto kfn = attention_pipe_kernel<T, REL, DROP>;
   static bool configured = false;
   if (!configured) {
     SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kBytes));
@@ -548,8 +573,8 @@ static int launch_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, co
   int grid = n_items < num_sms() ? n_items : num_sms();
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   SD_CUDA(launch_k(kfn, dim3(grid), dim3(kPipeThreads), C::kBytes, s, tq, tk, tv, te, to, mask, heads, Lq, Lk, P, static_cast<uint32_t>(fmt), nqb,
-                   n_items, g_attn_trace, pk ? pk->q_off : nullptr, pk ? pk->k_off : nullptr, pk ? pk->q_len : nullptr, pk ? pk->Lk_mask : Lk, out));
-  SD_LAUNCHED(REL ? "attention_pipe_rel" : "attention_pipe_norel", s);
+                   n_items, g_attn_trace, pk ? pk->q_off : nullptr, pk ? pk->k_off : nullptr, pk ? pk->q_len : nullptr, pk ? pk->Lk_mask : Lk, out, dr));
+  SD_LAUNCHED(DROP ? (REL ? "attention_pipe_rel_drop" : "attention_pipe_norel_drop") : (REL ? "attention_pipe_rel" : "attention_pipe_norel"), s);
   return SEQDIFF_OK;
 }
 
@@ -564,6 +589,21 @@ int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const 
   if (dist_emb) return launch_pipe<T, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, pack);
   return launch_pipe<T, false>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, pack);
 }
+// training-mode forward (attention-probability dropout inside the kernel); needs Lk % 4 == 0
+template <typename T>
+int attention_pipe_dropout(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
+                           const float* key_mask, DropSpec dr, T* out, cudaStream_t s) {
+  SD_CHECK(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "empty attention");
+  SD_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "row strides must be multiples of 8 elements");
+  SD_CHECK((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) % 16 == 0, "q/k/v must be 16B aligned");
+  SD_CHECK(!dist_emb || (Lq <= P && Lk <= P), "sequence longer than max_position_embeddings");
+  SD_CHECK(Lk % 4 == 0, "dropout in the pipelined kernel: Lk must be a multiple of 4 (one Philox call per 4 keys of a row)");
+  SD_CHECK(dr.p > 0.f && dr.p < 1.f, "dropout probability must be in (0, 1)");
+  if (dist_emb) return launch_pipe<T, true, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, nullptr, dr);
+  return launch_pipe<T, false, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, nullptr, dr);
+}
+template int attention_pipe_dropout<bf16>(int, int, int, int, const bf16*, int, const bf16*, int, const bf16*, int, const bf16*, int, const float*, DropSpec, bf16*, cudaStream_t);
+template int attention_pipe_dropout<f16>(int, int, int, int, const f16*, int, const f16*, int, const f16*, int, const f16*, int, const float*, DropSpec, f16*, cudaStream_t);
 template int attention_pipe<bf16>(int, int, int, int, const bf16*, int, const bf16*, int, const bf16*, int, const bf16*, int, const float*, bf16*, cudaStream_t, const AttnPack*);
 template int attention_pipe<f16>(int, int, int, int, const f16*, int, const f16*, int, const f16*, int, const f16*, int, const float*, f16*, cudaStream_t, const AttnPack*);
 

@@ -354,7 +354,8 @@ int seqdiff_op_attention(int precision, int B, int heads, int Lq, int Lk, const 
   SD_GUARD_END
 }
 
-// training attention, operator level: impl 0 = tensor-core kernels (16-bit modes), 1 = fp32 SIMT kernels (every mode)
+// training attention, operator level: impl 0 = wmma tensor-core kernels (16-bit modes), 1 = fp32 SIMT kernels (every mode),
+// 2 (forward only) = the pipelined tcgen05 kernel with in-kernel dropout
 int seqdiff_op_attention_train_fwd(int precision, int impl, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k, int ldk,
                                    const void* v, int ldv, const void* dist_emb, int P, const float* key_mask, float p_drop, uint64_t seed,
                                    uint32_t site, uint32_t step, void* out, void* stream) {
@@ -365,8 +366,12 @@ int seqdiff_op_attention_train_fwd(int precision, int impl, int B, int heads, in
 #define SD_ATF(T, FN) FN<T>(B, heads, Lq, Lk, static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv, \
                            static_cast<const T*>(dist_emb), P, key_mask, dr, static_cast<T*>(out), s)
   if (precision == SEQDIFF_FP32) return SD_ATF(float, attention_train_fwd);
+  SD_CHECK(precision == SEQDIFF_BF16 || precision == SEQDIFF_FP16, "bad precision");
+  if (impl == 2) {  // the pipelined tcgen05 kernel with in-kernel dropout: what the training step runs (p_drop > 0, Lk % 4 == 0)
+    if (precision == SEQDIFF_BF16) return SD_ATF(bf16, attention_pipe_dropout);
+    return SD_ATF(f16, attention_pipe_dropout);
+  }
   if (precision == SEQDIFF_BF16) return impl ? SD_ATF(bf16, attention_train_fwd) : SD_ATF(bf16, attention_train_fwd_tc);
-  SD_CHECK(precision == SEQDIFF_FP16, "bad precision");
   return impl ? SD_ATF(f16, attention_train_fwd) : SD_ATF(f16, attention_train_fwd_tc);
 #undef SD_ATF
   SD_GUARD_END

@@ -124,6 +124,10 @@ extern unsigned long long* g_attn_trace;  // debug timeline buffer of the pipeli
 template <typename T>
 int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
                    int P, const float* key_mask, T* out, cudaStream_t s, const AttnPack* pack = nullptr);
+// the same kernel with the training-mode attention-probability dropout applied to P (masks: DropSpec / Philox, philox.cuh); Lk % 4 == 0
+template <typename T>
+int attention_pipe_dropout(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
+                           int P, const float* key_mask, DropSpec dr, T* out, cudaStream_t s);
 
 
 // ---- reverse_step.cu --------------------------------------------------------------------------------

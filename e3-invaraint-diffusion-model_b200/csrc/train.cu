@@ -275,6 +275,8 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   const DropSpec nodrop{0.f, 0u, 0u, 0ull};
   // SEQDIFF_TRAIN_ATTN=simt: the fp32 SIMT attention kernels in the 16-bit modes as well (A/B reference of the tensor-core kernels)
   static const bool simt_attn = [] { const char* e = getenv("SEQDIFF_TRAIN_ATTN"); return e && std::string(e) == "simt"; }();
+  // SEQDIFF_TRAIN_ATTN=wmma: the wmma forward kernel instead of the pipelined tcgen05 one (A/B reference; the backward is wmma either way)
+  static const bool wmma_fwd = [] { const char* e = getenv("SEQDIFF_TRAIN_ATTN"); return e && std::string(e) == "wmma"; }();
 
   // ---- workspace ----------------------------------------------------------------------------------
   const size_t es = sizeof(T);
@@ -314,6 +316,8 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     const T* e = E ? static_cast<const T*>(wsel<T>(*E)) : nullptr;
     if (dr.p <= 0.f) return attention<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, out, s);
     if constexpr (k16) {
+      // the pipelined tcgen05 kernel of the inference path with the dropout mask applied to P (7x faster than the wmma forward)
+      if (!simt_attn && !wmma_fwd && Lk % 4 == 0) return attention_pipe_dropout<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s);
       if (!simt_attn) return attention_train_fwd_tc<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s);
     }
     return attention_train_fwd<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s);

@@ -210,7 +210,7 @@ def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
     lens = torch.randint(1, Lk + 1, (B,), generator=g)
     mask = (torch.arange(Lk)[None, :] < lens[:, None]).float()
 
-    def run(prec, impl, dt, pdrop):
+    def run(prec, impl, dt, pdrop, fwd_impl=None):
         dev = lambda x: None if x is None else x.to(DEV).to(dt).contiguous()
         dq_, dk_, dv_, do_, dE_ = dev(q), dev(k), dev(v), dev(do), dev(E)
         m_ = mask.to(DEV)
@@ -218,7 +218,7 @@ def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
         gq, gk, gv = torch.empty_like(dq_), torch.empty_like(dk_), torch.empty_like(dv_)
         gE = torch.zeros(2 * P - 1, 64, device=DEV) if rel else None
         st = stream_ptr()
-        assert lib.seqdiff_op_attention_train_fwd(prec, impl, B, heads, Lq, Lk, p(dq_), Hh, p(dk_), Hh, p(dv_), Hh, p(dE_), P, p(m_), pdrop, 9, 3, 1,
+        assert lib.seqdiff_op_attention_train_fwd(prec, impl if fwd_impl is None else fwd_impl, B, heads, Lq, Lk, p(dq_), Hh, p(dk_), Hh, p(dv_), Hh, p(dE_), P, p(m_), pdrop, 9, 3, 1,
                                                   p(out), st) == 0, lib.seqdiff_last_error()
         assert lib.seqdiff_op_attention_train_bwd(prec, impl, B, heads, Lq, Lk, p(dq_), Hh, p(dk_), Hh, p(dv_), Hh, p(dE_), P, p(m_), pdrop, 9, 3, 1,
                                                   p(do_), p(gq), p(gk), p(gv), p(gE), st) == 0, lib.seqdiff_last_error()
@@ -245,6 +245,10 @@ def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
                     assert err < tol, (name, prec, pdrop, err)
             if pdrop > 0:
                 assert float((simt[0] - run(prec, 1, dt, 0.0)[0]).abs().max()) > 1e-3  # the mask really was applied
+                if Lk % 4 == 0:  # the forward the training step runs: pipelined tcgen05 kernel, dropout inside, SAME Philox masks
+                    pipe_out = run(prec, 0, dt, pdrop, fwd_impl=2)[0]
+                    err = float((pipe_out - simt[0]).norm() / simt[0].norm())
+                    assert err < tol, ("out (tcgen05 pipe + dropout)", prec, err)
 
 
 @gpu
