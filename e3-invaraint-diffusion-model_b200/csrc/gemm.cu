@@ -206,6 +206,10 @@ template <> __device__ __forceinline__ void store4<f16>(f16* p, const float4& v)
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
 }
 
+// split-K partial products: one 128-bit vector atomic per 4 outputs (fp32 C only; the other instantiations never reach it)
+template <typename T> __device__ __forceinline__ void add4(T*, const float4&) {}
+template <> __device__ __forceinline__ void add4<float>(float* p, const float4& v) { atomicAdd(reinterpret_cast<float4*>(p), v); }
+
 // TOut: bf16 / f16 (operand for the next GEMM or attention) or float (LayerNorm input); resid is always fp32.
 // RESID: 0 none, 1 fp32 residual tensor, 2 residual = LayerNorm(resid) rebuilt from per-row (mean, rstd) + affine (g, b)
 // TH != void: fused output LayerNorm (LnOut in kernels.h).  The grid is then made of clusters of kLnCl = 4 CTAs; CTA r of a
@@ -223,7 +227,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
                     uint32_t idesc, const float2* __restrict__ ln_stats, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                    unsigned long long* __restrict__ trace, const LnOutArgs lno, int l2_stream) {
+                    unsigned long long* __restrict__ trace, const LnOutArgs lno, int l2_stream, int ksplit) {
+  // ksplit > 1 (fp32 C without residual only): split-K.  A scheduled tile is (output tile, k-range); every split ADDS its partial
+  // product into C with vector atomics (C pre-zeroed by the caller, bias added by split 0).  For the weight-gradient products
+  // dW[N,K] = dY^T X of the training step, whose outputs are a few dozen tiles with a contraction over every token of the batch.
   constexpr bool LNOUT = !std::is_void<TH>::value;
   using Cfg = GemmCfg<BN, CG2, LNOUT>;
   static_assert(!LNOUT || (!CG2 && RESID != 0 && EPI == 0 && std::is_same<TOut, float>::value), "fused LayerNorm: 1-CTA MMA, fp32 C with residual");
@@ -245,8 +252,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_n = N / BN;
   const int num_m = (M + TILE_M - 1) / TILE_M;
-  const int num_tiles = num_m * num_n;
+  const int num_tiles = num_m * num_n * ksplit;
   const int num_kb = (K + kBK - 1) / kBK;
+  auto kb_lo = [&](int ks) { return static_cast<int>(static_cast<long long>(num_kb) * ks / ksplit); };
   const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
   // LNOUT: CTA r of cluster c walks tiles (m = c, c + #clusters, ...; n = r) -- with num_n == kLnCl that is tile c * 4 + r, step 4 * #clusters
   const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -305,9 +313,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int ks = tile % ksplit, mn = tile / ksplit;
+        const int m_blk = mn / num_n, n_blk = mn % num_n;
         const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * kBM;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo(ks), kb_end = kb_lo(ks + 1); kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           TR(1);
           if (CG2) {
@@ -350,7 +359,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue(s) have drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_begin = kb_lo(tile % ksplit), kb_end = kb_lo(tile % ksplit + 1);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           TR(11);
@@ -362,8 +372,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < Cfg::kNSub; ++j) {
               const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + j * Cfg::kBoxRows * kBK * 2 + k * kUmmaK * 2);
-              if (CG2) umma_cg2_e(tmem_d + j * Cfg::kSubN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16_e(tmem_d + j * Cfg::kSubN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (CG2) umma_cg2_e(tmem_d + j * Cfg::kSubN, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+              else umma_bf16_e(tmem_d + j * Cfg::kSubN, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
             }
           }
           // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
@@ -397,7 +407,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     (void)pol_stream;
     constexpr int NCH = BN / 64;  // 32-column chunks per warp and tile
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int ks = tile % ksplit, mn = tile / ksplit;
+      const int m_blk = mn / num_n, n_blk = mn % num_n;
       const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * kBM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN) + half * (BN / 2);
       const int col0 = n_blk * BN + half * (BN / 2) + 4 * lc;  // this lane's 4 columns of chunk 0; chunk ci adds 32 ci
@@ -477,7 +488,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // entry re-filled for the next chunk right after it has been consumed (a second buffer costs 32 registers and spills).
       float4 rres[8], g4[2], h4[2], b4[2];
       auto fetch_small = [&](int ci, int buf) {
-        b4[buf] = __ldg(reinterpret_cast<const float4*>(bias + col0 + 32 * ci));
+        b4[buf] = ks == 0 ? __ldg(reinterpret_cast<const float4*>(bias + col0 + 32 * ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (RESID == 2) {
           g4[buf] = __ldg(reinterpret_cast<const float4*>(ln_g + col0 + 32 * ci));
           h4[buf] = __ldg(reinterpret_cast<const float4*>(ln_b + col0 + 32 * ci));
@@ -553,7 +564,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int row = row_base + 4 * (4 * hh + u) + lr;
-              if (!kGuard || row < M) store4<TOut>(C + static_cast<size_t>(row) * N + col, v[u]);
+              if (!kGuard || row < M) {
+                if (std::is_same<TOut, float>::value && RESID == 0 && ksplit > 1) add4(C + static_cast<size_t>(row) * N + col, v[u]);
+                else store4<TOut>(C + static_cast<size_t>(row) * N + col, v[u]);
+              }
             }
           }
         };
@@ -668,7 +682,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <int BN, int EPI, int RESID, typename TOut, bool CG2>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias, const float* resid, void* C, int M,
-                     int N, int K, uint32_t idesc, cudaStream_t s, const LnResid* ln = nullptr) {
+                     int N, int K, uint32_t idesc, cudaStream_t s, const LnResid* ln = nullptr, int ksplit = 1) {
   using Cfg = GemmCfg<BN, CG2>;
   auto kfn = gemm_tcgen05_kernel<BN, EPI, RESID, TOut, CG2>;
   static bool configured = false;  // per instantiation
@@ -676,7 +690,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = ceil_div(M, CG2 ? 2 * kBM : kBM) * (N / BN);
+  const int tiles = ceil_div(M, CG2 ? 2 * kBM : kBM) * (N / BN) * ksplit;
   const int slots = CG2 ? num_sms() / 2 : num_sms();
   const int grid = (tiles < slots ? tiles : slots) * (CG2 ? 2 : 1);
   // SEQDIFF_GEMM_L2HINT=1: a 16-bit output that cannot stay in L2 anyway (> 64 MB) is stored evict_first and the operands are
@@ -684,8 +698,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   static const int hint_on = [] { const char* e = getenv("SEQDIFF_GEMM_L2HINT"); return e ? atoi(e) : 0; }();
   const int l2_stream = (hint_on && !std::is_same<TOut, float>::value && RESID == 0 && static_cast<double>(M) * N * 2 > 64e6) ? 1 : 0;
   SD_CUDA(launch_kc(CG2 ? 2 : 1, kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, tc, bias, resid, static_cast<TOut*>(C), M, N, K,
-                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, LnOutArgs{}, l2_stream));
-  SD_LAUNCHED(CG2 ? "gemm_tcgen05_2cta" : "gemm_tcgen05", s);
+                    idesc, ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, LnOutArgs{}, l2_stream, ksplit));
+  SD_LAUNCHED(ksplit > 1 ? (CG2 ? "gemm_tcgen05_2cta_splitk" : "gemm_tcgen05_splitk") : (CG2 ? "gemm_tcgen05_2cta" : "gemm_tcgen05"), s);
   return SEQDIFF_OK;
 }
 
@@ -725,7 +739,7 @@ static int launch_tc_ln(const CUtensorMap& ta, const CUtensorMap& tb, const floa
   const int clusters = ceil_div(num_m, waves);
   const LnOutArgs a{lo.g, lo.b, lo.eps, lo.h, lo.stats};
   SD_CUDA(launch_kc(kLnCl, kfn, dim3(clusters * kLnCl), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, ta /*unused store map*/, bias, resid, C, M, N, K, idesc,
-                    ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, a, 0));
+                    ln ? ln->stats : nullptr, ln ? ln->g : nullptr, ln ? ln->b : nullptr, g_attn_trace, a, 0, 1));
   SD_LAUNCHED("gemm_tcgen05_ln", s);
   return SEQDIFF_OK;
 }
@@ -763,10 +777,10 @@ static int pick_cfg(int M, int N, int K) {
 
 template <int BN, bool CG2>
 static int dispatch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias, const float* resid, int epi, void* C,
-                       int out_kind, int M, int N, int K, uint32_t idesc, cudaStream_t s, const LnResid* ln) {
+                       int out_kind, int M, int N, int K, uint32_t idesc, cudaStream_t s, const LnResid* ln, int ksplit = 1) {
   if (resid && ln) return launch_tc<BN, 0, 2, float, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s, ln);
   if (resid) return launch_tc<BN, 0, 1, float, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
-  if (out_kind == 2) return launch_tc<BN, 0, 0, float, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
+  if (out_kind == 2) return launch_tc<BN, 0, 0, float, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s, nullptr, ksplit);
   if (out_kind == 1) {
     if (epi == 0) return launch_tc<BN, 0, 0, bf16, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
     if (epi == 1) return launch_tc<BN, 1, 0, bf16, CG2>(ta, tb, tc, bias, resid, C, M, N, K, idesc, s);
@@ -780,8 +794,11 @@ static int dispatch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 // a_fmt / w_fmt: 0 = fp16, 1 = bf16.  out_kind: 0 = fp16, 1 = bf16, 2 = fp32 (identity epilogue only; implied by resid).
 // force_cfg: 0 = auto, else  bn | (cg2 << 16)  with bn in {128,192,256} (tests / sweeps).
 int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
-            void* C, int out_kind, cudaStream_t s, int force_cfg, const LnResid* ln_resid, const LnOut* ln_out) {
+            void* C, int out_kind, cudaStream_t s, int force_cfg, const LnResid* ln_resid, const LnOut* ln_out, int split_k) {
   SD_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
+  // split_k: 1 = off; n > 1 = n k-ranges per output tile; -1 = as many as fill the GPU (>= 4 k-blocks each).  C must be pre-zeroed.
+  SD_CHECK(split_k >= -1 && split_k != 0, "split_k must be -1 (auto), 1 (off) or the number of k-ranges");
+  SD_CHECK(split_k == 1 || (out_kind == 2 && !resid && !ln_out && epi == 0), "split-K accumulates into an fp32 C without residual");
   SD_CHECK(N % 128 == 0, "tcgen05 GEMM needs N % 128 == 0");
   SD_CHECK(K % 8 == 0, "tcgen05 GEMM needs K % 8 == 0 (16B TMA pitch)");
   SD_CHECK(epi >= 0 && epi <= 2, "unknown GEMM epilogue");
@@ -811,6 +828,8 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
 #undef SD_LN_DISPATCH
   }
   int cfg = force_cfg;
+  int ksplit = split_k;
+  if (ksplit != 1 && !cfg) cfg = pick_cfg(M, N, K);  // the tuner replays launches on the caller's C: not idempotent under accumulation
   if (!cfg) {
     // First eager call of a (shape, epilogue) times every legal tile configuration on the caller's buffers and keeps the
     // fastest (the GEMM is idempotent unless C aliases an input); under stream capture, or with SEQDIFF_GEMM_TUNE=0, the
@@ -896,11 +915,22 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
   CUtensorMap tc = ta;  // store map of 16-bit outputs (unused for fp32 C)
   if (out_kind != 2) SD_TRY(make_tmap_store16(C, out_kind, M, N, &tc));
   const uint32_t idesc = umma_idesc_16(cg2 ? 2 * kBM : kBM, sub_n, static_cast<uint32_t>(a_fmt), static_cast<uint32_t>(w_fmt));
+  if (ksplit != 1) {
+    const int nkb = ceil_div(K, kBK);
+    if (ksplit < 0) {  // auto: one scheduled tile per CTA slot, at least 4 k-blocks per k-range
+      const int tiles = ceil_div(M, cg2 ? 2 * kBM : kBM) * (N / bn);
+      const int slots = cg2 ? num_sms() / 2 : num_sms();
+      ksplit = slots / tiles;
+      if (ksplit > nkb / 4) ksplit = nkb / 4;
+    }
+    if (ksplit > nkb) ksplit = nkb;  // no more k-ranges than k-blocks
+    if (ksplit < 1) ksplit = 1;
+  }
 #define SD_DISPATCH(BN_)                                                                                          \
-  return cg2 ? dispatch_tc<BN_, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)         \
-             : dispatch_tc<BN_, false>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid)
-  if (bn == 512) return dispatch_tc<512, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid);
-  if (bn == 384) return dispatch_tc<384, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid);
+  return cg2 ? dispatch_tc<BN_, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid, ksplit) \
+             : dispatch_tc<BN_, false>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid, ksplit)
+  if (bn == 512) return dispatch_tc<512, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid, ksplit);
+  if (bn == 384) return dispatch_tc<384, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid, ksplit);
   if (bn == 256) { SD_DISPATCH(256); }
   if (bn == 192) { SD_DISPATCH(192); }
   SD_DISPATCH(128);

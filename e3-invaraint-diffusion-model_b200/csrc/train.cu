@@ -43,11 +43,12 @@ struct Arena {
 
 // C[M,N] = A[M,K] B[N,K]^T + bias (+ resid); out_f32: fp32 C (always in fp32 mode)
 template <typename T>
-static int gemm_any(int M, int N, int K, const T* A, const void* Bw, const float* bias, const float* resid, void* C, bool out_f32, cudaStream_t s) {
+static int gemm_any(int M, int N, int K, const T* A, const void* Bw, const float* bias, const float* resid, void* C, bool out_f32, cudaStream_t s,
+                    int split_k = 1) {
   if constexpr (std::is_same<T, float>::value) {
     return gemm_f32(M, N, K, A, static_cast<const float*>(Bw), bias, resid, 0, static_cast<float*>(C), s);
   } else {
-    return gemm_16(M, N, K, A, TFmt<T>::v, Bw, TFmt<T>::v, bias, resid, 0, C, (out_f32 || resid) ? 2 : TFmt<T>::v, s);
+    return gemm_16(M, N, K, A, TFmt<T>::v, Bw, TFmt<T>::v, bias, resid, 0, C, (out_f32 || resid) ? 2 : TFmt<T>::v, s, 0, nullptr, nullptr, split_k);
   }
 }
 template <typename T> static const void* wsel(const Wt& w) {
@@ -497,7 +498,10 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     const int Mp = (M + 7) & ~7;  // contraction length of dW, padded with zero columns to a 16 B pitch
     SD_TRY(transpose_colsum<T>(dY, M, N, trA, gb, s, Mp));
     SD_TRY(transpose_colsum<T>(X, M, K, trB, nullptr, s, Mp));
-    SD_TRY(gemm_any<T>(N, K, Mp, trA, trB, d_zero_bias, nullptr, gW, true, s));
+    // dW [N,K]: a few dozen output tiles with a contraction over every token -> split-K over all SMs, partial products added
+    // into the gradient buffer (zeroed at the start of the backward pass); SEQDIFF_WGRAD_SPLITK=0 keeps one CTA per tile
+    static const bool splitk = [] { const char* e = getenv("SEQDIFF_WGRAD_SPLITK"); return !e || e[0] != '0'; }();
+    SD_TRY(gemm_any<T>(N, K, Mp, trA, trB, d_zero_bias, nullptr, gW, true, s, splitk ? -1 : 1));
     if (dx_kind) SD_TRY(gemm_any<T>(M, K, N, dY, W.t, d_zero_bias, resid, dX, dx_kind == 2, s));
     return SEQDIFF_OK;
   };
