@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libseqdiff_b200.so")
+# SEQDIFF_DEBUG_BOUNDS=1 selects the debug build (device-side asserts + workspace guard bands; build.py with the same variable)
+LIB_PATH = os.path.join(HERE, "libseqdiff_b200_dbg.so" if os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1" else "libseqdiff_b200.so")
 
 FP32, BF16, FP16 = 0, 1, 2
 PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
@@ -34,6 +35,7 @@ PROTOTYPES = {
     "seqdiff_profile_begin": (_i, [_vp]),
     "seqdiff_profile_end": (_i, [C.c_char_p, _i, C.POINTER(C.c_float), C.POINTER(C.c_int), _i]),
     "seqdiff_debug_attn_trace": (_i, [_vp]),
+    "seqdiff_debug_check_guards": (_i, [C.POINTER(_i), C.POINTER(_i), _vp]),
     "seqdiff_model_create": (_i, [C.POINTER(SeqdiffConfig), _i, C.POINTER(_vp)]),
     "seqdiff_model_destroy": (_i, [_vp]),
     "seqdiff_model_set_tensor": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),

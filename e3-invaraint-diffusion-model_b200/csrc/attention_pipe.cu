@@ -361,6 +361,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     bool m_inr = false, m_have = false, m_first = false;
     for (int it = 0; it < my_items; ++it, cur.next_item()) {
       const PipeItem w = cur.item();
+      SD_DEV_ASSERT(w.b >= 0 && w.h >= 0 && w.h < heads && (w.b * heads + w.h) * nqb + w.q0 / kPQ < n_items);  // the division-free cursor stays on the item list
+      SD_DEV_ASSERT(!q_off || (__ldg(q_len + w.b) > 0 && __ldg(q_len + w.b) <= Lq && __ldg(q_off + w.b) >= 0));
       float m_run = -INFINITY, l_run = 0.f;
       for (int kb = 0; kb < nkb; ++kb, ++g) {
         const int ss = g % NS;

@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_train_tc_kernel(int h
                                                                           T* __restrict__ dv, int lddv, float* __restrict__ dE, int n_items) {
   extern __shared__ __align__(128) uint8_t smraw[];
   uint8_t* sm = smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u);
+  // (nvcuda::wmma's load_matrix_sync lowers to state-space-less wmma.load: 17 % of the executed instructions are generic LD on
+  //  shared addresses -- an address-space hint does not change that; explicit ldmatrix would)
   T* sK = reinterpret_cast<T*>(sm + TcSmem::kK);
   T* sV = reinterpret_cast<T*>(sm + TcSmem::kV);
   T* sQ = reinterpret_cast<T*>(sm + TcSmem::kQ);
@@ -210,14 +212,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_train_tc_kernel(int h
       }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      float pd[2][8], dsv[2][8];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int r = 16 * c + i;
         const float ds = live ? p[i] * (dp[i] - dot) * 0.125f : 0.f;
-        sP[l * kLdK + r] = from_f32<T>(p[i] * keep[i]);
-        sdS[l * kLdK + r] = from_f32<T>(ds);
-        if (REL) sdSk[l * kLdW + l + 127 - r] = from_f32<T>(ds);
+        dsv[i >> 3][i & 7] = ds;
+        pd[i >> 3][i & 7] = p[i] * keep[i];
+        if (REL) sdSk[l * kLdW + l + 127 - r] = from_f32<T>(ds);  // skewed copy: row-dependent offset, scalar stores
       }
+      // 16 consecutive keys per thread: two 128-bit stores per tile (scalar 2-byte stores were 23 % of the stall samples, 46 % of
+      // the shared-memory wavefronts excess)
+      store8<T>(sP + l * kLdK + 16 * c, pd[0]);
+      store8<T>(sP + l * kLdK + 16 * c + 8, pd[1]);
+      store8<T>(sdS + l * kLdK + 16 * c, dsv[0]);
+      store8<T>(sdS + l * kLdK + 16 * c + 8, dsv[1]);
       if (REL) {  // window columns outside [l, l + 127] of row l hold no key: zeros (4 of the 32 per thread)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -227,8 +236,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_train_tc_kernel(int h
         }
       }
     } else {
+      float pd[2][8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) sP[l * kLdK + 16 * c + i] = from_f32<T>(p[i] * keep[i]);
+      for (int i = 0; i < 16; ++i) pd[i >> 3][i & 7] = p[i] * keep[i];
+      store8<T>(sP + l * kLdK + 16 * c, pd[0]);
+      store8<T>(sP + l * kLdK + 16 * c + 8, pd[1]);
     }
     __syncthreads();
 

@@ -47,6 +47,20 @@ int seqdiff_debug_attn_trace(void* device_buf) {
   return SEQDIFF_OK;
 }
 
+int seqdiff_debug_check_guards(int* n_bands, int* n_broken, void* stream) {
+  SD_GUARD_BEGIN
+  int nb = 0, nk = 0;
+  SD_TRY(debug_guard_check(static_cast<cudaStream_t>(stream), &nb, &nk));
+  if (n_bands) *n_bands = nb;
+  if (n_broken) *n_broken = nk;
+  if (nk) {
+    set_error(std::to_string(nk) + " of " + std::to_string(nb) + " workspace guard bands were overwritten (out-of-bounds write past a carved buffer)");
+    return SEQDIFF_ERR_STATE;
+  }
+  return SEQDIFF_OK;
+  SD_GUARD_END
+}
+
 int seqdiff_model_create(const seqdiff_config_t* cfg, int device, seqdiff_model_t** out) {
   SD_GUARD_BEGIN
   SD_CHECK(cfg != nullptr && out != nullptr, "null argument");

@@ -474,6 +474,30 @@ __host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, uint32_t a_fm
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---- SEQDIFF_DEBUG_BOUNDS build (python build.py with SEQDIFF_DEBUG_BOUNDS=1 -> libseqdiff_b200_dbg.so) --------------------------
+// The GPU pool does not allow compute-sanitizer, so the debug build carries its own checks:
+//  * SD_DEV_ASSERT(cond): device-side assert (printf + trap) on indices taken from device-resident maps and counters;
+//  * guard bands: every buffer carved out of a workspace (Bump in model.cu, Arena in train.cu) is followed by 256 B filled with a
+//    pattern by a kernel on the launching stream; seqdiff_debug_check_guards() verifies all of them -- an out-of-bounds write past
+//    the end of any activation / tape buffer shows up as a broken band.  In the product build all of this compiles to nothing.
+#ifdef SEQDIFF_DEBUG_BOUNDS
+#define SD_DEV_ASSERT(cond)                                                                                              \
+  do {                                                                                                                   \
+    if (!(cond)) {                                                                                                       \
+      printf("SD_DEV_ASSERT failed: %s at %s:%d (block %d,%d thread %d)\n", #cond, __FILE__, __LINE__, blockIdx.x, blockIdx.y, threadIdx.x); \
+      __trap();                                                                                                          \
+    }                                                                                                                    \
+  } while (0)
+constexpr size_t kGuardBytes = 256;
+#else
+#define SD_DEV_ASSERT(cond) ((void)0)
+constexpr size_t kGuardBytes = 0;
+#endif
+// (debug build) registers + fills the guard band at `p`; `owner` groups the bands of one workspace carve (re-carving replaces them)
+int debug_guard_begin(const void* owner);
+int debug_guard_add(const void* owner, void* p, cudaStream_t s);
+int debug_guard_check(cudaStream_t s, int* n_bands, int* n_broken);
+
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
 // Every kernel of the path is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may become resident
 // while its predecessor drains, runs its prologue (smem carve-up, mbarrier init, TMEM alloc, descriptor prefetch), and then

@@ -410,6 +410,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ks = tile % ksplit, mn = tile / ksplit;
       const int m_blk = mn / num_n, n_blk = mn % num_n;
       const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * kBM + q * 32;
+      SD_DEV_ASSERT(m_blk < num_m && n_blk * BN + half * (BN / 2) + (BN / 2) <= N && ks < ksplit);  // the tile decode stays inside C
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN) + half * (BN / 2);
       const int col0 = n_blk * BN + half * (BN / 2) + 4 * lc;  // this lane's 4 columns of chunk 0; chunk ci adds 32 ci
       const bool full = row_base + 32 <= M;                    // warp-uniform: no row of this warp's slab is out of range

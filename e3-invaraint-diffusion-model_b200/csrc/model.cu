@@ -10,6 +10,9 @@
 // fp32 (parity mode); LayerNorm statistics, softmax, biases and logits are always fp32.
 #include "model.cuh"
 
+#include <mutex>
+#include <vector>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -92,6 +95,67 @@ bool pdl_enabled() {
   static const int env = [] { const char* e = getenv("SEQDIFF_PDL"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
   return env >= 0 ? env == 1 : g_pdl_scope > 0;
 }
+
+// ---- debug-build guard bands (see common.cuh) -------------------------------------------------------------------------------
+#ifdef SEQDIFF_DEBUG_BOUNDS
+namespace {
+struct GuardRec { const void* owner; void* p; };
+std::vector<GuardRec> g_guards;
+std::mutex g_guard_mu;
+constexpr uint32_t kGuardWord = 0xA5C3F00Du;
+__global__ void guard_fill_kernel(uint32_t* p) { p[threadIdx.x] = kGuardWord; }
+__global__ void guard_check_kernel(uint32_t* const* bands, int n, int* broken) {
+  const int i = blockIdx.x;
+  if (i < n && bands[i][threadIdx.x] != kGuardWord) atomicAdd(broken, 1);
+}
+}  // namespace
+int debug_guard_begin(const void* owner) {
+  std::lock_guard<std::mutex> g(g_guard_mu);
+  size_t w = 0;
+  for (size_t i = 0; i < g_guards.size(); ++i)
+    if (g_guards[i].owner != owner) g_guards[w++] = g_guards[i];
+  g_guards.resize(w);
+  return SEQDIFF_OK;
+}
+int debug_guard_add(const void* owner, void* p, cudaStream_t s) {
+  {
+    std::lock_guard<std::mutex> g(g_guard_mu);
+    g_guards.push_back({owner, p});
+  }
+  guard_fill_kernel<<<1, 64, 0, s>>>(static_cast<uint32_t*>(p));  // capturable: re-armed by every replay of a captured step
+  SD_CUDA(cudaGetLastError());
+  return SEQDIFF_OK;
+}
+int debug_guard_check(cudaStream_t s, int* n_bands, int* n_broken) {
+  std::vector<uint32_t*> h;
+  {
+    std::lock_guard<std::mutex> g(g_guard_mu);
+    for (auto& r : g_guards) h.push_back(static_cast<uint32_t*>(r.p));
+  }
+  *n_bands = static_cast<int>(h.size());
+  *n_broken = 0;
+  if (h.empty()) return SEQDIFF_OK;
+  SD_CUDA(cudaDeviceSynchronize());  // every stream: the bands belong to workspaces used on private streams as well
+  if (const char* e = getenv("SEQDIFF_DEBUG_BREAK_GUARD"); e && e[0] == '1') SD_CUDA(cudaMemset(h[h.size() / 2], 0, 4));  // negative control of the check itself
+  uint32_t** d = nullptr;
+  int* cnt = nullptr;
+  SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), h.size() * sizeof(uint32_t*)));
+  SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&cnt), sizeof(int)));
+  SD_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+  SD_CUDA(cudaMemset(cnt, 0, sizeof(int)));
+  guard_check_kernel<<<static_cast<unsigned>(h.size()), 64, 0, s>>>(d, static_cast<int>(h.size()), cnt);
+  SD_CUDA(cudaGetLastError());
+  SD_CUDA(cudaStreamSynchronize(s));
+  SD_CUDA(cudaMemcpy(n_broken, cnt, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  cudaFree(cnt);
+  return SEQDIFF_OK;
+}
+#else
+int debug_guard_begin(const void*) { return SEQDIFF_OK; }
+int debug_guard_add(const void*, void*, cudaStream_t) { return SEQDIFF_OK; }
+int debug_guard_check(cudaStream_t, int* n_bands, int* n_broken) { *n_bands = 0; *n_broken = 0; return SEQDIFF_OK; }
+#endif
 
 int num_sms() {
   static int n = 0;
@@ -176,11 +240,11 @@ Model::~Model() {
   if (ev_out) cudaEventDestroy(ev_out);
   for (void* p : allocs) cudaFree(p);
   for (void* p : packed_allocs) cudaFree(p);
-  if (ws) cudaFree(ws);
-  if (samp_in) cudaFree(samp_in);
+  if (ws) { debug_guard_begin(ws); cudaFree(ws); }
+  if (samp_in) { debug_guard_begin(samp_in); cudaFree(samp_in); }
   if (d_tables) cudaFree(d_tables);
   if (d_pack) cudaFree(d_pack);
-  if (tws) cudaFree(tws);
+  if (tws) { debug_guard_begin(tws); cudaFree(tws); }
 }
 
 void* Model::dalloc(size_t bytes) {
@@ -514,13 +578,14 @@ size_t Model::workspace_need(int precision, int B, int Ll, int Lr) const {
   n += align256(Ml * H * 4) + align256(Ml * 3 * 8);   // third pre-LN buffer, LayerNorm row statistics
   n += align256(Ml * I * es);                         // ffn
   (void)dual;
-  return n + 8192;
+  return n + 8192 + 64 * kGuardBytes;  // (debug build: one guard band per carved buffer)
 }
 
 int Model::ensure_workspace(size_t bytes) {
   if (bytes <= ws_bytes) return SEQDIFF_OK;
   if (ws) {
     SD_CUDA(cudaDeviceSynchronize());
+    debug_guard_begin(ws);  // (debug build) the bands of the old workspace go with it
     SD_CUDA(cudaFree(ws));
     ws = nullptr;
     ws_bytes = 0;
@@ -532,9 +597,16 @@ int Model::ensure_workspace(size_t bytes) {
 
 struct Bump {
   uint8_t* p;
+  cudaStream_t gs;    // debug build: stream the guard bands are filled on
+  const void* owner;  // debug build: the carve these bands belong to (a new carve of the same workspace replaces them)
+  explicit Bump(uint8_t* base, cudaStream_t s = nullptr) : p(base), gs(s), owner(base) { debug_guard_begin(owner); }
   template <typename T> T* take(size_t n) {
     T* r = reinterpret_cast<T*>(p);
     p += align256(n * sizeof(T));
+    if (kGuardBytes) {
+      debug_guard_add(owner, p, gs);
+      p += kGuardBytes;
+    }
     return r;
   }
 };
@@ -617,7 +689,7 @@ int Model::forward_t(int wfmt, int B, int Ll, int Lr, const float* timestep, con
   const int Ml = pk ? pk->Ml : B * Ll, Mr = pk ? pk->Mr : B * Lr, Mt = Ml + Mr;
   const int Mlp = B * Ll, Mrp = B * Lr;  // padded row counts (input tensors, key masks)
   const size_t MtH = static_cast<size_t>(Mt) * H, MlH = static_cast<size_t>(Ml) * H;
-  Bump bp{ws};
+  Bump bp(ws, s);
   float* te = bp.take<float>(static_cast<size_t>(B) * H);
   T* teT = k16 ? bp.take<T>(static_cast<size_t>(B) * H) : reinterpret_cast<T*>(te);
   float* maskcat = bp.take<float>(static_cast<size_t>(Mlp) + Mrp);
@@ -902,10 +974,10 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
   // persistent inputs: x_cur | logits | lig_angle | lig_mask | rec_seq | rec_angle | rec_mask
   const size_t need_in = align256(Nl * 20 * 4) * 2 + align256(Nl * 8 * 4) + align256(Nl * 4) + align256(Nr * 20 * 4) +
                          align256(Nr * 8 * 4) + align256(Nr * 4);
-  if (need_in > samp_in_bytes) {
-    if (samp_in) { SD_CUDA(cudaDeviceSynchronize()); SD_CUDA(cudaFree(samp_in)); samp_in = nullptr; samp_in_bytes = 0; }
-    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&samp_in), need_in));
-    samp_in_bytes = need_in;
+  if (need_in + 16 * kGuardBytes > samp_in_bytes) {
+    if (samp_in) { SD_CUDA(cudaDeviceSynchronize()); debug_guard_begin(samp_in); SD_CUDA(cudaFree(samp_in)); samp_in = nullptr; samp_in_bytes = 0; }
+    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&samp_in), need_in + 16 * kGuardBytes));
+    samp_in_bytes = need_in + 16 * kGuardBytes;
   }
   const size_t tab_floats = static_cast<size_t>(T) * 3 * 400;
   if (tab_floats > tables_cap) {
@@ -914,7 +986,7 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
     tables_cap = tab_floats;
   }
   SD_TRY(ensure_workspace(workspace_need(precision, B, Ll, Lr)));
-  Bump bp{samp_in};
+  Bump bp(samp_in, s);
   float* x_cur = bp.take<float>(Nl * 20);
   float* logits = bp.take<float>(Nl * 20);
   float* c_lang = bp.take<float>(Nl * 8);
@@ -1073,7 +1145,7 @@ size_t Model::struct_workspace_need(int precision, int B, int Ll, int Lr) const 
   n += 5 * align256(Mx * H * es);                      // c, u, ctx, cq, y
   n += align256(Mx * 6 * H * es) + align256(Mx * 3 * H * es) + align256(Mx * 4 * H * es);  // mod, qkv, m1
   n += align256(Mx * I * es);                          // ffn
-  return n + 8192;
+  return n + 8192 + 64 * kGuardBytes;  // (debug build: one guard band per carved buffer)
 }
 
 template <typename T>
@@ -1085,7 +1157,7 @@ int Model::struct_forward_t(int wfmt, int B, int Ll, int Lr, const float* timest
   const float eps = cfg.layer_norm_eps;
   const int Ml = B * Ll, Mr = B * Lr, Mx = Ml > Mr ? Ml : Mr;
   const size_t MxH = static_cast<size_t>(Mx) * H;
-  Bump bp{ws};
+  Bump bp(ws, s);
   T* kv_all = bp.take<T>(static_cast<size_t>(Mr) * NL * 2 * H);  // first: same address for every (B, Ll, Lr) of a loop
   float* te = bp.take<float>(static_cast<size_t>(B) * H);
   T* teT = k16 ? bp.take<T>(static_cast<size_t>(B) * H) : reinterpret_cast<T*>(te);
@@ -1215,10 +1287,10 @@ int Model::struct_sample(int precision, int B, int Ll, int Lr, int T, const floa
   const size_t Nl = static_cast<size_t>(B) * Ll, Nr = static_cast<size_t>(B) * Lr;
   // persistent inputs: x_cur | model_out | lig_mask | rec_seq | rec_angle | rec_mask
   const size_t need_in = align256(Nl * F * 4) * 2 + align256(Nl * 4) + align256(Nr * 20 * 4) + align256(Nr * F * 4) + align256(Nr * 4);
-  if (need_in > samp_in_bytes) {
-    if (samp_in) { SD_CUDA(cudaDeviceSynchronize()); SD_CUDA(cudaFree(samp_in)); samp_in = nullptr; samp_in_bytes = 0; }
-    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&samp_in), need_in));
-    samp_in_bytes = need_in;
+  if (need_in + 16 * kGuardBytes > samp_in_bytes) {
+    if (samp_in) { SD_CUDA(cudaDeviceSynchronize()); debug_guard_begin(samp_in); SD_CUDA(cudaFree(samp_in)); samp_in = nullptr; samp_in_bytes = 0; }
+    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&samp_in), need_in + 16 * kGuardBytes));
+    samp_in_bytes = need_in + 16 * kGuardBytes;
   }
   const size_t tab_floats = static_cast<size_t>(T) * 4;
   if (tab_floats > tables_cap) {
@@ -1227,7 +1299,7 @@ int Model::struct_sample(int precision, int B, int Ll, int Lr, int T, const floa
     tables_cap = tab_floats;
   }
   SD_TRY(ensure_workspace(struct_workspace_need(precision, B, Ll, Lr)));
-  Bump bp{samp_in};
+  Bump bp(samp_in, s);
   float* x_cur = bp.take<float>(Nl * F);
   float* mout = bp.take<float>(Nl * F);
   float* c_lmask = bp.take<float>(Nl);

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(THREADS, MINB) reverse_step_kernel(const float
     }
     __syncthreads();
     const int sidx = s_sidx;
+    SD_DEV_ASSERT(sidx >= 0);  // the loop counter never runs past the last step
     if (sidx == 0) return;  // last step: caller keeps the raw logits (sample.py:147-148)
     step = static_cast<uint32_t>(sidx);
     q_tables += static_cast<size_t>(sidx) * (3 * C * C);

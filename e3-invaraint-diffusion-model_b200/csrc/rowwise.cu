@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_modulate_kernel(const float* _
     }
   }
   row_stats<VPL>(v, H, 1e-5f, mean, rstd);  // SELayer.norm1/norm2: elementwise_affine=False, default eps
+  SD_DEV_ASSERT(!row_graph || __ldg(row_graph + row) >= 0);
   const T* mrow = mod + static_cast<size_t>(row_graph ? __ldg(row_graph + row) : row / mod_div) * (6 * H);
   const float* xrow = x + static_cast<size_t>(row) * H;
 #pragma unroll

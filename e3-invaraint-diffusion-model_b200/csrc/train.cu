@@ -32,10 +32,17 @@ static size_t al256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
 struct Arena {
   uint8_t* p;
   uint8_t* end;
+  cudaStream_t gs;    // debug build: stream the guard bands are filled on (common.cuh: SEQDIFF_DEBUG_BOUNDS)
+  const void* owner;
   bool ok = true;
+  Arena(uint8_t* base, uint8_t* e, cudaStream_t s) : p(base), end(e), gs(s), owner(base) { debug_guard_begin(owner); }
   template <typename T> T* take(size_t n) {
     T* r = reinterpret_cast<T*>(p);
     p += al256(n * sizeof(T));
+    if (kGuardBytes && p + kGuardBytes <= end) {
+      debug_guard_add(owner, p, gs);
+      p += kGuardBytes;
+    }
     if (p > end) ok = false;
     return r;
   }
@@ -295,11 +302,11 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     need = 2 * need + (64u << 20);  // the tape is carved out while kernels are already being launched: keep a wide safety margin
   }
   if (need > tws_bytes) {
-    if (tws) { SD_CUDA(cudaDeviceSynchronize()); SD_CUDA(cudaFree(tws)); tws = nullptr; tws_bytes = 0; }
+    if (tws) { SD_CUDA(cudaDeviceSynchronize()); debug_guard_begin(tws); SD_CUDA(cudaFree(tws)); tws = nullptr; tws_bytes = 0; }
     SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&tws), need));
     tws_bytes = need;
   }
-  Arena ar{tws, tws + tws_bytes};
+  Arena ar(tws, tws + tws_bytes, s);
 
   // ---- small helpers ------------------------------------------------------------------------------
   // y (T) = x W^T + b

@@ -79,6 +79,10 @@ SEQDIFF_API int seqdiff_profile_end(char* tags, int tag_stride, float* ms, int* 
 /* debug: device buffer of 4 x 1024 uint64 that CTA 0 of the pipelined attention kernel fills with its role timelines
  * (slot 0 of each role = event count, then (SM clock << 8 | event id)); NULL (default) switches tracing off. */
 SEQDIFF_API int seqdiff_debug_attn_trace(void* device_buf);
+/* debug build only (SEQDIFF_DEBUG_BOUNDS=1 python build.py -> libseqdiff_b200_dbg.so; the GPU pool does not allow compute-sanitizer):
+ * every buffer carved out of a forward / sampling / training workspace is followed by a 256-byte guard band; this call waits for the
+ * device and verifies all bands (error = some kernel wrote past the end of a buffer).  The product build has no bands: 0 / 0, OK. */
+SEQDIFF_API int seqdiff_debug_check_guards(int* n_bands, int* n_broken, void* stream);
 
 /* ---- model handle: replaces ConditionalBertForDiffusionBase.__init__ + load_state_dict ---------
  * sequence_model/model.py:156-181, sample.py:106.  Tensor names are the reference state_dict keys
