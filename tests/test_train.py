@@ -90,7 +90,10 @@ def test_gradient_all_reduce_world2_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 500
+    import socket
+    with socket.socket() as sk:  # a port the OS reports free (a fixed offset from the pid collided with other jobs now and then)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
