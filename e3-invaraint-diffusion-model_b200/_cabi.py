@@ -50,6 +50,7 @@ PROTOTYPES = {
     "seqdiff_loss_terms": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "seqdiff_train_param_count": (_i64, [_vp]),
     "seqdiff_train_param_table": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i64), _i]),
+    "seqdiff_op_gemm_tn": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "seqdiff_train_grad_buckets": (_i, [_vp, C.POINTER(_i64), _i]),
     "seqdiff_train_set_bucket_events": (_i, [_vp, C.POINTER(_vp), _i]),
     "seqdiff_train_step": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _u64, _u32, _vp, _vp, _vp, _vp]),

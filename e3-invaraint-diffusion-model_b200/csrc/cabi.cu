@@ -409,6 +409,20 @@ int seqdiff_op_attention_train_bwd(int precision, int impl, int B, int heads, in
   SD_GUARD_END
 }
 
+int seqdiff_op_gemm_tn(int precision, int M, int N, int K, const void* At, const void* Bt, float* C, int split_k, void* stream) {
+  SD_GUARD_BEGIN
+  SD_CHECK(At && Bt && C, "null argument");
+  SD_CHECK(precision == SEQDIFF_BF16 || precision == SEQDIFF_FP16, "the TN product exists for the 16-bit modes");
+  static float* zero_bias = nullptr;  // (test entry point: one process-lifetime buffer)
+  if (!zero_bias) {
+    SD_CUDA(cudaMalloc(reinterpret_cast<void**>(&zero_bias), 16384 * sizeof(float)));
+    SD_CUDA(cudaMemset(zero_bias, 0, 16384 * sizeof(float)));
+  }
+  SD_CHECK(N <= 16384, "N too large for the test entry point");
+  return gemm_16_tn(M, N, K, At, Bt, precision == SEQDIFF_BF16 ? 1 : 0, zero_bias, C, static_cast<cudaStream_t>(stream), split_k);
+  SD_GUARD_END
+}
+
 int seqdiff_op_layernorm(int precision, int M, int H, const float* in, const float* ln_w, const float* ln_b, float eps, float* out32, void* out16,
                          float* stats, void* stream) {
   SD_GUARD_BEGIN

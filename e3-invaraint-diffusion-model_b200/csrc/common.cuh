@@ -468,6 +468,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
   return d;
 }
+// MN-major operand, SWIZZLE_128B: the tile is stored as [k][mn] with 64 mn-elements (128 B) per k-row -- what a TMA box of
+// 64 rows x 64 columns of a row-major [k, mn] matrix leaves in shared memory.  Canonical layout (cute: ((8,n),(8,k)):((1,LBO),(8,SBO))
+// in 16 B units): 8 k-rows of 128 B form a 1 KB swizzle group, SBO = stride between groups along k (1024 B), LBO = stride between
+// 64-element blocks along mn (`mn_block_stride`, the size of one TMA box).  A k-step of 16 advances the start address by 2048 B.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t mn_block_stride) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((mn_block_stride >> 4) & 0x3FFFu) << 16;  // LBO
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                           // SBO
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t kUmmaAMnMajor = 1u << 15, kUmmaBMnMajor = 1u << 16;  // instruction-descriptor bits: operand is MN-major
 // instruction descriptor, kind::f16: {f16|bf16} x {f16|bf16} -> f32, both operands K-major.
 // a_fmt / b_fmt: 0 = F16, 1 = BF16 (cute::UMMA::F16F32Format)
 __host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, uint32_t a_fmt, uint32_t b_fmt) {

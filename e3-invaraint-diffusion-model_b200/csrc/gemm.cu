@@ -222,7 +222,10 @@ struct LnOutArgs {
   void* h;
   float2* stats;
 };
-template <int BN, int EPI, int RESID, typename TOut, bool CG2, typename TH = void>
+// TN: C[M,N] = At^T Bt with At [K, M] and Bt [K, N] row-major (both operands MN-major for the MMA): the weight-gradient product
+// dW = dY^T X straight from the row-major activations / gradients -- no transposed copies.  tmA / tmB then carry boxes of
+// 64 k-rows x 64 columns; K (the token count) may be ragged, rows past it are zero-filled by TMA.
+template <int BN, int EPI, int RESID, typename TOut, bool CG2, typename TH = void, bool TN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const float* __restrict__ bias, const float* __restrict__ resid, TOut* __restrict__ C, int M, int N, int K,
@@ -234,6 +237,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr bool LNOUT = !std::is_void<TH>::value;
   using Cfg = GemmCfg<BN, CG2, LNOUT>;
   static_assert(!LNOUT || (!CG2 && RESID != 0 && EPI == 0 && std::is_same<TOut, float>::value), "fused LayerNorm: 1-CTA MMA, fp32 C with residual");
+  static_assert(!TN || (!CG2 && !LNOUT && RESID == 0 && EPI == 0 && std::is_same<TOut, float>::value && BN % 64 == 0 && BN <= 256), "TN: 1-CTA MMA, fp32 C");
   constexpr int STAGES = Cfg::kStages;
   constexpr int TILE_M = CG2 ? 2 * kBM : kBM;  // rows per scheduled tile (per CTA pair / per CTA)
   extern __shared__ uint8_t smem_raw[];
@@ -334,6 +338,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tma_load_2d_cg2_e(sB + stage * Cfg::kBBytes + j * Cfg::kBoxRows * kBK * 2, &tmB, bar, kb * kBK,
                                   n_blk * BN + j * Cfg::kSubN + static_cast<int>(cta_rank) * Cfg::kBoxRows);
             }
+          } else if (TN) {
+            mbar_expect_tx_e(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+            for (int j = 0; j < kBM / 64; ++j)  // A^T: 64-column blocks of the M (= output row) range, 64 k-rows each
+              tma_load_2d_e(sA + stage * Cfg::kABytes + j * 8192, &tmA, &full_bar[stage], a_row + 64 * j, kb * kBK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d_e(sB + stage * Cfg::kBBytes + j * 8192, &tmB, &full_bar[stage], n_blk * BN + 64 * j, kb * kBK);
           } else {
             mbar_expect_tx_e(&full_bar[stage], Cfg::kStageBytes);
             if (l2_stream) {
@@ -368,10 +380,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t adesc = TN ? umma_desc_mnmajor_sw128(a_addr + k * 2048, 8192) : umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
 #pragma unroll
             for (int j = 0; j < Cfg::kNSub; ++j) {
-              const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + j * Cfg::kBoxRows * kBK * 2 + k * kUmmaK * 2);
+              const uint64_t bdesc = TN ? umma_desc_mnmajor_sw128(b_addr + k * 2048, 8192)
+                                        : umma_desc_kmajor_sw128(b_addr + j * Cfg::kBoxRows * kBK * 2 + k * kUmmaK * 2);
               if (CG2) umma_cg2_e(tmem_d + j * Cfg::kSubN, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
               else umma_bf16_e(tmem_d + j * Cfg::kSubN, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
             }
@@ -749,6 +762,46 @@ static int dispatch_tc_ln(const CUtensorMap& ta, const CUtensorMap& tb, const fl
                           uint32_t idesc, cudaStream_t s, const LnResid* ln, const LnOut& lo) {
   if (ln) return launch_tc_ln<BN, 2, TH>(ta, tb, bias, resid, C, M, N, K, idesc, s, ln, lo);
   return launch_tc_ln<BN, 1, TH>(ta, tb, bias, resid, C, M, N, K, idesc, s, ln, lo);
+}
+
+// C[M,N] (+)= At^T Bt: At [K, M], Bt [K, N] row-major 16-bit (fmt 0 = fp16, 1 = bf16), fp32 C.  split_k as in gemm_16 (C pre-zeroed when != 1).
+template <int BN>
+static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, float* C, int M, int N, int K, uint32_t idesc, int ksplit, cudaStream_t s) {
+  using Cfg = GemmCfg<BN, false>;
+  auto kfn = gemm_tcgen05_kernel<BN, 0, 0, float, false, void, true>;
+  static bool configured = false;
+  if (!configured) {
+    SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ceil_div(M, kBM) * (N / BN) * ksplit;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  SD_CUDA(launch_kc(1, kfn, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, ta, bias, static_cast<const float*>(nullptr), C, M, N, K, idesc,
+                    static_cast<const float2*>(nullptr), static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), g_attn_trace, LnOutArgs{}, 0, ksplit));
+  SD_LAUNCHED(ksplit > 1 ? "gemm_tcgen05_tn_splitk" : "gemm_tcgen05_tn", s);
+  return SEQDIFF_OK;
+}
+int gemm_16_tn(int M, int N, int K, const void* At, const void* Bt, int fmt, const float* bias, float* C, cudaStream_t s, int split_k) {
+  SD_CHECK(M > 0 && N > 0 && K > 0, "empty GEMM");
+  SD_CHECK(M % 8 == 0 && N % 128 == 0, "TN GEMM: M % 8 == 0 (16B TMA pitch) and N % 128 == 0");
+  SD_CHECK((fmt | 1) == 1 && bias != nullptr, "bad operand format / bias required");
+  SD_CHECK(split_k >= -1 && split_k != 0, "split_k must be -1 (auto), 1 (off) or the number of k-ranges");
+  const int bn = N % 256 == 0 ? 256 : 128;
+  int ksplit = split_k;
+  const int nkb = ceil_div(K, kBK);
+  if (ksplit < 0) {
+    const int tiles = ceil_div(M, kBM) * (N / bn);
+    ksplit = num_sms() / tiles;
+    if (ksplit > nkb / 4) ksplit = nkb / 4;
+  }
+  if (ksplit > nkb) ksplit = nkb;
+  if (ksplit < 1) ksplit = 1;
+  CUtensorMap ta, tb;
+  SD_TRY(make_tmap(At, fmt, K, M, 64, &ta));  // boxes of 64 k-rows x 64 columns
+  SD_TRY(make_tmap(Bt, fmt, K, N, 64, &tb));
+  const uint32_t idesc = umma_idesc_16(kBM, bn, static_cast<uint32_t>(fmt), static_cast<uint32_t>(fmt)) | kUmmaAMnMajor | kUmmaBMnMajor;
+  if (bn == 256) return launch_tn<256>(ta, tb, bias, C, M, N, K, idesc, ksplit, s);
+  return launch_tn<128>(ta, tb, bias, C, M, N, K, idesc, ksplit, s);
 }
 
 // tile choice, from measurements on B200 (scripts/gemm_sweep.py, profiles/gemm_sweep_r01.log):

@@ -30,6 +30,9 @@ struct LnOut {
 int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_fmt, const float* bias, const float* resid, int epi,
             void* C, int out_kind, cudaStream_t s, int force_bn = 0, const LnResid* ln_resid = nullptr, const LnOut* ln_out = nullptr,
             int split_k = 1);  // split_k: 1 off | n k-ranges per tile | -1 auto; partial products are ADDED into a pre-zeroed fp32 C
+// C[M,N] (+)= At^T Bt + bias: At [K, M], Bt [K, N] row-major 16-bit (both MN-major for the MMA: no transposed copies); fp32 C.
+// The weight-gradient product dW[N_out, N_in] = dY^T X of the training step (At = dY [tokens, N_out], Bt = X [tokens, N_in]).
+int gemm_16_tn(int M, int N, int K, const void* At, const void* Bt, int fmt, const float* bias, float* C, cudaStream_t s, int split_k = 1);
 int gemm_f32(int M, int N, int K, const float* A, const float* W, const float* bias, const float* resid, int epi, float* C,
              cudaStream_t s);
 
@@ -168,6 +171,7 @@ int gauss_step(const float* coef, int T, int B, int per_graph, const float* x_t,
 // out[c][r] = in[r][c] for row-major [rows, cols]; colsum (optional, fp32 [cols]) += column sums (bias gradients); out may be NULL.
 // pitch (default rows): row pitch of `out` in elements, rows <= pitch < rows + 64; columns rows..pitch-1 are written as zeros (the
 // contraction dimension of the weight-gradient GEMM must be a multiple of 8 elements for TMA)
+template <typename T> int colsum_add(const T* in, int rows, int cols, float* colsum, cudaStream_t s);  // colsum[c] += sum_r in[r, c]
 template <typename T> int transpose_colsum(const T* in, int rows, int cols, T* out, float* colsum, cudaStream_t s, int pitch = 0);
 template <typename T> int transpose_cast(const float* in, int rows, int cols, T* out, cudaStream_t s);  // fp32 [r,c] -> T [c,r]
 // a = dropout(act(z)), kind 1 = erf-GELU, 2 = SiLU;  dz = da * keep * act'(z)

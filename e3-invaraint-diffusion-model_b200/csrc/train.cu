@@ -502,6 +502,18 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   // backward of y = x W^T + b.  dY: T [M,N]; X: T [M,K].  dx_kind 0: none; 1: T [M,K]; 2: fp32 [M,K] (+ resid)
   auto linear_bwd = [&](int M, int N, int K, const T* dY, const T* X, const Wt& W, float* gW, float* gb, int dx_kind, void* dX,
                         const float* resid) -> int {
+    // 16-bit modes: dW = dY^T X straight from the row-major tensors (both operands MN-major for the MMA, gemm_16_tn), db by a column-sum
+    // kernel -- the two 16-bit transposes per Linear (11 % of the step) are gone.  SEQDIFF_WGRAD_TN=0 restores the transposed form.
+    static const bool wgrad_tn = [] { const char* e = getenv("SEQDIFF_WGRAD_TN"); return !e || e[0] != '0'; }();
+    if constexpr (k16) {
+      if (wgrad_tn && N % 8 == 0 && K % 128 == 0) {
+        static const bool splitk_tn = [] { const char* e = getenv("SEQDIFF_WGRAD_SPLITK"); return !e || e[0] != '0'; }();
+        SD_TRY(colsum_add<T>(dY, M, N, gb, s));
+        SD_TRY(gemm_16_tn(N, K, M, dY, X, TFmt<T>::v, d_zero_bias, gW, s, splitk_tn ? -1 : 1));
+        if (dx_kind) SD_TRY(gemm_any<T>(M, K, N, dY, W.t, d_zero_bias, resid, dX, dx_kind == 2, s));
+        return SEQDIFF_OK;
+      }
+    }
     const int Mp = (M + 7) & ~7;  // contraction length of dW, padded with zero columns to a 16 B pitch
     SD_TRY(transpose_colsum<T>(dY, M, N, trA, gb, s, Mp));
     SD_TRY(transpose_colsum<T>(X, M, K, trB, nullptr, s, Mp));

@@ -121,6 +121,48 @@ template int transpose_colsum<float>(const float*, int, int, float*, float*, cud
 template int transpose_colsum<bf16>(const bf16*, int, int, bf16*, float*, cudaStream_t, int);
 template int transpose_colsum<f16>(const f16*, int, int, f16*, float*, cudaStream_t, int);
 
+// column sums of a 16-bit / fp32 [rows, cols] matrix, ADDED into colsum[cols] (pre-zeroed): the bias gradient db = sum over tokens of dY
+// when the weight-gradient GEMM reads dY in place (gemm_16_tn) and no transpose pass exists to fuse it into.
+// Block = 32 column-octets x 8 row lanes over a slab of 256 rows; partial sums meet in shared memory, one atomic per column.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int rows, int cols, float* __restrict__ colsum) {
+  __shared__ float part[8][256];
+  const int oct = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + oct * 8;
+  const int r0 = blockIdx.y * 256;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < cols) {
+    const int r_end = r0 + 256 < rows ? r0 + 256 : rows;
+    for (int r = r0 + rl; r < r_end; r += 8) {
+      float x[8];
+      load8<T>(in + static_cast<size_t>(r) * cols + c0, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += x[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[rl][oct * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += part[i][threadIdx.x];
+    atomicAdd(colsum + c, sum);
+  }
+}
+template <typename T>
+int colsum_add(const T* in, int rows, int cols, float* colsum, cudaStream_t s) {
+  SD_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "colsum: cols must be a multiple of 8");
+  SD_CUDA(launch_k(colsum_kernel<T>, dim3(ceil_div(cols, 256), ceil_div(rows, 256)), dim3(256), 0, s, in, rows, cols, colsum));
+  SD_LAUNCHED("colsum", s);
+  return SEQDIFF_OK;
+}
+template int colsum_add<bf16>(const bf16*, int, int, float*, cudaStream_t);
+template int colsum_add<f16>(const f16*, int, int, float*, cudaStream_t);
+
 // fp32 [rows, cols] -> T [cols, rows] (weights: the fp32 master -> the transposed operand copy the dgrad GEMMs read)
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ in, int rows, int cols, T* __restrict__ out) {

@@ -266,6 +266,9 @@ SEQDIFF_API int seqdiff_op_attention(int precision, int B, int heads, int Lq, in
  * (seed, site, element, step); p_drop = 0: none), and its backward.  impl 0: warp-level tensor-core kernels (16-bit modes only),
  * 1: fp32 SIMT kernels (all modes; the fp32 parity path).  L <= 128.  out / dout / dq / dk / dv: [B, L, heads*64] dense;
  * dE [2P-1, 64] f32 is ACCUMULATED into (zero it first); NULL when dist_emb is NULL. */
+/* C[M,N] (+)= At^T Bt: At [K,M], Bt [K,N] row-major 16-bit, C fp32 (pre-zeroed when split_k != 1; split_k = -1: auto).  The weight-gradient
+ * product of the training step with both operands MN-major for tcgen05 (no transposed copies).  Operator-level entry for tests. */
+SEQDIFF_API int seqdiff_op_gemm_tn(int precision, int M, int N, int K, const void* At, const void* Bt, float* C, int split_k, void* stream);
 SEQDIFF_API int seqdiff_op_attention_train_fwd(int precision, int impl, int B, int heads, int Lq, int Lk, const void* q, int ldq, const void* k,
                                    int ldk, const void* v, int ldv, const void* dist_emb, int P, const float* key_mask, float p_drop,
                                    uint64_t seed, uint32_t site, uint32_t step, void* out, void* stream);

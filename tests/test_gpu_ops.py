@@ -81,6 +81,28 @@ def test_gemm_tcgen05(M, N, K, bn, cg2, mode):
         assert err <= tol * scale + 1e-3 * (r is None), f"M{M} N{N} K{K} bn{bn} cg2{cg2} mode{mode} epi{epi} resid{r is not None}: err {err} scale {scale}"
 
 
+@pytest.mark.parametrize("M,N,K", [(768, 768, 8192), (2304, 768, 1000), (768, 1024, 16), (4608, 768, 4096), (1024, 768, 333), (768, 3072, 2048), (128, 128, 64)])
+@pytest.mark.parametrize("split", [1, -1, 5])
+@pytest.mark.parametrize("mode", [BF16, FP16])
+def test_gemm_tn_wgrad(M, N, K, split, mode):
+    """C[M,N] = At^T Bt with At [K,M], Bt [K,N] row-major (both operands MN-major for tcgen05): the weight-gradient product of the
+    training step read in place -- against an fp32 matmul of the same 16-bit values.  Ragged token counts K (TMA zero fill), split-K
+    (atomic accumulation into a zeroed C) and one k-block cases."""
+    if mode != BF16 and K > 2048:
+        pytest.skip("format variants share the tile code")
+    lib = sd_pkg().lib()
+    dt = _TDT[mode][0]
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + 7 * K)
+    At = torch.randn(K, M, generator=g).to(DEV).to(dt)
+    Bt = (torch.randn(K, N, generator=g) / math.sqrt(K)).to(DEV).to(dt)
+    C = torch.zeros(M, N, device=DEV)
+    _check(lib.seqdiff_op_gemm_tn(mode, M, N, K, _p(At), _p(Bt), _p(C), split, stream_ptr()))
+    torch.cuda.synchronize()
+    ref = At.float().t() @ Bt.float()
+    err = (C - ref).abs().max().item()
+    assert torch.isfinite(C).all() and err <= 2e-5 * ref.abs().max().item() + 1e-5 * math.sqrt(K), f"M{M} N{N} K{K} split{split}: err {err} scale {ref.abs().max().item()}"
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 768, 768), (77, 2304, 768), (33, 20, 768), (64, 768, 3072)])
 def test_gemm_fp32(M, N, K):
     lib = sd_pkg().lib()
