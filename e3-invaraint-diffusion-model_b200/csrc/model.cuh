@@ -164,6 +164,17 @@ struct Model {
   int train_prec = -1;                     // precision the transposed operand copies (Wt::t) were built for; -1 = none
   bool repack_reuse = false;               // finalize() after an optimizer step: re-fill the packed buffers in place
   size_t packed_cursor = 0;
+  // The packing operations of the last full finalize(), recorded so that the refresh after an optimizer step is three batched
+  // launches (copies, conversions, transposes) over device-resident chunk tables instead of ~270 small ones.
+  struct RpCopy { float* dst; const float* src; int64_t n; };
+  struct RpConv { const float* src; void* h; void* g; int64_t n; };
+  struct RpTrans { const float* src; void* dst; int rows, cols; };
+  std::vector<RpCopy> rp_copy;
+  std::vector<RpConv> rp_conv;
+  std::vector<RpTrans> rp_trans, rp_trans_f32;
+  void* d_rp_tables = nullptr;             // chunk tables of the three batched kernels (built on first use)
+  int rp_n_copy = 0, rp_n_conv = 0, rp_n_trans = 0, rp_n_trans_f32 = 0, rp_table_prec = -2;
+  int repack_fast(cudaStream_t s);
   float** d_slot_w = nullptr;
   int64_t* d_slot_off = nullptr;
   double* d_opt_scratch = nullptr;

@@ -373,4 +373,20 @@ def test_training_step_api_and_fit_reduce_the_loss():
     model.eval()
     out = sd.denoise_tensors(batch, model, sd.PredefinedNoiseScheduleDiscrete("cosine", 5), sd.BlosumTransition(x_classes=20), True, timesteps=5)
     assert torch.isfinite(out).all()
+    # the packed operand copies the optimizer refreshes in place (batched copy / convert / transpose kernels) must equal what a
+    # fresh handle builds from the same trained weights: eval forward of both, every precision, bit for bit
+    trained = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    sd.sample.CONFIG.update(num_hidden_layers=2)
+    fresh = sd.sample.get_model()
+    sd.sample.CONFIG.update(num_hidden_layers=6)
+    fresh.load_state_dict(trained, strict=True)
+    fresh = fresh.eval()
+    x_t = O.generate_discrete_noise(B, L, generator=torch.Generator().manual_seed(3))
+    args = [a.to(DEV) for a in (torch.full((B, 1), 17.0), x_t, batch["ligand_angles"], batch["ligand_attn_mask"], batch["receptor_seq"],
+                                batch["receptor_angles"], batch["receptor_attn_mask"])]
+    for prec in ("bf16", "fp16", "fp32"):
+        model.precision = fresh.precision = prec
+        with torch.no_grad():
+            assert torch.equal(model(*args), fresh(*args)), prec
+    fresh.release()
     model.release()
