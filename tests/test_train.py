@@ -197,7 +197,8 @@ def _attn_ref(q, k, v, E, mask, P):
 
 
 @gpu
-@pytest.mark.parametrize("B,heads,Lq,Lk,P,rel", [(3, 12, 128, 128, 128, True), (2, 4, 100, 77, 128, True), (2, 12, 48, 128, 128, False), (5, 2, 17, 33, 64, True)])
+@pytest.mark.parametrize("B,heads,Lq,Lk,P,rel", [(3, 12, 128, 128, 128, True), (2, 4, 100, 77, 128, True), (2, 12, 48, 128, 128, False), (5, 2, 17, 33, 64, True),
+                                                 (4, 12, 128, 128, 128, False), (3, 4, 100, 76, 128, False), (37, 12, 64, 128, 128, False), (5, 2, 17, 33, 64, False)])
 def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
     """training attention at operator level: (1) fp32 SIMT forward / backward == torch autograd on the attention core, 1e-5;
     (2) the tensor-core kernels (bf16 / fp16 operands) agree with the SIMT kernels run on the same 16-bit inputs -- with and
@@ -213,7 +214,7 @@ def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
     lens = torch.randint(1, Lk + 1, (B,), generator=g)
     mask = (torch.arange(Lk)[None, :] < lens[:, None]).float()
 
-    def run(prec, impl, dt, pdrop, fwd_impl=None):
+    def run(prec, impl, dt, pdrop, fwd_impl=None, bwd_impl=None):
         dev = lambda x: None if x is None else x.to(DEV).to(dt).contiguous()
         dq_, dk_, dv_, do_, dE_ = dev(q), dev(k), dev(v), dev(do), dev(E)
         m_ = mask.to(DEV)
@@ -223,7 +224,7 @@ def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
         st = stream_ptr()
         assert lib.seqdiff_op_attention_train_fwd(prec, impl if fwd_impl is None else fwd_impl, B, heads, Lq, Lk, p(dq_), Hh, p(dk_), Hh, p(dv_), Hh, p(dE_), P, p(m_), pdrop, 9, 3, 1,
                                                   p(out), st) == 0, lib.seqdiff_last_error()
-        assert lib.seqdiff_op_attention_train_bwd(prec, impl, B, heads, Lq, Lk, p(dq_), Hh, p(dk_), Hh, p(dv_), Hh, p(dE_), P, p(m_), pdrop, 9, 3, 1,
+        assert lib.seqdiff_op_attention_train_bwd(prec, impl if bwd_impl is None else bwd_impl, B, heads, Lq, Lk, p(dq_), Hh, p(dk_), Hh, p(dv_), Hh, p(dE_), P, p(m_), pdrop, 9, 3, 1,
                                                   p(do_), p(gq), p(gk), p(gv), p(gE), st) == 0, lib.seqdiff_last_error()
         torch.cuda.synchronize()
         return [x.float().cpu() if x is not None else None for x in (out, gq, gk, gv, gE)]
@@ -246,6 +247,11 @@ def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
                 if b is not None:
                     err = float((a - b).norm() / b.norm())
                     assert err < tol, (name, prec, pdrop, err)
+            if not rel and (pdrop == 0 or Lk % 4 == 0):  # the tcgen05 backward (what the training step runs for cross-attention)
+                pipe = run(prec, 0, dt, pdrop, bwd_impl=3)
+                for name, a, b in zip(("out", "dq", "dk", "dv"), pipe, simt):
+                    err = float((a - b).norm() / b.norm())
+                    assert err < tol, (name + " (tcgen05 backward)", prec, pdrop, err)
             if pdrop > 0:
                 assert float((simt[0] - run(prec, 1, dt, 0.0)[0]).abs().max()) > 1e-3  # the mask really was applied
                 if Lk % 4 == 0:  # the forward the training step runs: pipelined tcgen05 kernel, dropout inside, SAME Philox masks
