@@ -23,7 +23,7 @@ AB_KERNELS = os.environ.get("SEQDIFF_AB_KERNELS") == "1"
 DEBUG_BOUNDS = os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1"
 if AB_KERNELS:
     SOURCES.insert(3, "attention_tc.cu")
-HEADERS = ["common.cuh", "kernels.h", "model.cuh", "philox.cuh", os.path.join("..", "..", "include", "seqdiff_b200.h")]
+HEADERS = ["common.cuh", "kernels.h", "model.cuh", "philox.cuh", "skew.cuh", os.path.join("..", "..", "include", "seqdiff_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -402,13 +402,9 @@ int seqdiff_op_attention_train_bwd(int precision, int impl, int B, int heads, in
                            static_cast<const T*>(dist_emb), P, key_mask, dr, static_cast<const T*>(dout), static_cast<T*>(dq), Hh,        \
                            static_cast<T*>(dk), Hh, static_cast<T*>(dv), Hh, dE, s)
   if (precision == SEQDIFF_FP32) return SD_ATB(float, attention_bwd);
-  if (impl == 3) {  // tcgen05 backward (no relative_key term, Lq / Lk <= 128)
-    SD_CHECK(!dist_emb, "impl 3 (tcgen05 backward) has no relative_key term yet");
-    if (precision == SEQDIFF_BF16)
-      return attention_bwd_pipe<bf16>(B, heads, Lq, Lk, static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, static_cast<const bf16*>(v), ldv, key_mask,
-                                      dr, static_cast<const bf16*>(dout), static_cast<bf16*>(dq), Hh, static_cast<bf16*>(dk), Hh, static_cast<bf16*>(dv), Hh, s);
-    return attention_bwd_pipe<f16>(B, heads, Lq, Lk, static_cast<const f16*>(q), ldq, static_cast<const f16*>(k), ldk, static_cast<const f16*>(v), ldv, key_mask, dr,
-                                   static_cast<const f16*>(dout), static_cast<f16*>(dq), Hh, static_cast<f16*>(dk), Hh, static_cast<f16*>(dv), Hh, s);
+  if (impl == 3) {  // tcgen05 backward (Lq / Lk <= 128)
+    if (precision == SEQDIFF_BF16) return SD_ATB(bf16, attention_bwd_pipe);
+    return SD_ATB(f16, attention_bwd_pipe);
   }
   if (precision == SEQDIFF_BF16) return impl ? SD_ATB(bf16, attention_bwd) : SD_ATB(bf16, attention_bwd_tc);
   SD_CHECK(precision == SEQDIFF_FP16, "bad precision");

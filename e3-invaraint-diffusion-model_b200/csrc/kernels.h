@@ -128,11 +128,11 @@ extern unsigned long long* g_attn_trace;  // debug timeline buffer of the pipeli
 template <typename T>
 int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
                    int P, const float* key_mask, T* out, cudaStream_t s, const AttnPack* pack = nullptr);
-// ---- attention_bwd_pipe.cu: backward of the attention core on tcgen05 (Lq, Lk <= 128, no relative_key term) ----------------
+// ---- attention_bwd_pipe.cu: backward of the attention core on tcgen05 (Lq, Lk <= 128; dE += gradient of the distance embedding) ----
 bool attention_bwd_pipe_usable(int Lq, int Lk, const void* dist_emb, float p_drop);
 template <typename T>
-int attention_bwd_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const float* key_mask, DropSpec dr,
-                       const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, cudaStream_t s);
+int attention_bwd_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
+                       const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s);
 // the same kernel with the training-mode attention-probability dropout applied to P (masks: DropSpec / Philox, philox.cuh); Lk % 4 == 0
 template <typename T>
 int attention_pipe_dropout(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,

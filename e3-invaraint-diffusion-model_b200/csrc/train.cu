@@ -528,8 +528,8 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
                       const DropSpec& dr, const T* dctx, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* gE) -> int {
     const T* e = E ? static_cast<const T*>(wsel<T>(*E)) : nullptr;
     if constexpr (k16) {
-      if (!simt_attn && attention_bwd_pipe_usable(Lq, Lk, e, dr.p))  // tcgen05 backward (cross-attention: no relative term)
-        return attention_bwd_pipe<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, s);
+      if (!simt_attn && attention_bwd_pipe_usable(Lq, Lk, e, dr.p))  // tcgen05 backward
+        return attention_bwd_pipe<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s);
       if (!simt_attn) return attention_bwd_tc<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s);
     }
     return attention_bwd<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s);

@@ -198,7 +198,8 @@ def _attn_ref(q, k, v, E, mask, P):
 
 @gpu
 @pytest.mark.parametrize("B,heads,Lq,Lk,P,rel", [(3, 12, 128, 128, 128, True), (2, 4, 100, 77, 128, True), (2, 12, 48, 128, 128, False), (5, 2, 17, 33, 64, True),
-                                                 (4, 12, 128, 128, 128, False), (3, 4, 100, 76, 128, False), (37, 12, 64, 128, 128, False), (5, 2, 17, 33, 64, False)])
+                                                 (4, 12, 128, 128, 128, False), (3, 4, 100, 76, 128, False), (37, 12, 64, 128, 128, False), (5, 2, 17, 33, 64, False),
+                                                 (30, 12, 128, 128, 128, True), (3, 4, 100, 76, 128, True), (7, 12, 64, 64, 64, True)])
 def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
     """training attention at operator level: (1) fp32 SIMT forward / backward == torch autograd on the attention core, 1e-5;
     (2) the tensor-core kernels (bf16 / fp16 operands) agree with the SIMT kernels run on the same 16-bit inputs -- with and
@@ -247,11 +248,12 @@ def test_attention_train_kernels(B, heads, Lq, Lk, P, rel):
                 if b is not None:
                     err = float((a - b).norm() / b.norm())
                     assert err < tol, (name, prec, pdrop, err)
-            if not rel and (pdrop == 0 or Lk % 4 == 0):  # the tcgen05 backward (what the training step runs for cross-attention)
+            if pdrop == 0 or Lk % 4 == 0:  # the tcgen05 backward (what the training step runs)
                 pipe = run(prec, 0, dt, pdrop, bwd_impl=3)
-                for name, a, b in zip(("out", "dq", "dk", "dv"), pipe, simt):
-                    err = float((a - b).norm() / b.norm())
-                    assert err < tol, (name + " (tcgen05 backward)", prec, pdrop, err)
+                for name, a, b in zip(("out", "dq", "dk", "dv", "dE"), pipe, simt):
+                    if b is not None:
+                        err = float((a - b).norm() / b.norm())
+                        assert err < tol, (name + " (tcgen05 backward)", prec, pdrop, err)
             if pdrop > 0:
                 assert float((simt[0] - run(prec, 1, dt, 0.0)[0]).abs().max()) > 1e-3  # the mask really was applied
                 if Lk % 4 == 0:  # the forward the training step runs: pipelined tcgen05 kernel, dropout inside, SAME Philox masks
