@@ -121,20 +121,27 @@ template int transpose_colsum<float>(const float*, int, int, float*, float*, cud
 template int transpose_colsum<bf16>(const bf16*, int, int, bf16*, float*, cudaStream_t, int);
 template int transpose_colsum<f16>(const f16*, int, int, f16*, float*, cudaStream_t, int);
 
+// Shared-memory accumulators that every row of a warp adds into: column e = (i * 32 + lane) * 8 + j of a feature row lives in slot
+// (i * 8 + j) * 32 + lane, so the 32 lanes of one atomic instruction hit 32 different banks (with the natural index they are 8 words
+// apart: 8-way conflicts on every one of the ~10 k shared atomics per row -- ncu: embed_bwd 274 us per launch).
+__device__ __forceinline__ int acc_slot(int i, int lane, int j) { return (i * 8 + j) * 32 + lane; }
+__device__ __forceinline__ int acc_slot_of_col(int e) { return acc_slot(e >> 8, (e >> 3) & 31, e & 7); }
+
 // column sums of a 16-bit / fp32 [rows, cols] matrix, ADDED into colsum[cols] (pre-zeroed): the bias gradient db = sum over tokens of dY
 // when the weight-gradient GEMM reads dY in place (gemm_16_tn) and no transpose pass exists to fuse it into.
-// Block = 32 column-octets x 8 row lanes over a slab of 256 rows; partial sums meet in shared memory, one atomic per column.
+// Block = 32 column-octets x 8 row lanes over a slab of 64 rows (enough CTAs to fill the GPU at M = 2048 .. 32768 rows); partial sums
+// meet in shared memory, one atomic per column and CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int rows, int cols, float* __restrict__ colsum) {
   __shared__ float part[8][256];
   const int oct = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + oct * 8;
-  const int r0 = blockIdx.y * 256;
+  const int r0 = blockIdx.y * 64;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (c0 < cols) {
-    const int r_end = r0 + 256 < rows ? r0 + 256 : rows;
+    const int r_end = r0 + 64 < rows ? r0 + 64 : rows;
     for (int r = r0 + rl; r < r_end; r += 8) {
       float x[8];
       load8<T>(in + static_cast<size_t>(r) * cols + c0, x);
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, i
 template <typename T>
 int colsum_add(const T* in, int rows, int cols, float* colsum, cudaStream_t s) {
   SD_CHECK(rows > 0 && cols > 0 && cols % 8 == 0, "colsum: cols must be a multiple of 8");
-  SD_CUDA(launch_k(colsum_kernel<T>, dim3(ceil_div(cols, 256), ceil_div(rows, 256)), dim3(256), 0, s, in, rows, cols, colsum));
+  SD_CUDA(launch_k(colsum_kernel<T>, dim3(ceil_div(cols, 256), ceil_div(rows, 64)), dim3(256), 0, s, in, rows, cols, colsum));
   SD_LAUNCHED("colsum", s);
   return SEQDIFF_OK;
 }
@@ -544,7 +551,7 @@ __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __re
       for (int j = 0; j < 8; ++j) {
         const float go = g[i][j] * keep[j];
         v[i][j] = (v[i][j] - mean) * rstd;
-        const int e = (i * 32 + lane) * 8 + j;
+        const int e = acc_slot(i, lane, j);
         atomicAdd(sacc + (fin + 1) * H + e, go * v[i][j]);
         atomicAdd(sacc + (fin + 2) * H + e, go);
         g[i][j] = go * w8[j];
@@ -557,23 +564,24 @@ __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __re
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(k) * H + (i * 32 + lane) * 8 + j, xk * g[i][j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(k) * H + acc_slot(i, lane, j), xk * g[i][j]);
     }
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(fin) * H + (i * 32 + lane) * 8 + j, g[i][j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(fin) * H + acc_slot(i, lane, j), g[i][j]);
   }
   __syncthreads();
   for (int e = threadIdx.x; e < fin * H; e += kTrThreads) {
     const int k = e / H, h = e - k * H;
-    const float v = sacc[e];
+    const float v = sacc[k * H + acc_slot_of_col(h)];
     if (v != 0.f) atomicAdd(dW + static_cast<size_t>(h) * fin + k, v);
   }
   for (int e = threadIdx.x; e < H; e += kTrThreads) {
-    atomicAdd(db + e, sacc[fin * H + e]);
-    atomicAdd(dgamma + e, sacc[(fin + 1) * H + e]);
-    atomicAdd(dbeta + e, sacc[(fin + 2) * H + e]);
+    const int sl = acc_slot_of_col(e);
+    atomicAdd(db + e, sacc[fin * H + sl]);
+    atomicAdd(dgamma + e, sacc[(fin + 1) * H + sl]);
+    atomicAdd(dbeta + e, sacc[(fin + 2) * H + sl]);
   }
 }
 int embed_bwd(const float* dout, const float* x, int M, int fin, int H, const float* Wt, const float* b, const float* gamma, float eps, DropSpec dr,
@@ -649,7 +657,7 @@ __global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd_kernel(const fl
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           g[i][j] = fmaf(d, w8[j], g[i][j]);
-          atomicAdd(sdW + static_cast<size_t>(f) * H + (i * 32 + lane) * 8 + j, d * ln[i][j]);
+          atomicAdd(sdW + static_cast<size_t>(f) * H + acc_slot(i, lane, j), d * ln[i][j]);
         }
       }
     }
@@ -660,7 +668,7 @@ __global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd_kernel(const fl
         load8<float>(gamma + (i * 32 + lane) * 8, w8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int e = (i * 32 + lane) * 8 + j;
+          const int e = acc_slot(i, lane, j);
           atomicAdd(sG + e, g[i][j] * v[i][j]);
           atomicAdd(sG + H + e, g[i][j]);
           g[i][j] *= w8[j];
@@ -671,11 +679,15 @@ __global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd_kernel(const fl
     st_row<float, VPL>(dy + static_cast<size_t>(row) * H, lane, g);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < F * H; i += kTrThreads)
-    if (sdW[i] != 0.f) atomicAdd(dW2 + i, sdW[i]);
+  for (int i = threadIdx.x; i < F * H; i += kTrThreads) {
+    const int f = i / H, c = i - f * H;
+    const float x = sdW[f * H + acc_slot_of_col(c)];
+    if (x != 0.f) atomicAdd(dW2 + i, x);
+  }
   for (int i = threadIdx.x; i < H; i += kTrThreads) {
-    atomicAdd(dgamma + i, sG[i]);
-    atomicAdd(dbeta + i, sG[H + i]);
+    const int sl = acc_slot_of_col(i);
+    atomicAdd(dgamma + i, sG[sl]);
+    atomicAdd(dbeta + i, sG[H + sl]);
   }
   if (threadIdx.x < F) atomicAdd(db2 + threadIdx.x, sB[threadIdx.x]);
 }
