@@ -17,6 +17,7 @@
 // must share the format); GEMMs that feed a LayerNorm write fp32 and take an fp32 residual, so the residual stream of the
 // network never passes through a 16-bit rounding.
 // fp32 path (parity gate 1e-5): plain SIMT tiled kernel, fp32 FMA accumulation.
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <type_traits>
@@ -923,7 +924,13 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
         SD_CUDA(cudaStreamSynchronize(s));  // the operands are ready
         float best_ms = 0.f;
         constexpr int kReps = 8;
-        for (int cand : {128, 192, 256, 128 | (1 << 16), 192 | (1 << 16), 256 | (1 << 16), 384 | (1 << 16), 512 | (1 << 16)}) {
+        // (the 256 x 384 / 256 x 512 pair tiles of round 1 were never / once selected over cfg 1 / 2 / 3, the structure model and the
+        //  training shapes -- profiles/gemm_tune_selections_r02.log -- and are no longer built: SEQDIFF_WIDE_TILES brings them back)
+        for (int cand : {128, 192, 256, 128 | (1 << 16), 192 | (1 << 16), 256 | (1 << 16)
+#ifdef SEQDIFF_WIDE_TILES
+                         , 384 | (1 << 16), 512 | (1 << 16)
+#endif
+             }) {
           if (N % (cand & 0xffff)) continue;
           // eager warm-up launch: kernel attributes and the descriptor cache are set outside the capture
           SD_TRY(gemm_16(M, N, K, A, a_fmt, W, w_fmt, bias, resid, epi, C, out_kind, ts, cand, ln_resid));
@@ -955,6 +962,9 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
         SD_CUDA(cudaStreamSynchronize(ts));  // C holds the result of the last candidate before the caller's stream goes on
         std::lock_guard<std::mutex> g(mu);
         tuned[key] = cfg;
+        // SEQDIFF_GEMM_TUNE_LOG=1: one line per tuned (shape, epilogue) -- which tile configurations the model's shapes really select
+        static const bool tlog = [] { const char* e = getenv("SEQDIFF_GEMM_TUNE_LOG"); return e && e[0] == '1'; }();
+        if (tlog) fprintf(stderr, "[seqdiff gemm tune] M=%d N=%d K=%d epi=%d out=%d resid=%d -> bn=%d cg2=%d (%.1f us)\n", M, N, K, epi, out_kind, rkind, cfg & 0xffff, cfg >> 16, best_ms * 1e3 / kReps);
         return SEQDIFF_OK;  // C already holds the result (every candidate wrote it)
       }
     }
@@ -983,8 +993,12 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
 #define SD_DISPATCH(BN_)                                                                                          \
   return cg2 ? dispatch_tc<BN_, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid, ksplit) \
              : dispatch_tc<BN_, false>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid, ksplit)
+#ifdef SEQDIFF_WIDE_TILES
   if (bn == 512) return dispatch_tc<512, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid, ksplit);
   if (bn == 384) return dispatch_tc<384, true>(ta, tb, tc, bias, resid, epi, C, out_kind, M, N, K, idesc, s, ln_resid, ksplit);
+#else
+  SD_CHECK(bn <= 256, "the 384 / 512-wide pair tiles are not in this build (compile with -DSEQDIFF_WIDE_TILES)");
+#endif
   if (bn == 256) { SD_DISPATCH(256); }
   if (bn == 192) { SD_DISPATCH(192); }
   SD_DISPATCH(128);

@@ -20,7 +20,7 @@ for name, cnt, M, N, K, epi, kind in SHAPES:
     bias = torch.randn(N, device=dev); resid = torch.randn(M, N, device=dev) if kind == "r" else None
     C = torch.empty(M, N, device=dev, dtype=torch.float32 if kind == "r" else torch.bfloat16)
     best = {}
-    for bn in (128, 192, 256, 1128, 1192, 1256, 1384, 1512):   # 1xxx = CTA-pair (cta_group::2) kernel with tile width xxx
+    for bn in (128, 192, 256, 1128, 1192, 1256):   # 1xxx = CTA-pair (cta_group::2) kernel with tile width xxx
         cg2, bn = bn // 1000, bn % 1000
         if N % bn: continue
         def call():

@@ -48,7 +48,7 @@ _TDT = {BF16: (torch.bfloat16, torch.bfloat16), FP16: (torch.float16, torch.floa
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("bn", [0, 128, 192, 256, 384, 512])
+@pytest.mark.parametrize("bn", [0, 128, 192, 256])  # (384 / 512-wide pair tiles: out of the default build since round 2, -DSEQDIFF_WIDE_TILES)
 @pytest.mark.parametrize("cg2", [0, 1])
 @pytest.mark.parametrize("mode", [BF16, FP16])
 def test_gemm_tcgen05(M, N, K, bn, cg2, mode):
