@@ -91,8 +91,12 @@ struct PdlScope {
 // measured on B200 (profiles/pdl_small_r02.log) B = 1: 685 -> 616 us, B = 4: 711 -> 665 us per step; from B = 16 on the persistent
 // kernels fill every SM and the early launch only costs (846 -> 919 us).  Hence: on up to 2048 stacked token rows.
 static bool pdl_small_batch(int B, int Ll, int Lr) { return static_cast<long long>(B) * (Ll + Lr) <= 2048; }
+int pdl_mode() {
+  static const int env = [] { const char* e = getenv("SEQDIFF_PDL"); return e ? (e[0] >= '0' && e[0] <= '3' ? e[0] - '0' : 0) : -1; }();
+  return env;
+}
 bool pdl_enabled() {
-  static const int env = [] { const char* e = getenv("SEQDIFF_PDL"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+  const int env = pdl_mode();
   return env >= 0 ? env == 1 : g_pdl_scope > 0;
 }
 
