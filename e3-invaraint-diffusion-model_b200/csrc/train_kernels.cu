@@ -382,12 +382,12 @@ int layernorm_bwd(const float* dh, const float* o, int M, int H, const float* ga
 // the residual and, for the attention update, through o = ... + x), d(shift, scale, gate) either written as T rows of dmodT
 // (mod_div == 1) or atomically accumulated into dmod32 [M / mod_div, 6H] (conditioning broadcast over the graph).
 // =====================================================================================================
-template <typename T, int VPL, bool AFF>
+template <typename T, int VPL, bool AFF, bool PG>
 __global__ void __launch_bounds__(kTrThreads) ln_modulate_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ in, int M, int H,
                                                                      const float* __restrict__ lnw, const float* __restrict__ lnb, float eps1,
                                                                      const T* __restrict__ mod, int mod_div, int chunk0, float* __restrict__ din,
                                                                      float* __restrict__ sum_out, T* __restrict__ dmodT, float* __restrict__ dmod32,
-                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rpw) {
   extern __shared__ float sacc[];  // [2][H] (AFF only)
   if (AFF) {
     for (int e = threadIdx.x; e < 2 * H; e += kTrThreads) sacc[e] = 0.f;
@@ -399,7 +399,23 @@ __global__ void __launch_bounds__(kTrThreads) ln_modulate_bwd_kernel(const float
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
-  for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
+  // per-graph conditioning (dmod32): a warp takes `rpw` CONSECUTIVE rows of one graph and adds their shift / scale / gate gradients in
+  // registers -- one global atomic per element and warp instead of one per element and ROW (37 M contended atomics per launch at
+  // 128 graphs x 128 rows before).  Per-token conditioning (dmodT): rpw = 1, the grid-stride loop over single rows as before.
+  float am[PG ? 3 : 1][VPL][8];
+  (void)am;
+  for (int grp = blockIdx.x * (kTrThreads / 32) + warp; grp * rpw < M; grp += gridDim.x * (kTrThreads / 32)) {
+  if (PG) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) am[c][i][j] = 0.f;
+  }
+  for (int rr = 0; rr < rpw; ++rr) {
+    const int row = grp * rpw + rr;
+    if (row >= M) break;
     float y[VPL][8], xh1[VPL][8], g[VPL][8];
     ld_row<float, VPL>(in + static_cast<size_t>(row) * H, lane, y);
     ld_row<float, VPL>(dout + static_cast<size_t>(row) * H, lane, g);
@@ -443,13 +459,12 @@ __global__ void __launch_bounds__(kTrThreads) ln_modulate_bwd_kernel(const float
         store8<T>(drow + (chunk0 + 0) * H + e, dsh);
         store8<T>(drow + (chunk0 + 1) * H + e, dsc);
         store8<T>(drow + (chunk0 + 2) * H + e, dgt);
-      } else {
-        float* drow = dmod32 + static_cast<size_t>(row / mod_div) * (6 * H);
+      } else if constexpr (PG) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          atomicAdd(drow + (chunk0 + 0) * H + e + j, dsh[j]);
-          atomicAdd(drow + (chunk0 + 1) * H + e + j, dsc[j]);
-          atomicAdd(drow + (chunk0 + 2) * H + e + j, dgt[j]);
+          am[0][i][j] += dsh[j];
+          am[1][i][j] += dsc[j];
+          am[2][i][j] += dgt[j];
         }
       }
     }
@@ -478,7 +493,17 @@ __global__ void __launch_bounds__(kTrThreads) ln_modulate_bwd_kernel(const float
         for (int j = 0; j < 8; ++j) d2[i][j] += g[i][j];
       st_row<float, VPL>(sum_out + static_cast<size_t>(row) * H, lane, d2);
     }
+  }  // rows of the group
+  if constexpr (PG) {
+    float* drow = dmod32 + static_cast<size_t>((grp * rpw) / mod_div) * (6 * H);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(drow + (chunk0 + c) * H + (i * 32 + lane) * 8 + j, am[c][i][j]);
   }
+  }  // groups
   if constexpr (AFF) {
     flush_feature_sums<VPL>(ag, dgamma, sacc, H, lane);
     flush_feature_sums<VPL>(ab, dbeta, sacc + H, H, lane);
@@ -490,15 +515,22 @@ int ln_modulate_bwd(const float* dout, const float* in, int M, int H, bool affin
                     cudaStream_t s) {
   SD_CHECK((dmodT != nullptr) != (dmod32 != nullptr), "ln_modulate_bwd: exactly one of dmodT / dmod32");
   SD_CHECK(!dmodT || mod_div == 1, "ln_modulate_bwd: direct T rows only for per-token conditioning");
-  const int need = ceil_div(M, kTrThreads / 32);
+  // per-graph conditioning: rows per warp = the largest of 16, 8, 4, 2, 1 that divides the rows per graph (a warp's rows share one graph)
+  int rpw = 1;
+  if (dmod32)
+    for (int c : {16, 8, 4, 2})
+      if (mod_div % c == 0) { rpw = c; break; }
+  const int need = ceil_div(ceil_div(M, rpw), kTrThreads / 32);
   const int grid = need < 2 * num_sms() ? need : 2 * num_sms();
+#define SD_LNMB_LAUNCH(AFF_, PG_, SMEM_)                                                                                                       \
+  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_bwd_kernel<T, VPL, AFF_, PG_>, dim3(grid), dim3(kTrThreads), SMEM_, s, dout, in, M, H, lnw, lnb, \
+                                      eps1, mod, mod_div, chunk0, din, sum_out, dmodT, dmod32, dgamma, dbeta, rpw)))
   if (affine_first) {
-    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_bwd_kernel<T, VPL, true>, dim3(grid), dim3(kTrThreads), 2 * H * sizeof(float), s, dout, in, M, H,
-                                        lnw, lnb, eps1, mod, mod_div, chunk0, din, sum_out, dmodT, dmod32, dgamma, dbeta)));
+    if (dmod32) { SD_LNMB_LAUNCH(true, true, 2 * H * sizeof(float)); } else { SD_LNMB_LAUNCH(true, false, 2 * H * sizeof(float)); }
   } else {
-    SD_VPL_DISPATCH(H, SD_CUDA(launch_k(ln_modulate_bwd_kernel<T, VPL, false>, dim3(grid), dim3(kTrThreads), 0, s, dout, in, M, H, lnw, lnb, eps1,
-                                        mod, mod_div, chunk0, din, sum_out, dmodT, dmod32, dgamma, dbeta)));
+    if (dmod32) { SD_LNMB_LAUNCH(false, true, 0); } else { SD_LNMB_LAUNCH(false, false, 0); }
   }
+#undef SD_LNMB_LAUNCH
   SD_LAUNCHED("ln_modulate_bwd", s);
   return SEQDIFF_OK;
 }
