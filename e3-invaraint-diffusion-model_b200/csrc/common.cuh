@@ -520,7 +520,7 @@ int debug_guard_check(cudaStream_t s, int* n_bands, int* n_broken);
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
-int pdl_mode();  // SEQDIFF_PDL: -1 unset, 0 off, 1 every launch, 2 only light successors (< 64 KB of shared memory), 3 only heavy ones
+int pdl_mode();  // effective mode of this launch: 0 off, 1 every launch, 2 only light successors (< 64 KB of shared memory), 3 only heavy ones
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kc(int cluster_x, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -530,8 +530,8 @@ inline cudaError_t launch_kc(int cluster_x, void (*kernel)(KArgs...), dim3 grid,
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int n = 0;
-  const int pm = pdl_mode();
-  if (pm == 2 ? smem < 65536 : pm == 3 ? smem >= 65536 : pdl_enabled()) {
+  const int pm = pdl_mode();  // 0 off | 1 every launch | 2 light successors only | 3 heavy successors only (model.cu)
+  if (pm == 1 || (pm == 2 && smem < 65536) || (pm == 3 && smem >= 65536)) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

@@ -76,29 +76,30 @@ int profile_end(char* tags, int tag_stride, float* ms, int* counts, int cap) {
   return n;
 }
 
-// Programmatic dependent launch.  SEQDIFF_PDL=1 / 0 forces it on / off for every launch.  Unset: off for the sequence path -- measured on
-// B200 inside the replayed CUDA graph it changes the cfg-2 step by -1.8 .. +1 % (the kernels of consecutive nodes cannot co-reside: the
-// persistent GEMM / attention CTAs own the SM's shared memory) -- and ON for the structure model, whose M = 4096 steps are launch / ramp
-// bound (146 kernels of ~10 us): +2.5 .. 2.7 % there (profiles/struct_bench_r01.json vs gpurun A/B).
-static thread_local int g_pdl_scope = 0;
+// Programmatic dependent launch.  SEQDIFF_PDL=0 / 1 / 2 / 3 forces a mode for every launch (off / every launch / only light successors /
+// only heavy successors, i.e. kernels with >= 64 KB of shared memory: the GEMM and attention kernels).  Unset: chosen per call from the
+// measured behaviour on B200 inside the replayed CUDA graph --
+//   structure model (M = 4096 steps, 146 kernels of ~10 us): every launch, +2.5 .. 2.7 % (profiles/struct_bench_r01.json);
+//   sequence path, <= 2048 stacked token rows (grids of a few CTAs): every launch, B = 1 685 -> 616 us per step (profiles/pdl_small_r02.log);
+//   sequence path, <= 32768 rows (cfg 2: 16384 padded, ~7000 packed): heavy successors only, +1.1 % padded / +5.3 % packed; every launch
+//     costs 3 % there (the early-launched light kernels take registers next to the persistent CTAs), profiles/pdl_mode3_ab_r02.log;
+//   larger batches (cfg 3): off (+1.7 % padded but -7.6 % packed).
+static thread_local int g_pdl_scope = 0;   // 0 = none, else the mode (1 / 2 / 3) of the innermost scope
 struct PdlScope {
-  const bool on;
-  explicit PdlScope(bool enable = true) : on(enable) { if (on) ++g_pdl_scope; }
-  ~PdlScope() { if (on) --g_pdl_scope; }
+  const int prev;
+  explicit PdlScope(int mode = 1) : prev(g_pdl_scope) { if (mode) g_pdl_scope = mode; }
+  ~PdlScope() { g_pdl_scope = prev; }
 };
 // Sequence path: a step is ~90 kernels with a fixed cost of ~7 us each (B = 1: 685 us per step).  When the grids are a handful of
 // CTAs the successor's prologue (barrier init, TMEM allocation, descriptor prefetch) can run on idle SMs under the predecessor:
 // measured on B200 (profiles/pdl_small_r02.log) B = 1: 685 -> 616 us, B = 4: 711 -> 665 us per step; from B = 16 on the persistent
 // kernels fill every SM and the early launch only costs (846 -> 919 us).  Hence: on up to 2048 stacked token rows.
-static bool pdl_small_batch(int B, int Ll, int Lr) { return static_cast<long long>(B) * (Ll + Lr) <= 2048; }
+static int pdl_auto_mode(long long rows) { return rows <= 2048 ? 1 : (rows <= 32768 ? 3 : 0); }
 int pdl_mode() {
   static const int env = [] { const char* e = getenv("SEQDIFF_PDL"); return e ? (e[0] >= '0' && e[0] <= '3' ? e[0] - '0' : 0) : -1; }();
-  return env;
+  return env >= 0 ? env : g_pdl_scope;
 }
-bool pdl_enabled() {
-  const int env = pdl_mode();
-  return env >= 0 ? env == 1 : g_pdl_scope > 0;
-}
+bool pdl_enabled() { return pdl_mode() == 1; }
 
 // ---- debug-build guard bands (see common.cuh) -------------------------------------------------------------------------------
 #ifdef SEQDIFF_DEBUG_BOUNDS
@@ -969,7 +970,7 @@ int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, 
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
   SD_CUDA(cudaSetDevice(device));
   SD_TRY(ensure_workspace(workspace_need(precision, B, Ll, Lr)));
-  const PdlScope pdl_small(pdl_small_batch(B, Ll, Lr));
+  const PdlScope pdl_scope(pdl_auto_mode(pk ? static_cast<long long>(pk->Ml) + pk->Mr : static_cast<long long>(B) * (Ll + Lr)));
   switch (precision) {
     case SEQDIFF_FP32:
       return forward_t<float>(1, B, Ll, Lr, timestep, step_ptr, x_t, lig_angle, lig_mask, rec_seq_in, rec_angle, rec_mask, logits, s, nullptr);
@@ -1121,7 +1122,7 @@ int Model::sample(int precision, int B, int Ll, int Lr, int T, const float* q_ta
   key.ws_ptr = ws; key.in_ptr = samp_in; key.tab_ptr = d_tables;  // (seed, gid0) are NOT part of the key: device memory, see arm_loop_kernel
   uint64_t* d_rng = reinterpret_cast<uint64_t*>(d_step + 16);
   auto one_step = [&](cudaStream_t st) -> int {
-    const PdlScope pdl_small(pdl_small_batch(B, Ll, Lr));
+    const PdlScope pdl_scope(pdl_auto_mode(pk ? static_cast<long long>(pk->Ml) + pk->Mr : static_cast<long long>(B) * (Ll + Lr)));
     SD_TRY(forward(precision, B, Ll, Lr, nullptr, d_step, x_cur, c_lang, c_lmask, c_rseq, c_rang, c_rmask, logits, st, pk));
     SD_TRY(reverse_step(d_tables, 1, B, Ll, x_cur, logits, diverse, noise_E, 0, 0, 0, d_step, x_cur, nullptr, st, d_step + 1, d_rng));
     return SEQDIFF_OK;
@@ -1352,7 +1353,7 @@ int Model::struct_forward(int precision, int B, int Ll, int Lr, const float* tim
                           int phases, cudaStream_t s) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
   SD_CHECK(arch == kArchStructure, "handle holds a sequence model: use seqdiff_forward");
-  const PdlScope pdl_on;  // launch-bound path: programmatic dependent launch unless SEQDIFF_PDL=0
+  const PdlScope pdl_on(3);  // launch-bound path: programmatic dependent launch of the heavy kernels (42.3 -> 43.0 k graph-steps/s against every launch) unless SEQDIFF_PDL overrides
   SD_CHECK(precision >= SEQDIFF_FP32 && precision <= SEQDIFF_FP16, "unknown precision mode");
   SD_CHECK(B > 0 && Ll > 0 && Lr > 0, "empty batch");
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
@@ -1375,7 +1376,7 @@ int Model::struct_sample(int precision, int B, int Ll, int Lr, int T, const floa
                          uint64_t gid0, float* steps_out, float* final_out, cudaStream_t caller) {
   SD_CHECK(finalized, "model not finalised (seqdiff_model_finalize)");
   SD_CHECK(arch == kArchStructure, "handle holds a sequence model: use seqdiff_sample");
-  const PdlScope pdl_on;
+  const PdlScope pdl_on(3);
   SD_CHECK(T >= 1 && B > 0 && Ll > 0 && Lr > 0, "bad sampling arguments");
   SD_CUDA(cudaSetDevice(device));
   if (!loop_stream) {
