@@ -170,7 +170,23 @@ class FlatAdamW:
         pass  # seqdiff_train_step overwrites the flat gradient buffer
 
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "param_groups": self.param_groups}
+        """optimizer checkpoint: step count, the flat AdamW moments (handle index space, see FlatParams.table) and the lr / wd group"""
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "param_groups": self.param_groups,
+                "table": dict(self.flat.table)}
+
+    def load_state_dict(self, state):
+        """resume: restores what state_dict() saved (moments are copied into this optimizer's flat buffers; a checkpoint written for a
+        different parameter layout -- other layer count / hidden size -- is rejected)."""
+        if "table" in state and dict(state["table"]) != dict(self.flat.table):
+            raise ValueError("optimizer state was saved for a different parameter layout")
+        for k in ("exp_avg", "exp_avg_sq"):
+            src = state[k]
+            if src.numel() != getattr(self, k).numel():
+                raise ValueError(f"optimizer state '{k}' has {src.numel()} elements, expected {getattr(self, k).numel()}")
+            getattr(self, k).copy_(src.to(device=self.flat.device, dtype=torch.float32))
+        self.step_count = int(state["step"])
+        if state.get("param_groups"):
+            self.param_groups[0].update({k: state["param_groups"][0][k] for k in ("lr", "weight_decay") if k in state["param_groups"][0]})
 
 
 def linear_warmup_factor(epoch: int, warmup: int, total: int) -> float:

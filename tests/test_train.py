@@ -349,6 +349,62 @@ def test_dropout_masks_are_consistent_between_forward_and_backward():
 
 
 @gpu
+def test_optimizer_checkpoint_resume_is_exact():
+    """4 optimizer steps in one go == 2 steps, optimizer + model checkpoint (state_dict), a NEW model + optimizer restored from it,
+    2 more steps: the same weights (dropout masks are keyed by the step counter, AdamW by its step count and moments)."""
+    sd = sd_pkg()
+    L, B = 64, 4
+    sd.sample.DEVICE = torch.device(DEV)
+    sd.sample.CONFIG.update(max_seq_len=L, timesteps=50, num_hidden_layers=2)
+    batch = O.synthetic_batch(B, L, (20, 60), (30, 64), 5)
+    t_int = torch.full((B, 1), 30.0)
+    E = torch.empty(B * L, 20).exponential_(1, generator=torch.Generator().manual_seed(9))
+
+    def fresh(state=None):
+        torch.manual_seed(0)
+        m = sd.sample.get_model()
+        if state is not None:
+            m.load_state_dict(state, strict=True)
+        m.lr, m.lr_scheduler, m.precision = 2e-4, None, "fp16"
+        return m.train()
+
+    def steps(m, opt, first, n):
+        for i in range(first, first + n):
+            m._train_steps = i            # the dropout step counter of training_step (it increments before use)
+            m._noise_calls = i
+            m.training_step(batch, i, t_int=t_int, noise_E=E)
+            opt.step()
+
+    try:
+        a = fresh()
+        oa = a.configure_optimizers()["optimizer"]
+        steps(a, oa, 0, 4)
+        want = {k: v.detach().cpu().clone() for k, v in a.state_dict().items()}
+        b = fresh()
+        ob = b.configure_optimizers()["optimizer"]
+        steps(b, ob, 0, 2)
+        ck_model = {k: v.detach().cpu().clone() for k, v in b.state_dict().items()}
+        ck_opt = {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in ob.state_dict().items()}
+        c = fresh(ck_model)
+        oc = c.configure_optimizers()["optimizer"]
+        oc.load_state_dict(ck_opt)
+        assert oc.step_count == 2 and torch.equal(oc.exp_avg.cpu(), ck_opt["exp_avg"]) and torch.equal(oc.exp_avg_sq.cpu(), ck_opt["exp_avg_sq"])
+        steps(c, oc, 2, 2)
+        got = c.state_dict()
+        # (the gradient buffers are filled with floating-point atomics -- split-K, column sums, dE -- so two runs agree to rounding, not
+        #  bit for bit; a resume that lost the moments or the step count would be off by ~lr per element and step: 5e-3 relative)
+        num = sum(float((want[k].double() - got[k].cpu().double()).pow(2).sum()) for k in want)
+        den = sum(float(want[k].double().pow(2).sum()) for k in want)
+        assert math.sqrt(num / den) < 2e-4, math.sqrt(num / den)
+        with pytest.raises(ValueError):
+            oc.load_state_dict({**ck_opt, "exp_avg": ck_opt["exp_avg"][:-4]})
+        for m in (a, b, c):
+            m.release()
+    finally:
+        sd.sample.CONFIG.update(num_hidden_layers=6)
+
+
+@gpu
 def test_training_step_api_and_fit_reduce_the_loss():
     """PeptideDiff.training_step / configure_optimizers / train.fit: a few steps on one fixed batch drive the loss down, the trained
     weights come back through state_dict(), and sampling still works on the updated handle."""
