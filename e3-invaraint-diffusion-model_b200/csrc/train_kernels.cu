@@ -555,6 +555,13 @@ __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __re
   for (int e = threadIdx.x; e < (fin + 3) * H; e += kTrThreads) sacc[e] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // db / dgamma / dbeta: every row adds to the same H columns -> per-warp register accumulators, flushed once per CTA (they were
+  // 3 H of the (3 + nnz) H shared atomics per row); dW^T[k, :] += x_k g[:] stays on shared atomics (k varies with the row).
+  float a_db[VPL][8], a_dg[VPL][8], a_dbt[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a_db[i][j] = 0.f; a_dg[i][j] = 0.f; a_dbt[i][j] = 0.f; }
   for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
     float xin = lane < fin ? x[static_cast<size_t>(row) * fin + lane] : 0.f;
     float v[VPL][8], g[VPL][8];
@@ -583,9 +590,8 @@ __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __re
       for (int j = 0; j < 8; ++j) {
         const float go = g[i][j] * keep[j];
         v[i][j] = (v[i][j] - mean) * rstd;
-        const int e = acc_slot(i, lane, j);
-        atomicAdd(sacc + (fin + 1) * H + e, go * v[i][j]);
-        atomicAdd(sacc + (fin + 2) * H + e, go);
+        a_dg[i][j] = fmaf(go, v[i][j], a_dg[i][j]);
+        a_dbt[i][j] += go;
         g[i][j] = go * w8[j];
       }
     }
@@ -601,8 +607,17 @@ __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __re
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(fin) * H + acc_slot(i, lane, j), g[i][j]);
+      for (int j = 0; j < 8; ++j) a_db[i][j] += g[i][j];
   }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = acc_slot(i, lane, j);
+      atomicAdd(sacc + static_cast<size_t>(fin) * H + e, a_db[i][j]);
+      atomicAdd(sacc + (fin + 1) * H + e, a_dg[i][j]);
+      atomicAdd(sacc + (fin + 2) * H + e, a_dbt[i][j]);
+    }
   __syncthreads();
   for (int e = threadIdx.x; e < fin * H; e += kTrThreads) {
     const int k = e / H, h = e - k * H;
