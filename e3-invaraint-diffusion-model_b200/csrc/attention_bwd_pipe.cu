@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kBT, 1)
 attention_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmE, const float* __restrict__ key_mask, int heads,
                           int Lq, int Lk, int P, uint32_t fmt, int n_items, const DropSpec dr, T* __restrict__ dq, int lddq, T* __restrict__ dk, int lddk,
-                          T* __restrict__ dv, int lddv, float* __restrict__ dE) {
+                          T* __restrict__ dv, int lddv, float* __restrict__ dE, const uint32_t* __restrict__ keep_in) {
   using BwdSmem = seqdiff::BwdSmem<REL>;
   using C = BwdCols<REL>;
   constexpr int kColS = C::kS, kColdP = C::kdP, kColdQ = C::kdQ, kColdV = C::kdV, kColdK = C::kdK;
@@ -280,7 +280,10 @@ attention_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       const float inv = live ? 1.0f / sum : 0.f;  // rows past the graph's length contribute nothing to dK / dV
       // ---- dropout mask of this thread's 64 keys: one bit per key (regenerated from the forward's Philox stream) ----
       uint64_t keepbits = ~0ull;
-      if (dr.p > 0.f) {
+      if (dr.p > 0.f && keep_in) {  // the forward kernel left the mask as bits: chunks 2 hf and 2 hf + 1 of this row
+        const uint2 kb2 = __ldg(reinterpret_cast<const uint2*>(keep_in + ((static_cast<size_t>(b) * heads + h) * 128 + row) * 4 + 2 * hf));
+        keepbits = static_cast<uint64_t>(kb2.x) | (static_cast<uint64_t>(kb2.y) << 32);
+      } else if (dr.p > 0.f) {
         keepbits = 0ull;
         const size_t e_row = ((static_cast<size_t>(b) * heads + h) * Lq + row) * Lk + 64 * hf;
 #pragma unroll
@@ -429,7 +432,8 @@ bool attention_bwd_pipe_usable(int Lq, int Lk, const void* dist_emb, float p_dro
 
 template <typename T, bool REL>
 static int launch_bwd_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* E, int P,
-                           const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s) {
+                           const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s,
+                           const uint32_t* keep_in) {
   SD_CHECK(B > 0 && heads > 0 && Lq >= 1 && Lk >= 1 && Lq <= 128 && Lk <= 128, "attention_bwd_pipe: one 128-row tile per (graph, head)");
   SD_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "row strides must be multiples of 8 elements");
   SD_CHECK(dr.p <= 0.f || Lk % 4 == 0, "dropout: Lk must be a multiple of 4");
@@ -453,19 +457,21 @@ static int launch_bwd_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq
   const int n_items = B * heads;
   const int grid = n_items < num_sms() ? n_items : num_sms();
   SD_CUDA(launch_k(kfn, dim3(grid), dim3(kBT), Sm::kBytes, s, tq, tk, tv, to, te, key_mask, heads, Lq, Lk, P, static_cast<uint32_t>(fmt), n_items, dr, dq, lddq,
-                   dk, lddk, dv, lddv, dE));
+                   dk, lddk, dv, lddv, dE, keep_in));
   SD_LAUNCHED(REL ? "attention_bwd_pipe_rel" : "attention_bwd_pipe", s);
   return SEQDIFF_OK;
 }
 template <typename T>
 int attention_bwd_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
-                       const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s) {
-  if (dist_emb) return launch_bwd_pipe<T, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, dr, dout, dq, lddq, dk, lddk, dv, lddv, dE, s);
-  return launch_bwd_pipe<T, false>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, dr, dout, dq, lddq, dk, lddk, dv, lddv, dE, s);
+                       const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s,
+                       const uint32_t* keep_in) {
+  if (dist_emb)
+    return launch_bwd_pipe<T, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, dr, dout, dq, lddq, dk, lddk, dv, lddv, dE, s, keep_in);
+  return launch_bwd_pipe<T, false>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, dr, dout, dq, lddq, dk, lddk, dv, lddv, dE, s, keep_in);
 }
 template int attention_bwd_pipe<bf16>(int, int, int, int, const bf16*, int, const bf16*, int, const bf16*, int, const bf16*, int, const float*, DropSpec,
-                                      const bf16*, bf16*, int, bf16*, int, bf16*, int, float*, cudaStream_t);
+                                      const bf16*, bf16*, int, bf16*, int, bf16*, int, float*, cudaStream_t, const uint32_t*);
 template int attention_bwd_pipe<f16>(int, int, int, int, const f16*, int, const f16*, int, const f16*, int, const f16*, int, const float*, DropSpec, const f16*,
-                                     f16*, int, f16*, int, f16*, int, float*, cudaStream_t);
+                                     f16*, int, f16*, int, f16*, int, float*, cudaStream_t, const uint32_t*);
 
 }  // namespace seqdiff

@@ -111,7 +111,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO, const float* __restrict__ key_mask, int heads, int Lq,
                       int Lk, int P, uint32_t fmt, int nqb, int n_items, unsigned long long* __restrict__ trace, const int* __restrict__ q_off,
-                      const int* __restrict__ k_off, const int* __restrict__ q_len, int Lk_mask, T* __restrict__ out_raw, const DropSpec dr) {
+                      const int* __restrict__ k_off, const int* __restrict__ q_len, int Lk_mask, T* __restrict__ out_raw, const DropSpec dr,
+                      uint32_t* __restrict__ keep_out) {
+  // keep_out (DROP, Lq / Lk <= 128, optional): the dropout mask of item (b, h) as bits -- word ((b * heads + h) * 128 + row) * 4 + kc holds
+  // keys 32 kc .. 32 kc + 31 of query `row` -- so that the backward kernel reads 8 bytes per thread instead of regenerating 16 Philox calls
   // q_off != NULL: packed (ragged) batch -- graph b's rows start at q_off[b] / k_off[b] of the packed q / k / v matrices, Lq / Lk are
   // the largest lengths of the batch, key_mask keeps its padded pitch Lk_mask, and output rows are stored per thread with a
   // q_len[b] predicate (a bulk tile store would spill into the next graph's rows).
@@ -454,14 +457,20 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const size_t e_row = ((static_cast<size_t>(w.b) * heads + w.h) * Lq + w.q0 + row) * Lk + kb * kPK + 32 * hf;
           auto drop_chunk = [&](auto c_tag) {
             constexpr int c = decltype(c_tag)::value;
+            uint32_t bits = 0u;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const uint64_t qd = (e_row + 64 * c + 4 * j4) >> 2;
               uint32_t w4[4] = {static_cast<uint32_t>(qd), static_cast<uint32_t>(qd >> 32), dr.site, dr.step};
               philox4x32_10(w4, static_cast<uint32_t>(dr.seed), static_cast<uint32_t>(dr.seed >> 32));
 #pragma unroll
-              for (int u = 0; u < 4; ++u) t[c][4 * j4 + u] *= (w4[u] >= thr ? sc : 0.f);
+              for (int u = 0; u < 4; ++u) {
+                const bool kp = w4[u] >= thr;
+                t[c][4 * j4 + u] *= (kp ? sc : 0.f);
+                bits |= (kp ? 1u : 0u) << (4 * j4 + u);
+              }
             }
+            if (keep_out) keep_out[((static_cast<size_t>(w.b) * heads + w.h) * 128 + row) * 4 + (hf + 2 * c)] = bits;
           };
           if (cv0) drop_chunk(std::integral_constant<int, 0>{});
           if (cv1) drop_chunk(std::integral_constant<int, 1>{});
@@ -531,7 +540,8 @@ template <> struct PipeFmt<bf16> { static constexpr int v = 1; };
 
 template <typename T, bool REL, bool DROP = false>
 static int launch_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* E, int P,
-                       const float* mask, T* out, cudaStream_t s, const AttnPack* pk, const DropSpec dr = DropSpec{0.f, 0u, 0u, 0ull}) {
+                       const float* mask, T* out, cudaStream_t s, const AttnPack* pk, const DropSpec dr = DropSpec{0.f, 0u, 0u, 0ull},
+                       uint32_t* keep_out = nullptr) {
   using C = PipeCfg<REL>;
   auto kfn = attention_pipe_kernel<T, REL, DROP>;
   static bool configured = false;
@@ -555,7 +565,7 @@ static int launch_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, co
   int grid = n_items < num_sms() ? n_items : num_sms();
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   SD_CUDA(launch_k(kfn, dim3(grid), dim3(kPipeThreads), C::kBytes, s, tq, tk, tv, te, to, mask, heads, Lq, Lk, P, static_cast<uint32_t>(fmt), nqb,
-                   n_items, g_attn_trace, pk ? pk->q_off : nullptr, pk ? pk->k_off : nullptr, pk ? pk->q_len : nullptr, pk ? pk->Lk_mask : Lk, out, dr));
+                   n_items, g_attn_trace, pk ? pk->q_off : nullptr, pk ? pk->k_off : nullptr, pk ? pk->q_len : nullptr, pk ? pk->Lk_mask : Lk, out, dr, keep_out));
   SD_LAUNCHED(DROP ? (REL ? "attention_pipe_rel_drop" : "attention_pipe_norel_drop") : (REL ? "attention_pipe_rel" : "attention_pipe_norel"), s);
   return SEQDIFF_OK;
 }
@@ -574,18 +584,19 @@ int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const 
 // training-mode forward (attention-probability dropout inside the kernel); needs Lk % 4 == 0
 template <typename T>
 int attention_pipe_dropout(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
-                           const float* key_mask, DropSpec dr, T* out, cudaStream_t s) {
+                           const float* key_mask, DropSpec dr, T* out, cudaStream_t s, uint32_t* keep_out) {
   SD_CHECK(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "empty attention");
+  SD_CHECK(!keep_out || (Lq <= 128 && Lk <= 128), "the keep-bit buffer covers one 128 x 128 tile per (graph, head)");
   SD_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "row strides must be multiples of 8 elements");
   SD_CHECK((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) % 16 == 0, "q/k/v must be 16B aligned");
   SD_CHECK(!dist_emb || (Lq <= P && Lk <= P), "sequence longer than max_position_embeddings");
   SD_CHECK(Lk % 4 == 0, "dropout in the pipelined kernel: Lk must be a multiple of 4 (one Philox call per 4 keys of a row)");
   SD_CHECK(dr.p > 0.f && dr.p < 1.f, "dropout probability must be in (0, 1)");
-  if (dist_emb) return launch_pipe<T, true, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, nullptr, dr);
-  return launch_pipe<T, false, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, nullptr, dr);
+  if (dist_emb) return launch_pipe<T, true, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, nullptr, dr, keep_out);
+  return launch_pipe<T, false, true>(B, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, dist_emb, P, key_mask, out, s, nullptr, dr, keep_out);
 }
-template int attention_pipe_dropout<bf16>(int, int, int, int, const bf16*, int, const bf16*, int, const bf16*, int, const bf16*, int, const float*, DropSpec, bf16*, cudaStream_t);
-template int attention_pipe_dropout<f16>(int, int, int, int, const f16*, int, const f16*, int, const f16*, int, const f16*, int, const float*, DropSpec, f16*, cudaStream_t);
+template int attention_pipe_dropout<bf16>(int, int, int, int, const bf16*, int, const bf16*, int, const bf16*, int, const bf16*, int, const float*, DropSpec, bf16*, cudaStream_t, uint32_t*);
+template int attention_pipe_dropout<f16>(int, int, int, int, const f16*, int, const f16*, int, const f16*, int, const f16*, int, const float*, DropSpec, f16*, cudaStream_t, uint32_t*);
 template int attention_pipe<bf16>(int, int, int, int, const bf16*, int, const bf16*, int, const bf16*, int, const bf16*, int, const float*, bf16*, cudaStream_t, const AttnPack*);
 template int attention_pipe<f16>(int, int, int, int, const f16*, int, const f16*, int, const f16*, int, const f16*, int, const float*, f16*, cudaStream_t, const AttnPack*);
 

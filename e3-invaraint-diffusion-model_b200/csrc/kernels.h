@@ -132,11 +132,14 @@ int attention_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const 
 bool attention_bwd_pipe_usable(int Lq, int Lk, const void* dist_emb, float p_drop);
 template <typename T>
 int attention_bwd_pipe(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb, int P,
-                       const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s);
+                       const float* key_mask, DropSpec dr, const T* dout, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* dE, cudaStream_t s,
+                       const uint32_t* keep_in = nullptr);
 // the same kernel with the training-mode attention-probability dropout applied to P (masks: DropSpec / Philox, philox.cuh); Lk % 4 == 0
 template <typename T>
 int attention_pipe_dropout(int B, int heads, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const T* dist_emb,
-                           int P, const float* key_mask, DropSpec dr, T* out, cudaStream_t s);
+                           int P, const float* key_mask, DropSpec dr, T* out, cudaStream_t s, uint32_t* keep_out = nullptr);
+// keep_out / keep_in: [B * heads][128 rows][4] words, bit j of word kc = "key 32 kc + j of that query is kept" (Lq, Lk <= 128); written by the
+// forward, read by attention_bwd_pipe instead of regenerating the Philox stream
 
 
 // ---- reverse_step.cu --------------------------------------------------------------------------------

@@ -254,12 +254,14 @@ template <typename T> struct SETape {
   T *u_pre, *u, *mod, *qkv, *ctx, *m1_pre, *m1;
   float *o, *m2;
   std::vector<Segment> segs;
+  std::vector<uint32_t*> keep;  // per segment: the attention dropout mask as bits (forward -> backward), or NULL
   DropSpec d_attn, d_o, d_m1, d_m2;
 };
 template <typename T> struct LayerTape {
   Act2<T> h, h1, h2, h3;
   T *qkv, *ctx, *cq, *ctx2, *f_pre, *f;
   float *o1, *o2, *o3;
+  uint32_t *keep_self = nullptr, *keep_cross = nullptr;
   DropSpec d_attn, d_o1, d_cattn, d_o2, d_o3;
 };
 
@@ -299,6 +301,7 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     need += 6 * al256(MtH * 4);                                       // fp32 gradient streams
     need += 2 * al256(MtH * 6 * es) + al256(MtH * 6 * es) + al256(MtH * 4 * es);  // gradient operands + transposes
     need += al256(static_cast<size_t>(B) * 6 * H * 4) + 4 * al256(static_cast<size_t>(B) * 6 * H * es) + (1 << 20);
+    need += static_cast<size_t>(2 * NL + 3) * al256(static_cast<size_t>(2 * B) * heads * 128 * 4 * sizeof(uint32_t));  // attention keep bits
     need = 2 * need + (64u << 20);  // the tape is carved out while kernels are already being launched: keep a wide safety margin
   }
   if (need > tws_bytes) {
@@ -319,13 +322,19 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     SD_TRY(gemm_any<T>(M, N, K, X, wsel<T>(W), bias, nullptr, O, true, s));
     return dropout_add(O, resid, static_cast<size_t>(M) * N, dr, s);
   };
+  // the attention dropout mask travels from the forward to the backward kernel as bits (2 KB per (graph, head)) when both run on the
+  // tcgen05 kernels; every other combination regenerates it from the Philox stream
+  auto keep_buf = [&](int nb, int Lq, int Lk) -> uint32_t* {
+    if (!k16 || simt_attn || wmma_fwd || a.p_attn <= 0.f || Lk % 4 != 0 || !attention_bwd_pipe_usable(Lq, Lk, nullptr, a.p_attn)) return nullptr;
+    return ar.take<uint32_t>(static_cast<size_t>(nb) * heads * 128 * 4);
+  };
   auto attn_fwd = [&](int nb, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const Wt* E, const float* mask,
-                      const DropSpec& dr, T* out) -> int {
+                      const DropSpec& dr, T* out, uint32_t* keep) -> int {
     const T* e = E ? static_cast<const T*>(wsel<T>(*E)) : nullptr;
     if (dr.p <= 0.f) return attention<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, out, s);
     if constexpr (k16) {
       // the pipelined tcgen05 kernel of the inference path with the dropout mask applied to P (7x faster than the wmma forward)
-      if (!simt_attn && !wmma_fwd && Lk % 4 == 0) return attention_pipe_dropout<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s);
+      if (!simt_attn && !wmma_fwd && Lk % 4 == 0) return attention_pipe_dropout<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s, keep);
       if (!simt_attn) return attention_train_fwd_tc<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s);
     }
     return attention_train_fwd<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, out, s);
@@ -391,8 +400,9 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     for (const Segment& sg : tp.segs) {
       const T* base = tp.qkv + static_cast<size_t>(sg.row0) * 3 * H;
       DropSpec dr = tp.d_attn;
+      tp.keep.push_back(keep_buf(sg.B, sg.L, sg.L));
       SD_TRY(attn_fwd(sg.B, sg.L, sg.L, base, 3 * H, base + H, 3 * H, base + 2 * H, 3 * H, cfg.relative_key ? &w.attn.E : nullptr, sg.mask, dr,
-                      tp.ctx + static_cast<size_t>(sg.row0) * H));
+                      tp.ctx + static_cast<size_t>(sg.row0) * H, tp.keep.back()));
     }
     SD_TRY(lin_res(M, H, H, tp.ctx, w.attn.out, w.attn.out_b, tp.x.s, tp.o, tp.d_o));
     SD_TRY(ln_modulate<T>(tp.o, M, H, true, w.attn.ln_w, w.attn.ln_b, eps, tp.x.s, tp.mod, tp.mod_div, 0, tp.x1.s, tp.x1.t_out(), s));
@@ -446,13 +456,15 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     tp.d_o2 = hid();
     tp.d_o3 = hid();
     SD_TRY(lin_T(Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, tp.qkv));
+    tp.keep_self = keep_buf(B, Ll, Ll);
     SD_TRY(attn_fwd(B, Ll, Ll, tp.qkv, 3 * H, tp.qkv + H, 3 * H, tp.qkv + 2 * H, 3 * H, cfg.relative_key ? &w.self.E : nullptr, a.lig_mask, tp.d_attn,
-                    tp.ctx));
+                    tp.ctx, tp.keep_self));
     SD_TRY(lin_res(Ml, H, H, tp.ctx, w.self.out, w.self.out_b, h.s, tp.o1, tp.d_o1));
     SD_TRY(layernorm<T>(tp.o1, Ml, H, w.self.ln_w, w.self.ln_b, eps, tp.h1.s, tp.h1.t_out(), nullptr, s));
     SD_TRY(lin_T(Ml, H, H, tp.h1.t, w.cq, w.cq_b, tp.cq));
     const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
-    SD_TRY(attn_fwd(B, Ll, Lr, tp.cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, nullptr, a.rec_mask, tp.d_cattn, tp.ctx2));
+    tp.keep_cross = keep_buf(B, Ll, Lr);
+    SD_TRY(attn_fwd(B, Ll, Lr, tp.cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, nullptr, a.rec_mask, tp.d_cattn, tp.ctx2, tp.keep_cross));
     SD_TRY(lin_res(Ml, H, H, tp.ctx2, w.cout, w.cout_b, tp.h1.s, tp.o2, tp.d_o2));
     SD_TRY(layernorm<T>(tp.o2, Ml, H, w.cln_w, w.cln_b, eps, tp.h2.s, tp.h2.t_out(), nullptr, s));
     SD_TRY(lin_T(Ml, I, H, tp.h2.t, w.inter, w.inter_b, tp.f_pre));
@@ -525,11 +537,11 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     return SEQDIFF_OK;
   };
   auto attn_bwd = [&](int nb, int Lq, int Lk, const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, const Wt* E, const float* mask,
-                      const DropSpec& dr, const T* dctx, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* gE) -> int {
+                      const DropSpec& dr, const T* dctx, T* dq, int lddq, T* dk, int lddk, T* dv, int lddv, float* gE, const uint32_t* keep) -> int {
     const T* e = E ? static_cast<const T*>(wsel<T>(*E)) : nullptr;
     if constexpr (k16) {
       if (!simt_attn && attention_bwd_pipe_usable(Lq, Lk, e, dr.p))  // tcgen05 backward
-        return attention_bwd_pipe<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s);
+        return attention_bwd_pipe<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s, keep);
       if (!simt_attn) return attention_bwd_tc<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s);
     }
     return attention_bwd<T>(nb, heads, Lq, Lk, q, ldq, k, ldk, v, ldv, e, P, mask, dr, dctx, dq, lddq, dk, lddk, dv, lddv, gE, s);
@@ -557,12 +569,13 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
                               g(p + ".attn.output.LayerNorm.weight"), g(p + ".attn.output.LayerNorm.bias"), s));  // s2 = d(o); tmp = d(o) + d(x1)
     SD_TRY(grad_cast<T>(s2, MH, tp.d_o, gT, s));
     SD_TRY(linear_bwd(M, H, H, gT, tp.ctx, w.attn.out, g(p + ".attn.output.dense.weight"), g(p + ".attn.output.dense.bias"), 1, gT2, nullptr));  // d(ctx)
-    for (const Segment& sg : tp.segs) {
+    for (size_t si = 0; si < tp.segs.size(); ++si) {
+      const Segment& sg = tp.segs[si];
       const T* base = tp.qkv + static_cast<size_t>(sg.row0) * 3 * H;
       T* dbase = gT + static_cast<size_t>(sg.row0) * 3 * H;
       SD_TRY(attn_bwd(sg.B, sg.L, sg.L, base, 3 * H, base + H, 3 * H, base + 2 * H, 3 * H, cfg.relative_key ? &w.attn.E : nullptr, sg.mask, tp.d_attn,
                       gT2 + static_cast<size_t>(sg.row0) * H, dbase, 3 * H, dbase + H, 3 * H, dbase + 2 * H, 3 * H,
-                      cfg.relative_key ? g(p + ".attn.self.distance_embedding.weight") : nullptr));
+                      cfg.relative_key ? g(p + ".attn.self.distance_embedding.weight") : nullptr, si < tp.keep.size() ? tp.keep[si] : nullptr));
     }
     SD_TRY(linear_bwd(M, 3 * H, H, gT, tp.x.t, w.attn.qkv, g(p + ".attn.self.query.weight"), g(p + ".attn.self.query.bias"), 2, s1, tmp));  // d(x)
     // adaLN_modulation: mod = Linear2(SiLU(Linear0(c)))
@@ -615,7 +628,7 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
       const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
       T* dkbase = dkv_all + static_cast<size_t>(i) * 2 * H;
       SD_TRY(attn_bwd(B, Ll, Lr, tp.cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, nullptr, a.rec_mask, tp.d_cattn, gT2, gT, H, dkbase, NL * 2 * H,
-                      dkbase + H, NL * 2 * H, nullptr));
+                      dkbase + H, NL * 2 * H, nullptr, tp.keep_cross));
     }
     SD_TRY(linear_bwd(Ml, H, H, gT, tp.h1.t, w.cq, g(p + ".crossattention.self.query.weight"), g(p + ".crossattention.self.query.bias"), 2, s2, s1));  // d(h1)
     // h1 = LN(o1); o1 = dropout(ctx Wo^T + b) + h; ctx = self-attention(h Wqkv^T)
@@ -623,7 +636,7 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     SD_TRY(grad_cast<T>(s1, MlH, tp.d_o1, gT, s));
     SD_TRY(linear_bwd(Ml, H, H, gT, tp.ctx, w.self.out, g(p + ".attention.output.dense.weight"), g(p + ".attention.output.dense.bias"), 1, gT2, nullptr));
     SD_TRY(attn_bwd(B, Ll, Ll, tp.qkv, 3 * H, tp.qkv + H, 3 * H, tp.qkv + 2 * H, 3 * H, cfg.relative_key ? &w.self.E : nullptr, a.lig_mask, tp.d_attn, gT2, gT,
-                    3 * H, gT + H, 3 * H, gT + 2 * H, 3 * H, cfg.relative_key ? g(p + ".attention.self.distance_embedding.weight") : nullptr));
+                    3 * H, gT + H, 3 * H, gT + 2 * H, 3 * H, cfg.relative_key ? g(p + ".attention.self.distance_embedding.weight") : nullptr, tp.keep_self));
     SD_TRY(linear_bwd(Ml, 3 * H, H, gT, tp.h.t, w.self.qkv, g(p + ".attention.self.query.weight"), g(p + ".attention.self.query.bias"), 2, s2, s1));  // d(h)
     float* t_ = cur;
     cur = s2;
