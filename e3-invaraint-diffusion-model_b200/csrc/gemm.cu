@@ -947,12 +947,16 @@ int gemm_16(int M, int N, int K, const void* A, int a_fmt, const void* W, int w_
           cudaGraphDestroy(graph);
           SD_CUDA(ce);
           float ms = 0.f;
-          ce = cudaGraphLaunch(exec, ts);
-          if (ce == cudaSuccess) ce = cudaEventRecord(e0, ts);
-          if (ce == cudaSuccess) ce = cudaGraphLaunch(exec, ts);
-          if (ce == cudaSuccess) ce = cudaEventRecord(e1, ts);
-          if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
-          if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
+          ce = cudaGraphLaunch(exec, ts);  // warm-up replay
+          for (int rep = 0; rep < 3 && ce == cudaSuccess; ++rep) {  // best of three timed replays: one noisy sample flipped 128 / 192 / 256 picks between runs
+            float ms1 = 0.f;
+            ce = cudaEventRecord(e0, ts);
+            if (ce == cudaSuccess) ce = cudaGraphLaunch(exec, ts);
+            if (ce == cudaSuccess) ce = cudaEventRecord(e1, ts);
+            if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
+            if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms1, e0, e1);
+            if (rep == 0 || ms1 < ms) ms = ms1;
+          }
           cudaGraphExecDestroy(exec);
           SD_CUDA(ce);
           if (!cfg || ms < best_ms) { cfg = cand; best_ms = ms; }
