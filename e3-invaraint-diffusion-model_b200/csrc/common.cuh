@@ -520,6 +520,7 @@ int debug_guard_check(cudaStream_t s, int* n_bands, int* n_broken);
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
+int pdl_scope_exchange(int mode);  // sets the calling thread's scope mode (0 = none), returns the previous one
 int pdl_mode();  // effective mode of this launch: 0 off, 1 every launch, 2 only light successors (< 64 KB of shared memory), 3 only heavy ones
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kc(int cluster_x, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {

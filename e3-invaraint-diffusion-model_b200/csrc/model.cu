@@ -90,6 +90,11 @@ struct PdlScope {
   explicit PdlScope(int mode = 1) : prev(g_pdl_scope) { if (mode) g_pdl_scope = mode; }
   ~PdlScope() { g_pdl_scope = prev; }
 };
+int pdl_scope_exchange(int mode) {  // for the other translation units (train.cu): sets the mode, returns the previous one
+  const int prev = g_pdl_scope;
+  g_pdl_scope = mode;
+  return prev;
+}
 // Sequence path: a step is ~90 kernels with a fixed cost of ~7 us each (B = 1: 685 us per step).  When the grids are a handful of
 // CTAs the successor's prologue (barrier init, TMEM allocation, descriptor prefetch) can run on idle SMs under the predecessor:
 // measured on B200 (profiles/pdl_small_r02.log) B = 1: 685 -> 616 us, B = 4: 711 -> 665 us per step; from B = 16 on the persistent
@@ -970,6 +975,7 @@ int Model::forward(int precision, int B, int Ll, int Lr, const float* timestep, 
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
   SD_CUDA(cudaSetDevice(device));
   SD_TRY(ensure_workspace(workspace_need(precision, B, Ll, Lr)));
+  if (g_profiling) profile_mark("__begin__", s);  // host time between two calls is not the first kernel's
   const PdlScope pdl_scope(pdl_auto_mode(pk ? static_cast<long long>(pk->Ml) + pk->Mr : static_cast<long long>(B) * (Ll + Lr)));
   switch (precision) {
     case SEQDIFF_FP32:
@@ -1359,6 +1365,7 @@ int Model::struct_forward(int precision, int B, int Ll, int Lr, const float* tim
   if (cfg.relative_key) SD_CHECK(Ll <= cfg.max_position_embeddings && Lr <= cfg.max_position_embeddings, "Length exceed");
   SD_CUDA(cudaSetDevice(device));
   SD_TRY(ensure_workspace(struct_workspace_need(precision, B, Ll, Lr)));
+  if (g_profiling) profile_mark("__begin__", s);
   switch (precision) {
     case SEQDIFF_FP32:
       return struct_forward_t<float>(1, B, Ll, Lr, timestep, step_ptr, noised, lig_mask, rec_seq_in, rec_angle, rec_mask, out, phases, s);

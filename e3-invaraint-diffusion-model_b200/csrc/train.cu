@@ -68,6 +68,7 @@ template <typename T> static const void* wsel(const Wt& w) {
 template <typename T>
 __global__ void __launch_bounds__(256) embed_post_kernel(float* __restrict__ v, const float* __restrict__ te, int L, int H, size_t n8, DropSpec dr,
                                                          float* __restrict__ out32, T* __restrict__ outT) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float x[8], keep[8];
     load8<float>(v + 8 * i, x);
@@ -94,6 +95,7 @@ static int embed_post(float* v, const float* te, int L, int H, size_t n, DropSpe
   return SEQDIFF_OK;
 }
 __global__ void concat_masks_kernel(float* dst, const float* a, int na, const float* b, int nb) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += gridDim.x * blockDim.x) dst[i] = i < na ? a[i] : b[i - na];
 }
 
@@ -512,20 +514,25 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   SD_CHECK(ar.ok, "training workspace under-estimated");
 
   // backward of y = x W^T + b.  dY: T [M,N]; X: T [M,K].  dx_kind 0: none; 1: T [M,K]; 2: fp32 [M,K] (+ resid)
+  // 16-bit modes: dW = dY^T X straight from the row-major tensors (both operands MN-major for the MMA, gemm_16_tn), db by a column-sum
+  // kernel -- the two 16-bit transposes per Linear (11 % of the step) are gone.  SEQDIFF_WGRAD_TN=0 restores the transposed form.
+  static const bool wgrad_tn = [] { const char* e = getenv("SEQDIFF_WGRAD_TN"); return !e || e[0] != '0'; }();
+  auto tn_ok = [&](int N, int K) { return k16 && wgrad_tn && N % 8 == 0 && K % 128 == 0; };
+  // LayerNorm backward that also emits the 16-bit dY operand and the bias gradient of the Linear in front of it (one launch instead of
+  // layernorm_bwd + grad_cast + colsum).  SEQDIFF_LN_BWD_FUSE=0 restores the three launches.
+  static const bool ln_bwd_fuse = [] { const char* e = getenv("SEQDIFF_LN_BWD_FUSE"); return !e || e[0] != '0'; }();
   auto linear_bwd = [&](int M, int N, int K, const T* dY, const T* X, const Wt& W, float* gW, float* gb, int dx_kind, void* dX,
-                        const float* resid) -> int {
-    // 16-bit modes: dW = dY^T X straight from the row-major tensors (both operands MN-major for the MMA, gemm_16_tn), db by a column-sum
-    // kernel -- the two 16-bit transposes per Linear (11 % of the step) are gone.  SEQDIFF_WGRAD_TN=0 restores the transposed form.
-    static const bool wgrad_tn = [] { const char* e = getenv("SEQDIFF_WGRAD_TN"); return !e || e[0] != '0'; }();
+                        const float* resid, bool db_done = false) -> int {
     if constexpr (k16) {
-      if (wgrad_tn && N % 8 == 0 && K % 128 == 0) {
+      if (tn_ok(N, K)) {
         static const bool splitk_tn = [] { const char* e = getenv("SEQDIFF_WGRAD_SPLITK"); return !e || e[0] != '0'; }();
-        SD_TRY(colsum_add<T>(dY, M, N, gb, s));
+        if (!db_done) SD_TRY(colsum_add<T>(dY, M, N, gb, s));
         SD_TRY(gemm_16_tn(N, K, M, dY, X, TFmt<T>::v, d_zero_bias, gW, s, splitk_tn ? -1 : 1));
         if (dx_kind) SD_TRY(gemm_any<T>(M, K, N, dY, W.t, d_zero_bias, resid, dX, dx_kind == 2, s));
         return SEQDIFF_OK;
       }
     }
+    SD_CHECK(!db_done, "linear_bwd: fused bias gradient needs the in-place weight-gradient form");
     const int Mp = (M + 7) & ~7;  // contraction length of dW, padded with zero columns to a 16 B pitch
     SD_TRY(transpose_colsum<T>(dY, M, N, trA, gb, s, Mp));
     SD_TRY(transpose_colsum<T>(X, M, K, trB, nullptr, s, Mp));
@@ -609,21 +616,32 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   SD_TRY(bucket_done(n_bk - 1));
   // decoder layers, last to first
   float *cur = dA, *s1 = dB, *s2 = dC;
+  // post-LN sublayer h = LN(o), o = dropout(x W^T + b) + resid: d(o) in fp32 (it is also the gradient of resid) and, as the Linear's dY,
+  // masked by the dropout site `dr` in the operand type (gT).  K = fan-in of that Linear (decides the weight-gradient form, tn_ok).
+  auto ln_fused = [&](int K) { return ln_bwd_fuse && tn_ok(H, K); };
+  auto ln_bwd = [&](const float* dh, const float* o, const float* gamma, float* d_o, float* dgam, float* dbet, const DropSpec& dr, float* dbias,
+                    int K) -> int {
+    if constexpr (k16) {
+      if (ln_fused(K)) return layernorm_bwd_cast<T>(dh, o, Ml, H, gamma, eps, d_o, dgam, dbet, dr, gT, dbias, s);
+    }
+    SD_TRY(layernorm_bwd(dh, o, Ml, H, gamma, eps, d_o, dgam, dbet, s));
+    return grad_cast<T>(d_o, MlH, dr, gT, s);
+  };
   for (int i = NL - 1; i >= 0; --i) {
     const LayerW& w = layers[i];
     LayerTape<T>& tp = lt[i];
     const std::string p = "decoder.layer." + std::to_string(i);
     const size_t MlI = static_cast<size_t>(Ml) * I;
     // h3 = LN(o3); o3 = dropout(f Wod^T + b) + h2; f = GELU(h2 Wi^T + b)
-    SD_TRY(layernorm_bwd(cur, tp.o3, Ml, H, w.oln_w, eps, s1, g(p + ".output.LayerNorm.weight"), g(p + ".output.LayerNorm.bias"), s));
-    SD_TRY(grad_cast<T>(s1, MlH, tp.d_o3, gT, s));
-    SD_TRY(linear_bwd(Ml, H, I, gT, tp.f, w.outd, g(p + ".output.dense.weight"), g(p + ".output.dense.bias"), 1, gT2, nullptr));
+    SD_TRY(ln_bwd(cur, tp.o3, w.oln_w, s1, g(p + ".output.LayerNorm.weight"), g(p + ".output.LayerNorm.bias"), tp.d_o3, g(p + ".output.dense.bias"), I));
+    SD_TRY(linear_bwd(Ml, H, I, gT, tp.f, w.outd, g(p + ".output.dense.weight"), g(p + ".output.dense.bias"), 1, gT2, nullptr, ln_fused(I)));
     SD_TRY((act_bwd<T, T>(gT2, tp.f_pre, MlI, 1, nodrop, gT, s)));
     SD_TRY(linear_bwd(Ml, I, H, gT, tp.h2.t, w.inter, g(p + ".intermediate.dense.weight"), g(p + ".intermediate.dense.bias"), 2, s2, s1));  // d(h2)
     // h2 = LN(o2); o2 = dropout(ctx2 Wco^T + b) + h1; ctx2 = cross-attention(q = h1 Wcq^T, k | v = receptor projections)
-    SD_TRY(layernorm_bwd(s2, tp.o2, Ml, H, w.cln_w, eps, s1, g(p + ".crossattention.output.LayerNorm.weight"), g(p + ".crossattention.output.LayerNorm.bias"), s));
-    SD_TRY(grad_cast<T>(s1, MlH, tp.d_o2, gT, s));
-    SD_TRY(linear_bwd(Ml, H, H, gT, tp.ctx2, w.cout, g(p + ".crossattention.output.dense.weight"), g(p + ".crossattention.output.dense.bias"), 1, gT2, nullptr));
+    SD_TRY(ln_bwd(s2, tp.o2, w.cln_w, s1, g(p + ".crossattention.output.LayerNorm.weight"), g(p + ".crossattention.output.LayerNorm.bias"), tp.d_o2,
+                  g(p + ".crossattention.output.dense.bias"), H));
+    SD_TRY(linear_bwd(Ml, H, H, gT, tp.ctx2, w.cout, g(p + ".crossattention.output.dense.weight"), g(p + ".crossattention.output.dense.bias"), 1, gT2, nullptr,
+                      ln_fused(H)));
     {
       const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
       T* dkbase = dkv_all + static_cast<size_t>(i) * 2 * H;
@@ -632,9 +650,10 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     }
     SD_TRY(linear_bwd(Ml, H, H, gT, tp.h1.t, w.cq, g(p + ".crossattention.self.query.weight"), g(p + ".crossattention.self.query.bias"), 2, s2, s1));  // d(h1)
     // h1 = LN(o1); o1 = dropout(ctx Wo^T + b) + h; ctx = self-attention(h Wqkv^T)
-    SD_TRY(layernorm_bwd(s2, tp.o1, Ml, H, w.self.ln_w, eps, s1, g(p + ".attention.output.LayerNorm.weight"), g(p + ".attention.output.LayerNorm.bias"), s));
-    SD_TRY(grad_cast<T>(s1, MlH, tp.d_o1, gT, s));
-    SD_TRY(linear_bwd(Ml, H, H, gT, tp.ctx, w.self.out, g(p + ".attention.output.dense.weight"), g(p + ".attention.output.dense.bias"), 1, gT2, nullptr));
+    SD_TRY(ln_bwd(s2, tp.o1, w.self.ln_w, s1, g(p + ".attention.output.LayerNorm.weight"), g(p + ".attention.output.LayerNorm.bias"), tp.d_o1,
+                  g(p + ".attention.output.dense.bias"), H));
+    SD_TRY(linear_bwd(Ml, H, H, gT, tp.ctx, w.self.out, g(p + ".attention.output.dense.weight"), g(p + ".attention.output.dense.bias"), 1, gT2, nullptr,
+                      ln_fused(H)));
     SD_TRY(attn_bwd(B, Ll, Ll, tp.qkv, 3 * H, tp.qkv + H, 3 * H, tp.qkv + 2 * H, 3 * H, cfg.relative_key ? &w.self.E : nullptr, a.lig_mask, tp.d_attn, gT2, gT,
                     3 * H, gT + H, 3 * H, gT + 2 * H, 3 * H, cfg.relative_key ? g(p + ".attention.self.distance_embedding.weight") : nullptr, tp.keep_self));
     SD_TRY(linear_bwd(Ml, 3 * H, H, gT, tp.h.t, w.self.qkv, g(p + ".attention.self.query.weight"), g(p + ".attention.self.query.bias"), 2, s2, s1));  // d(h)
@@ -676,6 +695,16 @@ int Model::train_step(const TrainArgs& a, cudaStream_t s) {
     train_prec = a.precision;
     SD_TRY(finalize(s));
   }
+  if (g_profiling) profile_mark("__begin__", s);  // host time between two steps is not the first kernel's
+  // SEQDIFF_TRAIN_PDL=3: programmatic dependent launch of the heavy kernels of the step (tcgen05 GEMMs and attention: their prologue --
+  // barrier init, TMEM allocation, descriptor prefetch -- runs under the predecessor's tail; every kernel of the step starts with
+  // griddepcontrol.wait, so any mode is safe).  Off by default.
+  static const int train_pdl = [] { const char* e = getenv("SEQDIFF_TRAIN_PDL"); return e && e[0] >= '1' && e[0] <= '3' ? e[0] - '0' : 0; }();
+  struct Scope {
+    const int prev;
+    explicit Scope(int m) : prev(pdl_scope_exchange(m)) {}
+    ~Scope() { pdl_scope_exchange(prev); }
+  } pdl_scope(train_pdl);
   switch (a.precision) {
     case SEQDIFF_FP32: return train_t<float>(1, a, s);
     case SEQDIFF_BF16: return train_t<bf16>(1, a, s);

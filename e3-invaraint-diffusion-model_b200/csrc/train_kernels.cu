@@ -81,6 +81,7 @@ __device__ __forceinline__ void ln_bwd_core(const float (&xhat)[VPL][8], float (
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_colsum_kernel(const T* __restrict__ in, int rows, int cols, T* __restrict__ out, int pitch,
                                                                float* __restrict__ colsum) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   __shared__ float tile[64][65];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
@@ -133,6 +134,7 @@ __device__ __forceinline__ int acc_slot_of_col(int e) { return acc_slot(e >> 8, 
 // meet in shared memory, one atomic per column and CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int rows, int cols, float* __restrict__ colsum) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   __shared__ float part[8][256];
   const int oct = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + oct * 8;
@@ -173,6 +175,7 @@ template int colsum_add<f16>(const f16*, int, int, float*, cudaStream_t);
 // fp32 [rows, cols] -> T [cols, rows] (weights: the fp32 master -> the transposed operand copy the dgrad GEMMs read)
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ in, int rows, int cols, T* __restrict__ out) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   __shared__ float tile[64][65];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
@@ -213,6 +216,7 @@ __device__ __forceinline__ float silu_grad(float x) {
 // a = dropout(act(z)); kind 1 = erf-GELU, 2 = SiLU.  8 elements per thread.
 template <typename T>
 __global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ z, size_t n8, int kind, DropSpec dr, T* __restrict__ a) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float v[8];
     load8<T>(z + 8 * i, v);
@@ -236,6 +240,7 @@ int act_fwd(const T* z, size_t n, int kind, DropSpec dr, T* a, cudaStream_t s) {
 template <typename T, typename TG>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const TG* __restrict__ da, const T* __restrict__ z, size_t n8, int kind, DropSpec dr,
                                                       T* __restrict__ dz) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float g[8], v[8], keep[8];
     load8<TG>(da + 8 * i, g);
@@ -257,6 +262,7 @@ int act_bwd(const TG* da, const T* z, size_t n, int kind, DropSpec dr, T* dz, cu
 }
 // o = dropout(d) + resid (fp32, in place on d): the hidden-state dropout that sits between a Linear and its residual add
 __global__ void __launch_bounds__(256) dropout_add_kernel(float* __restrict__ d, const float* __restrict__ resid, size_t n8, DropSpec dr) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float v[8], r[8], keep[8];
     load8<float>(d + 8 * i, v);
@@ -283,6 +289,7 @@ int dropout_add(float* d, const float* resid, size_t n, DropSpec dr, cudaStream_
 // gT = T(g * keep): the fp32 gradient of a (dropout-ed) Linear output as the 16-bit operand of its backward GEMMs
 template <typename T>
 __global__ void __launch_bounds__(256) grad_cast_kernel(const float* __restrict__ g, size_t n8, DropSpec dr, T* __restrict__ out) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float v[8], keep[8];
     load8<float>(g + 8 * i, v);
@@ -328,19 +335,28 @@ __device__ __forceinline__ void flush_feature_sums(float (&acc)[VPL][8], float* 
   __syncthreads();
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(kTrThreads) layernorm_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ o, int M, int H,
+// FUSE: the gradient d_o is also the dY of the Linear that produced o (o = dropout(x W^T + b) + resid), so the same pass writes the
+// 16-bit GEMM operand gT = T(d_o * keep) and adds its column sums (the bias gradient, summed over the values the weight-gradient GEMM
+// reads) into dbias -- one grad_cast and one colsum launch less per LayerNorm, and d_o is not re-read twice.
+template <int VPL, typename T, bool FUSE, int MINB = 1>
+__global__ void __launch_bounds__(kTrThreads, MINB) layernorm_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ o, int M, int H,
                                                                    const float* __restrict__ gamma, float eps, float* __restrict__ d_o,
-                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float sacc[];  // [2][H]
-  for (int e = threadIdx.x; e < 2 * H; e += kTrThreads) sacc[e] = 0.f;
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, DropSpec dr,
+                                                                   T* __restrict__ gT, float* __restrict__ dbias) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  extern __shared__ float sacc[];  // [2 (+1)][H]
+  for (int e = threadIdx.x; e < (FUSE ? 3 : 2) * H; e += kTrThreads) sacc[e] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float ag[VPL][8], ab[VPL][8];
+  float ag[VPL][8], ab[VPL][8], ad[FUSE ? VPL : 1][8];
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
+    for (int j = 0; j < 8; ++j) {
+      ag[i][j] = 0.f;
+      ab[i][j] = 0.f;
+      if (FUSE) ad[FUSE ? i : 0][j] = 0.f;
+    }
   for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
     float x[VPL][8], g[VPL][8];
     ld_row<float, VPL>(o + static_cast<size_t>(row) * H, lane, x);
@@ -361,19 +377,67 @@ __global__ void __launch_bounds__(kTrThreads) layernorm_bwd_kernel(const float* 
     }
     ln_bwd_core<VPL>(x, g, H, rstd);
     st_row<float, VPL>(d_o + static_cast<size_t>(row) * H, lane, g);
+    if (FUSE) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const size_t e0 = static_cast<size_t>(row) * H + (i * 32 + lane) * 8;
+        float keep[8];
+        drop_scales8(dr, e0, keep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          g[i][j] = to_f32<T>(from_f32<T>(g[i][j] * keep[j]));  // the value the backward GEMMs will read
+          ad[FUSE ? i : 0][j] += g[i][j];
+        }
+        store8<T>(gT + e0, g[i]);
+      }
+    }
   }
   flush_feature_sums<VPL>(ag, dgamma, sacc, H, lane);
   flush_feature_sums<VPL>(ab, dbeta, sacc + H, H, lane);
+  if constexpr (FUSE) flush_feature_sums<VPL>(ad, dbias, sacc + 2 * H, H, lane);
+}
+static int ln_bwd_grid(int M) {
+  const int need = ceil_div(M, kTrThreads / 32);
+  return need < 2 * num_sms() ? need : 2 * num_sms();
+}
+// one wave of resident CTAs (grid-stride over the rows): a second wave would only repeat the per-CTA flush of the feature sums
+template <typename K>
+static int ln_bwd_resident_grid(K kernel, size_t smem, int M) {
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTrThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+  const int need = ceil_div(M, kTrThreads / 32), cap = occ * num_sms();
+  return need < cap ? need : cap;
 }
 int layernorm_bwd(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
                   cudaStream_t s) {
-  const int need = ceil_div(M, kTrThreads / 32);
-  const int grid = need < 2 * num_sms() ? need : 2 * num_sms();
-  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_bwd_kernel<VPL>, dim3(grid), dim3(kTrThreads), 2 * H * sizeof(float), s, dh, o, M, H, gamma, eps,
-                                      d_o, dgamma, dbeta)));
+  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_bwd_kernel<VPL, float, false>, dim3(ln_bwd_grid(M)), dim3(kTrThreads), 2 * H * sizeof(float), s, dh, o,
+                                      M, H, gamma, eps, d_o, dgamma, dbeta, no_drop(), static_cast<float*>(nullptr), static_cast<float*>(nullptr))));
   SD_LAUNCHED("layernorm_bwd", s);
   return SEQDIFF_OK;
 }
+template <typename T>
+int layernorm_bwd_cast(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
+                       DropSpec dr, T* gT, float* dbias, cudaStream_t s) {
+  SD_CHECK(gT && dbias, "layernorm_bwd_cast: operand and bias-gradient outputs are required");
+  // SEQDIFF_LNBWD_OCC=2: the 128-register build (two CTAs per SM, a few spilled accumulators) instead of the spill-free one-CTA build
+  static const bool occ2 = [] { const char* e = getenv("SEQDIFF_LNBWD_OCC"); return e && e[0] == '2'; }();
+  const size_t smem = 3 * H * sizeof(float);
+  if (occ2) {
+    SD_VPL_DISPATCH(H, auto kfn = layernorm_bwd_kernel<VPL, T, true, 2>;
+                    SD_CUDA(launch_k(kfn, dim3(ln_bwd_resident_grid(kfn, smem, M)), dim3(kTrThreads), smem, s, dh, o, M, H, gamma, eps, d_o, dgamma,
+                                     dbeta, dr, gT, dbias)));
+  } else {
+    SD_VPL_DISPATCH(H, auto kfn = layernorm_bwd_kernel<VPL, T, true>;
+                    SD_CUDA(launch_k(kfn, dim3(ln_bwd_resident_grid(kfn, smem, M)), dim3(kTrThreads), smem, s, dh, o, M, H, gamma, eps, d_o, dgamma,
+                                     dbeta, dr, gT, dbias)));
+  }
+  SD_LAUNCHED("layernorm_bwd", s);
+  return SEQDIFF_OK;
+}
+template int layernorm_bwd_cast<bf16>(const float*, const float*, int, int, const float*, float, float*, float*, float*, DropSpec, bf16*, float*,
+                                      cudaStream_t);
+template int layernorm_bwd_cast<f16>(const float*, const float*, int, int, const float*, float, float*, float*, float*, DropSpec, f16*, float*,
+                                     cudaStream_t);
 
 // =====================================================================================================
 // SELayer residual update backward (forward: rowwise.cu ln_modulate_kernel)
@@ -388,6 +452,7 @@ __global__ void __launch_bounds__(kTrThreads) ln_modulate_bwd_kernel(const float
                                                                      const T* __restrict__ mod, int mod_div, int chunk0, float* __restrict__ din,
                                                                      float* __restrict__ sum_out, T* __restrict__ dmodT, float* __restrict__ dmod32,
                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rpw) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   extern __shared__ float sacc[];  // [2][H] (AFF only)
   if (AFF) {
     for (int e = threadIdx.x; e < 2 * H; e += kTrThreads) sacc[e] = 0.f;
@@ -551,6 +616,7 @@ __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __re
                                                                const float* __restrict__ Wt, const float* __restrict__ b,
                                                                const float* __restrict__ gamma, float eps, DropSpec dr, float* __restrict__ dW,
                                                                float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   extern __shared__ float sacc[];  // [fin + 3][H]: dW^T rows | db | dgamma | dbeta
   for (int e = threadIdx.x; e < (fin + 3) * H; e += kTrThreads) sacc[e] = 0.f;
   __syncthreads();
@@ -663,6 +729,7 @@ __global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd_kernel(const fl
                                                                         const float* __restrict__ W2, int F, float* __restrict__ dy,
                                                                         float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dgamma,
                                                                         float* __restrict__ dbeta) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   extern __shared__ float smem[];
   float* sW = smem;                                   // [F][H]  W2
   float* sdW = sW + static_cast<size_t>(F) * H;       // [F][H]  dW2 accumulators
@@ -776,6 +843,7 @@ template int predictor_tail_bwd<f16>(const float*, const f16*, int, int, const f
 // =====================================================================================================
 __global__ void __launch_bounds__(256) loss_bwd_kernel(int N, const float* __restrict__ logits, const float* __restrict__ x0,
                                                        const float* __restrict__ x_t, const double* __restrict__ terms, float* __restrict__ dlogits) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   constexpr int C = SEQDIFF_NUM_CLASSES;
   const double n_noised = terms[1];
   const float inv_n = n_noised > 0.0 ? static_cast<float>(1.0 / n_noised) : 0.f;
@@ -842,9 +910,23 @@ int loss_bwd(int N, const float* logits, const float* x0, const float* x_t, cons
 // sum of squares of the flat gradient, fp64 accumulation, fixed-order fold by the last CTA
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ partial, unsigned* __restrict__ arrive,
                                                     double* __restrict__ out) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   double acc = 0.0;
   const size_t n4 = n / 4;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * 256) {
+  // four independent 16-byte loads per thread and pass: 2 CTAs x 256 threads per SM with one load each keep ~1 MB in flight on the whole
+  // part, a fifth of what the HBM latency needs
+  const size_t stride = static_cast<size_t>(gridDim.x) * 256;
+  size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(g + 4 * (i + u * stride));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      acc += static_cast<double>(v[u].x) * v[u].x + static_cast<double>(v[u].y) * v[u].y + static_cast<double>(v[u].z) * v[u].z +
+             static_cast<double>(v[u].w) * v[u].w;
+  }
+  for (; i < n4; i += stride) {
     const float4 v = *reinterpret_cast<const float4*>(g + 4 * i);
     acc += static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z + static_cast<double>(v.w) * v.w;
   }
@@ -880,46 +962,73 @@ struct AdamSlots {  // device table: one entry per parameter tensor
   const int64_t* off;     // [n + 1] offsets into the flat buffers
   int n;
 };
-// one CTA-stride pass over the flat index space; the tensor of an element is found by binary search in `off`
+// one CTA-stride pass over the flat index space in groups of four consecutive elements; the tensor of a group is found by binary search
+// in `off`.  A group that lies inside one tensor and whose master pointer is 16 B aligned moves as float4 (g, m, v, w: 4 loads + 3 stores
+// of 16 B); a group that straddles a tensor boundary (or an unaligned tensor) takes the scalar path element by element.  Same arithmetic
+// per element on both paths.
+__device__ __forceinline__ void adamw_one(float& p, float& mi, float& vi, float gi, float lr, float beta1, float beta2, float eps, float wd,
+                                          float bc1, float rs_bc2) {
+  p *= 1.0f - lr * wd;                       // decoupled weight decay (torch.optim.AdamW)
+  mi = beta1 * mi + (1.0f - beta1) * gi;
+  vi = beta2 * vi + (1.0f - beta2) * gi * gi;
+  const float denom = sqrtf(vi) / rs_bc2 + eps;
+  p -= (lr / bc1) * (mi / denom);
+}
 __global__ void __launch_bounds__(256) adamw_kernel(AdamSlots sl, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                     size_t total, const double* __restrict__ sumsq, float grad_scale, float max_norm, float lr,
                                                     float beta1, float beta2, float eps, float wd, float bc1, float bc2, float* __restrict__ norm_out) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
   // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
   const float total_norm = sqrtf(static_cast<float>(*sumsq)) * grad_scale;
   float coef = 1.0f;
   if (max_norm > 0.f) coef = fminf(max_norm / (total_norm + 1e-6f), 1.0f);
   if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = total_norm;
   const float gs = grad_scale * coef;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * 256) {
+  const float rs_bc2 = sqrtf(bc2);
+  const size_t groups = (total + 3) / 4;
+  for (size_t q = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; q < groups; q += static_cast<size_t>(gridDim.x) * 256) {
+    const size_t i = 4 * q;
     int lo = 0, hi = sl.n;  // off[lo] <= i < off[hi]
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if (static_cast<size_t>(sl.off[mid]) <= i) lo = mid; else hi = mid;
+      if (static_cast<size_t>(__ldg(sl.off + mid)) <= i) lo = mid; else hi = mid;
     }
     float* w = sl.w[lo] + (i - static_cast<size_t>(sl.off[lo]));
-    const float gi = g[i] * gs;
-    float p = *w;
-    p *= 1.0f - lr * wd;                       // decoupled weight decay (torch.optim.AdamW)
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
-    p -= (lr / bc1) * (mi / denom);
-    *w = p;
+    if (i + 4 <= static_cast<size_t>(sl.off[lo + 1]) && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+      float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i), p4 = *reinterpret_cast<const float4*>(w);
+      adamw_one(p4.x, m4.x, v4.x, g4.x * gs, lr, beta1, beta2, eps, wd, bc1, rs_bc2);
+      adamw_one(p4.y, m4.y, v4.y, g4.y * gs, lr, beta1, beta2, eps, wd, bc1, rs_bc2);
+      adamw_one(p4.z, m4.z, v4.z, g4.z * gs, lr, beta1, beta2, eps, wd, bc1, rs_bc2);
+      adamw_one(p4.w, m4.w, v4.w, g4.w * gs, lr, beta1, beta2, eps, wd, bc1, rs_bc2);
+      *reinterpret_cast<float4*>(m + i) = m4;
+      *reinterpret_cast<float4*>(v + i) = v4;
+      *reinterpret_cast<float4*>(w) = p4;
+    } else {
+      for (size_t e = i; e < i + 4 && e < total; ++e) {
+        while (e >= static_cast<size_t>(sl.off[lo + 1])) ++lo;  // zero-sized tensors are skipped too
+        float* we = sl.w[lo] + (e - static_cast<size_t>(sl.off[lo]));
+        float p = *we, mi = m[e], vi = v[e];
+        adamw_one(p, mi, vi, g[e] * gs, lr, beta1, beta2, eps, wd, bc1, rs_bc2);
+        m[e] = mi;
+        v[e] = vi;
+        *we = p;
+      }
+    }
   }
 }
 int adamw_step(float* const* d_w, const int64_t* d_off, int n_slots, size_t total, const float* g, float* m, float* v, float grad_scale,
                float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step, double* d_scratch, float* norm_out, cudaStream_t s) {
   SD_CHECK(step >= 1 && total > 0, "adamw: step counts from 1");
-  SD_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, "flat gradient buffer must be 16 B aligned");
+  SD_CHECK(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+           "flat gradient / moment buffers must be 16 B aligned");
   const int ctas = 2 * num_sms();
   unsigned* arrive = reinterpret_cast<unsigned*>(d_scratch + ctas + 1);
   SD_CUDA(launch_k(sumsq_kernel, dim3(ctas), dim3(256), 0, s, g, total, d_scratch + 1, arrive, d_scratch));
   SD_LAUNCHED("grad_sumsq", s);
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   AdamSlots sl{d_w, d_off, n_slots};
-  SD_CUDA(launch_k(adamw_kernel, dim3(4 * num_sms()), dim3(256), 0, s, sl, g, m, v, total, d_scratch, grad_scale, max_norm, lr, beta1, beta2, eps, wd,
+  SD_CUDA(launch_k(adamw_kernel, dim3(8 * num_sms()), dim3(256), 0, s, sl, g, m, v, total, d_scratch, grad_scale, max_norm, lr, beta1, beta2, eps, wd,
                    bc1, bc2, norm_out));
   SD_LAUNCHED("adamw", s);
   return SEQDIFF_OK;
