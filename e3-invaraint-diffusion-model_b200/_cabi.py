@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # SEQDIFF_DEBUG_BOUNDS=1 selects the debug build (device-side asserts + workspace guard bands; build.py with the same variable)
-LIB_PATH = os.path.join(HERE, "libseqdiff_b200_dbg.so" if os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1" else "libseqdiff_b200.so")
+LIB_PATH = os.environ.get("SEQDIFF_LIB") or os.path.join(HERE, "libseqdiff_b200_dbg.so" if os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1" else "libseqdiff_b200.so")
 
 FP32, BF16, FP16 = 0, 1, 2
 PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}

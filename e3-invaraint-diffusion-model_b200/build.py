@@ -13,8 +13,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build" + ("_ab" if os.environ.get("SEQDIFF_AB_KERNELS") == "1" else "") + ("_dbg" if os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1" else ""))
-LIB = os.path.join(HERE, "libseqdiff_b200_dbg.so" if os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1" else "libseqdiff_b200.so")
+# SEQDIFF_VARIANT=<name> with SEQDIFF_EXTRA_FLAGS="-D..." builds an experiment library libseqdiff_b200_<name>.so next to the product one
+# (own object directory); python loads it when SEQDIFF_LIB names its path (_cabi.py).  A/B measurements only.
+VARIANT = os.environ.get("SEQDIFF_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_ab" if os.environ.get("SEQDIFF_AB_KERNELS") == "1" else "") + ("_dbg" if os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1" else "") + (f"_{VARIANT}" if VARIANT else ""))
+LIB = os.path.join(HERE, f"libseqdiff_b200_{VARIANT}.so" if VARIANT else ("libseqdiff_b200_dbg.so" if os.environ.get("SEQDIFF_DEBUG_BOUNDS") == "1" else "libseqdiff_b200.so"))
 SOURCES = ["gemm.cu", "rowwise.cu", "attention.cu", "attention_pipe.cu", "reverse_step.cu", "gauss_step.cu", "decode_loss.cu", "collate.cu", "train_kernels.cu", "attention_train.cu", "attention_train_tc.cu", "attention_bwd_pipe.cu", "train.cu", "model.cu", "cabi.cu"]
 # SEQDIFF_AB_KERNELS=1: also build the superseded attention kernels (attention_tc.cu, the mma.sync kernel in attention.cu) as A/B
 # references selectable with SEQDIFF_ATTN=tc|mma.  SEQDIFF_DEBUG_BOUNDS=1: device-side bounds / invariant asserts in every kernel
@@ -32,6 +35,7 @@ FLAGS = [
 
 
 
+FLAGS += os.environ.get("SEQDIFF_EXTRA_FLAGS", "").split()
 if AB_KERNELS:
     FLAGS.append("-DSEQDIFF_AB_KERNELS")
 if DEBUG_BOUNDS:

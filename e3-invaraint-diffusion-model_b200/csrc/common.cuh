@@ -519,6 +519,13 @@ int debug_guard_check(cudaStream_t s, int* n_bands, int* n_broken);
 // pdl_trigger() lets the successor start being scheduled.  Both are no-ops without the attribute (SEQDIFF_PDL=0).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// first statement of every kernel of the training step: nothing but the wait (a no-op unless the launch carries the programmatic
+// stream serialization attribute, SEQDIFF_TRAIN_PDL); -DSEQDIFF_TRAIN_TRIGGER also lets the successor's CTAs become resident early
+#ifdef SEQDIFF_TRAIN_TRIGGER
+#define SD_TRAIN_PDL_PROLOGUE() do { ::seqdiff::pdl_trigger(); ::seqdiff::pdl_wait(); } while (0)
+#else
+#define SD_TRAIN_PDL_PROLOGUE() ::seqdiff::pdl_wait()
+#endif
 bool pdl_enabled();
 int pdl_scope_exchange(int mode);  // sets the calling thread's scope mode (0 = none), returns the previous one
 int pdl_mode();  // effective mode of this launch: 0 off, 1 every launch, 2 only light successors (< 64 KB of shared memory), 3 only heavy ones

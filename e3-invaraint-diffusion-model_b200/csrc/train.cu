@@ -68,7 +68,7 @@ template <typename T> static const void* wsel(const Wt& w) {
 template <typename T>
 __global__ void __launch_bounds__(256) embed_post_kernel(float* __restrict__ v, const float* __restrict__ te, int L, int H, size_t n8, DropSpec dr,
                                                          float* __restrict__ out32, T* __restrict__ outT) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float x[8], keep[8];
     load8<float>(v + 8 * i, x);
@@ -95,7 +95,7 @@ static int embed_post(float* v, const float* te, int L, int H, size_t n, DropSpe
   return SEQDIFF_OK;
 }
 __global__ void concat_masks_kernel(float* dst, const float* a, int na, const float* b, int nb) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += gridDim.x * blockDim.x) dst[i] = i < na ? a[i] : b[i - na];
 }
 
@@ -696,10 +696,11 @@ int Model::train_step(const TrainArgs& a, cudaStream_t s) {
     SD_TRY(finalize(s));
   }
   if (g_profiling) profile_mark("__begin__", s);  // host time between two steps is not the first kernel's
-  // SEQDIFF_TRAIN_PDL=3: programmatic dependent launch of the heavy kernels of the step (tcgen05 GEMMs and attention: their prologue --
-  // barrier init, TMEM allocation, descriptor prefetch -- runs under the predecessor's tail; every kernel of the step starts with
-  // griddepcontrol.wait, so any mode is safe).  Off by default.
-  static const int train_pdl = [] { const char* e = getenv("SEQDIFF_TRAIN_PDL"); return e && e[0] >= '1' && e[0] <= '3' ? e[0] - '0' : 0; }();
+  // Programmatic dependent launch of the heavy kernels of the step (mode 3: tcgen05 GEMMs and attention -- their prologue, i.e. barrier
+  // init, TMEM allocation, descriptor prefetch, runs under the predecessor's tail).  Every kernel launched inside this call starts with
+  // griddepcontrol.wait, so any mode is safe.  Measured on B200 (profiles/train_pdl_ab_r02.log): 128 graphs 15.15 -> 14.64 ms per step,
+  // 16 graphs 5.00 -> 4.55 ms; every launch (mode 1) 14.72 / 4.76 ms.  SEQDIFF_TRAIN_PDL=0 | 1 | 2 | 3 overrides.
+  static const int train_pdl = [] { const char* e = getenv("SEQDIFF_TRAIN_PDL"); return e && e[0] >= '0' && e[0] <= '3' ? e[0] - '0' : 3; }();
   struct Scope {
     const int prev;
     explicit Scope(int m) : prev(pdl_scope_exchange(m)) {}

@@ -81,7 +81,7 @@ __device__ __forceinline__ void ln_bwd_core(const float (&xhat)[VPL][8], float (
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_colsum_kernel(const T* __restrict__ in, int rows, int cols, T* __restrict__ out, int pitch,
                                                                float* __restrict__ colsum) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   __shared__ float tile[64][65];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
@@ -134,7 +134,7 @@ __device__ __forceinline__ int acc_slot_of_col(int e) { return acc_slot(e >> 8, 
 // meet in shared memory, one atomic per column and CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int rows, int cols, float* __restrict__ colsum) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   __shared__ float part[8][256];
   const int oct = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + oct * 8;
@@ -175,7 +175,7 @@ template int colsum_add<f16>(const f16*, int, int, float*, cudaStream_t);
 // fp32 [rows, cols] -> T [cols, rows] (weights: the fp32 master -> the transposed operand copy the dgrad GEMMs read)
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ in, int rows, int cols, T* __restrict__ out) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   __shared__ float tile[64][65];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
@@ -216,7 +216,7 @@ __device__ __forceinline__ float silu_grad(float x) {
 // a = dropout(act(z)); kind 1 = erf-GELU, 2 = SiLU.  8 elements per thread.
 template <typename T>
 __global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ z, size_t n8, int kind, DropSpec dr, T* __restrict__ a) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float v[8];
     load8<T>(z + 8 * i, v);
@@ -240,7 +240,7 @@ int act_fwd(const T* z, size_t n, int kind, DropSpec dr, T* a, cudaStream_t s) {
 template <typename T, typename TG>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const TG* __restrict__ da, const T* __restrict__ z, size_t n8, int kind, DropSpec dr,
                                                       T* __restrict__ dz) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float g[8], v[8], keep[8];
     load8<TG>(da + 8 * i, g);
@@ -262,7 +262,7 @@ int act_bwd(const TG* da, const T* z, size_t n, int kind, DropSpec dr, T* dz, cu
 }
 // o = dropout(d) + resid (fp32, in place on d): the hidden-state dropout that sits between a Linear and its residual add
 __global__ void __launch_bounds__(256) dropout_add_kernel(float* __restrict__ d, const float* __restrict__ resid, size_t n8, DropSpec dr) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float v[8], r[8], keep[8];
     load8<float>(d + 8 * i, v);
@@ -289,7 +289,7 @@ int dropout_add(float* d, const float* resid, size_t n, DropSpec dr, cudaStream_
 // gT = T(g * keep): the fp32 gradient of a (dropout-ed) Linear output as the 16-bit operand of its backward GEMMs
 template <typename T>
 __global__ void __launch_bounds__(256) grad_cast_kernel(const float* __restrict__ g, size_t n8, DropSpec dr, T* __restrict__ out) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * 256) {
     float v[8], keep[8];
     load8<float>(g + 8 * i, v);
@@ -335,17 +335,32 @@ __device__ __forceinline__ void flush_feature_sums(float (&acc)[VPL][8], float* 
   __syncthreads();
 }
 
+// Ampere-style asynchronous 16-byte copies global -> shared (LDGSTS): the prefetch of a warp's NEXT row under the reductions of its
+// current one.  Each lane copies and later reads only its own chunks, so no barrier is involved: wait_group orders a thread's own copies.
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // FUSE: the gradient d_o is also the dY of the Linear that produced o (o = dropout(x W^T + b) + resid), so the same pass writes the
 // 16-bit GEMM operand gT = T(d_o * keep) and adds its column sums (the bias gradient, summed over the values the weight-gradient GEMM
 // reads) into dbias -- one grad_cast and one colsum launch less per LayerNorm, and d_o is not re-read twice.
-template <int VPL, typename T, bool FUSE, int MINB = 1>
-__global__ void __launch_bounds__(kTrThreads, MINB) layernorm_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ o, int M, int H,
+// PIPE: the three register accumulator sets cap the kernel at one 8-warp CTA per SM, and a warp's row is a serial chain (load 6 KB ->
+// four warp reductions -> store), so the loads of a row were exposed (59 us per launch at 16384 x 768 against 27 us of HBM traffic).
+// With PIPE every warp double-buffers its rows in shared memory: the o / dh rows of its next row are in flight (cp.async) while it
+// reduces the current one.  Staging layout per array: chunk (i, half, lane) at float offset i * 256 + half * 128 + lane * 4 (conflict-free
+// 16-byte reads).
+template <int VPL, typename T, bool FUSE, bool PIPE = false>
+__global__ void __launch_bounds__(kTrThreads) layernorm_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ o, int M, int H,
                                                                    const float* __restrict__ gamma, float eps, float* __restrict__ d_o,
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta, DropSpec dr,
                                                                    T* __restrict__ gT, float* __restrict__ dbias) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
-  extern __shared__ float sacc[];  // [2 (+1)][H]
-  for (int e = threadIdx.x; e < (FUSE ? 3 : 2) * H; e += kTrThreads) sacc[e] = 0.f;
+  SD_TRAIN_PDL_PROLOGUE();
+  constexpr int NACC = FUSE ? 3 : 2;
+  extern __shared__ float sacc[];  // [NACC][H] feature sums, then (PIPE) [8 warps][2 stages][o row | dh row][H]
+  for (int e = threadIdx.x; e < NACC * H; e += kTrThreads) sacc[e] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float ag[VPL][8], ab[VPL][8], ad[FUSE ? VPL : 1][8];
@@ -357,10 +372,47 @@ __global__ void __launch_bounds__(kTrThreads, MINB) layernorm_bwd_kernel(const f
       ab[i][j] = 0.f;
       if (FUSE) ad[FUSE ? i : 0][j] = 0.f;
     }
-  for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
+  const int stride = gridDim.x * (kTrThreads / 32);
+  int row = blockIdx.x * (kTrThreads / 32) + warp;
+  float* stage = sacc + NACC * H + static_cast<size_t>(warp) * 4 * H;
+  auto prefetch = [&](int r, int st) {  // always commits a group (possibly empty) so that wait_group<1> counts uniformly
+    if (r < M) {
+      float* so = stage + static_cast<size_t>(st) * 2 * H;
+      float* sd = so + H;
+      const float* go = o + static_cast<size_t>(r) * H;
+      const float* gd = dh + static_cast<size_t>(r) * H;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = (i * 32 + lane) * 8 + h * 4, si = i * 256 + h * 128 + lane * 4;
+          cp_async16(so + si, go + c);
+          cp_async16(sd + si, gd + c);
+        }
+    }
+    cp_async_commit();
+  };
+  if (PIPE) prefetch(row, 0);
+  for (int it = 0; row < M; row += stride, ++it) {
     float x[VPL][8], g[VPL][8];
-    ld_row<float, VPL>(o + static_cast<size_t>(row) * H, lane, x);
-    ld_row<float, VPL>(dh + static_cast<size_t>(row) * H, lane, g);
+    if (PIPE) {
+      prefetch(row + stride, (it + 1) & 1);
+      cp_async_wait<1>();  // everything but the newest group: this row's copies have landed
+      const float* so = stage + static_cast<size_t>(it & 1) * 2 * H;
+      const float* sd = so + H;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int si = i * 256 + h * 128 + lane * 4;
+          const float4 a = *reinterpret_cast<const float4*>(so + si), b = *reinterpret_cast<const float4*>(sd + si);
+          x[i][h * 4 + 0] = a.x; x[i][h * 4 + 1] = a.y; x[i][h * 4 + 2] = a.z; x[i][h * 4 + 3] = a.w;
+          g[i][h * 4 + 0] = b.x; g[i][h * 4 + 1] = b.y; g[i][h * 4 + 2] = b.z; g[i][h * 4 + 3] = b.w;
+        }
+    } else {
+      ld_row<float, VPL>(o + static_cast<size_t>(row) * H, lane, x);
+      ld_row<float, VPL>(dh + static_cast<size_t>(row) * H, lane, g);
+    }
     float mean, rstd;
     stats_of<VPL>(x, H, eps, mean, rstd);
 #pragma unroll
@@ -392,6 +444,7 @@ __global__ void __launch_bounds__(kTrThreads, MINB) layernorm_bwd_kernel(const f
       }
     }
   }
+  if (PIPE) cp_async_wait<0>();
   flush_feature_sums<VPL>(ag, dgamma, sacc, H, lane);
   flush_feature_sums<VPL>(ab, dbeta, sacc + H, H, lane);
   if constexpr (FUSE) flush_feature_sums<VPL>(ad, dbias, sacc + 2 * H, H, lane);
@@ -419,14 +472,20 @@ template <typename T>
 int layernorm_bwd_cast(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
                        DropSpec dr, T* gT, float* dbias, cudaStream_t s) {
   SD_CHECK(gT && dbias, "layernorm_bwd_cast: operand and bias-gradient outputs are required");
-  // SEQDIFF_LNBWD_OCC=2: the 128-register build (two CTAs per SM, a few spilled accumulators) instead of the spill-free one-CTA build
-  static const bool occ2 = [] { const char* e = getenv("SEQDIFF_LNBWD_OCC"); return e && e[0] == '2'; }();
-  const size_t smem = 3 * H * sizeof(float);
-  if (occ2) {
-    SD_VPL_DISPATCH(H, auto kfn = layernorm_bwd_kernel<VPL, T, true, 2>;
+  // SEQDIFF_LNBWD_PIPE=0: rows loaded straight into registers (no cp.async double buffer)
+  static const bool pipe = [] { const char* e = getenv("SEQDIFF_LNBWD_PIPE"); return !e || e[0] != '0'; }();
+  if (pipe) {
+    const size_t smem = (3 + (kTrThreads / 32) * 4) * static_cast<size_t>(H) * sizeof(float);  // 108 KB at H = 768
+    SD_VPL_DISPATCH(H, auto kfn = layernorm_bwd_kernel<VPL, T, true, true>;
+                    static bool configured = false;
+                    if (!configured) {
+                      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 + (kTrThreads / 32) * 4) * 256 * VPL * 4));
+                      configured = true;
+                    }
                     SD_CUDA(launch_k(kfn, dim3(ln_bwd_resident_grid(kfn, smem, M)), dim3(kTrThreads), smem, s, dh, o, M, H, gamma, eps, d_o, dgamma,
                                      dbeta, dr, gT, dbias)));
   } else {
+    const size_t smem = 3 * static_cast<size_t>(H) * sizeof(float);
     SD_VPL_DISPATCH(H, auto kfn = layernorm_bwd_kernel<VPL, T, true>;
                     SD_CUDA(launch_k(kfn, dim3(ln_bwd_resident_grid(kfn, smem, M)), dim3(kTrThreads), smem, s, dh, o, M, H, gamma, eps, d_o, dgamma,
                                      dbeta, dr, gT, dbias)));
@@ -452,7 +511,7 @@ __global__ void __launch_bounds__(kTrThreads) ln_modulate_bwd_kernel(const float
                                                                      const T* __restrict__ mod, int mod_div, int chunk0, float* __restrict__ din,
                                                                      float* __restrict__ sum_out, T* __restrict__ dmodT, float* __restrict__ dmod32,
                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rpw) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   extern __shared__ float sacc[];  // [2][H] (AFF only)
   if (AFF) {
     for (int e = threadIdx.x; e < 2 * H; e += kTrThreads) sacc[e] = 0.f;
@@ -611,90 +670,141 @@ SD_INST_LNMB(f16);
 // dout [M,H] fp32 (gradient of `out`).  Parameter gradients only (the inputs are data): dW [H, fin] (nn.Linear layout),
 // db [H], dg [H], dbeta [H].  lin = x Wt + b is recomputed (fin <= 32 multiply-adds per feature).
 // =====================================================================================================
-template <int VPL>
+// DENSE (fin <= 8, the angle embeddings: every input feature is non-zero): dW^T[k, :] += x_k g[:] was fin * H / 32 shared atomics per
+// lane and row (192 at fin = 8, H = 768 -- the launch was bound by them: ~230 us against ~20 us for the one-hot sequence embeddings).
+// Instead the eight warps park their rows' g and x in shared memory, and after a barrier every THREAD owns H / 256 columns and adds
+// x[w][k] * g[w][col] over the eight rows into fin * H / 256 register accumulators: plain FMAs on conflict-free reads.
+template <int VPL, bool DENSE>
 __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, int M, int fin, int H,
                                                                const float* __restrict__ Wt, const float* __restrict__ b,
                                                                const float* __restrict__ gamma, float eps, DropSpec dr, float* __restrict__ dW,
                                                                float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
-  extern __shared__ float sacc[];  // [fin + 3][H]: dW^T rows | db | dgamma | dbeta
-  for (int e = threadIdx.x; e < (fin + 3) * H; e += kTrThreads) sacc[e] = 0.f;
+  SD_TRAIN_PDL_PROLOGUE();
+  constexpr int NW = kTrThreads / 32;
+  extern __shared__ float sacc[];  // sparse: [fin + 3][H] = dW^T rows | db | dgamma | dbeta;  DENSE: [3][H] sums | [NW][H] g rows | [NW][8] x rows
+  const int n_acc = DENSE ? 3 : fin + 3, base_acc = DENSE ? 0 : fin;
+  for (int e = threadIdx.x; e < n_acc * H; e += kTrThreads) sacc[e] = 0.f;
+  float* sg = sacc + 3 * H;
+  float* sx = sg + NW * H;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // db / dgamma / dbeta: every row adds to the same H columns -> per-warp register accumulators, flushed once per CTA (they were
-  // 3 H of the (3 + nnz) H shared atomics per row); dW^T[k, :] += x_k g[:] stays on shared atomics (k varies with the row).
-  float a_db[VPL][8], a_dg[VPL][8], a_dbt[VPL][8];
+  // 3 H of the (3 + nnz) H shared atomics per row); sparse inputs: dW^T[k, :] += x_k g[:] stays on shared atomics (k varies with the row).
+  float a_db[VPL][8], a_dg[VPL][8], a_dbt[VPL][8], a_w[DENSE ? 8 : 1][VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i)
+  for (int i = 0; i < VPL; ++i) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a_db[i][j] = 0.f; a_dg[i][j] = 0.f; a_dbt[i][j] = 0.f; }
-  for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
-    float xin = lane < fin ? x[static_cast<size_t>(row) * fin + lane] : 0.f;
-    float v[VPL][8], g[VPL][8];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) load8<float>(b + (i * 32 + lane) * 8, v[i]);
-    for (int k = 0; k < fin; ++k) {
-      const float xk = __shfl_sync(0xffffffffu, xin, k);
-      if (xk == 0.f) continue;
+    for (int k = 0; k < (DENSE ? 8 : 1); ++k) a_w[k][i] = 0.f;
+  }
+  // DENSE walks the rows in CTA-uniform passes of NW rows (barriers inside); the sparse form lets every warp run on its own
+  for (int row0 = blockIdx.x * NW; row0 < M; row0 += gridDim.x * NW) {
+    const int row = row0 + warp;
+    const bool live = row < M;
+    if (!DENSE && !live) break;
+    float g[VPL][8];
+    float xin = 0.f;
+    if (live) {
+      xin = lane < fin ? x[static_cast<size_t>(row) * fin + lane] : 0.f;
+      float v[VPL][8];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) load8<float>(b + (i * 32 + lane) * 8, v[i]);
+      for (int k = 0; k < fin; ++k) {
+        const float xk = __shfl_sync(0xffffffffu, xin, k);
+        if (xk == 0.f) continue;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          float w8[8];
+          load8<float>(Wt + static_cast<size_t>(k) * H + (i * 32 + lane) * 8, w8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = fmaf(xk, w8[j], v[i][j]);
+        }
+      }
+      float mean, rstd;
+      stats_of<VPL>(v, H, eps, mean, rstd);
+      ld_row<float, VPL>(dout + static_cast<size_t>(row) * H, lane, g);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        float w8[8];
-        load8<float>(Wt + static_cast<size_t>(k) * H + (i * 32 + lane) * 8, w8);
+        float keep[8], w8[8];
+        drop_scales8(dr, static_cast<size_t>(row) * H + (i * 32 + lane) * 8, keep);
+        load8<float>(gamma + (i * 32 + lane) * 8, w8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = fmaf(xk, w8[j], v[i][j]);
+        for (int j = 0; j < 8; ++j) {
+          const float go = g[i][j] * keep[j];
+          v[i][j] = (v[i][j] - mean) * rstd;
+          a_dg[i][j] = fmaf(go, v[i][j], a_dg[i][j]);
+          a_dbt[i][j] += go;
+          g[i][j] = go * w8[j];
+        }
       }
-    }
-    float mean, rstd;
-    stats_of<VPL>(v, H, eps, mean, rstd);
-    ld_row<float, VPL>(dout + static_cast<size_t>(row) * H, lane, g);
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float keep[8], w8[8];
-      drop_scales8(dr, static_cast<size_t>(row) * H + (i * 32 + lane) * 8, keep);
-      load8<float>(gamma + (i * 32 + lane) * 8, w8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float go = g[i][j] * keep[j];
-        v[i][j] = (v[i][j] - mean) * rstd;
-        a_dg[i][j] = fmaf(go, v[i][j], a_dg[i][j]);
-        a_dbt[i][j] += go;
-        g[i][j] = go * w8[j];
-      }
-    }
-    ln_bwd_core<VPL>(v, g, H, rstd);  // g = dL/d(lin)
-    for (int k = 0; k < fin; ++k) {
-      const float xk = __shfl_sync(0xffffffffu, xin, k);
-      if (xk == 0.f) continue;
+      ln_bwd_core<VPL>(v, g, H, rstd);  // g = dL/d(lin)
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(k) * H + acc_slot(i, lane, j), xk * g[i][j]);
+        for (int j = 0; j < 8; ++j) a_db[i][j] += g[i][j];
+    } else {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[i][j] = 0.f;
     }
+    if constexpr (DENSE) {
+      st_row<float, VPL>(sg + static_cast<size_t>(warp) * H, lane, g);
+      if (lane < 8) sx[warp * 8 + lane] = xin;  // lanes fin .. 7 hold 0
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < VPL; ++i)
+      for (int w = 0; w < NW; ++w) {
+        float xw[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a_db[i][j] += g[i][j];
+        for (int k = 0; k < 8; ++k) xw[k] = sx[w * 8 + k];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const float gv = sg[static_cast<size_t>(w) * H + i * 256 + threadIdx.x];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a_w[k][i] = fmaf(xw[k], gv, a_w[k][i]);
+        }
+      }
+      __syncthreads();
+    } else {
+      for (int k = 0; k < fin; ++k) {
+        const float xk = __shfl_sync(0xffffffffu, xin, k);
+        if (xk == 0.f) continue;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(sacc + static_cast<size_t>(k) * H + acc_slot(i, lane, j), xk * g[i][j]);
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int e = acc_slot(i, lane, j);
-      atomicAdd(sacc + static_cast<size_t>(fin) * H + e, a_db[i][j]);
-      atomicAdd(sacc + (fin + 1) * H + e, a_dg[i][j]);
-      atomicAdd(sacc + (fin + 2) * H + e, a_dbt[i][j]);
+      atomicAdd(sacc + static_cast<size_t>(base_acc) * H + e, a_db[i][j]);
+      atomicAdd(sacc + (base_acc + 1) * H + e, a_dg[i][j]);
+      atomicAdd(sacc + (base_acc + 2) * H + e, a_dbt[i][j]);
     }
   __syncthreads();
-  for (int e = threadIdx.x; e < fin * H; e += kTrThreads) {
-    const int k = e / H, h = e - k * H;
-    const float v = sacc[k * H + acc_slot_of_col(h)];
-    if (v != 0.f) atomicAdd(dW + static_cast<size_t>(h) * fin + k, v);
+  if constexpr (DENSE) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < fin && a_w[k][i] != 0.f) atomicAdd(dW + static_cast<size_t>(i * 256 + threadIdx.x) * fin + k, a_w[k][i]);
+  } else {
+    for (int e = threadIdx.x; e < fin * H; e += kTrThreads) {
+      const int k = e / H, h = e - k * H;
+      const float v = sacc[k * H + acc_slot_of_col(h)];
+      if (v != 0.f) atomicAdd(dW + static_cast<size_t>(h) * fin + k, v);
+    }
   }
   for (int e = threadIdx.x; e < H; e += kTrThreads) {
     const int sl = acc_slot_of_col(e);
-    atomicAdd(db + e, sacc[fin * H + sl]);
-    atomicAdd(dgamma + e, sacc[(fin + 1) * H + sl]);
-    atomicAdd(dbeta + e, sacc[(fin + 2) * H + sl]);
+    atomicAdd(db + e, sacc[base_acc * H + sl]);
+    atomicAdd(dgamma + e, sacc[(base_acc + 1) * H + sl]);
+    atomicAdd(dbeta + e, sacc[(base_acc + 2) * H + sl]);
   }
 }
 int embed_bwd(const float* dout, const float* x, int M, int fin, int H, const float* Wt, const float* b, const float* gamma, float eps, DropSpec dr,
@@ -702,10 +812,14 @@ int embed_bwd(const float* dout, const float* x, int M, int fin, int H, const fl
   SD_CHECK(fin >= 1 && fin <= 32, "embed_bwd: fin in [1,32]");
   const int need = ceil_div(M, kTrThreads / 32);
   const int grid = need < num_sms() ? need : num_sms();
-  const size_t smem = static_cast<size_t>(fin + 3) * H * sizeof(float);
-#define SD_EB_LAUNCH()                                                                                              \
+  // SEQDIFF_EMBED_BWD_DENSE=0: shared atomics for every input width (the form that stays for the one-hot sequence embeddings)
+  static const bool dense_ok = [] { const char* e = getenv("SEQDIFF_EMBED_BWD_DENSE"); return !e || e[0] != '0'; }();
+  const bool dense = dense_ok && fin <= 8;
+  const size_t smem = dense ? (static_cast<size_t>(3 + kTrThreads / 32) * H + (kTrThreads / 32) * 8) * sizeof(float)
+                            : static_cast<size_t>(fin + 3) * H * sizeof(float);
+#define SD_EB_LAUNCH_(DENSE_)                                                                                       \
   {                                                                                                                 \
-    auto kfn = embed_bwd_kernel<VPL>;                                                                               \
+    auto kfn = embed_bwd_kernel<VPL, DENSE_>;                                                                       \
     static bool configured = false;                                                                                 \
     if (!configured) {                                                                                              \
       SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 35 * 1024 * 4));               \
@@ -713,7 +827,9 @@ int embed_bwd(const float* dout, const float* x, int M, int fin, int H, const fl
     }                                                                                                               \
     SD_CUDA(launch_k(kfn, dim3(grid), dim3(kTrThreads), smem, s, dout, x, M, fin, H, Wt, b, gamma, eps, dr, dW, db, dgamma, dbeta)); \
   }
+#define SD_EB_LAUNCH() if (dense) SD_EB_LAUNCH_(true) else SD_EB_LAUNCH_(false)
   SD_VPL_DISPATCH(H, SD_EB_LAUNCH());
+#undef SD_EB_LAUNCH_
 #undef SD_EB_LAUNCH
   SD_LAUNCHED("embed_bwd", s);
   return SEQDIFF_OK;
@@ -729,7 +845,7 @@ __global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd_kernel(const fl
                                                                         const float* __restrict__ W2, int F, float* __restrict__ dy,
                                                                         float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dgamma,
                                                                         float* __restrict__ dbeta) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   extern __shared__ float smem[];
   float* sW = smem;                                   // [F][H]  W2
   float* sdW = sW + static_cast<size_t>(F) * H;       // [F][H]  dW2 accumulators
@@ -843,7 +959,7 @@ template int predictor_tail_bwd<f16>(const float*, const f16*, int, int, const f
 // =====================================================================================================
 __global__ void __launch_bounds__(256) loss_bwd_kernel(int N, const float* __restrict__ logits, const float* __restrict__ x0,
                                                        const float* __restrict__ x_t, const double* __restrict__ terms, float* __restrict__ dlogits) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   constexpr int C = SEQDIFF_NUM_CLASSES;
   const double n_noised = terms[1];
   const float inv_n = n_noised > 0.0 ? static_cast<float>(1.0 / n_noised) : 0.f;
@@ -910,7 +1026,7 @@ int loss_bwd(int N, const float* logits, const float* x0, const float* x_t, cons
 // sum of squares of the flat gradient, fp64 accumulation, fixed-order fold by the last CTA
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ partial, unsigned* __restrict__ arrive,
                                                     double* __restrict__ out) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   double acc = 0.0;
   const size_t n4 = n / 4;
   // four independent 16-byte loads per thread and pass: 2 CTAs x 256 threads per SM with one load each keep ~1 MB in flight on the whole
@@ -977,7 +1093,7 @@ __device__ __forceinline__ void adamw_one(float& p, float& mi, float& vi, float 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamSlots sl, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                     size_t total, const double* __restrict__ sumsq, float grad_scale, float max_norm, float lr,
                                                     float beta1, float beta2, float eps, float wd, float bc1, float bc2, float* __restrict__ norm_out) {
-  pdl_wait();  // no-op unless launched with programmatic stream serialization (SEQDIFF_TRAIN_PDL)
+  SD_TRAIN_PDL_PROLOGUE();
   // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
   const float total_norm = sqrtf(static_cast<float>(*sumsq)) * grad_scale;
   float coef = 1.0f;
