@@ -187,13 +187,19 @@ template <typename T> int act_fwd(const T* z, size_t n, int kind, DropSpec dr, T
 template <typename T, typename TG> int act_bwd(const TG* da, const T* z, size_t n, int kind, DropSpec dr, T* dz, cudaStream_t s);
 int dropout_add(float* d, const float* resid, size_t n, DropSpec dr, cudaStream_t s);           // d = dropout(d) + resid (resid may be NULL)
 template <typename T> int grad_cast(const float* g, size_t n, DropSpec dr, T* out, cudaStream_t s);  // out = T(g * keep)
+// d <- o = dropout(d) + resid;  out32 / outT (either optional) = LayerNorm(o) * w + b: dropout_add + layernorm in one pass;
+// keep_bits (optional) [M, H / 8] bytes: the mask, for layernorm_bwd_cast
+template <typename T>
+int dropout_add_layernorm(float* d, const float* resid, DropSpec dr, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT,
+                          uint8_t* keep_bits, cudaStream_t s);
 // h = LN(o) * gamma + beta:  d_o = LN-backward(dh); dgamma / dbeta += row sums (atomic, fp32 [H])
 int layernorm_bwd(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
                   cudaStream_t s);
-// the same, and in the same pass: gT = T(d_o * keep) (the 16-bit dY operand of the Linear that produced o) and dbias += column sums of gT
+// the same, and in the same pass: gT = T(d_o * keep) (the 16-bit dY operand of the Linear that produced o) and dbias += column sums of gT;
+// keep_bits (optional): the mask as dropout_add_layernorm() stored it, else regenerated from `dr`
 template <typename T>
 int layernorm_bwd_cast(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
-                       DropSpec dr, T* gT, float* dbias, cudaStream_t s);
+                       DropSpec dr, const uint8_t* keep_bits, T* gT, float* dbias, cudaStream_t s);
 // backward of ln_modulate(): din = gradient of `in`; sum_out (optional) = din + dout; d(shift, scale, gate) -> dmodT rows (mod_div == 1)
 // or atomically into dmod32 [M / mod_div, 6H]; dgamma / dbeta of the affine LayerNorm when affine_first
 template <typename T>

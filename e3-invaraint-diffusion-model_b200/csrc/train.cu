@@ -264,6 +264,7 @@ template <typename T> struct LayerTape {
   T *qkv, *ctx, *cq, *ctx2, *f_pre, *f;
   float *o1, *o2, *o3;
   uint32_t *keep_self = nullptr, *keep_cross = nullptr;
+  uint8_t *kb1 = nullptr, *kb2 = nullptr, *kb3 = nullptr;  // hidden-dropout masks of the three post-LN sublayers as bits (forward -> backward)
   DropSpec d_attn, d_o1, d_cattn, d_o2, d_o3;
 };
 
@@ -304,6 +305,7 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     need += 2 * al256(MtH * 6 * es) + al256(MtH * 6 * es) + al256(MtH * 4 * es);  // gradient operands + transposes
     need += al256(static_cast<size_t>(B) * 6 * H * 4) + 4 * al256(static_cast<size_t>(B) * 6 * H * es) + (1 << 20);
     need += static_cast<size_t>(2 * NL + 3) * al256(static_cast<size_t>(2 * B) * heads * 128 * 4 * sizeof(uint32_t));  // attention keep bits
+    need += static_cast<size_t>(3 * NL) * al256(MlH / 8);             // hidden-dropout keep bits of the post-LN sublayers
     need = 2 * need + (64u << 20);  // the tape is carved out while kernels are already being launched: keep a wide safety margin
   }
   if (need > tws_bytes) {
@@ -323,6 +325,18 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     if (dr.p <= 0.f) return gemm_any<T>(M, N, K, X, wsel<T>(W), bias, resid, O, true, s);
     SD_TRY(gemm_any<T>(M, N, K, X, wsel<T>(W), bias, nullptr, O, true, s));
     return dropout_add(O, resid, static_cast<size_t>(M) * N, dr, s);
+  };
+  // o = dropout(x W^T + b) + resid and h = LayerNorm(o): with dropout on, the residual add cannot ride in the GEMM epilogue (the mask sits
+  // between the two), so it is folded into the LayerNorm pass instead of a pass of its own.  SEQDIFF_DROP_LN_FUSE=0: separate launches.
+  static const bool drop_ln_fuse = [] { const char* e = getenv("SEQDIFF_DROP_LN_FUSE"); return !e || e[0] != '0'; }();
+  auto lin_res_ln = [&](int M, int N, int K, const T* X, const Wt& W, const float* bias, const float* resid, float* O, const DropSpec& dr,
+                        const float* ln_w, const float* ln_b, const Act2<T>& h, uint8_t* keep_bits) -> int {
+    if (dr.p > 0.f && drop_ln_fuse) {
+      SD_TRY(gemm_any<T>(M, N, K, X, wsel<T>(W), bias, nullptr, O, true, s));
+      return dropout_add_layernorm<T>(O, resid, dr, M, N, ln_w, ln_b, eps, h.s, h.t_out(), keep_bits, s);
+    }
+    SD_TRY(lin_res(M, N, K, X, W, bias, resid, O, dr));
+    return layernorm<T>(O, M, N, ln_w, ln_b, eps, h.s, h.t_out(), nullptr, s);
   };
   // the attention dropout mask travels from the forward to the backward kernel as bits (2 KB per (graph, head)) when both run on the
   // tcgen05 kernels; every other combination regenerates it from the Philox stream
@@ -457,22 +471,24 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     tp.d_cattn = att();
     tp.d_o2 = hid();
     tp.d_o3 = hid();
+    if (k16 && a.p_hidden > 0.f && drop_ln_fuse) {  // written by dropout_add_layernorm, read by the fused LayerNorm backward
+      tp.kb1 = ar.take<uint8_t>(MlH / 8);
+      tp.kb2 = ar.take<uint8_t>(MlH / 8);
+      tp.kb3 = ar.take<uint8_t>(MlH / 8);
+    }
     SD_TRY(lin_T(Ml, 3 * H, H, h.t, w.self.qkv, w.self.qkv_b, tp.qkv));
     tp.keep_self = keep_buf(B, Ll, Ll);
     SD_TRY(attn_fwd(B, Ll, Ll, tp.qkv, 3 * H, tp.qkv + H, 3 * H, tp.qkv + 2 * H, 3 * H, cfg.relative_key ? &w.self.E : nullptr, a.lig_mask, tp.d_attn,
                     tp.ctx, tp.keep_self));
-    SD_TRY(lin_res(Ml, H, H, tp.ctx, w.self.out, w.self.out_b, h.s, tp.o1, tp.d_o1));
-    SD_TRY(layernorm<T>(tp.o1, Ml, H, w.self.ln_w, w.self.ln_b, eps, tp.h1.s, tp.h1.t_out(), nullptr, s));
+    SD_TRY(lin_res_ln(Ml, H, H, tp.ctx, w.self.out, w.self.out_b, h.s, tp.o1, tp.d_o1, w.self.ln_w, w.self.ln_b, tp.h1, tp.kb1));
     SD_TRY(lin_T(Ml, H, H, tp.h1.t, w.cq, w.cq_b, tp.cq));
     const T* kbase = kv_all + static_cast<size_t>(i) * 2 * H;
     tp.keep_cross = keep_buf(B, Ll, Lr);
     SD_TRY(attn_fwd(B, Ll, Lr, tp.cq, H, kbase, NL * 2 * H, kbase + H, NL * 2 * H, nullptr, a.rec_mask, tp.d_cattn, tp.ctx2, tp.keep_cross));
-    SD_TRY(lin_res(Ml, H, H, tp.ctx2, w.cout, w.cout_b, tp.h1.s, tp.o2, tp.d_o2));
-    SD_TRY(layernorm<T>(tp.o2, Ml, H, w.cln_w, w.cln_b, eps, tp.h2.s, tp.h2.t_out(), nullptr, s));
+    SD_TRY(lin_res_ln(Ml, H, H, tp.ctx2, w.cout, w.cout_b, tp.h1.s, tp.o2, tp.d_o2, w.cln_w, w.cln_b, tp.h2, tp.kb2));
     SD_TRY(lin_T(Ml, I, H, tp.h2.t, w.inter, w.inter_b, tp.f_pre));
     SD_TRY(act_fwd<T>(tp.f_pre, static_cast<size_t>(Ml) * I, 1, nodrop, tp.f, s));
-    SD_TRY(lin_res(Ml, H, I, tp.f, w.outd, w.outd_b, tp.h2.s, tp.o3, tp.d_o3));
-    SD_TRY(layernorm<T>(tp.o3, Ml, H, w.oln_w, w.oln_b, eps, tp.h3.s, tp.h3.t_out(), nullptr, s));
+    SD_TRY(lin_res_ln(Ml, H, I, tp.f, w.outd, w.outd_b, tp.h2.s, tp.o3, tp.d_o3, w.oln_w, w.oln_b, tp.h3, tp.kb3));
     h = tp.h3;
   }
 
@@ -620,9 +636,9 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   // masked by the dropout site `dr` in the operand type (gT).  K = fan-in of that Linear (decides the weight-gradient form, tn_ok).
   auto ln_fused = [&](int K) { return ln_bwd_fuse && tn_ok(H, K); };
   auto ln_bwd = [&](const float* dh, const float* o, const float* gamma, float* d_o, float* dgam, float* dbet, const DropSpec& dr, float* dbias,
-                    int K) -> int {
+                    int K, const uint8_t* keep_bits) -> int {
     if constexpr (k16) {
-      if (ln_fused(K)) return layernorm_bwd_cast<T>(dh, o, Ml, H, gamma, eps, d_o, dgam, dbet, dr, gT, dbias, s);
+      if (ln_fused(K)) return layernorm_bwd_cast<T>(dh, o, Ml, H, gamma, eps, d_o, dgam, dbet, dr, keep_bits, gT, dbias, s);
     }
     SD_TRY(layernorm_bwd(dh, o, Ml, H, gamma, eps, d_o, dgam, dbet, s));
     return grad_cast<T>(d_o, MlH, dr, gT, s);
@@ -633,13 +649,13 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     const std::string p = "decoder.layer." + std::to_string(i);
     const size_t MlI = static_cast<size_t>(Ml) * I;
     // h3 = LN(o3); o3 = dropout(f Wod^T + b) + h2; f = GELU(h2 Wi^T + b)
-    SD_TRY(ln_bwd(cur, tp.o3, w.oln_w, s1, g(p + ".output.LayerNorm.weight"), g(p + ".output.LayerNorm.bias"), tp.d_o3, g(p + ".output.dense.bias"), I));
+    SD_TRY(ln_bwd(cur, tp.o3, w.oln_w, s1, g(p + ".output.LayerNorm.weight"), g(p + ".output.LayerNorm.bias"), tp.d_o3, g(p + ".output.dense.bias"), I, tp.kb3));
     SD_TRY(linear_bwd(Ml, H, I, gT, tp.f, w.outd, g(p + ".output.dense.weight"), g(p + ".output.dense.bias"), 1, gT2, nullptr, ln_fused(I)));
     SD_TRY((act_bwd<T, T>(gT2, tp.f_pre, MlI, 1, nodrop, gT, s)));
     SD_TRY(linear_bwd(Ml, I, H, gT, tp.h2.t, w.inter, g(p + ".intermediate.dense.weight"), g(p + ".intermediate.dense.bias"), 2, s2, s1));  // d(h2)
     // h2 = LN(o2); o2 = dropout(ctx2 Wco^T + b) + h1; ctx2 = cross-attention(q = h1 Wcq^T, k | v = receptor projections)
     SD_TRY(ln_bwd(s2, tp.o2, w.cln_w, s1, g(p + ".crossattention.output.LayerNorm.weight"), g(p + ".crossattention.output.LayerNorm.bias"), tp.d_o2,
-                  g(p + ".crossattention.output.dense.bias"), H));
+                  g(p + ".crossattention.output.dense.bias"), H, tp.kb2));
     SD_TRY(linear_bwd(Ml, H, H, gT, tp.ctx2, w.cout, g(p + ".crossattention.output.dense.weight"), g(p + ".crossattention.output.dense.bias"), 1, gT2, nullptr,
                       ln_fused(H)));
     {
@@ -651,7 +667,7 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
     SD_TRY(linear_bwd(Ml, H, H, gT, tp.h1.t, w.cq, g(p + ".crossattention.self.query.weight"), g(p + ".crossattention.self.query.bias"), 2, s2, s1));  // d(h1)
     // h1 = LN(o1); o1 = dropout(ctx Wo^T + b) + h; ctx = self-attention(h Wqkv^T)
     SD_TRY(ln_bwd(s2, tp.o1, w.self.ln_w, s1, g(p + ".attention.output.LayerNorm.weight"), g(p + ".attention.output.LayerNorm.bias"), tp.d_o1,
-                  g(p + ".attention.output.dense.bias"), H));
+                  g(p + ".attention.output.dense.bias"), H, tp.kb1));
     SD_TRY(linear_bwd(Ml, H, H, gT, tp.ctx, w.self.out, g(p + ".attention.output.dense.weight"), g(p + ".attention.output.dense.bias"), 1, gT2, nullptr,
                       ln_fused(H)));
     SD_TRY(attn_bwd(B, Ll, Ll, tp.qkv, 3 * H, tp.qkv + H, 3 * H, tp.qkv + 2 * H, 3 * H, cfg.relative_key ? &w.self.E : nullptr, a.lig_mask, tp.d_attn, gT2, gT,

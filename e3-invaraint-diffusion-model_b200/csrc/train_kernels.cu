@@ -286,6 +286,64 @@ int dropout_add(float* d, const float* resid, size_t n, DropSpec dr, cudaStream_
   SD_LAUNCHED("dropout_add", s);
   return SEQDIFF_OK;
 }
+// o = dropout(d) + resid (in place on d) AND h = LayerNorm(o) * w + b in one pass: the post-LN sublayers of the decoder
+// (BertSelfOutput / BertOutput: dense -> dropout -> + residual -> LayerNorm).  o stays in memory for the backward pass; compared with
+// dropout_add + layernorm the row is read and written once less (100 MB per launch at 16384 x 768) and one launch disappears.
+// keep_bits (optional): the mask of the row as bits -- byte [row][i][lane] holds the 8 keep flags of elements (i * 32 + lane) * 8 .. + 7 --
+// so that the LayerNorm backward of this sublayer does not have to regenerate it from Philox (half of its instruction stream).
+template <typename T, int VPL>
+__global__ void __launch_bounds__(kTrThreads) dropout_add_layernorm_kernel(float* __restrict__ d, const float* __restrict__ resid, DropSpec dr, int M,
+                                                                           int H, const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                                                           float* __restrict__ out32, T* __restrict__ outT,
+                                                                           uint8_t* __restrict__ keep_bits) {
+  SD_TRAIN_PDL_PROLOGUE();
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * kTrThreads + threadIdx.x) >> 5;
+  if (row >= M) return;
+  float v[VPL][8], r[VPL][8];
+  ld_row<float, VPL>(d + static_cast<size_t>(row) * H, lane, v);
+  ld_row<float, VPL>(resid + static_cast<size_t>(row) * H, lane, r);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float keep[8];
+    drop_scales8(dr, static_cast<size_t>(row) * H + (i * 32 + lane) * 8, keep);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[i][j] = fmaf(v[i][j], keep[j], r[i][j]);
+      bits |= (keep[j] != 0.f ? 1u : 0u) << j;
+    }
+    if (keep_bits) keep_bits[static_cast<size_t>(row) * (H / 8) + i * 32 + lane] = static_cast<uint8_t>(bits);
+  }
+  st_row<float, VPL>(d + static_cast<size_t>(row) * H, lane, v);
+  float mean, rstd;
+  stats_of<VPL>(v, H, eps, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float g8[8], b8[8];
+    load8<float>(w + (i * 32 + lane) * 8, g8);
+    load8<float>(b + (i * 32 + lane) * 8, b8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * g8[j] + b8[j];
+  }
+  if (out32) st_row<float, VPL>(out32 + static_cast<size_t>(row) * H, lane, v);
+  if (outT) st_row<T, VPL>(outT + static_cast<size_t>(row) * H, lane, v);
+}
+template <typename T>
+int dropout_add_layernorm(float* d, const float* resid, DropSpec dr, int M, int H, const float* w, const float* b, float eps, float* out32, T* outT,
+                          uint8_t* keep_bits, cudaStream_t s) {
+  SD_CHECK(M > 0 && resid, "dropout_add_layernorm: empty input");
+  SD_VPL_DISPATCH(H, SD_CUDA(launch_k(dropout_add_layernorm_kernel<T, VPL>, dim3(ceil_div(M, kTrThreads / 32)), dim3(kTrThreads), 0, s, d, resid, dr, M,
+                                      H, w, b, eps, out32, outT, keep_bits)));
+  SD_LAUNCHED("dropout_add_ln", s);
+  return SEQDIFF_OK;
+}
+template int dropout_add_layernorm<float>(float*, const float*, DropSpec, int, int, const float*, const float*, float, float*, float*, uint8_t*,
+                                          cudaStream_t);
+template int dropout_add_layernorm<bf16>(float*, const float*, DropSpec, int, int, const float*, const float*, float, float*, bf16*, uint8_t*,
+                                         cudaStream_t);
+template int dropout_add_layernorm<f16>(float*, const float*, DropSpec, int, int, const float*, const float*, float, float*, f16*, uint8_t*,
+                                        cudaStream_t);
 // gT = T(g * keep): the fp32 gradient of a (dropout-ed) Linear output as the 16-bit operand of its backward GEMMs
 template <typename T>
 __global__ void __launch_bounds__(256) grad_cast_kernel(const float* __restrict__ g, size_t n8, DropSpec dr, T* __restrict__ out) {
@@ -335,31 +393,23 @@ __device__ __forceinline__ void flush_feature_sums(float (&acc)[VPL][8], float* 
   __syncthreads();
 }
 
-// Ampere-style asynchronous 16-byte copies global -> shared (LDGSTS): the prefetch of a warp's NEXT row under the reductions of its
-// current one.  Each lane copies and later reads only its own chunks, so no barrier is involved: wait_group orders a thread's own copies.
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // FUSE: the gradient d_o is also the dY of the Linear that produced o (o = dropout(x W^T + b) + resid), so the same pass writes the
 // 16-bit GEMM operand gT = T(d_o * keep) and adds its column sums (the bias gradient, summed over the values the weight-gradient GEMM
-// reads) into dbias -- one grad_cast and one colsum launch less per LayerNorm, and d_o is not re-read twice.
-// PIPE: the three register accumulator sets cap the kernel at one 8-warp CTA per SM, and a warp's row is a serial chain (load 6 KB ->
-// four warp reductions -> store), so the loads of a row were exposed (59 us per launch at 16384 x 768 against 27 us of HBM traffic).
-// With PIPE every warp double-buffers its rows in shared memory: the o / dh rows of its next row are in flight (cp.async) while it
-// reduces the current one.  Staging layout per array: chunk (i, half, lane) at float offset i * 256 + half * 128 + lane * 4 (conflict-free
-// 16-byte reads).
-template <int VPL, typename T, bool FUSE, bool PIPE = false>
+// reads) into dbias -- one grad_cast and one colsum launch less per LayerNorm, and d_o is not re-read twice.  keep_bits (optional): the
+// dropout mask as the forward pass left it (dropout_add_layernorm), else it is regenerated from Philox.
+// The three register accumulator sets cap the kernel at one 8-warp CTA per SM; at two warps per scheduler it is bound by the issue latency
+// of each warp's serial instruction stream, not by its loads: prefetching a warp's next row with cp.async into a per-warp double buffer
+// was measured SLOWER (72 vs 60 us per launch at 16384 x 768, profiles/train_iter12_r02.log) and is not kept; a 128-register build with
+// two CTAs per SM spills the accumulators (67 us).  What does help is a shorter stream: the mask bits instead of six Philox calls per row.
+template <int VPL, typename T, bool FUSE>
 __global__ void __launch_bounds__(kTrThreads) layernorm_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ o, int M, int H,
                                                                    const float* __restrict__ gamma, float eps, float* __restrict__ d_o,
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta, DropSpec dr,
-                                                                   T* __restrict__ gT, float* __restrict__ dbias) {
+                                                                   T* __restrict__ gT, float* __restrict__ dbias,
+                                                                   const uint8_t* __restrict__ keep_bits) {
   SD_TRAIN_PDL_PROLOGUE();
   constexpr int NACC = FUSE ? 3 : 2;
-  extern __shared__ float sacc[];  // [NACC][H] feature sums, then (PIPE) [8 warps][2 stages][o row | dh row][H]
+  extern __shared__ float sacc[];  // [NACC][H]
   for (int e = threadIdx.x; e < NACC * H; e += kTrThreads) sacc[e] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -372,46 +422,15 @@ __global__ void __launch_bounds__(kTrThreads) layernorm_bwd_kernel(const float* 
       ab[i][j] = 0.f;
       if (FUSE) ad[FUSE ? i : 0][j] = 0.f;
     }
-  const int stride = gridDim.x * (kTrThreads / 32);
-  int row = blockIdx.x * (kTrThreads / 32) + warp;
-  float* stage = sacc + NACC * H + static_cast<size_t>(warp) * 4 * H;
-  auto prefetch = [&](int r, int st) {  // always commits a group (possibly empty) so that wait_group<1> counts uniformly
-    if (r < M) {
-      float* so = stage + static_cast<size_t>(st) * 2 * H;
-      float* sd = so + H;
-      const float* go = o + static_cast<size_t>(r) * H;
-      const float* gd = dh + static_cast<size_t>(r) * H;
-#pragma unroll
-      for (int i = 0; i < VPL; ++i)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = (i * 32 + lane) * 8 + h * 4, si = i * 256 + h * 128 + lane * 4;
-          cp_async16(so + si, go + c);
-          cp_async16(sd + si, gd + c);
-        }
-    }
-    cp_async_commit();
-  };
-  if (PIPE) prefetch(row, 0);
-  for (int it = 0; row < M; row += stride, ++it) {
+  const float keep_scale = dr.p > 0.f ? 1.0f / (1.0f - dr.p) : 1.0f;  // as drop_scales8
+  for (int row = blockIdx.x * (kTrThreads / 32) + warp; row < M; row += gridDim.x * (kTrThreads / 32)) {
     float x[VPL][8], g[VPL][8];
-    if (PIPE) {
-      prefetch(row + stride, (it + 1) & 1);
-      cp_async_wait<1>();  // everything but the newest group: this row's copies have landed
-      const float* so = stage + static_cast<size_t>(it & 1) * 2 * H;
-      const float* sd = so + H;
+    ld_row<float, VPL>(o + static_cast<size_t>(row) * H, lane, x);
+    ld_row<float, VPL>(dh + static_cast<size_t>(row) * H, lane, g);
+    uint32_t kb[VPL];
+    if (FUSE && keep_bits) {
 #pragma unroll
-      for (int i = 0; i < VPL; ++i)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int si = i * 256 + h * 128 + lane * 4;
-          const float4 a = *reinterpret_cast<const float4*>(so + si), b = *reinterpret_cast<const float4*>(sd + si);
-          x[i][h * 4 + 0] = a.x; x[i][h * 4 + 1] = a.y; x[i][h * 4 + 2] = a.z; x[i][h * 4 + 3] = a.w;
-          g[i][h * 4 + 0] = b.x; g[i][h * 4 + 1] = b.y; g[i][h * 4 + 2] = b.z; g[i][h * 4 + 3] = b.w;
-        }
-    } else {
-      ld_row<float, VPL>(o + static_cast<size_t>(row) * H, lane, x);
-      ld_row<float, VPL>(dh + static_cast<size_t>(row) * H, lane, g);
+      for (int i = 0; i < VPL; ++i) kb[i] = keep_bits[static_cast<size_t>(row) * (H / 8) + i * 32 + lane];
     }
     float mean, rstd;
     stats_of<VPL>(x, H, eps, mean, rstd);
@@ -434,7 +453,12 @@ __global__ void __launch_bounds__(kTrThreads) layernorm_bwd_kernel(const float* 
       for (int i = 0; i < VPL; ++i) {
         const size_t e0 = static_cast<size_t>(row) * H + (i * 32 + lane) * 8;
         float keep[8];
-        drop_scales8(dr, e0, keep);
+        if (keep_bits) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) keep[j] = (kb[i] >> j) & 1u ? keep_scale : 0.f;
+        } else {
+          drop_scales8(dr, e0, keep);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           g[i][j] = to_f32<T>(from_f32<T>(g[i][j] * keep[j]));  // the value the backward GEMMs will read
@@ -444,7 +468,6 @@ __global__ void __launch_bounds__(kTrThreads) layernorm_bwd_kernel(const float* 
       }
     }
   }
-  if (PIPE) cp_async_wait<0>();
   flush_feature_sums<VPL>(ag, dgamma, sacc, H, lane);
   flush_feature_sums<VPL>(ab, dbeta, sacc + H, H, lane);
   if constexpr (FUSE) flush_feature_sums<VPL>(ad, dbias, sacc + 2 * H, H, lane);
@@ -464,39 +487,26 @@ static int ln_bwd_resident_grid(K kernel, size_t smem, int M) {
 int layernorm_bwd(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
                   cudaStream_t s) {
   SD_VPL_DISPATCH(H, SD_CUDA(launch_k(layernorm_bwd_kernel<VPL, float, false>, dim3(ln_bwd_grid(M)), dim3(kTrThreads), 2 * H * sizeof(float), s, dh, o,
-                                      M, H, gamma, eps, d_o, dgamma, dbeta, no_drop(), static_cast<float*>(nullptr), static_cast<float*>(nullptr))));
+                                      M, H, gamma, eps, d_o, dgamma, dbeta, no_drop(), static_cast<float*>(nullptr), static_cast<float*>(nullptr),
+                                      static_cast<const uint8_t*>(nullptr))));
   SD_LAUNCHED("layernorm_bwd", s);
   return SEQDIFF_OK;
 }
 template <typename T>
 int layernorm_bwd_cast(const float* dh, const float* o, int M, int H, const float* gamma, float eps, float* d_o, float* dgamma, float* dbeta,
-                       DropSpec dr, T* gT, float* dbias, cudaStream_t s) {
+                       DropSpec dr, const uint8_t* keep_bits, T* gT, float* dbias, cudaStream_t s) {
   SD_CHECK(gT && dbias, "layernorm_bwd_cast: operand and bias-gradient outputs are required");
-  // SEQDIFF_LNBWD_PIPE=0: rows loaded straight into registers (no cp.async double buffer)
-  static const bool pipe = [] { const char* e = getenv("SEQDIFF_LNBWD_PIPE"); return !e || e[0] != '0'; }();
-  if (pipe) {
-    const size_t smem = (3 + (kTrThreads / 32) * 4) * static_cast<size_t>(H) * sizeof(float);  // 108 KB at H = 768
-    SD_VPL_DISPATCH(H, auto kfn = layernorm_bwd_kernel<VPL, T, true, true>;
-                    static bool configured = false;
-                    if (!configured) {
-                      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 + (kTrThreads / 32) * 4) * 256 * VPL * 4));
-                      configured = true;
-                    }
-                    SD_CUDA(launch_k(kfn, dim3(ln_bwd_resident_grid(kfn, smem, M)), dim3(kTrThreads), smem, s, dh, o, M, H, gamma, eps, d_o, dgamma,
-                                     dbeta, dr, gT, dbias)));
-  } else {
-    const size_t smem = 3 * static_cast<size_t>(H) * sizeof(float);
-    SD_VPL_DISPATCH(H, auto kfn = layernorm_bwd_kernel<VPL, T, true>;
-                    SD_CUDA(launch_k(kfn, dim3(ln_bwd_resident_grid(kfn, smem, M)), dim3(kTrThreads), smem, s, dh, o, M, H, gamma, eps, d_o, dgamma,
-                                     dbeta, dr, gT, dbias)));
-  }
+  const size_t smem = 3 * static_cast<size_t>(H) * sizeof(float);
+  SD_VPL_DISPATCH(H, auto kfn = layernorm_bwd_kernel<VPL, T, true>;
+                  SD_CUDA(launch_k(kfn, dim3(ln_bwd_resident_grid(kfn, smem, M)), dim3(kTrThreads), smem, s, dh, o, M, H, gamma, eps, d_o, dgamma,
+                                   dbeta, dr, gT, dbias, dr.p > 0.f ? keep_bits : nullptr)));
   SD_LAUNCHED("layernorm_bwd", s);
   return SEQDIFF_OK;
 }
-template int layernorm_bwd_cast<bf16>(const float*, const float*, int, int, const float*, float, float*, float*, float*, DropSpec, bf16*, float*,
-                                      cudaStream_t);
-template int layernorm_bwd_cast<f16>(const float*, const float*, int, int, const float*, float, float*, float*, float*, DropSpec, f16*, float*,
-                                     cudaStream_t);
+template int layernorm_bwd_cast<bf16>(const float*, const float*, int, int, const float*, float, float*, float*, float*, DropSpec, const uint8_t*,
+                                      bf16*, float*, cudaStream_t);
+template int layernorm_bwd_cast<f16>(const float*, const float*, int, int, const float*, float, float*, float*, float*, DropSpec, const uint8_t*,
+                                     f16*, float*, cudaStream_t);
 
 // =====================================================================================================
 // SELayer residual update backward (forward: rowwise.cu ln_modulate_kernel)

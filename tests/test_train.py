@@ -180,6 +180,64 @@ def test_gradient_parity_16bit(precision, l2_tol):
             a, b = flat.grad(k).cpu(), grads_ref[k].reshape(-1)
             cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
             assert cos > 0.999, (k, cos)
+    # the small tensors too (biases, LayerNorm affine, distance embeddings): they vanish in the flat L2 norm, and their gradients come out of
+    # the fused rowwise kernels (LayerNorm backward that also emits the bias gradient of the Linear in front of it, embedding backward)
+    worst = _worst_small_tensor_cosine(flat, m, grads_ref)
+    print(f"{precision}: worst cosine over the small gradient tensors {worst[0]:.5f} ({worst[1]})")
+    assert worst[0] > SMALL_COS[precision], worst
+    m.release()
+
+
+SMALL_COS = {"bf16": 0.98, "fp16": 0.999}
+
+
+def _worst_small_tensor_cosine(flat, m, grads_ref):
+    gmax = max(float(v.norm()) for v in grads_ref.values() if v is not None)
+    worst = (1.0, "")
+    for k, prm in m.named_parameters():
+        if k not in flat.table or prm.numel() >= 768 * 768:
+            continue
+        a, b = flat.grad(k).cpu().double(), grads_ref[k].reshape(-1).double()
+        if float(b.norm()) < 1e-4 * gmax:  # gradients that are ~0 (e.g. decoder_normalize gates at the reference init) have no direction
+            continue
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        if cos < worst[0]:
+            worst = (cos, k)
+    return worst
+
+
+@gpu
+@pytest.mark.parametrize("precision,l2_tol", [("bf16", 3e-2), ("fp16", 5e-3)])
+def test_gradient_parity_16bit_with_dropout(precision, l2_tol):
+    """p = 0.1 in the 16-bit modes against the fp32 mode UNDER THE SAME MASKS (masks are keyed by (seed, site, step, element), not by the
+    precision): the 16-bit step takes the fused paths the fp32 parity mode does not -- dropout + residual folded into the LayerNorm pass
+    with the mask handed to the backward pass as bits, LayerNorm backward that also writes the masked 16-bit operand and the bias
+    gradient, the tcgen05 attention kernels with their keep bits.  A mask applied at the wrong element shows up as a cosine of ~0.9."""
+    sd = sd_pkg()
+    L, B, NL, n_lig, n_rec, seed, Lr = CASES["cfg4-shape"]
+    cfg, state, batch, t_norm, x_t = _case(L, B, NL, n_lig, n_rec, seed)
+    kw = dict(p_hidden=0.1, p_attn=0.1, seed=23, step=4)
+    m32 = make_model(sd, cfg, state, "fp32", DEV)
+    m32.train()
+    flat32, terms32, _ = _run_train_step(sd, m32, batch, t_norm, x_t, **kw)
+    ref = {k: flat32.grad(k, tuple(prm.shape)).cpu().clone() for k, prm in m32.named_parameters() if k in flat32.table}
+    loss32 = float(sd.train.loss_from_terms(terms32)[0])
+    m32.release()
+    m = make_model(sd, cfg, state, precision, DEV)
+    m.train()
+    flat, terms, _ = _run_train_step(sd, m, batch, t_norm, x_t, **kw)
+    assert float(sd.train.loss_from_terms(terms)[0]) == pytest.approx(loss32, rel=2e-2)
+    got_all = torch.cat([flat.grad(k).cpu() for k in ref])
+    ref_all = torch.cat([v.reshape(-1) for v in ref.values()])
+    l2 = float((got_all - ref_all).norm() / ref_all.norm())
+    worst = _worst_small_tensor_cosine(flat, m, ref)
+    print(f"{precision}, dropout 0.1, vs fp32 mode with the same masks: flat L2 rel err {l2:.3e}; worst small-tensor cosine {worst[0]:.5f} ({worst[1]})")
+    assert l2 < l2_tol, l2
+    assert worst[0] > SMALL_COS[precision], worst
+    for k, v in ref.items():
+        if v.numel() >= 768 * 768:
+            a, b = flat.grad(k).cpu(), v.reshape(-1)
+            assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.999, k
     m.release()
 
 
