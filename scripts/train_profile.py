@@ -34,6 +34,10 @@ for i in range(5):
     model.training_step(dbatch, i); opt.step()
 e1.record(); torch.cuda.synchronize()
 print(f"batch {a.batch} L {a.L} p {a.p} {a.precision}: {e0.elapsed_time(e1)/5:.3f} ms per step (eager, incl. host gaps)")
+if os.environ.get("SEQDIFF_PROFILER_RANGE") == "1":  # ncu --profile-from-start off: exactly one training step + optimizer step
+    torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStart()
+    model.training_step(dbatch, 0); opt.step()
+    torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
 prof = sd._cabi.profile(lambda: (model.training_step(dbatch, 0), opt.step()))
 tot = sum(v[0] for v in prof.values())
 print(f"sum of kernel gaps {tot:.3f} ms, {sum(v[1] for v in prof.values())} launches")

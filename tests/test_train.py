@@ -188,7 +188,7 @@ def test_gradient_parity_16bit(precision, l2_tol):
     m.release()
 
 
-SMALL_COS = {"bf16": 0.98, "fp16": 0.999}
+SMALL_COS = {"bf16": 0.995, "fp16": 0.9999}  # measured on B200: 0.9996 / 0.99999 (dropout off), 0.9998 / 0.99999 (dropout on)
 
 
 def _worst_small_tensor_cosine(flat, m, grads_ref):
