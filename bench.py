@@ -307,11 +307,11 @@ def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return ms.item() / n, r
 
-        n0 = sd.lib().seqdiff_launch_count()
         for i in range(warmup):
             step(i)
-        launches_per_step = (sd.lib().seqdiff_launch_count() - n0) // max(warmup, 1)
+        n0 = sd.lib().seqdiff_launch_count()  # counted over the timed steps (the warm-up steps also hold the GEMM tuner's candidate launches)
         ms_full, loss = timed(lambda i: step(i), steps)                       # bucketed all-reduce under the backward pass
+        launches_per_step = (sd.lib().seqdiff_launch_count() - n0) // max(steps, 1)
         ms_block, _ = timed(lambda i: step(i, overlap=False), steps) if world > 1 else (ms_full, None)  # all-reduce after the backward pass
         ms_nocomm, _ = timed(lambda i: step(i, skip=True), steps)
         opt.overlap = True
