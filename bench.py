@@ -167,6 +167,14 @@ def cpu_reference_steps(state, batch, x_T, T, n_steps, n_warm, threads):
     return times
 
 
+def workload_config(wl, B, T, world):
+    """The `config` object of the JSON line: static description of the workload only, identical on the product and the reference arm
+    (what the reference arm samples of it is said in its `cpu_baseline.sample` / `sample` keys; derived rates live in `derived`)."""
+    return {"workload": wl["text"].format(T=T, B=B), "batch_per_gpu": B, "L": L, "timesteps": T,
+            "sharding": f"graphs x{world} (no data-path collective)",
+            "l2": "per-step working set of activations (0.9 GB at cfg2, ~10 GB at cfg3) >> 126 MB L2 (no explicit flush needed)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -178,6 +186,7 @@ def run_reference_arm(args):
     state = {k: v.detach().clone() for k, v in model.state_dict().items()}
     cpu_b = args.batch if args.workload == "cfg2" else 4  # L=512: a 4-graph sample keeps a step at a few seconds
     batch, x_T = synthetic_workload(cpu_b, n_lig=args.wl["n_lig"], n_rec=args.wl["n_rec"])
+    cfg_obj = workload_config(args.wl, args.batch, args.timesteps, int(os.environ.get("WORLD_SIZE", "1")))  # the product arm's config
     args.batch = cpu_b
     threads = os.cpu_count() or 1
     times = cpu_reference_steps(state, batch, x_T, args.timesteps, args.steps, args.warmup, threads)
@@ -186,8 +195,9 @@ def run_reference_arm(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.workload} sample: one denoise step (forward + reverse step) of a {args.batch}-pocket batch per bench step",
-                      "batch": args.batch, "L": L, "timesteps": args.timesteps, "device": "host CPU"},
+           "config": cfg_obj,
+           "sample": f"each bench step = ONE denoise step (forward + reverse step) of a {args.batch}-pocket batch on the host CPU; the metric is "
+                     "normalised per graph-step, so it compares with the product arm's full samplings (SURVEY.md section 8d)",
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"{len(times)} denoise steps x {args.batch} graphs (of {args.timesteps} steps); oracle port incl. the reference's Python multinomial loop"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -485,10 +495,8 @@ def main():
     result = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": args.precision,
               "data": "synthetic",
-              "config": {"workload": wl["text"].format(T=T, B=B),
-                         "batch_per_gpu": B, "L": L, "timesteps": T, "sharding": f"graphs x{world} (no data-path collective)",
-                         "l2": "per-step working set of activations (0.9 GB at cfg2, ~10 GB at cfg3) >> 126 MB L2 (no explicit flush needed)",
-                         "pocket_graphs_per_s": value / T, "edge_msgs_per_s": value * 15 * L * L},
+              "config": workload_config(wl, B, T, world),
+              "derived": {"pocket_graphs_per_s": value / T, "edge_msgs_per_s": value * 15 * L * L},
               "clocks": clk.summary(), "gpu_launches": int(launches)}
     if packed_rec is not None:
         result["packed"] = packed_rec
