@@ -127,6 +127,14 @@ template int transpose_colsum<f16>(const f16*, int, int, f16*, float*, cudaStrea
 // apart: 8-way conflicts on every one of the ~10 k shared atomics per row -- ncu: embed_bwd 274 us per launch).
 __device__ __forceinline__ int acc_slot(int i, int lane, int j) { return (i * 8 + j) * 32 + lane; }
 __device__ __forceinline__ int acc_slot_of_col(int e) { return acc_slot(e >> 8, (e >> 3) & 31, e & 7); }
+// End-of-kernel flush of per-CTA partial sums into the flat gradient buffer.  Every CTA of the grid adds to the SAME few thousand addresses
+// at the same moment, and same-address atomics serialise in L2 (ncu launch list of a training step: embed_bwd 80 - 113 us per launch, almost
+// all of it the 6 - 15 k scalar atomics per CTA): four consecutive elements go as ONE 128-bit atomic (sm_90+: atomicAdd(float4*)) whenever
+// the destination is 16 B aligned -- a quarter of the operations on the contended addresses.
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ void atomic_add4(float* dst, float a, float b, float c, float d) {
+  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(a, b, c, d));
+}
 
 // column sums of a 16-bit / fp32 [rows, cols] matrix, ADDED into colsum[cols] (pre-zeroed): the bias gradient db = sum over tokens of dY
 // when the weight-gradient GEMM reads dY in place (gemm_16_tn) and no transpose pass exists to fuse it into.
@@ -154,12 +162,25 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, i
 #pragma unroll
   for (int j = 0; j < 8; ++j) part[rl][oct * 8 + j] = acc[j];
   __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < cols) {
-    float sum = 0.f;
+  // rows / 64 CTAs add to the same `cols` addresses: four columns per 128-bit atomic when the destination allows it (cols % 8 == 0)
+  if (aligned16(colsum)) {
+    const int c = blockIdx.x * 256 + 4 * threadIdx.x;
+    if (threadIdx.x < 64 && c < cols) {
+      float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sum += part[i][threadIdx.x];
-    atomicAdd(colsum + c, sum);
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sum[u] += part[i][4 * threadIdx.x + u];
+      atomic_add4(colsum + c, sum[0], sum[1], sum[2], sum[3]);
+    }
+  } else {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += part[i][threadIdx.x];
+      atomicAdd(colsum + c, sum);
+    }
   }
 }
 template <typename T>
@@ -383,13 +404,19 @@ template int act_bwd<f16, float>(const float*, const f16*, size_t, int, DropSpec
 // atomicAdd per feature and CTA.  Grid-stride over rows so that the number of atomics stays ~ #CTAs * H.
 template <int VPL>
 __device__ __forceinline__ void flush_feature_sums(float (&acc)[VPL][8], float* __restrict__ dst, float* smem_acc /*[H]*/, int H, int lane) {
-  // caller has zeroed smem_acc and synchronised
+  // caller has zeroed smem_acc and synchronised; conflict-free slots (acc_slot), four columns per global atomic
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(smem_acc + (i * 32 + lane) * 8 + j, acc[i][j]);
+    for (int j = 0; j < 8; ++j) atomicAdd(smem_acc + acc_slot(i, lane, j), acc[i][j]);
   __syncthreads();
-  for (int e = threadIdx.x; e < H; e += blockDim.x) atomicAdd(dst + e, smem_acc[e]);
+  if (aligned16(dst)) {
+    for (int e = 4 * threadIdx.x; e < H; e += 4 * blockDim.x)
+      atomic_add4(dst + e, smem_acc[acc_slot_of_col(e)], smem_acc[acc_slot_of_col(e + 1)], smem_acc[acc_slot_of_col(e + 2)],
+                  smem_acc[acc_slot_of_col(e + 3)]);
+  } else {
+    for (int e = threadIdx.x; e < H; e += blockDim.x) atomicAdd(dst + e, smem_acc[acc_slot_of_col(e)]);
+  }
   __syncthreads();
 }
 
@@ -797,12 +824,28 @@ __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __re
       atomicAdd(sacc + (base_acc + 2) * H + e, a_dbt[i][j]);
     }
   __syncthreads();
+  // dW is [H, fin] (nn.Linear layout): the fin values of one output column are contiguous
+  const bool w4 = aligned16(dW) && fin % 4 == 0;
   if constexpr (DENSE) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i)
+    for (int i = 0; i < VPL; ++i) {
+      float* col = dW + static_cast<size_t>(i * 256 + threadIdx.x) * fin;
+      if (w4 && fin == 8) {
+        atomic_add4(col, a_w[0][i], a_w[1][i], a_w[2][i], a_w[3][i]);
+        atomic_add4(col + 4, a_w[4][i], a_w[5][i], a_w[6][i], a_w[7][i]);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (k < fin && a_w[k][i] != 0.f) atomicAdd(dW + static_cast<size_t>(i * 256 + threadIdx.x) * fin + k, a_w[k][i]);
+        for (int k = 0; k < 8; ++k)
+          if (k < fin && a_w[k][i] != 0.f) atomicAdd(col + k, a_w[k][i]);
+      }
+    }
+  } else if (w4) {
+    const int q = fin / 4;  // groups of four input features per output column
+    for (int e = threadIdx.x; e < q * H; e += kTrThreads) {
+      const int h = e / q, k = (e - h * q) * 4, sl = acc_slot_of_col(h);
+      const float v0 = sacc[k * H + sl], v1 = sacc[(k + 1) * H + sl], v2 = sacc[(k + 2) * H + sl], v3 = sacc[(k + 3) * H + sl];
+      if (v0 != 0.f || v1 != 0.f || v2 != 0.f || v3 != 0.f) atomic_add4(dW + static_cast<size_t>(h) * fin + k, v0, v1, v2, v3);
+    }
   } else {
     for (int e = threadIdx.x; e < fin * H; e += kTrThreads) {
       const int k = e / H, h = e - k * H;
@@ -810,11 +853,20 @@ __global__ void __launch_bounds__(kTrThreads) embed_bwd_kernel(const float* __re
       if (v != 0.f) atomicAdd(dW + static_cast<size_t>(h) * fin + k, v);
     }
   }
-  for (int e = threadIdx.x; e < H; e += kTrThreads) {
-    const int sl = acc_slot_of_col(e);
-    atomicAdd(db + e, sacc[base_acc * H + sl]);
-    atomicAdd(dgamma + e, sacc[(base_acc + 1) * H + sl]);
-    atomicAdd(dbeta + e, sacc[(base_acc + 2) * H + sl]);
+  if (aligned16(db) && aligned16(dgamma) && aligned16(dbeta)) {
+    for (int e = 4 * threadIdx.x; e < H; e += 4 * kTrThreads) {
+      const int s0 = acc_slot_of_col(e), s1 = acc_slot_of_col(e + 1), s2 = acc_slot_of_col(e + 2), s3 = acc_slot_of_col(e + 3);
+      atomic_add4(db + e, sacc[base_acc * H + s0], sacc[base_acc * H + s1], sacc[base_acc * H + s2], sacc[base_acc * H + s3]);
+      atomic_add4(dgamma + e, sacc[(base_acc + 1) * H + s0], sacc[(base_acc + 1) * H + s1], sacc[(base_acc + 1) * H + s2], sacc[(base_acc + 1) * H + s3]);
+      atomic_add4(dbeta + e, sacc[(base_acc + 2) * H + s0], sacc[(base_acc + 2) * H + s1], sacc[(base_acc + 2) * H + s2], sacc[(base_acc + 2) * H + s3]);
+    }
+  } else {
+    for (int e = threadIdx.x; e < H; e += kTrThreads) {
+      const int sl = acc_slot_of_col(e);
+      atomicAdd(db + e, sacc[base_acc * H + sl]);
+      atomicAdd(dgamma + e, sacc[(base_acc + 1) * H + sl]);
+      atomicAdd(dbeta + e, sacc[(base_acc + 2) * H + sl]);
+    }
   }
 }
 int embed_bwd(const float* dout, const float* x, int M, int fin, int H, const float* Wt, const float* b, const float* gamma, float eps, DropSpec dr,
@@ -919,15 +971,29 @@ __global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd_kernel(const fl
     st_row<float, VPL>(dy + static_cast<size_t>(row) * H, lane, g);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < F * H; i += kTrThreads) {
-    const int f = i / H, c = i - f * H;
-    const float x = sdW[f * H + acc_slot_of_col(c)];
-    if (x != 0.f) atomicAdd(dW2 + i, x);
-  }
-  for (int i = threadIdx.x; i < H; i += kTrThreads) {
-    const int sl = acc_slot_of_col(i);
-    atomicAdd(dgamma + i, sG[sl]);
-    atomicAdd(dbeta + i, sG[H + sl]);
+  if (aligned16(dW2) && aligned16(dgamma) && aligned16(dbeta)) {  // H % 4 == 0: four consecutive columns per 128-bit atomic
+    for (int i = 4 * threadIdx.x; i < F * H; i += 4 * kTrThreads) {
+      const int f = i / H, c = i - f * H;
+      const float x0 = sdW[f * H + acc_slot_of_col(c)], x1 = sdW[f * H + acc_slot_of_col(c + 1)], x2 = sdW[f * H + acc_slot_of_col(c + 2)],
+                  x3 = sdW[f * H + acc_slot_of_col(c + 3)];
+      if (x0 != 0.f || x1 != 0.f || x2 != 0.f || x3 != 0.f) atomic_add4(dW2 + i, x0, x1, x2, x3);
+    }
+    for (int i = 4 * threadIdx.x; i < H; i += 4 * kTrThreads) {
+      const int s0 = acc_slot_of_col(i), s1 = acc_slot_of_col(i + 1), s2 = acc_slot_of_col(i + 2), s3 = acc_slot_of_col(i + 3);
+      atomic_add4(dgamma + i, sG[s0], sG[s1], sG[s2], sG[s3]);
+      atomic_add4(dbeta + i, sG[H + s0], sG[H + s1], sG[H + s2], sG[H + s3]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < F * H; i += kTrThreads) {
+      const int f = i / H, c = i - f * H;
+      const float x = sdW[f * H + acc_slot_of_col(c)];
+      if (x != 0.f) atomicAdd(dW2 + i, x);
+    }
+    for (int i = threadIdx.x; i < H; i += kTrThreads) {
+      const int sl = acc_slot_of_col(i);
+      atomicAdd(dgamma + i, sG[sl]);
+      atomicAdd(dbeta + i, sG[H + sl]);
+    }
   }
   if (threadIdx.x < F) atomicAdd(db2 + threadIdx.x, sB[threadIdx.x]);
 }
