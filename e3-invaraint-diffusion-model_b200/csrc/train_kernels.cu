@@ -997,6 +997,119 @@ __global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd_kernel(const fl
   }
   if (threadIdx.x < F) atomicAdd(db2 + threadIdx.x, sB[threadIdx.x]);
 }
+// The same for F == 20 (the amino-acid head; seqdiff_train_step requires it) without the F * H / 32 = 480 shared atomics per lane and live row
+// that bound the kernel above (284 us per launch at 16384 rows): the eight warps of a CTA park LN(y) and dlogits of their rows in shared
+// memory, and after a barrier every THREAD owns H / 256 columns of dW2 for all 20 classes in registers (60 accumulators, plain FMAs on
+// conflict-free reads); dgamma / dbeta accumulate in per-warp registers and meet once per CTA (flush_feature_sums).
+template <typename T, int VPL>
+__global__ void __launch_bounds__(kTrThreads) predictor_tail_bwd20_kernel(const float* __restrict__ dlogits, const T* __restrict__ y, int M, int H,
+                                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                          const float* __restrict__ W2, float* __restrict__ dy,
+                                                                          float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dgamma,
+                                                                          float* __restrict__ dbeta) {
+  SD_TRAIN_PDL_PROLOGUE();
+  constexpr int F = 20, NW = kTrThreads / 32;
+  extern __shared__ float smem[];
+  float* sW = smem;                                   // [F][H]   W2
+  float* sG = sW + static_cast<size_t>(F) * H;        // [2][H]   dgamma | dbeta (flush)
+  float* sln = sG + 2 * H;                            // [NW][H]  LN(y) rows of the current pass
+  float* sdl = sln + static_cast<size_t>(NW) * H;     // [NW][32] dlogits rows of the current pass (zero = dead row / lane >= F)
+  float* sB = sdl + NW * 32;                          // [32]     db2
+  for (int i = threadIdx.x; i < F * H; i += kTrThreads) sW[i] = W2[i];
+  for (int i = threadIdx.x; i < 2 * H; i += kTrThreads) sG[i] = 0.f;
+  if (threadIdx.x < 32) sB[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float a_w[F][VPL], ag[VPL][8], ab[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int f = 0; f < F; ++f) a_w[f][i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
+  }
+  for (int row0 = blockIdx.x * NW; row0 < M; row0 += gridDim.x * NW) {  // CTA-uniform passes of NW rows (barriers inside)
+    const int row = row0 + warp;
+    float dl = 0.f;
+    if (row < M) {
+      float v[VPL][8], g[VPL][8], ln[VPL][8];
+      ld_row<T, VPL>(y + static_cast<size_t>(row) * H, lane, v);
+      float mean, rstd;
+      stats_of<VPL>(v, H, eps, mean, rstd);
+      dl = lane < F ? dlogits[static_cast<size_t>(row) * F + lane] : 0.f;
+      if (dl != 0.f) atomicAdd(sB + lane, dl);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float w8[8], b8[8];
+        load8<float>(gamma + (i * 32 + lane) * 8, w8);
+        load8<float>(beta + (i * 32 + lane) * 8, b8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[i][j] = (v[i][j] - mean) * rstd;
+          ln[i][j] = v[i][j] * w8[j] + b8[j];
+          g[i][j] = 0.f;
+        }
+      }
+      const bool any = __ballot_sync(0xffffffffu, dl != 0.f) != 0u;  // rows outside the noised set carry a zero gradient: skipped entirely
+      if (any) {
+        st_row<float, VPL>(sln + static_cast<size_t>(warp) * H, lane, ln);
+        for (int f = 0; f < F; ++f) {
+          const float d = __shfl_sync(0xffffffffu, dl, f);
+          if (d == 0.f) continue;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            float w8[8];
+            load8<float>(sW + static_cast<size_t>(f) * H + (i * 32 + lane) * 8, w8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[i][j] = fmaf(d, w8[j], g[i][j]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          float w8[8];
+          load8<float>(gamma + (i * 32 + lane) * 8, w8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ag[i][j] = fmaf(g[i][j], v[i][j], ag[i][j]);
+            ab[i][j] += g[i][j];
+            g[i][j] *= w8[j];
+          }
+        }
+        ln_bwd_core<VPL>(v, g, H, rstd);
+      }
+      st_row<float, VPL>(dy + static_cast<size_t>(row) * H, lane, g);
+    }
+    sdl[warp * 32 + lane] = dl;
+    __syncthreads();
+#pragma unroll 1
+    for (int w = 0; w < NW; ++w) {
+      float lnv[VPL];
+      bool live = false;
+      float d[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        d[f] = sdl[w * 32 + f];
+        live = live || d[f] != 0.f;
+      }
+      if (!live) continue;  // CTA-uniform (shared values): its sln row may be stale
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) lnv[i] = sln[static_cast<size_t>(w) * H + i * 256 + threadIdx.x];
+#pragma unroll
+      for (int f = 0; f < F; ++f)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) a_w[f][i] = fmaf(d[f], lnv[i], a_w[f][i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int f = 0; f < F; ++f)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (a_w[f][i] != 0.f) atomicAdd(dW2 + static_cast<size_t>(f) * H + i * 256 + threadIdx.x, a_w[f][i]);
+  flush_feature_sums<VPL>(ag, dgamma, sG, H, lane);
+  flush_feature_sums<VPL>(ab, dbeta, sG + H, H, lane);
+  if (threadIdx.x < F) atomicAdd(db2 + threadIdx.x, sB[threadIdx.x]);
+}
 template <typename T>
 int predictor_tail_bwd(const float* dlogits, const T* y, int M, int H, const float* gamma, const float* beta, float eps, const float* W2, int F,
                        float* dy, float* dW2, float* db2, float* dgamma, float* dbeta, cudaStream_t s) {
@@ -1013,6 +1126,25 @@ int predictor_tail_bwd(const float* dlogits, const T* y, int M, int H, const flo
       configured = true;                                                                                             \
     }                                                                                                                \
     SD_CUDA(launch_k(kfn, dim3(grid), dim3(kTrThreads), smem, s, dlogits, y, M, H, gamma, beta, eps, W2, F, dy, dW2, db2, dgamma, dbeta)); \
+  }
+  // SEQDIFF_PTB_DENSE=0: the generic (shared-atomic) kernel also for F == 20
+  static const bool dense_ok = [] { const char* e = getenv("SEQDIFF_PTB_DENSE"); return !e || e[0] != '0'; }();
+  if (dense_ok && F == 20) {
+    const size_t smem20 = (static_cast<size_t>(20 + 2 + kTrThreads / 32) * H + (kTrThreads / 32) * 32 + 32) * sizeof(float);
+#define SD_PTB20_LAUNCH()                                                                                            \
+  {                                                                                                                  \
+    auto kfn = predictor_tail_bwd20_kernel<T, VPL>;                                                                  \
+    static bool configured = false;                                                                                  \
+    if (!configured) {                                                                                               \
+      SD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                   \
+      configured = true;                                                                                             \
+    }                                                                                                                \
+    SD_CUDA(launch_k(kfn, dim3(grid), dim3(kTrThreads), smem20, s, dlogits, y, M, H, gamma, beta, eps, W2, dy, dW2, db2, dgamma, dbeta)); \
+  }
+    SD_VPL_DISPATCH(H, SD_PTB20_LAUNCH());
+#undef SD_PTB20_LAUNCH
+    SD_LAUNCHED("predictor_tail_bwd", s);
+    return SEQDIFF_OK;
   }
   SD_VPL_DISPATCH(H, SD_PTB_LAUNCH());
 #undef SD_PTB_LAUNCH
