@@ -183,18 +183,38 @@ __global__ void __launch_bounds__(kLossThreads) loss_terms_kernel(int N, const f
   }
 }
 
-int loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* mask, double* terms, cudaStream_t s) {
+size_t loss_terms_scratch_bytes() { return (static_cast<size_t>(kLossMaxCtas) * kLossTerms + 2) * sizeof(double); }
+int loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* mask, double* terms, cudaStream_t s, double* scratch_in) {
   SD_CHECK(N > 0, "empty loss");
-  // per-CTA partials + arrival counter: stream-ordered scratch, so concurrent calls on different streams never share it
   int ctas = ceil_div(N, kLossThreads);
   if (ctas > kLossMaxCtas) ctas = kLossMaxCtas;
   const size_t bytes = (static_cast<size_t>(ctas) * kLossTerms + 2) * sizeof(double);
-  double* scratch = nullptr;
-  SD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, s));
+  // per-CTA partials + arrival counter.  The training step hands in scratch from its own workspace (loss_terms_scratch_bytes()): a
+  // cudaMallocAsync per optimizer step can stall the launching thread for milliseconds whenever the pool has been trimmed at a
+  // synchronisation (seen as 3 - 90 ms gaps in front of this launch in the per-kernel profiles of the training step).  The stand-alone
+  // entry point keeps stream-ordered scratch, so concurrent calls on different streams never share it, with the pool told to keep
+  // what it has instead of returning it to the OS at every synchronisation.
+  double* scratch = scratch_in;
+  if (!scratch) {
+    static const bool pool_kept = [] {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = 64ull << 20;  // bytes the pool may hold across synchronisations (this scratch is 24 KB)
+        uint64_t cur = 0;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      return true;
+    }();
+    (void)pool_kept;
+    SD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, s));
+  }
   unsigned* arrive = reinterpret_cast<unsigned*>(scratch + static_cast<size_t>(ctas) * kLossTerms);
   cudaError_t e = cudaMemsetAsync(arrive, 0, 2 * sizeof(double), s);
   if (e == cudaSuccess) e = launch_k(loss_terms_kernel, dim3(ctas), dim3(kLossThreads), 0, s, N, logits, x0, x_t, mask, scratch, arrive, terms);
-  const cudaError_t ef = cudaFreeAsync(scratch, s);
+  const cudaError_t ef = scratch_in ? cudaSuccess : cudaFreeAsync(scratch, s);
   SD_CUDA(e);
   SD_CUDA(ef);
   SD_LAUNCHED("loss_terms", s);

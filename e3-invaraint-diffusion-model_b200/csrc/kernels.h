@@ -163,7 +163,9 @@ int decode_sequences(int B, int L, const float* final_seq, const float* true_seq
                      int* counts, cudaStream_t s);
 // model.py:313-345 + utils.py:132-161: the ten reduction terms documented at seqdiff_loss_terms (include/seqdiff_b200.h).
 // The per-CTA partials live in stream-ordered scratch (cudaMallocAsync / cudaFreeAsync on `s`).
-int loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* mask, double* terms, cudaStream_t s);
+int loss_terms(int N, const float* logits, const float* x0, const float* x_t, const float* mask, double* terms, cudaStream_t s,
+               double* scratch = nullptr);  // scratch (optional): loss_terms_scratch_bytes() of caller-owned, stream-private memory
+size_t loss_terms_scratch_bytes();
 
 // ---- gauss_step.cu ----------------------------------------------------------------------------------
 // Gaussian reverse step + angle wrap of the structure model (structure_model/sample.py:92-101,139-141) on B graphs of

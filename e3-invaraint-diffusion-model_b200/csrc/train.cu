@@ -510,7 +510,9 @@ int Model::train_t(int wfmt, const TrainArgs& a, cudaStream_t s) {
   SD_TRY(lin_T(Ml, H, H, se2.out.t, p1, p1_b, z1));
   SD_TRY(act_fwd<T>(z1, MlH, 1, nodrop, y, s));
   SD_TRY(predictor_tail<T>(y, Ml, H, p_ln_w, p_ln_b, 1e-12f, p2_w, p2_b, F, logits, s));
-  SD_TRY(loss_terms(Ml, logits, a.x0, a.x_t, a.lig_mask, a.terms, s));
+  double* loss_scratch = ar.take<double>(loss_terms_scratch_bytes() / sizeof(double));  // no allocator call inside the step
+  SD_CHECK(ar.ok, "training workspace under-estimated");
+  SD_TRY(loss_terms(Ml, logits, a.x0, a.x_t, a.lig_mask, a.terms, s, loss_scratch));
   SD_TRY(loss_bwd(Ml, logits, a.x0, a.x_t, a.terms, dlogits, s));
 
   // ---- backward -----------------------------------------------------------------------------------
