@@ -272,7 +272,7 @@ def cfg3_strong_record(sd, dev, world, rank, barrier, precision, steps=2, warmup
         L = keep_L
 
 
-def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=3, global_batch=128, grad_comm="fp32", weak=False):
+def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=10, warmup=10, global_batch=128, grad_comm="fp32", weak=False):
     """BASELINE configs[3]: one optimizer step of the sequence denoiser on a GLOBAL batch of 128 graphs (L = 128, T = 50, dropout 0.1,
     AdamW lr 5e-5 wd 0.1, clip 1.0: train_model.py:17-33), data-parallel over the ranks (128 / world graphs each), ONE gradient
     all-reduce per step over NCCL (61.06 M live parameters).  Reports whole steps (training_step + all-reduce + clip + AdamW), the
@@ -317,6 +317,8 @@ def cfg4_train_record(sd, dev, world, rank, barrier, precision, steps=5, warmup=
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return ms.item() / n, r
 
+        # ten warm-up steps by default: three 14 ms steps right after the GEMM tuner's host-bound first step are ~50 ms of GPU work, and the
+        # first timed steps were seen at 2.3 x their steady time once in a while (32.6 vs 14.0 ms, profiles/bench_r02_final2_outlier.json)
         for i in range(warmup):
             step(i)
         n0 = sd.lib().seqdiff_launch_count()  # counted over the timed steps (the warm-up steps also hold the GEMM tuner's candidate launches)
