@@ -25,7 +25,24 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["data"] == "synthetic" and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # the reference arm describes the SAME workload object as the product arm launched with the same flags (what it samples of it is
+    # said in `sample` / `cpu_baseline.sample`, never in `config`)
+    sys.path.insert(0, ROOT)
+    import bench
+    bench.L = bench.WORKLOADS["cfg2"]["L"]
+    assert d["config"] == bench.workload_config(bench.WORKLOADS["cfg2"], 2, bench.WORKLOADS["cfg2"]["T"], 1)
+    assert "one denoise step" in d["sample"].lower()
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_recorded_product_and_reference_lines_share_one_config():
+    """the two lines of the last B200 verification of the round (profiles/): same metric, unit, direction and config object."""
+    a = json.load(open(os.path.join(ROOT, "profiles", "bench_r02_final2.json")))
+    b = json.load(open(os.path.join(ROOT, "profiles", "bench_ref_r02_final2.json")))
+    assert b["impl"] == "reference" and "impl" not in a
+    for k in ("metric", "unit", "higher_is_better", "config"):
+        assert a[k] == b[k], k
+    assert a["gpu_launches"] > 0 and a["e2e"]["h2d_bytes_per_step"] > 0 and a["e2e"]["d2h_bytes_per_step"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
